@@ -1,0 +1,174 @@
+/* km_b200 -- C ABI of the B200-native find_mutation hot path of iric-soft/km.
+ *
+ * Drop-in boundary: the reference (pure Python, km 2.2.2) reaches its only native code,
+ * the Jellyfish library, through four calls in km/utils/Jellyfish.py.  A km maintainer
+ * would bind the functions below with ctypes (INTEGRATION.md shows the stub); this repo's
+ * own km-compatible host layer (km_b200/utils/*.py) is that binding.
+ *
+ * Conventions: plain C types only.  Every function returning int returns 0 on success and
+ * a negative KM_E_* code on failure; km_last_error() then holds a message (thread local).
+ * Buffers named *_host are host pointers; *_dev are device pointers on the table's device.
+ * k-mers are 2-bit packed uint64 (A0 C1 G2 T3, first base most significant), forward strand
+ * as written in the sequence -- canonicalisation happens inside, exactly like
+ * Jellyfish.query (km/utils/Jellyfish.py:47-53).  A missing k-mer counts 0, never an error
+ * (km/tests/test_main.py:596-623).  One host thread per table handle.
+ */
+#ifndef KM_B200_H
+#define KM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KM_E_ARG (-1)      /* bad argument */
+#define KM_E_IO (-2)       /* file could not be read / unsupported .jf format */
+#define KM_E_CUDA (-3)     /* CUDA runtime error (message has the detail) */
+#define KM_E_FULL (-4)     /* table capacity exhausted */
+#define KM_E_LIMIT (-5)    /* an internal capacity could not be satisfied after retries */
+#define KM_E_NOGPU (-6)    /* no CUDA device: there is no CPU fallback */
+
+typedef struct km_table km_table;
+typedef struct km_result km_result;
+
+const char* km_last_error(void);
+int km_device_count(void);
+const char* km_version(void);
+
+/* ---- k-mer count table ------------------------------------------------------------
+ * replaces jellyfish.QueryMerFile(filename) + jellyfish.MerDNA.k()  (Jellyfish.py:24-25)
+ * and the JSON header parse for `canonical`                         (Jellyfish.py:28-45) */
+int km_table_open_jf(const char* path, int device, km_table** out);
+int km_table_create(int device, int k, int canonical, uint64_t capacity_keys, km_table** out);
+/* keys are canonical keys as stored in a .jf (`jellyfish count -C` records);
+ * mode 0 keep existing, 1 overwrite, 2 add counts */
+int km_table_insert(km_table* t, const uint64_t* keys_host, const uint32_t* counts_host, uint64_t n, int mode);
+/* config-4 background: key_i = canonical(mix64(seed+(i+1)*G) & mask), count = f(key), i<n.
+ * Generated and inserted on device (mode keep). */
+int km_table_build_synthetic(km_table* t, uint64_t seed, uint64_t n_keys);
+/* C19 / config 5: count canonical k-mers of `n_reads` reads (ASCII, concatenated, offsets
+ * [n_reads+1]) on device; k-mers containing a non-ACGT letter are skipped. */
+int km_table_count_reads(km_table* t, const char* reads_host, const int64_t* offsets_host, int64_t n_reads);
+/* drop entries with count < min_count (jellyfish count -L); returns remaining through *n_left */
+int km_table_drop_below(km_table* t, uint32_t min_count, uint64_t* n_left);
+
+typedef struct km_table_info {
+    int32_t k;
+    int32_t canonical;
+    int32_t device;
+    int32_t reserved;
+    uint64_t n_keys;       /* distinct keys stored */
+    uint64_t n_buckets;    /* 32-byte buckets */
+    uint64_t bytes;        /* HBM held by the bucket array */
+} km_table_info;
+int km_table_get_info(km_table* t, km_table_info* info);
+void km_table_close(km_table* t);
+
+/* ---- lookups: Jellyfish.query (Jellyfish.py:47-53) ---------------------------------- */
+int km_query_batch(km_table* t, const uint64_t* kmers_host, uint64_t n, uint32_t* counts_host);
+int km_query_batch_device(km_table* t, const uint64_t* kmers_dev, uint64_t n, uint32_t* counts_dev, void* cuda_stream);
+/* n k-mers of k ASCII letters each, back to back; a non-ACGT letter yields KM_E_ARG */
+int km_query_ascii(km_table* t, const char* kmers_host, uint64_t n, uint32_t* counts_host);
+/* Jellyfish.get_child (Jellyfish.py:55-72): for each k-mer the 4 neighbour counts (A,C,G,T)
+ * and a 4-bit mask of those with count >= max(sum*ratio, count_floor) */
+int km_get_child_batch(km_table* t, const uint64_t* kmers_host, uint64_t n, int forward, double ratio,
+                       int64_t count_floor, uint32_t* child_counts_host /* 4n */, uint8_t* child_mask_host /* n */);
+
+/* ---- find_mutation over a batch of targets -------------------------------------------
+ * replaces the per-target loop of km/tools/find_mutation.py:47-58:
+ *   MutationFinder(refpath, jf, steps, branchs, nodes)   km/utils/MutationFinder.py:87-134
+ *   .graph_analysis()                                    :496-572 + km/utils/Graph.py
+ *   .quantify_paths() / .quantify_clusters()             :575-811 + km/utils/PathQuant.py */
+typedef struct km_find_params {
+    double ratio;        /* -p, default 0.05 */
+    int64_t count;       /* -c, default 5 */
+    int32_t steps;       /* -s, default 500  (max_stack) */
+    int32_t branchs;     /* -b, default 10   (max_break) */
+    int32_t nodes;       /* -n, default 10000 (max_node) */
+    int32_t extra_nodes; /* initial per-target capacity for explored novel nodes; 0 = default.
+                            Targets that overflow are re-run with 8x until `nodes`-bounded */
+} km_find_params;
+
+/* per-target status bits */
+#define KM_ST_BAD_BASE 1
+#define KM_ST_DUP_KMER 2
+#define KM_ST_NODE_OVERFLOW 4
+#define KM_ST_NODE_LIMIT 8
+#define KM_ST_TOUCHED_LIMIT 16
+#define KM_ST_PATH_OVERFLOW 32
+#define KM_ST_TOO_SHORT 64
+#define KM_ST_TOO_MANY_COLS 128
+#define KM_ST_SOLVER_WATCHDOG 256
+#define KM_ST_NAME_MISMATCH 512
+
+/* One output row (km/utils/PathQuant.py:10-49) in numeric form. */
+typedef struct km_row {
+    int32_t target;
+    int32_t kind;               /* 0 vs_ref, 1 cluster */
+    int32_t type;               /* 0 Reference 1 Substitution 2 ITD 3 Indel 4 Insertion 5 Deletion */
+    int32_t name_start;
+    int32_t name_end;
+    int32_t path_id;
+    int32_t var_begin, var_end;
+    int32_t ref_begin, ref_end;
+    int32_t del_begin, del_len;
+    int32_t ins_begin, ins_len;
+    int32_t start_off;
+    int32_t cluster_id, cluster_n;
+    int32_t n_iter;
+    int64_t min_cov;
+    double rvaf, expr, ref_rvaf, ref_expr;
+} km_row;
+
+/* seqs_host: the targets' sequences concatenated (ASCII, already upper-cased like
+ * common.file_2_seq, common.py:43); offsets_host[n_targets+1]. */
+int km_find_batch(km_table* t, const char* seqs_host, const int64_t* offsets_host, int32_t n_targets,
+                  const km_find_params* params, km_result** out);
+
+/* flat views into a result (valid until km_result_free) */
+typedef struct km_result_view {
+    int32_t n_targets;
+    int32_t n_paths;
+    int32_t n_rows;
+    int32_t k;
+    const uint32_t* status;        /* [n_targets] KM_ST_* bits */
+    const int32_t* n_nodes;        /* [n_targets] graph nodes incl. BigBang/BigCrunch */
+    const int64_t* node_off;       /* [n_targets+1] into node_kmer/node_count */
+    const uint64_t* node_kmer;     /* canonical numbering: reference k-mers, then novel ascending */
+    const uint32_t* node_count;
+    const int32_t* path_first;     /* [n_targets] */
+    const int32_t* path_count;     /* [n_targets] */
+    const int64_t* path_off;       /* [n_paths] into path_pool */
+    const int32_t* path_len;       /* [n_paths] */
+    const int32_t* path_pool;
+    const int32_t* row_first;      /* [n_targets] */
+    const int32_t* row_count;      /* [n_targets] */
+    const km_row* rows;            /* [n_rows] quantify_paths rows then quantify_clusters rows per target */
+    const uint64_t* lookups;       /* [n_targets] table lookups issued by the walk */
+    /* device time of the last run, milliseconds (CUDA events on the launch stream) */
+    float ms_h2d, ms_walk, ms_graph, ms_d2h, ms_total;
+    int32_t n_launches;            /* kernels launched for this result */
+    int32_t n_retries;
+} km_result_view;
+int km_result_get(const km_result* r, km_result_view* view);
+void km_result_free(km_result* r);
+
+/* Formats the rows of one target exactly like km find_mutation prints them (str(Path),
+ * PathQuant.py:37-49, sorted as MutationFinder.get_paths, :825-829).  Returns the number
+ * of bytes written (excluding the NUL), or the required size if buf is too small. */
+int64_t km_result_format_target(const km_result* r, int32_t target, const char* db_name, const char* query_name,
+                                char* buf, int64_t buf_len);
+
+/* ---- measurement helpers (bench.py) --------------------------------------------------- */
+/* random 32-byte-sector gather over `bytes` of HBM: the ceiling for hash probes */
+int km_bench_random_gather(int device, uint64_t bytes, uint64_t n_loads, int iters, float* best_ms);
+/* device-resident lookup benchmark: n queries (config-4 mix) generated on device, timed `iters` times */
+int km_bench_lookup(km_table* t, uint64_t table_seed, uint64_t table_n, uint64_t n_queries, uint64_t query_seed,
+                    int iters, float* best_ms, float* mean_ms, uint64_t* n_hits);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KM_B200_H */

@@ -1,0 +1,765 @@
+// C ABI of libkm_b200.so (see include/km_b200.h).  Host orchestration only: every piece of
+// arithmetic on the find_mutation path runs in the kernels of kernels.cuh.  There is no CPU
+// fallback -- without a CUDA device every entry point fails with KM_E_NOGPU.
+#include <algorithm>
+#include <cctype>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/km_b200.h"
+#include "kernels.cuh"
+
+using namespace km;
+
+static_assert(sizeof(km_row) == sizeof(Row), "km_row must mirror km::Row");
+static_assert(sizeof(Bucket) == 32, "bucket must be one 32-byte sector");
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            return fail(KM_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+extern "C" const char* km_last_error(void) { return g_err; }
+extern "C" const char* km_version(void) { return "km_b200 0.1 (sm_100a)"; }
+extern "C" int km_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+// A grow-only arena: one cudaMalloc / cudaMallocHost reused across calls (allocation calls
+// cost milliseconds, the whole panel runs in about one).
+struct Arena {
+    char* base = nullptr;
+    size_t cap = 0, used = 0;
+    bool host = false;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (base) { host ? cudaFreeHost(base) : cudaFree(base); base = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 4 + (1 << 20);
+        cudaError_t e = host ? cudaMallocHost((void**)&base, want) : cudaMalloc((void**)&base, want);
+        if (e != cudaSuccess) return fail(KM_E_CUDA, "arena alloc of %zu bytes failed: %s", want, cudaGetErrorString(e));
+        cap = want;
+        return 0;
+    }
+    void reset() { used = 0; }
+    template <class T> T* take(size_t n) {
+        used = (used + 255) & ~(size_t)255;
+        T* p = reinterpret_cast<T*>(base + used);
+        used += n * sizeof(T);
+        return p;
+    }
+    void release() { if (base) { host ? cudaFreeHost(base) : cudaFree(base); base = nullptr; cap = 0; } }
+};
+
+struct km_table {
+    int device = 0, k = 31, canonical = 1;
+    uint64_t n_buckets = 0, n_keys = 0;
+    Bucket* buckets = nullptr;
+    unsigned long long* d_counter = nullptr;   // [0] new keys, then a u32 "full" flag at +8
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6] = {};
+    Arena dev, pin;
+    int sm_count = 148;
+    TableView view() const {
+        TableView v;
+        v.buckets = buckets; v.n_buckets = n_buckets; v.kmask = (1ull << (2 * k)) - 1ull; v.k = k; v.canonical = canonical;
+        return v;
+    }
+};
+
+static int grid_for(const km_table* t, uint64_t n, int block, int per_sm) {
+    uint64_t want = (n + block - 1) / block;
+    uint64_t cap = (uint64_t)t->sm_count * per_sm;
+    if (want < 1) want = 1;
+    return (int)std::min(want, cap);
+}
+
+extern "C" int km_table_create(int device, int k, int canonical, uint64_t capacity_keys, km_table** out) {
+    if (!out || k < 1 || k > 31) return fail(KM_E_ARG, "km_table_create: k must be in 1..31 (got %d)", k);
+    int ndev = km_device_count();
+    if (ndev <= 0) return fail(KM_E_NOGPU, "no CUDA device visible: km_b200 has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(KM_E_ARG, "device %d out of range (0..%d)", device, ndev - 1);
+    CU(cudaSetDevice(device));
+    km_table* t = new km_table();
+    t->device = device; t->k = k; t->canonical = canonical ? 1 : 0;
+    // two slots per bucket at a target load of ~0.5
+    t->n_buckets = std::max<uint64_t>(64, capacity_keys);
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    t->sm_count = prop.multiProcessorCount;
+    cudaError_t e = cudaMalloc((void**)&t->buckets, t->n_buckets * sizeof(Bucket));
+    if (e != cudaSuccess) {
+        delete t;
+        return fail(KM_E_CUDA, "cudaMalloc of %llu table bytes failed: %s", (unsigned long long)(capacity_keys * sizeof(Bucket)),
+                    cudaGetErrorString(e));
+    }
+    CU(cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking));
+    for (auto& ev : t->ev) CU(cudaEventCreate(&ev));
+    CU(cudaMalloc((void**)&t->d_counter, 16));
+    t->pin.host = true;
+    km_table_clear_kernel<<<t->sm_count * 8, 256, 0, t->stream>>>(t->buckets, t->n_buckets);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(t->stream));
+    *out = t;
+    return 0;
+}
+
+extern "C" void km_table_close(km_table* t) {
+    if (!t) return;
+    cudaSetDevice(t->device);
+    if (t->buckets) cudaFree(t->buckets);
+    if (t->d_counter) cudaFree(t->d_counter);
+    t->dev.release();
+    t->pin.release();
+    for (auto& ev : t->ev) if (ev) cudaEventDestroy(ev);
+    if (t->stream) cudaStreamDestroy(t->stream);
+    delete t;
+}
+
+extern "C" int km_table_get_info(km_table* t, km_table_info* info) {
+    if (!t || !info) return fail(KM_E_ARG, "null argument");
+    info->k = t->k; info->canonical = t->canonical; info->device = t->device; info->reserved = 0;
+    info->n_keys = t->n_keys; info->n_buckets = t->n_buckets; info->bytes = t->n_buckets * sizeof(Bucket);
+    return 0;
+}
+
+static int finish_insert(km_table* t, const char* what) {
+    unsigned long long host[2] = {0, 0};
+    CU(cudaMemcpyAsync(host, t->d_counter, 16, cudaMemcpyDeviceToHost, t->stream));
+    CU(cudaStreamSynchronize(t->stream));
+    t->n_keys += host[0];
+    if ((uint32_t)host[1]) return fail(KM_E_FULL, "%s: table full (%llu buckets)", what, (unsigned long long)t->n_buckets);
+    return 0;
+}
+
+extern "C" int km_table_insert(km_table* t, const uint64_t* keys, const uint32_t* counts, uint64_t n, int mode) {
+    if (!t || (n && (!keys || !counts)) || mode < 0 || mode > 2) return fail(KM_E_ARG, "km_table_insert: bad argument");
+    CU(cudaSetDevice(t->device));
+    const uint64_t chunk = 1ull << 24;
+    for (uint64_t done = 0; done < n; done += chunk) {
+        const uint64_t m = std::min(chunk, n - done);
+        if (int rc = t->dev.reserve(m * 12 + 512)) return rc;
+        t->dev.reset();
+        uint64_t* dk = t->dev.take<uint64_t>(m);
+        uint32_t* dc = t->dev.take<uint32_t>(m);
+        CU(cudaMemsetAsync(t->d_counter, 0, 16, t->stream));
+        CU(cudaMemcpyAsync(dk, keys + done, m * 8, cudaMemcpyHostToDevice, t->stream));
+        CU(cudaMemcpyAsync(dc, counts + done, m * 4, cudaMemcpyHostToDevice, t->stream));
+        km_table_insert_kernel<<<grid_for(t, m, 256, 8), 256, 0, t->stream>>>(t->view(), dk, dc, m, mode, t->d_counter,
+                                                                             reinterpret_cast<uint32_t*>(t->d_counter + 1));
+        CU(cudaGetLastError());
+        if (int rc = finish_insert(t, "km_table_insert")) return rc;
+    }
+    return 0;
+}
+
+extern "C" int km_table_build_synthetic(km_table* t, uint64_t seed, uint64_t n_keys) {
+    if (!t) return fail(KM_E_ARG, "null table");
+    CU(cudaSetDevice(t->device));
+    CU(cudaMemsetAsync(t->d_counter, 0, 16, t->stream));
+    km_table_synth_kernel<<<t->sm_count * 16, 256, 0, t->stream>>>(t->view(), seed, n_keys, t->d_counter,
+                                                                   reinterpret_cast<uint32_t*>(t->d_counter + 1));
+    CU(cudaGetLastError());
+    return finish_insert(t, "km_table_build_synthetic");
+}
+
+extern "C" int km_table_count_reads(km_table* t, const char* reads, const int64_t* off, int64_t n_reads) {
+    if (!t || !reads || !off || n_reads < 0) return fail(KM_E_ARG, "km_table_count_reads: bad argument");
+    if (n_reads == 0) return 0;
+    CU(cudaSetDevice(t->device));
+    const int64_t total = off[n_reads];
+    if (int rc = t->dev.reserve((size_t)total + (size_t)(n_reads + 1) * 8 + 1024)) return rc;
+    t->dev.reset();
+    char* dr = t->dev.take<char>(total);
+    int64_t* doff = t->dev.take<int64_t>(n_reads + 1);
+    CU(cudaMemsetAsync(t->d_counter, 0, 16, t->stream));
+    CU(cudaMemcpyAsync(dr, reads, total, cudaMemcpyHostToDevice, t->stream));
+    CU(cudaMemcpyAsync(doff, off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, t->stream));
+    km_count_reads_kernel<<<grid_for(t, total, 256, 8), 256, 0, t->stream>>>(t->view(), dr, doff, n_reads, total, t->d_counter,
+                                                                            reinterpret_cast<uint32_t*>(t->d_counter + 1));
+    CU(cudaGetLastError());
+    return finish_insert(t, "km_table_count_reads");
+}
+
+extern "C" int km_table_drop_below(km_table* t, uint32_t min_count, uint64_t* n_left) {
+    if (!t) return fail(KM_E_ARG, "null table");
+    CU(cudaSetDevice(t->device));
+    Bucket* fresh = nullptr;
+    CU(cudaMalloc((void**)&fresh, t->n_buckets * sizeof(Bucket)));
+    km_table_clear_kernel<<<t->sm_count * 8, 256, 0, t->stream>>>(fresh, t->n_buckets);
+    TableView dst = t->view();
+    dst.buckets = fresh;
+    CU(cudaMemsetAsync(t->d_counter, 0, 16, t->stream));
+    km_table_filter_kernel<<<t->sm_count * 8, 256, 0, t->stream>>>(t->view(), dst, min_count, t->d_counter,
+                                                                   reinterpret_cast<uint32_t*>(t->d_counter + 1));
+    CU(cudaGetLastError());
+    t->n_keys = 0;
+    int rc = finish_insert(t, "km_table_drop_below");
+    cudaFree(t->buckets);
+    t->buckets = fresh;
+    if (n_left) *n_left = t->n_keys;
+    return rc;
+}
+
+// ---- .jf loader (binary/sorted) ---------------------------------------
+static bool json_field(const std::string& js, const char* name, std::string* out) {
+    std::string pat = std::string("\"") + name + "\"";
+    size_t p = js.find(pat);
+    if (p == std::string::npos) return false;
+    p = js.find(':', p + pat.size());
+    if (p == std::string::npos) return false;
+    ++p;
+    while (p < js.size() && isspace((unsigned char)js[p])) ++p;
+    size_t e = p;
+    if (js[p] == '"') { e = js.find('"', p + 1); if (e == std::string::npos) return false; *out = js.substr(p + 1, e - p - 1); return true; }
+    while (e < js.size() && js[e] != ',' && js[e] != '}' && !isspace((unsigned char)js[e])) ++e;
+    *out = js.substr(p, e - p);
+    return true;
+}
+
+extern "C" int km_table_open_jf(const char* path, int device, km_table** out) {
+    if (!path || !out) return fail(KM_E_ARG, "km_table_open_jf: null argument");
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(KM_E_IO, "cannot open %s", path);
+    char digits[10] = {0};
+    if (fread(digits, 1, 9, f) != 9) { fclose(f); return fail(KM_E_IO, "%s: truncated header", path); }
+    for (int i = 0; i < 9; ++i) if (!isdigit((unsigned char)digits[i])) { fclose(f); return fail(KM_E_IO, "%s: not a Jellyfish file (no header length)", path); }
+    const long hlen = atol(digits);
+    std::string js((size_t)hlen, '\0');
+    if (fread(&js[0], 1, (size_t)hlen, f) != (size_t)hlen) { fclose(f); return fail(KM_E_IO, "%s: truncated header", path); }
+    std::string fmt, canon, key_len, counter_len;
+    if (!json_field(js, "format", &fmt) || !json_field(js, "canonical", &canon) || !json_field(js, "key_len", &key_len) ||
+        !json_field(js, "counter_len", &counter_len)) { fclose(f); return fail(KM_E_IO, "%s: header lacks format/canonical/key_len/counter_len", path); }
+    if (fmt != "binary/sorted") { fclose(f); return fail(KM_E_IO, "%s: unsupported format '%s' (only binary/sorted)", path, fmt.c_str()); }
+    const int kbits = atoi(key_len.c_str()), cbytes = atoi(counter_len.c_str());
+    if (kbits < 2 || kbits > 62 || (kbits & 1) || cbytes < 1 || cbytes > 8) { fclose(f); return fail(KM_E_IO, "%s: key_len %d / counter_len %d not supported", path, kbits, cbytes); }
+    const int kbytes = (kbits + 7) / 8, rec = kbytes + cbytes;
+    fseek(f, 0, SEEK_END);
+    const long fsize = ftell(f);
+    const long payload = fsize - 9 - hlen;
+    if (payload < 0 || payload % rec) { fclose(f); return fail(KM_E_IO, "%s: payload of %ld bytes is not a multiple of %d", path, payload, rec); }
+    const uint64_t n = (uint64_t)(payload / rec);
+    std::vector<unsigned char> raw((size_t)payload);
+    fseek(f, 9 + hlen, SEEK_SET);
+    if (payload && fread(raw.data(), 1, (size_t)payload, f) != (size_t)payload) { fclose(f); return fail(KM_E_IO, "%s: short read", path); }
+    fclose(f);
+    std::vector<uint64_t> keys(n);
+    std::vector<uint32_t> counts(n);
+    for (uint64_t i = 0; i < n; ++i) {
+        const unsigned char* p = raw.data() + i * rec;
+        uint64_t key = 0, cnt = 0;
+        for (int b = 0; b < kbytes; ++b) key |= (uint64_t)p[b] << (8 * b);
+        for (int b = 0; b < cbytes; ++b) cnt |= (uint64_t)p[kbytes + b] << (8 * b);
+        keys[i] = key;
+        counts[i] = cnt > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)cnt;
+    }
+    km_table* t = nullptr;
+    if (int rc = km_table_create(device, kbits / 2, canon == "true", std::max<uint64_t>(n, 1024), &t)) return rc;
+    if (int rc = km_table_insert(t, keys.data(), counts.data(), n, KM_INSERT_OVERWRITE)) { km_table_close(t); return rc; }
+    *out = t;
+    return 0;
+}
+
+// ---- lookups --------------------------------------------------------------------------------
+extern "C" int km_query_batch_device(km_table* t, const uint64_t* kmers_dev, uint64_t n, uint32_t* counts_dev, void* stream) {
+    if (!t || (n && (!kmers_dev || !counts_dev))) return fail(KM_E_ARG, "km_query_batch_device: bad argument");
+    if (!n) return 0;
+    cudaStream_t s = stream ? (cudaStream_t)stream : t->stream;
+    km_query_kernel<<<grid_for(t, (n + KM_QUERY_ILP - 1) / KM_QUERY_ILP, 256, 8), 256, 0, s>>>(t->view(), kmers_dev, n, counts_dev);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int km_query_batch(km_table* t, const uint64_t* kmers, uint64_t n, uint32_t* counts) {
+    if (!t || (n && (!kmers || !counts))) return fail(KM_E_ARG, "km_query_batch: bad argument");
+    CU(cudaSetDevice(t->device));
+    // chunks staged through pinned memory so copy-in, probe and copy-out of neighbouring
+    // chunks overlap on the copy engines
+    const uint64_t chunk = 1ull << 22;
+    const uint64_t m_max = std::min(chunk, n);
+    if (int rc = t->dev.reserve(2 * (m_max * 12 + 1024))) return rc;
+    if (int rc = t->pin.reserve(2 * (m_max * 12 + 1024))) return rc;
+    t->dev.reset(); t->pin.reset();
+    uint64_t* dk[2]; uint32_t* dc[2]; uint64_t* hk[2]; uint32_t* hc[2];
+    for (int b = 0; b < 2; ++b) {
+        dk[b] = t->dev.take<uint64_t>(m_max); dc[b] = t->dev.take<uint32_t>(m_max);
+        hk[b] = t->pin.take<uint64_t>(m_max); hc[b] = t->pin.take<uint32_t>(m_max);
+    }
+    cudaEvent_t done[2] = {t->ev[4], t->ev[5]};
+    uint64_t pending_off[2] = {0, 0}, pending_n[2] = {0, 0};
+    int slot = 0;
+    for (uint64_t off = 0; off < n; off += chunk, slot ^= 1) {
+        const uint64_t m = std::min(chunk, n - off);
+        if (pending_n[slot]) {
+            CU(cudaEventSynchronize(done[slot]));
+            memcpy(counts + pending_off[slot], hc[slot], pending_n[slot] * 4);
+        }
+        memcpy(hk[slot], kmers + off, m * 8);
+        CU(cudaMemcpyAsync(dk[slot], hk[slot], m * 8, cudaMemcpyHostToDevice, t->stream));
+        if (int rc = km_query_batch_device(t, dk[slot], m, dc[slot], t->stream)) return rc;
+        CU(cudaMemcpyAsync(hc[slot], dc[slot], m * 4, cudaMemcpyDeviceToHost, t->stream));
+        CU(cudaEventRecord(done[slot], t->stream));
+        pending_off[slot] = off; pending_n[slot] = m;
+    }
+    for (int b = 0; b < 2; ++b) {
+        const int s2 = slot ^ b;   // older chunk first
+        if (pending_n[s2]) {
+            CU(cudaEventSynchronize(done[s2]));
+            memcpy(counts + pending_off[s2], hc[s2], pending_n[s2] * 4);
+        }
+    }
+    return 0;
+}
+
+static inline int base_code(char c) {
+    switch (c) { case 'A': return 0; case 'C': return 1; case 'G': return 2; case 'T': return 3; default: return -1; }
+}
+
+extern "C" int km_query_ascii(km_table* t, const char* kmers, uint64_t n, uint32_t* counts) {
+    if (!t || (n && (!kmers || !counts))) return fail(KM_E_ARG, "km_query_ascii: bad argument");
+    std::vector<uint64_t> packed(n);
+    for (uint64_t i = 0; i < n; ++i) {
+        uint64_t v = 0;
+        for (int j = 0; j < t->k; ++j) {
+            const int c = base_code(kmers[i * t->k + j]);
+            if (c < 0) return fail(KM_E_ARG, "k-mer %llu holds a letter outside ACGT", (unsigned long long)i);
+            v = (v << 2) | (uint64_t)c;
+        }
+        packed[i] = v;
+    }
+    return km_query_batch(t, packed.data(), n, counts);
+}
+
+extern "C" int km_get_child_batch(km_table* t, const uint64_t* kmers, uint64_t n, int forward, double ratio, int64_t floor_count,
+                                  uint32_t* child_counts, uint8_t* child_mask) {
+    if (!t || (n && (!kmers || !child_counts || !child_mask))) return fail(KM_E_ARG, "km_get_child_batch: bad argument");
+    if (!n) return 0;
+    CU(cudaSetDevice(t->device));
+    if (int rc = t->dev.reserve(n * 25 + 2048)) return rc;
+    t->dev.reset();
+    uint64_t* dk = t->dev.take<uint64_t>(n);
+    uint32_t* dc = t->dev.take<uint32_t>(4 * n);
+    uint8_t* dm = t->dev.take<uint8_t>(n);
+    CU(cudaMemcpyAsync(dk, kmers, n * 8, cudaMemcpyHostToDevice, t->stream));
+    km_get_child_kernel<<<grid_for(t, n, 256, 8), 256, 0, t->stream>>>(t->view(), dk, n, forward, ratio, floor_count, dc, dm);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(child_counts, dc, 4 * n * 4, cudaMemcpyDeviceToHost, t->stream));
+    CU(cudaMemcpyAsync(child_mask, dm, n, cudaMemcpyDeviceToHost, t->stream));
+    CU(cudaStreamSynchronize(t->stream));
+    return 0;
+}
+
+// ---- find_mutation batch ------------------------------------------------------------------------
+struct km_result {
+    int n_targets = 0, k = 31;
+    std::vector<uint32_t> status;
+    std::vector<int32_t> n_nodes, path_first, path_count, row_first, row_count, path_len;
+    std::vector<int64_t> node_off, path_off, path_seq_off, seq_off;
+    std::vector<uint64_t> node_kmer, lookups;
+    std::vector<uint32_t> node_count;
+    std::vector<int32_t> path_pool;
+    std::vector<km_row> rows;
+    std::vector<char> seq_pool;     // spelled unique paths
+    std::string targets;            // concatenated target sequences (for Reference_sequence / deleted bases)
+    float ms_h2d = 0, ms_walk = 0, ms_graph = 0, ms_d2h = 0, ms_total = 0;
+    int n_launches = 0, n_retries = 0;
+};
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static ScratchLayout make_layout(int maxcap) {
+    ScratchLayout L;
+    memset(&L, 0, sizeof(L));
+    const size_t maxN = (size_t)maxcap + 2, nce = 4 * maxN + 2;
+    size_t o = 0;
+    auto put = [&](size_t bytes) { size_t at = o; o = align_up(o + bytes, 16); return at; };
+    L.o_newidx = put(4 * (size_t)maxcap); L.o_kept = put(4 * (size_t)maxcap);
+    L.o_succ = put(16 * maxN); L.o_pred = put(16 * maxN);
+    L.o_dist = put(4 * maxN); L.o_before = put(4 * maxN); L.o_after = put(4 * maxN); L.o_cand = put(4 * maxN);
+    L.o_state = put(maxN); L.o_eflag = put(maxN); L.o_reach = put(maxN); L.o_occ = put(4 * maxN);
+    L.o_ce_a = put(4 * nce); L.o_ce_b = put(4 * nce); L.o_ce_len = put(4 * nce); L.o_ce_h1 = put(8 * nce); L.o_ce_h2 = put(8 * nce);
+    L.o_upath = put(4 * KM_MAX_PATHS); L.o_pdiff = put(16 * KM_MAX_PATHS); L.o_grp = put(20 * KM_MAX_PATHS);
+    L.o_G = put(8 * KM_MAX_COLS * KM_MAX_COLS); L.o_V = put(16 * KM_MAX_COLS * KM_MAX_COLS); L.o_vec = put(64 * KM_MAX_COLS);
+    L.stride = align_up(o, 256);
+    L.maxN = (int)maxN;
+    return L;
+}
+
+static uint32_t pow2_at_least(uint64_t x) { uint32_t p = 64; while (p < x) p <<= 1; return p; }
+
+// One complete run over all targets with the given per-target capacities and pool sizes.
+static int run_once(km_table* t, const std::vector<uint8_t>& codes, const int64_t* seq_off, int n, const km_find_params& prm,
+                    const std::vector<int32_t>& extra, int64_t pool_cap, int32_t path_cap, int32_t row_cap, int64_t seq_cap,
+                    km_result* res) {
+    const int k = t->k;
+    std::vector<int64_t> node_off(n + 1, 0), hash_off(n + 1, 0);
+    int maxcap = 1;
+    for (int i = 0; i < n; ++i) {
+        const int64_t len = seq_off[i + 1] - seq_off[i];
+        const int L = (int)std::max<int64_t>(0, len - k + 1);
+        const int cap = L + extra[i];
+        maxcap = std::max(maxcap, cap);
+        node_off[i + 1] = node_off[i] + cap;
+        hash_off[i + 1] = hash_off[i] + pow2_at_least(2 * (uint64_t)cap + 2 * KM_CTA * 4);
+    }
+    const int64_t n_node = node_off[n], n_hash = hash_off[n], n_code = seq_off[n];
+    const int grid_graph = std::min(n, t->sm_count * 8);
+    const ScratchLayout L0 = make_layout(maxcap);
+
+    // ---- carve the device arena
+    size_t need = 4096;
+    auto acc = [&](size_t bytes) { need = align_up(need, 256) + bytes; };
+    acc(n_code); acc(8 * (n + 1)); acc(8 * (n + 1)); acc(8 * (n + 1));
+    acc(8 * n_node); acc(4 * n_node); acc(4 * n_node); acc(16 * n_node);          // node arrays
+    acc(8 * n_hash); acc(4 * n_hash); acc(4 * n_hash); acc(n_hash);                // visited sets
+    acc(4 * n); acc(4 * n); acc(4 * n); acc(8 * n);                                // n_nodes n_kept status lookups
+    acc(4 * n * 5);                                                                // per-target result ints
+    acc(8 * n_node); acc(4 * n_node);                                              // canonical nodes
+    acc(8 * (size_t)path_cap); acc(4 * (size_t)path_cap); acc(8 * (size_t)path_cap); acc(4 * (size_t)pool_cap);
+    acc(sizeof(Row) * (size_t)row_cap); acc((size_t)seq_cap); acc(64);
+    acc(L0.stride * (size_t)grid_graph);
+    if (int rc = t->dev.reserve(need + 4096)) return rc;
+    t->dev.reset();
+    Arena& A = t->dev;
+    WalkView W;
+    W.n_targets = n;
+    uint8_t* d_codes = A.take<uint8_t>(n_code);
+    int64_t* d_seq_off = A.take<int64_t>(n + 1);
+    int64_t* d_node_off = A.take<int64_t>(n + 1);
+    int64_t* d_hash_off = A.take<int64_t>(n + 1);
+    W.codes = d_codes; W.seq_off = d_seq_off; W.node_off = d_node_off; W.hash_off = d_hash_off;
+    W.node_kmer = A.take<uint64_t>(n_node); W.node_count = A.take<uint32_t>(n_node);
+    W.node_slot = A.take<uint32_t>(n_node); W.node_kid = A.take<uint32_t>(4 * n_node);
+    W.hkey = A.take<uint64_t>(n_hash); W.hval = A.take<uint32_t>(n_hash); W.hmeta = A.take<uint32_t>(n_hash);
+    W.hflag = A.take<uint8_t>(n_hash);
+    // the four per-target state arrays are contiguous so one memset clears them
+    char* state0 = A.take<char>(0);
+    W.n_nodes = A.take<int32_t>(n); W.n_kept = A.take<int32_t>(n); W.status = A.take<uint32_t>(n);
+    W.lookups = A.take<unsigned long long>(n);
+    ResultView R;
+    R.t_n = A.take<int32_t>(n); R.t_n_paths = A.take<int32_t>(n); R.t_path_first = A.take<int32_t>(n);
+    R.t_n_rows = A.take<int32_t>(n); R.t_row_first = A.take<int32_t>(n);
+    char* state1 = A.take<char>(0);
+    R.out_kmer = A.take<uint64_t>(n_node); R.out_count = A.take<uint32_t>(n_node);
+    R.path_off = A.take<int64_t>(path_cap); R.path_len = A.take<int32_t>(path_cap);
+    int64_t* d_path_seq_off = A.take<int64_t>(path_cap);
+    R.pool = A.take<int32_t>(pool_cap); R.path_cap = path_cap; R.pool_cap = pool_cap;
+    R.rows = A.take<Row>(row_cap); R.row_cap = row_cap;
+    char* d_seq_pool = A.take<char>(seq_cap);
+    R.used = A.take<unsigned long long>(4);
+    ScratchLayout SL = L0;
+    SL.base = A.take<char>(L0.stride * (size_t)grid_graph);
+
+    // ---- host staging (pinned)
+    if (int rc = t->pin.reserve((size_t)n_code + 24 * (size_t)(n + 1) + 4096)) return rc;
+    t->pin.reset();
+    uint8_t* h_codes = t->pin.take<uint8_t>(n_code);
+    int64_t* h_seq_off = t->pin.take<int64_t>(n + 1);
+    int64_t* h_node_off = t->pin.take<int64_t>(n + 1);
+    int64_t* h_hash_off = t->pin.take<int64_t>(n + 1);
+    memcpy(h_codes, codes.data(), n_code);
+    memcpy(h_seq_off, seq_off, 8 * (n + 1));
+    memcpy(h_node_off, node_off.data(), 8 * (n + 1));
+    memcpy(h_hash_off, hash_off.data(), 8 * (n + 1));
+
+    FindParams P;
+    P.ratio = prm.ratio; P.count = prm.count; P.max_stack = prm.steps; P.max_break = prm.branchs; P.max_node = prm.nodes;
+
+    cudaStream_t s = t->stream;
+    CU(cudaEventRecord(t->ev[0], s));
+    CU(cudaMemcpyAsync(d_codes, h_codes, n_code, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(d_seq_off, h_seq_off, 8 * (n + 1), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(d_node_off, h_node_off, 8 * (n + 1), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(d_hash_off, h_hash_off, 8 * (n + 1), cudaMemcpyHostToDevice, s));
+    CU(cudaMemsetAsync(state0, 0, (size_t)(state1 - state0), s));
+    CU(cudaMemsetAsync(R.used, 0, 32, s));
+    CU(cudaEventRecord(t->ev[1], s));
+    km_walk_kernel<<<n, KM_CTA, 0, s>>>(t->view(), W, P);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(t->ev[2], s));
+    km_graph_kernel<<<grid_graph, KM_CTA, 0, s>>>(t->view(), W, SL, R, d_seq_pool, d_path_seq_off, seq_cap);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(t->ev[3], s));
+    res->n_launches += 2;
+
+    // ---- results: per-target ints first, then exactly the used extents
+    res->n_targets = n; res->k = k;
+    res->status.resize(n); res->n_nodes.resize(n); res->path_first.resize(n); res->path_count.resize(n);
+    res->row_first.resize(n); res->row_count.resize(n); res->lookups.resize(n);
+    unsigned long long used[4];
+    CU(cudaMemcpyAsync(res->status.data(), W.status, 4 * n, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(res->n_nodes.data(), R.t_n, 4 * n, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(res->path_count.data(), R.t_n_paths, 4 * n, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(res->path_first.data(), R.t_path_first, 4 * n, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(res->row_count.data(), R.t_n_rows, 4 * n, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(res->row_first.data(), R.t_row_first, 4 * n, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(res->lookups.data(), W.lookups, 8 * n, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(used, R.used, 32, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    const size_t n_paths = std::min<unsigned long long>(used[0], path_cap), n_pool = std::min<unsigned long long>(used[1], pool_cap);
+    const size_t n_rows = std::min<unsigned long long>(used[2], row_cap), n_seq = std::min<unsigned long long>(used[3], seq_cap);
+    res->path_off.resize(n_paths); res->path_len.resize(n_paths); res->path_seq_off.resize(n_paths);
+    res->path_pool.resize(n_pool); res->rows.resize(n_rows); res->seq_pool.resize(n_seq);
+    res->node_off = node_off;
+    res->node_kmer.resize(n_node); res->node_count.resize(n_node);
+    if (n_paths) {
+        CU(cudaMemcpyAsync(res->path_off.data(), R.path_off, 8 * n_paths, cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(res->path_len.data(), R.path_len, 4 * n_paths, cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(res->path_seq_off.data(), d_path_seq_off, 8 * n_paths, cudaMemcpyDeviceToHost, s));
+    }
+    if (n_pool) CU(cudaMemcpyAsync(res->path_pool.data(), R.pool, 4 * n_pool, cudaMemcpyDeviceToHost, s));
+    if (n_rows) CU(cudaMemcpyAsync(res->rows.data(), R.rows, sizeof(Row) * n_rows, cudaMemcpyDeviceToHost, s));
+    if (n_seq) CU(cudaMemcpyAsync(res->seq_pool.data(), d_seq_pool, n_seq, cudaMemcpyDeviceToHost, s));
+    if (n_node) {
+        CU(cudaMemcpyAsync(res->node_kmer.data(), R.out_kmer, 8 * n_node, cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(res->node_count.data(), R.out_count, 4 * n_node, cudaMemcpyDeviceToHost, s));
+    }
+    CU(cudaEventRecord(t->ev[4], s));
+    CU(cudaStreamSynchronize(s));
+    float ms;
+    CU(cudaEventElapsedTime(&ms, t->ev[0], t->ev[1])); res->ms_h2d = ms;
+    CU(cudaEventElapsedTime(&ms, t->ev[1], t->ev[2])); res->ms_walk = ms;
+    CU(cudaEventElapsedTime(&ms, t->ev[2], t->ev[3])); res->ms_graph = ms;
+    CU(cudaEventElapsedTime(&ms, t->ev[3], t->ev[4])); res->ms_d2h = ms;
+    CU(cudaEventElapsedTime(&ms, t->ev[0], t->ev[4])); res->ms_total = ms;
+    return 0;
+}
+
+extern "C" int km_find_batch(km_table* t, const char* seqs, const int64_t* offsets, int32_t n, const km_find_params* params,
+                             km_result** out) {
+    if (!t || !out || n < 0 || (n && (!seqs || !offsets)) || !params) return fail(KM_E_ARG, "km_find_batch: bad argument");
+    CU(cudaSetDevice(t->device));
+    km_find_params prm = *params;
+    if (prm.steps > 60000 || prm.branchs > 250) return fail(KM_E_ARG, "steps must be <= 60000 and branchs <= 250");
+    km_result* res = new km_result();
+    const int64_t total = n ? offsets[n] : 0;
+    res->targets.assign(seqs ? seqs : "", (size_t)total);
+    res->seq_off.assign(offsets, offsets + n + 1);
+    std::vector<uint8_t> codes((size_t)total);
+    for (int64_t i = 0; i < total; ++i) { const int c = base_code(seqs[i]); codes[i] = c < 0 ? 255 : (uint8_t)c; }
+    int64_t n_ref = 0;
+    for (int i = 0; i < n; ++i) n_ref += std::max<int64_t>(0, offsets[i + 1] - offsets[i] - t->k + 1);
+    std::vector<int32_t> extra((size_t)n, prm.extra_nodes > 0 ? prm.extra_nodes : 256);
+    int32_t path_cap = std::max(64, 8 * n);
+    int32_t row_cap = std::max(64, 16 * n);
+    int64_t pool_cap = std::max<int64_t>(1 << 16, 6 * (n_ref + 64ll * n));
+    int64_t seq_cap = pool_cap + (int64_t)path_cap * t->k;
+    const int32_t extra_max = std::max(1024, prm.nodes + 4 * prm.steps + 4096);
+    for (int attempt = 0; attempt < 12; ++attempt) {
+        int rc = run_once(t, codes, offsets, n, prm, extra, pool_cap, path_cap, row_cap, seq_cap, res);
+        if (rc) { delete res; return rc; }
+        bool again = false, pool_over = false;
+        for (int i = 0; i < n; ++i) {
+            if (res->status[i] & KM_ST_NODE_OVERFLOW) {
+                if (extra[i] >= extra_max) { delete res; return fail(KM_E_LIMIT, "target %d explores more than %d nodes", i, extra_max); }
+                extra[i] = std::min<int64_t>(extra_max, (int64_t)extra[i] * 8);
+                again = true;
+            }
+            if (res->status[i] & KM_ST_PATH_OVERFLOW) pool_over = true;
+        }
+        if (pool_over) { pool_cap *= 4; path_cap *= 4; row_cap *= 4; seq_cap = pool_cap + (int64_t)path_cap * t->k; again = true; }
+        if (!again) { *out = res; return 0; }
+        res->n_retries++;
+    }
+    delete res;
+    return fail(KM_E_LIMIT, "km_find_batch: capacities still exceeded after 12 attempts");
+}
+
+extern "C" int km_result_get(const km_result* r, km_result_view* v) {
+    if (!r || !v) return fail(KM_E_ARG, "null argument");
+    memset(v, 0, sizeof(*v));
+    v->n_targets = r->n_targets; v->n_paths = (int32_t)r->path_off.size(); v->n_rows = (int32_t)r->rows.size(); v->k = r->k;
+    v->status = r->status.data(); v->n_nodes = r->n_nodes.data(); v->node_off = r->node_off.data();
+    v->node_kmer = r->node_kmer.data(); v->node_count = r->node_count.data();
+    v->path_first = r->path_first.data(); v->path_count = r->path_count.data();
+    v->path_off = r->path_off.data(); v->path_len = r->path_len.data(); v->path_pool = r->path_pool.data();
+    v->row_first = r->row_first.data(); v->row_count = r->row_count.data(); v->rows = r->rows.data();
+    v->lookups = r->lookups.data();
+    v->ms_h2d = r->ms_h2d; v->ms_walk = r->ms_walk; v->ms_graph = r->ms_graph; v->ms_d2h = r->ms_d2h; v->ms_total = r->ms_total;
+    v->n_launches = r->n_launches; v->n_retries = r->n_retries;
+    return 0;
+}
+
+extern "C" void km_result_free(km_result* r) { delete r; }
+
+// ---- row formatting (PathQuant.Path.__str__, MutationFinder.get_paths) ------------------------
+static const char* TYPE_NAME[6] = {"Reference", "Substitution", "ITD", "Indel", "Insertion", "Deletion"};
+
+static void fmt_float(std::string& out, double v, int prec) {
+    char buf[64];
+    if (std::isnan(v)) { out += "nan"; return; }          // Python prints nan without a sign
+    if (std::isinf(v)) { out += v < 0 ? "-inf" : "inf"; return; }
+    snprintf(buf, sizeof(buf), "%.*f", prec, v);
+    out += buf;
+}
+
+// common.natsortkey (common.py:95-116): split on digit runs; digit runs compare as ints,
+// other chunks as lower-cased strings.
+struct NatTok { bool num; unsigned long long val; std::string txt; };
+static std::vector<NatTok> nat_split(const std::string& s) {
+    // re.split('([0-9]+)', key): alternating text / digits, text chunks may be empty
+    std::vector<NatTok> out;
+    size_t i = 0;
+    std::string cur;
+    while (i <= s.size()) {
+        if (i < s.size() && isdigit((unsigned char)s[i])) {
+            out.push_back({false, 0, cur}); cur.clear();
+            unsigned long long v = 0; std::string digits;
+            while (i < s.size() && isdigit((unsigned char)s[i])) { v = v * 10 + (s[i] - '0'); digits += s[i]; ++i; }
+            out.push_back({true, v, digits});
+        } else if (i < s.size()) { cur += (char)tolower((unsigned char)s[i]); ++i; }
+        else { out.push_back({false, 0, cur}); ++i; }
+    }
+    return out;
+}
+static int nat_cmp(const std::string& a, const std::string& b) {
+    const std::vector<NatTok> x = nat_split(a), y = nat_split(b);
+    for (size_t i = 0; i < x.size() && i < y.size(); ++i) {
+        // text and number tokens alternate identically in both lists, so kinds always match
+        if (x[i].num) { if (x[i].val != y[i].val) return x[i].val < y[i].val ? -1 : 1; }
+        else { const int c = x[i].txt.compare(y[i].txt); if (c) return c < 0 ? -1 : 1; }
+    }
+    return x.size() == y.size() ? 0 : (x.size() < y.size() ? -1 : 1);
+}
+
+struct FmtRow { std::vector<std::string> info_words; std::string name, type, min_cov, line; };
+
+extern "C" int64_t km_result_format_target(const km_result* r, int32_t tg, const char* db_name, const char* query_name, char* buf,
+                                           int64_t buf_len) {
+    if (!r || tg < 0 || tg >= r->n_targets || !db_name || !query_name) { fail(KM_E_ARG, "km_result_format_target: bad argument"); return -1; }
+    const int k = r->k;
+    const char* tseq = r->targets.data() + r->seq_off[tg];
+    std::vector<FmtRow> rows;
+    for (int i = 0; i < r->row_count[tg]; ++i) {
+        const km_row& w = r->rows[r->row_first[tg] + i];
+        const char* pseq = r->seq_pool.data() + r->path_seq_off[w.path_id];
+        FmtRow fr;
+        fr.type = TYPE_NAME[w.type];
+        if (w.type != 0) {      // "{}\t{}:{}:{}" (MutationFinder.py:483-488); Reference -> "Reference\t"
+            fr.name = std::to_string(w.name_start) + ":";
+            for (int j = 0; j < w.del_len; ++j) fr.name += (char)tolower((unsigned char)tseq[w.del_begin + j + k - 1]);
+            fr.name += "/";
+            for (int j = 0; j < w.ins_len; ++j) fr.name += pseq[w.ins_begin + j + k - 1];
+            fr.name += ":" + std::to_string(w.name_end);
+        }
+        std::string info = w.kind == 0 ? std::string("vs_ref")
+                                       : "cluster " + std::to_string(w.cluster_id) + " n=" + std::to_string(w.cluster_n);
+        fr.min_cov = std::to_string((long long)w.min_cov);
+        std::string& L = fr.line;
+        L = db_name; L += '\t'; L += query_name; L += '\t'; L += fr.type; L += '\t'; L += fr.name; L += '\t';
+        fmt_float(L, w.rvaf, 3); L += '\t'; fmt_float(L, w.expr, 1); L += '\t';
+        L += fr.min_cov; L += '\t'; L += std::to_string(w.start_off); L += '\t';
+        if (w.var_end > w.var_begin) L.append(pseq + w.var_begin, (size_t)(w.var_end - w.var_begin + k - 1));
+        L += '\t'; fmt_float(L, w.ref_expr, 1); L += '\t';
+        if (w.ref_end > w.ref_begin) L.append(tseq + w.ref_begin, (size_t)(w.ref_end - w.ref_begin + k - 1));
+        L += '\t'; L += info; L += '\n';
+        size_t p = 0;
+        while (true) { size_t q = info.find(' ', p); fr.info_words.push_back(info.substr(p, q == std::string::npos ? q : q - p)); if (q == std::string::npos) break; p = q + 1; }
+        rows.push_back(std::move(fr));
+    }
+    // key = natsortkey(*info.split(' '), query, variant_name, type, min_coverage, rev_ix=[0]) (:825-829;
+    // x[6] of the tab-split row is Min_coverage);
+    // tuples compare element-wise, a shorter tuple that is a prefix sorts first
+    const std::string qn = query_name;
+    auto key_of = [&](const FmtRow& f) {
+        std::vector<const std::string*> ks;
+        for (auto& wd : f.info_words) ks.push_back(&wd);
+        ks.push_back(&qn); ks.push_back(&f.name); ks.push_back(&f.type); ks.push_back(&f.min_cov);
+        return ks;
+    };
+    std::stable_sort(rows.begin(), rows.end(), [&](const FmtRow& a, const FmtRow& b) {
+        const auto ka = key_of(a), kb = key_of(b);
+        for (size_t i = 0; i < ka.size() && i < kb.size(); ++i) {
+            int c = nat_cmp(*ka[i], *kb[i]);
+            if (i == 0) c = -c;                 // rev_ix=[0]
+            if (c) return c < 0;
+        }
+        return ka.size() < kb.size();
+    });
+    int64_t need = 0;
+    for (auto& f : rows) need += (int64_t)f.line.size();
+    if (buf && need < buf_len) {
+        int64_t at = 0;
+        for (auto& f : rows) { memcpy(buf + at, f.line.data(), f.line.size()); at += (int64_t)f.line.size(); }
+        buf[at] = 0;
+    }
+    return need;
+}
+
+// ---- measurement helpers ---------------------------------------------------------------------------
+extern "C" int km_bench_random_gather(int device, uint64_t bytes, uint64_t n_loads, int iters, float* best_ms) {
+    if (!best_ms || bytes < 64 || iters < 1) return fail(KM_E_ARG, "km_bench_random_gather: bad argument");
+    if (km_device_count() <= 0) return fail(KM_E_NOGPU, "no CUDA device");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    void* buf = nullptr;
+    uint32_t* sink = nullptr;
+    CU(cudaMalloc(&buf, bytes));
+    CU(cudaMalloc((void**)&sink, 4));
+    CU(cudaMemset(buf, 0x5A, bytes));
+    cudaEvent_t a, b;
+    CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b));
+    float best = 1e30f;
+    for (int it = 0; it < iters + 1; ++it) {
+        CU(cudaEventRecord(a));
+        km_gather_kernel<<<prop.multiProcessorCount * 8, 256>>>((const uint4*)buf, bytes / 32, n_loads, 0x1234 + it, sink);
+        CU(cudaEventRecord(b));
+        CU(cudaEventSynchronize(b));
+        float ms; CU(cudaEventElapsedTime(&ms, a, b));
+        if (it > 0 && ms < best) best = ms;     // first pass is warm-up
+    }
+    CU(cudaGetLastError());
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(buf); cudaFree(sink);
+    *best_ms = best;
+    return 0;
+}
+
+extern "C" int km_bench_lookup(km_table* t, uint64_t table_seed, uint64_t table_n, uint64_t n_queries, uint64_t query_seed, int iters,
+                               float* best_ms, float* mean_ms, uint64_t* n_hits) {
+    if (!t || !n_queries || iters < 1) return fail(KM_E_ARG, "km_bench_lookup: bad argument");
+    CU(cudaSetDevice(t->device));
+    uint64_t* dq = nullptr; uint32_t* dc = nullptr;
+    CU(cudaMalloc((void**)&dq, n_queries * 8));
+    CU(cudaMalloc((void**)&dc, n_queries * 4));
+    cudaStream_t s = t->stream;
+    km_make_queries_kernel<<<t->sm_count * 8, 256, 0, s>>>(dq, n_queries, table_seed, table_n, query_seed, t->k);
+    CU(cudaGetLastError());
+    float best = 1e30f, sum = 0;
+    for (int it = 0; it < iters + 3; ++it) {       // 3 warm-up passes
+        CU(cudaEventRecord(t->ev[0], s));
+        if (int rc = km_query_batch_device(t, dq, n_queries, dc, s)) return rc;
+        CU(cudaEventRecord(t->ev[1], s));
+        CU(cudaEventSynchronize(t->ev[1]));
+        float ms; CU(cudaEventElapsedTime(&ms, t->ev[0], t->ev[1]));
+        if (it >= 3) { best = std::min(best, ms); sum += ms; }
+    }
+    CU(cudaMemsetAsync(t->d_counter, 0, 16, s));
+    km_count_nonzero_kernel<<<t->sm_count * 8, 256, 0, s>>>(dc, n_queries, t->d_counter);
+    unsigned long long hits = 0;
+    CU(cudaMemcpyAsync(&hits, t->d_counter, 8, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    cudaFree(dq); cudaFree(dc);
+    if (best_ms) *best_ms = best;
+    if (mean_ms) *mean_ms = sum / iters;
+    if (n_hits) *n_hits = hits;
+    return 0;
+}

@@ -1,0 +1,68 @@
+// Execution-model shim shared by every device header in this directory.
+//
+// Compiled by nvcc (the product, libkm_b200.so) the stage functions are __device__ ONLY:
+// there is no host-callable copy of the hot path in the shipped library and no CPU
+// fallback.  Compiled by g++ (tests/emu only, never by km_b200/) the same source becomes a
+// single-lane sequential program -- tid 0 of 1, barriers are no-ops, atomics are plain
+// loads/stores -- so the kernel LOGIC can be checked against the oracle on a machine
+// without a GPU (tests/test_emu_*.py).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define KM_HD __device__ __forceinline__
+#define KM_DEVICE_BUILD 1
+#else
+#define KM_HD static inline
+#define KM_HOST_EMU 1
+#include <cmath>
+#include <cstring>
+#endif
+
+namespace km {
+
+#if KM_DEVICE_BUILD
+// One CTA works on one target.
+struct CtaCtx {
+    KM_HD int tid() const { return threadIdx.x; }
+    KM_HD int nt() const { return blockDim.x; }
+    KM_HD void sync() const { __syncthreads(); }
+    KM_HD int sync_or(int p) const { return __syncthreads_or(p); }
+};
+KM_HD uint64_t atomic_cas64(uint64_t* p, uint64_t cmp, uint64_t val) {
+    return atomicCAS(reinterpret_cast<unsigned long long*>(p), (unsigned long long)cmp, (unsigned long long)val);
+}
+KM_HD uint32_t atomic_add32(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
+KM_HD int32_t atomic_addi32(int32_t* p, int32_t v) { return atomicAdd(p, v); }
+KM_HD uint32_t atomic_min32(uint32_t* p, uint32_t v) { return atomicMin(p, v); }
+KM_HD uint32_t atomic_or32(uint32_t* p, uint32_t v) { return atomicOr(p, v); }
+KM_HD unsigned long long atomic_add64(unsigned long long* p, unsigned long long v) { return atomicAdd(p, v); }
+// loads that must observe other threads' atomics: go to L2, never a stale L1 line
+KM_HD uint64_t load_cg64(const uint64_t* p) { return __ldcg(reinterpret_cast<const unsigned long long*>(p)); }
+KM_HD uint32_t load_cg32(const uint32_t* p) { return __ldcg(p); }
+KM_HD uint8_t load_cg8(const uint8_t* p) { return __ldcg(p); }
+KM_HD int clz64(uint64_t x) { return __clzll((long long)x); }
+KM_HD uint64_t mulhi64(uint64_t a, uint64_t b) { return __umul64hi(a, b); }
+KM_HD float add_f32(float a, float b) { return __fadd_rn(a, b); }
+#else
+struct CtaCtx {
+    int tid() const { return 0; }
+    int nt() const { return 1; }
+    void sync() const {}
+    int sync_or(int p) const { return p; }
+};
+KM_HD uint64_t atomic_cas64(uint64_t* p, uint64_t cmp, uint64_t val) { uint64_t o = *p; if (o == cmp) *p = val; return o; }
+KM_HD uint32_t atomic_add32(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
+KM_HD int32_t atomic_addi32(int32_t* p, int32_t v) { int32_t o = *p; *p = o + v; return o; }
+KM_HD uint32_t atomic_min32(uint32_t* p, uint32_t v) { uint32_t o = *p; if (v < o) *p = v; return o; }
+KM_HD uint32_t atomic_or32(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o | v; return o; }
+KM_HD unsigned long long atomic_add64(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }
+KM_HD uint64_t load_cg64(const uint64_t* p) { return *p; }
+KM_HD uint32_t load_cg32(const uint32_t* p) { return *p; }
+KM_HD uint8_t load_cg8(const uint8_t* p) { return *p; }
+KM_HD int clz64(uint64_t x) { return x ? __builtin_clzll(x) : 64; }
+KM_HD uint64_t mulhi64(uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)a * b) >> 64); }
+KM_HD float add_f32(float a, float b) { volatile float r = a + b; return r; }
+#endif
+
+}  // namespace km

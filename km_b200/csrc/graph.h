@@ -1,0 +1,384 @@
+// Stage 2 of km_find_batch: per-target graph analysis by one CTA.
+//
+// Reproduces MutationFinder.graph_analysis (km/utils/MutationFinder.py:496-572) and
+// km/utils/Graph.py on the node set kept by the walk:
+//   * canonical node numbering: reference k-mers 0..L-1 in sequence order, kept novel
+//     k-mers by ascending packed value, then BigBang = N-2, BigCrunch = N-1
+//     (MutationFinder.py:122-123; numbering rule shared with oracle/km_oracle.py)
+//   * (k-1)-overlap edges found by probing the target's visited set with the 4 successor /
+//     4 predecessor k-mers of every node instead of a dense N x N matrix (:515-531); weights
+//     1.0f, reference-consecutive and cap edges 0.01f (:535-551)
+//   * two single-source shortest-path trees in float32 with the reference's tie rules
+//     (Graph.py:63-119: settle the open node of least distance, lowest index on ties;
+//     re-parent only on a strictly smaller float32 sum)
+//   * removal of the reference chain's edges (Graph.py:178-198), then one candidate path
+//     per remaining edge (Graph.py:200-240), de-duplicated and sorted lexicographically
+#pragma once
+#include "walk.h"
+
+namespace km {
+
+#define KM_MAX_PATHS 1024       // unique alternative paths per target this build handles
+#define KM_MAX_COLS 64          // columns of one least-squares problem (1 + cluster size)
+
+// One output row (PathQuant.Path, km/utils/PathQuant.py:10-49) in numeric form; the host
+// spells the strings from the node k-mers.  Mirrored by km_row in include/km_b200.h.
+struct Row {
+    int32_t target;
+    int32_t kind;          // 0 = vs_ref, 1 = cluster
+    int32_t type;          // 0 Reference 1 Substitution 2 ITD 3 Indel 4 Insertion 5 Deletion
+    int32_t name_start;    // diff.start + k + offset          (MutationFinder.py:485)
+    int32_t name_end;      // diff.end_ref + 1 + offset        (MutationFinder.py:487)
+    int32_t path_id;       // global id of the variant path
+    int32_t var_begin, var_end;   // slice of that path printed as Sequence
+    int32_t ref_begin, ref_end;   // slice of the reference path printed as Reference_sequence
+    int32_t del_begin, del_len;   // deleted bases = last base of reference k-mers [del_begin, +del_len)
+    int32_t ins_begin, ins_len;   // inserted bases = last base of path nodes at positions [ins_begin, +ins_len)
+    int32_t start_off;
+    int32_t cluster_id, cluster_n;
+    int32_t n_iter;        // refine_coef iterations (PathQuant.py:128-136)
+    int64_t min_cov;
+    double rvaf, expr, ref_rvaf, ref_expr;
+};
+
+struct ResultView {
+    // per target
+    int32_t* t_n;            // node count incl. the two caps
+    int32_t* t_n_paths;
+    int32_t* t_path_first;
+    int32_t* t_n_rows;
+    int32_t* t_row_first;
+    // canonical node arrays, same offsets as WalkView::node_off
+    uint64_t* out_kmer;
+    uint32_t* out_count;
+    // path table
+    int64_t* path_off;
+    int32_t* path_len;
+    int32_t* pool;
+    int32_t path_cap;
+    int64_t pool_cap;
+    Row* rows;
+    int32_t row_cap;
+    // [0] paths used, [1] pool ints used, [2] rows used, [3] sequence chars used
+    unsigned long long* used;
+};
+
+// Per-CTA scratch in HBM (L2 resident in practice), sized for the largest target.
+struct GraphScratch {
+    int32_t* newidx;   // [maxcap]   discovery index -> canonical index, -1 dropped
+    int32_t* kept;     // [maxcap]   discovery indices of kept novel nodes
+    int32_t* succ;     // [4*maxN]
+    int32_t* pred;     // [4*maxN]
+    float* dist;       // [maxN]
+    int32_t* before;   // [maxN]
+    int32_t* after;    // [maxN]
+    int32_t* cand;     // [maxN]
+    uint8_t* state;    // [maxN]
+    uint8_t* eflag;    // [maxN]  bit c: edge to succ[c] still in edge_set; bit 4: cap edge
+    uint8_t* reach;    // [maxN]  bit 0 reachable from source, bit 1 reaches sink
+    int32_t* occ;      // [maxN]
+    int32_t* ce_a;     // [4*maxN+2] candidate edges
+    int32_t* ce_b;
+    int32_t* ce_len;
+    uint64_t* ce_h1;
+    uint64_t* ce_h2;
+    int32_t* upath;    // [KM_MAX_PATHS] candidate index of each unique path
+    int32_t* pdiff;    // [4*KM_MAX_PATHS] start, end_ref, end_var, end_ref_overlap
+    int32_t* grp;      // [5*KM_MAX_PATHS] cluster bookkeeping
+    double* G;         // [KM_MAX_COLS*KM_MAX_COLS]
+    double* V;         // [2*KM_MAX_COLS*KM_MAX_COLS]
+    double* vec;       // [8*KM_MAX_COLS]
+    int maxN;
+};
+
+#define KM_REF_W 0.01f
+#define KM_ALT_W 1.0f
+
+struct GraphDims {
+    int L, N, src, snk;
+};
+
+// weight of edge i -> j (MutationFinder.py:512, 535-551)
+KM_HD float edge_weight(const GraphDims& d, int i, int j) {
+    if (i == d.src || j == d.snk) return KM_REF_W;
+    if (i < d.L - 1 && j == i + 1) return KM_REF_W;
+    return KM_ALT_W;
+}
+
+// Out-neighbours of u in the forward graph: up to 4 overlap successors + the cap edges.
+// Calls f(j, slot) with slot 0..3 for overlap edges and 4 for the cap edge.
+template <class F>
+KM_HD void for_each_succ(const GraphScratch& S, const GraphDims& d, int u, F f) {
+    if (u == d.src) { f(0, 4); return; }
+    if (u == d.snk) return;
+    for (int c = 0; c < 4; ++c) {
+        const int j = S.succ[4 * u + c];
+        if (j >= 0) f(j, c);
+    }
+    if (u == d.L - 1) f(d.snk, 4);
+}
+
+template <class F>
+KM_HD void for_each_pred(const GraphScratch& S, const GraphDims& d, int u, F f) {
+    if (u == d.snk) { f(d.L - 1); return; }
+    if (u == d.src) return;
+    for (int c = 0; c < 4; ++c) {
+        const int j = S.pred[4 * u + c];
+        if (j >= 0) f(j);
+    }
+    if (u == 0) f(d.src);
+}
+
+// Graph._get_paths (Graph.py:63-119) on adjacency lists.  `forward` walks w, otherwise
+// w transposed.  Sequential: executed by one lane.  Only nodes that acquire a finite
+// distance are ever settled with effect, so the open set is kept as an explicit list.
+KM_HD void shortest_tree(const GraphScratch& S, const GraphDims& d, int start, bool forward, int32_t* prev,
+                         uint8_t reach_bit) {
+    for (int i = 0; i < d.N; ++i) { S.dist[i] = INFINITY; prev[i] = -1; S.state[i] = 0; }
+    S.dist[start] = 0.0f;
+    int nc = 0;
+    S.cand[nc++] = start;
+    S.state[start] = 1;
+    while (nc > 0) {
+        // open node of least distance, lowest index on ties (Graph.py:113-114)
+        int best = 0;
+        for (int c = 1; c < nc; ++c) {
+            const int a = S.cand[c], b = S.cand[best];
+            const float da = S.dist[a], db = S.dist[b];
+            if (da < db || (da == db && a < b)) best = c;
+        }
+        const int u = S.cand[best];
+        S.cand[best] = S.cand[--nc];
+        S.state[u] = 2;
+        S.reach[u] |= reach_bit;
+        const float du = S.dist[u];
+        auto relax = [&](int j, float w) {
+            const float trial = add_f32(w, du);          // w[i, :] + dist[i] in float32 (:93)
+            if (trial < S.dist[j]) {                     // strict (:103)
+                S.dist[j] = trial;
+                prev[j] = u;
+                if (S.state[j] == 0) { S.state[j] = 1; S.cand[nc++] = j; }
+            }
+        };
+        if (forward) for_each_succ(S, d, u, [&](int j, int) { relax(j, edge_weight(d, u, j)); });
+        else for_each_pred(S, d, u, [&](int j) { relax(j, edge_weight(d, j, u)); });
+    }
+}
+
+// Position-keyed additive hash: the same index sequence hashes identically no matter at which
+// edge it was split into a forward and a backward half.
+KM_HD void hash_step(uint64_t& h1, uint64_t& h2, int pos, int v) {
+    const uint64_t x = ((uint64_t)(uint32_t)pos << 32) | (uint64_t)(uint32_t)v;
+    h1 += mix64(x ^ 0x243F6A8885A308D3ull);
+    h2 += mix64((x + 0x13198A2E03707344ull) * 0xD1342543DE82EF95ull);
+}
+
+// Builds the graph of target t and emits its unique alternative paths (caps stripped).
+// Returns the number of unique paths through *n_unique; paths are written to the result
+// pool in lexicographic order.  All threads of the CTA must call this.
+template <class Ctx>
+KM_HD void graph_target(const Ctx& ctx, const TableView& T, const WalkView& W, const GraphScratch& S,
+                        const ResultView& R, int t, GraphDims* dims_out, int* sh /* 8 ints of CTA-shared memory */) {
+    const int k = T.k;
+    const TargetGeom g = target_geom(W, t, k);
+    const int tid = ctx.tid(), nt = ctx.nt();
+    const int n_all = W.n_nodes[t] < g.cap ? W.n_nodes[t] : g.cap;
+    const int L = g.L;
+
+    // ---- canonical numbering -------------------------------------------------
+    if (tid == 0) sh[0] = 0;
+    ctx.sync();
+    for (int q = tid; q < n_all; q += nt) {
+        if (q < L) { S.newidx[q] = q; continue; }
+        S.newidx[q] = -1;
+        if (W.hflag[g.hbase + W.node_slot[g.nbase + q]]) {
+            const int pos = atomic_addi32(&sh[0], 1);
+            S.kept[pos] = q;
+        }
+    }
+    ctx.sync();
+    const int nk = sh[0];
+    // rank kept novel nodes by packed k-mer value (all distinct)
+    for (int a = tid; a < nk; a += nt) {
+        const uint64_t ka = W.node_kmer[g.nbase + S.kept[a]];
+        int rank = 0;
+        for (int b = 0; b < nk; ++b) rank += W.node_kmer[g.nbase + S.kept[b]] < ka ? 1 : 0;
+        S.newidx[S.kept[a]] = L + rank;
+    }
+    ctx.sync();
+    GraphDims d;
+    d.L = L; d.N = L + nk + 2; d.src = d.N - 2; d.snk = d.N - 1;
+    *dims_out = d;
+    for (int q = tid; q < n_all; q += nt) {
+        const int i = S.newidx[q];
+        if (i >= 0) {
+            R.out_kmer[g.nbase + i] = W.node_kmer[g.nbase + q];
+            R.out_count[g.nbase + i] = W.node_count[g.nbase + q];
+        }
+    }
+    if (tid == 0) R.t_n[t] = d.N;
+    ctx.sync();
+
+    // ---- adjacency (MutationFinder.py:515-531) --------------------------------
+    const int n_real = d.N - 2;
+    for (int e = tid; e < 4 * n_real; e += nt) {
+        const int i = e >> 2, c = e & 3;
+        const uint64_t km = R.out_kmer[g.nbase + i];
+        int js = -1, jp = -1;
+        uint32_t s = visited_find(W, g, succ_kmer(km, c, T.kmask));
+        if (s != KM_NO_SLOT && W.hflag[g.hbase + s]) js = S.newidx[W.hval[g.hbase + s]];
+        if (js == i) js = -1;                       // `if i != j` (:530)
+        s = visited_find(W, g, pred_kmer(km, c, k));
+        if (s != KM_NO_SLOT && W.hflag[g.hbase + s]) jp = S.newidx[W.hval[g.hbase + s]];
+        if (jp == i) jp = -1;
+        S.succ[e] = js;
+        S.pred[e] = jp;
+    }
+    for (int i = tid; i < d.N; i += nt) { S.eflag[i] = 0x1F; S.reach[i] = 0; }
+    ctx.sync();
+
+    // ---- two shortest-path trees (Graph.py:175-176) ---------------------------
+    // TODO(perf): the two passes are independent; they share S.dist/S.cand here so they
+    // run back to back on one lane.
+    if (tid == 0) {
+        shortest_tree(S, d, d.src, true, S.before, 1);
+        shortest_tree(S, d, d.snk, false, S.after, 2);
+        // ---- strip the reference chain (Graph.py:178-198) ----------------------
+        for (int start = 0; start < d.N; ++start) {
+            if (S.before[start] != d.src) continue;
+            int cur = start, last = -1;
+            while (S.after[cur] != -1) {
+                cur = S.after[cur];
+                if (last > 0) {                      // `if last_cur and ...`: None and 0 are falsy
+                    if (cur == d.snk) { if (last == d.L - 1) S.eflag[last] &= (uint8_t)~0x10; }
+                    else for (int c = 0; c < 4; ++c)
+                        if (S.succ[4 * last + c] == cur) S.eflag[last] &= (uint8_t)~(1u << c);
+                }
+                last = cur;
+            }
+        }
+        sh[1] = 0;   // candidate count
+    }
+    ctx.sync();
+
+    // ---- candidate edges (Graph.py:220-240) -----------------------------------
+    // edge (a, b) yields a path iff a is reachable from the source and b reaches the sink
+    for (int a = tid; a < d.N; a += nt) {
+        if (!(S.reach[a] & 1)) continue;
+        for_each_succ(S, d, a, [&](int b, int slot) {
+            if (!(S.eflag[a] & (1u << slot))) return;
+            if (!(S.reach[b] & 2)) return;
+            const int pos = atomic_addi32(&sh[1], 1);
+            S.ce_a[pos] = a;
+            S.ce_b[pos] = b;
+        });
+    }
+    ctx.sync();
+    const int n_cand = sh[1];
+    // order candidates deterministically by (a, b) -- rank sort, n_cand is small
+    for (int c = tid; c < n_cand; c += nt) {
+        const int a = S.ce_a[c], b = S.ce_b[c];
+        int rank = 0;
+        for (int o = 0; o < n_cand; ++o) {
+            const int oa = S.ce_a[o], ob = S.ce_b[o];
+            rank += (oa < a || (oa == a && ob < b)) ? 1 : 0;
+        }
+        S.ce_len[c] = rank;    // borrowed as the destination index
+    }
+    ctx.sync();
+    for (int c = tid; c < n_cand; c += nt) {
+        // stash (a,b) in the hash arrays while permuting
+        S.ce_h1[c] = ((uint64_t)(uint32_t)S.ce_a[c] << 32) | (uint32_t)S.ce_b[c];
+        S.ce_h2[c] = (uint64_t)S.ce_len[c];
+    }
+    ctx.sync();
+    for (int c = tid; c < n_cand; c += nt) {
+        const int dst = (int)S.ce_h2[c];
+        S.ce_a[dst] = (int)(S.ce_h1[c] >> 32);
+        S.ce_b[dst] = (int)(uint32_t)S.ce_h1[c];
+    }
+    ctx.sync();
+    // length + two independent 64-bit hashes of the index sequence src..a, b..snk
+    for (int c = tid; c < n_cand; c += nt) {
+        uint64_t h1 = 0, h2 = 0;
+        int lf = 0;
+        for (int cur = S.ce_a[c]; cur != -1; cur = S.before[cur]) ++lf;
+        int pos = lf - 1;
+        for (int cur = S.ce_a[c]; cur != -1; cur = S.before[cur]) hash_step(h1, h2, pos--, cur);
+        pos = lf;
+        for (int cur = S.ce_b[c]; cur != -1; cur = S.after[cur]) hash_step(h1, h2, pos++, cur);
+        S.ce_len[c] = pos;
+        S.ce_h1[c] = h1;
+        S.ce_h2[c] = h2;
+    }
+    ctx.sync();
+
+    // ---- de-duplicate, materialise, sort (set of tuples -> sorted list) --------
+    if (tid == 0) {
+        int nu = 0;
+        bool overflow = false;
+        for (int c = 0; c < n_cand; ++c) {
+            bool dup = false;
+            for (int u = 0; u < nu && !dup; ++u) {
+                const int o = S.upath[u];
+                dup = S.ce_len[o] == S.ce_len[c] && S.ce_h1[o] == S.ce_h1[c] && S.ce_h2[o] == S.ce_h2[c];
+            }
+            if (dup) continue;
+            if (nu >= KM_MAX_PATHS) { overflow = true; break; }
+            S.upath[nu++] = c;
+        }
+        int first = 0;
+        if (!overflow && nu > 0) {
+            first = (int)atomic_add64(&R.used[0], (unsigned long long)nu);
+            if (first + nu > R.path_cap) overflow = true;
+        }
+        if (!overflow) {
+            for (int u = 0; u < nu && !overflow; ++u) {
+                const int c = S.upath[u];
+                const int len = S.ce_len[c] - 2;                 // caps stripped (MutationFinder.py:562)
+                const int64_t off = (int64_t)atomic_add64(&R.used[1], (unsigned long long)len);
+                if (off + len > R.pool_cap) { overflow = true; break; }
+                int32_t* dst = R.pool + off;
+                // forward half: positions len_f-2 .. 0 (source cap dropped)
+                int lf = 0;
+                for (int cur = S.ce_a[c]; cur != -1; cur = S.before[cur]) ++lf;
+                int p = lf - 2;
+                for (int cur = S.ce_a[c]; cur != d.src; cur = S.before[cur]) dst[p--] = cur;
+                p = lf - 1;
+                for (int cur = S.ce_b[c]; cur != d.snk; cur = S.after[cur]) dst[p++] = cur;
+                R.path_off[first + u] = off;
+                R.path_len[first + u] = len;
+            }
+        }
+        if (!overflow) {
+            // lexicographic insertion sort of the (few) unique paths
+            for (int u = 1; u < nu; ++u) {
+                const int64_t off_u = R.path_off[first + u];
+                const int len_u = R.path_len[first + u];
+                int v = u - 1;
+                while (v >= 0) {
+                    const int64_t off_v = R.path_off[first + v];
+                    const int len_v = R.path_len[first + v];
+                    const int32_t *pu = R.pool + off_u, *pv = R.pool + off_v;
+                    int m = len_u < len_v ? len_u : len_v, x = 0;
+                    while (x < m && pu[x] == pv[x]) ++x;
+                    const bool u_less = x < m ? pu[x] < pv[x] : len_u < len_v;
+                    if (!u_less) break;
+                    R.path_off[first + v + 1] = off_v;
+                    R.path_len[first + v + 1] = len_v;
+                    --v;
+                }
+                R.path_off[first + v + 1] = off_u;
+                R.path_len[first + v + 1] = len_u;
+            }
+        }
+        if (overflow) { atomic_or32(&W.status[t], KM_ST_PATH_OVERFLOW); nu = 0; first = 0; }
+        R.t_n_paths[t] = nu;
+        R.t_path_first[t] = first;
+        sh[2] = nu;
+        sh[3] = first;
+    }
+    ctx.sync();
+}
+
+}  // namespace km

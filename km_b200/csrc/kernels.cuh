@@ -1,0 +1,258 @@
+// __global__ entry points of libkm_b200.so (sm_100a).  Each kernel is a thin wrapper over
+// the stage functions in table.h / walk.h / graph.h / quant.h.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "quant.h"
+#include "synth.h"
+
+namespace km {
+
+#define KM_CTA 128
+
+// ---- table maintenance ----------------------------------------------------------------
+__global__ void km_table_clear_kernel(Bucket* buckets, uint64_t n) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * n; i += stride) {
+        // two 16-byte stores per bucket, consecutive lanes on consecutive halves
+        uint4* p = reinterpret_cast<uint4*>(buckets) + i;
+        *p = (i & 1) ? make_uint4(0u, 0u, 0u, 0u) : make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+    }
+}
+
+__global__ void km_table_insert_kernel(TableView T, const uint64_t* keys, const uint32_t* counts, uint64_t n, int mode,
+                                       unsigned long long* n_new, uint32_t* full) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    unsigned long long mine = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int r = table_insert(T, keys[i] & T.kmask, counts[i], mode);
+        if (r < 0) *full = 1;
+        mine += r > 0;
+    }
+    if (mine) atomicAdd(n_new, mine);
+}
+
+__global__ void km_table_synth_kernel(TableView T, uint64_t seed, uint64_t n, unsigned long long* n_new, uint32_t* full) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    unsigned long long mine = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t key = synth_key(seed, i, T.k);
+        const int r = table_insert(T, key, synth_count(key), KM_INSERT_KEEP);
+        if (r < 0) *full = 1;
+        mine += r > 0;
+    }
+    if (mine) atomicAdd(n_new, mine);
+}
+
+// K1': canonical k-mer counting from reads (jellyfish count -C; run_leucegene.sh:22)
+__global__ void km_count_reads_kernel(TableView T, const char* reads, const int64_t* off, int64_t n_reads, int64_t total,
+                                      unsigned long long* n_new, uint32_t* full) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    unsigned long long mine = 0;
+    for (int64_t pos = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pos < total; pos += stride) {
+        // binary search the read that owns this position
+        int64_t lo = 0, hi = n_reads;
+        while (hi - lo > 1) { const int64_t mid = (lo + hi) >> 1; if (off[mid] <= pos) lo = mid; else hi = mid; }
+        if (pos + T.k > off[lo + 1]) continue;
+        uint64_t v = 0; bool ok = true;
+        for (int j = 0; j < T.k; ++j) {
+            uint64_t c;
+            switch (reads[pos + j]) {
+                case 'A': case 'a': c = 0; break; case 'C': case 'c': c = 1; break;
+                case 'G': case 'g': c = 2; break; case 'T': case 't': c = 3; break;
+                default: c = 0; ok = false;
+            }
+            v = (v << 2) | c;
+        }
+        if (!ok) continue;
+        const int r = table_insert(T, T.canonical ? canonical(v, T.k) : v, 1u, KM_INSERT_ADD);
+        if (r < 0) *full = 1;
+        mine += r > 0;
+    }
+    if (mine) atomicAdd(n_new, mine);
+}
+
+__global__ void km_table_filter_kernel(TableView src, TableView dst, uint32_t min_count, unsigned long long* n_new, uint32_t* full) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    unsigned long long mine = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < src.n_buckets * KM_BUCKET_SLOTS; i += stride) {
+        const Bucket* b = src.buckets + i / KM_BUCKET_SLOTS;
+        const int s = (int)(i % KM_BUCKET_SLOTS);
+        const uint64_t key = b->key[s];
+        if (key == KM_EMPTY_KEY || b->count[s] < min_count) continue;
+        const int r = table_insert(dst, key, b->count[s], KM_INSERT_KEEP);
+        if (r < 0) *full = 1;
+        mine += r > 0;
+    }
+    if (mine) atomicAdd(n_new, mine);
+}
+
+// ---- K2: batched canonical probe (Jellyfish.query) ---------------------------------------
+#define KM_QUERY_ILP 4
+__global__ void __launch_bounds__(256) km_query_kernel(TableView T, const uint64_t* __restrict__ kmers, uint64_t n,
+                                                       uint32_t* __restrict__ out) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // each thread takes KM_QUERY_ILP queries `stride` apart: coalesced key reads and count
+    // writes, KM_QUERY_ILP independent random sector reads in flight
+    for (uint64_t base = tid; base < n; base += stride * KM_QUERY_ILP) {
+        uint64_t q[KM_QUERY_ILP];
+        uint32_t r[KM_QUERY_ILP];
+#pragma unroll
+        for (int i = 0; i < KM_QUERY_ILP; ++i) {
+            const uint64_t j = base + (uint64_t)i * stride;
+            q[i] = j < n ? kmers[j] : 0ull;
+        }
+        table_query_multi<KM_QUERY_ILP>(T, q, r);
+#pragma unroll
+        for (int i = 0; i < KM_QUERY_ILP; ++i) {
+            const uint64_t j = base + (uint64_t)i * stride;
+            if (j < n) out[j] = r[i];
+        }
+    }
+}
+
+// Jellyfish.get_child (Jellyfish.py:55-72), one thread per k-mer
+__global__ void __launch_bounds__(256) km_get_child_kernel(TableView T, const uint64_t* __restrict__ kmers, uint64_t n,
+                                                           int forward, double ratio, int64_t floor_count,
+                                                           uint32_t* __restrict__ counts, uint8_t* __restrict__ mask) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t v = kmers[i] & T.kmask;
+        uint64_t ck[4]; uint32_t cc[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) ck[c] = forward ? succ_kmer(v, c, T.kmask) : pred_kmer(v, c, T.k);
+        table_query_multi<4>(T, ck, cc);
+        const uint64_t sum = (uint64_t)cc[0] + cc[1] + cc[2] + cc[3];
+        double thr = (double)sum * ratio;
+        if (thr < (double)floor_count) thr = (double)floor_count;
+        uint8_t m = 0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { counts[4 * i + c] = cc[c]; m |= ((double)cc[c] >= thr) ? (1u << c) : 0u; }
+        mask[i] = m;
+    }
+}
+
+// ---- K3: walk, one CTA per target -----------------------------------------------------------
+__global__ void __launch_bounds__(KM_CTA) km_walk_kernel(TableView T, WalkView W, FindParams P) {
+    CtaCtx ctx;
+    walk_target(ctx, T, W, P, (int)blockIdx.x);
+}
+
+// ---- K4 + K5: graph, paths, FP64 quantification; persistent CTAs over targets -----------------
+struct ScratchLayout {
+    char* base;
+    size_t stride;          // bytes per CTA
+    size_t o_newidx, o_kept, o_succ, o_pred, o_dist, o_before, o_after, o_cand, o_state, o_eflag, o_reach, o_occ;
+    size_t o_ce_a, o_ce_b, o_ce_len, o_ce_h1, o_ce_h2, o_upath, o_pdiff, o_grp, o_G, o_V, o_vec;
+    int maxN;
+};
+
+__device__ __forceinline__ GraphScratch carve(const ScratchLayout& L, int cta) {
+    char* p = L.base + (size_t)cta * L.stride;
+    GraphScratch S;
+    S.newidx = (int32_t*)(p + L.o_newidx); S.kept = (int32_t*)(p + L.o_kept);
+    S.succ = (int32_t*)(p + L.o_succ); S.pred = (int32_t*)(p + L.o_pred);
+    S.dist = (float*)(p + L.o_dist); S.before = (int32_t*)(p + L.o_before); S.after = (int32_t*)(p + L.o_after);
+    S.cand = (int32_t*)(p + L.o_cand); S.state = (uint8_t*)(p + L.o_state); S.eflag = (uint8_t*)(p + L.o_eflag);
+    S.reach = (uint8_t*)(p + L.o_reach); S.occ = (int32_t*)(p + L.o_occ);
+    S.ce_a = (int32_t*)(p + L.o_ce_a); S.ce_b = (int32_t*)(p + L.o_ce_b); S.ce_len = (int32_t*)(p + L.o_ce_len);
+    S.ce_h1 = (uint64_t*)(p + L.o_ce_h1); S.ce_h2 = (uint64_t*)(p + L.o_ce_h2);
+    S.upath = (int32_t*)(p + L.o_upath); S.pdiff = (int32_t*)(p + L.o_pdiff); S.grp = (int32_t*)(p + L.o_grp);
+    S.G = (double*)(p + L.o_G); S.V = (double*)(p + L.o_V); S.vec = (double*)(p + L.o_vec);
+    S.maxN = L.maxN;
+    return S;
+}
+
+#define KM_ST_FATAL (KM_ST_BAD_BASE | KM_ST_DUP_KMER | KM_ST_NODE_OVERFLOW | KM_ST_NODE_LIMIT | KM_ST_TOO_SHORT)
+
+__global__ void __launch_bounds__(KM_CTA) km_graph_kernel(TableView T, WalkView W, ScratchLayout SL, ResultView R,
+                                                          char* seq_pool, int64_t* path_seq_off, int64_t seq_cap) {
+    __shared__ int sh[8];
+    CtaCtx ctx;
+    const GraphScratch S = carve(SL, (int)blockIdx.x);
+    for (int t = blockIdx.x; t < W.n_targets; t += gridDim.x) {
+        if (W.status[t] & KM_ST_FATAL) {
+            if (threadIdx.x == 0) {
+                R.t_n[t] = 0; R.t_n_paths[t] = 0; R.t_path_first[t] = 0; R.t_n_rows[t] = 0; R.t_row_first[t] = 0;
+            }
+            continue;
+        }
+        GraphDims d;
+        graph_target(ctx, T, W, S, R, t, &d, sh);
+        const int n_paths = sh[2], first = sh[3];
+        // spell every unique path once (MutationFinder.get_seq, :375-403): first k-mer, then
+        // the last base of each following node; rows print slices of these strings
+        const int64_t nbase = W.node_off[t];
+        for (int p = 0; p < n_paths; ++p) {
+            const int len = R.path_len[first + p];
+            const int32_t* idx = R.pool + R.path_off[first + p];
+            if (threadIdx.x == 0) {
+                const int64_t off = len > 0 ? (int64_t)atomicAdd(&R.used[3], (unsigned long long)(len + T.k - 1)) : 0;
+                sh[4] = (int)(off & 0x7FFFFFFF); sh[5] = (int)(off >> 31);
+            }
+            __syncthreads();
+            const int64_t off = ((int64_t)sh[5] << 31) | (int64_t)sh[4];
+            const bool fits = off + len + T.k - 1 <= seq_cap;
+            if (threadIdx.x == 0) path_seq_off[first + p] = fits ? off : -1;
+            if (!fits) { if (threadIdx.x == 0) atomicOr(&W.status[t], KM_ST_PATH_OVERFLOW); }
+            else if (len > 0) {
+                const uint64_t k0 = R.out_kmer[nbase + idx[0]];
+                for (int c = threadIdx.x; c < len + T.k - 1; c += blockDim.x) {
+                    int code;
+                    if (c < T.k) code = (int)((k0 >> (2 * (T.k - 1 - c))) & 3ull);
+                    else code = (int)(R.out_kmer[nbase + idx[c - T.k + 1]] & 3ull);
+                    seq_pool[off + c] = "ACGT"[code];
+                }
+            }
+            __syncthreads();
+        }
+        emit_rows(ctx, T, W, S, R, t, d, n_paths, first, sh);
+        __syncthreads();
+    }
+}
+
+// ---- measurement kernels -------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) km_gather_kernel(const uint4* __restrict__ buf, uint64_t n_sectors, uint64_t n_loads,
+                                                        uint64_t seed, uint32_t* sink) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint32_t acc = 0;
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; base < n_loads; base += stride * 4) {
+        uint64_t s[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s[i] = mulhi64(mix64(seed + (base + i * stride) * KM_GOLDEN), n_sectors);
+        uint64_t a[4], b[4]; uint32_t c[4], e[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) load_bucket(reinterpret_cast<const Bucket*>(buf) + s[i], a[i], b[i], c[i], e[i]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc ^= (uint32_t)a[i] ^ (uint32_t)b[i] ^ c[i] ^ e[i];
+    }
+    if (acc == 0x12345678u) *sink = acc;   // keeps the loads alive
+}
+
+// config-4 lookup mix generated on device: even j -> a background key (random strand), odd j -> random k-mer
+__global__ void km_make_queries_kernel(uint64_t* q, uint64_t n, uint64_t table_seed, uint64_t table_n, uint64_t seed, int k) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t mask = kmer_mask(k);
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+        const uint64_t r = mix64(seed + (j + 1) * KM_GOLDEN);
+        uint64_t v;
+        if ((r & 1ull) && table_n) {
+            const uint64_t i = mulhi64(mix64(r), table_n);
+            v = mix64(table_seed + (i + 1) * KM_GOLDEN) & mask;
+            if (r & 2ull) v = revcomp(v, k);
+        } else {
+            v = mix64(r ^ 0xA5A5A5A5A5A5A5A5ull) & mask;
+        }
+        q[j] = v;
+    }
+}
+
+__global__ void km_count_nonzero_kernel(const uint32_t* c, uint64_t n, unsigned long long* out) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    unsigned long long mine = 0;
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) mine += c[j] != 0;
+    if (mine) atomicAdd(out, mine);
+}
+
+}  // namespace km

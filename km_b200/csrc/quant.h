@@ -1,0 +1,374 @@
+// Stage 3 of km_find_batch: naming, clustering and FP64 quantification of one target's
+// alternative paths by the CTA that built its graph.
+//
+//   diff_paths      MutationFinder.diff_path_without_overlap   (MutationFinder.py:321-373)
+//   classify        MutationFinder.get_name                     (:429-488)
+//   solve_columns   PathQuant.__init__/compute_coef/refine_coef/get_ratio (PathQuant.py:94-149)
+//   emit_rows       quantify_paths (:613-648), _find_clusters (:651-723),
+//                   quantify_clusters (:749-811)
+//
+// The least-squares step works on the normal equations: G = A^T A and h = A^T b are sums of
+// small integers and float32-exact counts, hence EXACT in FP64; the minimum-norm solution
+// (what LAPACK gelsd returns for np.linalg.lstsq, PathQuant.py:116) is obtained from a
+// Jacobi eigen-decomposition of G with the singular-value cut of rcond = eps*max(M,N).
+// refine_coef is then iterated literally (fixed step 0.1, gradient / n_nodes, stop at
+// max|grad| <= 0.01): the reference's answer IS the iterate it stops at.
+#pragma once
+#include "graph.h"
+
+namespace km {
+
+// a (possibly clipped) path: idx == nullptr means the reference path, whose node at
+// position p is simply p
+struct PathView {
+    const int32_t* idx;
+    int begin;
+    int len;
+};
+KM_HD int pv_at(const PathView& p, int i) { return p.idx ? p.idx[p.begin + i] : p.begin + i; }
+
+struct Diff {
+    int start, end_ref, end_var, end_ref_overlap;
+};
+
+KM_HD Diff diff_paths(const PathView& ref, const PathView& alt, int k) {
+    Diff d;
+    const int nr = ref.len, na = alt.len;
+    int i = 0;
+    while (i < nr && i < na && pv_at(ref, i) == pv_at(alt, i)) ++i;
+    int jr = nr, ja = na;
+    while (jr >= i + k && ja >= i + k && pv_at(ref, jr - 1) == pv_at(alt, ja - 1)) { --jr; --ja; }
+    int kr = jr, ka = ja;
+    while (kr > i && pv_at(ref, kr - 1) == pv_at(alt, ka - 1)) { --kr; --ka; }
+    d.start = i; d.end_ref = jr; d.end_var = ja; d.end_ref_overlap = kr;
+    return d;
+}
+
+enum { KM_T_REFERENCE = 0, KM_T_SUBSTITUTION = 1, KM_T_ITD = 2, KM_T_INDEL = 3, KM_T_INSERTION = 4, KM_T_DELETION = 5 };
+
+// get_name: type + trimmed deleted / inserted runs.  kmers are the canonical node array.
+KM_HD int classify(const uint64_t* kmers, const PathView& ref, const PathView& alt, const Diff& d,
+                   int* del_len, int* ins_len) {
+    int gone = d.end_ref - d.start, fresh = d.end_var - d.start;
+    int cut = 0;
+    if (gone > 0) {     // strip the suffix both strings share (:446-456)
+        while (cut < gone && cut < fresh &&
+               (kmers[pv_at(ref, d.end_ref - 1 - cut)] & 3ull) == (kmers[pv_at(alt, d.end_var - 1 - cut)] & 3ull))
+            ++cut;
+    }
+    gone -= cut; fresh -= cut;
+    *del_len = gone; *ins_len = fresh;
+    if (d.end_ref == d.end_var) return d.start == d.end_ref ? KM_T_REFERENCE : KM_T_SUBSTITUTION;
+    if (d.start == d.end_ref_overlap) return KM_T_ITD;
+    if (d.end_ref < d.end_var) return gone == 0 ? KM_T_INSERTION : KM_T_INDEL;
+    return fresh == 0 ? KM_T_DELETION : KM_T_INDEL;
+}
+
+// cyclic Jacobi on the symmetric m x m matrix A (destroyed); V receives the eigenvectors
+// (columns), the diagonal of A the eigenvalues.
+KM_HD void jacobi_eigen(double* A, double* V, int m) {
+    for (int i = 0; i < m; ++i)
+        for (int j = 0; j < m; ++j) V[i * m + j] = i == j ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        double off = 0.0, diag = 0.0;
+        for (int i = 0; i < m; ++i) {
+            diag += A[i * m + i] * A[i * m + i];
+            for (int j = i + 1; j < m; ++j) off += A[i * m + j] * A[i * m + j];
+        }
+        if (off <= 1e-34 * diag || off == 0.0) break;
+        for (int p = 0; p < m - 1; ++p)
+            for (int q = p + 1; q < m; ++q) {
+                const double apq = A[p * m + q];
+                if (apq == 0.0) continue;
+                const double theta = (A[q * m + q] - A[p * m + p]) / (2.0 * apq);
+                const double tt = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(tt * tt + 1.0), s = tt * c;
+                for (int r = 0; r < m; ++r) {
+                    const double arp = A[r * m + p], arq = A[r * m + q];
+                    A[r * m + p] = c * arp - s * arq;
+                    A[r * m + q] = s * arp + c * arq;
+                }
+                for (int r = 0; r < m; ++r) {
+                    const double apr = A[p * m + r], aqr = A[q * m + r];
+                    A[p * m + r] = c * apr - s * aqr;
+                    A[q * m + r] = s * apr + c * aqr;
+                }
+                for (int r = 0; r < m; ++r) {
+                    const double vrp = V[r * m + p], vrq = V[r * m + q];
+                    V[r * m + p] = c * vrp - s * vrq;
+                    V[r * m + q] = s * vrp + c * vrq;
+                }
+            }
+    }
+}
+
+// Quantify m columns.  coef/rvaf receive m values each.  Returns refine iterations, or
+// -1 when the watchdog fired.  All threads of the CTA must call this.
+template <class Ctx>
+KM_HD int solve_columns(const Ctx& ctx, const GraphScratch& S, const uint32_t* counts, int n_nodes,
+                        const PathView* cols, int m, double* coef, double* rvaf, int* sh) {
+    const int tid = ctx.tid(), nt = ctx.nt();
+    double* G = S.G;
+    double* h = S.vec;   // [m]
+    // contrib[i, c] = occurrences of node i in column c (PathQuant.py:101-104);
+    // G[a][b] = sum_i contrib[i,a]*contrib[i,b]; h[a] = sum_i contrib[i,a]*float32(count_i)
+    for (int b = 0; b < m; ++b) {
+        for (int i = tid; i < n_nodes; i += nt) S.occ[i] = 0;
+        ctx.sync();
+        for (int p = tid; p < cols[b].len; p += nt) atomic_addi32(&S.occ[pv_at(cols[b], p)], 1);
+        ctx.sync();
+        if (tid == 0) {
+            // lane 0 accumulates: exact integer sums, order irrelevant
+            for (int a = b; a < m; ++a) {
+                long long acc = 0;
+                for (int p = 0; p < cols[a].len; ++p) acc += S.occ[pv_at(cols[a], p)];
+                G[a * m + b] = G[b * m + a] = (double)acc;
+            }
+            double hb = 0.0;
+            for (int p = 0; p < cols[b].len; ++p) hb += (double)(float)counts[pv_at(cols[b], p)];
+            h[b] = hb;
+        }
+        ctx.sync();
+    }
+    if (tid == 0) {
+        double* A = S.V;                 // working copy for the eigen solver
+        double* V = S.V + m * m;         // needs 2*m*m doubles: S.V is sized for that
+        for (int i = 0; i < m * m; ++i) A[i] = G[i];
+        jacobi_eigen(A, V, m);
+        double lmax = 0.0;
+        for (int i = 0; i < m; ++i) lmax = A[i * m + i] > lmax ? A[i * m + i] : lmax;
+        // singular values below eps*max(M,N)*s_max are dropped by lstsq(rcond=None); in
+        // eigenvalue terms that is far below FP64 resolution of G, so the cut is placed where
+        // an exactly rank-deficient integer G leaves its rounding noise.
+        const double cut = lmax * 1e-11;
+        for (int a = 0; a < m; ++a) coef[a] = 0.0;
+        for (int e = 0; e < m; ++e) {
+            const double lam = A[e * m + e];
+            if (!(lam > cut)) continue;
+            double proj = 0.0;
+            for (int a = 0; a < m; ++a) proj += V[a * m + e] * h[a];
+            proj /= lam;
+            for (int a = 0; a < m; ++a) coef[a] += V[a * m + e] * proj;
+        }
+        // refine_coef (PathQuant.py:120-136)
+        for (int a = 0; a < m; ++a) if (coef[a] < 0.0) coef[a] = 0.0;
+        double worst = INFINITY;
+        int iters = 0;
+        double* grad = S.vec + 2 * KM_MAX_COLS;
+        while (worst > 0.01) {
+            for (int a = 0; a < m; ++a) {
+                double fit = 0.0;
+                for (int b = 0; b < m; ++b) fit += G[a * m + b] * coef[b];
+                grad[a] = 2.0 * (h[a] - fit) / (double)n_nodes;
+            }
+            worst = 0.0;
+            for (int a = 0; a < m; ++a) {
+                coef[a] += 0.1 * grad[a];
+                if (coef[a] < 0.0) { grad[a] = 0.0; coef[a] = 0.0; }
+                const double ag = fabs(grad[a]);
+                worst = ag > worst ? ag : worst;     // NaN never enters: counts are finite
+            }
+            if (++iters > 10000000) { iters = -1; break; }
+        }
+        // get_ratio (PathQuant.py:144-149)
+        double cmax = coef[0], csum = 0.0;
+        for (int a = 0; a < m; ++a) { cmax = coef[a] > cmax ? coef[a] : cmax; csum += coef[a]; }
+        for (int a = 0; a < m; ++a) rvaf[a] = cmax == 0.0 ? coef[a] : coef[a] / csum;
+        sh[4] = iters;
+    }
+    ctx.sync();
+    return sh[4];
+}
+
+KM_HD int64_t min_count(const uint32_t* counts, const PathView& p) {
+    int64_t m = 0x7FFFFFFFFFFFFFFFll;
+    for (int i = 0; i < p.len; ++i) { const int64_t c = counts[pv_at(p, i)]; m = c < m ? c : m; }
+    return m;
+}
+
+// quantify_paths + quantify_clusters for target t.  `dims`, `n_paths`, `first_path` come
+// from graph_target.  All threads of the CTA must call this.
+template <class Ctx>
+KM_HD void emit_rows(const Ctx& ctx, const TableView& T, const WalkView& W, const GraphScratch& S,
+                     const ResultView& R, int t, const GraphDims& d, int n_paths, int first_path, int* sh) {
+    const int k = T.k;
+    const int tid = ctx.tid();
+    const int64_t nbase = W.node_off[t];
+    const uint64_t* kmers = R.out_kmer + nbase;
+    const uint32_t* counts = R.out_count + nbase;  // caps are not stored: rows never touch them
+    double* coef = S.vec + 4 * KM_MAX_COLS;
+    double* rvaf = S.vec + 5 * KM_MAX_COLS;
+    const PathView ref = {nullptr, 0, d.L};
+
+    // ---- cluster discovery by lane 0 (MutationFinder.py:656-694) ---------------
+    // grp[0..n) = cluster id of each path (-1 = none); clusters are numbered in seed order
+    if (tid == 0) {
+        int n_clusters = 0, n_rows = n_paths;
+        for (int p = 0; p < n_paths; ++p) {
+            const PathView alt = {R.pool + R.path_off[first_path + p], 0, R.path_len[first_path + p]};
+            const Diff df = diff_paths(ref, alt, k);
+            S.pdiff[4 * p + 0] = df.start; S.pdiff[4 * p + 1] = df.end_ref;
+            S.pdiff[4 * p + 2] = df.end_var; S.pdiff[4 * p + 3] = df.end_ref_overlap;
+            S.grp[p] = -2;                       // -2 = still in variant_set
+        }
+        // cluster records: grp[n_paths + 4*c ...] = lo, hi, first member (chain), size
+        int32_t* crec = S.grp + KM_MAX_PATHS;    // lo,hi per cluster are recomputed later; keep order only
+        for (int seed = 0; seed < n_paths; ++seed) {
+            if (S.grp[seed] != -2) continue;     // set.pop() on small ints == ascending order
+            int lo = S.pdiff[4 * seed], hi = S.pdiff[4 * seed + 1];
+            const int cid = n_clusters;
+            S.grp[seed] = cid;
+            int size = 1;
+            for (;;) {
+                int hit = -1;
+                for (int v = 0; v < n_paths && hit < 0; ++v) {
+                    if (S.grp[v] != -2) continue;
+                    const int s = S.pdiff[4 * v], e = S.pdiff[4 * v + 1];
+                    if (e >= lo && s <= hi) {
+                        if (lo == hi && hi == s && s == e) continue;                    // terminal ITD (:670-671)
+                        if (hi == e && (lo == hi || s == e)) continue;                  // quasi-terminal (:672-676)
+                        hit = v;
+                    }
+                }
+                if (hit < 0) break;
+                // members keep their join order through a per-cluster sequence number
+                S.grp[hit] = cid | (size << 16);
+                ++size;
+                lo = S.pdiff[4 * hit] < lo ? S.pdiff[4 * hit] : lo;
+                hi = S.pdiff[4 * hit + 1] > hi ? S.pdiff[4 * hit + 1] : hi;
+            }
+            // a lone path equal to the reference forms no cluster (:703-707)
+            bool skip = false;
+            if (size == 1) {
+                const PathView alt = {R.pool + R.path_off[first_path + seed], 0, R.path_len[first_path + seed]};
+                skip = alt.len == d.L;
+                for (int x = 0; skip && x < alt.len; ++x) skip = pv_at(alt, x) == x;
+            }
+            if (skip) { S.grp[seed] = -1; continue; }
+            crec[4 * cid + 0] = lo; crec[4 * cid + 1] = hi; crec[4 * cid + 2] = size; crec[4 * cid + 3] = 0;
+            ++n_clusters;
+            n_rows += size;
+        }
+        int first_row = 0;
+        bool overflow = false;
+        if (n_rows > 0) {
+            first_row = (int)atomic_add64(&R.used[2], (unsigned long long)n_rows);
+            if (first_row + n_rows > R.row_cap) overflow = true;
+        }
+        if (overflow) { atomic_or32(&W.status[t], KM_ST_PATH_OVERFLOW); n_rows = 0; n_clusters = 0; }
+        R.t_n_rows[t] = n_rows;
+        R.t_row_first[t] = first_row;
+        sh[5] = n_clusters;
+        sh[6] = first_row;
+        sh[7] = overflow ? 1 : 0;
+    }
+    ctx.sync();
+    const int n_clusters = sh[5];
+    const int first_row = sh[6];
+    if (sh[7]) return;
+    int32_t* crec = S.grp + KM_MAX_PATHS;
+
+    // ---- vs_ref rows (MutationFinder.py:613-648) -------------------------------
+    PathView cols[KM_MAX_COLS];
+    for (int p = 0; p < n_paths; ++p) {
+        const PathView alt = {R.pool + R.path_off[first_path + p], 0, R.path_len[first_path + p]};
+        cols[0] = alt; cols[1] = ref;
+        const int iters = solve_columns(ctx, S, counts, d.N, cols, 2, coef, rvaf, sh);
+        if (tid == 0) {
+            const Diff df = {S.pdiff[4 * p], S.pdiff[4 * p + 1], S.pdiff[4 * p + 2], S.pdiff[4 * p + 3]};
+            int dl, il;
+            const int type = classify(kmers, ref, alt, df, &dl, &il);
+            bool is_ref = alt.len == d.L;
+            for (int x = 0; is_ref && x < alt.len; ++x) is_ref = pv_at(alt, x) == x;
+            double c0 = coef[0], c1 = coef[1], r0 = rvaf[0], r1 = rvaf[1];
+            if (is_ref) {
+                // adjust_for_reference (PathQuant.py:151-154).  With all-zero coef rVAF aliases
+                // coef, so both turn NaN and the `coef >= 0` overwrite skips them.
+                const bool aliased = (c0 > c1 ? c0 : c1) == 0.0;
+                r0 = r1 = NAN;
+                if (aliased) { c0 = c1 = NAN; }
+                else { if (c0 >= 0.0) c0 = -1.0; if (c1 >= 0.0) c1 = -1.0; }   // min(counts) is the cap's -1
+            }
+            Row& row = R.rows[first_row + p];
+            row.target = t; row.kind = 0; row.type = type;
+            row.name_start = df.start + k; row.name_end = df.end_ref + 1;
+            row.path_id = first_path + p; row.var_begin = 0; row.var_end = alt.len;
+            row.ref_begin = 0; row.ref_end = d.L;
+            row.del_begin = df.start; row.del_len = dl; row.ins_begin = df.start; row.ins_len = il;
+            row.start_off = 0; row.cluster_id = 0; row.cluster_n = 0; row.n_iter = iters;
+            row.min_cov = min_count(counts, alt);
+            row.rvaf = r0; row.expr = c0; row.ref_rvaf = r1; row.ref_expr = c1;
+            if (iters < 0) atomic_or32(&W.status[t], KM_ST_SOLVER_WATCHDOG);
+            if (d.L - (df.end_ref - df.start) + (df.end_var - df.start) != alt.len)
+                atomic_or32(&W.status[t], KM_ST_NAME_MISMATCH);
+        }
+        ctx.sync();
+    }
+
+    // ---- cluster rows (MutationFinder.py:700-723, 758-811) ----------------------
+    int row_cursor = first_row + n_paths;
+    for (int c = 0; c < n_clusters; ++c) {
+        const int lo = crec[4 * c], hi = crec[4 * c + 1], size = crec[4 * c + 2];
+        if (size + 1 > KM_MAX_COLS) {
+            if (tid == 0) atomic_or32(&W.status[t], KM_ST_TOO_MANY_COLS);
+            // rows stay zeroed; the host refuses the target
+            row_cursor += size;
+            continue;
+        }
+        // members in join order
+        int members[KM_MAX_COLS];
+        for (int p = 0; p < n_paths; ++p) {
+            const int gcode = S.grp[p];
+            if (gcode >= 0 && (gcode & 0xFFFF) == c) members[gcode >> 16] = p;
+        }
+        int span = 0;
+        for (int j = 0; j < size; ++j) {
+            const int p = members[j];
+            int a = S.pdiff[4 * p + 2] - S.pdiff[4 * p + 1] + 1;      // abs(end_var - end_ref + 1) (:710-712)
+            a = a < 0 ? -a : a;
+            span = a > span ? a : span;
+        }
+        const int offset = lo - span > 0 ? lo - span : 0;               // (:713)
+        // Python slices clamp to the sequence (:714, :720)
+        const int ref_stop = hi < d.L ? hi : d.L;
+        const PathView ref_clip = {nullptr, offset, ref_stop - offset > 0 ? ref_stop - offset : 0};
+        cols[0] = ref_clip;
+        for (int j = 0; j < size; ++j) {
+            const int p = members[j];
+            const int plen = R.path_len[first_path + p];
+            int stop = S.pdiff[4 * p + 2] + hi - S.pdiff[4 * p + 1];   // (:719)
+            stop = stop < plen ? stop : plen;
+            const int beg = offset < plen ? offset : plen;
+            cols[1 + j].idx = R.pool + R.path_off[first_path + p];
+            cols[1 + j].begin = beg;
+            cols[1 + j].len = stop - beg > 0 ? stop - beg : 0;
+        }
+        const int iters = solve_columns(ctx, S, counts, d.N, cols, size + 1, coef, rvaf, sh);
+        if (tid == 0) {
+            for (int j = 0; j < size; ++j) {
+                const int p = members[j];
+                const PathView clip = cols[1 + j];
+                const Diff df = diff_paths(ref_clip, clip, k);
+                int dl, il;
+                const int type = classify(kmers, ref_clip, clip, df, &dl, &il);
+                Row& row = R.rows[row_cursor + j];
+                row.target = t; row.kind = 1; row.type = type;
+                row.name_start = df.start + k + offset; row.name_end = df.end_ref + 1 + offset;
+                row.path_id = first_path + p; row.var_begin = clip.begin; row.var_end = clip.begin + clip.len;
+                row.ref_begin = ref_clip.begin; row.ref_end = ref_clip.begin + ref_clip.len;
+                row.del_begin = ref_clip.begin + df.start; row.del_len = dl;
+                row.ins_begin = clip.begin + df.start; row.ins_len = il;
+                row.start_off = offset; row.cluster_id = c + 1; row.cluster_n = size; row.n_iter = iters;
+                row.min_cov = min_count(counts, clip);
+                row.rvaf = rvaf[1 + j]; row.expr = coef[1 + j]; row.ref_rvaf = rvaf[0]; row.ref_expr = coef[0];
+                if (ref_clip.len - (df.end_ref - df.start) + (df.end_var - df.start) != clip.len)
+                    atomic_or32(&W.status[t], KM_ST_NAME_MISMATCH);
+            }
+            if (iters < 0) atomic_or32(&W.status[t], KM_ST_SOLVER_WATCHDOG);
+        }
+        ctx.sync();
+        row_cursor += size;
+    }
+}
+
+}  // namespace km

@@ -1,0 +1,121 @@
+// TEST INFRASTRUCTURE ONLY -- single-lane host build of the device stage functions.
+//
+// Compiles km_b200/csrc/{table,walk,graph,quant}.h with g++ (KM_HOST_EMU: tid 0 of 1, barriers
+// no-ops, atomics plain) so the kernel LOGIC can be compared with the oracle on a machine
+// without a GPU (tests/test_emu_pipeline.py).  Never loaded by km_b200/: the product library
+// contains no host copy of these functions and fails with KM_E_NOGPU when there is no device.
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../km_b200/csrc/quant.h"
+#include "../../km_b200/csrc/synth.h"
+
+using namespace km;
+
+struct EmuTable {
+    TableView v;
+    std::vector<Bucket> store;
+};
+
+extern "C" {
+
+void* emu_table_create(int k, int canonical, uint64_t capacity) {
+    EmuTable* t = new EmuTable();
+    uint64_t nb = capacity < 64 ? 64 : capacity;
+    t->store.resize(nb);
+    for (auto& b : t->store) { b.key[0] = b.key[1] = KM_EMPTY_KEY; b.count[0] = b.count[1] = 0; b.pad[0] = b.pad[1] = 0; }
+    t->v.buckets = t->store.data(); t->v.n_buckets = nb; t->v.k = k; t->v.canonical = canonical; t->v.kmask = kmer_mask(k);
+    return t;
+}
+void emu_table_free(void* h) { delete (EmuTable*)h; }
+int emu_table_insert(void* h, const uint64_t* keys, const uint32_t* counts, uint64_t n, int mode) {
+    EmuTable* t = (EmuTable*)h;
+    for (uint64_t i = 0; i < n; ++i) if (table_insert(t->v, keys[i] & t->v.kmask, counts[i], mode) < 0) return -1;
+    return 0;
+}
+int emu_table_synthetic(void* h, uint64_t seed, uint64_t n) {
+    EmuTable* t = (EmuTable*)h;
+    for (uint64_t i = 0; i < n; ++i) { uint64_t key = synth_key(seed, i, t->v.k); if (table_insert(t->v, key, synth_count(key), KM_INSERT_KEEP) < 0) return -1; }
+    return 0;
+}
+uint32_t emu_query(void* h, uint64_t fwd) { return table_query(((EmuTable*)h)->v, fwd); }
+uint64_t emu_revcomp(uint64_t v, int k) { return revcomp(v, k); }
+uint64_t emu_synth_key(uint64_t seed, uint64_t i, int k) { return synth_key(seed, i, k); }
+uint32_t emu_synth_count(uint64_t key) { return synth_count(key); }
+int emu_row_size(void) { return (int)sizeof(Row); }
+
+// One target through walk -> graph -> rows.  Outputs go to caller buffers; returns status bits,
+// or -1 when an output buffer is too small.
+int emu_find_target(void* h, const uint8_t* codes, int len, double ratio, int64_t count, int steps, int branchs, int nodes,
+                    int extra, int32_t* out_n, uint64_t* out_kmer, uint32_t* out_count, int node_cap_out,
+                    int32_t* out_n_paths, int32_t* out_path_len, int32_t* out_pool, int path_cap, int pool_cap,
+                    int32_t* out_n_rows, Row* out_rows, int row_cap, uint64_t* out_lookups) {
+    EmuTable* t = (EmuTable*)h;
+    const int k = t->v.k;
+    const int L = len - k + 1 > 0 ? len - k + 1 : 0;
+    const int cap = L + extra;
+    uint32_t H = 64;
+    while (H < 2u * (uint32_t)cap + 1024u) H <<= 1;
+    int64_t seq_off[2] = {0, len}, node_off[2] = {0, cap}, hash_off[2] = {0, (int64_t)H};
+    std::vector<uint64_t> node_kmer(cap), hkey(H);
+    std::vector<uint32_t> node_count(cap), node_slot(cap), node_kid(4 * (size_t)cap), hval(H), hmeta(H);
+    std::vector<uint8_t> hflag(H);
+    int32_t n_nodes = 0, n_kept = 0;
+    uint32_t status = 0;
+    unsigned long long lookups = 0;
+    WalkView W;
+    W.n_targets = 1; W.codes = codes; W.seq_off = seq_off; W.node_off = node_off; W.hash_off = hash_off;
+    W.node_kmer = node_kmer.data(); W.node_count = node_count.data(); W.node_slot = node_slot.data(); W.node_kid = node_kid.data();
+    W.hkey = hkey.data(); W.hval = hval.data(); W.hmeta = hmeta.data(); W.hflag = hflag.data();
+    W.n_nodes = &n_nodes; W.n_kept = &n_kept; W.status = &status; W.lookups = &lookups;
+    FindParams P; P.ratio = ratio; P.count = count; P.max_stack = steps; P.max_break = branchs; P.max_node = nodes;
+    CtaCtx ctx;
+    walk_target(ctx, t->v, W, P, 0);
+    *out_lookups = lookups;
+    *out_n = 0; *out_n_paths = 0; *out_n_rows = 0;
+    if (status & (KM_ST_BAD_BASE | KM_ST_DUP_KMER | KM_ST_NODE_OVERFLOW | KM_ST_NODE_LIMIT | KM_ST_TOO_SHORT)) return (int)status;
+
+    const size_t maxN = (size_t)cap + 2, nce = 4 * maxN + 2;
+    std::vector<int32_t> newidx(cap), kept(cap), succ(4 * maxN), pred(4 * maxN), before(maxN), after(maxN), cand(maxN), occ(maxN);
+    std::vector<int32_t> ce_a(nce), ce_b(nce), ce_len(nce), upath(KM_MAX_PATHS), pdiff(4 * KM_MAX_PATHS), grp(5 * KM_MAX_PATHS);
+    std::vector<uint64_t> ce_h1(nce), ce_h2(nce);
+    std::vector<float> dist(maxN);
+    std::vector<uint8_t> state(maxN), eflag(maxN), reach(maxN);
+    std::vector<double> G(KM_MAX_COLS * KM_MAX_COLS), V(2 * KM_MAX_COLS * KM_MAX_COLS), vec(8 * KM_MAX_COLS);
+    GraphScratch S;
+    S.newidx = newidx.data(); S.kept = kept.data(); S.succ = succ.data(); S.pred = pred.data(); S.dist = dist.data();
+    S.before = before.data(); S.after = after.data(); S.cand = cand.data(); S.state = state.data(); S.eflag = eflag.data();
+    S.reach = reach.data(); S.occ = occ.data(); S.ce_a = ce_a.data(); S.ce_b = ce_b.data(); S.ce_len = ce_len.data();
+    S.ce_h1 = ce_h1.data(); S.ce_h2 = ce_h2.data(); S.upath = upath.data(); S.pdiff = pdiff.data(); S.grp = grp.data();
+    S.G = G.data(); S.V = V.data(); S.vec = vec.data(); S.maxN = (int)maxN;
+
+    std::vector<uint64_t> okmer(cap);
+    std::vector<uint32_t> ocount(cap);
+    std::vector<int64_t> path_off(path_cap);
+    int32_t t_n = 0, t_np = 0, t_pf = 0, t_nr = 0, t_rf = 0;
+    unsigned long long used[4] = {0, 0, 0, 0};
+    ResultView R;
+    R.t_n = &t_n; R.t_n_paths = &t_np; R.t_path_first = &t_pf; R.t_n_rows = &t_nr; R.t_row_first = &t_rf;
+    R.out_kmer = okmer.data(); R.out_count = ocount.data();
+    R.path_off = path_off.data(); R.path_len = out_path_len; R.pool = out_pool; R.path_cap = path_cap; R.pool_cap = pool_cap;
+    R.rows = out_rows; R.row_cap = row_cap; R.used = used;
+    int sh[8] = {0};
+    GraphDims d;
+    graph_target(ctx, t->v, W, S, R, 0, &d, sh);
+    emit_rows(ctx, t->v, W, S, R, 0, d, sh[2], sh[3], sh);
+    if (t_n - 2 > node_cap_out) return -1;
+    *out_n = t_n;
+    memcpy(out_kmer, okmer.data(), sizeof(uint64_t) * (size_t)(t_n - 2));
+    memcpy(out_count, ocount.data(), sizeof(uint32_t) * (size_t)(t_n - 2));
+    *out_n_paths = t_np;
+    *out_n_rows = t_nr;
+    // paths were bump-allocated from offset 0 in order of materialisation, then re-ordered: hand
+    // the offsets back through the first ints of a side channel -> compact them here instead
+    std::vector<int32_t> compact;
+    for (int p = 0; p < t_np; ++p) compact.insert(compact.end(), out_pool + path_off[p], out_pool + path_off[p] + out_path_len[p]);
+    memcpy(out_pool, compact.data(), sizeof(int32_t) * compact.size());
+    return (int)status;
+}
+
+}  // extern "C"

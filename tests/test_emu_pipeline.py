@@ -1,0 +1,125 @@
+"""Kernel LOGIC vs the reference, on the CPU: the device stage functions of
+km_b200/csrc/{table,walk,graph,quant}.h compiled single-lane by g++ (tests/emu/km_emu.cpp) are
+run on the bundled samples and the synthetic panel and compared with the golden records of the
+UNMODIFIED reference.  What this cannot show -- races, launch geometry, memory placement -- is
+covered by the -m gpu tests, which call the CUDA build through the C ABI."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import jf_format, km_oracle as ko
+from oracle.compare import compare_rows
+from oracle.store import KmerStore, lib as olib
+
+from emu_harness import EmuTable, lib as elib
+from helpers import record_of
+
+
+def _check(rec, got, tag):
+    assert got["nodes"] == rec["nodes"], tag
+    assert got["alt_sequences"] == rec["alt_sequences"], tag
+    errs, flips = compare_rows(rec["rows"], got["rows"], rec["raw"], got["raw"])
+    assert not errs, (tag, errs)
+    return flips
+
+
+def test_kmer_primitives_match_oracle():
+    rng = np.random.default_rng(3)
+    E, O = elib(), olib()
+    for v in rng.integers(0, 1 << 62, size=500, dtype=np.uint64).tolist():
+        assert E.emu_revcomp(v, 31) == O.ks_revcomp(v, 31)
+    for k in (5, 17, 31):
+        for v in rng.integers(0, 1 << (2 * k), size=50, dtype=np.uint64).tolist():
+            assert E.emu_revcomp(v, k) == jf_format.revcomp_packed(v, k)
+    for i in range(0, 5000, 37):
+        key = E.emu_synth_key(20240001, i, 31)
+        assert key == O.ks_synth_key(20240001, i, 31)
+        assert E.emu_synth_count(key) == O.ks_synth_count(key)
+
+
+def test_table_lookup_matches_store(bundled):
+    for name in ("02H025_NPM1", "03H116_ITD"):
+        _, keys, counts = jf_format.read_jf(os.path.join(bundled, "data/jf/%s.jf" % name))
+        t = EmuTable.from_keys(keys, counts.astype(np.uint32))
+        s = KmerStore.from_jf(os.path.join(bundled, "data/jf/%s.jf" % name))
+        rng = np.random.default_rng(1)
+        probes = np.concatenate([keys[:300], rng.integers(0, 1 << 62, size=300, dtype=np.uint64)])
+        for v in probes.tolist():
+            assert t.query_packed(v) == s.query_packed(v)
+            rc = jf_format.revcomp_packed(v, 31)
+            assert t.query_packed(rc) == s.query_packed(rc)
+
+
+def test_crowded_table_still_exact():
+    # load factor ~0.97 of the slots: long bucket chains, every key must still be found
+    rng = np.random.default_rng(9)
+    keys = np.unique(rng.integers(0, 1 << 62, size=3900, dtype=np.uint64))
+    keys = np.minimum(keys, np.array([jf_format.revcomp_packed(int(v), 31) for v in keys], dtype=np.uint64))
+    keys = np.unique(keys)
+    counts = rng.integers(1, 1 << 20, size=len(keys)).astype(np.uint32)
+    t = EmuTable(31, True, capacity=2000)        # 2000 buckets = 4000 slots
+    t.insert(keys, counts)
+    for kk, c in zip(keys.tolist(), counts.tolist()):
+        assert t.query_packed(kk) == c
+    for v in rng.integers(0, 1 << 62, size=500, dtype=np.uint64).tolist():
+        if v not in set(keys.tolist()) and jf_format.revcomp_packed(v, 31) not in set(keys.tolist()):
+            assert t.query_packed(v) == 0
+            break
+
+
+def test_bundled_pairs_match_reference(bundled, bundled_golden):
+    tables = {}
+    flips = 0
+    for rec in bundled_golden:
+        if rec["catalog"] != "GRCh38":
+            continue
+        s = rec["sample"]
+        if s not in tables:
+            _, keys, counts = jf_format.read_jf(os.path.join(bundled, "data/jf/%s.jf" % s))
+            tables[s] = EmuTable.from_keys(keys, counts.astype(np.uint32))
+        seqs, _ = ko.read_fasta_records(os.path.join(bundled, "data/catalog", rec["catalog"], rec["target"] + ".fa"))
+        res = tables[s].find_batch(["".join(seqs)])
+        assert int(res.status[0]) & ~16 == 0
+        got = record_of(res, 0, "./data/jf/%s.jf" % s, rec["target"])
+        flips += _check(rec, got, (rec["target"], s))
+    assert flips <= 2
+
+
+def test_synthetic_panel_matches_reference(synth_small):
+    t = EmuTable.from_keys(synth_small["keys"], synth_small["counts"])
+    res = t.find_batch(synth_small["targets"])
+    flips = 0
+    for i, rec in enumerate(synth_small["records"]):
+        assert int(res.status[i]) == 0
+        got = record_of(res, i, "synth_small.jf", rec["target"])
+        flips += _check(rec, got, rec["target"])
+    assert flips <= 4
+
+
+def test_lookup_accounting_matches_survey_formula(synth_small):
+    # algorithmic lookups per target = n_ref_kmers + 4 * n_nodes; the walk may
+    # issue more (dead-end tips) but never fewer
+    t = EmuTable.from_keys(synth_small["keys"], synth_small["counts"])
+    res = t.find_batch(synth_small["targets"][:20])
+    for i in range(20):
+        n_ref = len(synth_small["targets"][i]) - 30
+        algorithmic = n_ref + 4 * (int(res.n_nodes[i]) - 2)
+        assert int(res.lookups[i]) >= algorithmic
+
+
+def test_degenerate_targets():
+    t = EmuTable(31, True, 1024)
+    rng = np.random.default_rng(2)
+    seq = "".join("ACGT"[i] for i in rng.integers(0, 4, size=80))
+    res = t.find_batch([seq, "A" * 40, seq[:31], seq[:20], seq[:40] + "N" + seq[41:]])
+    # empty table: one Reference row with nan / nan / 0
+    assert int(res.status[0]) == 0
+    rec = record_of(res, 0, "empty.jf", "x")
+    assert len(rec["rows"]) == 1
+    cells = rec["rows"][0].split("\t")
+    assert cells[2] == "Reference" and cells[4:7] == ["nan", "nan", "0"] and cells[9] == "nan"
+    assert int(res.status[1]) & 2          # repeated k-mer -> ValueError on the host
+    assert int(res.status[2]) == 0 and int(res.n_nodes[2]) == 3      # a single k-mer target
+    assert int(res.status[3]) & 64         # shorter than k
+    assert int(res.status[4]) & 1          # non-ACGT letter

@@ -1,0 +1,218 @@
+"""Parity tests proper: the CUDA build, called through the C ABI (ctypes -> libkm_b200.so), against
+the oracle and the golden records of the unmodified reference.  Run with -m gpu on a B200."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import jf_format, km_oracle as ko
+from oracle.compare import compare_rows
+from oracle.store import KmerStore
+
+from helpers import record_of
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine():
+    import __graft_entry__ as ge
+    ge.build()
+    from km_b200 import engine as e
+    from km_b200._lib import lib
+    assert lib().km_device_count() > 0, "these tests need a CUDA device"
+    return e
+
+
+def _check(rec, got, tag):
+    assert got["nodes"] == rec["nodes"], tag
+    assert got["alt_sequences"] == rec["alt_sequences"], tag
+    errs, flips = compare_rows(rec["rows"], got["rows"], rec["raw"], got["raw"])
+    assert not errs, (tag, errs)
+    return flips
+
+
+def test_jf_load_and_query_match_store(engine, bundled):
+    rng = np.random.default_rng(1)
+    for name in ("02H025_NPM1", "02H033_DNMT3A_sub", "03H112_IandI", "03H116_ITD", "05H094_FLT3-TKD_del"):
+        path = os.path.join(bundled, "data/jf/%s.jf" % name)
+        t = engine.Table.open_jf(path)
+        s = KmerStore.from_jf(path)
+        _, keys, counts = jf_format.read_jf(path)
+        assert t.info()["n_keys"] == len(keys) and t.k == 31 and t.canonical
+        probes = np.concatenate([keys, np.array([jf_format.revcomp_packed(int(v), 31) for v in keys[:500]], dtype=np.uint64),
+                                 rng.integers(0, 1 << 62, size=5000, dtype=np.uint64)])
+        got = t.query_packed(probes)
+        assert (got == s.query_batch(probes)).all()
+        assert (got[:len(keys)] == counts.astype(np.uint32)).all()
+        t.close()
+
+
+def test_min_cov_known_answers(engine, bundled):
+    # km/tests/test_main.py:581-652
+    from km_b200.utils import common as uc
+    seq = "".join(uc.file_2_seq(os.path.join(bundled, "data/catalog/GRCh38/FLT3-ITD_exons_13-15.fa"))[0])
+    res = uc.get_cov(os.path.join(bundled, "data/jf/03H112_IandI.jf"), seq)
+    assert res[0] == 275596 and res[2] == 618 and res[3] == 1368 and "%.2f" % res[4] == "874.91"
+    assert res[5] == 315 and res[6] == 0
+    res = uc.get_cov(os.path.join(bundled, "data/jf/02H025_NPM1.jf"), seq)
+    assert res[0] == 0 and res[6] == 315
+
+
+def test_get_child_matches_oracle(engine, bundled):
+    from km_b200.utils.Jellyfish import Jellyfish
+    path = os.path.join(bundled, "data/jf/03H116_ITD.jf")
+    jf = Jellyfish(path, cutoff=0.05, n_cutoff=5)
+    oj = ko.OracleJellyfish(KmerStore.from_jf(path), path, 0.05, 5)
+    seq = "".join(ko.read_fasta_records(os.path.join(bundled, "data/catalog/GRCh38/FLT3-ITD_exons_13-15.fa"))[0])
+    kmers = [seq[i:i + 31] for i in range(len(seq) - 30)]
+    for fwd in (True, False):
+        got = jf.get_child_many(kmers, forward=fwd)
+        for km, g in zip(kmers, got):
+            assert g == oj.get_child(km, forward=fwd)
+    assert jf.query(kmers[0]) == oj.query(kmers[0])
+    assert jf.get_child(kmers[3]) == oj.get_child(kmers[3])
+    # class defaults are 0.30 / 500 (Jellyfish.py:23), not the CLI's
+    assert Jellyfish(path).cutoff == 0.30 and Jellyfish(path).n_cutoff == 500
+
+
+def test_bundled_catalog_matches_reference_records(engine, bundled, bundled_golden):
+    """configs 1-3: every bundled target x sample; the whole catalog goes down in ONE batch."""
+    flips = 0
+    for cat in ("GRCh38", "GRCh37"):
+        for sample in sorted({r["sample"] for r in bundled_golden}):
+            recs = [r for r in bundled_golden if r["catalog"] == cat and r["sample"] == sample]
+            t = engine.Table.open_jf(os.path.join(bundled, "data/jf/%s.jf" % sample))
+            seqs = ["".join(ko.read_fasta_records(os.path.join(bundled, "data/catalog", cat, r["target"] + ".fa"))[0])
+                    for r in recs]
+            res = t.find_batch(seqs)
+            assert res.timing["launches"] == 2
+            for i, rec in enumerate(recs):
+                assert int(res.status[i]) & ~16 == 0
+                db = "./data/jf/%s.jf" % sample
+                got = record_of(res, i, db, rec["target"])
+                flips += _check(rec, got, (cat, rec["target"], sample))
+                # the library's own formatter prints the same sorted rows
+                assert res.format_target(i, db, rec["target"]) == "".join(r + "\n" for r in got["rows"])
+            t.close()
+    assert flips <= 4
+
+
+def test_synthetic_panel_matches_reference_records(engine, synth_small):
+    t = engine.Table.create(capacity=len(synth_small["keys"]))
+    t.insert(synth_small["keys"], synth_small["counts"])
+    res = t.find_batch(synth_small["targets"])
+    flips = 0
+    for i, rec in enumerate(synth_small["records"]):
+        assert int(res.status[i]) == 0
+        got = record_of(res, i, "synth_small.jf", rec["target"])
+        flips += _check(rec, got, rec["target"])
+        assert res.format_target(i, "synth_small.jf", rec["target"]) == "".join(r + "\n" for r in got["rows"])
+    assert flips <= 4
+    # repeatability: a second run gives byte-identical text
+    res2 = t.find_batch(synth_small["targets"])
+    for i, rec in enumerate(synth_small["records"]):
+        assert res.format_target(i, "x", rec["target"]) == res2.format_target(i, "x", rec["target"])
+
+
+def test_synthetic_background_equals_analytic_oracle(engine):
+    from km_b200 import synth
+    n = 3_000_000
+    t = engine.Table.create(capacity=n)
+    t.build_synthetic(synth.TABLE_SEED, n)
+    s = KmerStore(31, True)
+    s.set_background(synth.TABLE_SEED, n)
+    assert abs(t.info()["n_keys"] - n) < 10          # collisions among 3e6 draws from 2^61 are ~0
+    q = synth.lookup_queries(1 << 20, synth.TABLE_SEED, n)
+    got = t.query_packed(q)
+    assert (got == s.query_batch(q)).all()
+    assert 0.45 < (got > 0).mean() < 0.55
+    # a crowded table (load ~0.9 of the slots) must still answer exactly
+    t2 = engine.Table.create(capacity=n // 2 + n // 20)
+    t2.build_synthetic(synth.TABLE_SEED, n)
+    assert (t2.query_packed(q) == got).all()
+
+
+def test_panel_against_oracle_with_full_background(engine):
+    """config 4 in miniature: planted panel + pseudo-random background; the oracle decides
+    background membership analytically, so the same comparison works at 2e9 keys (bench.py)."""
+    from km_b200 import synth
+    n_bg = 2_000_000
+    panel = synth.make_panel(300, seed=77, two_variant_frac=0.2)
+    t = engine.Table.create(capacity=n_bg + len(panel.keys))
+    t.build_synthetic(synth.TABLE_SEED, n_bg)
+    t.insert(panel.keys, panel.counts, mode="overwrite")
+    res = t.find_batch(panel.targets)
+    store = KmerStore(31, True, len(panel.keys))
+    store.set_background(synth.TABLE_SEED, n_bg)
+    store.insert(panel.keys, panel.counts)
+    jf = ko.OracleJellyfish(store, "panel.jf", 0.05, 5)
+    flips = 0
+    for i in range(0, 300, 3):
+        f = ko.OracleFinder(ko.Target(panel.targets[i], panel.names[i], 31), jf).run()
+        want = f.get_paths()
+        got = record_of(res, i, "panel.jf", panel.names[i])
+        errs, fl = compare_rows([str(r) for r in want], got["rows"],
+                                [[float(r.rvaf), float(r.expr), float(r.ref_expr)] for r in want], got["raw"])
+        assert not errs, (panel.names[i], errs)
+        assert got["nodes"] == sorted([k, int(v)] for k, v in f.node_data.items())
+        assert int(res.lookups[i]) >= ko.algorithmic_lookups(f)
+        flips += fl
+    assert flips <= 4
+
+
+def test_error_statuses_and_limits(engine):
+    from km_b200.utils.Jellyfish import Jellyfish
+    from km_b200.utils import MutationFinder as umf
+    from km_b200.utils import Sequence as us
+    rng = np.random.default_rng(4)
+    seq = "".join("ACGT"[i] for i in rng.integers(0, 4, size=120))
+    t = engine.Table.create(capacity=4096)
+    res = t.find_batch([seq, "A" * 40, seq[:20], seq[:40] + "N" + seq[41:], seq[:31]])
+    assert [int(s) for s in res.status] == [0, 2, 64, 1, 0]
+    rec = record_of(res, 0, "e.jf", "x")
+    cells = rec["rows"][0].split("\t")
+    assert len(rec["rows"]) == 1 and cells[2] == "Reference" and cells[4:7] == ["nan", "nan", "0"]
+    # non-linear target raises ValueError on the host, like the reference (test_not_linear)
+    with pytest.raises(ValueError):
+        us.RefSeq("A" * 32, "polyA", 31)
+    # node limit -> sys.exit with the reference's message (MutationFinder.py:143-148)
+    keys = np.array([min(jf_format.pack(seq[i:i + 31]), jf_format.revcomp_packed(jf_format.pack(seq[i:i + 31]), 31))
+                     for i in range(90)], dtype=np.uint64)
+    t.insert(keys, np.full(90, 100, np.uint32))
+    jf = Jellyfish("e.jf", cutoff=0.05, n_cutoff=5, table=t)
+    with pytest.raises(SystemExit) as ex:
+        umf.MutationFinder(us.RefSeq(seq[:60], "lim", 31), jf, 500, 10, 20)
+    assert "Node query count limit exceeded: max=20" in str(ex.value)
+    # the walk beyond the target's end is explored and dropped (dead-end tip)
+    f = umf.MutationFinder(us.RefSeq(seq[:60], "tip", 31), jf)
+    assert f.num_k == 30 + 2
+
+
+def test_mutation_finder_api_reads_like_the_reference(engine, bundled):
+    """Mirrors km/tests/test_main.py:36-71 (test_NPM1) on the drop-in classes."""
+    from km_b200.utils.Jellyfish import Jellyfish
+    from km_b200.utils import MutationFinder as umf
+    from km_b200.utils import Sequence as us
+    from km_b200.utils import common as uc
+    cwd = os.getcwd()
+    os.chdir(bundled)
+    try:
+        jf = Jellyfish("./data/jf/02H025_NPM1.jf", cutoff=0.05, n_cutoff=5)
+        seqs, _ = uc.file_2_seq("./data/catalog/GRCh38/NPM1_4ins_exons_10-11utr.fa")
+        refpath = us.RefSeq("".join(seqs), "NPM1_4ins_exons_10-11utr", jf.k)
+        finder = umf.MutationFinder(refpath, jf, 500, 10, 10000)
+        finder.graph_analysis()
+        finder.quantify_paths(False)
+        finder.quantify_clusters(False)
+        rows = [str(p).split("\t") for p in finder.get_paths(sort=True)]
+    finally:
+        os.chdir(cwd)
+    assert finder.num_k == 82 and len(finder.alt_paths) == 2
+    clus = rows[-1]
+    assert clus[2] == "Insertion" and clus[3] == "45:/TCTG:45"
+    assert clus[8] == "CGGATGACTGACCAAGAGGCTATTCAAGATCTCTGTCTGGCAGTGGAGGAAGTCTCTTTAAGAAAATAG"
+    vs = [r for r in rows if r[11] == "vs_ref" and r[2] != "Reference"][0]
+    assert (vs[4], vs[5], vs[9], vs[6]) == ("0.484", "2870.6", "3055.2", "2428")
+    ref = [r for r in rows if r[2] == "Reference"][0]
+    assert ref[3] == "" and ref[4] == "nan" and ref[5] == "-1.0" and ref[6] == "2379"
