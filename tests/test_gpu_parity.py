@@ -216,3 +216,45 @@ def test_mutation_finder_api_reads_like_the_reference(engine, bundled):
     assert (vs[4], vs[5], vs[9], vs[6]) == ("0.484", "2870.6", "3055.2", "2428")
     ref = [r for r in rows if r[2] == "Reference"][0]
     assert ref[3] == "" and ref[4] == "nan" and ref[5] == "-1.0" and ref[6] == "2379"
+
+
+def test_cli_find_mutation_and_report_equal_reference_text(engine, bundled, bundled_cli_golden):
+    """configs 1-2 through the CLI entry points: `km find_mutation ... | km find_report ...` must
+    print what the reference prints (volatile '#func:' / '#Elapsed time:' lines excluded, as in
+    SURVEY.md section 0), modulo printed-digit boundary flips."""
+    import io
+    import sys
+    from argparse import Namespace
+    from km_b200.tools import find_mutation as fm
+    from km_b200.tools import find_report as fr
+    cwd = os.getcwd()
+    os.chdir(bundled)
+    try:
+        for case in bundled_cli_golden:
+            target = "./data/catalog/GRCh38/%s.fa" % case["target"]
+            args = Namespace(count=5, graphical=False, jellyfish_fn="./data/jf/%s.jf" % case["sample"], ratio=0.05,
+                             steps=500, branchs=10, nodes=10000, target_fn=[target], verbose=False, debug=False)
+            old = sys.stdout
+            sys.stdout = buf = io.StringIO()
+            try:
+                fm.main_find_mut(args, None)
+            finally:
+                sys.stdout = old
+            mine = [l for l in buf.getvalue().split("\n") if not l.startswith("#Elapsed time:")]
+            want = case["find_mutation"].split("\n")
+            assert [l for l in mine if l.startswith("#")] == [l for l in want if l.startswith("#")]
+            body_m = [l for l in mine if l and not l.startswith("#")]
+            body_w = [l for l in want if l and not l.startswith("#")]
+            assert body_m[0] == body_w[0]
+            errs, flips = compare_rows(body_w[1:], body_m[1:])
+            assert not errs and flips == 0, (case["target"], errs)
+            assert body_m == body_w          # order and every printed digit
+            a = Namespace(target=target, infile=io.StringIO(buf.getvalue()), info="vs_ref", min_cov=1, exclu="", format=None)
+            sys.stdout = rep = io.StringIO()
+            try:
+                fr.main_find_report(a, None)
+            finally:
+                sys.stdout = old
+            assert rep.getvalue() == case["report"]["stdout"]
+    finally:
+        os.chdir(cwd)
