@@ -89,7 +89,10 @@ typedef struct km_find_params {
     int32_t nodes;       /* -n, default 10000 (max_node) */
     int32_t extra_nodes; /* initial per-target capacity for explored novel nodes; 0 = default.
                             Targets that overflow are re-run with 8x until `nodes`-bounded */
+    int32_t flags;       /* KM_FIND_* */
+    int32_t reserved;
 } km_find_params;
+#define KM_FIND_NO_GRAPH 1   /* do not copy node arrays / index paths back (rows and text only) */
 
 /* per-target status bits */
 #define KM_ST_BAD_BASE 1
@@ -127,6 +130,19 @@ typedef struct km_row {
 int km_find_batch(km_table* t, const char* seqs_host, const int64_t* offsets_host, int32_t n_targets,
                   const km_find_params* params, km_result** out);
 
+/* The same pipeline in three steps, for callers that keep a batch resident in HBM and launch it
+ * repeatedly (bench.py): create = size + upload inputs, launch = the two kernels on a stream
+ * (asynchronous, NULL = the table's stream), fetch = synchronise + copy results back (re-running
+ * with larger capacities if any target overflowed). */
+typedef struct km_plan km_plan;
+int km_find_plan_create(km_table* t, const char* seqs_host, const int64_t* offsets_host, int32_t n_targets,
+                        const km_find_params* params, km_plan** out);
+int km_find_plan_launch(km_plan* p, void* cuda_stream);
+/* device time of the most recent launch: memsets + walk kernel, and graph kernel (CUDA events) */
+int km_find_plan_last_ms(km_plan* p, float* walk_ms, float* graph_ms);
+int km_find_plan_fetch(km_plan* p, int want_graph, km_result** out);
+void km_find_plan_free(km_plan* p);
+
 /* flat views into a result (valid until km_result_free) */
 typedef struct km_result_view {
     int32_t n_targets;
@@ -151,6 +167,9 @@ typedef struct km_result_view {
     float ms_h2d, ms_walk, ms_graph, ms_d2h, ms_total;
     int32_t n_launches;            /* kernels launched for this result */
     int32_t n_retries;
+    int32_t has_graph;             /* 0: node_kmer/node_count/path_pool were not copied back */
+    int32_t reserved;
+    uint64_t bytes_h2d, bytes_d2h; /* bytes copied host->device / device->host for this result */
 } km_result_view;
 int km_result_get(const km_result* r, km_result_view* view);
 void km_result_free(km_result* r);
@@ -160,6 +179,10 @@ void km_result_free(km_result* r);
  * of bytes written (excluding the NUL), or the required size if buf is too small. */
 int64_t km_result_format_target(const km_result* r, int32_t target, const char* db_name, const char* query_name,
                                 char* buf, int64_t buf_len);
+/* All targets in order, names_host = query names concatenated, name_off[n_targets+1].  Formats
+ * on `threads` host threads (0 = hardware concurrency). */
+int64_t km_result_format_all(const km_result* r, const char* db_name, const char* names_host, const int64_t* name_off,
+                             int32_t threads, char* buf, int64_t buf_len);
 
 /* ---- measurement helpers (bench.py) --------------------------------------------------- */
 /* random 32-byte-sector gather over `bytes` of HBM: the ceiling for hash probes */

@@ -25,7 +25,7 @@ class TableInfo(ctypes.Structure):
 
 class FindParams(ctypes.Structure):
     _fields_ = [("ratio", cd), ("count", i64), ("steps", i32), ("branchs", i32), ("nodes", i32),
-                ("extra_nodes", i32)]
+                ("extra_nodes", i32), ("flags", i32), ("reserved", i32)]
 
 
 ROW_DTYPE = np.dtype([
@@ -43,7 +43,8 @@ class ResultView(ctypes.Structure):
                 ("path_first", vp), ("path_count", vp), ("path_off", vp), ("path_len", vp), ("path_pool", vp),
                 ("row_first", vp), ("row_count", vp), ("rows", vp), ("lookups", vp),
                 ("ms_h2d", cf), ("ms_walk", cf), ("ms_graph", cf), ("ms_d2h", cf), ("ms_total", cf),
-                ("n_launches", i32), ("n_retries", i32)]
+                ("n_launches", i32), ("n_retries", i32), ("has_graph", i32), ("reserved", i32),
+                ("bytes_h2d", u64), ("bytes_d2h", u64)]
 
 
 _LIB = None
@@ -82,12 +83,21 @@ def lib():
     L.km_result_free.restype = None
     L.km_result_format_target.argtypes = [vp, i32, cp, cp, vp, i64]
     L.km_result_format_target.restype = i64
+    L.km_result_format_all.argtypes = [vp, cp, cp, vp, i32, vp, i64]
+    L.km_result_format_all.restype = i64
+    L.km_find_plan_create.argtypes = [vp, cp, vp, i32, P(FindParams), P(vp)]
+    L.km_find_plan_launch.argtypes = [vp, vp]
+    L.km_find_plan_fetch.argtypes = [vp, ci, P(vp)]
+    L.km_find_plan_last_ms.argtypes = [vp, P(cf), P(cf)]
+    L.km_find_plan_free.argtypes = [vp]
+    L.km_find_plan_free.restype = None
     L.km_bench_random_gather.argtypes = [ci, u64, u64, ci, P(cf)]
     L.km_bench_lookup.argtypes = [vp, u64, u64, u64, u64, ci, P(cf), P(cf), P(u64)]
     for name in ("km_table_open_jf", "km_table_create", "km_table_insert", "km_table_build_synthetic",
                  "km_table_count_reads", "km_table_drop_below", "km_table_get_info", "km_query_batch",
                  "km_query_batch_device", "km_query_ascii", "km_get_child_batch", "km_find_batch",
-                 "km_result_get", "km_bench_random_gather", "km_bench_lookup"):
+                 "km_result_get", "km_bench_random_gather", "km_bench_lookup", "km_find_plan_create",
+                 "km_find_plan_launch", "km_find_plan_fetch", "km_find_plan_last_ms"):
         getattr(L, name).restype = ci
     _LIB = L
     return L
@@ -101,5 +111,6 @@ def check(rc):
 EXPORTS = ["km_last_error", "km_device_count", "km_version", "km_table_open_jf", "km_table_create",
            "km_table_insert", "km_table_build_synthetic", "km_table_count_reads", "km_table_drop_below",
            "km_table_get_info", "km_table_close", "km_query_batch", "km_query_batch_device", "km_query_ascii",
-           "km_get_child_batch", "km_find_batch", "km_result_get", "km_result_free", "km_result_format_target",
+           "km_get_child_batch", "km_find_batch", "km_result_get", "km_result_free", "km_result_format_target", "km_result_format_all",
+           "km_find_plan_create", "km_find_plan_launch", "km_find_plan_fetch", "km_find_plan_free", "km_find_plan_last_ms",
            "km_bench_random_gather", "km_bench_lookup"]

@@ -29,6 +29,14 @@ struct CtaCtx {
     KM_HD void sync() const { __syncthreads(); }
     KM_HD int sync_or(int p) const { return __syncthreads_or(p); }
 };
+// One warp works on one target (the walk: most of its life a target has one or two live lanes, so
+// a warp per target keeps 4x more targets in flight per SM than a CTA per target).
+struct WarpCtx {
+    KM_HD int tid() const { return threadIdx.x & 31; }
+    KM_HD int nt() const { return 32; }
+    KM_HD void sync() const { __syncwarp(); }
+    KM_HD int sync_or(int p) const { return __any_sync(0xFFFFFFFFu, p); }
+};
 KM_HD uint64_t atomic_cas64(uint64_t* p, uint64_t cmp, uint64_t val) {
     return atomicCAS(reinterpret_cast<unsigned long long*>(p), (unsigned long long)cmp, (unsigned long long)val);
 }
@@ -51,6 +59,7 @@ struct CtaCtx {
     void sync() const {}
     int sync_or(int p) const { return p; }
 };
+typedef CtaCtx WarpCtx;
 KM_HD uint64_t atomic_cas64(uint64_t* p, uint64_t cmp, uint64_t val) { uint64_t o = *p; if (o == cmp) *p = val; return o; }
 KM_HD uint32_t atomic_add32(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
 KM_HD int32_t atomic_addi32(int32_t* p, int32_t v) { int32_t o = *p; *p = o + v; return o; }

@@ -18,8 +18,19 @@
 
 namespace km {
 
-#define KM_MAX_PATHS 1024       // unique alternative paths per target this build handles
+// capacities of the general (HBM-scratch) pass; the shared-memory pass uses smaller ones and
+// hands a target over to the general pass when it exceeds them
+#define KM_MAX_PATHS 1024       // unique alternative paths per target
 #define KM_MAX_COLS 64          // columns of one least-squares problem (1 + cluster size)
+#define KM_ST_RETRY_LARGE 0x40000000u   // internal: redo this target in the general pass
+
+// a (possibly clipped) path: idx == nullptr means the reference path, whose node at
+// position p is simply p
+struct PathView {
+    const int32_t* idx;
+    int begin;
+    int len;
+};
 
 // One output row (PathQuant.Path, km/utils/PathQuant.py:10-49) in numeric form; the host
 // spells the strings from the node k-mers.  Mirrored by km_row in include/km_b200.h.
@@ -82,13 +93,19 @@ struct GraphScratch {
     int32_t* ce_len;
     uint64_t* ce_h1;
     uint64_t* ce_h2;
-    int32_t* upath;    // [KM_MAX_PATHS] candidate index of each unique path
-    int32_t* pdiff;    // [4*KM_MAX_PATHS] start, end_ref, end_var, end_ref_overlap
-    int32_t* grp;      // [5*KM_MAX_PATHS] cluster bookkeeping
-    double* G;         // [KM_MAX_COLS*KM_MAX_COLS]
-    double* V;         // [2*KM_MAX_COLS*KM_MAX_COLS]
-    double* vec;       // [8*KM_MAX_COLS]
+    int32_t* upath;    // [max_paths] candidate index of each unique path
+    int32_t* pdiff;    // [4*max_paths] start, end_ref, end_var, end_ref_overlap
+    int32_t* grp;      // [5*max_paths] cluster bookkeeping
+    double* G;         // [max_cols*max_cols]
+    double* V;         // [2*max_cols*max_cols]
+    double* vec;       // [8*max_cols]
+    PathView* cols;    // [max_cols] columns of the current least-squares problem
+    int32_t* members;  // [max_cols]
     int maxN;
+    int max_cand;      // capacity of the ce_* arrays
+    int max_paths;
+    int max_cols;
+    int retry;         // 1: exceeding a capacity defers the target to the general pass
 };
 
 #define KM_REF_W 0.01f
@@ -173,11 +190,12 @@ KM_HD void hash_step(uint64_t& h1, uint64_t& h2, int pos, int v) {
     h2 += mix64((x + 0x13198A2E03707344ull) * 0xD1342543DE82EF95ull);
 }
 
-// Builds the graph of target t and emits its unique alternative paths (caps stripped).
-// Returns the number of unique paths through *n_unique; paths are written to the result
-// pool in lexicographic order.  All threads of the CTA must call this.
+// Builds the graph of target t and emits its unique alternative paths (caps stripped), written
+// to the result pool in lexicographic order; sh[2] = their number, sh[3] = the first path id.
+// Returns false (uniformly) when a scratch capacity was exceeded and the target was deferred.
+// All threads of the CTA must call this.
 template <class Ctx>
-KM_HD void graph_target(const Ctx& ctx, const TableView& T, const WalkView& W, const GraphScratch& S,
+KM_HD bool graph_target(const Ctx& ctx, const TableView& T, const WalkView& W, const GraphScratch& S,
                         const ResultView& R, int t, GraphDims* dims_out, int* sh /* 8 ints of CTA-shared memory */) {
     const int k = T.k;
     const TargetGeom g = target_geom(W, t, k);
@@ -269,12 +287,17 @@ KM_HD void graph_target(const Ctx& ctx, const TableView& T, const WalkView& W, c
             if (!(S.eflag[a] & (1u << slot))) return;
             if (!(S.reach[b] & 2)) return;
             const int pos = atomic_addi32(&sh[1], 1);
-            S.ce_a[pos] = a;
-            S.ce_b[pos] = b;
+            if (pos < S.max_cand) { S.ce_a[pos] = a; S.ce_b[pos] = b; }
         });
     }
     ctx.sync();
     const int n_cand = sh[1];
+    if (n_cand > S.max_cand) {
+        if (tid == 0) atomic_or32(&W.status[t], S.retry ? KM_ST_RETRY_LARGE : (uint32_t)KM_ST_PATH_OVERFLOW);
+        if (tid == 0) { R.t_n_paths[t] = 0; R.t_path_first[t] = 0; R.t_n_rows[t] = 0; R.t_row_first[t] = 0; }
+        ctx.sync();
+        return false;
+    }
     // order candidates deterministically by (a, b) -- rank sort, n_cand is small
     for (int c = tid; c < n_cand; c += nt) {
         const int a = S.ce_a[c], b = S.ce_b[c];
@@ -316,7 +339,7 @@ KM_HD void graph_target(const Ctx& ctx, const TableView& T, const WalkView& W, c
     // ---- de-duplicate, materialise, sort (set of tuples -> sorted list) --------
     if (tid == 0) {
         int nu = 0;
-        bool overflow = false;
+        bool overflow = false, too_many = false;
         for (int c = 0; c < n_cand; ++c) {
             bool dup = false;
             for (int u = 0; u < nu && !dup; ++u) {
@@ -324,7 +347,7 @@ KM_HD void graph_target(const Ctx& ctx, const TableView& T, const WalkView& W, c
                 dup = S.ce_len[o] == S.ce_len[c] && S.ce_h1[o] == S.ce_h1[c] && S.ce_h2[o] == S.ce_h2[c];
             }
             if (dup) continue;
-            if (nu >= KM_MAX_PATHS) { overflow = true; break; }
+            if (nu >= S.max_paths) { overflow = true; too_many = true; break; }
             S.upath[nu++] = c;
         }
         int first = 0;
@@ -372,13 +395,19 @@ KM_HD void graph_target(const Ctx& ctx, const TableView& T, const WalkView& W, c
                 R.path_len[first + v + 1] = len_u;
             }
         }
-        if (overflow) { atomic_or32(&W.status[t], KM_ST_PATH_OVERFLOW); nu = 0; first = 0; }
-        R.t_n_paths[t] = nu;
+        if (overflow) {
+            const bool defer = too_many && S.retry;
+            atomic_or32(&W.status[t], defer ? KM_ST_RETRY_LARGE : (too_many ? (uint32_t)KM_ST_TOO_MANY_COLS : (uint32_t)KM_ST_PATH_OVERFLOW));
+            nu = -1; first = 0;
+        }
+        R.t_n_paths[t] = nu < 0 ? 0 : nu;
         R.t_path_first[t] = first;
+        if (nu < 0) { R.t_n_rows[t] = 0; R.t_row_first[t] = 0; }
         sh[2] = nu;
         sh[3] = first;
     }
     ctx.sync();
+    return sh[2] >= 0;
 }
 
 }  // namespace km

@@ -133,23 +133,52 @@ __global__ void __launch_bounds__(256) km_get_child_kernel(TableView T, const ui
     }
 }
 
-// ---- K3: walk, one CTA per target -----------------------------------------------------------
-__global__ void __launch_bounds__(KM_CTA) km_walk_kernel(TableView T, WalkView W, FindParams P) {
-    CtaCtx ctx;
-    walk_target(ctx, T, W, P, (int)blockIdx.x);
+// ---- K3: walk, one WARP per target ----------------------------------------------------------
+#define KM_WALK_WARPS 4
+__global__ void __launch_bounds__(32 * KM_WALK_WARPS) km_walk_kernel(TableView T, WalkView W, FindParams P) {
+    WarpCtx ctx;
+    const int t = (int)blockIdx.x * KM_WALK_WARPS + (int)(threadIdx.x >> 5);
+    if (t < W.n_targets) walk_target(ctx, T, W, P, t);
 }
 
 // ---- K4 + K5: graph, paths, FP64 quantification; persistent CTAs over targets -----------------
+// Two passes share one body.  The SHARED-MEMORY pass keeps the whole per-target working set
+// (adjacency, both shortest-path trees, candidate edges, solver matrices: ~50 KB) on chip and takes
+// every target whose graph has at most KM_SMALL_NODES nodes; the GENERAL pass uses per-CTA scratch
+// in HBM and takes the rest, plus any target the first pass deferred (KM_ST_RETRY_LARGE).
 struct ScratchLayout {
     char* base;
     size_t stride;          // bytes per CTA
     size_t o_newidx, o_kept, o_succ, o_pred, o_dist, o_before, o_after, o_cand, o_state, o_eflag, o_reach, o_occ;
-    size_t o_ce_a, o_ce_b, o_ce_len, o_ce_h1, o_ce_h2, o_upath, o_pdiff, o_grp, o_G, o_V, o_vec;
-    int maxN;
+    size_t o_ce_a, o_ce_b, o_ce_len, o_ce_h1, o_ce_h2, o_upath, o_pdiff, o_grp, o_G, o_V, o_vec, o_cols, o_members;
+    int maxN, max_cand, max_paths, max_cols;
 };
 
-__device__ __forceinline__ GraphScratch carve(const ScratchLayout& L, int cta) {
-    char* p = L.base + (size_t)cta * L.stride;
+#define KM_SMALL_NODES 512
+#define KM_SMALL_CAND 512
+#define KM_SMALL_PATHS 64
+#define KM_SMALL_COLS 8
+
+// the one place that knows the scratch layout (host sizing and device carving both use it)
+__host__ __device__ inline ScratchLayout make_layout(int maxcap, int max_cand, int max_paths, int max_cols) {
+    ScratchLayout L = {};
+    const size_t maxN = (size_t)maxcap + 2, nce = (size_t)max_cand;
+    size_t o = 0;
+    auto put = [&](size_t bytes) { size_t at = o; o = (o + bytes + 15) / 16 * 16; return at; };
+    L.o_newidx = put(4 * (size_t)maxcap); L.o_kept = put(4 * (size_t)maxcap);
+    L.o_succ = put(16 * maxN); L.o_pred = put(16 * maxN);
+    L.o_dist = put(4 * maxN); L.o_before = put(4 * maxN); L.o_after = put(4 * maxN); L.o_cand = put(4 * maxN);
+    L.o_state = put(maxN); L.o_eflag = put(maxN); L.o_reach = put(maxN); L.o_occ = put(4 * maxN);
+    L.o_ce_a = put(4 * nce); L.o_ce_b = put(4 * nce); L.o_ce_len = put(4 * nce); L.o_ce_h1 = put(8 * nce); L.o_ce_h2 = put(8 * nce);
+    L.o_upath = put(4 * (size_t)max_paths); L.o_pdiff = put(16 * (size_t)max_paths); L.o_grp = put(20 * (size_t)max_paths);
+    L.o_G = put(8 * (size_t)max_cols * max_cols); L.o_V = put(16 * (size_t)max_cols * max_cols); L.o_vec = put(64 * (size_t)max_cols);
+    L.o_cols = put(sizeof(PathView) * (size_t)max_cols); L.o_members = put(4 * (size_t)max_cols);
+    L.stride = (o + 255) / 256 * 256;
+    L.maxN = (int)maxN; L.max_cand = max_cand; L.max_paths = max_paths; L.max_cols = max_cols;
+    return L;
+}
+
+__device__ __forceinline__ GraphScratch carve(const ScratchLayout& L, char* p, int retry) {
     GraphScratch S;
     S.newidx = (int32_t*)(p + L.o_newidx); S.kept = (int32_t*)(p + L.o_kept);
     S.succ = (int32_t*)(p + L.o_succ); S.pred = (int32_t*)(p + L.o_pred);
@@ -160,26 +189,40 @@ __device__ __forceinline__ GraphScratch carve(const ScratchLayout& L, int cta) {
     S.ce_h1 = (uint64_t*)(p + L.o_ce_h1); S.ce_h2 = (uint64_t*)(p + L.o_ce_h2);
     S.upath = (int32_t*)(p + L.o_upath); S.pdiff = (int32_t*)(p + L.o_pdiff); S.grp = (int32_t*)(p + L.o_grp);
     S.G = (double*)(p + L.o_G); S.V = (double*)(p + L.o_V); S.vec = (double*)(p + L.o_vec);
-    S.maxN = L.maxN;
+    S.cols = (PathView*)(p + L.o_cols); S.members = (int32_t*)(p + L.o_members);
+    S.maxN = L.maxN; S.max_cand = L.max_cand; S.max_paths = L.max_paths; S.max_cols = L.max_cols; S.retry = retry;
     return S;
 }
 
 #define KM_ST_FATAL (KM_ST_BAD_BASE | KM_ST_DUP_KMER | KM_ST_NODE_OVERFLOW | KM_ST_NODE_LIMIT | KM_ST_TOO_SHORT)
 
+template <bool SMALL>
 __global__ void __launch_bounds__(KM_CTA) km_graph_kernel(TableView T, WalkView W, ScratchLayout SL, ResultView R,
                                                           char* seq_pool, int64_t* path_seq_off, int64_t seq_cap) {
+    extern __shared__ __align__(16) char km_smem[];
     __shared__ int sh[8];
     CtaCtx ctx;
-    const GraphScratch S = carve(SL, (int)blockIdx.x);
+    const GraphScratch S = SMALL ? carve(make_layout(KM_SMALL_NODES - 2, KM_SMALL_CAND, KM_SMALL_PATHS, KM_SMALL_COLS), km_smem, 1)
+                                 : carve(SL, SL.base + (size_t)blockIdx.x * SL.stride, 0);
     for (int t = blockIdx.x; t < W.n_targets; t += gridDim.x) {
-        if (W.status[t] & KM_ST_FATAL) {
-            if (threadIdx.x == 0) {
+        const uint32_t st = W.status[t];
+        if (st & KM_ST_FATAL) {
+            if (SMALL && threadIdx.x == 0) {
                 R.t_n[t] = 0; R.t_n_paths[t] = 0; R.t_path_first[t] = 0; R.t_n_rows[t] = 0; R.t_row_first[t] = 0;
             }
             continue;
         }
+        const int cap = (int)(W.node_off[t + 1] - W.node_off[t]);
+        const int n_all = W.n_nodes[t] < cap ? W.n_nodes[t] : cap;
+        const bool fits = n_all <= KM_SMALL_NODES - 2 && W.n_kept[t] + 2 <= KM_SMALL_NODES;
+        if (SMALL) { if (!fits) continue; }
+        else {
+            if (fits && !(st & KM_ST_RETRY_LARGE)) continue;
+            __syncthreads();
+            if (threadIdx.x == 0 && (st & KM_ST_RETRY_LARGE)) atomicAnd(&W.status[t], ~KM_ST_RETRY_LARGE);
+        }
         GraphDims d;
-        graph_target(ctx, T, W, S, R, t, &d, sh);
+        if (!graph_target(ctx, T, W, S, R, t, &d, sh)) continue;
         const int n_paths = sh[2], first = sh[3];
         // spell every unique path once (MutationFinder.get_seq, :375-403): first k-mer, then
         // the last base of each following node; rows print slices of these strings
@@ -187,15 +230,16 @@ __global__ void __launch_bounds__(KM_CTA) km_graph_kernel(TableView T, WalkView 
         for (int p = 0; p < n_paths; ++p) {
             const int len = R.path_len[first + p];
             const int32_t* idx = R.pool + R.path_off[first + p];
+            __syncthreads();
             if (threadIdx.x == 0) {
                 const int64_t off = len > 0 ? (int64_t)atomicAdd(&R.used[3], (unsigned long long)(len + T.k - 1)) : 0;
                 sh[4] = (int)(off & 0x7FFFFFFF); sh[5] = (int)(off >> 31);
             }
             __syncthreads();
             const int64_t off = ((int64_t)sh[5] << 31) | (int64_t)sh[4];
-            const bool fits = off + len + T.k - 1 <= seq_cap;
-            if (threadIdx.x == 0) path_seq_off[first + p] = fits ? off : -1;
-            if (!fits) { if (threadIdx.x == 0) atomicOr(&W.status[t], KM_ST_PATH_OVERFLOW); }
+            const bool fits_seq = off + len + T.k - 1 <= seq_cap;
+            if (threadIdx.x == 0) path_seq_off[first + p] = fits_seq ? off : -1;
+            if (!fits_seq) { if (threadIdx.x == 0) atomicOr(&W.status[t], KM_ST_PATH_OVERFLOW); }
             else if (len > 0) {
                 const uint64_t k0 = R.out_kmer[nbase + idx[0]];
                 for (int c = threadIdx.x; c < len + T.k - 1; c += blockDim.x) {
@@ -205,8 +249,8 @@ __global__ void __launch_bounds__(KM_CTA) km_graph_kernel(TableView T, WalkView 
                     seq_pool[off + c] = "ACGT"[code];
                 }
             }
-            __syncthreads();
         }
+        __syncthreads();
         emit_rows(ctx, T, W, S, R, t, d, n_paths, first, sh);
         __syncthreads();
     }

@@ -18,13 +18,6 @@
 
 namespace km {
 
-// a (possibly clipped) path: idx == nullptr means the reference path, whose node at
-// position p is simply p
-struct PathView {
-    const int32_t* idx;
-    int begin;
-    int len;
-};
 KM_HD int pv_at(const PathView& p, int i) { return p.idx ? p.idx[p.begin + i] : p.begin + i; }
 
 struct Diff {
@@ -154,7 +147,7 @@ KM_HD int solve_columns(const Ctx& ctx, const GraphScratch& S, const uint32_t* c
         for (int a = 0; a < m; ++a) if (coef[a] < 0.0) coef[a] = 0.0;
         double worst = INFINITY;
         int iters = 0;
-        double* grad = S.vec + 2 * KM_MAX_COLS;
+        double* grad = S.vec + 2 * S.max_cols;
         while (worst > 0.01) {
             for (int a = 0; a < m; ++a) {
                 double fit = 0.0;
@@ -196,8 +189,8 @@ KM_HD void emit_rows(const Ctx& ctx, const TableView& T, const WalkView& W, cons
     const int64_t nbase = W.node_off[t];
     const uint64_t* kmers = R.out_kmer + nbase;
     const uint32_t* counts = R.out_count + nbase;  // caps are not stored: rows never touch them
-    double* coef = S.vec + 4 * KM_MAX_COLS;
-    double* rvaf = S.vec + 5 * KM_MAX_COLS;
+    double* coef = S.vec + 4 * S.max_cols;
+    double* rvaf = S.vec + 5 * S.max_cols;
     const PathView ref = {nullptr, 0, d.L};
 
     // ---- cluster discovery by lane 0 (MutationFinder.py:656-694) ---------------
@@ -212,7 +205,7 @@ KM_HD void emit_rows(const Ctx& ctx, const TableView& T, const WalkView& W, cons
             S.grp[p] = -2;                       // -2 = still in variant_set
         }
         // cluster records: grp[n_paths + 4*c ...] = lo, hi, first member (chain), size
-        int32_t* crec = S.grp + KM_MAX_PATHS;    // lo,hi per cluster are recomputed later; keep order only
+        int32_t* crec = S.grp + S.max_paths;     // lo, hi, size per cluster, in seed order
         for (int seed = 0; seed < n_paths; ++seed) {
             if (S.grp[seed] != -2) continue;     // set.pop() on small ints == ascending order
             int lo = S.pdiff[4 * seed], hi = S.pdiff[4 * seed + 1];
@@ -266,13 +259,14 @@ KM_HD void emit_rows(const Ctx& ctx, const TableView& T, const WalkView& W, cons
     const int n_clusters = sh[5];
     const int first_row = sh[6];
     if (sh[7]) return;
-    int32_t* crec = S.grp + KM_MAX_PATHS;
+    int32_t* crec = S.grp + S.max_paths;
 
     // ---- vs_ref rows (MutationFinder.py:613-648) -------------------------------
-    PathView cols[KM_MAX_COLS];
+    PathView* cols = S.cols;
     for (int p = 0; p < n_paths; ++p) {
         const PathView alt = {R.pool + R.path_off[first_path + p], 0, R.path_len[first_path + p]};
-        cols[0] = alt; cols[1] = ref;
+        if (tid == 0) { cols[0] = alt; cols[1] = ref; }
+        ctx.sync();
         const int iters = solve_columns(ctx, S, counts, d.N, cols, 2, coef, rvaf, sh);
         if (tid == 0) {
             const Diff df = {S.pdiff[4 * p], S.pdiff[4 * p + 1], S.pdiff[4 * p + 2], S.pdiff[4 * p + 3]};
@@ -309,40 +303,44 @@ KM_HD void emit_rows(const Ctx& ctx, const TableView& T, const WalkView& W, cons
     int row_cursor = first_row + n_paths;
     for (int c = 0; c < n_clusters; ++c) {
         const int lo = crec[4 * c], hi = crec[4 * c + 1], size = crec[4 * c + 2];
-        if (size + 1 > KM_MAX_COLS) {
-            if (tid == 0) atomic_or32(&W.status[t], KM_ST_TOO_MANY_COLS);
-            // rows stay zeroed; the host refuses the target
+        if (size + 1 > S.max_cols) {
+            if (tid == 0) atomic_or32(&W.status[t], S.retry ? KM_ST_RETRY_LARGE : (uint32_t)KM_ST_TOO_MANY_COLS);
+            // rows stay unset; the general pass redoes the target, or the host refuses it
             row_cursor += size;
             continue;
         }
-        // members in join order
-        int members[KM_MAX_COLS];
-        for (int p = 0; p < n_paths; ++p) {
-            const int gcode = S.grp[p];
-            if (gcode >= 0 && (gcode & 0xFFFF) == c) members[gcode >> 16] = p;
+        int32_t* members = S.members;
+        if (tid == 0) {
+            // members in join order
+            for (int p = 0; p < n_paths; ++p) {
+                const int gcode = S.grp[p];
+                if (gcode >= 0 && (gcode & 0xFFFF) == c) members[gcode >> 16] = p;
+            }
+            int span = 0;
+            for (int j = 0; j < size; ++j) {
+                const int p = members[j];
+                int a = S.pdiff[4 * p + 2] - S.pdiff[4 * p + 1] + 1;      // abs(end_var - end_ref + 1) (:710-712)
+                a = a < 0 ? -a : a;
+                span = a > span ? a : span;
+            }
+            const int off0 = lo - span > 0 ? lo - span : 0;             // (:713)
+            // Python slices clamp to the sequence (:714, :720)
+            const int ref_stop = hi < d.L ? hi : d.L;
+            cols[0].idx = nullptr; cols[0].begin = off0; cols[0].len = ref_stop - off0 > 0 ? ref_stop - off0 : 0;
+            for (int j = 0; j < size; ++j) {
+                const int p = members[j];
+                const int plen = R.path_len[first_path + p];
+                int stop = S.pdiff[4 * p + 2] + hi - S.pdiff[4 * p + 1];   // (:719)
+                stop = stop < plen ? stop : plen;
+                const int beg = off0 < plen ? off0 : plen;
+                cols[1 + j].idx = R.pool + R.path_off[first_path + p];
+                cols[1 + j].begin = beg;
+                cols[1 + j].len = stop - beg > 0 ? stop - beg : 0;
+            }
         }
-        int span = 0;
-        for (int j = 0; j < size; ++j) {
-            const int p = members[j];
-            int a = S.pdiff[4 * p + 2] - S.pdiff[4 * p + 1] + 1;      // abs(end_var - end_ref + 1) (:710-712)
-            a = a < 0 ? -a : a;
-            span = a > span ? a : span;
-        }
-        const int offset = lo - span > 0 ? lo - span : 0;               // (:713)
-        // Python slices clamp to the sequence (:714, :720)
-        const int ref_stop = hi < d.L ? hi : d.L;
-        const PathView ref_clip = {nullptr, offset, ref_stop - offset > 0 ? ref_stop - offset : 0};
-        cols[0] = ref_clip;
-        for (int j = 0; j < size; ++j) {
-            const int p = members[j];
-            const int plen = R.path_len[first_path + p];
-            int stop = S.pdiff[4 * p + 2] + hi - S.pdiff[4 * p + 1];   // (:719)
-            stop = stop < plen ? stop : plen;
-            const int beg = offset < plen ? offset : plen;
-            cols[1 + j].idx = R.pool + R.path_off[first_path + p];
-            cols[1 + j].begin = beg;
-            cols[1 + j].len = stop - beg > 0 ? stop - beg : 0;
-        }
+        ctx.sync();
+        const int offset = cols[0].begin;
+        const PathView ref_clip = cols[0];
         const int iters = solve_columns(ctx, S, counts, d.N, cols, size + 1, coef, rvaf, sh);
         if (tid == 0) {
             for (int j = 0; j < size; ++j) {

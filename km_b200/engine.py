@@ -114,20 +114,71 @@ class Table:
                                        int(count), counts.ctypes.data, mask.ctypes.data))
         return counts, mask
 
-    def find_batch(self, sequences, count=5, ratio=0.05, steps=500, branchs=10, nodes=10000, extra_nodes=0):
-        """Run the whole find_mutation path for a list of target sequences in one call."""
+    @staticmethod
+    def _pack_targets(sequences):
         blob = "".join(sequences).encode("ascii")
         off = np.zeros(len(sequences) + 1, dtype=np.int64)
         if sequences:
             np.cumsum([len(s) for s in sequences], out=off[1:])
-        prm = FindParams(float(ratio), int(count), int(steps), int(branchs), int(nodes), int(extra_nodes))
+        return blob, off
+
+    def find_batch(self, sequences, count=5, ratio=0.05, steps=500, branchs=10, nodes=10000, extra_nodes=0,
+                   want_graph=True):
+        """Run the whole find_mutation path for a list of target sequences in one call.
+        want_graph=False skips copying node arrays / index paths back (rows and text only)."""
+        blob, off = self._pack_targets(sequences)
+        prm = FindParams(float(ratio), int(count), int(steps), int(branchs), int(nodes), int(extra_nodes),
+                         0 if want_graph else 1, 0)
         h = ctypes.c_void_p()
         check(lib().km_find_batch(self._h, blob, off.ctypes.data, len(sequences), ctypes.byref(prm), ctypes.byref(h)))
         return BatchResult.from_handle(h, list(sequences), self.k)
 
+    def plan(self, sequences, count=5, ratio=0.05, steps=500, branchs=10, nodes=10000, extra_nodes=0):
+        """Upload a batch once; launch it any number of times (FindPlan)."""
+        return FindPlan(self, sequences, count, ratio, steps, branchs, nodes, extra_nodes)
+
     def close(self):
         if getattr(self, "_h", None):
             lib().km_table_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class FindPlan:
+    """km_find_plan_*: a batch resident in HBM.  launch() enqueues the two kernels on a CUDA stream
+    (asynchronously), fetch() synchronises and returns a BatchResult."""
+
+    def __init__(self, table, sequences, count, ratio, steps, branchs, nodes, extra_nodes):
+        self.table = table
+        self.sequences = list(sequences)
+        blob, off = Table._pack_targets(self.sequences)
+        prm = FindParams(float(ratio), int(count), int(steps), int(branchs), int(nodes), int(extra_nodes), 0, 0)
+        self._h = ctypes.c_void_p()
+        check(lib().km_find_plan_create(table._h, blob, off.ctypes.data, len(self.sequences), ctypes.byref(prm),
+                                        ctypes.byref(self._h)))
+
+    def launch(self, stream=None):
+        check(lib().km_find_plan_launch(self._h, ctypes.c_void_p(stream) if stream else None))
+
+    def last_ms(self):
+        """(walk_ms, graph_ms) of the most recent launch, from CUDA events on its stream."""
+        w, g = ctypes.c_float(), ctypes.c_float()
+        check(lib().km_find_plan_last_ms(self._h, ctypes.byref(w), ctypes.byref(g)))
+        return w.value, g.value
+
+    def fetch(self, want_graph=True):
+        h = ctypes.c_void_p()
+        check(lib().km_find_plan_fetch(self._h, int(bool(want_graph)), ctypes.byref(h)))
+        return BatchResult.from_handle(h, self.sequences, self.table.k)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().km_find_plan_free(self._h)
             self._h = None
 
     def __del__(self):
@@ -163,21 +214,23 @@ class BatchResult:
         r.status = _view(v.status, np.uint32, n)
         r.n_nodes = _view(v.n_nodes, np.int32, n)
         r.node_off = _view(v.node_off, np.int64, n + 1)
-        total_nodes = int(r.node_off[-1]) if n else 0
+        r.has_graph = bool(v.has_graph)
+        total_nodes = int(r.node_off[-1]) if (n and r.has_graph) else 0
         r.node_kmer = _view(v.node_kmer, np.uint64, total_nodes)
         r.node_count = _view(v.node_count, np.uint32, total_nodes)
         r.path_first = _view(v.path_first, np.int32, n)
         r.path_count = _view(v.path_count, np.int32, n)
         r.path_off = _view(v.path_off, np.int64, v.n_paths)
         r.path_len = _view(v.path_len, np.int32, v.n_paths)
-        pool_n = int((r.path_off + r.path_len).max()) if v.n_paths else 0
+        pool_n = int((r.path_off + r.path_len).max()) if (v.n_paths and r.has_graph) else 0
         r.path_pool = _view(v.path_pool, np.int32, pool_n)
         r.row_first = _view(v.row_first, np.int32, n)
         r.row_count = _view(v.row_count, np.int32, n)
         r.rows = _view(v.rows, ROW_DTYPE, v.n_rows)
         r.lookups = _view(v.lookups, np.uint64, n)
         r.timing = {"h2d_ms": v.ms_h2d, "walk_ms": v.ms_walk, "graph_ms": v.ms_graph, "d2h_ms": v.ms_d2h,
-                    "total_ms": v.ms_total, "launches": v.n_launches, "retries": v.n_retries}
+                    "total_ms": v.ms_total, "launches": v.n_launches, "retries": v.n_retries,
+                    "h2d_bytes": int(v.bytes_h2d), "d2h_bytes": int(v.bytes_d2h)}
         return r
 
     # ---- per-target accessors ------------------------------------------------------------
@@ -250,6 +303,19 @@ class BatchResult:
             check(int(need))
         buf = ctypes.create_string_buffer(int(need) + 1)
         lib().km_result_format_target(self._h, int(t), db_name.encode(), query_name.encode(), buf, int(need) + 1)
+        return buf.raw[:int(need)].decode("ascii")
+
+    def format_all(self, db_name, names, threads=0):
+        """Sorted TSV text of every target, in target order, formatted on host threads."""
+        blob = "".join(names).encode()
+        off = np.zeros(len(names) + 1, dtype=np.int64)
+        if names:
+            np.cumsum([len(x.encode()) for x in names], out=off[1:])
+        need = lib().km_result_format_all(self._h, db_name.encode(), blob, off.ctypes.data, int(threads), None, 0)
+        if need < 0:
+            check(int(need))
+        buf = ctypes.create_string_buffer(int(need) + 1)
+        lib().km_result_format_all(self._h, db_name.encode(), blob, off.ctypes.data, int(threads), buf, int(need) + 1)
         return buf.raw[:int(need)].decode("ascii")
 
     def close(self):

@@ -50,7 +50,8 @@ int emu_row_size(void) { return (int)sizeof(Row); }
 int emu_find_target(void* h, const uint8_t* codes, int len, double ratio, int64_t count, int steps, int branchs, int nodes,
                     int extra, int32_t* out_n, uint64_t* out_kmer, uint32_t* out_count, int node_cap_out,
                     int32_t* out_n_paths, int32_t* out_path_len, int32_t* out_pool, int path_cap, int pool_cap,
-                    int32_t* out_n_rows, Row* out_rows, int row_cap, uint64_t* out_lookups) {
+                    int32_t* out_n_rows, Row* out_rows, int row_cap, uint64_t* out_lookups,
+                    int small_nodes, int small_cand, int small_paths, int small_cols, int32_t* out_pass) {
     EmuTable* t = (EmuTable*)h;
     const int k = t->v.k;
     const int L = len - k + 1 > 0 ? len - k + 1 : 0;
@@ -76,20 +77,6 @@ int emu_find_target(void* h, const uint8_t* codes, int len, double ratio, int64_
     *out_n = 0; *out_n_paths = 0; *out_n_rows = 0;
     if (status & (KM_ST_BAD_BASE | KM_ST_DUP_KMER | KM_ST_NODE_OVERFLOW | KM_ST_NODE_LIMIT | KM_ST_TOO_SHORT)) return (int)status;
 
-    const size_t maxN = (size_t)cap + 2, nce = 4 * maxN + 2;
-    std::vector<int32_t> newidx(cap), kept(cap), succ(4 * maxN), pred(4 * maxN), before(maxN), after(maxN), cand(maxN), occ(maxN);
-    std::vector<int32_t> ce_a(nce), ce_b(nce), ce_len(nce), upath(KM_MAX_PATHS), pdiff(4 * KM_MAX_PATHS), grp(5 * KM_MAX_PATHS);
-    std::vector<uint64_t> ce_h1(nce), ce_h2(nce);
-    std::vector<float> dist(maxN);
-    std::vector<uint8_t> state(maxN), eflag(maxN), reach(maxN);
-    std::vector<double> G(KM_MAX_COLS * KM_MAX_COLS), V(2 * KM_MAX_COLS * KM_MAX_COLS), vec(8 * KM_MAX_COLS);
-    GraphScratch S;
-    S.newidx = newidx.data(); S.kept = kept.data(); S.succ = succ.data(); S.pred = pred.data(); S.dist = dist.data();
-    S.before = before.data(); S.after = after.data(); S.cand = cand.data(); S.state = state.data(); S.eflag = eflag.data();
-    S.reach = reach.data(); S.occ = occ.data(); S.ce_a = ce_a.data(); S.ce_b = ce_b.data(); S.ce_len = ce_len.data();
-    S.ce_h1 = ce_h1.data(); S.ce_h2 = ce_h2.data(); S.upath = upath.data(); S.pdiff = pdiff.data(); S.grp = grp.data();
-    S.G = G.data(); S.V = V.data(); S.vec = vec.data(); S.maxN = (int)maxN;
-
     std::vector<uint64_t> okmer(cap);
     std::vector<uint32_t> ocount(cap);
     std::vector<int64_t> path_off(path_cap);
@@ -100,10 +87,40 @@ int emu_find_target(void* h, const uint8_t* codes, int len, double ratio, int64_
     R.out_kmer = okmer.data(); R.out_count = ocount.data();
     R.path_off = path_off.data(); R.path_len = out_path_len; R.pool = out_pool; R.path_cap = path_cap; R.pool_cap = pool_cap;
     R.rows = out_rows; R.row_cap = row_cap; R.used = used;
-    int sh[8] = {0};
-    GraphDims d;
-    graph_target(ctx, t->v, W, S, R, 0, &d, sh);
-    emit_rows(ctx, t->v, W, S, R, 0, d, sh[2], sh[3], sh);
+
+    // the two passes of km_graph_kernel: small capacities with deferral, then the general ones
+    auto run_pass = [&](int maxcap, int max_cand, int max_paths, int max_cols, int retry) -> bool {
+        const size_t maxN = (size_t)maxcap + 2;
+        std::vector<int32_t> newidx(maxcap), kept(maxcap), succ(4 * maxN), pred(4 * maxN), before(maxN), after(maxN), cand(maxN), occ(maxN);
+        std::vector<int32_t> ce_a(max_cand), ce_b(max_cand), ce_len(max_cand), upath(max_paths), pdiff(4 * max_paths), grp(5 * max_paths);
+        std::vector<int32_t> members(max_cols);
+        std::vector<uint64_t> ce_h1(max_cand), ce_h2(max_cand);
+        std::vector<float> dist(maxN);
+        std::vector<uint8_t> state(maxN), eflag(maxN), reach(maxN);
+        std::vector<double> G(max_cols * max_cols), V(2 * max_cols * max_cols), vec(8 * max_cols);
+        std::vector<PathView> cols(max_cols);
+        GraphScratch S;
+        S.newidx = newidx.data(); S.kept = kept.data(); S.succ = succ.data(); S.pred = pred.data(); S.dist = dist.data();
+        S.before = before.data(); S.after = after.data(); S.cand = cand.data(); S.state = state.data(); S.eflag = eflag.data();
+        S.reach = reach.data(); S.occ = occ.data(); S.ce_a = ce_a.data(); S.ce_b = ce_b.data(); S.ce_len = ce_len.data();
+        S.ce_h1 = ce_h1.data(); S.ce_h2 = ce_h2.data(); S.upath = upath.data(); S.pdiff = pdiff.data(); S.grp = grp.data();
+        S.G = G.data(); S.V = V.data(); S.vec = vec.data(); S.cols = cols.data(); S.members = members.data();
+        S.maxN = (int)maxN; S.max_cand = max_cand; S.max_paths = max_paths; S.max_cols = max_cols; S.retry = retry;
+        int sh[8] = {0};
+        GraphDims d;
+        if (!graph_target(ctx, t->v, W, S, R, 0, &d, sh)) return false;
+        emit_rows(ctx, t->v, W, S, R, 0, d, sh[2], sh[3], sh);
+        return true;
+    };
+    const int n_all = n_nodes < cap ? n_nodes : cap;
+    const bool fits = n_all <= small_nodes - 2 && n_kept + 2 <= small_nodes;
+    bool done = false;
+    if (fits) done = run_pass(small_nodes - 2, small_cand, small_paths, small_cols, 1) && !(status & KM_ST_RETRY_LARGE);
+    if (!done) {
+        status &= ~KM_ST_RETRY_LARGE;
+        run_pass(cap, 4 * (cap + 2) + 2, KM_MAX_PATHS, KM_MAX_COLS, 0);
+    }
+    *out_pass = done ? 1 : 2;
     if (t_n - 2 > node_cap_out) return -1;
     *out_n = t_n;
     memcpy(out_kmer, okmer.data(), sizeof(uint64_t) * (size_t)(t_n - 2));
@@ -113,8 +130,12 @@ int emu_find_target(void* h, const uint8_t* codes, int len, double ratio, int64_
     // paths were bump-allocated from offset 0 in order of materialisation, then re-ordered: hand
     // the offsets back through the first ints of a side channel -> compact them here instead
     std::vector<int32_t> compact;
-    for (int p = 0; p < t_np; ++p) compact.insert(compact.end(), out_pool + path_off[p], out_pool + path_off[p] + out_path_len[p]);
+    std::vector<int32_t> lens;
+    for (int p = t_pf; p < t_pf + t_np; ++p) { compact.insert(compact.end(), out_pool + path_off[p], out_pool + path_off[p] + out_path_len[p]); lens.push_back(out_path_len[p]); }
     memcpy(out_pool, compact.data(), sizeof(int32_t) * compact.size());
+    for (int p = 0; p < t_np; ++p) out_path_len[p] = lens[p];
+    // rows of the last pass start at t_rf and refer to path ids t_pf..: rebase both to 0
+    for (int r = 0; r < t_nr; ++r) { out_rows[r] = out_rows[t_rf + r]; out_rows[r].path_id -= t_pf; }
     return (int)status;
 }
 

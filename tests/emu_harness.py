@@ -41,7 +41,7 @@ def lib():
         L.emu_synth_count.argtypes = [u64]
         L.emu_find_target.restype = ci
         L.emu_find_target.argtypes = [vp, vp, ci, ctypes.c_double, ctypes.c_int64, ci, ci, ci, ci,
-                                      vp, vp, vp, ci, vp, vp, vp, ci, ci, vp, vp, ci, vp]
+                                      vp, vp, vp, ci, vp, vp, vp, ci, ci, vp, vp, ci, vp, ci, ci, ci, ci, vp]
         assert L.emu_row_size() == ROW_DTYPE.itemsize
         _L = L
     return _L
@@ -69,12 +69,15 @@ class EmuTable:
     def query_packed(self, v):
         return int(lib().emu_query(self._h, int(v)))
 
-    def find_batch(self, sequences, count=5, ratio=0.05, steps=500, branchs=10, nodes=10000, extra_nodes=256):
+    def find_batch(self, sequences, count=5, ratio=0.05, steps=500, branchs=10, nodes=10000, extra_nodes=256,
+                   small=(512, 512, 64, 8)):
+        """small = (nodes, candidate edges, paths, columns) capacities of the shared-memory pass."""
         n = len(sequences)
         res = engine.BatchResult()
         res.k = self.k
         res.sequences = list(sequences)
         status, n_nodes, lookups = [], [], []
+        self.passes = []
         node_off = [0]
         kmers, cnts, pfirst, pcount, plen, poff, pool, rfirst, rcount, rows = [], [], [], [], [], [], [], [], [], []
         for t, seq in enumerate(sequences):
@@ -90,16 +93,19 @@ class EmuTable:
                 po = np.zeros(1 << 20, np.int32)
                 rw = np.zeros(4096, dtype=ROW_DTYPE)
                 lk = ctypes.c_uint64()
+                which = ctypes.c_int32()
                 st = lib().emu_find_target(self._h, codes.ctypes.data, len(seq), float(ratio), int(count), int(steps),
                                            int(branchs), int(nodes), extra, ctypes.byref(out_n), o_k.ctypes.data,
                                            o_c.ctypes.data, cap, ctypes.byref(npaths), pl.ctypes.data, po.ctypes.data,
-                                           1024, 1 << 20, ctypes.byref(nrows), rw.ctypes.data, 4096, ctypes.byref(lk))
+                                           1024, 1 << 20, ctypes.byref(nrows), rw.ctypes.data, 4096, ctypes.byref(lk),
+                                           small[0], small[1], small[2], small[3], ctypes.byref(which))
                 assert st >= 0
                 if st & engine.ST_NODE_OVERFLOW:
                     extra *= 8
                     continue
                 break
             status.append(st)
+            self.passes.append(which.value)
             n_nodes.append(out_n.value)
             lookups.append(lk.value)
             nn = max(0, out_n.value - 2)

@@ -123,3 +123,18 @@ def test_degenerate_targets():
     assert int(res.status[2]) == 0 and int(res.n_nodes[2]) == 3      # a single k-mer target
     assert int(res.status[3]) & 64         # shorter than k
     assert int(res.status[4]) & 1          # non-ACGT letter
+
+
+@pytest.mark.parametrize("small", [(512, 512, 64, 8), (512, 512, 1, 8), (512, 8, 64, 8), (512, 512, 64, 2), (64, 512, 64, 8)])
+def test_both_scratch_passes_agree(synth_small, small):
+    """The shared-memory pass defers to the general pass when a capacity is exceeded; whichever
+    pass finishes a target, the records are the reference's."""
+    t = EmuTable.from_keys(synth_small["keys"], synth_small["counts"])
+    res = t.find_batch(synth_small["targets"][:40], small=small)
+    if small == (512, 512, 64, 8):
+        assert set(t.passes) == {1}
+    else:
+        assert 2 in t.passes
+    for i, rec in enumerate(synth_small["records"][:40]):
+        assert int(res.status[i]) == 0
+        _check(rec, record_of(res, i, "synth_small.jf", rec["target"]), rec["target"])
