@@ -44,6 +44,7 @@ KM_HD uint32_t atomic_add32(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
 KM_HD int32_t atomic_addi32(int32_t* p, int32_t v) { return atomicAdd(p, v); }
 KM_HD uint32_t atomic_min32(uint32_t* p, uint32_t v) { return atomicMin(p, v); }
 KM_HD uint32_t atomic_or32(uint32_t* p, uint32_t v) { return atomicOr(p, v); }
+KM_HD int32_t atomic_mini32(int32_t* p, int32_t v) { return atomicMin(p, v); }
 KM_HD unsigned long long atomic_add64(unsigned long long* p, unsigned long long v) { return atomicAdd(p, v); }
 // loads that must observe other threads' atomics: go to L2, never a stale L1 line
 KM_HD uint64_t load_cg64(const uint64_t* p) { return __ldcg(reinterpret_cast<const unsigned long long*>(p)); }
@@ -65,6 +66,7 @@ KM_HD uint32_t atomic_add32(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o +
 KM_HD int32_t atomic_addi32(int32_t* p, int32_t v) { int32_t o = *p; *p = o + v; return o; }
 KM_HD uint32_t atomic_min32(uint32_t* p, uint32_t v) { uint32_t o = *p; if (v < o) *p = v; return o; }
 KM_HD uint32_t atomic_or32(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o | v; return o; }
+KM_HD int32_t atomic_mini32(int32_t* p, int32_t v) { int32_t o = *p; if (v < o) *p = v; return o; }
 KM_HD unsigned long long atomic_add64(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }
 KM_HD uint64_t load_cg64(const uint64_t* p) { return *p; }
 KM_HD uint32_t load_cg32(const uint32_t* p) { return *p; }

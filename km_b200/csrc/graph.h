@@ -80,13 +80,13 @@ struct GraphScratch {
     int32_t* kept;     // [maxcap]   discovery indices of kept novel nodes
     int32_t* succ;     // [4*maxN]
     int32_t* pred;     // [4*maxN]
-    float* dist;       // [maxN]
+    float* dist;       // [maxN]  distance from the source cap (+inf = unreachable)
+    float* dist2;      // [maxN]  distance to the sink cap
     int32_t* before;   // [maxN]
     int32_t* after;    // [maxN]
-    int32_t* cand;     // [maxN]
-    uint8_t* state;    // [maxN]
+    int32_t* cand;     // [maxN]  open set of the forward pass
+    int32_t* cand2;    // [maxN]  open set of the backward pass
     uint8_t* eflag;    // [maxN]  bit c: edge to succ[c] still in edge_set; bit 4: cap edge
-    uint8_t* reach;    // [maxN]  bit 0 reachable from source, bit 1 reaches sink
     int32_t* occ;      // [maxN]
     int32_t* ce_a;     // [4*maxN+2] candidate edges
     int32_t* ce_b;
@@ -99,6 +99,7 @@ struct GraphScratch {
     double* G;         // [max_cols*max_cols]
     double* V;         // [2*max_cols*max_cols]
     double* vec;       // [8*max_cols]
+    unsigned long long* acc;  // [max_cols*max_cols + max_cols] exact integer accumulators of G and h
     PathView* cols;    // [max_cols] columns of the current least-squares problem
     int32_t* members;  // [max_cols]
     int maxN;
@@ -146,39 +147,67 @@ KM_HD void for_each_pred(const GraphScratch& S, const GraphDims& d, int u, F f) 
     if (u == 0) f(d.src);
 }
 
-// Graph._get_paths (Graph.py:63-119) on adjacency lists.  `forward` walks w, otherwise
-// w transposed.  Sequential: executed by one lane.  Only nodes that acquire a finite
-// distance are ever settled with effect, so the open set is kept as an explicit list.
-KM_HD void shortest_tree(const GraphScratch& S, const GraphDims& d, int start, bool forward, int32_t* prev,
-                         uint8_t reach_bit) {
-    for (int i = 0; i < d.N; ++i) { S.dist[i] = INFINITY; prev[i] = -1; S.state[i] = 0; }
-    S.dist[start] = 0.0f;
+// Graph._get_paths (Graph.py:63-119) on adjacency lists; `forward` walks w, otherwise w
+// transposed.  Sequential by nature -- every distance is the float32 sum of its parent's distance
+// and one weight -- so it runs on ONE lane, and the loop is kept to two dependent shared-memory
+// round trips per settled node: the 4 neighbour slots come in with one 16-byte load, the current
+// node and its distance live in registers, "unseen" is dist == +inf (no state array), and the
+// open set is an explicit list that almost always holds a single node.
+// dist/prev must be pre-filled with +inf / -1.
+struct alignas(16) Slot4 { int32_t v[4]; };
+
+KM_HD void shortest_tree(const GraphScratch& S, const GraphDims& d, bool forward, float* dist, int32_t* prev,
+                         int32_t* cand) {
+    const int32_t* nbr = forward ? S.succ : S.pred;
     int nc = 0;
-    S.cand[nc++] = start;
-    S.state[start] = 1;
-    while (nc > 0) {
-        // open node of least distance, lowest index on ties (Graph.py:113-114)
-        int best = 0;
-        for (int c = 1; c < nc; ++c) {
-            const int a = S.cand[c], b = S.cand[best];
-            const float da = S.dist[a], db = S.dist[b];
-            if (da < db || (da == db && a < b)) best = c;
-        }
-        const int u = S.cand[best];
-        S.cand[best] = S.cand[--nc];
-        S.state[u] = 2;
-        S.reach[u] |= reach_bit;
-        const float du = S.dist[u];
+    int u = forward ? d.src : d.snk;
+    float du = 0.0f;
+    dist[u] = 0.0f;
+    for (;;) {
         auto relax = [&](int j, float w) {
-            const float trial = add_f32(w, du);          // w[i, :] + dist[i] in float32 (:93)
-            if (trial < S.dist[j]) {                     // strict (:103)
-                S.dist[j] = trial;
+            const float trial = add_f32(w, du);              // w[i, :] + dist[i] in float32 (:93)
+            const float old = dist[j];
+            if (trial < old) {                               // strict (:103)
+                dist[j] = trial;
                 prev[j] = u;
-                if (S.state[j] == 0) { S.state[j] = 1; S.cand[nc++] = j; }
+                if (old == INFINITY) cand[nc++] = j;         // first time seen -> joins the open set
             }
         };
-        if (forward) for_each_succ(S, d, u, [&](int j, int) { relax(j, edge_weight(d, u, j)); });
-        else for_each_pred(S, d, u, [&](int j) { relax(j, edge_weight(d, j, u)); });
+        if (forward) {
+            if (u == d.src) relax(0, KM_REF_W);              // BigBang -> first k-mer (:545-547)
+            else if (u != d.snk) {
+                const Slot4 s4 = *reinterpret_cast<const Slot4*>(nbr + 4 * u);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int j = s4.v[c];
+                    if (j >= 0) relax(j, (j == u + 1 && u < d.L - 1) ? KM_REF_W : KM_ALT_W);
+                }
+                if (u == d.L - 1) relax(d.snk, KM_REF_W);    // last k-mer -> BigCrunch (:549-551)
+            }
+        } else {
+            if (u == d.snk) relax(d.L - 1, KM_REF_W);
+            else if (u != d.src) {
+                const Slot4 s4 = *reinterpret_cast<const Slot4*>(nbr + 4 * u);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int j = s4.v[c];
+                    if (j >= 0) relax(j, (u == j + 1 && j < d.L - 1) ? KM_REF_W : KM_ALT_W);
+                }
+                if (u == 0) relax(d.src, KM_REF_W);
+            }
+        }
+        if (nc == 0) break;
+        // open node of least distance, lowest index on ties (Graph.py:113-114)
+        int best = 0;
+        float db = dist[cand[0]];
+        for (int c = 1; c < nc; ++c) {
+            const int a = cand[c];
+            const float da = dist[a];
+            if (da < db || (da == db && a < cand[best])) { best = c; db = da; }
+        }
+        u = cand[best];
+        du = db;
+        cand[best] = cand[--nc];
     }
 }
 
@@ -196,7 +225,7 @@ KM_HD void hash_step(uint64_t& h1, uint64_t& h2, int pos, int v) {
 // All threads of the CTA must call this.
 template <class Ctx>
 KM_HD bool graph_target(const Ctx& ctx, const TableView& T, const WalkView& W, const GraphScratch& S,
-                        const ResultView& R, int t, GraphDims* dims_out, int* sh /* 8 ints of CTA-shared memory */) {
+                        const ResultView& R, int t, GraphDims* dims_out, int* sh /* 16 ints of CTA-shared memory */) {
     const int k = T.k;
     const TargetGeom g = target_geom(W, t, k);
     const int tid = ctx.tid(), nt = ctx.nt();
@@ -252,25 +281,35 @@ KM_HD bool graph_target(const Ctx& ctx, const TableView& T, const WalkView& W, c
         S.succ[e] = js;
         S.pred[e] = jp;
     }
-    for (int i = tid; i < d.N; i += nt) { S.eflag[i] = 0x1F; S.reach[i] = 0; }
+    for (int i = tid; i < d.N; i += nt) {
+        S.eflag[i] = 0x1F;
+        S.dist[i] = INFINITY; S.dist2[i] = INFINITY; S.before[i] = -1; S.after[i] = -1;
+    }
     ctx.sync();
 
-    // ---- two shortest-path trees (Graph.py:175-176) ---------------------------
-    // TODO(perf): the two passes are independent; they share S.dist/S.cand here so they
-    // run back to back on one lane.
+    // ---- two shortest-path trees (Graph.py:175-176), concurrently on two warps ------
+    {
+        const int lane_b = nt > 32 ? 32 : 0;                 // the backward pass's lane
+        if (tid == 0) shortest_tree(S, d, true, S.dist, S.before, S.cand);
+        if (tid == lane_b) shortest_tree(S, d, false, S.dist2, S.after, S.cand2);
+    }
+    ctx.sync();
     if (tid == 0) {
-        shortest_tree(S, d, d.src, true, S.before, 1);
-        shortest_tree(S, d, d.snk, false, S.after, 2);
         // ---- strip the reference chain (Graph.py:178-198) ----------------------
-        for (int start = 0; start < d.N; ++start) {
-            if (S.before[start] != d.src) continue;
-            int cur = start, last = -1;
-            while (S.after[cur] != -1) {
-                cur = S.after[cur];
+        // the only out-edge of the source cap goes to node 0, so node 0 is the one start whose
+        // predecessor is the source (`np.where(before == first_node)`, :184)
+        if (S.before[0] == d.src) {
+            int cur = 0, last = -1;
+            for (int nxt = S.after[cur]; nxt != -1; nxt = S.after[cur]) {
+                cur = nxt;
                 if (last > 0) {                      // `if last_cur and ...`: None and 0 are falsy
                     if (cur == d.snk) { if (last == d.L - 1) S.eflag[last] &= (uint8_t)~0x10; }
-                    else for (int c = 0; c < 4; ++c)
-                        if (S.succ[4 * last + c] == cur) S.eflag[last] &= (uint8_t)~(1u << c);
+                    else {
+                        const Slot4 s4 = *reinterpret_cast<const Slot4*>(S.succ + 4 * last);
+                        uint8_t m = 0;
+                        for (int c = 0; c < 4; ++c) if (s4.v[c] == cur) m |= (uint8_t)(1u << c);
+                        if (m) S.eflag[last] &= (uint8_t)~m;
+                    }
                 }
                 last = cur;
             }
@@ -282,10 +321,10 @@ KM_HD bool graph_target(const Ctx& ctx, const TableView& T, const WalkView& W, c
     // ---- candidate edges (Graph.py:220-240) -----------------------------------
     // edge (a, b) yields a path iff a is reachable from the source and b reaches the sink
     for (int a = tid; a < d.N; a += nt) {
-        if (!(S.reach[a] & 1)) continue;
+        if (!(S.dist[a] < INFINITY)) continue;
         for_each_succ(S, d, a, [&](int b, int slot) {
             if (!(S.eflag[a] & (1u << slot))) return;
-            if (!(S.reach[b] & 2)) return;
+            if (!(S.dist2[b] < INFINITY)) return;
             const int pos = atomic_addi32(&sh[1], 1);
             if (pos < S.max_cand) { S.ce_a[pos] = a; S.ce_b[pos] = b; }
         });
@@ -336,10 +375,11 @@ KM_HD bool graph_target(const Ctx& ctx, const TableView& T, const WalkView& W, c
     }
     ctx.sync();
 
-    // ---- de-duplicate, materialise, sort (set of tuples -> sorted list) --------
+    // ---- de-duplicate (set of tuples), lane 0: few candidates, all in scratch ---------
     if (tid == 0) {
         int nu = 0;
         bool overflow = false, too_many = false;
+        int64_t total = 0;
         for (int c = 0; c < n_cand; ++c) {
             bool dup = false;
             for (int u = 0; u < nu && !dup; ++u) {
@@ -349,50 +389,21 @@ KM_HD bool graph_target(const Ctx& ctx, const TableView& T, const WalkView& W, c
             if (dup) continue;
             if (nu >= S.max_paths) { overflow = true; too_many = true; break; }
             S.upath[nu++] = c;
+            total += S.ce_len[c] - 2;                            // caps stripped (MutationFinder.py:562)
         }
         int first = 0;
         if (!overflow && nu > 0) {
             first = (int)atomic_add64(&R.used[0], (unsigned long long)nu);
             if (first + nu > R.path_cap) overflow = true;
         }
-        if (!overflow) {
-            for (int u = 0; u < nu && !overflow; ++u) {
-                const int c = S.upath[u];
-                const int len = S.ce_len[c] - 2;                 // caps stripped (MutationFinder.py:562)
-                const int64_t off = (int64_t)atomic_add64(&R.used[1], (unsigned long long)len);
-                if (off + len > R.pool_cap) { overflow = true; break; }
-                int32_t* dst = R.pool + off;
-                // forward half: positions len_f-2 .. 0 (source cap dropped)
-                int lf = 0;
-                for (int cur = S.ce_a[c]; cur != -1; cur = S.before[cur]) ++lf;
-                int p = lf - 2;
-                for (int cur = S.ce_a[c]; cur != d.src; cur = S.before[cur]) dst[p--] = cur;
-                p = lf - 1;
-                for (int cur = S.ce_b[c]; cur != d.snk; cur = S.after[cur]) dst[p++] = cur;
+        if (!overflow && nu > 0) {
+            int64_t off = (int64_t)atomic_add64(&R.used[1], (unsigned long long)total);
+            if (off + total > R.pool_cap) overflow = true;
+            else for (int u = 0; u < nu; ++u) {
+                const int len = S.ce_len[S.upath[u]] - 2;
                 R.path_off[first + u] = off;
                 R.path_len[first + u] = len;
-            }
-        }
-        if (!overflow) {
-            // lexicographic insertion sort of the (few) unique paths
-            for (int u = 1; u < nu; ++u) {
-                const int64_t off_u = R.path_off[first + u];
-                const int len_u = R.path_len[first + u];
-                int v = u - 1;
-                while (v >= 0) {
-                    const int64_t off_v = R.path_off[first + v];
-                    const int len_v = R.path_len[first + v];
-                    const int32_t *pu = R.pool + off_u, *pv = R.pool + off_v;
-                    int m = len_u < len_v ? len_u : len_v, x = 0;
-                    while (x < m && pu[x] == pv[x]) ++x;
-                    const bool u_less = x < m ? pu[x] < pv[x] : len_u < len_v;
-                    if (!u_less) break;
-                    R.path_off[first + v + 1] = off_v;
-                    R.path_len[first + v + 1] = len_v;
-                    --v;
-                }
-                R.path_off[first + v + 1] = off_u;
-                R.path_len[first + v + 1] = len_u;
+                off += len;
             }
         }
         if (overflow) {
@@ -405,6 +416,54 @@ KM_HD bool graph_target(const Ctx& ctx, const TableView& T, const WalkView& W, c
         if (nu < 0) { R.t_n_rows[t] = 0; R.t_row_first[t] = 0; }
         sh[2] = nu;
         sh[3] = first;
+    }
+    ctx.sync();
+    const int nu = sh[2], first = sh[3];
+    if (nu < 0) return false;
+
+    // ---- materialise: one lane per unique path walks its two chains ------------------
+    for (int u = tid; u < nu; u += nt) {
+        const int c = S.upath[u];
+        int32_t* dst = R.pool + R.path_off[first + u];
+        int lf = 0;
+        for (int cur = S.ce_a[c]; cur != -1; cur = S.before[cur]) ++lf;
+        int p = lf - 2;                                          // source cap dropped
+        for (int cur = S.ce_a[c]; cur != d.src; cur = S.before[cur]) dst[p--] = cur;
+        p = lf - 1;
+        for (int cur = S.ce_b[c]; cur != d.snk; cur = S.after[cur]) dst[p++] = cur;
+    }
+    ctx.sync();
+
+    // ---- lexicographic order (sorted(set of tuples)): rank by pairwise CTA-parallel compares ----
+    if (nu > 1) {
+        int* slot = sh + 8;
+        for (int u = tid; u < nu; u += nt) S.upath[u] = 0;       // rank of each path
+        ctx.sync();
+        for (int x = 0; x < nu - 1; ++x)
+            for (int y = x + 1; y < nu; ++y) {
+                const int32_t* px = R.pool + R.path_off[first + x];
+                const int32_t* py = R.pool + R.path_off[first + y];
+                const int lx = R.path_len[first + x], ly = R.path_len[first + y], m = lx < ly ? lx : ly;
+                if (tid == 0) *slot = m;
+                ctx.sync();
+                for (int q = tid; q < m; q += nt)
+                    if (px[q] != py[q]) { atomic_mini32(slot, q); break; }
+                ctx.sync();
+                if (tid == 0) {
+                    const int q = *slot;
+                    const bool x_less = q < m ? px[q] < py[q] : lx < ly;
+                    S.upath[x_less ? y : x] += 1;
+                }
+                ctx.sync();
+            }
+        if (tid == 0) {
+            // permute (offset, length) into rank order; ce_h1 / ce_len serve as temporaries
+            for (int u = 0; u < nu; ++u) { S.ce_h1[u] = (uint64_t)R.path_off[first + u]; S.ce_len[u] = R.path_len[first + u]; }
+            for (int u = 0; u < nu; ++u) {
+                R.path_off[first + S.upath[u]] = (int64_t)S.ce_h1[u];
+                R.path_len[first + S.upath[u]] = S.ce_len[u];
+            }
+        }
     }
     ctx.sync();
     return sh[2] >= 0;

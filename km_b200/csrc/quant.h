@@ -7,33 +7,61 @@
 //   emit_rows       quantify_paths (:613-648), _find_clusters (:651-723),
 //                   quantify_clusters (:749-811)
 //
+// Every scan over a path (common prefix / suffix, minimum count, contribution sums) is done by
+// the whole CTA: lanes test strided positions and combine with one shared-memory atomic, so the
+// index pool in HBM is read with independent loads instead of a loop-carried chain.
+//
 // The least-squares step works on the normal equations: G = A^T A and h = A^T b are sums of
-// small integers and float32-exact counts, hence EXACT in FP64; the minimum-norm solution
-// (what LAPACK gelsd returns for np.linalg.lstsq, PathQuant.py:116) is obtained from a
-// Jacobi eigen-decomposition of G with the singular-value cut of rcond = eps*max(M,N).
-// refine_coef is then iterated literally (fixed step 0.1, gradient / n_nodes, stop at
-// max|grad| <= 0.01): the reference's answer IS the iterate it stops at.
+// small integers and float32-exact counts, accumulated in 64-bit integers, hence EXACT; the
+// minimum-norm solution (what LAPACK gelsd returns for np.linalg.lstsq, PathQuant.py:116) comes
+// from a Jacobi eigen-decomposition of G.  refine_coef is then iterated literally (fixed step
+// 0.1, gradient / n_nodes, stop at max|grad| <= 0.01): the reference's answer IS the iterate it
+// stops at.
 #pragma once
 #include "graph.h"
 
 namespace km {
 
 KM_HD int pv_at(const PathView& p, int i) { return p.idx ? p.idx[p.begin + i] : p.begin + i; }
+// Python indexing: a negative position counts from the end (the reference's third scan can run
+// its alt cursor below zero, MutationFinder.py:362-369); beyond that Python raises -> no match
+KM_HD int pv_at_wrap(const PathView& p, int i) {
+    if (i < 0) i += p.len;
+    return i < 0 ? -1 : pv_at(p, i);
+}
 
 struct Diff {
     int start, end_ref, end_var, end_ref_overlap;
 };
 
-KM_HD Diff diff_paths(const PathView& ref, const PathView& alt, int k) {
+// smallest p in [0, n) with f(p), else n.  All threads call; `slot` is CTA-shared.
+template <class Ctx, class F>
+KM_HD int first_true(const Ctx& ctx, int n, F f, int* slot) {
+    if (ctx.tid() == 0) *slot = n;
+    ctx.sync();
+    for (int p = ctx.tid(); p < n; p += ctx.nt())
+        if (f(p)) { atomic_mini32(slot, p); break; }
+    ctx.sync();
+    const int r = *slot;
+    ctx.sync();
+    return r;
+}
+
+template <class Ctx>
+KM_HD Diff diff_paths(const Ctx& ctx, const PathView& ref, const PathView& alt, int k, int* slot) {
+    const int nr = ref.len, na = alt.len, m = nr < na ? nr : na;
+    // common prefix (:321-331)
+    const int i = first_true(ctx, m, [&](int p) { return pv_at(ref, p) != pv_at(alt, p); }, slot);
+    // common suffix, keeping k positions clear of the prefix (:334-356): the loop runs while
+    // both ends stay >= i + k, i.e. for at most m - i - k + 1 steps
+    int room = m - i - k + 1;
+    if (room < 0) room = 0;
+    const int s1 = first_true(ctx, room, [&](int s) { return pv_at(ref, nr - 1 - s) != pv_at(alt, na - 1 - s); }, slot);
+    const int jr = nr - s1, ja = na - s1;
+    // the same scan allowed to run back to the prefix on the reference side (:358-369)
+    const int s2 = first_true(ctx, jr - i, [&](int s) { return pv_at(ref, jr - 1 - s) != pv_at_wrap(alt, ja - 1 - s); }, slot);
     Diff d;
-    const int nr = ref.len, na = alt.len;
-    int i = 0;
-    while (i < nr && i < na && pv_at(ref, i) == pv_at(alt, i)) ++i;
-    int jr = nr, ja = na;
-    while (jr >= i + k && ja >= i + k && pv_at(ref, jr - 1) == pv_at(alt, ja - 1)) { --jr; --ja; }
-    int kr = jr, ka = ja;
-    while (kr > i && pv_at(ref, kr - 1) == pv_at(alt, ka - 1)) { --kr; --ka; }
-    d.start = i; d.end_ref = jr; d.end_var = ja; d.end_ref_overlap = kr;
+    d.start = i; d.end_ref = jr; d.end_var = ja; d.end_ref_overlap = jr - s2;
     return d;
 }
 
@@ -103,27 +131,33 @@ KM_HD int solve_columns(const Ctx& ctx, const GraphScratch& S, const uint32_t* c
     const int tid = ctx.tid(), nt = ctx.nt();
     double* G = S.G;
     double* h = S.vec;   // [m]
+    unsigned long long* acc = S.acc;   // [m*m + m] exact integer accumulators
+    for (int i = tid; i < m * m + m; i += nt) acc[i] = 0ull;
     // contrib[i, c] = occurrences of node i in column c (PathQuant.py:101-104);
     // G[a][b] = sum_i contrib[i,a]*contrib[i,b]; h[a] = sum_i contrib[i,a]*float32(count_i)
     for (int b = 0; b < m; ++b) {
         for (int i = tid; i < n_nodes; i += nt) S.occ[i] = 0;
         ctx.sync();
-        for (int p = tid; p < cols[b].len; p += nt) atomic_addi32(&S.occ[pv_at(cols[b], p)], 1);
+        unsigned long long hb = 0ull;
+        for (int p = tid; p < cols[b].len; p += nt) {
+            const int node = pv_at(cols[b], p);
+            atomic_addi32(&S.occ[node], 1);
+            hb += (unsigned long long)(float)counts[node];      // counts -> float32 (PathQuant.py:99), an integer
+        }
+        if (hb) atomic_add64(&acc[m * m + b], hb);
         ctx.sync();
-        if (tid == 0) {
-            // lane 0 accumulates: exact integer sums, order irrelevant
-            for (int a = b; a < m; ++a) {
-                long long acc = 0;
-                for (int p = 0; p < cols[a].len; ++p) acc += S.occ[pv_at(cols[a], p)];
-                G[a * m + b] = G[b * m + a] = (double)acc;
-            }
-            double hb = 0.0;
-            for (int p = 0; p < cols[b].len; ++p) hb += (double)(float)counts[pv_at(cols[b], p)];
-            h[b] = hb;
+        for (int a = b; a < m; ++a) {
+            unsigned long long part = 0ull;
+            for (int p = tid; p < cols[a].len; p += nt) part += (unsigned long long)S.occ[pv_at(cols[a], p)];
+            if (part) atomic_add64(&acc[a * m + b], part);
         }
         ctx.sync();
     }
     if (tid == 0) {
+        for (int a = 0; a < m; ++a) {
+            h[a] = (double)acc[m * m + a];
+            for (int b = 0; b <= a; ++b) G[a * m + b] = G[b * m + a] = (double)acc[a * m + b];
+        }
         double* A = S.V;                 // working copy for the eigen solver
         double* V = S.V + m * m;         // needs 2*m*m doubles: S.V is sized for that
         for (int i = 0; i < m * m; ++i) A[i] = G[i];
@@ -173,10 +207,19 @@ KM_HD int solve_columns(const Ctx& ctx, const GraphScratch& S, const uint32_t* c
     return sh[4];
 }
 
-KM_HD int64_t min_count(const uint32_t* counts, const PathView& p) {
-    int64_t m = 0x7FFFFFFFFFFFFFFFll;
-    for (int i = 0; i < p.len; ++i) { const int64_t c = counts[pv_at(p, i)]; m = c < m ? c : m; }
-    return m;
+// min(counts over the path) by the whole CTA; `slot` is CTA-shared.  An empty path gives 2^32-1.
+template <class Ctx>
+KM_HD int64_t min_count(const Ctx& ctx, const uint32_t* counts, const PathView& p, int* slot) {
+    uint32_t* us = reinterpret_cast<uint32_t*>(slot);
+    if (ctx.tid() == 0) *us = 0xFFFFFFFFu;
+    ctx.sync();
+    uint32_t mine = 0xFFFFFFFFu;
+    for (int i = ctx.tid(); i < p.len; i += ctx.nt()) { const uint32_t c = counts[pv_at(p, i)]; mine = c < mine ? c : mine; }
+    if (mine != 0xFFFFFFFFu) atomic_min32(us, mine);
+    ctx.sync();
+    const int64_t r = (int64_t)*us;
+    ctx.sync();
+    return r;
 }
 
 // quantify_paths + quantify_clusters for target t.  `dims`, `n_paths`, `first_path` come
@@ -191,20 +234,25 @@ KM_HD void emit_rows(const Ctx& ctx, const TableView& T, const WalkView& W, cons
     const uint32_t* counts = R.out_count + nbase;  // caps are not stored: rows never touch them
     double* coef = S.vec + 4 * S.max_cols;
     double* rvaf = S.vec + 5 * S.max_cols;
+    int* slot = sh + 8;                              // reduction scratch (sh holds 16 ints)
     const PathView ref = {nullptr, 0, d.L};
 
-    // ---- cluster discovery by lane 0 (MutationFinder.py:656-694) ---------------
-    // grp[0..n) = cluster id of each path (-1 = none); clusters are numbered in seed order
-    if (tid == 0) {
-        int n_clusters = 0, n_rows = n_paths;
-        for (int p = 0; p < n_paths; ++p) {
-            const PathView alt = {R.pool + R.path_off[first_path + p], 0, R.path_len[first_path + p]};
-            const Diff df = diff_paths(ref, alt, k);
+    // ---- per-path diffs against the whole reference (CTA-parallel scans) ---------
+    for (int p = 0; p < n_paths; ++p) {
+        const PathView alt = {R.pool + R.path_off[first_path + p], 0, R.path_len[first_path + p]};
+        const Diff df = diff_paths(ctx, ref, alt, k, slot);
+        if (tid == 0) {
             S.pdiff[4 * p + 0] = df.start; S.pdiff[4 * p + 1] = df.end_ref;
             S.pdiff[4 * p + 2] = df.end_var; S.pdiff[4 * p + 3] = df.end_ref_overlap;
             S.grp[p] = -2;                       // -2 = still in variant_set
         }
-        // cluster records: grp[n_paths + 4*c ...] = lo, hi, first member (chain), size
+    }
+    ctx.sync();
+
+    // ---- cluster discovery by lane 0 (MutationFinder.py:656-694) ---------------
+    // grp[p] = cluster id | (join order << 16), -1 = none; clusters are numbered in seed order
+    if (tid == 0) {
+        int n_clusters = 0, n_rows = n_paths;
         int32_t* crec = S.grp + S.max_paths;     // lo, hi, size per cluster, in seed order
         for (int seed = 0; seed < n_paths; ++seed) {
             if (S.grp[seed] != -2) continue;     // set.pop() on small ints == ascending order
@@ -224,20 +272,14 @@ KM_HD void emit_rows(const Ctx& ctx, const TableView& T, const WalkView& W, cons
                     }
                 }
                 if (hit < 0) break;
-                // members keep their join order through a per-cluster sequence number
                 S.grp[hit] = cid | (size << 16);
                 ++size;
                 lo = S.pdiff[4 * hit] < lo ? S.pdiff[4 * hit] : lo;
                 hi = S.pdiff[4 * hit + 1] > hi ? S.pdiff[4 * hit + 1] : hi;
             }
-            // a lone path equal to the reference forms no cluster (:703-707)
-            bool skip = false;
-            if (size == 1) {
-                const PathView alt = {R.pool + R.path_off[first_path + seed], 0, R.path_len[first_path + seed]};
-                skip = alt.len == d.L;
-                for (int x = 0; skip && x < alt.len; ++x) skip = pv_at(alt, x) == x;
-            }
-            if (skip) { S.grp[seed] = -1; continue; }
+            // a lone path equal to the reference forms no cluster (:703-707): the path IS the
+            // reference exactly when the common prefix covers both completely
+            if (size == 1 && R.path_len[first_path + seed] == d.L && S.pdiff[4 * seed] == d.L) { S.grp[seed] = -1; continue; }
             crec[4 * cid + 0] = lo; crec[4 * cid + 1] = hi; crec[4 * cid + 2] = size; crec[4 * cid + 3] = 0;
             ++n_clusters;
             n_rows += size;
@@ -260,20 +302,20 @@ KM_HD void emit_rows(const Ctx& ctx, const TableView& T, const WalkView& W, cons
     const int first_row = sh[6];
     if (sh[7]) return;
     int32_t* crec = S.grp + S.max_paths;
+    PathView* cols = S.cols;
 
     // ---- vs_ref rows (MutationFinder.py:613-648) -------------------------------
-    PathView* cols = S.cols;
     for (int p = 0; p < n_paths; ++p) {
         const PathView alt = {R.pool + R.path_off[first_path + p], 0, R.path_len[first_path + p]};
         if (tid == 0) { cols[0] = alt; cols[1] = ref; }
         ctx.sync();
         const int iters = solve_columns(ctx, S, counts, d.N, cols, 2, coef, rvaf, sh);
+        const int64_t mc = min_count(ctx, counts, alt, slot);
         if (tid == 0) {
             const Diff df = {S.pdiff[4 * p], S.pdiff[4 * p + 1], S.pdiff[4 * p + 2], S.pdiff[4 * p + 3]};
             int dl, il;
             const int type = classify(kmers, ref, alt, df, &dl, &il);
-            bool is_ref = alt.len == d.L;
-            for (int x = 0; is_ref && x < alt.len; ++x) is_ref = pv_at(alt, x) == x;
+            const bool is_ref = alt.len == d.L && df.start == d.L;      // alt_index == ref_index (:627)
             double c0 = coef[0], c1 = coef[1], r0 = rvaf[0], r1 = rvaf[1];
             if (is_ref) {
                 // adjust_for_reference (PathQuant.py:151-154).  With all-zero coef rVAF aliases
@@ -290,7 +332,7 @@ KM_HD void emit_rows(const Ctx& ctx, const TableView& T, const WalkView& W, cons
             row.ref_begin = 0; row.ref_end = d.L;
             row.del_begin = df.start; row.del_len = dl; row.ins_begin = df.start; row.ins_len = il;
             row.start_off = 0; row.cluster_id = 0; row.cluster_n = 0; row.n_iter = iters;
-            row.min_cov = min_count(counts, alt);
+            row.min_cov = mc;
             row.rvaf = r0; row.expr = c0; row.ref_rvaf = r1; row.ref_expr = c1;
             if (iters < 0) atomic_or32(&W.status[t], KM_ST_SOLVER_WATCHDOG);
             if (d.L - (df.end_ref - df.start) + (df.end_var - df.start) != alt.len)
@@ -342,11 +384,12 @@ KM_HD void emit_rows(const Ctx& ctx, const TableView& T, const WalkView& W, cons
         const int offset = cols[0].begin;
         const PathView ref_clip = cols[0];
         const int iters = solve_columns(ctx, S, counts, d.N, cols, size + 1, coef, rvaf, sh);
-        if (tid == 0) {
-            for (int j = 0; j < size; ++j) {
+        for (int j = 0; j < size; ++j) {
+            const PathView clip = cols[1 + j];
+            const Diff df = diff_paths(ctx, ref_clip, clip, k, slot);
+            const int64_t mc = min_count(ctx, counts, clip, slot);
+            if (tid == 0) {
                 const int p = members[j];
-                const PathView clip = cols[1 + j];
-                const Diff df = diff_paths(ref_clip, clip, k);
                 int dl, il;
                 const int type = classify(kmers, ref_clip, clip, df, &dl, &il);
                 Row& row = R.rows[row_cursor + j];
@@ -357,13 +400,13 @@ KM_HD void emit_rows(const Ctx& ctx, const TableView& T, const WalkView& W, cons
                 row.del_begin = ref_clip.begin + df.start; row.del_len = dl;
                 row.ins_begin = clip.begin + df.start; row.ins_len = il;
                 row.start_off = offset; row.cluster_id = c + 1; row.cluster_n = size; row.n_iter = iters;
-                row.min_cov = min_count(counts, clip);
+                row.min_cov = mc;
                 row.rvaf = rvaf[1 + j]; row.expr = coef[1 + j]; row.ref_rvaf = rvaf[0]; row.ref_expr = coef[0];
                 if (ref_clip.len - (df.end_ref - df.start) + (df.end_var - df.start) != clip.len)
                     atomic_or32(&W.status[t], KM_ST_NAME_MISMATCH);
             }
-            if (iters < 0) atomic_or32(&W.status[t], KM_ST_SOLVER_WATCHDOG);
         }
+        if (tid == 0 && iters < 0) atomic_or32(&W.status[t], KM_ST_SOLVER_WATCHDOG);
         ctx.sync();
         row_cursor += size;
     }

@@ -15,6 +15,7 @@ import tempfile
 def main():
     rep, so, kern = sys.argv[1:4]
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+    ncu_name = sys.argv[5] if len(sys.argv) > 5 else kern      # demangled base name for ncu -k
     with tempfile.TemporaryDirectory() as d:
         subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=d, check=True, capture_output=True)
         cubin = [f for f in os.listdir(d) if f.endswith(".cubin")][0]
@@ -36,7 +37,7 @@ def main():
         m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*);", ln)
         if m and cur:
             line_of[int(m.group(1), 16)] = (cur, m.group(2).strip())
-    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + kern], capture_output=True,
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + ncu_name], capture_output=True,
                          text=True).stdout
     rows = list(csv.reader(out.split("\n")))
     hdr = None
