@@ -442,7 +442,7 @@ static int plan_layout(km_plan* p) {
     const int64_t n_node = p->n_node = p->node_off[n], n_hash = p->n_hash = p->hash_off[n], n_code = p->n_code = p->seq_off[n];
     p->grid_graph = std::max(1, std::min(n, t->sm_count * 8));
     p->grid_large = std::max(1, std::min(n, t->sm_count * 2));
-    const ScratchLayout L0 = make_layout(maxcap, 4 * (maxcap + 2) + 2, KM_MAX_PATHS, KM_MAX_COLS);
+    const ScratchLayout L0 = make_layout(maxcap, KM_MAX_PATHS, KM_MAX_PATHS, KM_MAX_COLS);
     const int32_t path_cap = p->path_cap, row_cap = p->row_cap;
     const int64_t pool_cap = p->pool_cap, seq_cap = p->seq_cap;
 

@@ -88,11 +88,9 @@ struct GraphScratch {
     int32_t* cand2;    // [maxN]  open set of the backward pass
     uint8_t* eflag;    // [maxN]  bit c: edge to succ[c] still in edge_set; bit 4: cap edge
     int32_t* occ;      // [maxN]
-    int32_t* ce_a;     // [4*maxN+2] candidate edges
+    int32_t* ce_a;     // [max_cand] edges that each yield one distinct alternative path
     int32_t* ce_b;
     int32_t* ce_len;
-    uint64_t* ce_h1;
-    uint64_t* ce_h2;
     int32_t* upath;    // [max_paths] candidate index of each unique path
     int32_t* pdiff;    // [4*max_paths] start, end_ref, end_var, end_ref_overlap
     int32_t* grp;      // [5*max_paths] cluster bookkeeping
@@ -211,14 +209,6 @@ KM_HD void shortest_tree(const GraphScratch& S, const GraphDims& d, bool forward
     }
 }
 
-// Position-keyed additive hash: the same index sequence hashes identically no matter at which
-// edge it was split into a forward and a backward half.
-KM_HD void hash_step(uint64_t& h1, uint64_t& h2, int pos, int v) {
-    const uint64_t x = ((uint64_t)(uint32_t)pos << 32) | (uint64_t)(uint32_t)v;
-    h1 += mix64(x ^ 0x243F6A8885A308D3ull);
-    h2 += mix64((x + 0x13198A2E03707344ull) * 0xD1342543DE82EF95ull);
-}
-
 // Builds the graph of target t and emits its unique alternative paths (caps stripped), written
 // to the result pool in lexicographic order; sh[2] = their number, sh[3] = the first path id.
 // Returns false (uniformly) when a scratch capacity was exceeded and the target was deferred.
@@ -319,80 +309,62 @@ KM_HD bool graph_target(const Ctx& ctx, const TableView& T, const WalkView& W, c
     ctx.sync();
 
     // ---- candidate edges (Graph.py:220-240) -----------------------------------
-    // edge (a, b) yields a path iff a is reachable from the source and b reaches the sink
+    // Edge (a, b) of the remaining edge_set yields the path src..a (forward tree) + b..snk
+    // (backward tree) iff a is reachable from the source and b reaches the sink.  The reference
+    // de-duplicates the resulting tuples in a set; here duplicates are recognised WITHOUT
+    // building them: (a, b) repeats the path of (before[a], a) exactly when after[a] == b and that
+    // earlier edge is itself still in the edge_set.  (The edges of one path that reproduce it are
+    // contiguous -- a stripped reference edge can only follow them, never sit between two --
+    // so the earliest one is the unique representative.)
     for (int a = tid; a < d.N; a += nt) {
         if (!(S.dist[a] < INFINITY)) continue;
         for_each_succ(S, d, a, [&](int b, int slot) {
             if (!(S.eflag[a] & (1u << slot))) return;
             if (!(S.dist2[b] < INFINITY)) return;
+            if (a != d.src && S.after[a] == b) {
+                const int pa = S.before[a];
+                bool earlier;
+                if (pa == d.src) earlier = (S.eflag[pa] & 0x10) != 0;
+                else {
+                    const Slot4 s4 = *reinterpret_cast<const Slot4*>(S.succ + 4 * pa);
+                    uint8_t m = 0;
+                    for (int c = 0; c < 4; ++c) if (s4.v[c] == a) m |= (uint8_t)(1u << c);
+                    earlier = (S.eflag[pa] & m) != 0;
+                }
+                if (earlier) return;
+            }
             const int pos = atomic_addi32(&sh[1], 1);
             if (pos < S.max_cand) { S.ce_a[pos] = a; S.ce_b[pos] = b; }
         });
     }
     ctx.sync();
     const int n_cand = sh[1];
-    if (n_cand > S.max_cand) {
-        if (tid == 0) atomic_or32(&W.status[t], S.retry ? KM_ST_RETRY_LARGE : (uint32_t)KM_ST_PATH_OVERFLOW);
-        if (tid == 0) { R.t_n_paths[t] = 0; R.t_path_first[t] = 0; R.t_n_rows[t] = 0; R.t_row_first[t] = 0; }
+    if (n_cand > S.max_cand || n_cand > S.max_paths) {
+        if (tid == 0) {
+            atomic_or32(&W.status[t], S.retry ? KM_ST_RETRY_LARGE : (uint32_t)KM_ST_TOO_MANY_COLS);
+            R.t_n_paths[t] = 0; R.t_path_first[t] = 0; R.t_n_rows[t] = 0; R.t_row_first[t] = 0;
+        }
         ctx.sync();
         return false;
     }
-    // order candidates deterministically by (a, b) -- rank sort, n_cand is small
+    // length of each unique path incl. both caps: hops to the source + hops to the sink
     for (int c = tid; c < n_cand; c += nt) {
-        const int a = S.ce_a[c], b = S.ce_b[c];
-        int rank = 0;
-        for (int o = 0; o < n_cand; ++o) {
-            const int oa = S.ce_a[o], ob = S.ce_b[o];
-            rank += (oa < a || (oa == a && ob < b)) ? 1 : 0;
-        }
-        S.ce_len[c] = rank;    // borrowed as the destination index
-    }
-    ctx.sync();
-    for (int c = tid; c < n_cand; c += nt) {
-        // stash (a,b) in the hash arrays while permuting
-        S.ce_h1[c] = ((uint64_t)(uint32_t)S.ce_a[c] << 32) | (uint32_t)S.ce_b[c];
-        S.ce_h2[c] = (uint64_t)S.ce_len[c];
-    }
-    ctx.sync();
-    for (int c = tid; c < n_cand; c += nt) {
-        const int dst = (int)S.ce_h2[c];
-        S.ce_a[dst] = (int)(S.ce_h1[c] >> 32);
-        S.ce_b[dst] = (int)(uint32_t)S.ce_h1[c];
-    }
-    ctx.sync();
-    // length + two independent 64-bit hashes of the index sequence src..a, b..snk
-    for (int c = tid; c < n_cand; c += nt) {
-        uint64_t h1 = 0, h2 = 0;
-        int lf = 0;
-        for (int cur = S.ce_a[c]; cur != -1; cur = S.before[cur]) ++lf;
-        int pos = lf - 1;
-        for (int cur = S.ce_a[c]; cur != -1; cur = S.before[cur]) hash_step(h1, h2, pos--, cur);
-        pos = lf;
-        for (int cur = S.ce_b[c]; cur != -1; cur = S.after[cur]) hash_step(h1, h2, pos++, cur);
-        S.ce_len[c] = pos;
-        S.ce_h1[c] = h1;
-        S.ce_h2[c] = h2;
+        int len = 0;
+        for (int cur = S.ce_a[c]; cur != -1; cur = S.before[cur]) ++len;
+        for (int cur = S.ce_b[c]; cur != -1; cur = S.after[cur]) ++len;
+        S.ce_len[c] = len;
+        S.upath[c] = c;
     }
     ctx.sync();
 
-    // ---- de-duplicate (set of tuples), lane 0: few candidates, all in scratch ---------
+    // ---- allocate path ids and pool space (lane 0) ---------------------------------------
     if (tid == 0) {
-        int nu = 0;
-        bool overflow = false, too_many = false;
+        int nu = n_cand;
+        bool overflow = false;
         int64_t total = 0;
-        for (int c = 0; c < n_cand; ++c) {
-            bool dup = false;
-            for (int u = 0; u < nu && !dup; ++u) {
-                const int o = S.upath[u];
-                dup = S.ce_len[o] == S.ce_len[c] && S.ce_h1[o] == S.ce_h1[c] && S.ce_h2[o] == S.ce_h2[c];
-            }
-            if (dup) continue;
-            if (nu >= S.max_paths) { overflow = true; too_many = true; break; }
-            S.upath[nu++] = c;
-            total += S.ce_len[c] - 2;                            // caps stripped (MutationFinder.py:562)
-        }
+        for (int c = 0; c < nu; ++c) total += S.ce_len[c] - 2;     // caps stripped (MutationFinder.py:562)
         int first = 0;
-        if (!overflow && nu > 0) {
+        if (nu > 0) {
             first = (int)atomic_add64(&R.used[0], (unsigned long long)nu);
             if (first + nu > R.path_cap) overflow = true;
         }
@@ -400,17 +372,13 @@ KM_HD bool graph_target(const Ctx& ctx, const TableView& T, const WalkView& W, c
             int64_t off = (int64_t)atomic_add64(&R.used[1], (unsigned long long)total);
             if (off + total > R.pool_cap) overflow = true;
             else for (int u = 0; u < nu; ++u) {
-                const int len = S.ce_len[S.upath[u]] - 2;
+                const int len = S.ce_len[u] - 2;
                 R.path_off[first + u] = off;
                 R.path_len[first + u] = len;
                 off += len;
             }
         }
-        if (overflow) {
-            const bool defer = too_many && S.retry;
-            atomic_or32(&W.status[t], defer ? KM_ST_RETRY_LARGE : (too_many ? (uint32_t)KM_ST_TOO_MANY_COLS : (uint32_t)KM_ST_PATH_OVERFLOW));
-            nu = -1; first = 0;
-        }
+        if (overflow) { atomic_or32(&W.status[t], KM_ST_PATH_OVERFLOW); nu = -1; first = 0; }
         R.t_n_paths[t] = nu < 0 ? 0 : nu;
         R.t_path_first[t] = first;
         if (nu < 0) { R.t_n_rows[t] = 0; R.t_row_first[t] = 0; }
@@ -457,10 +425,14 @@ KM_HD bool graph_target(const Ctx& ctx, const TableView& T, const WalkView& W, c
                 ctx.sync();
             }
         if (tid == 0) {
-            // permute (offset, length) into rank order; ce_h1 / ce_len serve as temporaries
-            for (int u = 0; u < nu; ++u) { S.ce_h1[u] = (uint64_t)R.path_off[first + u]; S.ce_len[u] = R.path_len[first + u]; }
+            // permute (offset, length) into rank order; pdiff / ce_len serve as temporaries
             for (int u = 0; u < nu; ++u) {
-                R.path_off[first + S.upath[u]] = (int64_t)S.ce_h1[u];
+                const int64_t off = R.path_off[first + u];
+                S.pdiff[2 * u] = (int32_t)(off & 0x7FFFFFFF); S.pdiff[2 * u + 1] = (int32_t)(off >> 31);
+                S.ce_len[u] = R.path_len[first + u];
+            }
+            for (int u = 0; u < nu; ++u) {
+                R.path_off[first + S.upath[u]] = ((int64_t)S.pdiff[2 * u + 1] << 31) | (int64_t)S.pdiff[2 * u];
                 R.path_len[first + S.upath[u]] = S.ce_len[u];
             }
         }

@@ -150,12 +150,12 @@ struct ScratchLayout {
     char* base;
     size_t stride;          // bytes per CTA
     size_t o_newidx, o_kept, o_succ, o_pred, o_dist, o_dist2, o_before, o_after, o_cand, o_cand2, o_eflag, o_occ;
-    size_t o_ce_a, o_ce_b, o_ce_len, o_ce_h1, o_ce_h2, o_upath, o_pdiff, o_grp, o_G, o_V, o_vec, o_acc, o_cols, o_members;
+    size_t o_ce_a, o_ce_b, o_ce_len, o_upath, o_pdiff, o_grp, o_G, o_V, o_vec, o_acc, o_cols, o_members;
     int maxN, max_cand, max_paths, max_cols;
 };
 
 #define KM_SMALL_NODES 512
-#define KM_SMALL_CAND 512
+#define KM_SMALL_CAND 64
 #define KM_SMALL_PATHS 64
 #define KM_SMALL_COLS 8
 
@@ -169,7 +169,7 @@ __host__ __device__ inline ScratchLayout make_layout(int maxcap, int max_cand, i
     L.o_succ = put(16 * maxN); L.o_pred = put(16 * maxN);
     L.o_dist = put(4 * maxN); L.o_dist2 = put(4 * maxN); L.o_before = put(4 * maxN); L.o_after = put(4 * maxN);
     L.o_cand = put(4 * maxN); L.o_cand2 = put(4 * maxN); L.o_eflag = put(maxN); L.o_occ = put(4 * maxN);
-    L.o_ce_a = put(4 * nce); L.o_ce_b = put(4 * nce); L.o_ce_len = put(4 * nce); L.o_ce_h1 = put(8 * nce); L.o_ce_h2 = put(8 * nce);
+    L.o_ce_a = put(4 * nce); L.o_ce_b = put(4 * nce); L.o_ce_len = put(4 * nce);
     L.o_upath = put(4 * (size_t)max_paths); L.o_pdiff = put(16 * (size_t)max_paths); L.o_grp = put(20 * (size_t)max_paths);
     L.o_G = put(8 * (size_t)max_cols * max_cols); L.o_V = put(16 * (size_t)max_cols * max_cols); L.o_vec = put(64 * (size_t)max_cols);
     L.o_acc = put(8 * ((size_t)max_cols * max_cols + max_cols));
@@ -188,7 +188,6 @@ __device__ __forceinline__ GraphScratch carve(const ScratchLayout& L, char* p, i
     S.cand = (int32_t*)(p + L.o_cand); S.cand2 = (int32_t*)(p + L.o_cand2); S.eflag = (uint8_t*)(p + L.o_eflag);
     S.occ = (int32_t*)(p + L.o_occ);
     S.ce_a = (int32_t*)(p + L.o_ce_a); S.ce_b = (int32_t*)(p + L.o_ce_b); S.ce_len = (int32_t*)(p + L.o_ce_len);
-    S.ce_h1 = (uint64_t*)(p + L.o_ce_h1); S.ce_h2 = (uint64_t*)(p + L.o_ce_h2);
     S.upath = (int32_t*)(p + L.o_upath); S.pdiff = (int32_t*)(p + L.o_pdiff); S.grp = (int32_t*)(p + L.o_grp);
     S.G = (double*)(p + L.o_G); S.V = (double*)(p + L.o_V); S.vec = (double*)(p + L.o_vec);
     S.acc = (unsigned long long*)(p + L.o_acc);

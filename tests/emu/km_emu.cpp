@@ -94,7 +94,6 @@ int emu_find_target(void* h, const uint8_t* codes, int len, double ratio, int64_
         std::vector<int32_t> newidx(maxcap), kept(maxcap), succ(4 * maxN), pred(4 * maxN), before(maxN), after(maxN), cand(maxN), cand2(maxN), occ(maxN);
         std::vector<int32_t> ce_a(max_cand), ce_b(max_cand), ce_len(max_cand), upath(max_paths), pdiff(4 * max_paths), grp(5 * max_paths);
         std::vector<int32_t> members(max_cols);
-        std::vector<uint64_t> ce_h1(max_cand), ce_h2(max_cand);
         std::vector<float> dist(maxN), dist2(maxN);
         std::vector<uint8_t> eflag(maxN);
         std::vector<double> G(max_cols * max_cols), V(2 * max_cols * max_cols), vec(8 * max_cols);
@@ -104,7 +103,7 @@ int emu_find_target(void* h, const uint8_t* codes, int len, double ratio, int64_
         S.newidx = newidx.data(); S.kept = kept.data(); S.succ = succ.data(); S.pred = pred.data(); S.dist = dist.data();
         S.before = before.data(); S.after = after.data(); S.cand = cand.data(); S.cand2 = cand2.data(); S.dist2 = dist2.data();
         S.eflag = eflag.data(); S.occ = occ.data(); S.ce_a = ce_a.data(); S.ce_b = ce_b.data(); S.ce_len = ce_len.data();
-        S.ce_h1 = ce_h1.data(); S.ce_h2 = ce_h2.data(); S.upath = upath.data(); S.pdiff = pdiff.data(); S.grp = grp.data();
+        S.upath = upath.data(); S.pdiff = pdiff.data(); S.grp = grp.data();
         S.G = G.data(); S.V = V.data(); S.vec = vec.data(); S.cols = cols.data(); S.members = members.data(); S.acc = acc.data();
         S.maxN = (int)maxN; S.max_cand = max_cand; S.max_paths = max_paths; S.max_cols = max_cols; S.retry = retry;
         int sh[16] = {0};
@@ -119,7 +118,7 @@ int emu_find_target(void* h, const uint8_t* codes, int len, double ratio, int64_
     if (fits) done = run_pass(small_nodes - 2, small_cand, small_paths, small_cols, 1) && !(status & KM_ST_RETRY_LARGE);
     if (!done) {
         status &= ~KM_ST_RETRY_LARGE;
-        run_pass(cap, 4 * (cap + 2) + 2, KM_MAX_PATHS, KM_MAX_COLS, 0);
+        run_pass(cap, KM_MAX_PATHS, KM_MAX_PATHS, KM_MAX_COLS, 0);
     }
     *out_pass = done ? 1 : 2;
     if (t_n - 2 > node_cap_out) return -1;
