@@ -288,13 +288,21 @@ def main():
     walk_ms, graph_ms = float(np.mean(walk_ms)), float(np.mean(graph_ms))
 
     # ---- e2e: host buffers in, TSV text out ---------------------------------------------------
+    e2e_split = {"find_batch_ms": 0.0, "format_ms": 0.0}
+
     def e2e_step():
+        t_a = time.perf_counter()
         res = table.find_batch(panel.targets, want_graph=False)
-        text = res.format_all("panel.jf", panel.names)
+        t_b = time.perf_counter()
+        text = res.format_all("panel.jf", panel.names, as_bytes=True)
+        t_c = time.perf_counter()
+        e2e_split["find_batch_ms"] += 1e3 * (t_b - t_a)
+        e2e_split["format_ms"] += 1e3 * (t_c - t_b)
         return res, text
 
     for _ in range(args.warmup):
         res, text = e2e_step()
+    e2e_split = {k: 0.0 for k in e2e_split}
     barrier()
     torch.cuda.synchronize(dev)
     t0 = time.perf_counter()
@@ -306,6 +314,8 @@ def main():
     e2e_value = world * args.targets / (e2e_ms / 1e3)
     h2d, d2h = res.timing["h2d_bytes"], res.timing["d2h_bytes"]
     e2e_breakdown = {k: res.timing[k] for k in ("h2d_ms", "walk_ms", "graph_ms", "d2h_ms")}
+    e2e_breakdown.update({k: v / args.steps for k, v in e2e_split.items()})
+    text = text.tobytes().decode("ascii")
 
     # ---- lookup microbenchmark (device-resident queries) ---------------------------------------
     lookup = None

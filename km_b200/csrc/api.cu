@@ -390,6 +390,9 @@ struct km_result {
     int n_launches = 0, n_retries = 0;
     bool has_graph = true;
     unsigned long long bytes_h2d = 0, bytes_d2h = 0;
+    // km_result_format_all is called twice (size, then fill): the text is built once
+    mutable std::string fmt_key;
+    mutable std::vector<std::string> fmt_parts;
 };
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -839,19 +842,25 @@ extern "C" int64_t km_result_format_all(const km_result* r, const char* db_name,
                                         int32_t threads, char* buf, int64_t buf_len) {
     if (!r || !db_name || (r->n_targets && (!names || !name_off))) { fail(KM_E_ARG, "km_result_format_all: bad argument"); return -1; }
     const int n = r->n_targets;
-    std::vector<std::string> parts((size_t)n);
-    int nt = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
-    nt = std::max(1, std::min(nt, std::max(1, n / 64)));
-    auto work = [&](int lo, int hi) {
-        for (int t = lo; t < hi; ++t)
-            format_rows_of(r, t, db_name, std::string(names + name_off[t], (size_t)(name_off[t + 1] - name_off[t])), parts[t]);
-    };
-    if (nt == 1) work(0, n);
-    else {
-        std::vector<std::thread> pool;
-        for (int i = 0; i < nt; ++i) pool.emplace_back(work, (int)((int64_t)n * i / nt), (int)((int64_t)n * (i + 1) / nt));
-        for (auto& th : pool) th.join();
+    std::string key = std::string(db_name) + '\0' + (n ? std::string(names, (size_t)name_off[n]) : std::string());
+    if (r->fmt_key != key || r->fmt_parts.size() != (size_t)n) {
+        r->fmt_parts.assign((size_t)n, std::string());
+        std::vector<std::string>& build = r->fmt_parts;
+        int nt = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
+        nt = std::max(1, std::min(nt, std::max(1, n / 64)));
+        auto work = [&](int lo, int hi) {
+            for (int t = lo; t < hi; ++t)
+                format_rows_of(r, t, db_name, std::string(names + name_off[t], (size_t)(name_off[t + 1] - name_off[t])), build[t]);
+        };
+        if (nt == 1) work(0, n);
+        else {
+            std::vector<std::thread> pool;
+            for (int i = 0; i < nt; ++i) pool.emplace_back(work, (int)((int64_t)n * i / nt), (int)((int64_t)n * (i + 1) / nt));
+            for (auto& th : pool) th.join();
+        }
+        r->fmt_key.swap(key);
     }
+    const std::vector<std::string>& parts = r->fmt_parts;
     int64_t need = 0;
     for (auto& p : parts) need += (int64_t)p.size();
     if (buf && need < buf_len) {

@@ -119,7 +119,7 @@ class Table:
         blob = "".join(sequences).encode("ascii")
         off = np.zeros(len(sequences) + 1, dtype=np.int64)
         if sequences:
-            np.cumsum([len(s) for s in sequences], out=off[1:])
+            np.cumsum(np.fromiter((len(s) for s in sequences), dtype=np.int64, count=len(sequences)), out=off[1:])
         return blob, off
 
     def find_batch(self, sequences, count=5, ratio=0.05, steps=500, branchs=10, nodes=10000, extra_nodes=0,
@@ -305,18 +305,24 @@ class BatchResult:
         lib().km_result_format_target(self._h, int(t), db_name.encode(), query_name.encode(), buf, int(need) + 1)
         return buf.raw[:int(need)].decode("ascii")
 
-    def format_all(self, db_name, names, threads=0):
-        """Sorted TSV text of every target, in target order, formatted on host threads."""
+    def format_all(self, db_name, names, threads=0, as_bytes=False):
+        """Sorted TSV text of every target, in target order, formatted on host threads.
+        as_bytes=True returns a uint8 numpy array (no extra copies of a multi-megabyte text)."""
         blob = "".join(names).encode()
         off = np.zeros(len(names) + 1, dtype=np.int64)
         if names:
-            np.cumsum([len(x.encode()) for x in names], out=off[1:])
+            np.cumsum(np.fromiter((len(x) for x in names), dtype=np.int64, count=len(names)), out=off[1:])
+            if off[-1] != len(blob):          # non-ASCII names: fall back to byte lengths
+                np.cumsum([len(x.encode()) for x in names], out=off[1:])
         need = lib().km_result_format_all(self._h, db_name.encode(), blob, off.ctypes.data, int(threads), None, 0)
         if need < 0:
             check(int(need))
-        buf = ctypes.create_string_buffer(int(need) + 1)
-        lib().km_result_format_all(self._h, db_name.encode(), blob, off.ctypes.data, int(threads), buf, int(need) + 1)
-        return buf.raw[:int(need)].decode("ascii")
+        buf = np.empty(int(need) + 1, dtype=np.uint8)
+        lib().km_result_format_all(self._h, db_name.encode(), blob, off.ctypes.data, int(threads), buf.ctypes.data,
+                                   int(need) + 1)
+        if as_bytes:
+            return buf[:int(need)]
+        return buf[:int(need)].tobytes().decode("ascii")
 
     def close(self):
         if getattr(self, "_h", None):

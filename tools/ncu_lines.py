@@ -37,14 +37,20 @@ def main():
         m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*);", ln)
         if m and cur:
             line_of[int(m.group(1), 16)] = (cur, m.group(2).strip())
-    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + ncu_name], capture_output=True,
-                         text=True).stdout
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.split("\n")))
     hdr = None
     base = None
     per_line, per_ins = {}, []
     total = 0
+    wanted = False
     for r in rows:
+        if r and r[0] == "Kernel Name":
+            wanted = ncu_name in r[1]
+            hdr = None
+            continue
+        if not wanted:
+            continue
         if r and r[0] == "Address":
             hdr = r
             base = None
