@@ -185,6 +185,8 @@ int64_t km_result_format_all(const km_result* r, const char* db_name, const char
                              int32_t threads, char* buf, int64_t buf_len);
 
 /* ---- measurement helpers (bench.py) --------------------------------------------------- */
+/* per-phase SM cycles of the graph pass (only in a -DKM_PHASE_TIMERS build; tools/phase_times.py) */
+int km_debug_phase_cycles(unsigned long long* out32, int reset);
 /* random 32-byte-sector gather over `bytes` of HBM: the ceiling for hash probes */
 int km_bench_random_gather(int device, uint64_t bytes, uint64_t n_loads, int iters, float* best_ms);
 /* device-resident lookup benchmark: n queries (config-4 mix) generated on device, timed `iters` times */

@@ -23,6 +23,9 @@ def _stale():
 
 
 def build(force=False, verbose=False):
+    if os.environ.get("KM_PHASE_TIMERS") and "-DKM_PHASE_TIMERS" not in NVCC_FLAGS:
+        NVCC_FLAGS.append("-DKM_PHASE_TIMERS")
+        force = True
     if not force and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

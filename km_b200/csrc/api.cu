@@ -872,6 +872,17 @@ extern "C" int64_t km_result_format_all(const km_result* r, const char* db_name,
 }
 
 // ---- measurement helpers ---------------------------------------------------------------------------
+extern "C" int km_debug_phase_cycles(unsigned long long* out32, int reset) {
+#ifdef KM_PHASE_TIMERS
+    if (out32) CU(cudaMemcpyFromSymbol(out32, km_phase_cycles, 32 * sizeof(unsigned long long)));
+    if (reset) { unsigned long long z[32] = {0}; CU(cudaMemcpyToSymbol(km_phase_cycles, z, sizeof(z))); }
+    return 0;
+#else
+    (void)out32; (void)reset;
+    return fail(KM_E_ARG, "library built without KM_PHASE_TIMERS");
+#endif
+}
+
 extern "C" int km_bench_random_gather(int device, uint64_t bytes, uint64_t n_loads, int iters, float* best_ms) {
     if (!best_ms || bytes < 64 || iters < 1) return fail(KM_E_ARG, "km_bench_random_gather: bad argument");
     if (km_device_count() <= 0) return fail(KM_E_NOGPU, "no CUDA device");

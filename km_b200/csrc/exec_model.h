@@ -21,6 +21,29 @@
 
 namespace km {
 
+// Phase timer (measurement only): lane 0 of each CTA adds the SM cycles it spent between marks to
+// a global table, read back by km_debug_phase_cycles.  Compiled in when KM_PHASE_TIMERS is defined.
+#if KM_DEVICE_BUILD && defined(KM_PHASE_TIMERS)
+__device__ unsigned long long km_phase_cycles[32];
+struct PhaseTimer {
+    long long t0;
+    __device__ __forceinline__ PhaseTimer() {
+#ifdef __CUDA_ARCH__
+        t0 = clock64();
+#endif
+    }
+    __device__ __forceinline__ void mark(int phase) {
+#ifdef __CUDA_ARCH__
+        if (threadIdx.x == 0) { const long long t1 = clock64(); atomicAdd(&km_phase_cycles[phase], (unsigned long long)(t1 - t0)); t0 = t1; }
+#endif
+    }
+};
+#else
+struct PhaseTimer {
+    KM_HD void mark(int) {}
+};
+#endif
+
 #if KM_DEVICE_BUILD
 // One CTA works on one target.
 struct CtaCtx {

@@ -222,6 +222,7 @@ KM_HD bool graph_target(const Ctx& ctx, const TableView& T, const WalkView& W, c
     const int n_all = W.n_nodes[t] < g.cap ? W.n_nodes[t] : g.cap;
     const int L = g.L;
 
+    PhaseTimer pt;
     // ---- canonical numbering -------------------------------------------------
     if (tid == 0) sh[0] = 0;
     ctx.sync();
@@ -256,6 +257,7 @@ KM_HD bool graph_target(const Ctx& ctx, const TableView& T, const WalkView& W, c
     if (tid == 0) R.t_n[t] = d.N;
     ctx.sync();
 
+    pt.mark(0);
     // ---- adjacency (MutationFinder.py:515-531) --------------------------------
     const int n_real = d.N - 2;
     for (int e = tid; e < 4 * n_real; e += nt) {
@@ -277,6 +279,7 @@ KM_HD bool graph_target(const Ctx& ctx, const TableView& T, const WalkView& W, c
     }
     ctx.sync();
 
+    pt.mark(1);
     // ---- two shortest-path trees (Graph.py:175-176), concurrently on two warps ------
     {
         const int lane_b = nt > 32 ? 32 : 0;                 // the backward pass's lane
@@ -284,6 +287,7 @@ KM_HD bool graph_target(const Ctx& ctx, const TableView& T, const WalkView& W, c
         if (tid == lane_b) shortest_tree(S, d, false, S.dist2, S.after, S.cand2);
     }
     ctx.sync();
+    pt.mark(2);
     if (tid == 0) {
         // ---- strip the reference chain (Graph.py:178-198) ----------------------
         // the only out-edge of the source cap goes to node 0, so node 0 is the one start whose
@@ -308,6 +312,7 @@ KM_HD bool graph_target(const Ctx& ctx, const TableView& T, const WalkView& W, c
     }
     ctx.sync();
 
+    pt.mark(3);
     // ---- candidate edges (Graph.py:220-240) -----------------------------------
     // Edge (a, b) of the remaining edge_set yields the path src..a (forward tree) + b..snk
     // (backward tree) iff a is reachable from the source and b reaches the sink.  The reference
@@ -357,6 +362,7 @@ KM_HD bool graph_target(const Ctx& ctx, const TableView& T, const WalkView& W, c
     }
     ctx.sync();
 
+    pt.mark(4);
     // ---- allocate path ids and pool space (lane 0) ---------------------------------------
     if (tid == 0) {
         int nu = n_cand;
@@ -389,6 +395,7 @@ KM_HD bool graph_target(const Ctx& ctx, const TableView& T, const WalkView& W, c
     const int nu = sh[2], first = sh[3];
     if (nu < 0) return false;
 
+    pt.mark(5);
     // ---- materialise: one lane per unique path walks its two chains ------------------
     for (int u = tid; u < nu; u += nt) {
         const int c = S.upath[u];
@@ -402,6 +409,7 @@ KM_HD bool graph_target(const Ctx& ctx, const TableView& T, const WalkView& W, c
     }
     ctx.sync();
 
+    pt.mark(6);
     // ---- lexicographic order (sorted(set of tuples)): rank by pairwise CTA-parallel compares ----
     if (nu > 1) {
         int* slot = sh + 8;
@@ -438,6 +446,7 @@ KM_HD bool graph_target(const Ctx& ctx, const TableView& T, const WalkView& W, c
         }
     }
     ctx.sync();
+    pt.mark(7);
     return sh[2] >= 0;
 }
 

@@ -226,6 +226,7 @@ __global__ void __launch_bounds__(KM_CTA) km_graph_kernel(TableView T, WalkView 
         GraphDims d;
         if (!graph_target(ctx, T, W, S, R, t, &d, sh)) continue;
         const int n_paths = sh[2], first = sh[3];
+        PhaseTimer pt;
         // spell every unique path once (MutationFinder.get_seq, :375-403): first k-mer, then
         // the last base of each following node; rows print slices of these strings
         const int64_t nbase = W.node_off[t];
@@ -253,6 +254,7 @@ __global__ void __launch_bounds__(KM_CTA) km_graph_kernel(TableView T, WalkView 
             }
         }
         __syncthreads();
+        pt.mark(8);
         emit_rows(ctx, T, W, S, R, t, d, n_paths, first, sh);
         __syncthreads();
     }

@@ -237,6 +237,7 @@ KM_HD void emit_rows(const Ctx& ctx, const TableView& T, const WalkView& W, cons
     int* slot = sh + 8;                              // reduction scratch (sh holds 16 ints)
     const PathView ref = {nullptr, 0, d.L};
 
+    PhaseTimer pt;
     // ---- per-path diffs against the whole reference (CTA-parallel scans) ---------
     for (int p = 0; p < n_paths; ++p) {
         const PathView alt = {R.pool + R.path_off[first_path + p], 0, R.path_len[first_path + p]};
@@ -249,6 +250,7 @@ KM_HD void emit_rows(const Ctx& ctx, const TableView& T, const WalkView& W, cons
     }
     ctx.sync();
 
+    pt.mark(10);
     // ---- cluster discovery by lane 0 (MutationFinder.py:656-694) ---------------
     // grp[p] = cluster id | (join order << 16), -1 = none; clusters are numbered in seed order
     if (tid == 0) {
@@ -304,13 +306,17 @@ KM_HD void emit_rows(const Ctx& ctx, const TableView& T, const WalkView& W, cons
     int32_t* crec = S.grp + S.max_paths;
     PathView* cols = S.cols;
 
+    pt.mark(11);
     // ---- vs_ref rows (MutationFinder.py:613-648) -------------------------------
     for (int p = 0; p < n_paths; ++p) {
         const PathView alt = {R.pool + R.path_off[first_path + p], 0, R.path_len[first_path + p]};
         if (tid == 0) { cols[0] = alt; cols[1] = ref; }
         ctx.sync();
+        pt.mark(12);
         const int iters = solve_columns(ctx, S, counts, d.N, cols, 2, coef, rvaf, sh);
+        pt.mark(14);
         const int64_t mc = min_count(ctx, counts, alt, slot);
+        pt.mark(15);
         if (tid == 0) {
             const Diff df = {S.pdiff[4 * p], S.pdiff[4 * p + 1], S.pdiff[4 * p + 2], S.pdiff[4 * p + 3]};
             int dl, il;
@@ -341,6 +347,7 @@ KM_HD void emit_rows(const Ctx& ctx, const TableView& T, const WalkView& W, cons
         ctx.sync();
     }
 
+    pt.mark(12);
     // ---- cluster rows (MutationFinder.py:700-723, 758-811) ----------------------
     int row_cursor = first_row + n_paths;
     for (int c = 0; c < n_clusters; ++c) {
@@ -410,6 +417,7 @@ KM_HD void emit_rows(const Ctx& ctx, const TableView& T, const WalkView& W, cons
         ctx.sync();
         row_cursor += size;
     }
+    pt.mark(13);
 }
 
 }  // namespace km

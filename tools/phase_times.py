@@ -1,0 +1,38 @@
+"""Per-phase SM cycles of the graph pass (build with KM_PHASE_TIMERS=1).  Run on a GPU box:
+    KM_PHASE_TIMERS=1 python tools/phase_times.py [n_targets]"""
+import ctypes
+import os
+import sys
+
+os.environ["KM_PHASE_TIMERS"] = "1"
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from km_b200 import build as kb     # noqa: E402
+kb.build(force=True)
+from km_b200 import engine, synth   # noqa: E402
+from km_b200._lib import lib        # noqa: E402
+
+NAMES = {0: "numbering", 1: "adjacency", 2: "shortest trees", 3: "strip chain", 4: "candidates", 5: "alloc",
+         6: "materialise", 7: "sort paths", 8: "spell", 10: "diffs", 11: "clusters", 12: "vs_ref setup / cluster rows",
+         13: "cluster rows tail", 14: "solve_columns", 15: "min_count"}
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 10000
+panel = synth.make_panel(n, seed=synth.PANEL_SEED)
+t = engine.Table.create(capacity=50_000_000 + len(panel.keys))
+t.build_synthetic(synth.TABLE_SEED, 50_000_000)
+t.insert(panel.keys, panel.counts)
+plan = t.plan(panel.targets)
+for _ in range(3):
+    plan.launch()
+plan.last_ms()
+L = lib()
+L.km_debug_phase_cycles.argtypes = [ctypes.c_void_p, ctypes.c_int]
+buf = (ctypes.c_ulonglong * 32)()
+L.km_debug_phase_cycles(buf, 1)
+plan.launch()
+w, g = plan.last_ms()
+L.km_debug_phase_cycles(buf, 0)
+tot = sum(buf)
+print("walk %.3f ms  graph %.3f ms   targets %d" % (w, g, n))
+for i, c in enumerate(buf):
+    if c:
+        print("%2d %-28s %8.1f cycles/target  %5.1f%%" % (i, NAMES.get(i, "?"), c / n, 100.0 * c / tot))
+print("sum %.0f cycles/target" % (tot / n))
