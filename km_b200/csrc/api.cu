@@ -119,7 +119,7 @@ extern "C" int km_table_create(int device, int k, int canonical, uint64_t capaci
     t->pin.host = true;
     t->pin_find.host = true;
     CU(cudaFuncSetAttribute(km_graph_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)make_layout(KM_SMALL_NODES - 2, KM_SMALL_CAND, KM_SMALL_PATHS, KM_SMALL_COLS).stride));
+                            (int)small_layout().stride));
     km_table_clear_kernel<<<t->sm_count * 8, 256, 0, t->stream>>>(t->buckets, t->n_buckets);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(t->stream));
@@ -445,7 +445,7 @@ static int plan_layout(km_plan* p) {
     const int64_t n_node = p->n_node = p->node_off[n], n_hash = p->n_hash = p->hash_off[n], n_code = p->n_code = p->seq_off[n];
     p->grid_graph = std::max(1, std::min(n, t->sm_count * 8));
     p->grid_large = std::max(1, std::min(n, t->sm_count * 2));
-    const ScratchLayout L0 = make_layout(maxcap, KM_MAX_PATHS, KM_MAX_PATHS, KM_MAX_COLS);
+    const ScratchLayout L0 = make_layout(maxcap, KM_MAX_PATHS, KM_MAX_PATHS, KM_MAX_COLS, 0);
     const int32_t path_cap = p->path_cap, row_cap = p->row_cap;
     const int64_t pool_cap = p->pool_cap, seq_cap = p->seq_cap;
 
@@ -525,7 +525,7 @@ static int plan_launch(km_plan* p, cudaStream_t s) {
     CU(cudaGetLastError());
     CU(cudaEventRecord(t->ev[2], s));
     // shared-memory pass first, then the general pass for large or deferred targets
-    const size_t small_smem = make_layout(KM_SMALL_NODES - 2, KM_SMALL_CAND, KM_SMALL_PATHS, KM_SMALL_COLS).stride;
+    const size_t small_smem = small_layout().stride;
     km_graph_kernel<true><<<p->grid_graph, KM_CTA, small_smem, s>>>(t->view(), p->W, p->SL, p->R, p->d_seq_pool,
                                                                      p->d_path_seq_off, p->seq_cap);
     CU(cudaGetLastError());

@@ -11,9 +11,11 @@
 
 #if defined(__CUDACC__)
 #define KM_HD __device__ __forceinline__
+#define KM_HOSTDEV __host__ __device__ inline
 #define KM_DEVICE_BUILD 1
 #else
 #define KM_HD static inline
+#define KM_HOSTDEV static inline
 #define KM_HOST_EMU 1
 #include <cmath>
 #include <cstring>
@@ -51,6 +53,7 @@ struct CtaCtx {
     KM_HD int nt() const { return blockDim.x; }
     KM_HD void sync() const { __syncthreads(); }
     KM_HD int sync_or(int p) const { return __syncthreads_or(p); }
+    KM_HD int sync_and(int p) const { return __syncthreads_and(p); }
 };
 // One warp works on one target (the walk: most of its life a target has one or two live lanes, so
 // a warp per target keeps 4x more targets in flight per SM than a CTA per target).
@@ -59,7 +62,16 @@ struct WarpCtx {
     KM_HD int nt() const { return 32; }
     KM_HD void sync() const { __syncwarp(); }
     KM_HD int sync_or(int p) const { return __any_sync(0xFFFFFFFFu, p); }
+    KM_HD int sync_and(int p) const { return __all_sync(0xFFFFFFFFu, p); }
 };
+// Sum over the lanes of the calling warp (all 32 lanes must call); the total is valid on the lane
+// for which warp_leader() is true.  Used to turn one atomic per lane into one per warp.
+KM_HD unsigned long long warp_sum64(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, o);
+    return v;
+}
+KM_HD bool warp_leader() { return (threadIdx.x & 31) == 0; }
 KM_HD uint64_t atomic_cas64(uint64_t* p, uint64_t cmp, uint64_t val) {
     return atomicCAS(reinterpret_cast<unsigned long long*>(p), (unsigned long long)cmp, (unsigned long long)val);
 }
@@ -82,8 +94,11 @@ struct CtaCtx {
     int nt() const { return 1; }
     void sync() const {}
     int sync_or(int p) const { return p; }
+    int sync_and(int p) const { return p; }
 };
 typedef CtaCtx WarpCtx;
+KM_HD unsigned long long warp_sum64(unsigned long long v) { return v; }
+KM_HD bool warp_leader() { return true; }
 KM_HD uint64_t atomic_cas64(uint64_t* p, uint64_t cmp, uint64_t val) { uint64_t o = *p; if (o == cmp) *p = val; return o; }
 KM_HD uint32_t atomic_add32(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
 KM_HD int32_t atomic_addi32(int32_t* p, int32_t v) { int32_t o = *p; *p = o + v; return o; }

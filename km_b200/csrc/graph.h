@@ -74,20 +74,28 @@ struct ResultView {
     unsigned long long* used;
 };
 
-// Per-CTA scratch in HBM (L2 resident in practice), sized for the largest target.
+// Per-target working set of the CTA: shared memory in the small pass, per-CTA HBM scratch
+// (L2 resident in practice) in the general pass.  Arrays whose lifetimes do not overlap share
+// storage in the compact (shared-memory) layout -- see make_layout.
 struct GraphScratch {
-    int32_t* newidx;   // [maxcap]   discovery index -> canonical index, -1 dropped
-    int32_t* kept;     // [maxcap]   discovery indices of kept novel nodes
+    int32_t* newidx;   // [maxN]     discovery index -> canonical index, -1 dropped; later nxtB
+    int32_t* kept;     // [maxcap]   discovery indices of kept novel nodes          (numbering only)
+    uint64_t* keptk;   // [maxcap]   their packed k-mers                             (numbering only)
+    uint64_t* hk;      // [hcap]     k-mer -> canonical index map of this target's nodes (adjacency only)
+    int32_t* hv;       // [hcap]
     int32_t* succ;     // [4*maxN]
     int32_t* pred;     // [4*maxN]
+    uint8_t* deg;      // [maxN]  out-degree | in-degree << 4, cap edges included
     float* dist;       // [maxN]  distance from the source cap (+inf = unreachable)
     float* dist2;      // [maxN]  distance to the sink cap
     int32_t* before;   // [maxN]
     int32_t* after;    // [maxN]
+    int32_t* hopF;     // [maxN]  edges between the source cap and the node along `before`
+    int32_t* hopB;     // [maxN]  edges between the node and the sink cap along `after`
     int32_t* cand;     // [maxN]  open set of the forward pass
     int32_t* cand2;    // [maxN]  open set of the backward pass
     uint8_t* eflag;    // [maxN]  bit c: edge to succ[c] still in edge_set; bit 4: cap edge
-    int32_t* occ;      // [maxN]
+    int32_t* occ;      // [maxN]  nxtF during the tree phase, then occurrence counts of the solver
     int32_t* ce_a;     // [max_cand] edges that each yield one distinct alternative path
     int32_t* ce_b;
     int32_t* ce_len;
@@ -101,25 +109,93 @@ struct GraphScratch {
     PathView* cols;    // [max_cols] columns of the current least-squares problem
     int32_t* members;  // [max_cols]
     int maxN;
+    int hcap;          // capacity of hk/hv (a power of two >= 2*maxN)
     int max_cand;      // capacity of the ce_* arrays
     int max_paths;
     int max_cols;
     int retry;         // 1: exceeding a capacity defers the target to the general pass
 };
 
+// The one place that knows the scratch layout (host sizing, device carving and the CPU emulation
+// all use it).  compact = 1 (the shared-memory pass) overlays arrays with disjoint lifetimes:
+//   kept  -> cand, keptk -> succ          numbering ends before either is written
+//   hk,hv -> dist .. cand2                the adjacency map dies before the trees are initialised
+//   hopF,hopB -> pdiff .. acc             hop counts die when the paths are materialised
+// Each overlay is used only when it fits; otherwise the array gets storage of its own.
+struct ScratchLayout {
+    char* base;
+    size_t stride;          // bytes per CTA
+    size_t o_newidx, o_kept, o_keptk, o_hk, o_hv, o_succ, o_pred, o_deg, o_dist, o_dist2, o_before, o_after, o_hopF, o_hopB,
+        o_cand, o_cand2, o_eflag, o_occ;
+    size_t o_ce_a, o_ce_b, o_ce_len, o_upath, o_pdiff, o_grp, o_G, o_V, o_vec, o_acc, o_cols, o_members;
+    int maxN, hcap, max_cand, max_paths, max_cols;
+};
+
+KM_HOSTDEV ScratchLayout make_layout(int maxcap, int max_cand, int max_paths, int max_cols, int compact) {
+    ScratchLayout L = {};
+    const size_t maxN = (size_t)maxcap + 2, nce = (size_t)max_cand, np = (size_t)max_paths, nc = (size_t)max_cols;
+    size_t hcap = 64;
+    while (hcap < 2 * maxN) hcap <<= 1;
+    size_t o = 0;
+    auto put = [&](size_t bytes) { size_t at = o; o = (o + bytes + 15) / 16 * 16; return at; };
+    L.o_newidx = put(4 * maxN);
+    L.o_succ = put(16 * maxN); L.o_pred = put(16 * maxN); L.o_deg = put(maxN);
+    L.o_dist = put(4 * maxN); L.o_dist2 = put(4 * maxN); L.o_before = put(4 * maxN); L.o_after = put(4 * maxN);
+    L.o_cand = put(4 * maxN); L.o_cand2 = put(4 * maxN);
+    const size_t tree_end = o;
+    L.o_eflag = put(maxN); L.o_occ = put(4 * maxN);
+    L.o_ce_a = put(4 * nce); L.o_ce_b = put(4 * nce); L.o_ce_len = put(4 * nce);
+    L.o_upath = put(4 * np);
+    L.o_pdiff = put(16 * np); L.o_grp = put(20 * np);
+    L.o_G = put(8 * nc * nc); L.o_V = put(16 * nc * nc); L.o_vec = put(64 * nc);
+    L.o_acc = put(8 * (nc * nc + nc));
+    const size_t quant_end = o;
+    L.o_cols = put(sizeof(PathView) * nc); L.o_members = put(4 * nc);
+    if (compact) { L.o_kept = L.o_cand; L.o_keptk = L.o_succ; }
+    else { L.o_kept = put(4 * maxN); L.o_keptk = put(8 * maxN); }
+    if (compact && 12 * hcap <= tree_end - L.o_dist) { L.o_hk = L.o_dist; L.o_hv = L.o_dist + 8 * hcap; }
+    else { L.o_hk = put(8 * hcap); L.o_hv = put(4 * hcap); }
+    if (compact && 8 * maxN + 16 <= quant_end - L.o_pdiff) { L.o_hopF = L.o_pdiff; L.o_hopB = L.o_pdiff + (4 * maxN + 15) / 16 * 16; }
+    else { L.o_hopF = put(4 * maxN); L.o_hopB = put(4 * maxN); }
+    L.stride = (o + 255) / 256 * 256;
+    L.maxN = (int)maxN; L.hcap = (int)hcap; L.max_cand = max_cand; L.max_paths = max_paths; L.max_cols = max_cols;
+    return L;
+}
+
+KM_HOSTDEV GraphScratch carve(const ScratchLayout& L, char* p, int retry) {
+    GraphScratch S;
+    S.newidx = (int32_t*)(p + L.o_newidx); S.kept = (int32_t*)(p + L.o_kept); S.keptk = (uint64_t*)(p + L.o_keptk);
+    S.hk = (uint64_t*)(p + L.o_hk); S.hv = (int32_t*)(p + L.o_hv);
+    S.succ = (int32_t*)(p + L.o_succ); S.pred = (int32_t*)(p + L.o_pred); S.deg = (uint8_t*)(p + L.o_deg);
+    S.dist = (float*)(p + L.o_dist); S.dist2 = (float*)(p + L.o_dist2);
+    S.before = (int32_t*)(p + L.o_before); S.after = (int32_t*)(p + L.o_after);
+    S.hopF = (int32_t*)(p + L.o_hopF); S.hopB = (int32_t*)(p + L.o_hopB);
+    S.cand = (int32_t*)(p + L.o_cand); S.cand2 = (int32_t*)(p + L.o_cand2); S.eflag = (uint8_t*)(p + L.o_eflag);
+    S.occ = (int32_t*)(p + L.o_occ);
+    S.ce_a = (int32_t*)(p + L.o_ce_a); S.ce_b = (int32_t*)(p + L.o_ce_b); S.ce_len = (int32_t*)(p + L.o_ce_len);
+    S.upath = (int32_t*)(p + L.o_upath); S.pdiff = (int32_t*)(p + L.o_pdiff); S.grp = (int32_t*)(p + L.o_grp);
+    S.G = (double*)(p + L.o_G); S.V = (double*)(p + L.o_V); S.vec = (double*)(p + L.o_vec);
+    S.acc = (unsigned long long*)(p + L.o_acc);
+    S.cols = (PathView*)(p + L.o_cols); S.members = (int32_t*)(p + L.o_members);
+    S.maxN = L.maxN; S.hcap = L.hcap; S.max_cand = L.max_cand; S.max_paths = L.max_paths; S.max_cols = L.max_cols; S.retry = retry;
+    return S;
+}
+
 #define KM_REF_W 0.01f
 #define KM_ALT_W 1.0f
+#define KM_NXT_REF 0x40000000          // nxt entry: the edge carries the reference weight
+#define KM_NXT_MASK 0x3FFFFFFF
 
 struct GraphDims {
     int L, N, src, snk;
 };
 
 // weight of edge i -> j (MutationFinder.py:512, 535-551)
-KM_HD float edge_weight(const GraphDims& d, int i, int j) {
-    if (i == d.src || j == d.snk) return KM_REF_W;
-    if (i < d.L - 1 && j == i + 1) return KM_REF_W;
-    return KM_ALT_W;
+KM_HD bool edge_is_ref(const GraphDims& d, int i, int j) {
+    return i == d.src || j == d.snk || (i < d.L - 1 && j == i + 1);
 }
+
+struct alignas(16) Slot4 { int32_t v[4]; };
 
 // Out-neighbours of u in the forward graph: up to 4 overlap successors + the cap edges.
 // Calls f(j, slot) with slot 0..3 for overlap edges and 4 for the cap edge.
@@ -127,47 +203,65 @@ template <class F>
 KM_HD void for_each_succ(const GraphScratch& S, const GraphDims& d, int u, F f) {
     if (u == d.src) { f(0, 4); return; }
     if (u == d.snk) return;
-    for (int c = 0; c < 4; ++c) {
-        const int j = S.succ[4 * u + c];
-        if (j >= 0) f(j, c);
-    }
+    const Slot4 s4 = *reinterpret_cast<const Slot4*>(S.succ + 4 * u);
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+        if (s4.v[c] >= 0) f(s4.v[c], c);
     if (u == d.L - 1) f(d.snk, 4);
 }
 
-template <class F>
-KM_HD void for_each_pred(const GraphScratch& S, const GraphDims& d, int u, F f) {
-    if (u == d.snk) { f(d.L - 1); return; }
-    if (u == d.src) return;
-    for (int c = 0; c < 4; ++c) {
-        const int j = S.pred[4 * u + c];
-        if (j >= 0) f(j);
+// k-mer -> canonical node index of this target (adjacency phase only)
+KM_HD uint32_t node_hash(uint64_t key) { return (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 37); }
+
+KM_HD int node_find(const GraphScratch& S, uint32_t hmask, uint64_t key) {
+    uint32_t s = node_hash(key) & hmask;
+    for (;;) {
+        const uint64_t cur = S.hk[s];
+        if (cur == key) return S.hv[s];
+        if (cur == KM_EMPTY_KEY) return -1;
+        s = (s + 1) & hmask;
     }
-    if (u == 0) f(d.src);
 }
 
 // Graph._get_paths (Graph.py:63-119) on adjacency lists; `forward` walks w, otherwise w
-// transposed.  Sequential by nature -- every distance is the float32 sum of its parent's distance
-// and one weight -- so it runs on ONE lane, and the loop is kept to two dependent shared-memory
-// round trips per settled node: the 4 neighbour slots come in with one 16-byte load, the current
-// node and its distance live in registers, "unseen" is dist == +inf (no state array), and the
-// open set is an explicit list that almost always holds a single node.
+// transposed.  Every distance is the float32 sum of its parent's distance and one weight, so the
+// pass is sequential and runs on ONE lane.  Two things keep the chain short:
+//   * nxt[u] >= 0 marks a node whose only out-edge leads to a node with no other in-edge.  If that
+//     successor's distance is strictly below every open node's, it is the next node the reference
+//     would settle (Graph.py:113-114), nothing else changes, and the lane moves on after one
+//     dependent load -- almost every node of a target graph is of this kind.
+//   * otherwise the general step: the 4 neighbour slots come in with one 16-byte load, "unseen" is
+//     dist == +inf, and the open set is an explicit list that rarely holds more than two nodes.
+// Settling order = ascending (distance, index) and a node is re-parented only on a strictly smaller
+// float32 sum (Graph.py:103), exactly as in the reference.
 // dist/prev must be pre-filled with +inf / -1.
-struct alignas(16) Slot4 { int32_t v[4]; };
-
-KM_HD void shortest_tree(const GraphScratch& S, const GraphDims& d, bool forward, float* dist, int32_t* prev,
-                         int32_t* cand) {
+KM_HD void shortest_tree(const GraphScratch& S, const GraphDims& d, bool forward, float* dist, int32_t* prev, int32_t* hop,
+                         int32_t* cand, const int32_t* nxt) {
     const int32_t* nbr = forward ? S.succ : S.pred;
     int nc = 0;
     int u = forward ? d.src : d.snk;
-    float du = 0.0f;
+    int hu = 0;
+    float du = 0.0f, open_min = INFINITY;
     dist[u] = 0.0f;
+    hop[u] = 0;
     for (;;) {
+        const int x = nxt[u];
+        if (x >= 0) {
+            const float trial = add_f32((x & KM_NXT_REF) ? KM_REF_W : KM_ALT_W, du);
+            if (trial < open_min) {
+                const int j = x & KM_NXT_MASK;
+                dist[j] = trial; prev[j] = u; hop[j] = ++hu;
+                u = j; du = trial;
+                continue;
+            }
+        }
         auto relax = [&](int j, float w) {
             const float trial = add_f32(w, du);              // w[i, :] + dist[i] in float32 (:93)
             const float old = dist[j];
             if (trial < old) {                               // strict (:103)
                 dist[j] = trial;
                 prev[j] = u;
+                hop[j] = hu + 1;
                 if (old == INFINITY) cand[nc++] = j;         // first time seen -> joins the open set
             }
         };
@@ -205,7 +299,10 @@ KM_HD void shortest_tree(const GraphScratch& S, const GraphDims& d, bool forward
         }
         u = cand[best];
         du = db;
+        hu = hop[u];
         cand[best] = cand[--nc];
+        open_min = INFINITY;
+        for (int c = 0; c < nc; ++c) { const float da = dist[cand[c]]; open_min = da < open_min ? da : open_min; }
     }
 }
 
@@ -226,56 +323,94 @@ KM_HD bool graph_target(const Ctx& ctx, const TableView& T, const WalkView& W, c
     // ---- canonical numbering -------------------------------------------------
     if (tid == 0) sh[0] = 0;
     ctx.sync();
-    for (int q = tid; q < n_all; q += nt) {
-        if (q < L) { S.newidx[q] = q; continue; }
+    for (int q = L + tid; q < n_all; q += nt) {
         S.newidx[q] = -1;
         if (W.hflag[g.hbase + W.node_slot[g.nbase + q]]) {
             const int pos = atomic_addi32(&sh[0], 1);
             S.kept[pos] = q;
+            S.keptk[pos] = W.node_kmer[g.nbase + q];
         }
     }
     ctx.sync();
     const int nk = sh[0];
     // rank kept novel nodes by packed k-mer value (all distinct)
     for (int a = tid; a < nk; a += nt) {
-        const uint64_t ka = W.node_kmer[g.nbase + S.kept[a]];
+        const uint64_t ka = S.keptk[a];
         int rank = 0;
-        for (int b = 0; b < nk; ++b) rank += W.node_kmer[g.nbase + S.kept[b]] < ka ? 1 : 0;
+        for (int b = 0; b < nk; ++b) rank += S.keptk[b] < ka ? 1 : 0;
         S.newidx[S.kept[a]] = L + rank;
     }
-    ctx.sync();
     GraphDims d;
     d.L = L; d.N = L + nk + 2; d.src = d.N - 2; d.snk = d.N - 1;
     *dims_out = d;
-    for (int q = tid; q < n_all; q += nt) {
-        const int i = S.newidx[q];
-        if (i >= 0) {
-            R.out_kmer[g.nbase + i] = W.node_kmer[g.nbase + q];
-            R.out_count[g.nbase + i] = W.node_count[g.nbase + q];
-        }
-    }
+    const int n_real = d.N - 2;
+    uint32_t hmask = 63;
+    while (hmask + 1 < 2u * (uint32_t)n_real) hmask = 2 * hmask + 1;
+    ctx.sync();                                       // kept / keptk are dead from here on
+    for (uint32_t s = tid; s <= hmask; s += nt) S.hk[s] = KM_EMPTY_KEY;
     if (tid == 0) R.t_n[t] = d.N;
+    ctx.sync();
+    // canonical node arrays (what the host sees) + the k-mer -> index map used for the edges
+    for (int q = tid; q < n_all; q += nt) {
+        const int i = q < L ? q : S.newidx[q];
+        if (i < 0) continue;
+        const uint64_t km = W.node_kmer[g.nbase + q];
+        R.out_kmer[g.nbase + i] = km;
+        R.out_count[g.nbase + i] = W.node_count[g.nbase + q];
+        uint32_t s = node_hash(km) & hmask;
+        while (atomic_cas64(&S.hk[s], KM_EMPTY_KEY, km) != KM_EMPTY_KEY) s = (s + 1) & hmask;   // keys are distinct
+        S.hv[s] = i;
+    }
     ctx.sync();
 
     pt.mark(0);
-    // ---- adjacency (MutationFinder.py:515-531) --------------------------------
-    const int n_real = d.N - 2;
-    for (int e = tid; e < 4 * n_real; e += nt) {
-        const int i = e >> 2, c = e & 3;
+    // ---- adjacency (MutationFinder.py:515-531): edge i -> j iff kmer[i][1:] == kmer[j][:-1], i != j ------
+    for (int i = tid; i < n_real; i += nt) {
         const uint64_t km = R.out_kmer[g.nbase + i];
-        int js = -1, jp = -1;
-        uint32_t s = visited_find(W, g, succ_kmer(km, c, T.kmask));
-        if (s != KM_NO_SLOT && W.hflag[g.hbase + s]) js = S.newidx[W.hval[g.hbase + s]];
-        if (js == i) js = -1;                       // `if i != j` (:530)
-        s = visited_find(W, g, pred_kmer(km, c, k));
-        if (s != KM_NO_SLOT && W.hflag[g.hbase + s]) jp = S.newidx[W.hval[g.hbase + s]];
-        if (jp == i) jp = -1;
-        S.succ[e] = js;
-        S.pred[e] = jp;
+        Slot4 sv, pv;
+        int outdeg = i == L - 1 ? 1 : 0, indeg = i == 0 ? 1 : 0;          // cap edges (:545-551)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            int js = node_find(S, hmask, succ_kmer(km, c, T.kmask));
+            int jp = node_find(S, hmask, pred_kmer(km, c, k));
+            if (js == i) js = -1;                       // `if i != j` (:530)
+            if (jp == i) jp = -1;
+            sv.v[c] = js; pv.v[c] = jp;
+            outdeg += js >= 0; indeg += jp >= 0;
+        }
+        *reinterpret_cast<Slot4*>(S.succ + 4 * i) = sv;
+        *reinterpret_cast<Slot4*>(S.pred + 4 * i) = pv;
+        S.deg[i] = (uint8_t)(outdeg | (indeg << 4));
     }
+    if (tid == 0) { S.deg[d.src] = 1; S.deg[d.snk] = 1 << 4; }
+    ctx.sync();                                       // the k-mer map is dead from here on
+    // simple edges: (u, j) with u's only out-edge and j's only in-edge (see shortest_tree)
+    int32_t* nxtF = S.occ;
+    int32_t* nxtB = S.newidx;
     for (int i = tid; i < d.N; i += nt) {
         S.eflag[i] = 0x1F;
         S.dist[i] = INFINITY; S.dist2[i] = INFINITY; S.before[i] = -1; S.after[i] = -1;
+        int f = -1, b = -1;
+        if (i == d.src) { if ((S.deg[0] >> 4) == 1) f = 0 | KM_NXT_REF; }
+        else if (i == d.snk) { if ((S.deg[L - 1] & 15) == 1) b = (L - 1) | KM_NXT_REF; }
+        else {
+            const int dg = S.deg[i];
+            if ((dg & 15) == 1) {
+                int j = d.snk;                           // the cap edge unless an overlap successor exists
+                const Slot4 s4 = *reinterpret_cast<const Slot4*>(S.succ + 4 * i);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) if (s4.v[c] >= 0) j = s4.v[c];
+                if ((S.deg[j] >> 4) == 1) f = j | (edge_is_ref(d, i, j) ? KM_NXT_REF : 0);
+            }
+            if ((dg >> 4) == 1) {
+                int u = d.src;
+                const Slot4 p4 = *reinterpret_cast<const Slot4*>(S.pred + 4 * i);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) if (p4.v[c] >= 0) u = p4.v[c];
+                if ((S.deg[u] & 15) == 1) b = u | (edge_is_ref(d, u, i) ? KM_NXT_REF : 0);
+            }
+        }
+        nxtF[i] = f; nxtB[i] = b;
     }
     ctx.sync();
 
@@ -283,32 +418,49 @@ KM_HD bool graph_target(const Ctx& ctx, const TableView& T, const WalkView& W, c
     // ---- two shortest-path trees (Graph.py:175-176), concurrently on two warps ------
     {
         const int lane_b = nt > 32 ? 32 : 0;                 // the backward pass's lane
-        if (tid == 0) shortest_tree(S, d, true, S.dist, S.before, S.cand);
-        if (tid == lane_b) shortest_tree(S, d, false, S.dist2, S.after, S.cand2);
+        if (tid == 0) shortest_tree(S, d, true, S.dist, S.before, S.hopF, S.cand, nxtF);
+        if (tid == lane_b) shortest_tree(S, d, false, S.dist2, S.after, S.hopB, S.cand2, nxtB);
     }
     ctx.sync();
     pt.mark(2);
-    if (tid == 0) {
-        // ---- strip the reference chain (Graph.py:178-198) ----------------------
-        // the only out-edge of the source cap goes to node 0, so node 0 is the one start whose
-        // predecessor is the source (`np.where(before == first_node)`, :184)
+    // ---- strip the reference chain (Graph.py:178-198) ----------------------
+    // The only out-edge of the source cap goes to node 0, so node 0 is the one start whose
+    // predecessor is the source (`np.where(before == first_node)`, :184).  The walk follows
+    // `after` from it and drops edge (last_cur, cur) from the second step on (`if last_cur and`:
+    // None is falsy).  Nearly always that chain is 0,1,..,L-1,sink: checked by the whole CTA, and
+    // then every lane strips its own edges; any other shape is walked by lane 0.
+    {
+        int bad = 0;
+        for (int i = tid; i < L; i += nt) bad |= S.after[i] != (i == L - 1 ? d.snk : i + 1);
+        const bool straight = !ctx.sync_or(bad);
         if (S.before[0] == d.src) {
-            int cur = 0, last = -1;
-            for (int nxt = S.after[cur]; nxt != -1; nxt = S.after[cur]) {
-                cur = nxt;
-                if (last > 0) {                      // `if last_cur and ...`: None and 0 are falsy
-                    if (cur == d.snk) { if (last == d.L - 1) S.eflag[last] &= (uint8_t)~0x10; }
-                    else {
-                        const Slot4 s4 = *reinterpret_cast<const Slot4*>(S.succ + 4 * last);
-                        uint8_t m = 0;
-                        for (int c = 0; c < 4; ++c) if (s4.v[c] == cur) m |= (uint8_t)(1u << c);
-                        if (m) S.eflag[last] &= (uint8_t)~m;
-                    }
+            if (straight) {
+                for (int last = 1 + tid; last < L; last += nt) {
+                    if (last == L - 1) { S.eflag[last] &= (uint8_t)~0x10; continue; }
+                    const Slot4 s4 = *reinterpret_cast<const Slot4*>(S.succ + 4 * last);
+                    uint8_t m = 0;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) if (s4.v[c] == last + 1) m |= (uint8_t)(1u << c);
+                    if (m) S.eflag[last] &= (uint8_t)~m;
                 }
-                last = cur;
+            } else if (tid == 0) {
+                int cur = 0, last = -1;
+                for (int nxt = S.after[cur]; nxt != -1; nxt = S.after[cur]) {
+                    cur = nxt;
+                    if (last > 0) {                      // `if last_cur and ...`: None and 0 are falsy
+                        if (cur == d.snk) { if (last == d.L - 1) S.eflag[last] &= (uint8_t)~0x10; }
+                        else {
+                            const Slot4 s4 = *reinterpret_cast<const Slot4*>(S.succ + 4 * last);
+                            uint8_t m = 0;
+                            for (int c = 0; c < 4; ++c) if (s4.v[c] == cur) m |= (uint8_t)(1u << c);
+                            if (m) S.eflag[last] &= (uint8_t)~m;
+                        }
+                    }
+                    last = cur;
+                }
             }
         }
-        sh[1] = 0;   // candidate count
+        if (tid == 0) sh[1] = 0;   // candidate count
     }
     ctx.sync();
 
@@ -323,8 +475,9 @@ KM_HD bool graph_target(const Ctx& ctx, const TableView& T, const WalkView& W, c
     // so the earliest one is the unique representative.)
     for (int a = tid; a < d.N; a += nt) {
         if (!(S.dist[a] < INFINITY)) continue;
+        const uint8_t fl = S.eflag[a];
         for_each_succ(S, d, a, [&](int b, int slot) {
-            if (!(S.eflag[a] & (1u << slot))) return;
+            if (!(fl & (1u << slot))) return;
             if (!(S.dist2[b] < INFINITY)) return;
             if (a != d.src && S.after[a] == b) {
                 const int pa = S.before[a];
@@ -333,13 +486,18 @@ KM_HD bool graph_target(const Ctx& ctx, const TableView& T, const WalkView& W, c
                 else {
                     const Slot4 s4 = *reinterpret_cast<const Slot4*>(S.succ + 4 * pa);
                     uint8_t m = 0;
+#pragma unroll
                     for (int c = 0; c < 4; ++c) if (s4.v[c] == a) m |= (uint8_t)(1u << c);
                     earlier = (S.eflag[pa] & m) != 0;
                 }
                 if (earlier) return;
             }
             const int pos = atomic_addi32(&sh[1], 1);
-            if (pos < S.max_cand) { S.ce_a[pos] = a; S.ce_b[pos] = b; }
+            if (pos < S.max_cand) {
+                S.ce_a[pos] = a; S.ce_b[pos] = b;
+                S.ce_len[pos] = S.hopF[a] + S.hopB[b] + 2;   // nodes incl. both caps
+                S.upath[pos] = pos;
+            }
         });
     }
     ctx.sync();
@@ -352,15 +510,6 @@ KM_HD bool graph_target(const Ctx& ctx, const TableView& T, const WalkView& W, c
         ctx.sync();
         return false;
     }
-    // length of each unique path incl. both caps: hops to the source + hops to the sink
-    for (int c = tid; c < n_cand; c += nt) {
-        int len = 0;
-        for (int cur = S.ce_a[c]; cur != -1; cur = S.before[cur]) ++len;
-        for (int cur = S.ce_b[c]; cur != -1; cur = S.after[cur]) ++len;
-        S.ce_len[c] = len;
-        S.upath[c] = c;
-    }
-    ctx.sync();
 
     pt.mark(4);
     // ---- allocate path ids and pool space (lane 0) ---------------------------------------
@@ -396,16 +545,18 @@ KM_HD bool graph_target(const Ctx& ctx, const TableView& T, const WalkView& W, c
     if (nu < 0) return false;
 
     pt.mark(5);
-    // ---- materialise: one lane per unique path walks its two chains ------------------
-    for (int u = tid; u < nu; u += nt) {
-        const int c = S.upath[u];
+    // ---- materialise: two lanes per unique path, one per chain; positions come from the hop counts ----
+    for (int w = tid; w < 2 * nu; w += nt) {
+        const int u = w >> 1;
         int32_t* dst = R.pool + R.path_off[first + u];
-        int lf = 0;
-        for (int cur = S.ce_a[c]; cur != -1; cur = S.before[cur]) ++lf;
-        int p = lf - 2;                                          // source cap dropped
-        for (int cur = S.ce_a[c]; cur != d.src; cur = S.before[cur]) dst[p--] = cur;
-        p = lf - 1;
-        for (int cur = S.ce_b[c]; cur != d.snk; cur = S.after[cur]) dst[p++] = cur;
+        const int a = S.ce_a[u];
+        if (!(w & 1)) {
+            int p = S.hopF[a] - 1;                                   // source cap dropped
+            for (int cur = a; cur != d.src; cur = S.before[cur]) dst[p--] = cur;
+        } else {
+            int p = S.hopF[a];
+            for (int cur = S.ce_b[u]; cur != d.snk; cur = S.after[cur]) dst[p++] = cur;
+        }
     }
     ctx.sync();
 

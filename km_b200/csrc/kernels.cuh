@@ -146,54 +146,13 @@ __global__ void __launch_bounds__(32 * KM_WALK_WARPS) km_walk_kernel(TableView T
 // (adjacency, both shortest-path trees, candidate edges, solver matrices: ~50 KB) on chip and takes
 // every target whose graph has at most KM_SMALL_NODES nodes; the GENERAL pass uses per-CTA scratch
 // in HBM and takes the rest, plus any target the first pass deferred (KM_ST_RETRY_LARGE).
-struct ScratchLayout {
-    char* base;
-    size_t stride;          // bytes per CTA
-    size_t o_newidx, o_kept, o_succ, o_pred, o_dist, o_dist2, o_before, o_after, o_cand, o_cand2, o_eflag, o_occ;
-    size_t o_ce_a, o_ce_b, o_ce_len, o_upath, o_pdiff, o_grp, o_G, o_V, o_vec, o_acc, o_cols, o_members;
-    int maxN, max_cand, max_paths, max_cols;
-};
-
 #define KM_SMALL_NODES 512
 #define KM_SMALL_CAND 64
 #define KM_SMALL_PATHS 64
 #define KM_SMALL_COLS 8
 
-// the one place that knows the scratch layout (host sizing and device carving both use it)
-__host__ __device__ inline ScratchLayout make_layout(int maxcap, int max_cand, int max_paths, int max_cols) {
-    ScratchLayout L = {};
-    const size_t maxN = (size_t)maxcap + 2, nce = (size_t)max_cand;
-    size_t o = 0;
-    auto put = [&](size_t bytes) { size_t at = o; o = (o + bytes + 15) / 16 * 16; return at; };
-    L.o_newidx = put(4 * (size_t)maxcap); L.o_kept = put(4 * (size_t)maxcap);
-    L.o_succ = put(16 * maxN); L.o_pred = put(16 * maxN);
-    L.o_dist = put(4 * maxN); L.o_dist2 = put(4 * maxN); L.o_before = put(4 * maxN); L.o_after = put(4 * maxN);
-    L.o_cand = put(4 * maxN); L.o_cand2 = put(4 * maxN); L.o_eflag = put(maxN); L.o_occ = put(4 * maxN);
-    L.o_ce_a = put(4 * nce); L.o_ce_b = put(4 * nce); L.o_ce_len = put(4 * nce);
-    L.o_upath = put(4 * (size_t)max_paths); L.o_pdiff = put(16 * (size_t)max_paths); L.o_grp = put(20 * (size_t)max_paths);
-    L.o_G = put(8 * (size_t)max_cols * max_cols); L.o_V = put(16 * (size_t)max_cols * max_cols); L.o_vec = put(64 * (size_t)max_cols);
-    L.o_acc = put(8 * ((size_t)max_cols * max_cols + max_cols));
-    L.o_cols = put(sizeof(PathView) * (size_t)max_cols); L.o_members = put(4 * (size_t)max_cols);
-    L.stride = (o + 255) / 256 * 256;
-    L.maxN = (int)maxN; L.max_cand = max_cand; L.max_paths = max_paths; L.max_cols = max_cols;
-    return L;
-}
-
-__device__ __forceinline__ GraphScratch carve(const ScratchLayout& L, char* p, int retry) {
-    GraphScratch S;
-    S.newidx = (int32_t*)(p + L.o_newidx); S.kept = (int32_t*)(p + L.o_kept);
-    S.succ = (int32_t*)(p + L.o_succ); S.pred = (int32_t*)(p + L.o_pred);
-    S.dist = (float*)(p + L.o_dist); S.dist2 = (float*)(p + L.o_dist2);
-    S.before = (int32_t*)(p + L.o_before); S.after = (int32_t*)(p + L.o_after);
-    S.cand = (int32_t*)(p + L.o_cand); S.cand2 = (int32_t*)(p + L.o_cand2); S.eflag = (uint8_t*)(p + L.o_eflag);
-    S.occ = (int32_t*)(p + L.o_occ);
-    S.ce_a = (int32_t*)(p + L.o_ce_a); S.ce_b = (int32_t*)(p + L.o_ce_b); S.ce_len = (int32_t*)(p + L.o_ce_len);
-    S.upath = (int32_t*)(p + L.o_upath); S.pdiff = (int32_t*)(p + L.o_pdiff); S.grp = (int32_t*)(p + L.o_grp);
-    S.G = (double*)(p + L.o_G); S.V = (double*)(p + L.o_V); S.vec = (double*)(p + L.o_vec);
-    S.acc = (unsigned long long*)(p + L.o_acc);
-    S.cols = (PathView*)(p + L.o_cols); S.members = (int32_t*)(p + L.o_members);
-    S.maxN = L.maxN; S.max_cand = L.max_cand; S.max_paths = L.max_paths; S.max_cols = L.max_cols; S.retry = retry;
-    return S;
+__host__ __device__ inline ScratchLayout small_layout() {
+    return make_layout(KM_SMALL_NODES - 2, KM_SMALL_CAND, KM_SMALL_PATHS, KM_SMALL_COLS, 1);
 }
 
 #define KM_ST_FATAL (KM_ST_BAD_BASE | KM_ST_DUP_KMER | KM_ST_NODE_OVERFLOW | KM_ST_NODE_LIMIT | KM_ST_TOO_SHORT)
@@ -204,7 +163,7 @@ __global__ void __launch_bounds__(KM_CTA) km_graph_kernel(TableView T, WalkView 
     extern __shared__ __align__(16) char km_smem[];
     __shared__ int sh[16];
     CtaCtx ctx;
-    const GraphScratch S = SMALL ? carve(make_layout(KM_SMALL_NODES - 2, KM_SMALL_CAND, KM_SMALL_PATHS, KM_SMALL_COLS), km_smem, 1)
+    const GraphScratch S = SMALL ? carve(small_layout(), km_smem, 1)
                                  : carve(SL, SL.base + (size_t)blockIdx.x * SL.stride, 0);
     for (int t = blockIdx.x; t < W.n_targets; t += gridDim.x) {
         const uint32_t st = W.status[t];

@@ -123,37 +123,108 @@ KM_HD void jacobi_eigen(double* A, double* V, int m) {
     }
 }
 
+// a*d - b*c with one rounding of the exact result's neighbourhood (Kahan); inputs are integers
+// below 2^53 held in doubles, so the only error is the final ~1.5 ulp
+KM_HD double det2(double a, double b, double c, double d) {
+    const double w = b * c;
+    const double e = fma(-b, c, w);
+    const double f = fma(a, d, -w);
+    return f + e;
+}
+
+// refine_coef (PathQuant.py:120-136) + get_ratio (:144-149) on the normal equations, iterated
+// literally: fixed step 0.1, gradient / n_nodes, stop at max|grad| <= 0.01.
+KM_HD int refine_and_ratio(const double* G, const double* h, int m, int n_nodes, double* coef, double* rvaf, double* grad) {
+    for (int a = 0; a < m; ++a) if (coef[a] < 0.0) coef[a] = 0.0;
+    double worst = INFINITY;
+    int iters = 0;
+    while (worst > 0.01) {
+        for (int a = 0; a < m; ++a) {
+            double fit = 0.0;
+            for (int b = 0; b < m; ++b) fit += G[a * m + b] * coef[b];
+            grad[a] = 2.0 * (h[a] - fit) / (double)n_nodes;
+        }
+        worst = 0.0;
+        for (int a = 0; a < m; ++a) {
+            coef[a] += 0.1 * grad[a];
+            if (coef[a] < 0.0) { grad[a] = 0.0; coef[a] = 0.0; }
+            const double ag = fabs(grad[a]);
+            worst = ag > worst ? ag : worst;     // NaN never enters: counts are finite
+        }
+        if (++iters > 10000000) { iters = -1; break; }
+    }
+    double cmax = coef[0], csum = 0.0;
+    for (int a = 0; a < m; ++a) { cmax = coef[a] > cmax ? coef[a] : cmax; csum += coef[a]; }
+    for (int a = 0; a < m; ++a) rvaf[a] = cmax == 0.0 ? coef[a] : coef[a] / csum;
+    return iters;
+}
+
 // Quantify m columns.  coef/rvaf receive m values each.  Returns refine iterations, or
-// -1 when the watchdog fired.  All threads of the CTA must call this.
+// -1 when the watchdog fired.  All threads of the CTA must call this; S.occ must be all zero on
+// entry and is all zero again on return.
 template <class Ctx>
 KM_HD int solve_columns(const Ctx& ctx, const GraphScratch& S, const uint32_t* counts, int n_nodes,
                         const PathView* cols, int m, double* coef, double* rvaf, int* sh) {
     const int tid = ctx.tid(), nt = ctx.nt();
-    double* G = S.G;
-    double* h = S.vec;   // [m]
     unsigned long long* acc = S.acc;   // [m*m + m] exact integer accumulators
     for (int i = tid; i < m * m + m; i += nt) acc[i] = 0ull;
+    ctx.sync();
     // contrib[i, c] = occurrences of node i in column c (PathQuant.py:101-104);
-    // G[a][b] = sum_i contrib[i,a]*contrib[i,b]; h[a] = sum_i contrib[i,a]*float32(count_i)
+    // G[a][b] = sum_i contrib[i,a]*contrib[i,b]; h[a] = sum_i contrib[i,a]*float32(count_i).
+    // A column that is a slice of the reference (idx == nullptr) touches each node of its range
+    // once, so its occurrence vector is a range test; only real paths are scattered into S.occ.
+    // Every lane sums privately, lanes combine by shuffle, and one lane per warp adds to acc.
     for (int b = 0; b < m; ++b) {
-        for (int i = tid; i < n_nodes; i += nt) S.occ[i] = 0;
-        ctx.sync();
+        const PathView cb = cols[b];
         unsigned long long hb = 0ull;
-        for (int p = tid; p < cols[b].len; p += nt) {
-            const int node = pv_at(cols[b], p);
-            atomic_addi32(&S.occ[node], 1);
+        for (int p = tid; p < cb.len; p += nt) {
+            const int node = pv_at(cb, p);
+            if (cb.idx) atomic_addi32(&S.occ[node], 1);
             hb += (unsigned long long)(float)counts[node];      // counts -> float32 (PathQuant.py:99), an integer
         }
-        if (hb) atomic_add64(&acc[m * m + b], hb);
+        hb = warp_sum64(hb);
+        if (warp_leader() && hb) atomic_add64(&acc[m * m + b], hb);
         ctx.sync();
         for (int a = b; a < m; ++a) {
+            const PathView ca = cols[a];
             unsigned long long part = 0ull;
-            for (int p = tid; p < cols[a].len; p += nt) part += (unsigned long long)S.occ[pv_at(cols[a], p)];
-            if (part) atomic_add64(&acc[a * m + b], part);
+            for (int p = tid; p < ca.len; p += nt) {
+                const int node = pv_at(ca, p);
+                part += cb.idx ? (unsigned long long)S.occ[node] : (unsigned long long)(node >= cb.begin && node < cb.begin + cb.len);
+            }
+            part = warp_sum64(part);
+            if (warp_leader() && part) atomic_add64(&acc[a * m + b], part);
         }
         ctx.sync();
+        if (cb.idx) {
+            for (int p = tid; p < cb.len; p += nt) S.occ[pv_at(cb, p)] = 0;
+            ctx.sync();
+        }
     }
-    if (tid == 0) {
+    if (tid == 0 && m == 2) {
+        // 2 x 2 (every vs_ref row and every single-variant cluster): G is an exact integer matrix,
+        // so its rank is decided exactly, and the minimum-norm solution (what lstsq returns,
+        // PathQuant.py:116) has a closed form in either case.
+        double G[4], h[2], c[2], r[2], grad[2];
+        G[0] = (double)acc[0]; G[1] = G[2] = (double)acc[2]; G[3] = (double)acc[3];
+        h[0] = (double)acc[4]; h[1] = (double)acc[5];
+        const long long det = (long long)acc[0] * (long long)acc[3] - (long long)acc[2] * (long long)acc[2];
+        if (det != 0) {
+            c[0] = det2(h[0], h[1], G[1], G[3]) / (double)det;       // Cramer
+            c[1] = det2(G[0], G[1], h[0], h[1]) / (double)det;
+        } else if (acc[0] + acc[3] == 0ull) {
+            c[0] = c[1] = 0.0;
+        } else {
+            // rank 1: G = lambda u u^T, lambda = trace; any non-zero column v of G is parallel to u
+            const double v0 = acc[0] >= acc[3] ? G[0] : G[1], v1 = acc[0] >= acc[3] ? G[1] : G[3];
+            const double s = (v0 * h[0] + v1 * h[1]) / ((v0 * v0 + v1 * v1) * (G[0] + G[3]));
+            c[0] = v0 * s; c[1] = v1 * s;
+        }
+        sh[4] = refine_and_ratio(G, h, 2, n_nodes, c, r, grad);
+        coef[0] = c[0]; coef[1] = c[1]; rvaf[0] = r[0]; rvaf[1] = r[1];
+    } else if (tid == 0) {
+        double* G = S.G;
+        double* h = S.vec;   // [m]
         for (int a = 0; a < m; ++a) {
             h[a] = (double)acc[m * m + a];
             for (int b = 0; b <= a; ++b) G[a * m + b] = G[b * m + a] = (double)acc[a * m + b];
@@ -177,31 +248,7 @@ KM_HD int solve_columns(const Ctx& ctx, const GraphScratch& S, const uint32_t* c
             proj /= lam;
             for (int a = 0; a < m; ++a) coef[a] += V[a * m + e] * proj;
         }
-        // refine_coef (PathQuant.py:120-136)
-        for (int a = 0; a < m; ++a) if (coef[a] < 0.0) coef[a] = 0.0;
-        double worst = INFINITY;
-        int iters = 0;
-        double* grad = S.vec + 2 * S.max_cols;
-        while (worst > 0.01) {
-            for (int a = 0; a < m; ++a) {
-                double fit = 0.0;
-                for (int b = 0; b < m; ++b) fit += G[a * m + b] * coef[b];
-                grad[a] = 2.0 * (h[a] - fit) / (double)n_nodes;
-            }
-            worst = 0.0;
-            for (int a = 0; a < m; ++a) {
-                coef[a] += 0.1 * grad[a];
-                if (coef[a] < 0.0) { grad[a] = 0.0; coef[a] = 0.0; }
-                const double ag = fabs(grad[a]);
-                worst = ag > worst ? ag : worst;     // NaN never enters: counts are finite
-            }
-            if (++iters > 10000000) { iters = -1; break; }
-        }
-        // get_ratio (PathQuant.py:144-149)
-        double cmax = coef[0], csum = 0.0;
-        for (int a = 0; a < m; ++a) { cmax = coef[a] > cmax ? coef[a] : cmax; csum += coef[a]; }
-        for (int a = 0; a < m; ++a) rvaf[a] = cmax == 0.0 ? coef[a] : coef[a] / csum;
-        sh[4] = iters;
+        sh[4] = refine_and_ratio(G, h, m, n_nodes, coef, rvaf, S.vec + 2 * S.max_cols);
     }
     ctx.sync();
     return sh[4];
@@ -238,6 +285,7 @@ KM_HD void emit_rows(const Ctx& ctx, const TableView& T, const WalkView& W, cons
     const PathView ref = {nullptr, 0, d.L};
 
     PhaseTimer pt;
+    for (int i = tid; i < d.N; i += ctx.nt()) S.occ[i] = 0;     // held nxtF during the tree phase; the solver needs zeros
     // ---- per-path diffs against the whole reference (CTA-parallel scans) ---------
     for (int p = 0; p < n_paths; ++p) {
         const PathView alt = {R.pool + R.path_off[first_path + p], 0, R.path_len[first_path + p]};

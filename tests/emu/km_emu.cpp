@@ -90,22 +90,11 @@ int emu_find_target(void* h, const uint8_t* codes, int len, double ratio, int64_
 
     // the two passes of km_graph_kernel: small capacities with deferral, then the general ones
     auto run_pass = [&](int maxcap, int max_cand, int max_paths, int max_cols, int retry) -> bool {
-        const size_t maxN = (size_t)maxcap + 2;
-        std::vector<int32_t> newidx(maxcap), kept(maxcap), succ(4 * maxN), pred(4 * maxN), before(maxN), after(maxN), cand(maxN), cand2(maxN), occ(maxN);
-        std::vector<int32_t> ce_a(max_cand), ce_b(max_cand), ce_len(max_cand), upath(max_paths), pdiff(4 * max_paths), grp(5 * max_paths);
-        std::vector<int32_t> members(max_cols);
-        std::vector<float> dist(maxN), dist2(maxN);
-        std::vector<uint8_t> eflag(maxN);
-        std::vector<double> G(max_cols * max_cols), V(2 * max_cols * max_cols), vec(8 * max_cols);
-        std::vector<PathView> cols(max_cols);
-        std::vector<unsigned long long> acc(max_cols * max_cols + max_cols);
-        GraphScratch S;
-        S.newidx = newidx.data(); S.kept = kept.data(); S.succ = succ.data(); S.pred = pred.data(); S.dist = dist.data();
-        S.before = before.data(); S.after = after.data(); S.cand = cand.data(); S.cand2 = cand2.data(); S.dist2 = dist2.data();
-        S.eflag = eflag.data(); S.occ = occ.data(); S.ce_a = ce_a.data(); S.ce_b = ce_b.data(); S.ce_len = ce_len.data();
-        S.upath = upath.data(); S.pdiff = pdiff.data(); S.grp = grp.data();
-        S.G = G.data(); S.V = V.data(); S.vec = vec.data(); S.cols = cols.data(); S.members = members.data(); S.acc = acc.data();
-        S.maxN = (int)maxN; S.max_cand = max_cand; S.max_paths = max_paths; S.max_cols = max_cols; S.retry = retry;
+        // the product's own layout + carving, overlays included (compact = the shared-memory pass)
+        const ScratchLayout SL = make_layout(maxcap, max_cand, max_paths, max_cols, retry);
+        std::vector<char> arena(SL.stride + 64, (char)0x5A);
+        char* basep = arena.data() + ((64 - ((uintptr_t)arena.data() & 63)) & 63);
+        const GraphScratch S = carve(SL, basep, retry);
         int sh[16] = {0};
         GraphDims d;
         if (!graph_target(ctx, t->v, W, S, R, 0, &d, sh)) return false;
