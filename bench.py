@@ -386,7 +386,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms, "device_ms": e2e_breakdown,
                     "what": "km_find_batch(host sequences) + km_result_format_all -> TSV text"},
-            "gpu_launches": 2 * args.steps,
+            "gpu_launches": 5 * args.steps,
             "kernels": {"km_walk_kernel_ms": walk_ms, "km_graph_kernel_ms": graph_ms,
                         "dominant": "km_walk_kernel" if walk_ms >= graph_ms else "km_graph_kernel"},
             "roofline": {"kernel": "km_walk_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -140,6 +140,8 @@ int km_find_plan_create(km_table* t, const char* seqs_host, const int64_t* offse
 int km_find_plan_launch(km_plan* p, void* cuda_stream);
 /* device time of the most recent launch: memsets + walk kernel, and graph kernel (CUDA events) */
 int km_find_plan_last_ms(km_plan* p, float* walk_ms, float* graph_ms);
+/* the same split three ways: out3[0] memsets + reference-probe kernel, [1] walk kernels, [2] graph kernels */
+int km_find_plan_kernel_ms(km_plan* p, float* out3);
 int km_find_plan_fetch(km_plan* p, int want_graph, km_result** out);
 void km_find_plan_free(km_plan* p);
 
@@ -186,7 +188,7 @@ int64_t km_result_format_all(const km_result* r, const char* db_name, const char
 
 /* ---- measurement helpers (bench.py) --------------------------------------------------- */
 /* per-phase SM cycles of the graph pass (only in a -DKM_PHASE_TIMERS build; tools/phase_times.py) */
-int km_debug_phase_cycles(unsigned long long* out32, int reset);
+int km_debug_phase_cycles(unsigned long long* out64, int reset);   /* 64 counters */
 /* random 32-byte-sector gather over `bytes` of HBM: the ceiling for hash probes */
 int km_bench_random_gather(int device, uint64_t bytes, uint64_t n_loads, int iters, float* best_ms);
 /* device-resident lookup benchmark: n queries (config-4 mix) generated on device, timed `iters` times */

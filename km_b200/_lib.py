@@ -89,6 +89,8 @@ def lib():
     L.km_find_plan_launch.argtypes = [vp, vp]
     L.km_find_plan_fetch.argtypes = [vp, ci, P(vp)]
     L.km_find_plan_last_ms.argtypes = [vp, P(cf), P(cf)]
+    L.km_find_plan_kernel_ms.argtypes = [vp, P(cf)]
+    L.km_find_plan_kernel_ms.restype = ci
     L.km_find_plan_free.argtypes = [vp]
     L.km_find_plan_free.restype = None
     L.km_bench_random_gather.argtypes = [ci, u64, u64, ci, P(cf)]
@@ -112,5 +114,5 @@ EXPORTS = ["km_last_error", "km_device_count", "km_version", "km_table_open_jf",
            "km_table_insert", "km_table_build_synthetic", "km_table_count_reads", "km_table_drop_below",
            "km_table_get_info", "km_table_close", "km_query_batch", "km_query_batch_device", "km_query_ascii",
            "km_get_child_batch", "km_find_batch", "km_result_get", "km_result_free", "km_result_format_target", "km_result_format_all",
-           "km_find_plan_create", "km_find_plan_launch", "km_find_plan_fetch", "km_find_plan_free", "km_find_plan_last_ms",
+           "km_find_plan_create", "km_find_plan_launch", "km_find_plan_fetch", "km_find_plan_free", "km_find_plan_last_ms", "km_find_plan_kernel_ms",
            "km_bench_random_gather", "km_bench_lookup", "km_debug_phase_cycles"]

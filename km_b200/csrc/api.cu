@@ -76,7 +76,7 @@ struct km_table {
     Bucket* buckets = nullptr;
     unsigned long long* d_counter = nullptr;   // [0] new keys, then a u32 "full" flag at +8
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[6] = {};
+    cudaEvent_t ev[8] = {};
     Arena dev, pin;            // lookups / inserts
     Arena dev_find, pin_find;  // km_find_batch workspace, reused across calls
     int sm_count = 148;
@@ -407,6 +407,7 @@ struct km_plan {
     km_find_params prm{};
     std::string targets;
     std::vector<int64_t> seq_off, node_off, hash_off;
+    std::vector<int32_t> chunk_target, chunk_start;   // <= 32 consecutive reference k-mers each (ref_probe_chunk)
     std::vector<uint8_t> codes;
     std::vector<int32_t> extra;
     int64_t pool_cap = 0, seq_cap = 0, n_node = 0, n_hash = 0, n_code = 0;
@@ -442,6 +443,12 @@ static int plan_layout(km_plan* p) {
         p->node_off[i + 1] = p->node_off[i] + cap;
         p->hash_off[i + 1] = p->hash_off[i] + pow2_at_least(2 * (uint64_t)cap + 256);
     }
+    p->chunk_target.clear(); p->chunk_start.clear();
+    for (int i = 0; i < n; ++i) {
+        const int L = (int)std::max<int64_t>(0, p->seq_off[i + 1] - p->seq_off[i] - k + 1);
+        for (int s0 = 0; s0 < L; s0 += 32) { p->chunk_target.push_back(i); p->chunk_start.push_back(s0); }
+    }
+    const size_t n_chunks = p->chunk_target.size();
     const int64_t n_node = p->n_node = p->node_off[n], n_hash = p->n_hash = p->hash_off[n], n_code = p->n_code = p->seq_off[n];
     p->grid_graph = std::max(1, std::min(n, t->sm_count * 8));
     p->grid_large = std::max(1, std::min(n, t->sm_count * 2));
@@ -451,7 +458,7 @@ static int plan_layout(km_plan* p) {
 
     size_t need = 4096;
     auto acc = [&](size_t bytes) { need = align_up(need, 256) + bytes; };
-    acc(n_code); acc(8 * (n + 1)); acc(8 * (n + 1)); acc(8 * (n + 1));
+    acc(n_code); acc(8 * (n + 1)); acc(8 * (n + 1)); acc(8 * (n + 1)); acc(4 * n_chunks); acc(4 * n_chunks);
     acc(8 * n_node); acc(4 * n_node); acc(4 * n_node); acc(16 * n_node);          // node arrays
     acc(8 * n_hash); acc(4 * n_hash); acc(4 * n_hash); acc(n_hash);                // visited sets
     acc(4 * n); acc(4 * n); acc(4 * n); acc(8 * n);                                // n_nodes n_kept status lookups
@@ -467,6 +474,7 @@ static int plan_layout(km_plan* p) {
     W.n_targets = n;
     W.codes = A.take<uint8_t>(n_code);
     W.seq_off = A.take<int64_t>(n + 1); W.node_off = A.take<int64_t>(n + 1); W.hash_off = A.take<int64_t>(n + 1);
+    W.chunk_target = A.take<int32_t>(n_chunks); W.chunk_start = A.take<int32_t>(n_chunks); W.n_chunks = (int)n_chunks;
     W.node_kmer = A.take<uint64_t>(n_node); W.node_count = A.take<uint32_t>(n_node);
     W.node_slot = A.take<uint32_t>(n_node); W.node_kid = A.take<uint32_t>(4 * n_node);
     W.hkey = A.take<uint64_t>(n_hash); W.hval = A.take<uint32_t>(n_hash); W.hmeta = A.take<uint32_t>(n_hash);
@@ -485,6 +493,7 @@ static int plan_layout(km_plan* p) {
     R.pool = A.take<int32_t>(pool_cap); R.path_cap = path_cap; R.pool_cap = pool_cap;
     R.rows = A.take<Row>(row_cap); R.row_cap = row_cap;
     p->d_seq_pool = A.take<char>(seq_cap);
+    R.seq_pool = p->d_seq_pool; R.path_seq_off = p->d_path_seq_off; R.seq_cap = seq_cap;
     R.used = A.take<unsigned long long>(4);
     p->SL = L0;
     p->SL.base = A.take<char>(L0.stride * (size_t)p->grid_large);
@@ -495,12 +504,16 @@ static int plan_layout(km_plan* p) {
 
 static int plan_upload(km_plan* p, cudaStream_t s) {
     const int n = p->n;
-    if (int rc = p->pin->reserve((size_t)p->n_code + 24 * (size_t)(n + 1) + 4096)) return rc;
+    const size_t n_chunks = p->chunk_target.size();
+    if (int rc = p->pin->reserve((size_t)p->n_code + 24 * (size_t)(n + 1) + 8 * n_chunks + 8192)) return rc;
     p->pin->reset();
     uint8_t* h_codes = p->pin->take<uint8_t>(p->n_code);
     int64_t* h_seq_off = p->pin->take<int64_t>(n + 1);
     int64_t* h_node_off = p->pin->take<int64_t>(n + 1);
     int64_t* h_hash_off = p->pin->take<int64_t>(n + 1);
+    int32_t* h_ct = p->pin->take<int32_t>(n_chunks);
+    int32_t* h_cs = p->pin->take<int32_t>(n_chunks);
+    if (n_chunks) { memcpy(h_ct, p->chunk_target.data(), 4 * n_chunks); memcpy(h_cs, p->chunk_start.data(), 4 * n_chunks); }
     memcpy(h_codes, p->codes.data(), p->n_code);
     memcpy(h_seq_off, p->seq_off.data(), 8 * (n + 1));
     memcpy(h_node_off, p->node_off.data(), 8 * (n + 1));
@@ -510,7 +523,11 @@ static int plan_upload(km_plan* p, cudaStream_t s) {
     CU(cudaMemcpyAsync((void*)p->W.seq_off, h_seq_off, 8 * (n + 1), cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync((void*)p->W.node_off, h_node_off, 8 * (n + 1), cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync((void*)p->W.hash_off, h_hash_off, 8 * (n + 1), cudaMemcpyHostToDevice, s));
-    p->bytes_h2d = (unsigned long long)p->n_code + 24ull * (n + 1);
+    if (n_chunks) {
+        CU(cudaMemcpyAsync((void*)p->W.chunk_target, h_ct, 4 * n_chunks, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync((void*)p->W.chunk_start, h_cs, 4 * n_chunks, cudaMemcpyHostToDevice, s));
+    }
+    p->bytes_h2d = (unsigned long long)p->n_code + 24ull * (n + 1) + 8ull * n_chunks;
     return 0;
 }
 
@@ -521,19 +538,24 @@ static int plan_launch(km_plan* p, cudaStream_t s) {
     CU(cudaEventRecord(t->ev[1], s));
     CU(cudaMemsetAsync(p->state0, 0, p->state_bytes, s));
     CU(cudaMemsetAsync(p->R.used, 0, 32, s));
+    if (p->W.n_chunks) {
+        km_ref_probe_kernel<<<(p->W.n_chunks + KM_PROBE_WARPS - 1) / KM_PROBE_WARPS, 32 * KM_PROBE_WARPS, 0, s>>>(t->view(), p->W, p->P);
+        CU(cudaGetLastError());
+    }
+    CU(cudaEventRecord(t->ev[6], s));
+    km_walk_small_kernel<<<(p->n + KM_WALK_WARPS - 1) / KM_WALK_WARPS, 32 * KM_WALK_WARPS, 0, s>>>(t->view(), p->W, p->P);
+    CU(cudaGetLastError());
     km_walk_kernel<<<(p->n + KM_WALK_WARPS - 1) / KM_WALK_WARPS, 32 * KM_WALK_WARPS, 0, s>>>(t->view(), p->W, p->P);
     CU(cudaGetLastError());
     CU(cudaEventRecord(t->ev[2], s));
     // shared-memory pass first, then the general pass for large or deferred targets
     const size_t small_smem = small_layout().stride;
-    km_graph_kernel<true><<<p->grid_graph, KM_CTA, small_smem, s>>>(t->view(), p->W, p->SL, p->R, p->d_seq_pool,
-                                                                     p->d_path_seq_off, p->seq_cap);
+    km_graph_kernel<true><<<p->grid_graph, KM_CTA, small_smem, s>>>(t->view(), p->W, p->SL, p->R);
     CU(cudaGetLastError());
-    km_graph_kernel<false><<<p->grid_large, KM_CTA, 0, s>>>(t->view(), p->W, p->SL, p->R, p->d_seq_pool,
-                                                            p->d_path_seq_off, p->seq_cap);
+    km_graph_kernel<false><<<p->grid_large, KM_CTA, 0, s>>>(t->view(), p->W, p->SL, p->R);
     CU(cudaGetLastError());
     CU(cudaEventRecord(t->ev[3], s));
-    p->n_launches += 3;
+    p->n_launches += 5;
     p->launched = true;
     return 0;
 }
@@ -678,6 +700,16 @@ extern "C" int km_find_plan_last_ms(km_plan* p, float* walk_ms, float* graph_ms)
     CU(cudaEventSynchronize(p->t->ev[3]));
     if (walk_ms) CU(cudaEventElapsedTime(walk_ms, p->t->ev[1], p->t->ev[2]));
     if (graph_ms) CU(cudaEventElapsedTime(graph_ms, p->t->ev[2], p->t->ev[3]));
+    return 0;
+}
+
+extern "C" int km_find_plan_kernel_ms(km_plan* p, float* out3) {
+    if (!p || !p->launched || !out3) return fail(KM_E_ARG, "km_find_plan_kernel_ms: nothing launched");
+    CU(cudaSetDevice(p->t->device));
+    CU(cudaEventSynchronize(p->t->ev[3]));
+    CU(cudaEventElapsedTime(&out3[0], p->t->ev[1], p->t->ev[6]));    // memsets + reference probe
+    CU(cudaEventElapsedTime(&out3[1], p->t->ev[6], p->t->ev[2]));    // the two walk kernels
+    CU(cudaEventElapsedTime(&out3[2], p->t->ev[2], p->t->ev[3]));    // the two graph kernels
     return 0;
 }
 
@@ -874,8 +906,8 @@ extern "C" int64_t km_result_format_all(const km_result* r, const char* db_name,
 // ---- measurement helpers ---------------------------------------------------------------------------
 extern "C" int km_debug_phase_cycles(unsigned long long* out32, int reset) {
 #ifdef KM_PHASE_TIMERS
-    if (out32) CU(cudaMemcpyFromSymbol(out32, km_phase_cycles, 32 * sizeof(unsigned long long)));
-    if (reset) { unsigned long long z[32] = {0}; CU(cudaMemcpyToSymbol(km_phase_cycles, z, sizeof(z))); }
+    if (out32) CU(cudaMemcpyFromSymbol(out32, km_phase_cycles, 64 * sizeof(unsigned long long)));
+    if (reset) { unsigned long long z[64] = {0}; CU(cudaMemcpyToSymbol(km_phase_cycles, z, sizeof(z))); }
     return 0;
 #else
     (void)out32; (void)reset;

@@ -26,7 +26,7 @@ namespace km {
 // Phase timer (measurement only): lane 0 of each CTA adds the SM cycles it spent between marks to
 // a global table, read back by km_debug_phase_cycles.  Compiled in when KM_PHASE_TIMERS is defined.
 #if KM_DEVICE_BUILD && defined(KM_PHASE_TIMERS)
-__device__ unsigned long long km_phase_cycles[32];
+__device__ unsigned long long km_phase_cycles[64];
 struct PhaseTimer {
     long long t0;
     __device__ __forceinline__ PhaseTimer() {
@@ -39,10 +39,17 @@ struct PhaseTimer {
         if (threadIdx.x == 0) { const long long t1 = clock64(); atomicAdd(&km_phase_cycles[phase], (unsigned long long)(t1 - t0)); t0 = t1; }
 #endif
     }
+    // the same for a warp-per-target kernel: lane 0 of every warp reports
+    __device__ __forceinline__ void mark_warp(int phase) {
+#ifdef __CUDA_ARCH__
+        if ((threadIdx.x & 31) == 0) { const long long t1 = clock64(); atomicAdd(&km_phase_cycles[phase], (unsigned long long)(t1 - t0)); t0 = t1; }
+#endif
+    }
 };
 #else
 struct PhaseTimer {
     KM_HD void mark(int) {}
+    KM_HD void mark_warp(int) {}
 };
 #endif
 
@@ -72,6 +79,19 @@ KM_HD unsigned long long warp_sum64(unsigned long long v) {
     return v;
 }
 KM_HD bool warp_leader() { return (threadIdx.x & 31) == 0; }
+KM_HD uint32_t warp_min32(uint32_t v) { return __reduce_min_sync(0xFFFFFFFFu, v); }
+KM_HD uint32_t warp_or32(uint32_t v) { return __reduce_or_sync(0xFFFFFFFFu, v); }
+// lanes holding the same 64-bit value (all 32 lanes must call)
+KM_HD uint32_t warp_match64(uint64_t v) { return __match_any_sync(0xFFFFFFFFu, (unsigned long long)v); }
+KM_HD int warp_shfl32(int v, int src_lane) { return __shfl_sync(0xFFFFFFFFu, v, src_lane); }
+KM_HD int warp_shfl_down32(int v, int delta) { return __shfl_down_sync(0xFFFFFFFFu, v, delta); }
+KM_HD int popc32(uint32_t x) { return __popc(x); }
+KM_HD void fence_block() { __threadfence_block(); }
+KM_HD uint32_t load_shared_volatile32(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
+KM_HD uint8_t load_shared_volatile8(const uint8_t* p) { return *reinterpret_cast<const volatile uint8_t*>(p); }
+KM_HD uint32_t atomic_cas32(uint32_t* p, uint32_t cmp, uint32_t val) { return atomicCAS(p, cmp, val); }
+KM_HD int warp_index(const CtaCtx&) { return threadIdx.x >> 5; }
+KM_HD int warp_count(const CtaCtx&) { return blockDim.x >> 5; }
 KM_HD uint64_t atomic_cas64(uint64_t* p, uint64_t cmp, uint64_t val) {
     return atomicCAS(reinterpret_cast<unsigned long long*>(p), (unsigned long long)cmp, (unsigned long long)val);
 }
@@ -86,6 +106,8 @@ KM_HD uint64_t load_cg64(const uint64_t* p) { return __ldcg(reinterpret_cast<con
 KM_HD uint32_t load_cg32(const uint32_t* p) { return __ldcg(p); }
 KM_HD uint8_t load_cg8(const uint8_t* p) { return __ldcg(p); }
 KM_HD int clz64(uint64_t x) { return __clzll((long long)x); }
+KM_HD int clz32(uint32_t x) { return __clz((int)x); }
+KM_HD int ffs32(uint32_t x) { return __ffs((int)x); }
 KM_HD uint64_t mulhi64(uint64_t a, uint64_t b) { return __umul64hi(a, b); }
 KM_HD float add_f32(float a, float b) { return __fadd_rn(a, b); }
 #else
@@ -99,6 +121,18 @@ struct CtaCtx {
 typedef CtaCtx WarpCtx;
 KM_HD unsigned long long warp_sum64(unsigned long long v) { return v; }
 KM_HD bool warp_leader() { return true; }
+KM_HD uint32_t warp_min32(uint32_t v) { return v; }
+KM_HD uint32_t warp_or32(uint32_t v) { return v; }
+KM_HD uint32_t warp_match64(uint64_t) { return 1u; }
+KM_HD int warp_shfl32(int v, int) { return v; }
+KM_HD int warp_shfl_down32(int v, int) { return v; }
+KM_HD int popc32(uint32_t x) { return __builtin_popcount(x); }
+KM_HD void fence_block() {}
+KM_HD uint32_t load_shared_volatile32(const uint32_t* p) { return *p; }
+KM_HD uint8_t load_shared_volatile8(const uint8_t* p) { return *p; }
+KM_HD uint32_t atomic_cas32(uint32_t* p, uint32_t cmp, uint32_t val) { uint32_t o = *p; if (o == cmp) *p = val; return o; }
+KM_HD int warp_index(const CtaCtx&) { return 0; }
+KM_HD int warp_count(const CtaCtx&) { return 1; }
 KM_HD uint64_t atomic_cas64(uint64_t* p, uint64_t cmp, uint64_t val) { uint64_t o = *p; if (o == cmp) *p = val; return o; }
 KM_HD uint32_t atomic_add32(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
 KM_HD int32_t atomic_addi32(int32_t* p, int32_t v) { int32_t o = *p; *p = o + v; return o; }
@@ -110,6 +144,8 @@ KM_HD uint64_t load_cg64(const uint64_t* p) { return *p; }
 KM_HD uint32_t load_cg32(const uint32_t* p) { return *p; }
 KM_HD uint8_t load_cg8(const uint8_t* p) { return *p; }
 KM_HD int clz64(uint64_t x) { return x ? __builtin_clzll(x) : 64; }
+KM_HD int clz32(uint32_t x) { return x ? __builtin_clz(x) : 32; }
+KM_HD int ffs32(uint32_t x) { return __builtin_ffs((int)x); }
 KM_HD uint64_t mulhi64(uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)a * b) >> 64); }
 KM_HD float add_f32(float a, float b) { volatile float r = a + b; return r; }
 #endif

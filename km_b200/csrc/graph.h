@@ -70,6 +70,10 @@ struct ResultView {
     int64_t pool_cap;
     Row* rows;
     int32_t row_cap;
+    // spelled unique paths (MutationFinder.get_seq): nullptr = do not spell
+    char* seq_pool;
+    int64_t* path_seq_off;   // [path_cap] offset of each path's string, -1 = did not fit
+    int64_t seq_cap;
     // [0] paths used, [1] pool ints used, [2] rows used, [3] sequence chars used
     unsigned long long* used;
 };
@@ -92,8 +96,10 @@ struct GraphScratch {
     int32_t* after;    // [maxN]
     int32_t* hopF;     // [maxN]  edges between the source cap and the node along `before`
     int32_t* hopB;     // [maxN]  edges between the node and the sink cap along `after`
-    int32_t* cand;     // [maxN]  open set of the forward pass
+    int32_t* cand;     // [maxN]  open set of the forward pass; later the run list of the materialise step
     int32_t* cand2;    // [maxN]  open set of the backward pass
+    uint32_t* bitsF;   // [maxN/32 + 2]  bit u: u -> u+1 is u's only out-edge and u+1's only in-edge (a reference step)
+    uint32_t* bitsB;   // [maxN/32 + 2]  bit u: the same for u -> u-1 in the transposed graph
     uint8_t* eflag;    // [maxN]  bit c: edge to succ[c] still in edge_set; bit 4: cap edge
     int32_t* occ;      // [maxN]  nxtF during the tree phase, then occurrence counts of the solver
     int32_t* ce_a;     // [max_cand] edges that each yield one distinct alternative path
@@ -126,7 +132,7 @@ struct ScratchLayout {
     char* base;
     size_t stride;          // bytes per CTA
     size_t o_newidx, o_kept, o_keptk, o_hk, o_hv, o_succ, o_pred, o_deg, o_dist, o_dist2, o_before, o_after, o_hopF, o_hopB,
-        o_cand, o_cand2, o_eflag, o_occ;
+        o_cand, o_cand2, o_bitsF, o_bitsB, o_eflag, o_occ;
     size_t o_ce_a, o_ce_b, o_ce_len, o_upath, o_pdiff, o_grp, o_G, o_V, o_vec, o_acc, o_cols, o_members;
     int maxN, hcap, max_cand, max_paths, max_cols;
 };
@@ -143,6 +149,7 @@ KM_HOSTDEV ScratchLayout make_layout(int maxcap, int max_cand, int max_paths, in
     L.o_dist = put(4 * maxN); L.o_dist2 = put(4 * maxN); L.o_before = put(4 * maxN); L.o_after = put(4 * maxN);
     L.o_cand = put(4 * maxN); L.o_cand2 = put(4 * maxN);
     const size_t tree_end = o;
+    L.o_bitsF = put(4 * (maxN / 32 + 2)); L.o_bitsB = put(4 * (maxN / 32 + 2));
     L.o_eflag = put(maxN); L.o_occ = put(4 * maxN);
     L.o_ce_a = put(4 * nce); L.o_ce_b = put(4 * nce); L.o_ce_len = put(4 * nce);
     L.o_upath = put(4 * np);
@@ -171,6 +178,7 @@ KM_HOSTDEV GraphScratch carve(const ScratchLayout& L, char* p, int retry) {
     S.before = (int32_t*)(p + L.o_before); S.after = (int32_t*)(p + L.o_after);
     S.hopF = (int32_t*)(p + L.o_hopF); S.hopB = (int32_t*)(p + L.o_hopB);
     S.cand = (int32_t*)(p + L.o_cand); S.cand2 = (int32_t*)(p + L.o_cand2); S.eflag = (uint8_t*)(p + L.o_eflag);
+    S.bitsF = (uint32_t*)(p + L.o_bitsF); S.bitsB = (uint32_t*)(p + L.o_bitsB);
     S.occ = (int32_t*)(p + L.o_occ);
     S.ce_a = (int32_t*)(p + L.o_ce_a); S.ce_b = (int32_t*)(p + L.o_ce_b); S.ce_len = (int32_t*)(p + L.o_ce_len);
     S.upath = (int32_t*)(p + L.o_upath); S.pdiff = (int32_t*)(p + L.o_pdiff); S.grp = (int32_t*)(p + L.o_grp);
@@ -223,36 +231,105 @@ KM_HD int node_find(const GraphScratch& S, uint32_t hmask, uint64_t key) {
     }
 }
 
+// number of consecutive set bits at u, u+1, ... / at u, u-1, ... (bits past the last node are zero)
+KM_HD int run_up(const uint32_t* bits, int u) {
+    int r = 0;
+    for (;;) {
+        const int sh = (u + r) & 31;
+        const uint32_t inv = ~(bits[(u + r) >> 5] >> sh);       // the shifted-in top bits read as "not set"
+        const int c = ffs32(inv) - 1;                            // inv != 0 whenever sh > 0
+        if (inv != 0u && c < 32 - sh) return r + c;
+        r += 32 - sh;
+    }
+}
+KM_HD int run_down(const uint32_t* bits, int u) {
+    int r = 0;
+    for (;;) {
+        if (u - r < 0) return r;
+        const int sh = 31 - ((u - r) & 31);
+        const uint32_t inv = ~(bits[(u - r) >> 5] << sh);
+        const int c = inv ? clz32(inv) : 32;
+        if (c < 32 - sh) return r + c;
+        r += 32 - sh;
+    }
+}
+KM_HD bool bit_at(const uint32_t* bits, int u) { return (bits[u >> 5] >> (u & 31)) & 1u; }
+
 // Graph._get_paths (Graph.py:63-119) on adjacency lists; `forward` walks w, otherwise w
 // transposed.  Every distance is the float32 sum of its parent's distance and one weight, so the
-// pass is sequential and runs on ONE lane.  Two things keep the chain short:
+// pass is sequential and runs on ONE lane.  Three things keep the dependent chain short:
 //   * nxt[u] >= 0 marks a node whose only out-edge leads to a node with no other in-edge.  If that
 //     successor's distance is strictly below every open node's, it is the next node the reference
-//     would settle (Graph.py:113-114), nothing else changes, and the lane moves on after one
-//     dependent load -- almost every node of a target graph is of this kind.
+//     would settle (Graph.py:113-114) and nothing else changes -- almost every node of a target
+//     graph is of this kind; the next nxt entry is fetched while the distance is being compared.
+//   * a run of such steps along the reference (u -> u+1 -> ..., marked in `bits`) is taken in
+//     registers: one float32 add, one compare and one store per node, no dependent load.  The
+//     parents and hop counts of the nodes inside a run are filled in by the whole CTA afterwards
+//     (fill_runs): they are determined by the run alone.
 //   * otherwise the general step: the 4 neighbour slots come in with one 16-byte load, "unseen" is
 //     dist == +inf, and the open set is an explicit list that rarely holds more than two nodes.
 // Settling order = ascending (distance, index) and a node is re-parented only on a strictly smaller
 // float32 sum (Graph.py:103), exactly as in the reference.
 // dist/prev must be pre-filled with +inf / -1.
+#if KM_DEVICE_BUILD && defined(KM_PHASE_TIMERS)
+#define KM_DBG_DECL long long dbg_t0 = 0;
+#define KM_DBG_TICK(p) dbg_t0 = clock64();
+#define KM_DBG_TOCK(p, n) { atomicAdd(&km_phase_cycles[p], (unsigned long long)(clock64() - dbg_t0)); atomicAdd(&km_phase_cycles[(p) + 8], (unsigned long long)(n)); }
+#else
+#define KM_DBG_DECL
+#define KM_DBG_TICK(p)
+#define KM_DBG_TOCK(p, n)
+#endif
 KM_HD void shortest_tree(const GraphScratch& S, const GraphDims& d, bool forward, float* dist, int32_t* prev, int32_t* hop,
-                         int32_t* cand, const int32_t* nxt) {
+                         int32_t* cand, const int32_t* nxt, const uint32_t* bits) {
     const int32_t* nbr = forward ? S.succ : S.pred;
+    const int step = forward ? 1 : -1;
     int nc = 0;
     int u = forward ? d.src : d.snk;
     int hu = 0;
     float du = 0.0f, open_min = INFINITY;
     dist[u] = 0.0f;
     hop[u] = 0;
+    int x = nxt[u];
+    KM_DBG_DECL
     for (;;) {
-        const int x = nxt[u];
+        KM_DBG_TICK(forward ? 16 : 20)
         if (x >= 0) {
-            const float trial = add_f32((x & KM_NXT_REF) ? KM_REF_W : KM_ALT_W, du);
-            if (trial < open_min) {
+            if (bit_at(bits, u)) {
+                const int r = forward ? run_up(bits, u) : run_down(bits, u);
+                int done = 0;
+                float t = du;
+                // four steps at a time: the sums only grow, so testing the fourth against the open
+                // set covers the three before it
+                while (done + 4 <= r) {
+                    const float t1 = add_f32(KM_REF_W, t), t2 = add_f32(KM_REF_W, t1), t3 = add_f32(KM_REF_W, t2),
+                                t4 = add_f32(KM_REF_W, t3);
+                    if (!(t4 < open_min)) break;
+                    dist[u + step] = t1; dist[u + 2 * step] = t2; dist[u + 3 * step] = t3; dist[u + 4 * step] = t4;
+                    t = t4; u += 4 * step; done += 4;
+                }
+                while (done < r) {
+                    const float tn = add_f32(KM_REF_W, t);
+                    if (!(tn < open_min)) break;
+                    t = tn; u += step; dist[u] = t; ++done;
+                }
+                if (done) {
+                    du = t; hu += done;
+                    hop[u] = hu; prev[u] = u - step;
+                    x = nxt[u];
+                    KM_DBG_TOCK(forward ? 17 : 21, done)
+                    continue;
+                }
+            } else {
                 const int j = x & KM_NXT_MASK;
-                dist[j] = trial; prev[j] = u; hop[j] = ++hu;
-                u = j; du = trial;
-                continue;
+                const int xn = nxt[j];                                   // fetched early: off the critical path
+                const float trial = add_f32((x & KM_NXT_REF) ? KM_REF_W : KM_ALT_W, du);
+                if (trial < open_min) {
+                    dist[j] = trial; prev[j] = u; hop[j] = ++hu;
+                    u = j; du = trial; x = xn;
+                    KM_DBG_TOCK(forward ? 18 : 22, 1)
+                    continue;
+                }
             }
         }
         auto relax = [&](int j, float w) {
@@ -288,7 +365,7 @@ KM_HD void shortest_tree(const GraphScratch& S, const GraphDims& d, bool forward
                 if (u == 0) relax(d.src, KM_REF_W);
             }
         }
-        if (nc == 0) break;
+        if (nc == 0) { KM_DBG_TOCK(forward ? 19 : 23, 1) break; }
         // open node of least distance, lowest index on ties (Graph.py:113-114)
         int best = 0;
         float db = dist[cand[0]];
@@ -303,6 +380,8 @@ KM_HD void shortest_tree(const GraphScratch& S, const GraphDims& d, bool forward
         cand[best] = cand[--nc];
         open_min = INFINITY;
         for (int c = 0; c < nc; ++c) { const float da = dist[cand[c]]; open_min = da < open_min ? da : open_min; }
+        x = nxt[u];
+        KM_DBG_TOCK(forward ? 19 : 23, 1)
     }
 }
 
@@ -325,7 +404,7 @@ KM_HD bool graph_target(const Ctx& ctx, const TableView& T, const WalkView& W, c
     ctx.sync();
     for (int q = L + tid; q < n_all; q += nt) {
         S.newidx[q] = -1;
-        if (W.hflag[g.hbase + W.node_slot[g.nbase + q]]) {
+        if (W.node_slot[g.nbase + q] != KM_NO_SLOT) {            // the walk marks dropped nodes (walk.h)
             const int pos = atomic_addi32(&sh[0], 1);
             S.kept[pos] = q;
             S.keptk[pos] = W.node_kmer[g.nbase + q];
@@ -365,25 +444,41 @@ KM_HD bool graph_target(const Ctx& ctx, const TableView& T, const WalkView& W, c
 
     pt.mark(0);
     // ---- adjacency (MutationFinder.py:515-531): edge i -> j iff kmer[i][1:] == kmer[j][:-1], i != j ------
+    // Each node probes the map with its 4 successor k-mers; predecessor lists are filled by the
+    // successors' owners (slot order is irrelevant to every later step).
+    int32_t* indeg = S.hopB;                          // free until the tree phase
+    for (int i = tid; i < n_real; i += nt) {
+        Slot4 none; none.v[0] = none.v[1] = none.v[2] = none.v[3] = -1;
+        *reinterpret_cast<Slot4*>(S.pred + 4 * i) = none;
+        indeg[i] = 0;
+    }
+    for (int w = tid; w < (d.N >> 5) + 2; w += nt) { S.bitsF[w] = 0u; S.bitsB[w] = 0u; }
+    ctx.sync();
     for (int i = tid; i < n_real; i += nt) {
         const uint64_t km = R.out_kmer[g.nbase + i];
-        Slot4 sv, pv;
-        int outdeg = i == L - 1 ? 1 : 0, indeg = i == 0 ? 1 : 0;          // cap edges (:545-551)
+        Slot4 sv;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             int js = node_find(S, hmask, succ_kmer(km, c, T.kmask));
-            int jp = node_find(S, hmask, pred_kmer(km, c, k));
             if (js == i) js = -1;                       // `if i != j` (:530)
-            if (jp == i) jp = -1;
-            sv.v[c] = js; pv.v[c] = jp;
-            outdeg += js >= 0; indeg += jp >= 0;
+            sv.v[c] = js;
+            if (js >= 0) S.pred[4 * js + atomic_addi32(&indeg[js], 1)] = i;
         }
         *reinterpret_cast<Slot4*>(S.succ + 4 * i) = sv;
-        *reinterpret_cast<Slot4*>(S.pred + 4 * i) = pv;
-        S.deg[i] = (uint8_t)(outdeg | (indeg << 4));
     }
-    if (tid == 0) { S.deg[d.src] = 1; S.deg[d.snk] = 1 << 4; }
     ctx.sync();                                       // the k-mer map is dead from here on
+    for (int i = tid; i < d.N; i += nt) {
+        int od = 0, id = 0;
+        if (i == d.src) od = 1;
+        else if (i == d.snk) id = 1;
+        else {
+            const Slot4 s4 = *reinterpret_cast<const Slot4*>(S.succ + 4 * i);
+            od = (s4.v[0] >= 0) + (s4.v[1] >= 0) + (s4.v[2] >= 0) + (s4.v[3] >= 0) + (i == L - 1);   // cap edges (:545-551)
+            id = indeg[i] + (i == 0);
+        }
+        S.deg[i] = (uint8_t)(od | (id << 4));
+    }
+    ctx.sync();
     // simple edges: (u, j) with u's only out-edge and j's only in-edge (see shortest_tree)
     int32_t* nxtF = S.occ;
     int32_t* nxtB = S.newidx;
@@ -400,14 +495,20 @@ KM_HD bool graph_target(const Ctx& ctx, const TableView& T, const WalkView& W, c
                 const Slot4 s4 = *reinterpret_cast<const Slot4*>(S.succ + 4 * i);
 #pragma unroll
                 for (int c = 0; c < 4; ++c) if (s4.v[c] >= 0) j = s4.v[c];
-                if ((S.deg[j] >> 4) == 1) f = j | (edge_is_ref(d, i, j) ? KM_NXT_REF : 0);
+                if ((S.deg[j] >> 4) == 1) {
+                    f = j | (edge_is_ref(d, i, j) ? KM_NXT_REF : 0);
+                    if (j == i + 1 && i < L - 1) atomic_or32(&S.bitsF[i >> 5], 1u << (i & 31));
+                }
             }
             if ((dg >> 4) == 1) {
                 int u = d.src;
                 const Slot4 p4 = *reinterpret_cast<const Slot4*>(S.pred + 4 * i);
 #pragma unroll
                 for (int c = 0; c < 4; ++c) if (p4.v[c] >= 0) u = p4.v[c];
-                if ((S.deg[u] & 15) == 1) b = u | (edge_is_ref(d, u, i) ? KM_NXT_REF : 0);
+                if ((S.deg[u] & 15) == 1) {
+                    b = u | (edge_is_ref(d, u, i) ? KM_NXT_REF : 0);
+                    if (u == i - 1 && u < L - 1) atomic_or32(&S.bitsB[i >> 5], 1u << (i & 31));
+                }
             }
         }
         nxtF[i] = f; nxtB[i] = b;
@@ -418,8 +519,21 @@ KM_HD bool graph_target(const Ctx& ctx, const TableView& T, const WalkView& W, c
     // ---- two shortest-path trees (Graph.py:175-176), concurrently on two warps ------
     {
         const int lane_b = nt > 32 ? 32 : 0;                 // the backward pass's lane
-        if (tid == 0) shortest_tree(S, d, true, S.dist, S.before, S.hopF, S.cand, nxtF);
-        if (tid == lane_b) shortest_tree(S, d, false, S.dist2, S.after, S.hopB, S.cand2, nxtB);
+        if (tid == 0) shortest_tree(S, d, true, S.dist, S.before, S.hopF, S.cand, nxtF, S.bitsF);
+        if (tid == lane_b) shortest_tree(S, d, false, S.dist2, S.after, S.hopB, S.cand2, nxtB, S.bitsB);
+    }
+    ctx.sync();
+    // parents and hop counts inside reference runs: node i entered over the step (i-1 -> i) of a
+    // run has parent i-1 and lies (i - s) hops past the run's first node s
+    for (int i = tid; i < L; i += nt) {
+        if (i >= 1 && bit_at(S.bitsF, i - 1) && S.dist[i] < INFINITY) {
+            const int r = run_down(S.bitsF, i - 1);
+            S.before[i] = i - 1; S.hopF[i] = S.hopF[i - r] + r;
+        }
+        if (i + 1 < L && bit_at(S.bitsB, i + 1) && S.dist2[i] < INFINITY) {
+            const int r = run_up(S.bitsB, i + 1);
+            S.after[i] = i + 1; S.hopB[i] = S.hopB[i + r] + r;
+        }
     }
     ctx.sync();
     pt.mark(2);
@@ -512,50 +626,96 @@ KM_HD bool graph_target(const Ctx& ctx, const TableView& T, const WalkView& W, c
     }
 
     pt.mark(4);
-    // ---- allocate path ids and pool space (lane 0) ---------------------------------------
+    // ---- allocate everything this target will write, in one place (lane 0) -------------------
+    // path ids, pool ints, rows and spelled characters come from four independent atomics issued
+    // back to back; rows are reserved by their upper bound (every path gives one vs_ref row and at
+    // most one cluster row, MutationFinder.py:613-648, 758-811).
     if (tid == 0) {
         int nu = n_cand;
-        bool overflow = false;
         int64_t total = 0;
         for (int c = 0; c < nu; ++c) total += S.ce_len[c] - 2;     // caps stripped (MutationFinder.py:562)
-        int first = 0;
+        int first = 0, first_row = 0;
+        int64_t off = 0, soff = 0;
+        bool overflow = false;
         if (nu > 0) {
-            first = (int)atomic_add64(&R.used[0], (unsigned long long)nu);
-            if (first + nu > R.path_cap) overflow = true;
+            const unsigned long long a0 = atomic_add64(&R.used[0], (unsigned long long)nu);
+            const unsigned long long a1 = atomic_add64(&R.used[1], (unsigned long long)total);
+            const unsigned long long a2 = atomic_add64(&R.used[2], 2ull * (unsigned long long)nu);
+            const unsigned long long a3 = R.seq_pool ? atomic_add64(&R.used[3], (unsigned long long)(total + (int64_t)nu * (k - 1))) : 0ull;
+            first = (int)a0; off = (int64_t)a1; first_row = (int)a2; soff = (int64_t)a3;
+            overflow = a0 + nu > (unsigned long long)R.path_cap || a1 + total > (unsigned long long)R.pool_cap ||
+                       a2 + 2ull * nu > (unsigned long long)R.row_cap ||
+                       (R.seq_pool && a3 + total + (int64_t)nu * (k - 1) > (unsigned long long)R.seq_cap);
         }
-        if (!overflow && nu > 0) {
-            int64_t off = (int64_t)atomic_add64(&R.used[1], (unsigned long long)total);
-            if (off + total > R.pool_cap) overflow = true;
-            else for (int u = 0; u < nu; ++u) {
-                const int len = S.ce_len[u] - 2;
-                R.path_off[first + u] = off;
-                R.path_len[first + u] = len;
-                off += len;
-            }
+        if (!overflow) for (int u = 0; u < nu; ++u) {
+            const int len = S.ce_len[u] - 2;
+            R.path_off[first + u] = off;
+            R.path_len[first + u] = len;
+            off += len;
         }
         if (overflow) { atomic_or32(&W.status[t], KM_ST_PATH_OVERFLOW); nu = -1; first = 0; }
         R.t_n_paths[t] = nu < 0 ? 0 : nu;
         R.t_path_first[t] = first;
-        if (nu < 0) { R.t_n_rows[t] = 0; R.t_row_first[t] = 0; }
+        if (nu <= 0) { R.t_n_rows[t] = 0; R.t_row_first[t] = 0; }
         sh[2] = nu;
         sh[3] = first;
+        sh[6] = first_row;
+        sh[10] = (int)(soff & 0x7FFFFFFF); sh[11] = (int)(soff >> 31);
     }
     ctx.sync();
     const int nu = sh[2], first = sh[3];
     if (nu < 0) return false;
 
     pt.mark(5);
-    // ---- materialise: two lanes per unique path, one per chain; positions come from the hop counts ----
+    // ---- materialise: two lanes per unique path, one per chain; positions come from the hop counts.
+    // A lane steps through novel nodes one dependent load at a time but crosses a reference run in
+    // one go (the run bitmaps give its length); long runs are only recorded and then written by the
+    // whole CTA.
+    int32_t* runs = S.cand;                                  // 4 ints per entry: path, position, first node, length
+    const int run_cap = S.maxN / 4;
+    if (tid == 0) sh[9] = 0;
+    ctx.sync();
     for (int w = tid; w < 2 * nu; w += nt) {
         const int u = w >> 1;
         int32_t* dst = R.pool + R.path_off[first + u];
         const int a = S.ce_a[u];
+        auto emit = [&](int pos, int node, int len) {         // dst[pos + o] = node + o
+            int e = run_cap;
+            if (len >= 8) e = atomic_addi32(&sh[9], 1);
+            if (e < run_cap) { runs[4 * e] = u; runs[4 * e + 1] = pos; runs[4 * e + 2] = node; runs[4 * e + 3] = len; }
+            else for (int o = 0; o < len; ++o) dst[pos + o] = node + o;
+        };
         if (!(w & 1)) {
             int p = S.hopF[a] - 1;                                   // source cap dropped
-            for (int cur = a; cur != d.src; cur = S.before[cur]) dst[p--] = cur;
+            int cur = a;
+            while (cur != d.src) {
+                if (cur >= 1 && cur < L && bit_at(S.bitsF, cur - 1)) {
+                    const int r = run_down(S.bitsF, cur - 1);        // cur-r .. cur are consecutive ancestors
+                    emit(p - r, cur - r, r + 1);
+                    p -= r + 1;
+                    cur = S.before[cur - r];
+                } else { dst[p--] = cur; cur = S.before[cur]; }
+            }
         } else {
             int p = S.hopF[a];
-            for (int cur = S.ce_b[u]; cur != d.snk; cur = S.after[cur]) dst[p++] = cur;
+            int cur = S.ce_b[u];
+            while (cur != d.snk) {
+                if (cur + 1 < L && bit_at(S.bitsB, cur + 1)) {
+                    const int r = run_up(S.bitsB, cur + 1);          // cur .. cur+r follow each other
+                    emit(p, cur, r + 1);
+                    p += r + 1;
+                    cur = S.after[cur + r];
+                } else { dst[p++] = cur; cur = S.after[cur]; }
+            }
+        }
+    }
+    ctx.sync();
+    {
+        const int n_runs = sh[9] < run_cap ? sh[9] : run_cap;
+        for (int e = 0; e < n_runs; ++e) {
+            int32_t* dst = R.pool + R.path_off[first + runs[4 * e]] + runs[4 * e + 1];
+            const int node = runs[4 * e + 2], len = runs[4 * e + 3];
+            for (int o = tid; o < len; o += nt) dst[o] = node + o;
         }
     }
     ctx.sync();
@@ -595,9 +755,31 @@ KM_HD bool graph_target(const Ctx& ctx, const TableView& T, const WalkView& W, c
                 R.path_len[first + S.upath[u]] = S.ce_len[u];
             }
         }
+        ctx.sync();
+    }
+    pt.mark(7);
+    // ---- spell every unique path once (MutationFinder.get_seq, :375-403): first k-mer, then the last
+    // base of each following node; rows print slices of these strings
+    if (R.seq_pool) {
+        int64_t soff = ((int64_t)sh[11] << 31) | (int64_t)sh[10];
+        for (int p = 0; p < nu; ++p) {
+            const int len = R.path_len[first + p];
+            const int32_t* idx = R.pool + R.path_off[first + p];
+            if (tid == 0) R.path_seq_off[first + p] = soff;
+            if (len > 0) {
+                const uint64_t k0 = R.out_kmer[g.nbase + idx[0]];
+                for (int c = tid; c < len + k - 1; c += nt) {
+                    int code;
+                    if (c < k) code = (int)((k0 >> (2 * (k - 1 - c))) & 3ull);
+                    else code = (int)(R.out_kmer[g.nbase + idx[c - k + 1]] & 3ull);
+                    R.seq_pool[soff + c] = "ACGT"[code];
+                }
+            }
+            soff += len + k - 1;
+        }
     }
     ctx.sync();
-    pt.mark(7);
+    pt.mark(8);
     return sh[2] >= 0;
 }
 

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include "quant.h"
+#include "walk_small.h"
 #include "synth.h"
 
 namespace km {
@@ -134,11 +135,37 @@ __global__ void __launch_bounds__(256) km_get_child_kernel(TableView T, const ui
 }
 
 // ---- K3: walk, one WARP per target ----------------------------------------------------------
+// Two launches: the shared-memory walk takes every target of ordinary size (walk_small.h); the
+// general walk, whose per-target state lives in HBM, takes the targets the first one deferred.
 #define KM_WALK_WARPS 4
+#define KM_PROBE_WARPS 8
+// K3a: level 0 of every walk, one warp per 32 reference k-mers, flat over the batch
+__global__ void __launch_bounds__(32 * KM_PROBE_WARPS) km_ref_probe_kernel(TableView T, WalkView W, FindParams P) {
+    WarpCtx ctx;
+    const int ch = (int)blockIdx.x * KM_PROBE_WARPS + (int)(threadIdx.x >> 5);
+    if (ch >= W.n_chunks) return;
+    ref_probe_chunk(ctx, T, W, P, W.chunk_target[ch], W.chunk_start[ch]);
+}
+
+__global__ void __launch_bounds__(32 * KM_WALK_WARPS) km_walk_small_kernel(TableView T, WalkView W, FindParams P) {
+    __shared__ WalkSmall M[KM_WALK_WARPS];
+    WarpCtx ctx;
+    const int t = (int)blockIdx.x * KM_WALK_WARPS + (int)(threadIdx.x >> 5);
+    if (t >= W.n_targets) return;
+    const TargetGeom g = target_geom(W, t, T.k);
+    if (!walk_small_fits(g)) { if ((threadIdx.x & 31) == 0) W.status[t] = KM_ST_WALK_DEFER; return; }   // also drops the probe's limit flag
+    walk_small_target(ctx, T, W, P, t, M[threadIdx.x >> 5]);
+}
+
 __global__ void __launch_bounds__(32 * KM_WALK_WARPS) km_walk_kernel(TableView T, WalkView W, FindParams P) {
     WarpCtx ctx;
     const int t = (int)blockIdx.x * KM_WALK_WARPS + (int)(threadIdx.x >> 5);
-    if (t < W.n_targets) walk_target(ctx, T, W, P, t);
+    if (t >= W.n_targets) return;
+    if (!(W.status[t] & KM_ST_WALK_DEFER)) return;
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) { W.status[t] = 0; W.lookups[t] = 0; W.n_kept[t] = 0; }
+    __syncwarp();
+    walk_target(ctx, T, W, P, t);
 }
 
 // ---- K4 + K5: graph, paths, FP64 quantification; persistent CTAs over targets -----------------
@@ -158,10 +185,9 @@ __host__ __device__ inline ScratchLayout small_layout() {
 #define KM_ST_FATAL (KM_ST_BAD_BASE | KM_ST_DUP_KMER | KM_ST_NODE_OVERFLOW | KM_ST_NODE_LIMIT | KM_ST_TOO_SHORT)
 
 template <bool SMALL>
-__global__ void __launch_bounds__(KM_CTA) km_graph_kernel(TableView T, WalkView W, ScratchLayout SL, ResultView R,
-                                                          char* seq_pool, int64_t* path_seq_off, int64_t seq_cap) {
+__global__ void __launch_bounds__(KM_CTA) km_graph_kernel(TableView T, WalkView W, ScratchLayout SL, ResultView R) {
     extern __shared__ __align__(16) char km_smem[];
-    __shared__ int sh[16];
+    __shared__ int sh[32];
     CtaCtx ctx;
     const GraphScratch S = SMALL ? carve(small_layout(), km_smem, 1)
                                  : carve(SL, SL.base + (size_t)blockIdx.x * SL.stride, 0);
@@ -184,37 +210,7 @@ __global__ void __launch_bounds__(KM_CTA) km_graph_kernel(TableView T, WalkView 
         }
         GraphDims d;
         if (!graph_target(ctx, T, W, S, R, t, &d, sh)) continue;
-        const int n_paths = sh[2], first = sh[3];
-        PhaseTimer pt;
-        // spell every unique path once (MutationFinder.get_seq, :375-403): first k-mer, then
-        // the last base of each following node; rows print slices of these strings
-        const int64_t nbase = W.node_off[t];
-        for (int p = 0; p < n_paths; ++p) {
-            const int len = R.path_len[first + p];
-            const int32_t* idx = R.pool + R.path_off[first + p];
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                const int64_t off = len > 0 ? (int64_t)atomicAdd(&R.used[3], (unsigned long long)(len + T.k - 1)) : 0;
-                sh[4] = (int)(off & 0x7FFFFFFF); sh[5] = (int)(off >> 31);
-            }
-            __syncthreads();
-            const int64_t off = ((int64_t)sh[5] << 31) | (int64_t)sh[4];
-            const bool fits_seq = off + len + T.k - 1 <= seq_cap;
-            if (threadIdx.x == 0) path_seq_off[first + p] = fits_seq ? off : -1;
-            if (!fits_seq) { if (threadIdx.x == 0) atomicOr(&W.status[t], KM_ST_PATH_OVERFLOW); }
-            else if (len > 0) {
-                const uint64_t k0 = R.out_kmer[nbase + idx[0]];
-                for (int c = threadIdx.x; c < len + T.k - 1; c += blockDim.x) {
-                    int code;
-                    if (c < T.k) code = (int)((k0 >> (2 * (T.k - 1 - c))) & 3ull);
-                    else code = (int)(R.out_kmer[nbase + idx[c - T.k + 1]] & 3ull);
-                    seq_pool[off + c] = "ACGT"[code];
-                }
-            }
-        }
-        __syncthreads();
-        pt.mark(8);
-        emit_rows(ctx, T, W, S, R, t, d, n_paths, first, sh);
+        emit_rows(ctx, T, W, S, R, t, d, sh[2], sh[3], sh[6], sh);
         __syncthreads();
     }
 }

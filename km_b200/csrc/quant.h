@@ -254,7 +254,7 @@ KM_HD int solve_columns(const Ctx& ctx, const GraphScratch& S, const uint32_t* c
     return sh[4];
 }
 
-// min(counts over the path) by the whole CTA; `slot` is CTA-shared.  An empty path gives 2^32-1.
+// min(counts over the path) by the whole group; `slot` is shared by the group.  An empty path gives 2^32-1.
 template <class Ctx>
 KM_HD int64_t min_count(const Ctx& ctx, const uint32_t* counts, const PathView& p, int* slot) {
     uint32_t* us = reinterpret_cast<uint32_t*>(slot);
@@ -269,28 +269,149 @@ KM_HD int64_t min_count(const Ctx& ctx, const uint32_t* counts, const PathView& 
     return r;
 }
 
-// quantify_paths + quantify_clusters for target t.  `dims`, `n_paths`, `first_path` come
-// from graph_target.  All threads of the CTA must call this.
+// Two-column quantification by ONE WARP: `path` is a real (possibly clipped) path, `range` a slice
+// of the reference.  This is every vs_ref row ([alt, ref], MutationFinder.py:618-631) and every
+// single-variant cluster ([ref_clip, alt_clip], :784-790).  The path's occurrence counts go into
+// byte lane `lane8` of S.occ (a node occurs at most once on each of the two tree chains a path is
+// stitched from), so the warps of a CTA work on different rows at the same time without CTA
+// barriers; sums are combined by shuffles.  `path_first` says which column comes first in the
+// reference's column order.  Returns refine iterations in *iters; coef/rvaf in reference order.
+struct Quant2 {
+    double coef[2], rvaf[2];
+    int64_t min_cov;
+    int iters;
+};
+
+template <class WCtx>
+KM_HD Quant2 quant_pair(const WCtx& wctx, const GraphScratch& S, const uint32_t* counts, int n_nodes, const PathView& path,
+                        const PathView& range, bool path_first, int lane8) {
+    const int lane = wctx.tid(), nl = wctx.nt();
+    const uint32_t one = 1u << (8 * lane8);
+    uint32_t* occ = reinterpret_cast<uint32_t*>(S.occ);
+    unsigned long long h_p = 0ull, h_r = 0ull, g_pr = 0ull, g_pp = 0ull;
+    uint32_t mn = 0xFFFFFFFFu;
+    for (int p = lane; p < path.len; p += nl) {
+        const int node = pv_at(path, p);
+        const uint32_t c = counts[node];
+        atomic_add32(&occ[node], one);
+        h_p += (unsigned long long)(float)c;                    // counts -> float32 (PathQuant.py:99), an integer
+        g_pr += (unsigned long long)(node >= range.begin && node < range.begin + range.len);
+        mn = c < mn ? c : mn;
+    }
+    for (int p = lane; p < range.len; p += nl) h_r += (unsigned long long)(float)counts[range.begin + p];
+    wctx.sync();
+    for (int p = lane; p < path.len; p += nl) g_pp += (unsigned long long)((occ[pv_at(path, p)] >> (8 * lane8)) & 255u);
+    wctx.sync();
+    for (int p = lane; p < path.len; p += nl) atomic_add32(&occ[pv_at(path, p)], 0u - one);
+    h_p = warp_sum64(h_p); h_r = warp_sum64(h_r); g_pr = warp_sum64(g_pr); g_pp = warp_sum64(g_pp);
+    mn = warp_min32(mn);
+    Quant2 q;
+    q.iters = 0; q.min_cov = 0; q.coef[0] = q.coef[1] = q.rvaf[0] = q.rvaf[1] = 0.0;
+    if (lane == 0) {
+        // exact integer normal equations in the reference's column order
+        const unsigned long long g_rr = (unsigned long long)range.len;
+        const unsigned long long a00 = path_first ? g_pp : g_rr, a11 = path_first ? g_rr : g_pp, a01 = g_pr;
+        double G[4], h[2], grad[2];
+        G[0] = (double)a00; G[1] = G[2] = (double)a01; G[3] = (double)a11;
+        h[0] = (double)(path_first ? h_p : h_r); h[1] = (double)(path_first ? h_r : h_p);
+        const long long det = (long long)a00 * (long long)a11 - (long long)a01 * (long long)a01;
+        double* c = q.coef;
+        if (det != 0) {                                          // full rank: Cramer on exact integers
+            c[0] = det2(h[0], h[1], G[1], G[3]) / (double)det;
+            c[1] = det2(G[0], G[1], h[0], h[1]) / (double)det;
+        } else if (a00 + a11 == 0ull) {
+            c[0] = c[1] = 0.0;
+        } else {
+            // rank 1: G = lambda u u^T, lambda = trace; any non-zero column v of G is parallel to u,
+            // and the minimum-norm solution (what lstsq returns, PathQuant.py:116) is v (v.h) / (|v|^2 lambda)
+            const double v0 = a00 >= a11 ? G[0] : G[1], v1 = a00 >= a11 ? G[1] : G[3];
+            const double sc = (v0 * h[0] + v1 * h[1]) / ((v0 * v0 + v1 * v1) * (G[0] + G[3]));
+            c[0] = v0 * sc; c[1] = v1 * sc;
+        }
+        q.iters = refine_and_ratio(G, h, 2, n_nodes, c, q.rvaf, grad);
+        q.min_cov = (int64_t)mn;
+    }
+    return q;
+}
+
+// One output row.  `variant` is the (possibly clipped) path, `refv` the (possibly clipped) reference.
+KM_HD void write_row(const ResultView& R, const WalkView& W, const uint64_t* kmers, int t, int k, int row_index, int kind,
+                     const PathView& refv, const PathView& variant, const Diff& df, int path_id, int offset, int cluster_id,
+                     int cluster_n, int iters, int64_t mc, double rvaf, double expr, double ref_rvaf, double ref_expr) {
+    int dl, il;
+    const int type = classify(kmers, refv, variant, df, &dl, &il);
+    Row& row = R.rows[row_index];
+    row.target = t; row.kind = kind; row.type = type;
+    row.name_start = df.start + k + offset; row.name_end = df.end_ref + 1 + offset;
+    row.path_id = path_id; row.var_begin = variant.begin; row.var_end = variant.begin + variant.len;
+    row.ref_begin = refv.begin; row.ref_end = refv.begin + refv.len;
+    row.del_begin = refv.begin + df.start; row.del_len = dl;
+    row.ins_begin = variant.begin + df.start; row.ins_len = il;
+    row.start_off = offset; row.cluster_id = cluster_id; row.cluster_n = cluster_n; row.n_iter = iters;
+    row.min_cov = mc;
+    row.rvaf = rvaf; row.expr = expr; row.ref_rvaf = ref_rvaf; row.ref_expr = ref_expr;
+    if (iters < 0) atomic_or32(&W.status[t], KM_ST_SOLVER_WATCHDOG);
+    if (refv.len - (df.end_ref - df.start) + (df.end_var - df.start) != variant.len)     // MutationFinder.py:431-440
+        atomic_or32(&W.status[t], KM_ST_NAME_MISMATCH);
+}
+
+// the clipped columns of cluster c (MutationFinder.py:700-723): cols[0] = reference slice,
+// cols[1 + j] = member j in join order; members[] receives the path numbers
+KM_HD void cluster_columns(const GraphScratch& S, const ResultView& R, const GraphDims& d, int n_paths, int first_path, int c,
+                           const int32_t* crec, PathView* cols, int32_t* members) {
+    const int lo = crec[4 * c], hi = crec[4 * c + 1], size = crec[4 * c + 2];
+    for (int p = 0; p < n_paths; ++p) {
+        const int gcode = S.grp[p];
+        if (gcode >= 0 && (gcode & 0xFFFF) == c) members[gcode >> 16] = p;
+    }
+    int span = 0;
+    for (int j = 0; j < size; ++j) {
+        const int p = members[j];
+        int a = S.pdiff[4 * p + 2] - S.pdiff[4 * p + 1] + 1;      // abs(end_var - end_ref + 1) (:710-712)
+        a = a < 0 ? -a : a;
+        span = a > span ? a : span;
+    }
+    const int off0 = lo - span > 0 ? lo - span : 0;             // (:713)
+    // Python slices clamp to the sequence (:714, :720)
+    const int ref_stop = hi < d.L ? hi : d.L;
+    cols[0].idx = nullptr; cols[0].begin = off0; cols[0].len = ref_stop - off0 > 0 ? ref_stop - off0 : 0;
+    for (int j = 0; j < size; ++j) {
+        const int p = members[j];
+        const int plen = R.path_len[first_path + p];
+        int stop = S.pdiff[4 * p + 2] + hi - S.pdiff[4 * p + 1];   // (:719)
+        stop = stop < plen ? stop : plen;
+        const int beg = off0 < plen ? off0 : plen;
+        cols[1 + j].idx = R.pool + R.path_off[first_path + p];
+        cols[1 + j].begin = beg;
+        cols[1 + j].len = stop - beg > 0 ? stop - beg : 0;
+    }
+}
+
+// quantify_paths + quantify_clusters for target t.  `dims`, `n_paths`, `first_path` come from
+// graph_target, which also reserved rows [first_row, first_row + 2*n_paths).  `sh` = 32 ints of
+// CTA-shared memory.  All threads of the CTA must call this.
 template <class Ctx>
 KM_HD void emit_rows(const Ctx& ctx, const TableView& T, const WalkView& W, const GraphScratch& S,
-                     const ResultView& R, int t, const GraphDims& d, int n_paths, int first_path, int* sh) {
+                     const ResultView& R, int t, const GraphDims& d, int n_paths, int first_path, int first_row, int* sh) {
     const int k = T.k;
     const int tid = ctx.tid();
+    const int wid = warp_index(ctx), nw = warp_count(ctx);
+    const WarpCtx wctx;
+    const int lane = wctx.tid();
     const int64_t nbase = W.node_off[t];
     const uint64_t* kmers = R.out_kmer + nbase;
     const uint32_t* counts = R.out_count + nbase;  // caps are not stored: rows never touch them
-    double* coef = S.vec + 4 * S.max_cols;
-    double* rvaf = S.vec + 5 * S.max_cols;
-    int* slot = sh + 8;                              // reduction scratch (sh holds 16 ints)
+    int* slot = sh + 8;                              // CTA-wide reduction scratch
+    int* wslot = sh + 16 + wid;                      // this warp's reduction scratch
     const PathView ref = {nullptr, 0, d.L};
 
     PhaseTimer pt;
-    for (int i = tid; i < d.N; i += ctx.nt()) S.occ[i] = 0;     // held nxtF during the tree phase; the solver needs zeros
-    // ---- per-path diffs against the whole reference (CTA-parallel scans) ---------
-    for (int p = 0; p < n_paths; ++p) {
+    for (int i = tid; i < d.N; i += ctx.nt()) S.occ[i] = 0;     // held nxtF during the tree phase; the solvers need zeros
+    // ---- per-path diffs against the whole reference: one warp per path ---------
+    for (int p = wid; p < n_paths; p += nw) {
         const PathView alt = {R.pool + R.path_off[first_path + p], 0, R.path_len[first_path + p]};
-        const Diff df = diff_paths(ctx, ref, alt, k, slot);
-        if (tid == 0) {
+        const Diff df = diff_paths(wctx, ref, alt, k, wslot);
+        if (lane == 0) {
             S.pdiff[4 * p + 0] = df.start; S.pdiff[4 * p + 1] = df.end_ref;
             S.pdiff[4 * p + 2] = df.end_var; S.pdiff[4 * p + 3] = df.end_ref_overlap;
             S.grp[p] = -2;                       // -2 = still in variant_set
@@ -301,9 +422,9 @@ KM_HD void emit_rows(const Ctx& ctx, const TableView& T, const WalkView& W, cons
     pt.mark(10);
     // ---- cluster discovery by lane 0 (MutationFinder.py:656-694) ---------------
     // grp[p] = cluster id | (join order << 16), -1 = none; clusters are numbered in seed order
+    int32_t* crec = S.grp + S.max_paths;         // lo, hi, size, first row per cluster, in seed order
     if (tid == 0) {
         int n_clusters = 0, n_rows = n_paths;
-        int32_t* crec = S.grp + S.max_paths;     // lo, hi, size per cluster, in seed order
         for (int seed = 0; seed < n_paths; ++seed) {
             if (S.grp[seed] != -2) continue;     // set.pop() on small ints == ascending order
             int lo = S.pdiff[4 * seed], hi = S.pdiff[4 * seed + 1];
@@ -330,111 +451,79 @@ KM_HD void emit_rows(const Ctx& ctx, const TableView& T, const WalkView& W, cons
             // a lone path equal to the reference forms no cluster (:703-707): the path IS the
             // reference exactly when the common prefix covers both completely
             if (size == 1 && R.path_len[first_path + seed] == d.L && S.pdiff[4 * seed] == d.L) { S.grp[seed] = -1; continue; }
-            crec[4 * cid + 0] = lo; crec[4 * cid + 1] = hi; crec[4 * cid + 2] = size; crec[4 * cid + 3] = 0;
+            crec[4 * cid + 0] = lo; crec[4 * cid + 1] = hi; crec[4 * cid + 2] = size; crec[4 * cid + 3] = first_row + n_rows;
             ++n_clusters;
             n_rows += size;
         }
-        int first_row = 0;
-        bool overflow = false;
-        if (n_rows > 0) {
-            first_row = (int)atomic_add64(&R.used[2], (unsigned long long)n_rows);
-            if (first_row + n_rows > R.row_cap) overflow = true;
-        }
-        if (overflow) { atomic_or32(&W.status[t], KM_ST_PATH_OVERFLOW); n_rows = 0; n_clusters = 0; }
         R.t_n_rows[t] = n_rows;
         R.t_row_first[t] = first_row;
         sh[5] = n_clusters;
-        sh[6] = first_row;
-        sh[7] = overflow ? 1 : 0;
     }
     ctx.sync();
     const int n_clusters = sh[5];
-    const int first_row = sh[6];
-    if (sh[7]) return;
-    int32_t* crec = S.grp + S.max_paths;
-    PathView* cols = S.cols;
 
     pt.mark(11);
-    // ---- vs_ref rows (MutationFinder.py:613-648) -------------------------------
-    for (int p = 0; p < n_paths; ++p) {
-        const PathView alt = {R.pool + R.path_off[first_path + p], 0, R.path_len[first_path + p]};
-        if (tid == 0) { cols[0] = alt; cols[1] = ref; }
-        ctx.sync();
-        pt.mark(12);
-        const int iters = solve_columns(ctx, S, counts, d.N, cols, 2, coef, rvaf, sh);
-        pt.mark(14);
-        const int64_t mc = min_count(ctx, counts, alt, slot);
-        pt.mark(15);
-        if (tid == 0) {
-            const Diff df = {S.pdiff[4 * p], S.pdiff[4 * p + 1], S.pdiff[4 * p + 2], S.pdiff[4 * p + 3]};
-            int dl, il;
-            const int type = classify(kmers, ref, alt, df, &dl, &il);
-            const bool is_ref = alt.len == d.L && df.start == d.L;      // alt_index == ref_index (:627)
-            double c0 = coef[0], c1 = coef[1], r0 = rvaf[0], r1 = rvaf[1];
-            if (is_ref) {
-                // adjust_for_reference (PathQuant.py:151-154).  With all-zero coef rVAF aliases
-                // coef, so both turn NaN and the `coef >= 0` overwrite skips them.
-                const bool aliased = (c0 > c1 ? c0 : c1) == 0.0;
-                r0 = r1 = NAN;
-                if (aliased) { c0 = c1 = NAN; }
-                else { if (c0 >= 0.0) c0 = -1.0; if (c1 >= 0.0) c1 = -1.0; }   // min(counts) is the cap's -1
+    // ---- two-column jobs, one per warp at a time: the vs_ref row of every path (:613-648) and every
+    // single-variant cluster (:758-811) --------------------------------------------------------------
+    for (int j = wid; j < n_paths + n_clusters; j += nw) {
+        if (j < n_paths) {
+            const int p = j;
+            const PathView alt = {R.pool + R.path_off[first_path + p], 0, R.path_len[first_path + p]};
+            const Quant2 q = quant_pair(wctx, S, counts, d.N, alt, ref, true, wid);
+            if (lane == 0) {
+                const Diff df = {S.pdiff[4 * p], S.pdiff[4 * p + 1], S.pdiff[4 * p + 2], S.pdiff[4 * p + 3]};
+                const bool is_ref = alt.len == d.L && df.start == d.L;      // alt_index == ref_index (:627)
+                double c0 = q.coef[0], c1 = q.coef[1], r0 = q.rvaf[0], r1 = q.rvaf[1];
+                if (is_ref) {
+                    // adjust_for_reference (PathQuant.py:151-154).  With all-zero coef rVAF aliases
+                    // coef, so both turn NaN and the `coef >= 0` overwrite skips them.
+                    const bool aliased = (c0 > c1 ? c0 : c1) == 0.0;
+                    r0 = r1 = NAN;
+                    if (aliased) { c0 = c1 = NAN; }
+                    else { if (c0 >= 0.0) c0 = -1.0; if (c1 >= 0.0) c1 = -1.0; }   // min(counts) is the cap's -1
+                }
+                write_row(R, W, kmers, t, k, first_row + p, 0, ref, alt, df, first_path + p, 0, 0, 0, q.iters, q.min_cov, r0, c0, r1, c1);
             }
-            Row& row = R.rows[first_row + p];
-            row.target = t; row.kind = 0; row.type = type;
-            row.name_start = df.start + k; row.name_end = df.end_ref + 1;
-            row.path_id = first_path + p; row.var_begin = 0; row.var_end = alt.len;
-            row.ref_begin = 0; row.ref_end = d.L;
-            row.del_begin = df.start; row.del_len = dl; row.ins_begin = df.start; row.ins_len = il;
-            row.start_off = 0; row.cluster_id = 0; row.cluster_n = 0; row.n_iter = iters;
-            row.min_cov = mc;
-            row.rvaf = r0; row.expr = c0; row.ref_rvaf = r1; row.ref_expr = c1;
-            if (iters < 0) atomic_or32(&W.status[t], KM_ST_SOLVER_WATCHDOG);
-            if (d.L - (df.end_ref - df.start) + (df.end_var - df.start) != alt.len)
-                atomic_or32(&W.status[t], KM_ST_NAME_MISMATCH);
+        } else {
+            const int c = j - n_paths;
+            if (crec[4 * c + 2] != 1) continue;                  // wider clusters: whole CTA, below
+            // a one-member cluster: columns [ref_clip, alt_clip]
+            int p = 0;
+            for (int v = 0; v < n_paths; ++v) if (S.grp[v] == c) p = v;      // join order 0 -> code == cluster id
+            const int lo = crec[4 * c], hi = crec[4 * c + 1];
+            int span = S.pdiff[4 * p + 2] - S.pdiff[4 * p + 1] + 1;          // (:710-712)
+            span = span < 0 ? -span : span;
+            const int off0 = lo - span > 0 ? lo - span : 0;                  // (:713)
+            const int ref_stop = hi < d.L ? hi : d.L;
+            const PathView ref_clip = {nullptr, off0, ref_stop - off0 > 0 ? ref_stop - off0 : 0};
+            const int plen = R.path_len[first_path + p];
+            int stop = S.pdiff[4 * p + 2] + hi - S.pdiff[4 * p + 1];         // (:719)
+            stop = stop < plen ? stop : plen;
+            const int beg = off0 < plen ? off0 : plen;
+            const PathView clip = {R.pool + R.path_off[first_path + p], beg, stop - beg > 0 ? stop - beg : 0};
+            const Quant2 q = quant_pair(wctx, S, counts, d.N, clip, ref_clip, false, wid);
+            const Diff df = diff_paths(wctx, ref_clip, clip, k, wslot);
+            if (lane == 0)
+                write_row(R, W, kmers, t, k, crec[4 * c + 3], 1, ref_clip, clip, df, first_path + p, off0, c + 1, 1, q.iters,
+                          q.min_cov, q.rvaf[1], q.coef[1], q.rvaf[0], q.coef[0]);
         }
-        ctx.sync();
     }
+    ctx.sync();
 
     pt.mark(12);
-    // ---- cluster rows (MutationFinder.py:700-723, 758-811) ----------------------
-    int row_cursor = first_row + n_paths;
+    // ---- clusters of several variants (MutationFinder.py:700-723, 758-811): whole CTA, general solver ----
+    double* coef = S.vec + 4 * S.max_cols;
+    double* rvaf = S.vec + 5 * S.max_cols;
+    PathView* cols = S.cols;
+    int32_t* members = S.members;
     for (int c = 0; c < n_clusters; ++c) {
-        const int lo = crec[4 * c], hi = crec[4 * c + 1], size = crec[4 * c + 2];
+        const int size = crec[4 * c + 2];
+        if (size == 1) continue;
         if (size + 1 > S.max_cols) {
             if (tid == 0) atomic_or32(&W.status[t], S.retry ? KM_ST_RETRY_LARGE : (uint32_t)KM_ST_TOO_MANY_COLS);
-            // rows stay unset; the general pass redoes the target, or the host refuses it
-            row_cursor += size;
-            continue;
+            continue;          // rows stay unset; the general pass redoes the target, or the host refuses it
         }
-        int32_t* members = S.members;
-        if (tid == 0) {
-            // members in join order
-            for (int p = 0; p < n_paths; ++p) {
-                const int gcode = S.grp[p];
-                if (gcode >= 0 && (gcode & 0xFFFF) == c) members[gcode >> 16] = p;
-            }
-            int span = 0;
-            for (int j = 0; j < size; ++j) {
-                const int p = members[j];
-                int a = S.pdiff[4 * p + 2] - S.pdiff[4 * p + 1] + 1;      // abs(end_var - end_ref + 1) (:710-712)
-                a = a < 0 ? -a : a;
-                span = a > span ? a : span;
-            }
-            const int off0 = lo - span > 0 ? lo - span : 0;             // (:713)
-            // Python slices clamp to the sequence (:714, :720)
-            const int ref_stop = hi < d.L ? hi : d.L;
-            cols[0].idx = nullptr; cols[0].begin = off0; cols[0].len = ref_stop - off0 > 0 ? ref_stop - off0 : 0;
-            for (int j = 0; j < size; ++j) {
-                const int p = members[j];
-                const int plen = R.path_len[first_path + p];
-                int stop = S.pdiff[4 * p + 2] + hi - S.pdiff[4 * p + 1];   // (:719)
-                stop = stop < plen ? stop : plen;
-                const int beg = off0 < plen ? off0 : plen;
-                cols[1 + j].idx = R.pool + R.path_off[first_path + p];
-                cols[1 + j].begin = beg;
-                cols[1 + j].len = stop - beg > 0 ? stop - beg : 0;
-            }
-        }
+        if (tid == 0) cluster_columns(S, R, d, n_paths, first_path, c, crec, cols, members);
         ctx.sync();
         const int offset = cols[0].begin;
         const PathView ref_clip = cols[0];
@@ -443,27 +532,11 @@ KM_HD void emit_rows(const Ctx& ctx, const TableView& T, const WalkView& W, cons
             const PathView clip = cols[1 + j];
             const Diff df = diff_paths(ctx, ref_clip, clip, k, slot);
             const int64_t mc = min_count(ctx, counts, clip, slot);
-            if (tid == 0) {
-                const int p = members[j];
-                int dl, il;
-                const int type = classify(kmers, ref_clip, clip, df, &dl, &il);
-                Row& row = R.rows[row_cursor + j];
-                row.target = t; row.kind = 1; row.type = type;
-                row.name_start = df.start + k + offset; row.name_end = df.end_ref + 1 + offset;
-                row.path_id = first_path + p; row.var_begin = clip.begin; row.var_end = clip.begin + clip.len;
-                row.ref_begin = ref_clip.begin; row.ref_end = ref_clip.begin + ref_clip.len;
-                row.del_begin = ref_clip.begin + df.start; row.del_len = dl;
-                row.ins_begin = clip.begin + df.start; row.ins_len = il;
-                row.start_off = offset; row.cluster_id = c + 1; row.cluster_n = size; row.n_iter = iters;
-                row.min_cov = mc;
-                row.rvaf = rvaf[1 + j]; row.expr = coef[1 + j]; row.ref_rvaf = rvaf[0]; row.ref_expr = coef[0];
-                if (ref_clip.len - (df.end_ref - df.start) + (df.end_var - df.start) != clip.len)
-                    atomic_or32(&W.status[t], KM_ST_NAME_MISMATCH);
-            }
+            if (tid == 0)
+                write_row(R, W, kmers, t, k, crec[4 * c + 3] + j, 1, ref_clip, clip, df, first_path + members[j], offset, c + 1, size,
+                          iters, mc, rvaf[1 + j], coef[1 + j], rvaf[0], coef[0]);
         }
-        if (tid == 0 && iters < 0) atomic_or32(&W.status[t], KM_ST_SOLVER_WATCHDOG);
         ctx.sync();
-        row_cursor += size;
     }
     pt.mark(13);
 }

@@ -64,6 +64,10 @@ struct WalkView {
     int32_t* n_kept;          // kept nodes (excludes the two caps)
     uint32_t* status;
     unsigned long long* lookups;  // [n] table lookups issued (measurement only)
+    // chunks of <= 32 consecutive reference k-mers, flat over all targets (ref_probe_chunk)
+    const int32_t* chunk_target;
+    const int32_t* chunk_start;
+    int n_chunks;
 };
 
 KM_HD uint32_t pack_meta(int depth, int breaks) { return ((uint32_t)depth << 8) | (uint32_t)(breaks > 255 ? 255 : breaks); }
@@ -250,9 +254,13 @@ KM_HD void walk_target(const Ctx& ctx, const TableView& T, const WalkView& W, co
     }
 
     // kept-node count and the node limit (MutationFinder.py:143-148)
+    // a dropped node's slot entry is overwritten with KM_NO_SLOT: the graph pass reads one array
+    // (node_slot) to tell kept from dropped instead of chasing the visited set
     int kept = 0;
-    for (int q = g.L + tid; q < n_all; q += nt)
-        kept += load_cg8(&W.hflag[g.hbase + W.node_slot[g.nbase + q]]) ? 1 : 0;
+    for (int q = g.L + tid; q < n_all; q += nt) {
+        if (load_cg8(&W.hflag[g.hbase + W.node_slot[g.nbase + q]])) kept += 1;
+        else W.node_slot[g.nbase + q] = KM_NO_SLOT;
+    }
     if (kept) atomic_addi32(&W.n_kept[t], kept);
     if (st) atomic_or32(&W.status[t], st);
     if (nlook) atomic_add64(&W.lookups[t], nlook);

@@ -171,6 +171,13 @@ class FindPlan:
         check(lib().km_find_plan_last_ms(self._h, ctypes.byref(w), ctypes.byref(g)))
         return w.value, g.value
 
+    def kernel_ms(self):
+        """(probe_ms, walk_ms, graph_ms) of the most recent launch: reference-probe kernel (with the
+        memsets), the two walk kernels, the two graph kernels."""
+        out = (ctypes.c_float * 3)()
+        check(lib().km_find_plan_kernel_ms(self._h, out))
+        return out[0], out[1], out[2]
+
     def fetch(self, want_graph=True):
         h = ctypes.c_void_p()
         check(lib().km_find_plan_fetch(self._h, int(bool(want_graph)), ctypes.byref(h)))

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../km_b200/csrc/quant.h"
+#include "../../km_b200/csrc/walk_small.h"
 #include "../../km_b200/csrc/synth.h"
 
 using namespace km;
@@ -72,7 +73,19 @@ int emu_find_target(void* h, const uint8_t* codes, int len, double ratio, int64_
     W.n_nodes = &n_nodes; W.n_kept = &n_kept; W.status = &status; W.lookups = &lookups;
     FindParams P; P.ratio = ratio; P.count = count; P.max_stack = steps; P.max_break = branchs; P.max_node = nodes;
     CtaCtx ctx;
-    walk_target(ctx, t->v, W, P, 0);
+    // the two walk kernels: shared-memory walk first, the general one for what it defers
+    bool walked = false;
+    {
+        const TargetGeom g = target_geom(W, 0, k);
+        if (walk_small_fits(g)) {
+            W.chunk_target = nullptr; W.chunk_start = nullptr; W.n_chunks = 0;
+            for (int i0 = 0; i0 < g.L; i0 += ctx.nt()) ref_probe_chunk(ctx, t->v, W, P, 0, i0);     // km_ref_probe_kernel
+            static WalkSmall M;
+            memset(&M, 0x5A, sizeof(M));
+            walked = walk_small_target(ctx, t->v, W, P, 0, M);
+        }
+    }
+    if (!walked) { status = 0; lookups = 0; n_kept = 0; walk_target(ctx, t->v, W, P, 0); }
     *out_lookups = lookups;
     *out_n = 0; *out_n_paths = 0; *out_n_rows = 0;
     if (status & (KM_ST_BAD_BASE | KM_ST_DUP_KMER | KM_ST_NODE_OVERFLOW | KM_ST_NODE_LIMIT | KM_ST_TOO_SHORT)) return (int)status;
@@ -87,6 +100,7 @@ int emu_find_target(void* h, const uint8_t* codes, int len, double ratio, int64_
     R.out_kmer = okmer.data(); R.out_count = ocount.data();
     R.path_off = path_off.data(); R.path_len = out_path_len; R.pool = out_pool; R.path_cap = path_cap; R.pool_cap = pool_cap;
     R.rows = out_rows; R.row_cap = row_cap; R.used = used;
+    R.seq_pool = nullptr; R.path_seq_off = nullptr; R.seq_cap = 0;
 
     // the two passes of km_graph_kernel: small capacities with deferral, then the general ones
     auto run_pass = [&](int maxcap, int max_cand, int max_paths, int max_cols, int retry) -> bool {
@@ -95,10 +109,10 @@ int emu_find_target(void* h, const uint8_t* codes, int len, double ratio, int64_
         std::vector<char> arena(SL.stride + 64, (char)0x5A);
         char* basep = arena.data() + ((64 - ((uintptr_t)arena.data() & 63)) & 63);
         const GraphScratch S = carve(SL, basep, retry);
-        int sh[16] = {0};
+        int sh[32] = {0};
         GraphDims d;
         if (!graph_target(ctx, t->v, W, S, R, 0, &d, sh)) return false;
-        emit_rows(ctx, t->v, W, S, R, 0, d, sh[2], sh[3], sh);
+        emit_rows(ctx, t->v, W, S, R, 0, d, sh[2], sh[3], sh[6], sh);
         return true;
     };
     const int n_all = n_nodes < cap ? n_nodes : cap;

@@ -86,7 +86,7 @@ def test_bundled_catalog_matches_reference_records(engine, bundled, bundled_gold
             seqs = ["".join(ko.read_fasta_records(os.path.join(bundled, "data/catalog", cat, r["target"] + ".fa"))[0])
                     for r in recs]
             res = t.find_batch(seqs)
-            assert res.timing["launches"] == 3         # walk + two graph passes for the whole catalog
+            assert res.timing["launches"] == 5         # reference probe + two walk passes + two graph passes for the whole catalog
             for i, rec in enumerate(recs):
                 assert int(res.status[i]) & ~16 == 0
                 db = "./data/jf/%s.jf" % sample
@@ -156,7 +156,8 @@ def test_panel_against_oracle_with_full_background(engine):
                                 [[float(r.rvaf), float(r.expr), float(r.ref_expr)] for r in want], got["raw"])
         assert not errs, (panel.names[i], errs)
         assert got["nodes"] == sorted([k, int(v)] for k, v in f.node_data.items())
-        assert int(res.lookups[i]) >= ko.algorithmic_lookups(f)
+        # the reference-probe kernel reuses a neighbour's count for the successor along the reference
+        assert int(res.lookups[i]) >= ko.algorithmic_lookups(f) - (len(panel.targets[i]) - 31)
         flips += fl
     assert flips <= 4
 

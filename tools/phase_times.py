@@ -25,14 +25,22 @@ for _ in range(3):
 plan.last_ms()
 L = lib()
 L.km_debug_phase_cycles.argtypes = [ctypes.c_void_p, ctypes.c_int]
-buf = (ctypes.c_ulonglong * 32)()
+buf = (ctypes.c_ulonglong * 64)()
 L.km_debug_phase_cycles(buf, 1)
 plan.launch()
 w, g = plan.last_ms()
 L.km_debug_phase_cycles(buf, 0)
-tot = sum(buf)
-print("walk %.3f ms  graph %.3f ms   targets %d" % (w, g, n))
-for i, c in enumerate(buf):
+tot = sum(buf[:16])
+print("walk %.3f ms  graph %.3f ms   targets %d   (probe %.3f, walks %.3f, graph %.3f)" % ((w, g, n) + tuple(plan.kernel_ms())))
+WALK = {32: "walk: set-up", 33: "walk: phase 1 (ref k-mers)", 34: "walk: level 0", 35: "walk: later levels", 36: "walk: peel", 37: "walk: results"}
+for i in range(32, 40):
+    if buf[i]:
+        print("%2d %-28s %8.1f cycles/target" % (i, WALK[i], buf[i] / n))
+TREE = {16: "fwd tree: all iterations", 17: "fwd run", 18: "fwd simple step", 19: "fwd general", 20: "bwd all", 21: "bwd run", 22: "bwd simple step", 23: "bwd general"}
+for i in range(16, 24):
+    if buf[i]:
+        print("%2d %-28s %8.1f cycles/target  count/target %.1f  cycles/count %.1f" % (i, TREE[i], buf[i] / n, buf[i + 8] / n, buf[i] / max(1, buf[i + 8])))
+for i, c in enumerate(buf[:16]):
     if c:
         print("%2d %-28s %8.1f cycles/target  %5.1f%%" % (i, NAMES.get(i, "?"), c / n, 100.0 * c / tot))
 print("sum %.0f cycles/target" % (tot / n))
