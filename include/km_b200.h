@@ -186,6 +186,17 @@ int64_t km_result_format_target(const km_result* r, int32_t target, const char* 
 int64_t km_result_format_all(const km_result* r, const char* db_name, const char* names_host, const int64_t* name_off,
                              int32_t threads, char* buf, int64_t buf_len);
 
+/* The same text without a copy: *text points at the result's own buffer (valid until km_result_free or a
+ * call with other names); returns its length. */
+int64_t km_result_text(const km_result* r, const char* db_name, const char* names_host, const int64_t* name_off,
+                       int32_t threads, const char** text);
+
+/* ---- test hooks for the host-side text path (no GPU needed) ------------------------------ */
+/* "%.{prec}f" as the formatter prints it (prec 0..3), NUL-terminated into buf64; returns the length */
+int km_debug_format_fixed(double v, int prec, char* buf64);
+/* natural-sort comparison of two strings (common.natsortkey, common.py:95-116): -1, 0, 1 */
+int km_debug_nat_cmp(const char* a, const char* b);
+
 /* ---- measurement helpers (bench.py) --------------------------------------------------- */
 /* per-phase SM cycles of the graph pass (only in a -DKM_PHASE_TIMERS build; tools/phase_times.py) */
 int km_debug_phase_cycles(unsigned long long* out64, int reset);   /* 64 counters */

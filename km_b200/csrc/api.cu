@@ -8,6 +8,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -70,6 +72,58 @@ struct Arena {
     void release() { if (base) { host ? cudaFreeHost(base) : cudaFree(base); base = nullptr; cap = 0; } }
 };
 
+// Pinned host blocks recycled between results: a result's arrays are the direct target of the
+// device-to-host copies (no pageable staging, no zero-filled vectors), and cudaMallocHost -- which
+// costs milliseconds -- is paid once per size class instead of once per call.
+struct PinPool {
+    std::mutex m;
+    std::vector<std::pair<char*, size_t>> idle;
+    int acquire(size_t bytes, char** out, size_t* cap) {
+        std::lock_guard<std::mutex> g(m);
+        int best = -1;
+        for (size_t i = 0; i < idle.size(); ++i)
+            if (idle[i].second >= bytes && (best < 0 || idle[i].second < idle[(size_t)best].second)) best = (int)i;
+        if (best >= 0) { *out = idle[(size_t)best].first; *cap = idle[(size_t)best].second; idle.erase(idle.begin() + best); return 0; }
+        // nothing fits: drop the smaller idle blocks (they would never be picked again for this workload)
+        for (auto& b : idle) cudaFreeHost(b.first);
+        idle.clear();
+        const size_t want = bytes + bytes / 4 + (1 << 16);
+        cudaError_t e = cudaMallocHost((void**)out, want);
+        if (e != cudaSuccess) return fail(KM_E_CUDA, "pinned alloc of %zu bytes failed: %s", want, cudaGetErrorString(e));
+        *cap = want;
+        return 0;
+    }
+    void release(char* p, size_t cap) { if (p) { std::lock_guard<std::mutex> g(m); idle.emplace_back(p, cap); } }
+    ~PinPool() { for (auto& b : idle) cudaFreeHost(b.first); }
+};
+
+template <class T> struct Span {
+    T* p = nullptr;
+    size_t n = 0;
+    T* data() const { return p; }
+    size_t size() const { return n; }
+    T& operator[](size_t i) const { return p[i]; }
+};
+struct PinBlock {
+    std::shared_ptr<PinPool> pool;
+    char* base = nullptr;
+    size_t cap = 0, used = 0;
+    int reserve(const std::shared_ptr<PinPool>& from, size_t bytes) {
+        drop();
+        pool = from;
+        used = 0;
+        return pool->acquire(bytes, &base, &cap);
+    }
+    template <class T> Span<T> take(size_t n) {
+        used = (used + 63) & ~(size_t)63;
+        Span<T> s; s.p = reinterpret_cast<T*>(base + used); s.n = n;
+        used += n * sizeof(T);
+        return s;
+    }
+    void drop() { if (base && pool) pool->release(base, cap); base = nullptr; cap = 0; }
+    ~PinBlock() { drop(); }
+};
+
 struct km_table {
     int device = 0, k = 31, canonical = 1;
     uint64_t n_buckets = 0, n_keys = 0;
@@ -79,6 +133,7 @@ struct km_table {
     cudaEvent_t ev[8] = {};
     Arena dev, pin;            // lookups / inserts
     Arena dev_find, pin_find;  // km_find_batch workspace, reused across calls
+    std::shared_ptr<PinPool> pool = std::make_shared<PinPool>();   // result buffers (outlive the table if a result does)
     int sm_count = 148;
     TableView view() const {
         TableView v;
@@ -377,22 +432,26 @@ extern "C" int km_get_child_batch(km_table* t, const uint64_t* kmers, uint64_t n
 // ---- find_mutation batch ------------------------------------------------------------------------
 struct km_result {
     int n_targets = 0, k = 31;
-    std::vector<uint32_t> status;
-    std::vector<int32_t> n_nodes, path_first, path_count, row_first, row_count, path_len;
-    std::vector<int64_t> node_off, path_off, path_seq_off, seq_off;
-    std::vector<uint64_t> node_kmer, lookups;
-    std::vector<uint32_t> node_count;
-    std::vector<int32_t> path_pool;
-    std::vector<km_row> rows;
-    std::vector<char> seq_pool;     // spelled unique paths
+    PinBlock head, body;            // per-target arrays; paths, rows, spelled sequences (+ graph arrays)
+    Span<uint32_t> status;
+    Span<int32_t> n_nodes, path_first, path_count, row_first, row_count, path_len;
+    Span<int64_t> path_off, path_seq_off;
+    Span<unsigned long long> lookups, used;
+    Span<uint64_t> node_kmer;
+    Span<uint32_t> node_count;
+    Span<int32_t> path_pool;
+    Span<km_row> rows;
+    Span<char> seq_pool;            // spelled unique paths
+    std::vector<int64_t> node_off, seq_off;
     std::string targets;            // concatenated target sequences (for Reference_sequence / deleted bases)
     float ms_h2d = 0, ms_walk = 0, ms_graph = 0, ms_d2h = 0, ms_total = 0;
     int n_launches = 0, n_retries = 0;
     bool has_graph = true;
     unsigned long long bytes_h2d = 0, bytes_d2h = 0;
-    // km_result_format_all is called twice (size, then fill): the text is built once
+    // the formatted text of all targets is built once and kept (km_result_format_all / km_result_text)
     mutable std::string fmt_key;
-    mutable std::vector<std::string> fmt_parts;
+    mutable std::unique_ptr<char[]> text;
+    mutable int64_t text_len = -1;
 };
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -408,7 +467,6 @@ struct km_plan {
     std::string targets;
     std::vector<int64_t> seq_off, node_off, hash_off;
     std::vector<int32_t> chunk_target, chunk_start;   // <= 32 consecutive reference k-mers each (ref_probe_chunk)
-    std::vector<uint8_t> codes;
     std::vector<int32_t> extra;
     int64_t pool_cap = 0, seq_cap = 0, n_node = 0, n_hash = 0, n_code = 0;
     int32_t path_cap = 0, row_cap = 0, extra_max = 0;
@@ -514,12 +572,16 @@ static int plan_upload(km_plan* p, cudaStream_t s) {
     int32_t* h_ct = p->pin->take<int32_t>(n_chunks);
     int32_t* h_cs = p->pin->take<int32_t>(n_chunks);
     if (n_chunks) { memcpy(h_ct, p->chunk_target.data(), 4 * n_chunks); memcpy(h_cs, p->chunk_start.data(), 4 * n_chunks); }
-    memcpy(h_codes, p->codes.data(), p->n_code);
+    memcpy(h_codes, p->targets.data(), p->n_code);          // letters; km_encode_kernel turns them into codes on the device
     memcpy(h_seq_off, p->seq_off.data(), 8 * (n + 1));
     memcpy(h_node_off, p->node_off.data(), 8 * (n + 1));
     memcpy(h_hash_off, p->hash_off.data(), 8 * (n + 1));
     CU(cudaEventRecord(p->t->ev[0], s));
     CU(cudaMemcpyAsync((void*)p->W.codes, h_codes, p->n_code, cudaMemcpyHostToDevice, s));
+    if (p->n_code) {
+        km_encode_kernel<<<grid_for(p->t, (uint64_t)p->n_code, 256, 8), 256, 0, s>>>(const_cast<uint8_t*>(p->W.codes), p->n_code);
+        CU(cudaGetLastError());
+    }
     CU(cudaMemcpyAsync((void*)p->W.seq_off, h_seq_off, 8 * (n + 1), cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync((void*)p->W.node_off, h_node_off, 8 * (n + 1), cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync((void*)p->W.hash_off, h_hash_off, 8 * (n + 1), cudaMemcpyHostToDevice, s));
@@ -569,10 +631,15 @@ static int plan_download(km_plan* p, cudaStream_t s, km_result* res, bool want_g
     const WalkView& W = p->W;
     const ResultView& R = p->R;
     res->n_targets = n; res->k = t->k;
-    res->status.resize(n); res->n_nodes.resize(n); res->path_first.resize(n); res->path_count.resize(n);
-    res->row_first.resize(n); res->row_count.resize(n); res->lookups.resize(n);
-    unsigned long long used[4] = {0, 0, 0, 0};
+    if (int rc = res->head.reserve(t->pool, 36 * (size_t)n + 64 * 10)) return rc;
+    res->status = res->head.take<uint32_t>(n); res->n_nodes = res->head.take<int32_t>(n);
+    res->path_count = res->head.take<int32_t>(n); res->path_first = res->head.take<int32_t>(n);
+    res->row_count = res->head.take<int32_t>(n); res->row_first = res->head.take<int32_t>(n);
+    res->lookups = res->head.take<unsigned long long>(n); res->used = res->head.take<unsigned long long>(4);
+    unsigned long long* used = res->used.data();
+    used[0] = used[1] = used[2] = used[3] = 0;
     if (n) {
+        // per-target state and result ints sit back to back on the device (plan_layout)
         CU(cudaMemcpyAsync(res->status.data(), W.status, 4 * n, cudaMemcpyDeviceToHost, s));
         CU(cudaMemcpyAsync(res->n_nodes.data(), R.t_n, 4 * n, cudaMemcpyDeviceToHost, s));
         CU(cudaMemcpyAsync(res->path_count.data(), R.t_n_paths, 4 * n, cudaMemcpyDeviceToHost, s));
@@ -585,8 +652,13 @@ static int plan_download(km_plan* p, cudaStream_t s, km_result* res, bool want_g
     CU(cudaStreamSynchronize(s));
     const size_t n_paths = std::min<unsigned long long>(used[0], p->path_cap), n_pool = std::min<unsigned long long>(used[1], p->pool_cap);
     const size_t n_rows = std::min<unsigned long long>(used[2], p->row_cap), n_seq = std::min<unsigned long long>(used[3], p->seq_cap);
-    res->path_off.resize(n_paths); res->path_len.resize(n_paths); res->path_seq_off.resize(n_paths);
-    res->rows.resize(n_rows); res->seq_pool.resize(n_seq);
+    const size_t n_node = want_graph ? (size_t)p->n_node : 0, n_pool_c = want_graph ? n_pool : 0;
+    if (int rc = res->body.reserve(t->pool, 20 * n_paths + sizeof(Row) * n_rows + n_seq + 4 * n_pool_c + 12 * n_node + 64 * 10)) return rc;
+    res->path_off = res->body.take<int64_t>(n_paths); res->path_len = res->body.take<int32_t>(n_paths);
+    res->path_seq_off = res->body.take<int64_t>(n_paths);
+    res->rows = res->body.take<km_row>(n_rows); res->seq_pool = res->body.take<char>(n_seq);
+    res->path_pool = res->body.take<int32_t>(n_pool_c);
+    res->node_kmer = res->body.take<uint64_t>(n_node); res->node_count = res->body.take<uint32_t>(n_node);
     res->node_off = p->node_off;
     if (n_paths) {
         CU(cudaMemcpyAsync(res->path_off.data(), R.path_off, 8 * n_paths, cudaMemcpyDeviceToHost, s));
@@ -597,17 +669,16 @@ static int plan_download(km_plan* p, cudaStream_t s, km_result* res, bool want_g
     if (n_seq) CU(cudaMemcpyAsync(res->seq_pool.data(), p->d_seq_pool, n_seq, cudaMemcpyDeviceToHost, s));
     res->has_graph = want_graph;
     if (want_graph) {
-        res->path_pool.resize(n_pool);
-        res->node_kmer.resize(p->n_node); res->node_count.resize(p->n_node);
         if (n_pool) CU(cudaMemcpyAsync(res->path_pool.data(), R.pool, 4 * n_pool, cudaMemcpyDeviceToHost, s));
-        if (p->n_node) {
-            CU(cudaMemcpyAsync(res->node_kmer.data(), R.out_kmer, 8 * p->n_node, cudaMemcpyDeviceToHost, s));
-            CU(cudaMemcpyAsync(res->node_count.data(), R.out_count, 4 * p->n_node, cudaMemcpyDeviceToHost, s));
+        if (n_node) {
+            CU(cudaMemcpyAsync(res->node_kmer.data(), R.out_kmer, 8 * n_node, cudaMemcpyDeviceToHost, s));
+            CU(cudaMemcpyAsync(res->node_count.data(), R.out_count, 4 * n_node, cudaMemcpyDeviceToHost, s));
         }
     }
     res->bytes_h2d = p->bytes_h2d;
     res->bytes_d2h = 36ull * n + 32 + 20ull * n_paths + sizeof(Row) * n_rows + n_seq +
                      (want_graph ? 4ull * n_pool + 12ull * p->n_node : 0ull);
+    res->text_len = -1; res->text.reset(); res->fmt_key.clear();
     CU(cudaEventRecord(t->ev[4], s));
     CU(cudaStreamSynchronize(s));
     float ms;
@@ -629,8 +700,6 @@ static int plan_init(km_table* t, const char* seqs, const int64_t* offsets, int3
     p->targets.assign(seqs ? seqs : "", (size_t)total);
     p->seq_off.assign(1, 0);
     if (n) p->seq_off.assign(offsets, offsets + n + 1);
-    p->codes.resize((size_t)total);
-    for (int64_t i = 0; i < total; ++i) { const int c = base_code(seqs[i]); p->codes[i] = c < 0 ? 255 : (uint8_t)c; }
     int64_t n_ref = 0;
     for (int i = 0; i < n; ++i) n_ref += std::max<int64_t>(0, offsets[i + 1] - offsets[i] - t->k + 1);
     p->extra.assign((size_t)n, p->prm.extra_nodes > 0 ? p->prm.extra_nodes : 256);
@@ -740,9 +809,9 @@ extern "C" int km_find_batch(km_table* t, const char* seqs, const int64_t* offse
     km_plan plan;
     if (int rc = plan_init(t, seqs, offsets, n, params, &plan, true)) return rc;
     km_result* res = new km_result();
-    res->targets.swap(plan.targets);
     res->seq_off = plan.seq_off;
     if (int rc = plan_fetch(&plan, res, (params->flags & KM_FIND_NO_GRAPH) == 0)) { delete res; return rc; }
+    res->targets.swap(plan.targets);      // after the fetch: a capacity retry uploads the letters again
     *out = res;
     return 0;
 }
@@ -756,7 +825,7 @@ extern "C" int km_result_get(const km_result* r, km_result_view* v) {
     v->path_first = r->path_first.data(); v->path_count = r->path_count.data();
     v->path_off = r->path_off.data(); v->path_len = r->path_len.data(); v->path_pool = r->path_pool.data();
     v->row_first = r->row_first.data(); v->row_count = r->row_count.data(); v->rows = r->rows.data();
-    v->lookups = r->lookups.data();
+    v->lookups = reinterpret_cast<const uint64_t*>(r->lookups.data());
     v->ms_h2d = r->ms_h2d; v->ms_walk = r->ms_walk; v->ms_graph = r->ms_graph; v->ms_d2h = r->ms_d2h; v->ms_total = r->ms_total;
     v->n_launches = r->n_launches; v->n_retries = r->n_retries; v->has_graph = r->has_graph ? 1 : 0;
     v->bytes_h2d = r->bytes_h2d; v->bytes_d2h = r->bytes_d2h;
@@ -768,140 +837,245 @@ extern "C" void km_result_free(km_result* r) { delete r; }
 // ---- row formatting (PathQuant.Path.__str__, MutationFinder.get_paths) ------------------------
 static const char* TYPE_NAME[6] = {"Reference", "Substitution", "ITD", "Indel", "Insertion", "Deletion"};
 
-static void fmt_float(std::string& out, double v, int prec) {
-    char buf[64];
-    if (std::isnan(v)) { out += "nan"; return; }          // Python prints nan without a sign
-    if (std::isinf(v)) { out += v < 0 ? "-inf" : "inf"; return; }
-    snprintf(buf, sizeof(buf), "%.*f", prec, v);
-    out += buf;
+// "%.{prec}f" of a double, digit for digit what Python / glibc print (the exact binary value rounded
+// half-to-even at the last printed digit), without snprintf: |v| = m * 2^e with m < 2^53, so
+// m * 10^prec fits 64 bits for prec <= 3 and the rounding is decided on integers.
+static char* put_uint(char* o, unsigned long long v) {
+    char tmp[24]; int n = 0;
+    do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+    while (n) *o++ = tmp[--n];
+    return o;
 }
-
-// common.natsortkey (common.py:95-116): split on digit runs; digit runs compare as ints,
-// other chunks as lower-cased strings.
-struct NatTok { bool num; unsigned long long val; std::string txt; };
-static std::vector<NatTok> nat_split(const std::string& s) {
-    // re.split('([0-9]+)', key): alternating text / digits, text chunks may be empty
-    std::vector<NatTok> out;
-    size_t i = 0;
-    std::string cur;
-    while (i <= s.size()) {
-        if (i < s.size() && isdigit((unsigned char)s[i])) {
-            out.push_back({false, 0, cur}); cur.clear();
-            unsigned long long v = 0; std::string digits;
-            while (i < s.size() && isdigit((unsigned char)s[i])) { v = v * 10 + (s[i] - '0'); digits += s[i]; ++i; }
-            out.push_back({true, v, digits});
-        } else if (i < s.size()) { cur += (char)tolower((unsigned char)s[i]); ++i; }
-        else { out.push_back({false, 0, cur}); ++i; }
+static char* put_int(char* o, long long v) {
+    if (v < 0) { *o++ = '-'; return put_uint(o, 0ull - (unsigned long long)v); }
+    return put_uint(o, (unsigned long long)v);
+}
+static char* put_fixed(char* o, double v, int prec) {
+    if (std::isnan(v)) { memcpy(o, "nan", 3); return o + 3; }          // Python prints nan without a sign
+    if (std::isinf(v)) { if (v < 0) *o++ = '-'; memcpy(o, "inf", 3); return o + 3; }
+    const double a = fabs(v);
+    if (prec > 3 || a >= 4503599627370496.0) return o + snprintf(o, 400, "%.*f", prec, v);
+    if (std::signbit(v)) *o++ = '-';
+    static const unsigned long long P10[4] = {1ull, 10ull, 100ull, 1000ull};
+    int e;
+    const double fr = frexp(a, &e);                                    // a = fr * 2^e, fr in [0.5, 1)
+    unsigned long long q = 0;
+    if (a != 0.0) {
+        const unsigned long long m = (unsigned long long)ldexp(fr, 53);   // exact 53-bit integer
+        const int e2 = e - 53;                                            // a = m * 2^e2, e2 < 0 here
+        const unsigned long long scaled = m * P10[prec];
+        const int sh = -e2;
+        if (sh <= 0) q = scaled << (-sh);
+        else if (sh >= 64) q = 0;
+        else {
+            q = scaled >> sh;
+            const unsigned long long rem = scaled & ((1ull << sh) - 1ull), half = 1ull << (sh - 1);
+            if (rem > half || (rem == half && (q & 1ull))) ++q;
+        }
     }
-    return out;
-}
-static int nat_cmp(const std::string& a, const std::string& b) {
-    const std::vector<NatTok> x = nat_split(a), y = nat_split(b);
-    for (size_t i = 0; i < x.size() && i < y.size(); ++i) {
-        // text and number tokens alternate identically in both lists, so kinds always match
-        if (x[i].num) { if (x[i].val != y[i].val) return x[i].val < y[i].val ? -1 : 1; }
-        else { const int c = x[i].txt.compare(y[i].txt); if (c) return c < 0 ? -1 : 1; }
+    const unsigned long long ip = q / P10[prec], fp = q % P10[prec];
+    o = put_uint(o, ip);
+    if (prec > 0) {
+        *o++ = '.';
+        for (int d = prec - 1; d >= 0; --d) *o++ = (char)('0' + (fp / P10[d]) % 10);
     }
-    return x.size() == y.size() ? 0 : (x.size() < y.size() ? -1 : 1);
+    return o;
 }
 
-struct FmtRow { std::vector<std::string> info_words; std::string name, type, min_cov, line; };
+// common.natsortkey (common.py:95-116) on two strings without building the token lists:
+// re.split('([0-9]+)', key) alternates text / digit runs starting and ending with a (possibly empty)
+// text chunk; text compares lower-cased, digit runs as integers, and a list that is a prefix of the
+// other sorts first.
+static int nat_cmp(const char* a, size_t na, const char* b, size_t nb) {
+    size_t i = 0, j = 0;
+    for (;;) {
+        // text chunks
+        for (;;) {
+            const bool ea = i >= na || isdigit((unsigned char)a[i]), eb = j >= nb || isdigit((unsigned char)b[j]);
+            if (ea || eb) { if (ea != eb) return ea ? -1 : 1; break; }
+            const int ca = tolower((unsigned char)a[i]), cb = tolower((unsigned char)b[j]);
+            if (ca != cb) return ca < cb ? -1 : 1;
+            ++i; ++j;
+        }
+        const bool enda = i >= na, endb = j >= nb;
+        if (enda || endb) return enda == endb ? 0 : (enda ? -1 : 1);
+        // digit runs as integers of any length
+        size_t i2 = i, j2 = j;
+        while (i2 < na && isdigit((unsigned char)a[i2])) ++i2;
+        while (j2 < nb && isdigit((unsigned char)b[j2])) ++j2;
+        size_t ia = i, jb = j;
+        while (ia + 1 < i2 && a[ia] == '0') ++ia;
+        while (jb + 1 < j2 && b[jb] == '0') ++jb;
+        if (i2 - ia != j2 - jb) return i2 - ia < j2 - jb ? -1 : 1;
+        const int c = memcmp(a + ia, b + jb, i2 - ia);
+        if (c) return c < 0 ? -1 : 1;
+        i = i2; j = j2;
+    }
+}
 
-static void format_rows_of(const km_result* r, int32_t tg, const char* db_name, const std::string& qn, std::string& text) {
-    const char* query_name = qn.c_str();
+struct FmtRow {
+    const km_row* w;
+    const char* name; uint32_t name_len;       // variant name ("" for Reference)
+    const char* line; uint32_t line_len;
+};
+
+// the rows of target tg: text into `arena` (unsorted), then sorted as MutationFinder.get_paths does
+// (:825-829) and appended to `out`
+static void format_rows_of(const km_result* r, int32_t tg, const char* db_name, size_t db_len, const char* qn, size_t qn_len,
+                           std::vector<char>& arena, std::vector<FmtRow>& rows, std::vector<char>& out) {
     const int k = r->k;
     const char* tseq = r->targets.data() + r->seq_off[tg];
-    std::vector<FmtRow> rows;
-    for (int i = 0; i < r->row_count[tg]; ++i) {
+    const int nrow = r->row_count[tg];
+    rows.clear();
+    if (nrow <= 0) return;
+    // upper bound of this target's text
+    size_t need = 0;
+    for (int i = 0; i < nrow; ++i) {
+        const km_row& w = r->rows[r->row_first[tg] + i];
+        need += db_len + qn_len + 256 + (size_t)(w.del_len + w.ins_len) + (size_t)(w.var_end - w.var_begin + k) +
+                (size_t)(w.ref_end - w.ref_begin + k);
+    }
+    arena.resize(need);
+    char* o = arena.data();
+    for (int i = 0; i < nrow; ++i) {
         const km_row& w = r->rows[r->row_first[tg] + i];
         const char* pseq = r->seq_pool.data() + r->path_seq_off[w.path_id];
         FmtRow fr;
-        fr.type = TYPE_NAME[w.type];
+        fr.w = &w;
+        fr.line = o;
+        memcpy(o, db_name, db_len); o += db_len; *o++ = '\t';
+        memcpy(o, qn, qn_len); o += qn_len; *o++ = '\t';
+        const size_t tl = strlen(TYPE_NAME[w.type]);
+        memcpy(o, TYPE_NAME[w.type], tl); o += tl; *o++ = '\t';
+        fr.name = o;
         if (w.type != 0) {      // "{}\t{}:{}:{}" (MutationFinder.py:483-488); Reference -> "Reference\t"
-            fr.name = std::to_string(w.name_start) + ":";
-            for (int j = 0; j < w.del_len; ++j) fr.name += (char)tolower((unsigned char)tseq[w.del_begin + j + k - 1]);
-            fr.name += "/";
-            for (int j = 0; j < w.ins_len; ++j) fr.name += pseq[w.ins_begin + j + k - 1];
-            fr.name += ":" + std::to_string(w.name_end);
+            o = put_int(o, w.name_start); *o++ = ':';
+            for (int j = 0; j < w.del_len; ++j) *o++ = (char)tolower((unsigned char)tseq[w.del_begin + j + k - 1]);
+            *o++ = '/';
+            memcpy(o, pseq + w.ins_begin + k - 1, (size_t)w.ins_len); o += w.ins_len;
+            *o++ = ':'; o = put_int(o, w.name_end);
         }
-        std::string info = w.kind == 0 ? std::string("vs_ref")
-                                       : "cluster " + std::to_string(w.cluster_id) + " n=" + std::to_string(w.cluster_n);
-        fr.min_cov = std::to_string((long long)w.min_cov);
-        std::string& L = fr.line;
-        L = db_name; L += '\t'; L += query_name; L += '\t'; L += fr.type; L += '\t'; L += fr.name; L += '\t';
-        fmt_float(L, w.rvaf, 3); L += '\t'; fmt_float(L, w.expr, 1); L += '\t';
-        L += fr.min_cov; L += '\t'; L += std::to_string(w.start_off); L += '\t';
-        if (w.var_end > w.var_begin) L.append(pseq + w.var_begin, (size_t)(w.var_end - w.var_begin + k - 1));
-        L += '\t'; fmt_float(L, w.ref_expr, 1); L += '\t';
-        if (w.ref_end > w.ref_begin) L.append(tseq + w.ref_begin, (size_t)(w.ref_end - w.ref_begin + k - 1));
-        L += '\t'; L += info; L += '\n';
-        size_t p = 0;
-        while (true) { size_t q = info.find(' ', p); fr.info_words.push_back(info.substr(p, q == std::string::npos ? q : q - p)); if (q == std::string::npos) break; p = q + 1; }
-        rows.push_back(std::move(fr));
+        fr.name_len = (uint32_t)(o - fr.name);
+        *o++ = '\t';
+        o = put_fixed(o, w.rvaf, 3); *o++ = '\t';
+        o = put_fixed(o, w.expr, 1); *o++ = '\t';
+        o = put_int(o, (long long)w.min_cov); *o++ = '\t';
+        o = put_int(o, w.start_off); *o++ = '\t';
+        if (w.var_end > w.var_begin) { const size_t n = (size_t)(w.var_end - w.var_begin + k - 1); memcpy(o, pseq + w.var_begin, n); o += n; }
+        *o++ = '\t';
+        o = put_fixed(o, w.ref_expr, 1); *o++ = '\t';
+        if (w.ref_end > w.ref_begin) { const size_t n = (size_t)(w.ref_end - w.ref_begin + k - 1); memcpy(o, tseq + w.ref_begin, n); o += n; }
+        *o++ = '\t';
+        if (w.kind == 0) { memcpy(o, "vs_ref", 6); o += 6; }
+        else { memcpy(o, "cluster ", 8); o += 8; o = put_int(o, w.cluster_id); memcpy(o, " n=", 3); o += 3; o = put_int(o, w.cluster_n); }
+        *o++ = '\n';
+        fr.line_len = (uint32_t)(o - fr.line);
+        rows.push_back(fr);
     }
-    // key = natsortkey(*info.split(' '), query, variant_name, type, min_coverage, rev_ix=[0]) (:825-829;
-    // x[6] of the tab-split row is Min_coverage);
-    // tuples compare element-wise, a shorter tuple that is a prefix sorts first
-    auto key_of = [&](const FmtRow& f) {
-        std::vector<const std::string*> ks;
-        for (auto& wd : f.info_words) ks.push_back(&wd);
-        ks.push_back(&qn); ks.push_back(&f.name); ks.push_back(&f.type); ks.push_back(&f.min_cov);
-        return ks;
-    };
-    std::stable_sort(rows.begin(), rows.end(), [&](const FmtRow& a, const FmtRow& b) {
-        const auto ka = key_of(a), kb = key_of(b);
-        for (size_t i = 0; i < ka.size() && i < kb.size(); ++i) {
-            int c = nat_cmp(*ka[i], *kb[i]);
-            if (i == 0) c = -c;                 // rev_ix=[0]
+    // key = natsortkey(*info.split(' '), query, variant_name, type, min_coverage, rev_ix=[0]) (:825-829):
+    // info is "vs_ref" or "cluster <i> n=<j>"; the first word compares REVERSED (vs_ref rows first),
+    // then the words (numbers as numbers), the query (equal inside a target), the variant name, the
+    // type, Min_coverage; a key that is a prefix of the other sorts first (vs_ref has one word, a
+    // cluster three, but those never tie on the first word).
+    if (nrow > 1) {
+        std::stable_sort(rows.begin(), rows.end(), [&](const FmtRow& x, const FmtRow& y) {
+            const km_row& a = *x.w; const km_row& b = *y.w;
+            if (a.kind != b.kind) return a.kind < b.kind;                       // "vs_ref" > "cluster", reversed
+            if (a.kind != 0) {
+                if (a.cluster_id != b.cluster_id) return a.cluster_id < b.cluster_id;
+                if (a.cluster_n != b.cluster_n) return a.cluster_n < b.cluster_n;
+            }
+            int c = nat_cmp(x.name, x.name_len, y.name, y.name_len);
             if (c) return c < 0;
-        }
-        return ka.size() < kb.size();
-    });
-    for (auto& f : rows) text += f.line;
+            c = nat_cmp(TYPE_NAME[a.type], strlen(TYPE_NAME[a.type]), TYPE_NAME[b.type], strlen(TYPE_NAME[b.type]));
+            if (c) return c < 0;
+            // Min_coverage prints as a decimal integer; the counts are never negative
+            return a.min_cov < b.min_cov;
+        });
+    }
+    for (const FmtRow& f : rows) out.insert(out.end(), f.line, f.line + f.line_len);
 }
 
 extern "C" int64_t km_result_format_target(const km_result* r, int32_t tg, const char* db_name, const char* query_name, char* buf,
                                            int64_t buf_len) {
     if (!r || tg < 0 || tg >= r->n_targets || !db_name || !query_name) { fail(KM_E_ARG, "km_result_format_target: bad argument"); return -1; }
-    std::string text;
-    format_rows_of(r, tg, db_name, query_name, text);
+    std::vector<char> arena, text;
+    std::vector<FmtRow> rows;
+    format_rows_of(r, tg, db_name, strlen(db_name), query_name, strlen(query_name), arena, rows, text);
     const int64_t need = (int64_t)text.size();
     if (buf && need < buf_len) { memcpy(buf, text.data(), text.size()); buf[need] = 0; }
     return need;
 }
 
+// Builds (once) the text of all targets in target order on host threads: every thread formats a
+// contiguous range of targets into its own buffer, the pieces are then copied side by side.
+static int build_text(const km_result* r, const char* db_name, const char* names, const int64_t* name_off, int32_t threads) {
+    const int n = r->n_targets;
+    std::string key = std::string(db_name) + '\0' + (n ? std::string(names, (size_t)name_off[n]) : std::string());
+    if (r->text_len >= 0 && r->fmt_key == key) return 0;
+    int nt = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
+    nt = std::max(1, std::min(nt, std::max(1, n / 64)));
+    std::vector<std::vector<char>> piece((size_t)nt);
+    const size_t db_len = strlen(db_name);
+    auto work = [&](int w) {
+        const int lo = (int)((int64_t)n * w / nt), hi = (int)((int64_t)n * (w + 1) / nt);
+        std::vector<char> arena;
+        std::vector<FmtRow> rows;
+        std::vector<char>& out = piece[(size_t)w];
+        size_t guess = 0;
+        for (int t = lo; t < hi; ++t) guess += (size_t)r->row_count[t] * (size_t)(2 * (r->seq_off[t + 1] - r->seq_off[t]) + 160 + db_len);
+        out.reserve(guess);
+        for (int t = lo; t < hi; ++t)
+            format_rows_of(r, t, db_name, db_len, names + name_off[t], (size_t)(name_off[t + 1] - name_off[t]), arena, rows, out);
+    };
+    if (nt == 1) work(0);
+    else {
+        std::vector<std::thread> pool;
+        for (int i = 0; i < nt; ++i) pool.emplace_back(work, i);
+        for (auto& th : pool) th.join();
+    }
+    int64_t total = 0;
+    std::vector<int64_t> at((size_t)nt);
+    for (int i = 0; i < nt; ++i) { at[(size_t)i] = total; total += (int64_t)piece[(size_t)i].size(); }
+    r->text.reset(new char[(size_t)total + 1]);
+    char* dst = r->text.get();
+    auto copy = [&](int w) { if (!piece[(size_t)w].empty()) memcpy(dst + at[(size_t)w], piece[(size_t)w].data(), piece[(size_t)w].size()); };
+    if (nt == 1) copy(0);
+    else {
+        std::vector<std::thread> pool;
+        for (int i = 0; i < nt; ++i) pool.emplace_back(copy, i);
+        for (auto& th : pool) th.join();
+    }
+    dst[total] = 0;
+    r->text_len = total;
+    r->fmt_key.swap(key);
+    return 0;
+}
+
 extern "C" int64_t km_result_format_all(const km_result* r, const char* db_name, const char* names, const int64_t* name_off,
                                         int32_t threads, char* buf, int64_t buf_len) {
     if (!r || !db_name || (r->n_targets && (!names || !name_off))) { fail(KM_E_ARG, "km_result_format_all: bad argument"); return -1; }
-    const int n = r->n_targets;
-    std::string key = std::string(db_name) + '\0' + (n ? std::string(names, (size_t)name_off[n]) : std::string());
-    if (r->fmt_key != key || r->fmt_parts.size() != (size_t)n) {
-        r->fmt_parts.assign((size_t)n, std::string());
-        std::vector<std::string>& build = r->fmt_parts;
-        int nt = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
-        nt = std::max(1, std::min(nt, std::max(1, n / 64)));
-        auto work = [&](int lo, int hi) {
-            for (int t = lo; t < hi; ++t)
-                format_rows_of(r, t, db_name, std::string(names + name_off[t], (size_t)(name_off[t + 1] - name_off[t])), build[t]);
-        };
-        if (nt == 1) work(0, n);
-        else {
-            std::vector<std::thread> pool;
-            for (int i = 0; i < nt; ++i) pool.emplace_back(work, (int)((int64_t)n * i / nt), (int)((int64_t)n * (i + 1) / nt));
-            for (auto& th : pool) th.join();
-        }
-        r->fmt_key.swap(key);
-    }
-    const std::vector<std::string>& parts = r->fmt_parts;
-    int64_t need = 0;
-    for (auto& p : parts) need += (int64_t)p.size();
-    if (buf && need < buf_len) {
-        int64_t at = 0;
-        for (auto& p : parts) { memcpy(buf + at, p.data(), p.size()); at += (int64_t)p.size(); }
-        buf[at] = 0;
-    }
+    build_text(r, db_name, names, name_off, threads);
+    const int64_t need = r->text_len;
+    if (buf && need < buf_len) memcpy(buf, r->text.get(), (size_t)need + 1);
     return need;
 }
+
+extern "C" int64_t km_result_text(const km_result* r, const char* db_name, const char* names, const int64_t* name_off,
+                                  int32_t threads, const char** text) {
+    if (!r || !db_name || !text || (r->n_targets && (!names || !name_off))) { fail(KM_E_ARG, "km_result_text: bad argument"); return -1; }
+    build_text(r, db_name, names, name_off, threads);
+    *text = r->text.get();
+    return r->text_len;
+}
+
+extern "C" int km_debug_format_fixed(double v, int prec, char* buf64) {
+    if (!buf64 || prec < 0 || prec > 3) return fail(KM_E_ARG, "km_debug_format_fixed: bad argument");
+    char* e = put_fixed(buf64, v, prec);
+    *e = 0;
+    return (int)(e - buf64);
+}
+extern "C" int km_debug_nat_cmp(const char* a, const char* b) { return nat_cmp(a, strlen(a), b, strlen(b)); }
 
 // ---- measurement helpers ---------------------------------------------------------------------------
 extern "C" int km_debug_phase_cycles(unsigned long long* out32, int reset) {

@@ -88,6 +88,16 @@ __global__ void km_table_filter_kernel(TableView src, TableView dst, uint32_t mi
     if (mine) atomicAdd(n_new, mine);
 }
 
+// target letters -> 2-bit codes in place (A0 C1 G2 T3, anything else 255): the host uploads the
+// sequences as they came in
+__global__ void km_encode_kernel(uint8_t* seq, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint8_t c = seq[i];
+        seq[i] = c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : 255;
+    }
+}
+
 // ---- K2: batched canonical probe (Jellyfish.query) ---------------------------------------
 #define KM_QUERY_ILP 4
 __global__ void __launch_bounds__(256) km_query_kernel(TableView T, const uint64_t* __restrict__ kmers, uint64_t n,

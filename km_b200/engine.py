@@ -321,15 +321,14 @@ class BatchResult:
             np.cumsum(np.fromiter((len(x) for x in names), dtype=np.int64, count=len(names)), out=off[1:])
             if off[-1] != len(blob):          # non-ASCII names: fall back to byte lengths
                 np.cumsum([len(x.encode()) for x in names], out=off[1:])
-        need = lib().km_result_format_all(self._h, db_name.encode(), blob, off.ctypes.data, int(threads), None, 0)
+        ptr = ctypes.c_void_p()
+        need = lib().km_result_text(self._h, db_name.encode(), blob, off.ctypes.data, int(threads), ctypes.byref(ptr))
         if need < 0:
             check(int(need))
-        buf = np.empty(int(need) + 1, dtype=np.uint8)
-        lib().km_result_format_all(self._h, db_name.encode(), blob, off.ctypes.data, int(threads), buf.ctypes.data,
-                                   int(need) + 1)
+        view = _view(ptr.value, np.uint8, int(need))      # the library's own buffer, valid while the result lives
         if as_bytes:
-            return buf[:int(need)]
-        return buf[:int(need)].tobytes().decode("ascii")
+            return view
+        return view.tobytes().decode("ascii")
 
     def close(self):
         if getattr(self, "_h", None):
