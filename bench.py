@@ -278,14 +278,20 @@ def main():
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
     ms_per_step = ms_total / args.steps
     value = world * args.targets / (ms_per_step / 1e3)
-    # per-kernel durations, averaged over K more launches (CUDA events inside the library)
-    walk_ms, graph_ms = [], []
+    # per-kernel durations, averaged over K more launches (CUDA events inside the library, on the launch stream)
+    probe_ms, walk_ms, graph_ms = [], [], []
     for _ in range(args.steps):
         plan.launch(stream.cuda_stream)
-        w, g = plan.last_ms()
-        walk_ms.append(w)
-        graph_ms.append(g)
-    walk_ms, graph_ms = float(np.mean(walk_ms)), float(np.mean(graph_ms))
+        a, b, c = plan.kernel_ms()
+        probe_ms.append(a)
+        walk_ms.append(b)
+        graph_ms.append(c)
+    probe_ms, walk_ms, graph_ms = float(np.mean(probe_ms)), float(np.mean(walk_ms)), float(np.mean(graph_ms))
+    # lookups the reference-probe kernel issues per launch: per reference k-mer its own count + the three
+    # successors off the reference (all four for a target's last k-mer); the successor along the reference
+    # comes from the neighbouring lane, except for the last lane of a 32-k-mer chunk, which fetches it
+    L = n_ref[n_ref > 0]
+    probe_lookups = int((L + 3 * (L - 1) + 4 + (L - 1) // 32).sum())
 
     # ---- e2e: host buffers in, TSV text out ---------------------------------------------------
     e2e_split = {"find_batch_ms": 0.0, "format_ms": 0.0}
@@ -369,7 +375,15 @@ def main():
                    "issued_lookups_per_s": lps}
 
     peak, peak_src = load_peaks()
-    achieved = algorithmic * 32 / (walk_ms / 1e3) / 1e9
+    achieved = probe_lookups * 32 / (probe_ms / 1e3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tj = json.load(f)
+        if tj.get("targets") == args.targets and tj.get("table_keys") == table_keys:
+            traffic = tj["km_ref_probe_kernel"]["dram_bytes_per_launch"]
+    except Exception:
+        pass
     issued_total = sum_over_ranks(issued)
     if rank == 0:
         out = {
@@ -387,13 +401,19 @@ def main():
                     "ms_per_step": e2e_ms, "device_ms": e2e_breakdown,
                     "what": "km_find_batch(host sequences) + km_result_format_all -> TSV text"},
             "gpu_launches": 5 * args.steps,
-            "kernels": {"km_walk_kernel_ms": walk_ms, "km_graph_kernel_ms": graph_ms,
-                        "dominant": "km_walk_kernel" if walk_ms >= graph_ms else "km_graph_kernel"},
-            "roofline": {"kernel": "km_walk_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "algorithmic_lookups": algorithmic, "issued_lookups": issued, "bytes_per_lookup": 32,
+            "kernels": {"km_ref_probe_kernel_ms": probe_ms, "km_walk_kernels_ms": walk_ms, "km_graph_kernels_ms": graph_ms,
+                        "what": "reference probe (HBM-bound: ~87% of the panel's lookups), shared-memory + general walk "
+                                "(latency-bound tails), graph/paths/quantification (shared memory, latency-bound)"},
+            "roofline": {"kernel": "km_ref_probe_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "units_per_launch": probe_lookups, "bytes_per_unit": 32,
+                         "unit_is": "one canonical k-mer lookup = one 32-byte HBM sector (SURVEY.md 8d)",
                          "random_gather_GBps": gather["GBps"] if gather else None,
-                         "frac_of_random_gather": (achieved / gather["GBps"]) if gather else None},
+                         "frac_of_random_gather": (achieved / gather["GBps"]) if gather else None,
+                         "panel": {"algorithmic_lookups": algorithmic, "issued_lookups": issued,
+                                   "GBps_over_whole_step": algorithmic * 32 / (ms_per_step / 1e3) / 1e9,
+                                   "frac_of_random_gather_over_whole_step":
+                                       (algorithmic * 32 / (ms_per_step / 1e3) / 1e9 / gather["GBps"]) if gather else None}},
             "lookup": lookup, "random_gather": gather,
             "lookups_per_s_in_panel": issued_total / (ms_per_step / 1e3),
             "clocks": clocks, "parity": parity, "cpu_baseline": cpu,

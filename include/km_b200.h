@@ -66,6 +66,22 @@ typedef struct km_table_info {
 int km_table_get_info(km_table* t, km_table_info* info);
 void km_table_close(km_table* t);
 
+/* ---- cohort mode (BASELINE.json config 5; no counterpart in the reference): the table is
+ * hash-sharded over the GPUs of one box, one process per GPU.  Every process creates ITS shard
+ * (rank of n_shards <= 8, the same capacity on every rank), fills it -- km_table_insert /
+ * km_table_build_synthetic / km_table_count_reads take the full key stream and keep only the keys this
+ * shard owns -- and exports a POSIX file descriptor of its memory (CUDA virtual-memory API, 2 MiB pages).
+ * The descriptors travel between the processes (SCM_RIGHTS; km_b200/cohort.py); once a process has
+ * attached every other rank's descriptor, a probe of a remote key is a 32-byte peer load over NVLink from
+ * inside the same kernels (km_query_batch, km_find_batch, ...).  Until then only owned keys may be asked. */
+int km_table_create_shard(int device, int k, int canonical, uint64_t capacity_keys_per_shard, int rank, int n_shards,
+                          km_table** out);
+int km_table_shard_export_fd(km_table* t, int* fd);
+int km_table_shard_attach_fd(km_table* t, int rank, int fd);      /* takes ownership of fd */
+/* owner shard of each k-mer (forward-strand, packed): host arithmetic only, no GPU needed.  This is what
+ * routes a query in the explicit all-to-all exchange (km_b200/cohort.py). */
+int km_shard_owner(const uint64_t* kmers, uint64_t n, int k, int canonical, int n_shards, int32_t* owner);
+
 /* ---- lookups: Jellyfish.query (Jellyfish.py:47-53) ---------------------------------- */
 int km_query_batch(km_table* t, const uint64_t* kmers_host, uint64_t n, uint32_t* counts_host);
 int km_query_batch_device(km_table* t, const uint64_t* kmers_dev, uint64_t n, uint32_t* counts_dev, void* cuda_stream);

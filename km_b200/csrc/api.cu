@@ -14,6 +14,9 @@
 #include <thread>
 #include <vector>
 
+#include <cuda.h>        // driver-API TYPES only: the entry points are fetched at run time (vmm_load)
+#include <unistd.h>
+
 #include "../../include/km_b200.h"
 #include "kernels.cuh"
 
@@ -135,12 +138,27 @@ struct km_table {
     Arena dev_find, pin_find;  // km_find_batch workspace, reused across calls
     std::shared_ptr<PinPool> pool = std::make_shared<PinPool>();   // result buffers (outlive the table if a result does)
     int sm_count = 148;
+    // cohort mode: this table is shard `my_shard` of `n_shards`; peer[r] = rank r's buckets mapped through CUDA IPC
+    int n_shards = 1, my_shard = 0;
+    const Bucket* peer[KM_MAX_SHARDS] = {};
+    bool attached = false;
+    // a shard is allocated through the virtual-memory API so that peers can map it with its own 2 MiB
+    // pages (a legacy cudaIpc mapping gets small pages: random probes of a 32 GB peer shard then run
+    // ~70x slower, all TLB misses -- measured, profiles/README.md)
+    bool vmm = false;
+    CUmemGenericAllocationHandle vmm_handle = 0, peer_handle[KM_MAX_SHARDS] = {};
+    size_t vmm_size = 0;
     TableView view() const {
         TableView v;
         v.buckets = buckets; v.n_buckets = n_buckets; v.kmask = (1ull << (2 * k)) - 1ull; v.k = k; v.canonical = canonical;
+        v.n_shards = n_shards; v.my_shard = my_shard;
+        for (int r = 0; r < KM_MAX_SHARDS; ++r) v.shard[r] = peer[r];
+        v.shard[my_shard] = buckets;
         return v;
     }
 };
+
+static size_t align_up_sz(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 static int grid_for(const km_table* t, uint64_t n, int block, int per_sm) {
     uint64_t want = (n + block - 1) / block;
@@ -182,9 +200,165 @@ extern "C" int km_table_create(int device, int k, int canonical, uint64_t capaci
     return 0;
 }
 
+// ---- cohort mode: one shard per GPU, peers mapped over NVLink ---------------------------------------
+// Driver entry points of the virtual-memory API, resolved at run time so that the library still loads
+// on a machine without libcuda (the CPU-only test container).
+struct Vmm {
+    CUresult (*create)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long) = nullptr;
+    CUresult (*reserve)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+    CUresult (*map)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+    CUresult (*set_access)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t) = nullptr;
+    CUresult (*export_fd)(void*, CUmemGenericAllocationHandle, CUmemAllocationHandleType, unsigned long long) = nullptr;
+    CUresult (*import_fd)(CUmemGenericAllocationHandle*, void*, CUmemAllocationHandleType) = nullptr;
+    CUresult (*granularity)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags) = nullptr;
+    CUresult (*unmap)(CUdeviceptr, size_t) = nullptr;
+    CUresult (*release)(CUmemGenericAllocationHandle) = nullptr;
+    CUresult (*addr_free)(CUdeviceptr, size_t) = nullptr;
+    bool ok = false;
+};
+static Vmm g_vmm;
+static int vmm_load() {
+    if (g_vmm.ok) return 0;
+    auto get = [](const char* name, void** fn) -> bool {
+        cudaDriverEntryPointQueryResult q;
+        return cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess && *fn;
+    };
+    if (!get("cuMemCreate", (void**)&g_vmm.create) || !get("cuMemAddressReserve", (void**)&g_vmm.reserve) ||
+        !get("cuMemMap", (void**)&g_vmm.map) || !get("cuMemSetAccess", (void**)&g_vmm.set_access) ||
+        !get("cuMemExportToShareableHandle", (void**)&g_vmm.export_fd) ||
+        !get("cuMemImportFromShareableHandle", (void**)&g_vmm.import_fd) ||
+        !get("cuMemGetAllocationGranularity", (void**)&g_vmm.granularity) || !get("cuMemUnmap", (void**)&g_vmm.unmap) ||
+        !get("cuMemRelease", (void**)&g_vmm.release) || !get("cuMemAddressFree", (void**)&g_vmm.addr_free))
+        return fail(KM_E_CUDA, "CUDA virtual-memory API is not available from this driver");
+    g_vmm.ok = true;
+    return 0;
+}
+#define DRV(call)                                                                                       \
+    do {                                                                                                \
+        CUresult r_ = (call);                                                                           \
+        if (r_ != CUDA_SUCCESS) return fail(KM_E_CUDA, "%s failed: CUresult %d (%s:%d)", #call, (int)r_, __FILE__, __LINE__); \
+    } while (0)
+
+static CUmemAllocationProp shard_prop(int device) {
+    CUmemAllocationProp prop;
+    memset(&prop, 0, sizeof(prop));
+    prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    prop.location.id = device;
+    prop.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+    return prop;
+}
+
+// map `handle` (size bytes) into this process for device `device`
+static int vmm_map(CUmemGenericAllocationHandle handle, size_t size, size_t gran, int device, void** out) {
+    CUdeviceptr ptr = 0;
+    DRV(g_vmm.reserve(&ptr, size, gran, 0, 0));
+    DRV(g_vmm.map(ptr, size, 0, handle, 0));
+    CUmemAccessDesc acc;
+    memset(&acc, 0, sizeof(acc));
+    acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    acc.location.id = device;
+    acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+    DRV(g_vmm.set_access(ptr, size, &acc, 1));
+    *out = (void*)ptr;
+    return 0;
+}
+
+extern "C" int km_table_create_shard(int device, int k, int canonical, uint64_t capacity_keys_per_shard, int rank, int n_shards,
+                                     km_table** out) {
+    if (n_shards < 1 || n_shards > KM_MAX_SHARDS || rank < 0 || rank >= n_shards)
+        return fail(KM_E_ARG, "km_table_create_shard: rank %d of %d shards (at most %d)", rank, n_shards, KM_MAX_SHARDS);
+    if (!out || k < 1 || k > 31) return fail(KM_E_ARG, "km_table_create_shard: k must be in 1..31 (got %d)", k);
+    if (km_device_count() <= 0) return fail(KM_E_NOGPU, "no CUDA device visible: km_b200 has no CPU fallback");
+    // the ordinary constructor with a token allocation, then the bucket array is replaced by a
+    // shareable one of the real size
+    if (int rc = km_table_create(device, k, canonical, 64, out)) return rc;
+    km_table* t = *out;
+    t->n_shards = n_shards; t->my_shard = rank;
+    if (int rc = vmm_load()) { km_table_close(t); *out = nullptr; return rc; }
+    CUmemAllocationProp prop = shard_prop(device);
+    size_t gran = 0;
+    DRV(g_vmm.granularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED));
+    const uint64_t n_buckets = std::max<uint64_t>(64, capacity_keys_per_shard);
+    const size_t size = align_up_sz(n_buckets * sizeof(Bucket), gran);
+    CUmemGenericAllocationHandle h = 0;
+    CUresult cr = g_vmm.create(&h, size, &prop, 0);
+    if (cr != CUDA_SUCCESS) { km_table_close(t); *out = nullptr; return fail(KM_E_CUDA, "cuMemCreate of %zu shard bytes failed: CUresult %d", size, (int)cr); }
+    void* ptr = nullptr;
+    if (int rc = vmm_map(h, size, gran, device, &ptr)) { km_table_close(t); *out = nullptr; return rc; }
+    cudaFree(t->buckets);
+    t->buckets = (Bucket*)ptr; t->n_buckets = n_buckets;
+    t->vmm = true; t->vmm_handle = h; t->vmm_size = size;
+    km_table_clear_kernel<<<t->sm_count * 8, 256, 0, t->stream>>>(t->buckets, t->n_buckets);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(t->stream));
+    return 0;
+}
+
+// a POSIX file descriptor for this shard's memory: send it to the peers (SCM_RIGHTS), they attach it
+extern "C" int km_table_shard_export_fd(km_table* t, int* fd) {
+    if (!t || !fd || !t->vmm) return fail(KM_E_ARG, "km_table_shard_export_fd: not a shard");
+    CU(cudaSetDevice(t->device));
+    int out = -1;
+    DRV(g_vmm.export_fd(&out, t->vmm_handle, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0));
+    *fd = out;
+    return 0;
+}
+
+extern "C" int km_table_shard_attach_fd(km_table* t, int rank, int fd) {
+    if (!t || !t->vmm || rank < 0 || rank >= t->n_shards || rank == t->my_shard || fd < 0)
+        return fail(KM_E_ARG, "km_table_shard_attach_fd: bad argument");
+    CU(cudaSetDevice(t->device));
+    CUmemGenericAllocationHandle h = 0;
+    DRV(g_vmm.import_fd(&h, (void*)(uintptr_t)fd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR));
+    CUmemAllocationProp prop = shard_prop(t->device);
+    size_t gran = 0;
+    DRV(g_vmm.granularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED));
+    void* ptr = nullptr;
+    if (int rc = vmm_map(h, t->vmm_size, gran, t->device, &ptr)) return rc;     // every shard has the same size
+    t->peer[rank] = (const Bucket*)ptr;
+    t->peer_handle[rank] = h;
+    t->attached = true;
+    close(fd);
+    return 0;
+}
+
+// owner shard of each k-mer (host arithmetic, no GPU): what routes a query in the all-to-all path
+extern "C" int km_shard_owner(const uint64_t* kmers, uint64_t n, int k, int canonical, int n_shards, int32_t* owner) {
+    if ((n && (!kmers || !owner)) || k < 1 || k > 31 || n_shards < 1) return fail(KM_E_ARG, "km_shard_owner: bad argument");
+    const uint64_t mask = (1ull << (2 * k)) - 1ull;
+    for (uint64_t i = 0; i < n; ++i) {
+        uint64_t v = kmers[i] & mask;
+        if (canonical) {
+            uint64_t rc = ~v;
+            rc = ((rc >> 2) & 0x3333333333333333ull) | ((rc & 0x3333333333333333ull) << 2);
+            rc = ((rc >> 4) & 0x0F0F0F0F0F0F0F0Full) | ((rc & 0x0F0F0F0F0F0F0F0Full) << 4);
+            rc = __builtin_bswap64(rc) >> (64 - 2 * k);
+            if (rc < v) v = rc;
+        }
+        uint64_t z = v + 0x9E3779B97F4A7C15ull;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z ^= z >> 31;
+        owner[i] = n_shards > 1 ? (int32_t)(((unsigned __int128)z * (unsigned __int128)(uint64_t)n_shards) >> 64) : 0;
+    }
+    return 0;
+}
+
 extern "C" void km_table_close(km_table* t) {
     if (!t) return;
     cudaSetDevice(t->device);
+    if (t->vmm) {
+        cudaDeviceSynchronize();
+        for (int r = 0; r < KM_MAX_SHARDS; ++r)
+            if (t->peer[r] && r != t->my_shard) {
+                g_vmm.unmap((CUdeviceptr)t->peer[r], t->vmm_size); g_vmm.addr_free((CUdeviceptr)t->peer[r], t->vmm_size);
+                g_vmm.release(t->peer_handle[r]);
+            }
+        if (t->buckets) { g_vmm.unmap((CUdeviceptr)t->buckets, t->vmm_size); g_vmm.addr_free((CUdeviceptr)t->buckets, t->vmm_size); }
+        g_vmm.release(t->vmm_handle);
+        t->buckets = nullptr;
+    }
     if (t->buckets) cudaFree(t->buckets);
     if (t->d_counter) cudaFree(t->d_counter);
     t->dev.release();
@@ -269,14 +443,22 @@ extern "C" int km_table_drop_below(km_table* t, uint32_t min_count, uint64_t* n_
     km_table_clear_kernel<<<t->sm_count * 8, 256, 0, t->stream>>>(fresh, t->n_buckets);
     TableView dst = t->view();
     dst.buckets = fresh;
+    dst.shard[t->my_shard] = fresh;
     CU(cudaMemsetAsync(t->d_counter, 0, 16, t->stream));
     km_table_filter_kernel<<<t->sm_count * 8, 256, 0, t->stream>>>(t->view(), dst, min_count, t->d_counter,
                                                                    reinterpret_cast<uint32_t*>(t->d_counter + 1));
     CU(cudaGetLastError());
     t->n_keys = 0;
     int rc = finish_insert(t, "km_table_drop_below");
-    cudaFree(t->buckets);
-    t->buckets = fresh;
+    if (t->vmm) {
+        // a shard keeps its (peer-mapped) memory: the filtered copy goes back in place
+        CU(cudaMemcpyAsync(t->buckets, fresh, t->n_buckets * sizeof(Bucket), cudaMemcpyDeviceToDevice, t->stream));
+        CU(cudaStreamSynchronize(t->stream));
+        cudaFree(fresh);
+    } else {
+        cudaFree(t->buckets);
+        t->buckets = fresh;
+    }
     if (n_left) *n_left = t->n_keys;
     return rc;
 }

@@ -109,12 +109,14 @@ __global__ void __launch_bounds__(256) km_query_kernel(TableView T, const uint64
     for (uint64_t base = tid; base < n; base += stride * KM_QUERY_ILP) {
         uint64_t q[KM_QUERY_ILP];
         uint32_t r[KM_QUERY_ILP];
+        uint32_t live = 0;                 // a padded slot must not be probed: in a sharded table its key may live on a peer
 #pragma unroll
         for (int i = 0; i < KM_QUERY_ILP; ++i) {
             const uint64_t j = base + (uint64_t)i * stride;
             q[i] = j < n ? kmers[j] : 0ull;
+            live |= j < n ? (1u << i) : 0u;
         }
-        table_query_multi<KM_QUERY_ILP>(T, q, r);
+        table_query_masked<KM_QUERY_ILP>(T, q, live, r);
 #pragma unroll
         for (int i = 0; i < KM_QUERY_ILP; ++i) {
             const uint64_t j = base + (uint64_t)i * stride;

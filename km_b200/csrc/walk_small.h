@@ -86,36 +86,6 @@ KM_HD int ws_insert(WalkSmall& M, uint64_t key, int idx, int L, int k) {
     }
 }
 
-// N independent lookups in flight, only where `mask` has the bit set (others return 0).
-template <int N>
-KM_HD void table_query_masked(const TableView& T, const uint64_t (&fwd)[N], uint32_t mask, uint32_t (&out)[N]) {
-    uint64_t key[N], b[N], k0[N], k1[N];
-    uint32_t c0[N], c1[N];
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-        const uint64_t v = fwd[i] & T.kmask;
-        key[i] = T.canonical ? canonical(v, T.k) : v;
-        b[i] = bucket_of(T, key[i]);
-    }
-#pragma unroll
-    for (int i = 0; i < N; ++i)
-        if (mask & (1u << i)) load_bucket(T.buckets + b[i], k0[i], k1[i], c0[i], c1[i]);
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-        uint32_t r = 0;
-        if (mask & (1u << i)) {
-            for (;;) {
-                if (k0[i] == key[i]) { r = c0[i]; break; }
-                if (k1[i] == key[i]) { r = c1[i]; break; }
-                if (k0[i] == KM_EMPTY_KEY || k1[i] == KM_EMPTY_KEY) break;
-                if (++b[i] == T.n_buckets) b[i] = 0;      // rare: full bucket without the key
-                load_bucket(T.buckets + b[i], k0[i], k1[i], c0[i], c1[i]);
-            }
-        }
-        out[i] = r;
-    }
-}
-
 // Level 0 of every walk, flat over the reference k-mers of ALL targets (K3a).  One warp takes 32
 // consecutive reference k-mers of one target: each lane fetches the count of its own k-mer
 // (MutationFinder.py:111-112) and of the three successors that leave the reference

@@ -27,6 +27,7 @@ void* emu_table_create(int k, int canonical, uint64_t capacity) {
     t->store.resize(nb);
     for (auto& b : t->store) { b.key[0] = b.key[1] = KM_EMPTY_KEY; b.count[0] = b.count[1] = 0; b.pad[0] = b.pad[1] = 0; }
     t->v.buckets = t->store.data(); t->v.n_buckets = nb; t->v.k = k; t->v.canonical = canonical; t->v.kmask = kmer_mask(k);
+    t->v.n_shards = 1; t->v.my_shard = 0; for (auto& sp : t->v.shard) sp = nullptr; t->v.shard[0] = t->v.buckets;
     return t;
 }
 void emu_table_free(void* h) { delete (EmuTable*)h; }
