@@ -647,7 +647,7 @@ struct km_plan {
     int n = 0;
     km_find_params prm{};
     std::string targets;
-    std::vector<int64_t> seq_off, node_off, hash_off;
+    std::vector<int64_t> seq_off, node_off, hash_off, pack_off;
     std::vector<int32_t> chunk_target, chunk_start;   // <= 32 consecutive reference k-mers each (ref_probe_chunk)
     std::vector<int32_t> extra;
     int64_t pool_cap = 0, seq_cap = 0, n_node = 0, n_hash = 0, n_code = 0;
@@ -683,6 +683,9 @@ static int plan_layout(km_plan* p) {
         p->node_off[i + 1] = p->node_off[i] + cap;
         p->hash_off[i + 1] = p->hash_off[i] + pow2_at_least(2 * (uint64_t)cap + 256);
     }
+    p->pack_off.assign(n + 1, 0);
+    for (int i = 0; i < n; ++i) p->pack_off[i + 1] = p->pack_off[i] + (p->seq_off[i + 1] - p->seq_off[i] + 15) / 16 + 2;
+    const int64_t n_pack = p->pack_off[n];
     p->chunk_target.clear(); p->chunk_start.clear();
     for (int i = 0; i < n; ++i) {
         const int L = (int)std::max<int64_t>(0, p->seq_off[i + 1] - p->seq_off[i] - k + 1);
@@ -699,6 +702,7 @@ static int plan_layout(km_plan* p) {
     size_t need = 4096;
     auto acc = [&](size_t bytes) { need = align_up(need, 256) + bytes; };
     acc(n_code); acc(8 * (n + 1)); acc(8 * (n + 1)); acc(8 * (n + 1)); acc(4 * n_chunks); acc(4 * n_chunks);
+    acc(4 * (size_t)n_pack); acc(8 * (n + 1)); acc(n);
     acc(8 * n_node); acc(4 * n_node); acc(4 * n_node); acc(16 * n_node);          // node arrays
     acc(8 * n_hash); acc(4 * n_hash); acc(4 * n_hash); acc(n_hash);                // visited sets
     acc(4 * n); acc(4 * n); acc(4 * n); acc(8 * n);                                // n_nodes n_kept status lookups
@@ -715,6 +719,7 @@ static int plan_layout(km_plan* p) {
     W.codes = A.take<uint8_t>(n_code);
     W.seq_off = A.take<int64_t>(n + 1); W.node_off = A.take<int64_t>(n + 1); W.hash_off = A.take<int64_t>(n + 1);
     W.chunk_target = A.take<int32_t>(n_chunks); W.chunk_start = A.take<int32_t>(n_chunks); W.n_chunks = (int)n_chunks;
+    W.pack = A.take<uint32_t>((size_t)n_pack); W.pack_off = A.take<int64_t>(n + 1); W.pre_bad = A.take<uint8_t>(n);
     W.node_kmer = A.take<uint64_t>(n_node); W.node_count = A.take<uint32_t>(n_node);
     W.node_slot = A.take<uint32_t>(n_node); W.node_kid = A.take<uint32_t>(4 * n_node);
     W.hkey = A.take<uint64_t>(n_hash); W.hval = A.take<uint32_t>(n_hash); W.hmeta = A.take<uint32_t>(n_hash);
@@ -745,12 +750,14 @@ static int plan_layout(km_plan* p) {
 static int plan_upload(km_plan* p, cudaStream_t s) {
     const int n = p->n;
     const size_t n_chunks = p->chunk_target.size();
-    if (int rc = p->pin->reserve((size_t)p->n_code + 24 * (size_t)(n + 1) + 8 * n_chunks + 8192)) return rc;
+    if (int rc = p->pin->reserve((size_t)p->n_code + 32 * (size_t)(n + 1) + 8 * n_chunks + 8192)) return rc;
     p->pin->reset();
     uint8_t* h_codes = p->pin->take<uint8_t>(p->n_code);
     int64_t* h_seq_off = p->pin->take<int64_t>(n + 1);
     int64_t* h_node_off = p->pin->take<int64_t>(n + 1);
     int64_t* h_hash_off = p->pin->take<int64_t>(n + 1);
+    int64_t* h_pack_off = p->pin->take<int64_t>(n + 1);
+    memcpy(h_pack_off, p->pack_off.data(), 8 * (n + 1));
     int32_t* h_ct = p->pin->take<int32_t>(n_chunks);
     int32_t* h_cs = p->pin->take<int32_t>(n_chunks);
     if (n_chunks) { memcpy(h_ct, p->chunk_target.data(), 4 * n_chunks); memcpy(h_cs, p->chunk_start.data(), 4 * n_chunks); }
@@ -760,10 +767,6 @@ static int plan_upload(km_plan* p, cudaStream_t s) {
     memcpy(h_hash_off, p->hash_off.data(), 8 * (n + 1));
     CU(cudaEventRecord(p->t->ev[0], s));
     CU(cudaMemcpyAsync((void*)p->W.codes, h_codes, p->n_code, cudaMemcpyHostToDevice, s));
-    if (p->n_code) {
-        km_encode_kernel<<<grid_for(p->t, (uint64_t)p->n_code, 256, 8), 256, 0, s>>>(const_cast<uint8_t*>(p->W.codes), p->n_code);
-        CU(cudaGetLastError());
-    }
     CU(cudaMemcpyAsync((void*)p->W.seq_off, h_seq_off, 8 * (n + 1), cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync((void*)p->W.node_off, h_node_off, 8 * (n + 1), cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync((void*)p->W.hash_off, h_hash_off, 8 * (n + 1), cudaMemcpyHostToDevice, s));
@@ -771,7 +774,13 @@ static int plan_upload(km_plan* p, cudaStream_t s) {
         CU(cudaMemcpyAsync((void*)p->W.chunk_target, h_ct, 4 * n_chunks, cudaMemcpyHostToDevice, s));
         CU(cudaMemcpyAsync((void*)p->W.chunk_start, h_cs, 4 * n_chunks, cudaMemcpyHostToDevice, s));
     }
-    p->bytes_h2d = (unsigned long long)p->n_code + 24ull * (n + 1) + 8ull * n_chunks;
+    CU(cudaMemcpyAsync((void*)p->W.pack_off, h_pack_off, 8 * (n + 1), cudaMemcpyHostToDevice, s));
+    if (n) {
+        km_encode_kernel<<<(n + 7) / 8, 256, 0, s>>>(const_cast<uint8_t*>(p->W.codes), p->W.seq_off, const_cast<uint32_t*>(p->W.pack),
+                                                     p->W.pack_off, const_cast<uint8_t*>(p->W.pre_bad), n);
+        CU(cudaGetLastError());
+    }
+    p->bytes_h2d = (unsigned long long)p->n_code + 32ull * (n + 1) + 8ull * n_chunks;
     return 0;
 }
 

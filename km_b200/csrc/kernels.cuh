@@ -88,14 +88,33 @@ __global__ void km_table_filter_kernel(TableView src, TableView dst, uint32_t mi
     if (mine) atomicAdd(n_new, mine);
 }
 
-// target letters -> 2-bit codes in place (A0 C1 G2 T3, anything else 255): the host uploads the
-// sequences as they came in
-__global__ void km_encode_kernel(uint8_t* seq, int64_t n) {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const uint8_t c = seq[i];
-        seq[i] = c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : 255;
+// Once per upload, one warp per target: letters -> codes in place (A0 C1 G2 T3, anything else 255; the
+// general walk reads these) and the 2-bit packed copy the probe and shared-memory walk kernels read
+// (16 bases per word, first base in the top bits, >= 2 zero words after each target).
+__global__ void km_encode_kernel(uint8_t* seq, const int64_t* seq_off, uint32_t* pack, const int64_t* pack_off, uint8_t* pre_bad,
+                                 int n_targets) {
+    const int t = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (t >= n_targets) return;
+    const int64_t s0 = seq_off[t], w0 = pack_off[t];
+    const int len = (int)(seq_off[t + 1] - s0), nw = (int)(pack_off[t + 1] - w0);
+    bool bad = false;
+    for (int w = lane; w < nw; w += 32) {
+        uint32_t word = 0;
+        for (int j = 0; j < 16; ++j) {
+            const int pos = 16 * w + j;
+            uint32_t c = 0;
+            if (pos < len) {
+                const uint8_t ch = seq[s0 + pos];
+                c = ch == 'A' ? 0u : ch == 'C' ? 1u : ch == 'G' ? 2u : ch == 'T' ? 3u : 255u;
+                seq[s0 + pos] = (uint8_t)c;
+                if (c > 3u) { bad = true; c = 0u; }
+            }
+            word = (word << 2) | c;
+        }
+        pack[w0 + w] = word;
     }
+    bad = __any_sync(0xFFFFFFFFu, bad);
+    if (lane == 0) pre_bad[t] = bad ? 1 : 0;
 }
 
 // ---- K2: batched canonical probe (Jellyfish.query) ---------------------------------------
@@ -152,7 +171,7 @@ __global__ void __launch_bounds__(256) km_get_child_kernel(TableView T, const ui
 #define KM_WALK_WARPS 4
 #define KM_PROBE_WARPS 8
 // K3a: level 0 of every walk, one warp per 32 reference k-mers, flat over the batch
-__global__ void __launch_bounds__(32 * KM_PROBE_WARPS) km_ref_probe_kernel(TableView T, WalkView W, FindParams P) {
+__global__ void __launch_bounds__(32 * KM_PROBE_WARPS, 4) km_ref_probe_kernel(TableView T, WalkView W, FindParams P) {
     WarpCtx ctx;
     const int ch = (int)blockIdx.x * KM_PROBE_WARPS + (int)(threadIdx.x >> 5);
     if (ch >= W.n_chunks) return;

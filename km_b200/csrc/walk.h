@@ -49,6 +49,11 @@ struct WalkView {
     const int64_t* seq_off;   // [n+1]
     const int64_t* node_off;  // [n+1]  node capacity of target t = node_off[t+1]-node_off[t]
     const int64_t* hash_off;  // [n+1]  visited-set slots (power of two per target)
+    // the same targets 2-bit packed, 16 bases per word, first base in the top bits; every target starts on a
+    // word and is followed by >= 2 zero words (written once per upload by km_encode_kernel)
+    const uint32_t* pack;
+    const int64_t* pack_off;  // [n+1]  word offsets
+    const uint8_t* pre_bad;   // [n]    1 = the target holds a letter outside ACGT
     // node arrays, discovery order: reference k-mers first (index = position), then novel
     uint64_t* node_kmer;
     uint32_t* node_count;
@@ -92,6 +97,15 @@ KM_HD TargetGeom target_geom(const WalkView& W, int t, int k) {
     g.hmask = (uint32_t)(W.hash_off[t + 1] - g.hbase) - 1u;
     return g;
 }
+
+// k-mer starting at base i of a packed sequence (k <= 31; words[w+2] must be readable)
+KM_HD uint64_t packed_kmer(const uint32_t* words, int i, int k) {
+    const int w = i >> 4, o = i & 15;
+    const uint64_t hi = ((uint64_t)words[w] << 32) | (uint64_t)words[w + 1];
+    const uint64_t x = o ? ((hi << (2 * o)) | ((uint64_t)words[w + 2] >> (32 - 2 * o))) : hi;
+    return x >> (64 - 2 * k);
+}
+KM_HD int packed_base(const uint32_t* words, int i) { return (int)((words[i >> 4] >> (2 * (15 - (i & 15)))) & 3u); }
 
 // Find `key` in the target's visited set or claim a slot for it.  Returns the slot;
 // *is_new tells whether THIS caller won the claim.

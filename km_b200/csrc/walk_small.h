@@ -42,12 +42,7 @@ struct alignas(16) WalkSmall {
 KM_HD bool walk_small_fits(const TargetGeom& g) { return g.L >= 1 && g.L <= KM_WS_MAXL; }
 
 // reference k-mer i from the packed target (k <= 31)
-KM_HD uint64_t ws_ref_kmer(const WalkSmall& M, int i, int k) {
-    const int w = i >> 4, o = i & 15;
-    const uint64_t hi = ((uint64_t)M.seq2[w] << 32) | (uint64_t)M.seq2[w + 1];
-    const uint64_t x = o ? ((hi << (2 * o)) | ((uint64_t)M.seq2[w + 2] >> (32 - 2 * o))) : hi;
-    return x >> (64 - 2 * k);
-}
+KM_HD uint64_t ws_ref_kmer(const WalkSmall& M, int i, int k) { return packed_kmer(M.seq2, i, k); }
 
 KM_HD uint64_t ws_node_key(const WalkSmall& M, int idx, int L, int k) { return idx < L ? ws_ref_kmer(M, idx, k) : M.nk[idx - L]; }
 
@@ -109,9 +104,9 @@ KM_HD void ref_probe_chunk(const Ctx& ctx, const TableView& T, const WalkView& W
     int ref_c = -1;
     uint32_t mask = 0;
     if (active) {
-        uint64_t v = 0;
-        for (int j = 0; j < k; ++j) v = (v << 2) | (uint64_t)(W.codes[g.sbase + i + j] & 3);
-        if (i + 1 < g.L) ref_c = (int)(W.codes[g.sbase + i + k] & 3);
+        const uint32_t* words = W.pack + W.pack_off[t];
+        const uint64_t v = packed_kmer(words, i, k);
+        if (i + 1 < g.L) ref_c = packed_base(words, i + k);
         q[0] = v;
         mask = 1u;
 #pragma unroll
@@ -123,7 +118,10 @@ KM_HD void ref_probe_chunk(const Ctx& ctx, const TableView& T, const WalkView& W
     table_query_masked<5>(T, q, mask, r);
     const uint32_t next_own = (uint32_t)warp_shfl_down32((int)r[0], 1);
     if (active) {
-        if (ref_c >= 0 && lane != nl - 1) r[1 + ref_c] = next_own;
+        if (lane != nl - 1) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) if (c == ref_c) r[1 + c] = next_own;      // (no dynamic index: r stays in registers)
+        }
         W.node_kmer[g.nbase + i] = q[0];
         W.node_count[g.nbase + i] = r[0];
         uint32_t* cc = W.node_kid + 4 * (g.nbase + i);
@@ -210,17 +208,12 @@ KM_HD bool walk_small_target(const Ctx& ctx, const TableView& T, const WalkView&
     PhaseTimer pt;
     // ---- set-up: clear the set, pack the target ---------------------------------------------
     for (int s = lane; s < KM_WS_HASH / 2; s += nl) M.slot[s] = 0u;
-    const int len = L + k - 1;
-    for (int w = lane; w < KM_WS_SEQW; w += nl) {
-        uint32_t word = 0;
-        for (int j = 0; j < 16; ++j) {
-            const int pos = 16 * w + j;
-            uint32_t c = 0;
-            if (pos < len) { c = W.codes[g.sbase + pos]; if (c > 3) { st |= KM_ST_BAD_BASE; c &= 3; } }
-            word = (word << 2) | c;
-        }
-        M.seq2[w] = word;
+    {
+        const int64_t w0 = W.pack_off[t];
+        const int nw = (int)(W.pack_off[t + 1] - w0);
+        for (int w = lane; w < KM_WS_SEQW; w += nl) M.seq2[w] = w < nw ? W.pack[w0 + w] : 0u;
     }
+    if (W.pre_bad[t]) st |= KM_ST_BAD_BASE;
     if (lane == 0) { M.n_nodes = L; M.flags = 0; }
     ctx.sync();
 

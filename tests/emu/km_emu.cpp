@@ -72,6 +72,17 @@ int emu_find_target(void* h, const uint8_t* codes, int len, double ratio, int64_
     W.node_kmer = node_kmer.data(); W.node_count = node_count.data(); W.node_slot = node_slot.data(); W.node_kid = node_kid.data();
     W.hkey = hkey.data(); W.hval = hval.data(); W.hmeta = hmeta.data(); W.hflag = hflag.data();
     W.n_nodes = &n_nodes; W.n_kept = &n_kept; W.status = &status; W.lookups = &lookups;
+    // what km_encode_kernel prepares once per upload
+    const int n_words = (len + 15) / 16 + 2;
+    std::vector<uint32_t> pack((size_t)n_words, 0u);
+    uint8_t pre_bad = 0;
+    for (int pos = 0; pos < len; ++pos) {
+        uint32_t c = codes[pos];
+        if (c > 3) { pre_bad = 1; c = 0; }
+        pack[(size_t)(pos >> 4)] |= c << (2 * (15 - (pos & 15)));
+    }
+    int64_t pack_off[2] = {0, n_words};
+    W.pack = pack.data(); W.pack_off = pack_off; W.pre_bad = &pre_bad;
     FindParams P; P.ratio = ratio; P.count = count; P.max_stack = steps; P.max_break = branchs; P.max_node = nodes;
     CtaCtx ctx;
     // the two walk kernels: shared-memory walk first, the general one for what it defers

@@ -2,6 +2,7 @@
 // which load flavour does the fabric like?   nvcc -O3 -arch=sm_100a peer_gather.cu -o peer_gather
 #include <cstdio>
 #include <cstdint>
+#include <cstdlib>
 #include <cuda_runtime.h>
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e)); return 1; } } while (0)
 __device__ __forceinline__ uint64_t mix64(uint64_t z) { z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; return z ^ (z >> 31); }
@@ -59,8 +60,10 @@ int main(int argc, char** argv) {
     CK(cudaSetDevice(0)); CK(cudaMalloc(&sink, 4));
     const char* names[6] = {"ld.global.nc.L1::no_allocate 2x16B", "ld.global 2x16B", "ld.global.cg 2x16B", "ld.global 1x16B", "ld.global.v4.u64 1x32B", "ld.global.L1::no_allocate.v4.u64 1x32B"};
     if (n >= 2) CK(cudaDeviceEnablePeerAccess(1, 0));
+    size_t gran = 0; cudaDeviceGetLimit(&gran, cudaLimitMaxL2FetchGranularity); printf("default L2 fetch granularity %zu\n", gran);
+    if (argc > 1) { cudaError_t e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, atoi(argv[1])); cudaDeviceGetLimit(&gran, cudaLimitMaxL2FetchGranularity); printf("set %s -> %s, now %zu\n", argv[1], cudaGetErrorString(e), gran); }
     for (int where = 0; where < (n >= 2 ? 2 : 1); ++where)
-        for (uint64_t gib : {8ull, 32ull, 64ull}) {
+        for (uint64_t gib : {64ull}) {
             uint4* buf;
             const uint64_t bytes = gib << 30, n_sectors = bytes / 32;
             CK(cudaSetDevice(where)); CK(cudaMalloc(&buf, bytes)); CK(cudaMemset(buf, 1, bytes)); CK(cudaDeviceSynchronize());
