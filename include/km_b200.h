@@ -207,6 +207,14 @@ int64_t km_result_format_all(const km_result* r, const char* db_name, const char
 int64_t km_result_text(const km_result* r, const char* db_name, const char* names_host, const int64_t* name_off,
                        int32_t threads, const char** text);
 
+/* `km find_mutation` for a whole batch as ONE call: host buffers in (sequences + offsets, query names +
+ * offsets), the sorted TSV text out (read it with km_result_text, same db_name / names; km_result_get
+ * gives the per-target status).  The batch runs as n_sub sub-batches in flight at once (0 = choose), so
+ * copies, kernels and the host-side text building overlap.  Same text as km_find_batch +
+ * km_result_format_all. */
+int km_find_text(km_table* t, const char* seqs_host, const int64_t* offsets, int32_t n_targets, const km_find_params* params,
+                 const char* db_name, const char* names_host, const int64_t* name_off, int32_t n_sub, km_result** out);
+
 /* ---- test hooks for the host-side text path (no GPU needed) ------------------------------ */
 /* "%.{prec}f" as the formatter prints it (prec 0..3), NUL-terminated into buf64; returns the length */
 int km_debug_format_fixed(double v, int prec, char* buf64);

@@ -95,6 +95,8 @@ def lib():
     L.km_debug_format_fixed.restype = ci
     L.km_debug_nat_cmp.argtypes = [cp, cp]
     L.km_debug_nat_cmp.restype = ci
+    L.km_find_text.argtypes = [vp, cp, vp, i32, P(FindParams), cp, cp, vp, i32, P(vp)]
+    L.km_find_text.restype = ci
     L.km_result_text.argtypes = [vp, cp, cp, vp, i32, P(vp)]
     L.km_result_text.restype = i64
     L.km_find_plan_create.argtypes = [vp, cp, vp, i32, P(FindParams), P(vp)]
@@ -125,6 +127,6 @@ def check(rc):
 EXPORTS = ["km_last_error", "km_device_count", "km_version", "km_table_open_jf", "km_table_create",
            "km_table_insert", "km_table_build_synthetic", "km_table_count_reads", "km_table_drop_below",
            "km_table_get_info", "km_table_close", "km_query_batch", "km_query_batch_device", "km_query_ascii",
-           "km_get_child_batch", "km_find_batch", "km_result_get", "km_result_free", "km_result_format_target", "km_result_format_all", "km_result_text", "km_table_create_shard", "km_table_shard_export_fd", "km_table_shard_attach_fd", "km_shard_owner", "km_debug_format_fixed", "km_debug_nat_cmp",
+           "km_get_child_batch", "km_find_batch", "km_result_get", "km_result_free", "km_result_format_target", "km_result_format_all", "km_result_text", "km_find_text", "km_table_create_shard", "km_table_shard_export_fd", "km_table_shard_attach_fd", "km_shard_owner", "km_debug_format_fixed", "km_debug_nat_cmp",
            "km_find_plan_create", "km_find_plan_launch", "km_find_plan_fetch", "km_find_plan_free", "km_find_plan_last_ms", "km_find_plan_kernel_ms",
            "km_bench_random_gather", "km_bench_lookup", "km_debug_phase_cycles"]

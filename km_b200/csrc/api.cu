@@ -8,6 +8,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <deque>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -87,16 +90,25 @@ struct PinPool {
         for (size_t i = 0; i < idle.size(); ++i)
             if (idle[i].second >= bytes && (best < 0 || idle[i].second < idle[(size_t)best].second)) best = (int)i;
         if (best >= 0) { *out = idle[(size_t)best].first; *cap = idle[(size_t)best].second; idle.erase(idle.begin() + best); return 0; }
-        // nothing fits: drop the smaller idle blocks (they would never be picked again for this workload)
-        for (auto& b : idle) cudaFreeHost(b.first);
-        idle.clear();
+        // nothing fits: allocate (with headroom, so that a slightly larger batch next time still fits);
+        // the pool is trimmed when blocks come back (release)
         const size_t want = bytes + bytes / 4 + (1 << 16);
         cudaError_t e = cudaMallocHost((void**)out, want);
         if (e != cudaSuccess) return fail(KM_E_CUDA, "pinned alloc of %zu bytes failed: %s", want, cudaGetErrorString(e));
         *cap = want;
         return 0;
     }
-    void release(char* p, size_t cap) { if (p) { std::lock_guard<std::mutex> g(m); idle.emplace_back(p, cap); } }
+    void release(char* p, size_t cap) {
+        if (!p) return;
+        std::lock_guard<std::mutex> g(m);
+        idle.emplace_back(p, cap);
+        if (idle.size() > 48) {            // keep the largest blocks
+            size_t small = 0;
+            for (size_t i = 1; i < idle.size(); ++i) if (idle[i].second < idle[small].second) small = i;
+            cudaFreeHost(idle[small].first);
+            idle.erase(idle.begin() + (long)small);
+        }
+    }
     ~PinPool() { for (auto& b : idle) cudaFreeHost(b.first); }
 };
 
@@ -136,6 +148,10 @@ struct km_table {
     cudaEvent_t ev[8] = {};
     Arena dev, pin;            // lookups / inserts
     Arena dev_find, pin_find;  // km_find_batch workspace, reused across calls
+    // km_find_text runs a batch as several sub-batches in flight at once: each has its own workspace,
+    // stream and events, kept across calls
+    struct Lane { Arena dev, pin; cudaStream_t stream = nullptr; cudaEvent_t ev[8] = {}; };
+    std::vector<std::unique_ptr<Lane>> lanes;
     std::shared_ptr<PinPool> pool = std::make_shared<PinPool>();   // result buffers (outlive the table if a result does)
     int sm_count = 148;
     // cohort mode: this table is shard `my_shard` of `n_shards`; peer[r] = rank r's buckets mapped through CUDA IPC
@@ -365,6 +381,11 @@ extern "C" void km_table_close(km_table* t) {
     t->pin.release();
     t->dev_find.release();
     t->pin_find.release();
+    for (auto& L : t->lanes) {
+        L->dev.release(); L->pin.release();
+        for (auto& e : L->ev) if (e) cudaEventDestroy(e);
+        if (L->stream) cudaStreamDestroy(L->stream);
+    }
     for (auto& ev : t->ev) if (ev) cudaEventDestroy(ev);
     if (t->stream) cudaStreamDestroy(t->stream);
     delete t;
@@ -634,6 +655,9 @@ struct km_result {
     mutable std::string fmt_key;
     mutable std::unique_ptr<char[]> text;
     mutable int64_t text_len = -1;
+    // km_find_text: the result of a pipelined run keeps its sub-batches and the joined text
+    std::vector<std::unique_ptr<km_result>> parts;
+    std::vector<uint32_t> all_status;
 };
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -667,6 +691,8 @@ struct km_plan {
     int n_launches = 0, n_retries = 0;
     bool launched = false;
     unsigned long long bytes_h2d = 0;
+    cudaStream_t stream = nullptr;      // the table's own unless the plan runs on a lane
+    cudaEvent_t* ev = nullptr;
 };
 
 static int plan_layout(km_plan* p) {
@@ -765,7 +791,7 @@ static int plan_upload(km_plan* p, cudaStream_t s) {
     memcpy(h_seq_off, p->seq_off.data(), 8 * (n + 1));
     memcpy(h_node_off, p->node_off.data(), 8 * (n + 1));
     memcpy(h_hash_off, p->hash_off.data(), 8 * (n + 1));
-    CU(cudaEventRecord(p->t->ev[0], s));
+    CU(cudaEventRecord(p->ev[0], s));
     CU(cudaMemcpyAsync((void*)p->W.codes, h_codes, p->n_code, cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync((void*)p->W.seq_off, h_seq_off, 8 * (n + 1), cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync((void*)p->W.node_off, h_node_off, 8 * (n + 1), cudaMemcpyHostToDevice, s));
@@ -788,26 +814,26 @@ static int plan_upload(km_plan* p, cudaStream_t s) {
 static int plan_launch(km_plan* p, cudaStream_t s) {
     km_table* t = p->t;
     if (p->n == 0) return 0;
-    CU(cudaEventRecord(t->ev[1], s));
+    CU(cudaEventRecord(p->ev[1], s));
     CU(cudaMemsetAsync(p->state0, 0, p->state_bytes, s));
     CU(cudaMemsetAsync(p->R.used, 0, 32, s));
     if (p->W.n_chunks) {
         km_ref_probe_kernel<<<(p->W.n_chunks + KM_PROBE_WARPS - 1) / KM_PROBE_WARPS, 32 * KM_PROBE_WARPS, 0, s>>>(t->view(), p->W, p->P);
         CU(cudaGetLastError());
     }
-    CU(cudaEventRecord(t->ev[6], s));
+    CU(cudaEventRecord(p->ev[6], s));
     km_walk_small_kernel<<<(p->n + KM_WALK_WARPS - 1) / KM_WALK_WARPS, 32 * KM_WALK_WARPS, 0, s>>>(t->view(), p->W, p->P);
     CU(cudaGetLastError());
     km_walk_kernel<<<(p->n + KM_WALK_WARPS - 1) / KM_WALK_WARPS, 32 * KM_WALK_WARPS, 0, s>>>(t->view(), p->W, p->P);
     CU(cudaGetLastError());
-    CU(cudaEventRecord(t->ev[2], s));
+    CU(cudaEventRecord(p->ev[2], s));
     // shared-memory pass first, then the general pass for large or deferred targets
     const size_t small_smem = small_layout().stride;
     km_graph_kernel<true><<<p->grid_graph, KM_CTA, small_smem, s>>>(t->view(), p->W, p->SL, p->R);
     CU(cudaGetLastError());
     km_graph_kernel<false><<<p->grid_large, KM_CTA, 0, s>>>(t->view(), p->W, p->SL, p->R);
     CU(cudaGetLastError());
-    CU(cudaEventRecord(t->ev[3], s));
+    CU(cudaEventRecord(p->ev[3], s));
     p->n_launches += 5;
     p->launched = true;
     return 0;
@@ -870,22 +896,24 @@ static int plan_download(km_plan* p, cudaStream_t s, km_result* res, bool want_g
     res->bytes_d2h = 36ull * n + 32 + 20ull * n_paths + sizeof(Row) * n_rows + n_seq +
                      (want_graph ? 4ull * n_pool + 12ull * p->n_node : 0ull);
     res->text_len = -1; res->text.reset(); res->fmt_key.clear();
-    CU(cudaEventRecord(t->ev[4], s));
+    CU(cudaEventRecord(p->ev[4], s));
     CU(cudaStreamSynchronize(s));
     float ms;
     if (n) {
-        CU(cudaEventElapsedTime(&ms, t->ev[0], t->ev[1])); res->ms_h2d = ms;
-        CU(cudaEventElapsedTime(&ms, t->ev[1], t->ev[2])); res->ms_walk = ms;
-        CU(cudaEventElapsedTime(&ms, t->ev[2], t->ev[3])); res->ms_graph = ms;
-        CU(cudaEventElapsedTime(&ms, t->ev[3], t->ev[4])); res->ms_d2h = ms;
-        CU(cudaEventElapsedTime(&ms, t->ev[0], t->ev[4])); res->ms_total = ms;
+        CU(cudaEventElapsedTime(&ms, p->ev[0], p->ev[1])); res->ms_h2d = ms;
+        CU(cudaEventElapsedTime(&ms, p->ev[1], p->ev[2])); res->ms_walk = ms;
+        CU(cudaEventElapsedTime(&ms, p->ev[2], p->ev[3])); res->ms_graph = ms;
+        CU(cudaEventElapsedTime(&ms, p->ev[3], p->ev[4])); res->ms_d2h = ms;
+        CU(cudaEventElapsedTime(&ms, p->ev[0], p->ev[4])); res->ms_total = ms;
     }
     return 0;
 }
 
 static int plan_init(km_table* t, const char* seqs, const int64_t* offsets, int32_t n, const km_find_params* params, km_plan* p,
-                     bool borrow_arena) {
+                     bool borrow_arena, km_table::Lane* lane = nullptr) {
     p->t = t; p->n = n; p->prm = *params;
+    p->stream = lane ? lane->stream : t->stream;
+    p->ev = lane ? lane->ev : t->ev;
     if (p->prm.steps > 60000 || p->prm.branchs > 250) return fail(KM_E_ARG, "steps must be <= 60000 and branchs <= 250");
     const int64_t total = n ? offsets[n] : 0;
     p->targets.assign(seqs ? seqs : "", (size_t)total);
@@ -900,10 +928,10 @@ static int plan_init(km_table* t, const char* seqs, const int64_t* offsets, int3
     p->seq_cap = p->pool_cap + (int64_t)p->path_cap * t->k;
     p->extra_max = std::max(1024, p->prm.nodes + 4 * p->prm.steps + 4096);
     p->own_pin.host = true;
-    p->dev = borrow_arena ? &t->dev_find : &p->own_dev;
-    p->pin = borrow_arena ? &t->pin_find : &p->own_pin;
+    p->dev = lane ? &lane->dev : borrow_arena ? &t->dev_find : &p->own_dev;
+    p->pin = lane ? &lane->pin : borrow_arena ? &t->pin_find : &p->own_pin;
     if (int rc = plan_layout(p)) return rc;
-    return plan_upload(p, t->stream);
+    return plan_upload(p, p->stream);
 }
 
 // fetch with the capacity-retry loop: targets whose exploration overflowed get 8x the node
@@ -911,8 +939,8 @@ static int plan_init(km_table* t, const char* seqs, const int64_t* offsets, int3
 static int plan_fetch(km_plan* p, km_result* res, bool want_graph) {
     km_table* t = p->t;
     for (int attempt = 0; attempt < 12; ++attempt) {
-        if (!p->launched) if (int rc = plan_launch(p, t->stream)) return rc;
-        if (int rc = plan_download(p, t->stream, res, want_graph)) return rc;
+        if (!p->launched) if (int rc = plan_launch(p, p->stream)) return rc;
+        if (int rc = plan_download(p, p->stream, res, want_graph)) return rc;
         bool again = false, pool_over = false;
         for (int i = 0; i < p->n; ++i) {
             if (res->status[i] & KM_ST_NODE_OVERFLOW) {
@@ -932,7 +960,7 @@ static int plan_fetch(km_plan* p, km_result* res, bool want_graph) {
         p->n_retries++;
         p->launched = false;
         if (int rc = plan_layout(p)) return rc;
-        if (int rc = plan_upload(p, t->stream)) return rc;
+        if (int rc = plan_upload(p, p->stream)) return rc;
     }
     return fail(KM_E_LIMIT, "km_find: capacities still exceeded after 12 attempts");
 }
@@ -951,25 +979,25 @@ extern "C" int km_find_plan_create(km_table* t, const char* seqs, const int64_t*
 extern "C" int km_find_plan_launch(km_plan* p, void* stream) {
     if (!p) return fail(KM_E_ARG, "null plan");
     CU(cudaSetDevice(p->t->device));
-    return plan_launch(p, stream ? (cudaStream_t)stream : p->t->stream);
+    return plan_launch(p, stream ? (cudaStream_t)stream : p->stream);
 }
 
 extern "C" int km_find_plan_last_ms(km_plan* p, float* walk_ms, float* graph_ms) {
     if (!p || !p->launched) return fail(KM_E_ARG, "km_find_plan_last_ms: nothing launched");
     CU(cudaSetDevice(p->t->device));
-    CU(cudaEventSynchronize(p->t->ev[3]));
-    if (walk_ms) CU(cudaEventElapsedTime(walk_ms, p->t->ev[1], p->t->ev[2]));
-    if (graph_ms) CU(cudaEventElapsedTime(graph_ms, p->t->ev[2], p->t->ev[3]));
+    CU(cudaEventSynchronize(p->ev[3]));
+    if (walk_ms) CU(cudaEventElapsedTime(walk_ms, p->ev[1], p->ev[2]));
+    if (graph_ms) CU(cudaEventElapsedTime(graph_ms, p->ev[2], p->ev[3]));
     return 0;
 }
 
 extern "C" int km_find_plan_kernel_ms(km_plan* p, float* out3) {
     if (!p || !p->launched || !out3) return fail(KM_E_ARG, "km_find_plan_kernel_ms: nothing launched");
     CU(cudaSetDevice(p->t->device));
-    CU(cudaEventSynchronize(p->t->ev[3]));
-    CU(cudaEventElapsedTime(&out3[0], p->t->ev[1], p->t->ev[6]));    // memsets + reference probe
-    CU(cudaEventElapsedTime(&out3[1], p->t->ev[6], p->t->ev[2]));    // the two walk kernels
-    CU(cudaEventElapsedTime(&out3[2], p->t->ev[2], p->t->ev[3]));    // the two graph kernels
+    CU(cudaEventSynchronize(p->ev[3]));
+    CU(cudaEventElapsedTime(&out3[0], p->ev[1], p->ev[6]));    // memsets + reference probe
+    CU(cudaEventElapsedTime(&out3[1], p->ev[6], p->ev[2]));    // the two walk kernels
+    CU(cudaEventElapsedTime(&out3[2], p->ev[2], p->ev[3]));    // the two graph kernels
     return 0;
 }
 
@@ -1011,6 +1039,13 @@ extern "C" int km_result_get(const km_result* r, km_result_view* v) {
     if (!r || !v) return fail(KM_E_ARG, "null argument");
     memset(v, 0, sizeof(*v));
     v->n_targets = r->n_targets; v->n_paths = (int32_t)r->path_off.size(); v->n_rows = (int32_t)r->rows.size(); v->k = r->k;
+    if (!r->parts.empty()) {      // a km_find_text result: the text and the per-target status are what it holds
+        v->status = r->all_status.data();
+        v->ms_h2d = r->ms_h2d; v->ms_walk = r->ms_walk; v->ms_graph = r->ms_graph; v->ms_d2h = r->ms_d2h; v->ms_total = r->ms_total;
+        v->n_launches = r->n_launches; v->n_retries = r->n_retries; v->has_graph = 0;
+        v->bytes_h2d = r->bytes_h2d; v->bytes_d2h = r->bytes_d2h;
+        return 0;
+    }
     v->status = r->status.data(); v->n_nodes = r->n_nodes.data(); v->node_off = r->node_off.data();
     v->node_kmer = r->node_kmer.data(); v->node_count = r->node_count.data();
     v->path_first = r->path_first.data(); v->path_count = r->path_count.data();
@@ -1258,6 +1293,141 @@ extern "C" int64_t km_result_text(const km_result* r, const char* db_name, const
     build_text(r, db_name, names, name_off, threads);
     *text = r->text.get();
     return r->text_len;
+}
+
+// ---- pipelined batch -> text ---------------------------------------------------------------------
+// A small persistent pool of host threads (thread creation costs more than formatting a sub-batch).
+struct HostPool {
+    std::mutex m;
+    std::condition_variable cv;
+    std::deque<std::function<void()>> q;
+    std::vector<std::thread> workers;
+    bool stop = false;
+    explicit HostPool(int n) {
+        for (int i = 0; i < n; ++i)
+            workers.emplace_back([this] {
+                for (;;) {
+                    std::function<void()> job;
+                    {
+                        std::unique_lock<std::mutex> lk(m);
+                        cv.wait(lk, [this] { return stop || !q.empty(); });
+                        if (stop && q.empty()) return;
+                        job = std::move(q.front());
+                        q.pop_front();
+                    }
+                    job();
+                }
+            });
+    }
+    void submit(std::function<void()> f) { { std::lock_guard<std::mutex> g(m); q.push_back(std::move(f)); } cv.notify_one(); }
+    ~HostPool() { { std::lock_guard<std::mutex> g(m); stop = true; } cv.notify_all(); for (auto& w : workers) w.join(); }
+};
+static HostPool& host_pool() {
+    static HostPool pool((int)std::max(2u, std::min(64u, std::thread::hardware_concurrency())));
+    return pool;
+}
+struct Latch {
+    std::mutex m; std::condition_variable cv; int left;
+    explicit Latch(int n) : left(n) {}
+    void done() { std::lock_guard<std::mutex> g(m); if (--left == 0) cv.notify_all(); }
+    void wait() { std::unique_lock<std::mutex> lk(m); cv.wait(lk, [this] { return left == 0; }); }
+};
+
+// km find_mutation for a whole batch, host buffers in, text out, as ONE call: the batch is cut into
+// sub-batches that are all enqueued at once on their own streams; while the GPU works on the later
+// ones the host formats the rows of the earlier ones (pool threads), so copies, kernels and text
+// building overlap.  The text equals km_find_batch + km_result_format_all.
+extern "C" int km_find_text(km_table* t, const char* seqs, const int64_t* offsets, int32_t n, const km_find_params* params,
+                            const char* db_name, const char* names, const int64_t* name_off, int32_t n_sub, km_result** out) {
+    if (!t || !out || n < 0 || (n && (!seqs || !offsets || !names || !name_off)) || !params || !db_name)
+        return fail(KM_E_ARG, "km_find_text: bad argument");
+    CU(cudaSetDevice(t->device));
+    if (n_sub <= 0) n_sub = n >= 4096 ? 4 : n >= 1024 ? 2 : 1;
+    n_sub = std::max(1, std::min(n_sub, std::max(1, n)));
+    while ((int)t->lanes.size() < n_sub) {
+        std::unique_ptr<km_table::Lane> L(new km_table::Lane());
+        L->pin.host = true;
+        CU(cudaStreamCreateWithFlags(&L->stream, cudaStreamNonBlocking));
+        for (auto& e : L->ev) CU(cudaEventCreate(&e));
+        t->lanes.push_back(std::move(L));
+    }
+    // sub-batches balanced by sequence length (contiguous ranges)
+    std::vector<int> cut(1, 0);
+    const int64_t total = n ? offsets[n] - offsets[0] : 0;
+    for (int c = 1; c < n_sub; ++c) {
+        const int64_t want = offsets[0] + total * c / n_sub;
+        int i = (int)(std::lower_bound(offsets, offsets + n + 1, want) - offsets);
+        i = std::max(cut.back(), std::min(i, n));
+        cut.push_back(i);
+    }
+    cut.push_back(n);
+    km_result* res = new km_result();
+    res->n_targets = n; res->k = t->k; res->has_graph = false;
+    std::vector<std::unique_ptr<km_plan>> plans;
+    std::vector<std::vector<int64_t>> offs((size_t)n_sub), noffs((size_t)n_sub);
+    km_find_params prm = *params;
+    prm.flags |= KM_FIND_NO_GRAPH;
+    // enqueue everything
+    for (int c = 0; c < n_sub; ++c) {
+        const int lo = cut[(size_t)c], hi = cut[(size_t)c + 1];
+        auto& o = offs[(size_t)c]; auto& no = noffs[(size_t)c];
+        o.resize((size_t)(hi - lo) + 1); no.resize((size_t)(hi - lo) + 1);
+        for (int i = lo; i <= hi; ++i) { o[(size_t)(i - lo)] = offsets[i] - offsets[lo]; no[(size_t)(i - lo)] = name_off[i] - name_off[lo]; }
+        std::unique_ptr<km_plan> p(new km_plan());
+        if (int rc = plan_init(t, seqs + offsets[lo], o.data(), hi - lo, &prm, p.get(), false, t->lanes[(size_t)c].get())) { delete res; return rc; }
+        if (int rc = plan_launch(p.get(), p->stream)) { delete res; return rc; }
+        plans.push_back(std::move(p));
+    }
+    // collect in order; each sub-batch is formatted by the pool while the next one is awaited
+    Latch latch(n_sub);
+    int first_error = 0;
+    for (int c = 0; c < n_sub; ++c) {
+        const int lo = cut[(size_t)c];
+        std::unique_ptr<km_result> part(new km_result());
+        part->seq_off = plans[(size_t)c]->seq_off;
+        int rc = plan_fetch(plans[(size_t)c].get(), part.get(), false);
+        part->targets.swap(plans[(size_t)c]->targets);
+        km_result* pr = part.get();
+        res->parts.push_back(std::move(part));
+        if (rc) { if (!first_error) first_error = rc; latch.done(); continue; }
+        const char* nm = names + name_off[lo];
+        const int64_t* no = noffs[(size_t)c].data();
+        host_pool().submit([pr, db_name, nm, no, &latch] {
+            build_text(pr, db_name, nm, no, 4);
+            latch.done();
+        });
+    }
+    latch.wait();
+    if (first_error) { delete res; return first_error; }
+    int64_t len = 0;
+    std::vector<int64_t> at_of;
+    for (auto& part : res->parts) { at_of.push_back(len); len += part->text_len; }
+    res->text.reset(new char[(size_t)len + 1]);
+    {
+        Latch joined((int)res->parts.size());
+        char* dst = res->text.get();
+        for (size_t c = 0; c < res->parts.size(); ++c) {
+            km_result* part = res->parts[c].get();
+            const int64_t at = at_of[c];
+            host_pool().submit([part, dst, at, &joined] {
+                memcpy(dst + at, part->text.get(), (size_t)part->text_len);
+                part->text.reset();
+                joined.done();
+            });
+        }
+        joined.wait();
+    }
+    for (auto& part : res->parts) {
+        res->all_status.insert(res->all_status.end(), part->status.data(), part->status.data() + part->status.size());
+        res->ms_h2d += part->ms_h2d; res->ms_walk += part->ms_walk; res->ms_graph += part->ms_graph; res->ms_d2h += part->ms_d2h;
+        res->n_launches += part->n_launches; res->n_retries += part->n_retries;
+        res->bytes_h2d += part->bytes_h2d; res->bytes_d2h += part->bytes_d2h;
+    }
+    res->text.get()[len] = 0;
+    res->text_len = len;
+    res->fmt_key = std::string(db_name) + '\0' + (n ? std::string(names, (size_t)name_off[n]) : std::string());
+    *out = res;
+    return 0;
 }
 
 extern "C" int km_debug_format_fixed(double v, int prec, char* buf64) {

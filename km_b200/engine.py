@@ -40,6 +40,32 @@ def unpack_kmer(v, k):
     return "".join(BASES[(v >> (2 * (k - 1 - i))) & 3] for i in range(k))
 
 
+class PackedTargets:
+    """A batch of targets as the C ABI takes it: the sequences concatenated in one host buffer plus
+    offsets (and, optionally, the query names the same way).  Build it once when the same batch is
+    submitted repeatedly; `Table.find_batch` and `BatchResult.format_all` accept it in place of lists."""
+
+    def __init__(self, sequences, names=None):
+        self.sequences = list(sequences)
+        self.blob, self.off = Table._pack_targets(self.sequences)
+        self.names = list(names) if names is not None else None
+        if self.names is not None:
+            self.name_blob, self.name_off = _pack_names(self.names)
+
+    def __len__(self):
+        return len(self.sequences)
+
+
+def _pack_names(names):
+    blob = "".join(names).encode()
+    off = np.zeros(len(names) + 1, dtype=np.int64)
+    if names:
+        np.cumsum(np.fromiter(map(len, names), dtype=np.int64, count=len(names)), out=off[1:])
+        if off[-1] != len(blob):          # non-ASCII names: fall back to byte lengths
+            np.cumsum([len(x.encode()) for x in names], out=off[1:])
+    return blob, off
+
+
 class Table:
     """Device-resident k-mer count table (replaces jellyfish.QueryMerFile)."""
 
@@ -119,19 +145,40 @@ class Table:
         blob = "".join(sequences).encode("ascii")
         off = np.zeros(len(sequences) + 1, dtype=np.int64)
         if sequences:
-            np.cumsum(np.fromiter((len(s) for s in sequences), dtype=np.int64, count=len(sequences)), out=off[1:])
+            np.cumsum(np.fromiter(map(len, sequences), dtype=np.int64, count=len(sequences)), out=off[1:])
         return blob, off
 
     def find_batch(self, sequences, count=5, ratio=0.05, steps=500, branchs=10, nodes=10000, extra_nodes=0,
                    want_graph=True):
         """Run the whole find_mutation path for a list of target sequences in one call.
         want_graph=False skips copying node arrays / index paths back (rows and text only)."""
-        blob, off = self._pack_targets(sequences)
+        if isinstance(sequences, PackedTargets):
+            blob, off, seqs = sequences.blob, sequences.off, sequences.sequences
+        else:
+            seqs = list(sequences)
+            blob, off = self._pack_targets(seqs)
         prm = FindParams(float(ratio), int(count), int(steps), int(branchs), int(nodes), int(extra_nodes),
                          0 if want_graph else 1, 0)
         h = ctypes.c_void_p()
-        check(lib().km_find_batch(self._h, blob, off.ctypes.data, len(sequences), ctypes.byref(prm), ctypes.byref(h)))
-        return BatchResult.from_handle(h, list(sequences), self.k)
+        check(lib().km_find_batch(self._h, blob, off.ctypes.data, len(seqs), ctypes.byref(prm), ctypes.byref(h)))
+        return BatchResult.from_handle(h, seqs, self.k)
+
+    def find_text(self, targets, db_name, count=5, ratio=0.05, steps=500, branchs=10, nodes=10000, extra_nodes=0,
+                  n_sub=0, as_bytes=False):
+        """The text `km find_mutation` prints for a batch (rows of every target, sorted, in target
+        order) in one library call; `targets` is a PackedTargets with names.  Sub-batches are in
+        flight at once, so copies, kernels and text building overlap.  Returns (text, status array)."""
+        if not isinstance(targets, PackedTargets) or targets.names is None:
+            raise TypeError("find_text takes PackedTargets(sequences, names)")
+        prm = FindParams(float(ratio), int(count), int(steps), int(branchs), int(nodes), int(extra_nodes), 1, 0)
+        h = ctypes.c_void_p()
+        db = db_name.encode()
+        check(lib().km_find_text(self._h, targets.blob, targets.off.ctypes.data, len(targets), ctypes.byref(prm), db,
+                                 targets.name_blob, targets.name_off.ctypes.data, int(n_sub), ctypes.byref(h)))
+        out = TextResult(h, db, targets)
+        self.last_timing = out.timing
+        view = out.text_view()
+        return ((view if as_bytes else view.tobytes().decode("ascii")), out.status)
 
     def plan(self, sequences, count=5, ratio=0.05, steps=500, branchs=10, nodes=10000, extra_nodes=0):
         """Upload a batch once; launch it any number of times (FindPlan)."""
@@ -191,6 +238,41 @@ class FindPlan:
     def __del__(self):
         try:
             self.close()
+        except Exception:
+            pass
+
+
+class TextResult:
+    """Owner of a km_find_text result.  `text_view()` returns a uint8 array over the library's text buffer
+    (no copy); the array keeps this object -- and with it the buffer -- alive, and this object does not
+    refer back to the array, so the result is released as soon as the last view goes away."""
+
+    def __init__(self, handle, db, targets):
+        self._h = handle
+        v = ResultView()
+        check(lib().km_result_get(handle, ctypes.byref(v)))
+        self.status = np.array(_view(v.status, np.uint32, v.n_targets))
+        self.timing = {"h2d_ms": v.ms_h2d, "walk_ms": v.ms_walk, "graph_ms": v.ms_graph, "d2h_ms": v.ms_d2h,
+                       "launches": v.n_launches, "retries": v.n_retries, "h2d_bytes": int(v.bytes_h2d),
+                       "d2h_bytes": int(v.bytes_d2h)}
+        ptr = ctypes.c_void_p()
+        need = lib().km_result_text(handle, db, targets.name_blob, targets.name_off.ctypes.data, 0, ctypes.byref(ptr))
+        if need < 0:
+            check(int(need))
+        self._ptr, self._len = ptr.value, int(need)
+
+    def text_view(self):
+        if not self._len:
+            return np.zeros(0, dtype=np.uint8)
+        raw = (ctypes.c_char * self._len).from_address(self._ptr)
+        raw._owner = self
+        return np.frombuffer(raw, dtype=np.uint8, count=self._len)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                lib().km_result_free(self._h)
+                self._h = None
         except Exception:
             pass
 
@@ -315,12 +397,10 @@ class BatchResult:
     def format_all(self, db_name, names, threads=0, as_bytes=False):
         """Sorted TSV text of every target, in target order, formatted on host threads.
         as_bytes=True returns a uint8 numpy array (no extra copies of a multi-megabyte text)."""
-        blob = "".join(names).encode()
-        off = np.zeros(len(names) + 1, dtype=np.int64)
-        if names:
-            np.cumsum(np.fromiter((len(x) for x in names), dtype=np.int64, count=len(names)), out=off[1:])
-            if off[-1] != len(blob):          # non-ASCII names: fall back to byte lengths
-                np.cumsum([len(x.encode()) for x in names], out=off[1:])
+        if isinstance(names, PackedTargets):
+            blob, off = names.name_blob, names.name_off
+        else:
+            blob, off = _pack_names(list(names))
         ptr = ctypes.c_void_p()
         need = lib().km_result_text(self._h, db_name.encode(), blob, off.ctypes.data, int(threads), ctypes.byref(ptr))
         if need < 0:

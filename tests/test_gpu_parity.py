@@ -259,3 +259,23 @@ def test_cli_find_mutation_and_report_equal_reference_text(engine, bundled, bund
             assert rep.getvalue() == case["report"]["stdout"]
     finally:
         os.chdir(cwd)
+
+
+def test_pipelined_text_call_equals_two_step_path(engine, synth_small):
+    """km_find_text (sub-batches in flight, rows formatted while later sub-batches run) must print
+    exactly what km_find_batch + km_result_format_all print, for every split."""
+    from km_b200 import synth
+    panel = synth.make_panel(700, seed=21, two_variant_frac=0.2)
+    t = engine.Table.create(capacity=len(panel.keys) + 200000)
+    t.build_synthetic(synth.TABLE_SEED, 200000)
+    t.insert(panel.keys, panel.counts, mode="overwrite")
+    packed = engine.PackedTargets(panel.targets, panel.names)
+    res = t.find_batch(packed, want_graph=False)
+    want = res.format_all("panel.jf", packed)
+    assert want.count("\n") >= 700
+    for n_sub in (1, 2, 3, 7):
+        got, status = t.find_text(packed, "panel.jf", n_sub=n_sub)
+        assert got == want, n_sub
+        assert (status == res.status).all()
+    got, _ = t.find_text(engine.PackedTargets(panel.targets[:5], panel.names[:5]), "panel.jf")
+    assert got == t.find_batch(panel.targets[:5], want_graph=False).format_all("panel.jf", panel.names[:5])
