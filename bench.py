@@ -157,6 +157,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0, help="targets in the CPU sample (0 = 24 per core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-lookup", action="store_true")
+    ap.add_argument("--n-sub", type=int, default=0, help="sub-batches in flight in km_find_text (0 = library default)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "native":
         args.warmup = 3                       # timing rule: at least 3 warm-up steps
@@ -303,7 +304,7 @@ def main():
     def e2e_step():
         # ONE library call: H2D of the sequences, kernels, D2H of rows and spelled paths, text building;
         # sub-batches in flight so that these overlap (km_find_text)
-        return table.find_text(packed, "panel.jf", as_bytes=True)
+        return table.find_text(packed, "panel.jf", as_bytes=True, n_sub=args.n_sub)
 
     def two_step():
         t_a = time.perf_counter()

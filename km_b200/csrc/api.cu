@@ -1233,6 +1233,19 @@ extern "C" int64_t km_result_format_target(const km_result* r, int32_t tg, const
     return need;
 }
 
+// rows of targets [lo, hi) in order, appended to `out`
+static void format_range(const km_result* r, int lo, int hi, const char* db_name, const char* names, const int64_t* name_off,
+                         std::vector<char>& out) {
+    const size_t db_len = strlen(db_name);
+    std::vector<char> arena;
+    std::vector<FmtRow> rows;
+    size_t guess = 0;
+    for (int t = lo; t < hi; ++t) guess += (size_t)r->row_count[t] * (size_t)(2 * (r->seq_off[t + 1] - r->seq_off[t]) + 160 + db_len);
+    out.reserve(out.size() + guess);
+    for (int t = lo; t < hi; ++t)
+        format_rows_of(r, t, db_name, db_len, names + name_off[t], (size_t)(name_off[t + 1] - name_off[t]), arena, rows, out);
+}
+
 // Builds (once) the text of all targets in target order on host threads: every thread formats a
 // contiguous range of targets into its own buffer, the pieces are then copied side by side.
 static int build_text(const km_result* r, const char* db_name, const char* names, const int64_t* name_off, int32_t threads) {
@@ -1242,17 +1255,9 @@ static int build_text(const km_result* r, const char* db_name, const char* names
     int nt = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
     nt = std::max(1, std::min(nt, std::max(1, n / 64)));
     std::vector<std::vector<char>> piece((size_t)nt);
-    const size_t db_len = strlen(db_name);
     auto work = [&](int w) {
         const int lo = (int)((int64_t)n * w / nt), hi = (int)((int64_t)n * (w + 1) / nt);
-        std::vector<char> arena;
-        std::vector<FmtRow> rows;
-        std::vector<char>& out = piece[(size_t)w];
-        size_t guess = 0;
-        for (int t = lo; t < hi; ++t) guess += (size_t)r->row_count[t] * (size_t)(2 * (r->seq_off[t + 1] - r->seq_off[t]) + 160 + db_len);
-        out.reserve(guess);
-        for (int t = lo; t < hi; ++t)
-            format_rows_of(r, t, db_name, db_len, names + name_off[t], (size_t)(name_off[t + 1] - name_off[t]), arena, rows, out);
+        format_range(r, lo, hi, db_name, names, name_off, piece[(size_t)w]);
     };
     if (nt == 1) work(0);
     else {
@@ -1342,7 +1347,7 @@ extern "C" int km_find_text(km_table* t, const char* seqs, const int64_t* offset
     if (!t || !out || n < 0 || (n && (!seqs || !offsets || !names || !name_off)) || !params || !db_name)
         return fail(KM_E_ARG, "km_find_text: bad argument");
     CU(cudaSetDevice(t->device));
-    if (n_sub <= 0) n_sub = n >= 4096 ? 4 : n >= 1024 ? 2 : 1;
+    if (n_sub <= 0) n_sub = n >= 4096 ? 6 : n >= 1024 ? 2 : 1;
     n_sub = std::max(1, std::min(n_sub, std::max(1, n)));
     while ((int)t->lanes.size() < n_sub) {
         std::unique_ptr<km_table::Lane> L(new km_table::Lane());
@@ -1378,8 +1383,11 @@ extern "C" int km_find_text(km_table* t, const char* seqs, const int64_t* offset
         if (int rc = plan_launch(p.get(), p->stream)) { delete res; return rc; }
         plans.push_back(std::move(p));
     }
-    // collect in order; each sub-batch is formatted by the pool while the next one is awaited
-    Latch latch(n_sub);
+    // collect in order; the rows of each sub-batch are formatted in slices by the pool while the next
+    // sub-batch is awaited; the pieces are joined once at the end
+    const int n_slice = 4;
+    std::vector<std::vector<char>> piece((size_t)n_sub * n_slice);
+    Latch latch(n_sub * n_slice);
     int first_error = 0;
     for (int c = 0; c < n_sub; ++c) {
         const int lo = cut[(size_t)c];
@@ -1389,29 +1397,33 @@ extern "C" int km_find_text(km_table* t, const char* seqs, const int64_t* offset
         part->targets.swap(plans[(size_t)c]->targets);
         km_result* pr = part.get();
         res->parts.push_back(std::move(part));
-        if (rc) { if (!first_error) first_error = rc; latch.done(); continue; }
+        if (rc) { if (!first_error) first_error = rc; for (int j = 0; j < n_slice; ++j) latch.done(); continue; }
         const char* nm = names + name_off[lo];
         const int64_t* no = noffs[(size_t)c].data();
-        host_pool().submit([pr, db_name, nm, no, &latch] {
-            build_text(pr, db_name, nm, no, 4);
-            latch.done();
-        });
+        const int m = pr->n_targets;
+        for (int j = 0; j < n_slice; ++j) {
+            std::vector<char>* dst = &piece[(size_t)c * n_slice + (size_t)j];
+            const int a = (int)((int64_t)m * j / n_slice), b = (int)((int64_t)m * (j + 1) / n_slice);
+            host_pool().submit([pr, db_name, nm, no, a, b, dst, &latch] {
+                format_range(pr, a, b, db_name, nm, no, *dst);
+                latch.done();
+            });
+        }
     }
     latch.wait();
     if (first_error) { delete res; return first_error; }
     int64_t len = 0;
     std::vector<int64_t> at_of;
-    for (auto& part : res->parts) { at_of.push_back(len); len += part->text_len; }
+    for (auto& pc : piece) { at_of.push_back(len); len += (int64_t)pc.size(); }
     res->text.reset(new char[(size_t)len + 1]);
     {
-        Latch joined((int)res->parts.size());
+        Latch joined((int)piece.size());
         char* dst = res->text.get();
-        for (size_t c = 0; c < res->parts.size(); ++c) {
-            km_result* part = res->parts[c].get();
+        for (size_t c = 0; c < piece.size(); ++c) {
+            std::vector<char>* pc = &piece[c];
             const int64_t at = at_of[c];
-            host_pool().submit([part, dst, at, &joined] {
-                memcpy(dst + at, part->text.get(), (size_t)part->text_len);
-                part->text.reset();
+            host_pool().submit([pc, dst, at, &joined] {
+                if (!pc->empty()) memcpy(dst + at, pc->data(), pc->size());
                 joined.done();
             });
         }
