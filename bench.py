@@ -417,7 +417,7 @@ def main():
                     "ms_per_step": e2e_ms, "device_ms": e2e_breakdown,
                     "what": "km_find_text(host buffers: sequences + offsets, names) -> the TSV text km find_mutation prints; "
                             "device_ms = the same work as two calls (km_find_batch, km_result_text), not pipelined"},
-            "gpu_launches": 5 * args.steps,
+            "gpu_launches": 7 * args.steps,
             "kernels": {"km_ref_probe_kernel_ms": probe_ms, "km_walk_kernels_ms": walk_ms, "km_graph_kernels_ms": graph_ms,
                         "what": "reference probe (HBM-bound: ~87% of the panel's lookups), shared-memory + general walk "
                                 "(latency-bound tails), graph/paths/quantification (shared memory, latency-bound)"},

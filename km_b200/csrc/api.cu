@@ -207,8 +207,10 @@ extern "C" int km_table_create(int device, int k, int canonical, uint64_t capaci
     CU(cudaMalloc((void**)&t->d_counter, 16));
     t->pin.host = true;
     t->pin_find.host = true;
-    CU(cudaFuncSetAttribute(km_graph_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)small_layout().stride));
+    CU(cudaFuncSetAttribute(km_graph_kernel<KM_TINY_NODES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)class_layout(KM_TINY_NODES).stride));
+    CU(cudaFuncSetAttribute(km_graph_kernel<KM_SMALL_NODES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)class_layout(KM_SMALL_NODES).stride));
     km_table_clear_kernel<<<t->sm_count * 8, 256, 0, t->stream>>>(t->buckets, t->n_buckets);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(t->stream));
@@ -676,7 +678,7 @@ struct km_plan {
     std::vector<int32_t> extra;
     int64_t pool_cap = 0, seq_cap = 0, n_node = 0, n_hash = 0, n_code = 0;
     int32_t path_cap = 0, row_cap = 0, extra_max = 0;
-    int grid_graph = 1, grid_large = 1;
+    int grid_tiny = 1, grid_graph = 1, grid_large = 1;
     Arena own_dev, own_pin;
     Arena* dev = nullptr;
     Arena* pin = nullptr;
@@ -719,7 +721,8 @@ static int plan_layout(km_plan* p) {
     }
     const size_t n_chunks = p->chunk_target.size();
     const int64_t n_node = p->n_node = p->node_off[n], n_hash = p->n_hash = p->hash_off[n], n_code = p->n_code = p->seq_off[n];
-    p->grid_graph = std::max(1, std::min(n, t->sm_count * 8));
+    p->grid_tiny = std::max(1, std::min(n, t->sm_count * 10));
+    p->grid_graph = std::max(1, std::min(n, t->sm_count * 5));
     p->grid_large = std::max(1, std::min(n, t->sm_count * 2));
     const ScratchLayout L0 = make_layout(maxcap, KM_MAX_PATHS, KM_MAX_PATHS, KM_MAX_COLS, 0);
     const int32_t path_cap = p->path_cap, row_cap = p->row_cap;
@@ -735,7 +738,7 @@ static int plan_layout(km_plan* p) {
     for (int i = 0; i < 5; ++i) acc(4 * n);                                        // per-target result ints
     acc(8 * n_node); acc(4 * n_node);                                              // canonical nodes
     acc(8 * (size_t)path_cap); acc(4 * (size_t)path_cap); acc(8 * (size_t)path_cap); acc(4 * (size_t)pool_cap);
-    acc(sizeof(Row) * (size_t)row_cap); acc((size_t)seq_cap); acc(64);
+    acc(sizeof(Row) * (size_t)row_cap); acc((size_t)seq_cap); acc(64); acc(12 * (size_t)n + 64);
     acc(L0.stride * (size_t)p->grid_large);
     if (int rc = p->dev->reserve(need + 8192)) return rc;
     p->dev->reset();
@@ -765,7 +768,8 @@ static int plan_layout(km_plan* p) {
     R.rows = A.take<Row>(row_cap); R.row_cap = row_cap;
     p->d_seq_pool = A.take<char>(seq_cap);
     R.seq_pool = p->d_seq_pool; R.path_seq_off = p->d_path_seq_off; R.seq_cap = seq_cap;
-    R.used = A.take<unsigned long long>(4);
+    R.sched_order = A.take<int32_t>(3 * (size_t)n); R.sched_count = A.take<int32_t>(4);
+    R.used = A.take<unsigned long long>(8);     // [0..3] pool cursors, [4..6] work counters of the three graph passes
     p->SL = L0;
     p->SL.base = A.take<char>(L0.stride * (size_t)p->grid_large);
     p->P.ratio = p->prm.ratio; p->P.count = p->prm.count; p->P.max_stack = p->prm.steps;
@@ -816,7 +820,7 @@ static int plan_launch(km_plan* p, cudaStream_t s) {
     if (p->n == 0) return 0;
     CU(cudaEventRecord(p->ev[1], s));
     CU(cudaMemsetAsync(p->state0, 0, p->state_bytes, s));
-    CU(cudaMemsetAsync(p->R.used, 0, 32, s));
+    CU(cudaMemsetAsync(p->R.used, 0, 64, s));
     if (p->W.n_chunks) {
         km_ref_probe_kernel<<<(p->W.n_chunks + KM_PROBE_WARPS - 1) / KM_PROBE_WARPS, 32 * KM_PROBE_WARPS, 0, s>>>(t->view(), p->W, p->P);
         CU(cudaGetLastError());
@@ -828,13 +832,16 @@ static int plan_launch(km_plan* p, cudaStream_t s) {
     CU(cudaGetLastError());
     CU(cudaEventRecord(p->ev[2], s));
     // shared-memory pass first, then the general pass for large or deferred targets
-    const size_t small_smem = small_layout().stride;
-    km_graph_kernel<true><<<p->grid_graph, KM_CTA, small_smem, s>>>(t->view(), p->W, p->SL, p->R);
+    km_schedule_kernel<<<1, 1024, 0, s>>>(p->W, p->R);
     CU(cudaGetLastError());
-    km_graph_kernel<false><<<p->grid_large, KM_CTA, 0, s>>>(t->view(), p->W, p->SL, p->R);
+    km_graph_kernel<KM_TINY_NODES><<<p->grid_tiny, KM_CTA, class_layout(KM_TINY_NODES).stride, s>>>(t->view(), p->W, p->SL, p->R);
+    CU(cudaGetLastError());
+    km_graph_kernel<KM_SMALL_NODES><<<p->grid_graph, KM_CTA, class_layout(KM_SMALL_NODES).stride, s>>>(t->view(), p->W, p->SL, p->R);
+    CU(cudaGetLastError());
+    km_graph_kernel<0><<<p->grid_large, KM_CTA, 0, s>>>(t->view(), p->W, p->SL, p->R);
     CU(cudaGetLastError());
     CU(cudaEventRecord(p->ev[3], s));
-    p->n_launches += 5;
+    p->n_launches += 7;
     p->launched = true;
     return 0;
 }

@@ -55,8 +55,12 @@ struct PhaseTimer {
 
 #if KM_DEVICE_BUILD
 // One CTA works on one target.
+// `rot` rotates the warp numbering: the serial stretches of a target run on "warp 0, lane 0", and
+// with 4-warp CTAs warp w of every CTA lands on scheduler w of the SM -- rotating by the target
+// number spreads those stretches over the four schedulers instead of queueing them all on one.
 struct CtaCtx {
-    KM_HD int tid() const { return threadIdx.x; }
+    int rot = 0;
+    KM_HD int tid() const { return (int)((threadIdx.x + 32u * (unsigned)rot) & (blockDim.x - 1u)); }   // blockDim is a power of two
     KM_HD int nt() const { return blockDim.x; }
     KM_HD void sync() const { __syncthreads(); }
     KM_HD int sync_or(int p) const { return __syncthreads_or(p); }
@@ -90,7 +94,7 @@ KM_HD void fence_block() { __threadfence_block(); }
 KM_HD uint32_t load_shared_volatile32(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
 KM_HD uint8_t load_shared_volatile8(const uint8_t* p) { return *reinterpret_cast<const volatile uint8_t*>(p); }
 KM_HD uint32_t atomic_cas32(uint32_t* p, uint32_t cmp, uint32_t val) { return atomicCAS(p, cmp, val); }
-KM_HD int warp_index(const CtaCtx&) { return threadIdx.x >> 5; }
+KM_HD int warp_index(const CtaCtx& c) { return c.tid() >> 5; }
 KM_HD int warp_count(const CtaCtx&) { return blockDim.x >> 5; }
 KM_HD uint64_t atomic_cas64(uint64_t* p, uint64_t cmp, uint64_t val) {
     return atomicCAS(reinterpret_cast<unsigned long long*>(p), (unsigned long long)cmp, (unsigned long long)val);

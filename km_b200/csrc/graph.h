@@ -74,8 +74,13 @@ struct ResultView {
     char* seq_pool;
     int64_t* path_seq_off;   // [path_cap] offset of each path's string, -1 = did not fit
     int64_t seq_cap;
-    // [0] paths used, [1] pool ints used, [2] rows used, [3] sequence chars used
+    // [0] paths used, [1] pool ints used, [2] rows used, [3] sequence chars used, [4..6] work cursors of
+    // the three graph passes
     unsigned long long* used;
+    // work lists of the three graph passes (km_schedule_kernel): targets of each class, largest graphs
+    // first; sched_count[c] entries in sched_order[c * n_targets ...]
+    int32_t* sched_order;
+    int32_t* sched_count;
 };
 
 // Per-target working set of the CTA: shared memory in the small pass, per-CTA HBM scratch
@@ -187,6 +192,12 @@ KM_HOSTDEV GraphScratch carve(const ScratchLayout& L, char* p, int retry) {
     S.cols = (PathView*)(p + L.o_cols); S.members = (int32_t*)(p + L.o_members);
     S.maxN = L.maxN; S.hcap = L.hcap; S.max_cand = L.max_cand; S.max_paths = L.max_paths; S.max_cols = L.max_cols; S.retry = retry;
     return S;
+}
+
+// hand target t to the general pass (its list is read after the shared-memory passes have finished)
+KM_HD void defer_to_general(const ResultView& R, const WalkView& W, int t) {
+    const int pos = atomic_addi32(&R.sched_count[2], 1);
+    R.sched_order[2 * (size_t)W.n_targets + pos] = t;
 }
 
 #define KM_REF_W 0.01f
@@ -619,6 +630,7 @@ KM_HD bool graph_target(const Ctx& ctx, const TableView& T, const WalkView& W, c
     if (n_cand > S.max_cand || n_cand > S.max_paths) {
         if (tid == 0) {
             atomic_or32(&W.status[t], S.retry ? KM_ST_RETRY_LARGE : (uint32_t)KM_ST_TOO_MANY_COLS);
+            if (S.retry) defer_to_general(R, W, t);
             R.t_n_paths[t] = 0; R.t_path_first[t] = 0; R.t_n_rows[t] = 0; R.t_row_first[t] = 0;
         }
         ctx.sync();

@@ -200,46 +200,88 @@ __global__ void __launch_bounds__(32 * KM_WALK_WARPS) km_walk_kernel(TableView T
 }
 
 // ---- K4 + K5: graph, paths, FP64 quantification; persistent CTAs over targets -----------------
-// Two passes share one body.  The SHARED-MEMORY pass keeps the whole per-target working set
-// (adjacency, both shortest-path trees, candidate edges, solver matrices: ~50 KB) on chip and takes
-// every target whose graph has at most KM_SMALL_NODES nodes; the GENERAL pass uses per-CTA scratch
-// in HBM and takes the rest, plus any target the first pass deferred (KM_ST_RETRY_LARGE).
-#define KM_SMALL_NODES 512
+// Three passes share one body.  The two SHARED-MEMORY passes keep the whole per-target working set
+// (adjacency, both shortest-path trees, candidate edges, solver matrices) on chip; a target goes to the
+// smallest class its graph fits, so the many small graphs run with twice the CTAs per SM of the
+// larger ones (the pass is latency-bound: resident CTAs are throughput).  The GENERAL pass uses
+// per-CTA scratch in HBM and takes the rest, plus any target a shared-memory pass deferred
+// (KM_ST_RETRY_LARGE).
+#define KM_SMALL_NODES 512      // largest shared-memory class (graph nodes incl. the two caps)
+#define KM_TINY_NODES 256
 #define KM_SMALL_CAND 64
 #define KM_SMALL_PATHS 64
 #define KM_SMALL_COLS 8
 
-__host__ __device__ inline ScratchLayout small_layout() {
-    return make_layout(KM_SMALL_NODES - 2, KM_SMALL_CAND, KM_SMALL_PATHS, KM_SMALL_COLS, 1);
+__host__ __device__ inline ScratchLayout class_layout(int nodes) {
+    return make_layout(nodes - 2, KM_SMALL_CAND, KM_SMALL_PATHS, KM_SMALL_COLS, 1);
 }
 
 #define KM_ST_FATAL (KM_ST_BAD_BASE | KM_ST_DUP_KMER | KM_ST_NODE_OVERFLOW | KM_ST_NODE_LIMIT | KM_ST_TOO_SHORT)
 
-template <bool SMALL>
+// NODES = node capacity of a shared-memory class, 0 = the general pass
+// Work lists of the three graph passes: every target whose walk succeeded goes to the smallest class
+// its graph fits, each list ordered by descending node count (64 size bins; a counting sort in one CTA).
+__global__ void __launch_bounds__(1024) km_schedule_kernel(WalkView W, ResultView R) {
+    __shared__ int hist[3][64], start[3][64];
+    const int n = W.n_targets;
+    for (int i = threadIdx.x; i < 3 * 64; i += blockDim.x) (&hist[0][0])[i] = 0;
+    __syncthreads();
+    auto classify = [&](int t, int* bin) -> int {
+        if (W.status[t] & KM_ST_FATAL) return -1;
+        const int cap = (int)(W.node_off[t + 1] - W.node_off[t]);
+        const int n_all = W.n_nodes[t] < cap ? W.n_nodes[t] : cap;
+        const int kept2 = W.n_kept[t] + 2;
+        const int b = 63 - (kept2 >> 3);
+        *bin = b < 0 ? 0 : b;                                         // bin 0 = the largest graphs
+        if (n_all <= KM_TINY_NODES - 2 && kept2 <= KM_TINY_NODES) return 0;
+        if (n_all <= KM_SMALL_NODES - 2 && kept2 <= KM_SMALL_NODES) return 1;
+        return 2;
+    };
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+        int b;
+        const int c = classify(t, &b);
+        if (c < 0) { R.t_n[t] = 0; R.t_n_paths[t] = 0; R.t_path_first[t] = 0; R.t_n_rows[t] = 0; R.t_row_first[t] = 0; }
+        else atomicAdd(&hist[c][b], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        int at = 0;
+        for (int b = 0; b < 64; ++b) { start[threadIdx.x][b] = at; at += hist[threadIdx.x][b]; }
+        R.sched_count[threadIdx.x] = at;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+        int b;
+        const int c = classify(t, &b);
+        if (c >= 0) R.sched_order[(size_t)c * n + atomicAdd(&start[c][b], 1)] = t;
+    }
+}
+
+template <int NODES>
 __global__ void __launch_bounds__(KM_CTA) km_graph_kernel(TableView T, WalkView W, ScratchLayout SL, ResultView R) {
     extern __shared__ __align__(16) char km_smem[];
     __shared__ int sh[32];
     CtaCtx ctx;
-    const GraphScratch S = SMALL ? carve(small_layout(), km_smem, 1)
+    const GraphScratch S = NODES ? carve(class_layout(NODES ? NODES : 4), km_smem, 1)
                                  : carve(SL, SL.base + (size_t)blockIdx.x * SL.stride, 0);
-    for (int t = blockIdx.x; t < W.n_targets; t += gridDim.x) {
-        const uint32_t st = W.status[t];
-        if (st & KM_ST_FATAL) {
-            if (SMALL && threadIdx.x == 0) {
-                R.t_n[t] = 0; R.t_n_paths[t] = 0; R.t_path_first[t] = 0; R.t_n_rows[t] = 0; R.t_row_first[t] = 0;
-            }
-            continue;
+    // Targets come from this pass's work list (km_schedule_kernel: largest graphs first), handed out one
+    // at a time from a global cursor: their cost varies several-fold (a tandem duplication has six times
+    // the novel nodes of a substitution), a fixed deal leaves most CTAs idle behind the unluckiest one.
+    const int cls = NODES == KM_TINY_NODES ? 0 : NODES == KM_SMALL_NODES ? 1 : 2;
+    unsigned long long* next = R.used + 4 + cls;
+    const int32_t* order = R.sched_order + (size_t)cls * W.n_targets;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int i = (int)atomicAdd(next, 1ull);
+            sh[12] = i < R.sched_count[cls] ? order[i] : -1;
         }
-        const int cap = (int)(W.node_off[t + 1] - W.node_off[t]);
-        const int n_all = W.n_nodes[t] < cap ? W.n_nodes[t] : cap;
-        const bool fits = n_all <= KM_SMALL_NODES - 2 && W.n_kept[t] + 2 <= KM_SMALL_NODES;
-        if (SMALL) { if (!fits) continue; }
-        else {
-            if (fits && !(st & KM_ST_RETRY_LARGE)) continue;
-            __syncthreads();
-            if (threadIdx.x == 0 && (st & KM_ST_RETRY_LARGE)) atomicAnd(&W.status[t], ~KM_ST_RETRY_LARGE);
-        }
+        __syncthreads();
+        const int t = sh[12];
+        if (t < 0) break;
+        if (NODES == 0 && threadIdx.x == 0) atomicAnd(&W.status[t], ~KM_ST_RETRY_LARGE);
         GraphDims d;
+        ctx.rot = t & 3;
         if (!graph_target(ctx, T, W, S, R, t, &d, sh)) continue;
         emit_rows(ctx, T, W, S, R, t, d, sh[2], sh[3], sh[6], sh);
         __syncthreads();

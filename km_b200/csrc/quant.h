@@ -520,7 +520,10 @@ KM_HD void emit_rows(const Ctx& ctx, const TableView& T, const WalkView& W, cons
         const int size = crec[4 * c + 2];
         if (size == 1) continue;
         if (size + 1 > S.max_cols) {
-            if (tid == 0) atomic_or32(&W.status[t], S.retry ? KM_ST_RETRY_LARGE : (uint32_t)KM_ST_TOO_MANY_COLS);
+            if (tid == 0) {
+                const uint32_t before = atomic_or32(&W.status[t], S.retry ? KM_ST_RETRY_LARGE : (uint32_t)KM_ST_TOO_MANY_COLS);
+                if (S.retry && !(before & KM_ST_RETRY_LARGE)) defer_to_general(R, W, t);
+            }
             continue;          // rows stay unset; the general pass redoes the target, or the host refuses it
         }
         if (tid == 0) cluster_columns(S, R, d, n_paths, first_path, c, crec, cols, members);

@@ -113,6 +113,8 @@ int emu_find_target(void* h, const uint8_t* codes, int len, double ratio, int64_
     R.path_off = path_off.data(); R.path_len = out_path_len; R.pool = out_pool; R.path_cap = path_cap; R.pool_cap = pool_cap;
     R.rows = out_rows; R.row_cap = row_cap; R.used = used;
     R.seq_pool = nullptr; R.path_seq_off = nullptr; R.seq_cap = 0;
+    int32_t sched_order[3] = {0, 0, 0}, sched_count[4] = {0, 0, 0, 0};
+    R.sched_order = sched_order; R.sched_count = sched_count;
 
     // the two passes of km_graph_kernel: small capacities with deferral, then the general ones
     auto run_pass = [&](int maxcap, int max_cand, int max_paths, int max_cols, int retry) -> bool {

@@ -1,4 +1,5 @@
-"""Attribute ncu warp-stall samples to source lines without the GUI.
+"""Attribute ncu warp-stall samples to source lines without the GUI (NCU_COLUMN="Instructions Executed"
+ranks lines by executed warp-instructions instead).
 
     python tools/ncu_lines.py report.ncu-rep km_b200/libkm_b200.so <kernel substring> [top N]
 
@@ -59,7 +60,7 @@ def main():
             a = int(r[0], 16)
             if base is None:
                 base = a
-            s = int(r[hdr.index("# Samples")] or 0)
+            s = int(float(r[hdr.index(os.environ.get("NCU_COLUMN", "# Samples"))] or 0))
             total += s
             key = line_of.get(a - base, (("?", 0), r[1]))[0]
             per_line[key] = per_line.get(key, 0) + s
