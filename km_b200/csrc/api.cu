@@ -144,13 +144,13 @@ struct km_table {
     uint64_t n_buckets = 0, n_keys = 0;
     Bucket* buckets = nullptr;
     unsigned long long* d_counter = nullptr;   // [0] new keys, then a u32 "full" flag at +8
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev[8] = {};
+    cudaStream_t stream = nullptr, side = nullptr;   // side: the second shared-memory graph pass runs beside the first
+    cudaEvent_t ev[8] = {}, fork = nullptr, join = nullptr;
     Arena dev, pin;            // lookups / inserts
     Arena dev_find, pin_find;  // km_find_batch workspace, reused across calls
     // km_find_text runs a batch as several sub-batches in flight at once: each has its own workspace,
     // stream and events, kept across calls
-    struct Lane { Arena dev, pin; cudaStream_t stream = nullptr; cudaEvent_t ev[8] = {}; };
+    struct Lane { Arena dev, pin; cudaStream_t stream = nullptr, side = nullptr; cudaEvent_t ev[8] = {}, fork = nullptr, join = nullptr; };
     std::vector<std::unique_ptr<Lane>> lanes;
     std::shared_ptr<PinPool> pool = std::make_shared<PinPool>();   // result buffers (outlive the table if a result does)
     int sm_count = 148;
@@ -203,7 +203,10 @@ extern "C" int km_table_create(int device, int k, int canonical, uint64_t capaci
                     cudaGetErrorString(e));
     }
     CU(cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&t->side, cudaStreamNonBlocking));
     for (auto& ev : t->ev) CU(cudaEventCreate(&ev));
+    CU(cudaEventCreateWithFlags(&t->fork, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&t->join, cudaEventDisableTiming));
     CU(cudaMalloc((void**)&t->d_counter, 16));
     t->pin.host = true;
     t->pin_find.host = true;
@@ -387,9 +390,15 @@ extern "C" void km_table_close(km_table* t) {
         L->dev.release(); L->pin.release();
         for (auto& e : L->ev) if (e) cudaEventDestroy(e);
         if (L->stream) cudaStreamDestroy(L->stream);
+        if (L->side) cudaStreamDestroy(L->side);
+        if (L->fork) cudaEventDestroy(L->fork);
+        if (L->join) cudaEventDestroy(L->join);
     }
     for (auto& ev : t->ev) if (ev) cudaEventDestroy(ev);
     if (t->stream) cudaStreamDestroy(t->stream);
+    if (t->side) cudaStreamDestroy(t->side);
+    if (t->fork) cudaEventDestroy(t->fork);
+    if (t->join) cudaEventDestroy(t->join);
     delete t;
 }
 
@@ -693,8 +702,9 @@ struct km_plan {
     int n_launches = 0, n_retries = 0;
     bool launched = false;
     unsigned long long bytes_h2d = 0;
-    cudaStream_t stream = nullptr;      // the table's own unless the plan runs on a lane
+    cudaStream_t stream = nullptr, side = nullptr;      // the table's own unless the plan runs on a lane
     cudaEvent_t* ev = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
 };
 
 static int plan_layout(km_plan* p) {
@@ -834,10 +844,15 @@ static int plan_launch(km_plan* p, cudaStream_t s) {
     // shared-memory pass first, then the general pass for large or deferred targets
     km_schedule_kernel<<<1, 1024, 0, s>>>(p->W, p->R);
     CU(cudaGetLastError());
+    // the two shared-memory passes side by side (their CTAs co-reside; each pass's tail fills with the other)
+    CU(cudaEventRecord(p->fork, s));
+    CU(cudaStreamWaitEvent(p->side, p->fork, 0));
+    km_graph_kernel<KM_SMALL_NODES><<<p->grid_graph, KM_CTA, class_layout(KM_SMALL_NODES).stride, p->side>>>(t->view(), p->W, p->SL, p->R);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(p->join, p->side));
     km_graph_kernel<KM_TINY_NODES><<<p->grid_tiny, KM_CTA, class_layout(KM_TINY_NODES).stride, s>>>(t->view(), p->W, p->SL, p->R);
     CU(cudaGetLastError());
-    km_graph_kernel<KM_SMALL_NODES><<<p->grid_graph, KM_CTA, class_layout(KM_SMALL_NODES).stride, s>>>(t->view(), p->W, p->SL, p->R);
-    CU(cudaGetLastError());
+    CU(cudaStreamWaitEvent(s, p->join, 0));
     km_graph_kernel<0><<<p->grid_large, KM_CTA, 0, s>>>(t->view(), p->W, p->SL, p->R);
     CU(cudaGetLastError());
     CU(cudaEventRecord(p->ev[3], s));
@@ -920,7 +935,10 @@ static int plan_init(km_table* t, const char* seqs, const int64_t* offsets, int3
                      bool borrow_arena, km_table::Lane* lane = nullptr) {
     p->t = t; p->n = n; p->prm = *params;
     p->stream = lane ? lane->stream : t->stream;
+    p->side = lane ? lane->side : t->side;
     p->ev = lane ? lane->ev : t->ev;
+    p->fork = lane ? lane->fork : t->fork;
+    p->join = lane ? lane->join : t->join;
     if (p->prm.steps > 60000 || p->prm.branchs > 250) return fail(KM_E_ARG, "steps must be <= 60000 and branchs <= 250");
     const int64_t total = n ? offsets[n] : 0;
     p->targets.assign(seqs ? seqs : "", (size_t)total);
@@ -1360,7 +1378,10 @@ extern "C" int km_find_text(km_table* t, const char* seqs, const int64_t* offset
         std::unique_ptr<km_table::Lane> L(new km_table::Lane());
         L->pin.host = true;
         CU(cudaStreamCreateWithFlags(&L->stream, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&L->side, cudaStreamNonBlocking));
         for (auto& e : L->ev) CU(cudaEventCreate(&e));
+        CU(cudaEventCreateWithFlags(&L->fork, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&L->join, cudaEventDisableTiming));
         t->lanes.push_back(std::move(L));
     }
     // sub-batches balanced by sequence length (contiguous ranges)
