@@ -279,3 +279,115 @@ def test_pipelined_text_call_equals_two_step_path(engine, synth_small):
         assert (status == res.status).all()
     got, _ = t.find_text(engine.PackedTargets(panel.targets[:5], panel.names[:5]), "panel.jf")
     assert got == t.find_batch(panel.targets[:5], want_graph=False).format_all("panel.jf", panel.names[:5])
+
+
+def test_long_targets_take_the_general_kernels(engine):
+    """Targets beyond the shared-memory capacities (more than 448 reference k-mers for the walk, more than
+    510 graph nodes for the graph pass) go through the general walk / graph kernels: same answers."""
+    from km_b200 import synth
+    panel = synth.make_panel(60, seed=31, len_lo=430, len_hi=900, two_variant_frac=0.3)
+    t = engine.Table.create(capacity=len(panel.keys) + 500000)
+    t.build_synthetic(synth.TABLE_SEED, 500000)
+    t.insert(panel.keys, panel.counts, mode="overwrite")
+    res = t.find_batch(panel.targets)
+    assert (np.array([len(s) for s in panel.targets]) - 30 > 448).sum() >= 20       # the general walk is exercised
+    assert (res.n_nodes > 512).sum() >= 10                                           # and the general graph pass
+    store = KmerStore(31, True, len(panel.keys))
+    store.set_background(synth.TABLE_SEED, 500000)
+    store.insert(panel.keys, panel.counts)
+    jf = ko.OracleJellyfish(store, "panel.jf", 0.05, 5)
+    flips = 0
+    for i in range(0, 60, 2):
+        f = ko.OracleFinder(ko.Target(panel.targets[i], panel.names[i], 31), jf).run()
+        want = f.get_paths()
+        got = record_of(res, i, "panel.jf", panel.names[i])
+        errs, fl = compare_rows([str(r) for r in want], got["rows"],
+                                [[float(r.rvaf), float(r.expr), float(r.ref_expr)] for r in want], got["raw"])
+        assert not errs, (panel.names[i], errs)
+        assert got["nodes"] == sorted([k, int(v)] for k, v in f.node_data.items())
+        flips += fl
+    assert flips <= 4
+
+
+def test_full_size_panel_properties(engine):
+    """BASELINE.json config 4 at full size (10,000 targets x 2e9-key table, if the GPU has the memory):
+    properties that need no oracle -- the planted variant of every target is reported with its type, the
+    text does not depend on the order or the grouping of the targets, lookups match the SURVEY formula."""
+    import torch
+    from km_b200 import synth
+    free, _ = torch.cuda.mem_get_info(0)
+    n_bg = 2_000_000_000 if free > (90 << 30) else 50_000_000
+    n_t = 10000
+    panel = synth.make_panel(n_t, seed=synth.PANEL_SEED)
+    t = engine.Table.create(capacity=n_bg + len(panel.keys))
+    t.build_synthetic(synth.TABLE_SEED, n_bg)
+    t.insert(panel.keys, panel.counts, mode="overwrite")
+    packed = engine.PackedTargets(panel.targets, panel.names)
+    text, status = t.find_text(packed, "panel.jf")
+    assert (status & ~np.uint32(16) == 0).all()
+    blocks = {}
+    for ln in text.split("\n"):
+        if ln:
+            blocks.setdefault(ln.split("\t")[1], []).append(ln)
+    assert len(blocks) == n_t
+    want_type = {"snv": "Substitution", "ins": ("Insertion", "ITD"), "del": "Deletion", "dup": ("ITD", "Insertion"), "none": "Reference"}
+    missing = 0
+    for name, truth in zip(panel.names, panel.truth):
+        types = {ln.split("\t")[2] for ln in blocks[name]}
+        w = want_type[truth["kind"]]
+        if not (types & set([w] if isinstance(w, str) else w)):
+            missing += 1
+        assert "Reference" in types                          # every target prints its reference row
+    assert missing <= n_t // 200, missing                    # a stray background hit can hide a variant; almost never
+    # order / grouping invariance: a shuffled batch cut differently prints the same block per target
+    rng = np.random.default_rng(0)
+    perm = rng.permutation(n_t)[:3000]
+    sub = engine.PackedTargets([panel.targets[i] for i in perm], [panel.names[i] for i in perm])
+    text2, _ = t.find_text(sub, "panel.jf", n_sub=5)
+    blocks2 = {}
+    for ln in text2.split("\n"):
+        if ln:
+            blocks2.setdefault(ln.split("\t")[1], []).append(ln)
+    assert all(blocks2[panel.names[i]] == blocks[panel.names[i]] for i in perm)
+    # lookups: the walk issues the algorithmic count minus the reused reference successors, plus dead-end tips
+    res = t.find_batch(engine.PackedTargets(panel.targets[:2000]), want_graph=False)
+    n_ref = np.array([len(s) - 30 for s in panel.targets[:2000]])
+    algorithmic = n_ref + 4 * (res.n_nodes.astype(np.int64) - 2)
+    assert (res.lookups.astype(np.int64) >= algorithmic - (n_ref - 1)).all()
+    assert (res.lookups.astype(np.int64) <= algorithmic + 4 * 64).all()
+
+
+def test_table_counted_from_reads_equals_host_count(engine):
+    """config 5's table build (C19: jellyfish count -C ... -L 2): canonical 31-mers of synthetic reads counted
+    on the device, count < 2 dropped, against a host count of the same reads."""
+    from collections import Counter
+    rng = np.random.default_rng(12)
+    genome = "".join("ACGT"[i] for i in rng.integers(0, 4, size=5000))
+    reads = []
+    for _ in range(3000):
+        s = int(rng.integers(0, 5000 - 100))
+        r = genome[s:s + 100]
+        if rng.random() < 0.5:
+            r = r.translate(str.maketrans("ACGT", "TGCA"))[::-1]
+        if rng.random() < 0.05:
+            p = int(rng.integers(0, 100))
+            r = r[:p] + "N" + r[p + 1:]
+        reads.append(r)
+    host = Counter()
+    for r in reads:
+        for i in range(len(r) - 30):
+            km = r[i:i + 31]
+            if "N" in km:
+                continue
+            v = jf_format.pack(km)
+            host[min(v, jf_format.revcomp_packed(v, 31))] += 1
+    t = engine.Table.create(capacity=4 * len(host) + 1024)
+    t.count_reads(reads)
+    assert t.info()["n_keys"] == len(host)
+    left = t.drop_below(2)
+    kept = {k: c for k, c in host.items() if c >= 2}
+    assert left == len(kept)
+    keys = np.array(list(host.keys()), dtype=np.uint64)
+    got = t.query_packed(keys)
+    want = np.array([host[int(k)] if host[int(k)] >= 2 else 0 for k in keys], dtype=np.uint32)
+    assert (got == want).all()
