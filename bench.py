@@ -154,7 +154,7 @@ def main():
     ap.add_argument("--targets", type=int, default=10000)
     ap.add_argument("--table-keys", type=int, default=2_000_000_000)
     ap.add_argument("--lookup-queries", type=int, default=1 << 30)
-    ap.add_argument("--cpu-sample", type=int, default=0, help="targets in the CPU sample (0 = 24 per core)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="targets in the CPU sample (0 = 640 per core, at most the panel: ~5-10 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-lookup", action="store_true")
     ap.add_argument("--n-sub", type=int, default=0, help="sub-batches in flight in km_find_text (0 = library default)")
@@ -178,7 +178,7 @@ def main():
         store.build()
         panel = synth.make_panel(args.targets, seed=synth.PANEL_SEED)
         cores = os.cpu_count() or 1
-        n_sample = args.cpu_sample or 24 * cores
+        n_sample = args.cpu_sample or 640 * cores
         v, used, sample, lps, ms = cpu_arm(panel, synth.TABLE_SEED, args.table_keys, n_sample, max(1, args.steps),
                                            min(args.warmup, 1), cores)
         print(json.dumps({
@@ -386,7 +386,7 @@ def main():
         parity = {"targets_checked": checked, "mismatching": bad, "printed_digit_flips": flips}
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            v, used, sample, lps, _ = cpu_arm(panel, synth.TABLE_SEED, table_keys, args.cpu_sample or 24 * cores, 1, 1, cores)
+            v, used, sample, lps, _ = cpu_arm(panel, synth.TABLE_SEED, table_keys, args.cpu_sample or 640 * cores, 1, 1, cores)
             cpu = {"value": v, "unit": UNIT, "cores": used, "kind": "port", "sample": sample,
                    "issued_lookups_per_s": lps}
 
