@@ -70,6 +70,14 @@ def _worker(rank, world, port, out_dir):
     a = shard.find_batch(seqs, want_graph=False).format_all("panel.jf", names)
     b = whole.find_batch(seqs, want_graph=False).format_all("panel.jf", names)
     assert a == b and a.count("\n") >= len(seqs)
+    # default regime through the same ranks: targets dealt to the ranks, replicated table, rows gathered in order
+    texts = cohort.find_mutation_sharded(whole, panel.targets, panel.names, "panel.jf", dist)
+    if rank == 0:
+        one = whole.find_batch(panel.targets, want_graph=False)
+        assert texts == [one.format_target(i, "panel.jf", panel.names[i]) for i in range(len(panel.targets))]
+    else:
+        assert texts is None
+    _say(rank, "sharded targets done")
     dist.barrier()
     with open(os.path.join(out_dir, "ok%d" % rank), "w") as f:
         f.write("%d %d\n" % (kept, len(seqs)))

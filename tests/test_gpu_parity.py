@@ -391,3 +391,23 @@ def test_table_counted_from_reads_equals_host_count(engine):
     got = t.query_packed(keys)
     want = np.array([host[int(k)] if host[int(k)] >= 2 else 0 for k in keys], dtype=np.uint32)
     assert (got == want).all()
+
+
+def test_repeated_runs_print_the_same_text(engine):
+    """The kernels race by design (atomics hand out node numbers, path slots and rows); the canonical
+    numbering and the sorted output must hide it: the same batch, run again and again, prints the same text."""
+    from km_b200 import synth
+    panel = synth.make_panel(900, seed=41, two_variant_frac=0.3)
+    t = engine.Table.create(capacity=len(panel.keys) + 300000)
+    t.build_synthetic(synth.TABLE_SEED, 300000)
+    t.insert(panel.keys, panel.counts, mode="overwrite")
+    packed = engine.PackedTargets(panel.targets, panel.names)
+    first, status = t.find_text(packed, "panel.jf")
+    assert (status & ~np.uint32(16) == 0).all()
+    for n_sub in (1, 4, 6, 2, 5, 3, 6, 1):
+        again, _ = t.find_text(packed, "panel.jf", n_sub=n_sub)
+        assert again == first
+    plan = t.plan(panel.targets)
+    for _ in range(5):
+        plan.launch()
+        assert plan.fetch(want_graph=False).format_all("panel.jf", packed) == first

@@ -45,8 +45,16 @@ def test_shard_targets_is_a_balanced_partition():
         assert all((np.diff(p) > 0).all() for p in parts)
 
 
-def _gather_worker(rank, world, port, n):
+def _both_worker(rank, world, port, n):
+    """gather + routing in ONE pair of processes (starting them is most of the test's time)"""
     dist = _init(rank, world, port)
+    _gather_body(rank, world, dist, n)
+    _route_body(rank, world, dist)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _gather_body(rank, world, dist, n):
     lengths = [62 + (7 * i) % 300 for i in range(n)]
     mine = cohort.shard_targets(lengths, world)[rank]
     texts = ["row-of-%d-by-%d\n" % (i, rank) for i in mine.tolist()]
@@ -60,17 +68,10 @@ def _gather_worker(rank, world, port, n):
         assert got == ["row-of-%d-by-%d\n" % (i, owner[i]) for i in range(n)]
     else:
         assert got is None
-    dist.barrier()
-    dist.destroy_process_group()
 
 
-def test_rows_come_back_in_target_order():
-    _spawn(_gather_worker, 57)
-
-
-def _route_worker(rank, world, port):
+def _route_body(rank, world, dist):
     import torch
-    dist = _init(rank, world, port)
     rng = np.random.default_rng(1234)                      # the same key universe on every rank
     keys = rng.integers(0, 1 << 62, size=5000, dtype=np.uint64)
     counts = rng.integers(1, 1 << 32, size=5000, dtype=np.uint64).astype(np.uint32)
@@ -94,12 +95,10 @@ def _route_worker(rank, world, port):
     e = np.zeros(0, dtype=np.uint64) if rank == 0 else q[:5]
     got = cohort.route_queries(e, cohort.shard_owner(e, 31, False, world), dist, lookup_local)
     assert len(got) == len(e)
-    dist.barrier()
-    dist.destroy_process_group()
 
 
-def test_all_to_all_query_routing_equals_direct_lookup():
-    _spawn(_route_worker)
+def test_rows_come_back_in_order_and_all_to_all_routing_equals_direct_lookup():
+    _spawn(_both_worker, 57)
 
 
 def test_owner_is_strand_independent_for_canonical_tables():
