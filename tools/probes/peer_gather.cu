@@ -54,6 +54,11 @@ template <int MODE> float run(const uint4* buf, uint64_t n_sectors, uint64_t n_l
     return best;
 }
 int main(int argc, char** argv) {
+    if (argc > 1) {   // before anything else touches the device
+        cudaError_t e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, atoi(argv[1]));
+        size_t g0 = 0; cudaDeviceGetLimit(&g0, cudaLimitMaxL2FetchGranularity);
+        printf("early set %s -> %s, now %zu\n", argv[1], cudaGetErrorString(e), g0);
+    }
     int n = 0; CK(cudaGetDeviceCount(&n));
     const uint64_t n_loads = 1ull << 26;
     uint32_t* sink;
