@@ -237,9 +237,10 @@ def main():
 
     free, total_mem = torch.cuda.mem_get_info(dev)
     table_keys = args.table_keys
-    need = (table_keys + len(all_keys)) * 32 + (12 << 30) + (0 if args.no_lookup else args.lookup_queries * 12)
+    per_key = 52 if os.environ.get("KM_TABLE_LINES", "0") not in ("", "0") else 32      # family lines store every key twice
+    need = (table_keys + len(all_keys)) * per_key + (12 << 30) + (0 if args.no_lookup else args.lookup_queries * 12)
     if need > free:
-        table_keys = max(1 << 20, int((free - (16 << 30)) // 32 // 2))
+        table_keys = max(1 << 20, int((free - (16 << 30)) // per_key // 2))
         args.lookup_queries = min(args.lookup_queries, 1 << 28)
     t_build = time.time()
     table = engine.Table.create(k=31, canonical=True, capacity=table_keys + len(all_keys), device=local)
@@ -409,6 +410,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": workload, "targets_per_gpu": args.targets, "table_keys": table_keys,
                        "table_distinct": info["n_keys"], "table_gb": info["bytes"] / 1e9, "table_build_s": t_build,
+                       "table_layout": "family lines (128 B, two copies per k-mer)" if info["layout"] else "sector buckets (32 B)",
                        "parallelism": "targets sharded x%d, table replicated, no data-path collective" % world,
                        "l2": "table (%.0f GB) and per-step visited sets are far larger than the 126 MB L2; no explicit flush"
                              % (info["bytes"] / 1e9),

@@ -42,6 +42,12 @@ const char* km_version(void);
  * and the JSON header parse for `canonical`                         (Jellyfish.py:28-45) */
 int km_table_open_jf(const char* path, int device, km_table** out);
 int km_table_create(int device, int k, int canonical, uint64_t capacity_keys, km_table** out);
+/* The same with the table layout chosen explicitly: 0 = one 32-byte bucket per k-mer hash (one sector per
+ * lookup), 1 = FAMILY LINES: 128-byte lines addressed by a canonical (k-1)-mer, holding the k-mers that start
+ * or end with it; every k-mer is stored twice (~51 bytes per key instead of 32), and a k-mer's own count
+ * plus its four successors -- what MutationFinder asks for together -- come from ONE line.  km_table_create
+ * uses layout 0 unless the environment variable KM_TABLE_LINES is set. */
+int km_table_create_layout(int device, int k, int canonical, uint64_t capacity_keys, int layout, km_table** out);
 /* keys are canonical keys as stored in a .jf (`jellyfish count -C` records);
  * mode 0 keep existing, 1 overwrite, 2 add counts */
 int km_table_insert(km_table* t, const uint64_t* keys_host, const uint32_t* counts_host, uint64_t n, int mode);
@@ -58,7 +64,7 @@ typedef struct km_table_info {
     int32_t k;
     int32_t canonical;
     int32_t device;
-    int32_t reserved;
+    int32_t reserved;      /* table layout: 0 sector buckets, 1 family lines */
     uint64_t n_keys;       /* distinct keys stored */
     uint64_t n_buckets;    /* 32-byte buckets */
     uint64_t bytes;        /* HBM held by the bucket array */

@@ -155,6 +155,8 @@ struct km_table {
     std::shared_ptr<PinPool> pool = std::make_shared<PinPool>();   // result buffers (outlive the table if a result does)
     int sm_count = 148;
     // cohort mode: this table is shard `my_shard` of `n_shards`; peer[r] = rank r's buckets mapped through CUDA IPC
+    int lines = 0;             // 1: family-line layout (table.h), n_buckets counts 128-byte lines
+    size_t unit() const { return lines ? sizeof(Line) : sizeof(Bucket); }
     int n_shards = 1, my_shard = 0;
     const Bucket* peer[KM_MAX_SHARDS] = {};
     bool attached = false;
@@ -167,7 +169,7 @@ struct km_table {
     TableView view() const {
         TableView v;
         v.buckets = buckets; v.n_buckets = n_buckets; v.kmask = (1ull << (2 * k)) - 1ull; v.k = k; v.canonical = canonical;
-        v.n_shards = n_shards; v.my_shard = my_shard;
+        v.n_shards = n_shards; v.my_shard = my_shard; v.lines = lines;
         for (int r = 0; r < KM_MAX_SHARDS; ++r) v.shard[r] = peer[r];
         v.shard[my_shard] = buckets;
         return v;
@@ -176,6 +178,14 @@ struct km_table {
 
 static size_t align_up_sz(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+static bool default_lines() { const char* e = getenv("KM_TABLE_LINES"); return e && *e && *e != '0'; }
+// units (sector buckets or family lines) for `capacity_keys` keys: buckets hold 2 records at load <= 0.5;
+// lines hold 8 slots, every key takes two of them, load 0.625
+static uint64_t units_for(uint64_t capacity_keys, int lines) {
+    return std::max<uint64_t>(64, lines ? (capacity_keys * 2 + 4) / 5 : capacity_keys);
+}
+static void clear_units(km_table* t, void* mem, uint64_t n);
+
 static int grid_for(const km_table* t, uint64_t n, int block, int per_sm) {
     uint64_t want = (n + block - 1) / block;
     uint64_t cap = (uint64_t)t->sm_count * per_sm;
@@ -183,7 +193,17 @@ static int grid_for(const km_table* t, uint64_t n, int block, int per_sm) {
     return (int)std::min(want, cap);
 }
 
+static void clear_units(km_table* t, void* mem, uint64_t n) {
+    if (t->lines) km_table_clear_lines_kernel<<<t->sm_count * 8, 256, 0, t->stream>>>((Line*)mem, n);
+    else km_table_clear_kernel<<<t->sm_count * 8, 256, 0, t->stream>>>((Bucket*)mem, n);
+}
+
+extern "C" int km_table_create_layout(int device, int k, int canonical, uint64_t capacity_keys, int lines, km_table** out);
 extern "C" int km_table_create(int device, int k, int canonical, uint64_t capacity_keys, km_table** out) {
+    return km_table_create_layout(device, k, canonical, capacity_keys, default_lines() ? 1 : 0, out);
+}
+
+extern "C" int km_table_create_layout(int device, int k, int canonical, uint64_t capacity_keys, int lines, km_table** out) {
     if (!out || k < 1 || k > 31) return fail(KM_E_ARG, "km_table_create: k must be in 1..31 (got %d)", k);
     int ndev = km_device_count();
     if (ndev <= 0) return fail(KM_E_NOGPU, "no CUDA device visible: km_b200 has no CPU fallback");
@@ -191,16 +211,17 @@ extern "C" int km_table_create(int device, int k, int canonical, uint64_t capaci
     CU(cudaSetDevice(device));
     km_table* t = new km_table();
     t->device = device; t->k = k; t->canonical = canonical ? 1 : 0;
-    // two slots per bucket at a target load of ~0.5
-    t->n_buckets = std::max<uint64_t>(64, capacity_keys);
+    t->lines = lines ? 1 : 0;
+    if (t->lines && k < 2) { delete t; return fail(KM_E_ARG, "the family-line layout needs k >= 2"); }
+    t->n_buckets = units_for(capacity_keys, t->lines);
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     t->sm_count = prop.multiProcessorCount;
-    cudaError_t e = cudaMalloc((void**)&t->buckets, t->n_buckets * sizeof(Bucket));
+    cudaError_t e = cudaMalloc((void**)&t->buckets, t->n_buckets * t->unit());
     if (e != cudaSuccess) {
+        const unsigned long long want = (unsigned long long)(t->n_buckets * t->unit());
         delete t;
-        return fail(KM_E_CUDA, "cudaMalloc of %llu table bytes failed: %s", (unsigned long long)(capacity_keys * sizeof(Bucket)),
-                    cudaGetErrorString(e));
+        return fail(KM_E_CUDA, "cudaMalloc of %llu table bytes failed: %s", want, cudaGetErrorString(e));
     }
     CU(cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&t->side, cudaStreamNonBlocking));
@@ -214,7 +235,7 @@ extern "C" int km_table_create(int device, int k, int canonical, uint64_t capaci
                             (int)class_layout(KM_TINY_NODES).stride));
     CU(cudaFuncSetAttribute(km_graph_kernel<KM_SMALL_NODES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)class_layout(KM_SMALL_NODES).stride));
-    km_table_clear_kernel<<<t->sm_count * 8, 256, 0, t->stream>>>(t->buckets, t->n_buckets);
+    clear_units(t, t->buckets, t->n_buckets);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(t->stream));
     *out = t;
@@ -293,15 +314,15 @@ extern "C" int km_table_create_shard(int device, int k, int canonical, uint64_t 
     if (km_device_count() <= 0) return fail(KM_E_NOGPU, "no CUDA device visible: km_b200 has no CPU fallback");
     // the ordinary constructor with a token allocation, then the bucket array is replaced by a
     // shareable one of the real size
-    if (int rc = km_table_create(device, k, canonical, 64, out)) return rc;
+    if (int rc = km_table_create(device, k, canonical, 64, out)) return rc;      // layout from KM_TABLE_LINES
     km_table* t = *out;
     t->n_shards = n_shards; t->my_shard = rank;
     if (int rc = vmm_load()) { km_table_close(t); *out = nullptr; return rc; }
     CUmemAllocationProp prop = shard_prop(device);
     size_t gran = 0;
     DRV(g_vmm.granularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED));
-    const uint64_t n_buckets = std::max<uint64_t>(64, capacity_keys_per_shard);
-    const size_t size = align_up_sz(n_buckets * sizeof(Bucket), gran);
+    const uint64_t n_buckets = units_for(capacity_keys_per_shard, t->lines);
+    const size_t size = align_up_sz(n_buckets * t->unit(), gran);
     CUmemGenericAllocationHandle h = 0;
     CUresult cr = g_vmm.create(&h, size, &prop, 0);
     if (cr != CUDA_SUCCESS) { km_table_close(t); *out = nullptr; return fail(KM_E_CUDA, "cuMemCreate of %zu shard bytes failed: CUresult %d", size, (int)cr); }
@@ -310,7 +331,7 @@ extern "C" int km_table_create_shard(int device, int k, int canonical, uint64_t 
     cudaFree(t->buckets);
     t->buckets = (Bucket*)ptr; t->n_buckets = n_buckets;
     t->vmm = true; t->vmm_handle = h; t->vmm_size = size;
-    km_table_clear_kernel<<<t->sm_count * 8, 256, 0, t->stream>>>(t->buckets, t->n_buckets);
+    clear_units(t, t->buckets, t->n_buckets);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(t->stream));
     return 0;
@@ -405,7 +426,8 @@ extern "C" void km_table_close(km_table* t) {
 extern "C" int km_table_get_info(km_table* t, km_table_info* info) {
     if (!t || !info) return fail(KM_E_ARG, "null argument");
     info->k = t->k; info->canonical = t->canonical; info->device = t->device; info->reserved = 0;
-    info->n_keys = t->n_keys; info->n_buckets = t->n_buckets; info->bytes = t->n_buckets * sizeof(Bucket);
+    info->n_keys = t->n_keys; info->n_buckets = t->n_buckets; info->bytes = t->n_buckets * t->unit();
+    info->reserved = t->lines;
     return 0;
 }
 
@@ -414,7 +436,7 @@ static int finish_insert(km_table* t, const char* what) {
     CU(cudaMemcpyAsync(host, t->d_counter, 16, cudaMemcpyDeviceToHost, t->stream));
     CU(cudaStreamSynchronize(t->stream));
     t->n_keys += host[0];
-    if ((uint32_t)host[1]) return fail(KM_E_FULL, "%s: table full (%llu buckets)", what, (unsigned long long)t->n_buckets);
+    if ((uint32_t)host[1]) return fail(KM_E_FULL, "%s: table full (%llu %s)", what, (unsigned long long)t->n_buckets, t->lines ? "lines" : "buckets");
     return 0;
 }
 
@@ -471,8 +493,8 @@ extern "C" int km_table_drop_below(km_table* t, uint32_t min_count, uint64_t* n_
     if (!t) return fail(KM_E_ARG, "null table");
     CU(cudaSetDevice(t->device));
     Bucket* fresh = nullptr;
-    CU(cudaMalloc((void**)&fresh, t->n_buckets * sizeof(Bucket)));
-    km_table_clear_kernel<<<t->sm_count * 8, 256, 0, t->stream>>>(fresh, t->n_buckets);
+    CU(cudaMalloc((void**)&fresh, t->n_buckets * t->unit()));
+    clear_units(t, fresh, t->n_buckets);
     TableView dst = t->view();
     dst.buckets = fresh;
     dst.shard[t->my_shard] = fresh;
@@ -484,7 +506,7 @@ extern "C" int km_table_drop_below(km_table* t, uint32_t min_count, uint64_t* n_
     int rc = finish_insert(t, "km_table_drop_below");
     if (t->vmm) {
         // a shard keeps its (peer-mapped) memory: the filtered copy goes back in place
-        CU(cudaMemcpyAsync(t->buckets, fresh, t->n_buckets * sizeof(Bucket), cudaMemcpyDeviceToDevice, t->stream));
+        CU(cudaMemcpyAsync(t->buckets, fresh, t->n_buckets * t->unit(), cudaMemcpyDeviceToDevice, t->stream));
         CU(cudaStreamSynchronize(t->stream));
         cudaFree(fresh);
     } else {
@@ -559,7 +581,8 @@ extern "C" int km_query_batch_device(km_table* t, const uint64_t* kmers_dev, uin
     if (!t || (n && (!kmers_dev || !counts_dev))) return fail(KM_E_ARG, "km_query_batch_device: bad argument");
     if (!n) return 0;
     cudaStream_t s = stream ? (cudaStream_t)stream : t->stream;
-    km_query_kernel<<<grid_for(t, (n + KM_QUERY_ILP - 1) / KM_QUERY_ILP, 256, 8), 256, 0, s>>>(t->view(), kmers_dev, n, counts_dev);
+    if (t->lines) km_query_lines_kernel<<<grid_for(t, n, 256, 8), 256, 0, s>>>(t->view(), kmers_dev, n, counts_dev);
+    else km_query_kernel<<<grid_for(t, (n + KM_QUERY_ILP - 1) / KM_QUERY_ILP, 256, 8), 256, 0, s>>>(t->view(), kmers_dev, n, counts_dev);
     CU(cudaGetLastError());
     return 0;
 }

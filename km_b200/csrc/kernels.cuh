@@ -73,9 +73,28 @@ __global__ void km_count_reads_kernel(TableView T, const char* reads, const int6
     if (mine) atomicAdd(n_new, mine);
 }
 
+__global__ void km_table_clear_lines_kernel(Line* lines, uint64_t n) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < KM_LINE_SLOTS * n; i += stride)
+        reinterpret_cast<uint4*>(lines)[i] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);      // key = empty, count = 0
+}
+
 __global__ void km_table_filter_kernel(TableView src, TableView dst, uint32_t min_count, unsigned long long* n_new, uint32_t* full) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     unsigned long long mine = 0;
+    if (src.lines) {
+        // every k-mer sits in two lines; both copies are visited, the second insertion finds the key in place
+        const LineSlot* slots = reinterpret_cast<const LineSlot*>(src.buckets);
+        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < src.n_buckets * KM_LINE_SLOTS; i += stride) {
+            const uint64_t stored = slots[i].key;
+            if (stored == KM_EMPTY_KEY || slots[i].count < min_count) continue;
+            const int r = table_insert(dst, KM_KEY_OF(stored), slots[i].count, KM_INSERT_KEEP);
+            if (r < 0) *full = 1;
+            mine += r > 0;
+        }
+        if (mine) atomicAdd(n_new, mine);
+        return;
+    }
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < src.n_buckets * KM_BUCKET_SLOTS; i += stride) {
         const Bucket* b = src.buckets + i / KM_BUCKET_SLOTS;
         const int s = (int)(i % KM_BUCKET_SLOTS);
@@ -135,11 +154,62 @@ __global__ void __launch_bounds__(256) km_query_kernel(TableView T, const uint64
             q[i] = j < n ? kmers[j] : 0ull;
             live |= j < n ? (1u << i) : 0u;
         }
-        table_query_masked<KM_QUERY_ILP>(T, q, live, r);
+        if (T.lines) {
+#pragma unroll
+            for (int i = 0; i < KM_QUERY_ILP; ++i) r[i] = (live >> i) & 1u ? table_query(T, q[i]) : 0u;
+        } else {
+            table_query_masked<KM_QUERY_ILP>(T, q, live, r);
+        }
 #pragma unroll
         for (int i = 0; i < KM_QUERY_ILP; ++i) {
             const uint64_t j = base + (uint64_t)i * stride;
             if (j < n) out[j] = r[i];
+        }
+    }
+}
+
+// The same for a table of family lines: FOUR LANES PER QUERY.  An isolated k-mer sits somewhere in the
+// 128-byte line of its prefix family; lane j of a quad loads sector j, so the line is one coalesced request
+// (what a random 32-byte read costs in DRAM anyway), each lane checks its two slots and the quad combines by
+// shuffle.  KM_QUERY_ILP queries per quad are in flight.
+__global__ void __launch_bounds__(256) km_query_lines_kernel(TableView T, const uint64_t* __restrict__ kmers, uint64_t n,
+                                                             uint32_t* __restrict__ out) {
+    const uint64_t n_quads = ((uint64_t)gridDim.x * blockDim.x) >> 2;
+    const uint64_t quad = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    const int sec = threadIdx.x & 3;
+    for (uint64_t base = quad; base < n; base += n_quads * KM_QUERY_ILP) {      // the quads of a warp stay together: n_quads is a multiple of 8
+        uint64_t key[KM_QUERY_ILP], k0[KM_QUERY_ILP], k1[KM_QUERY_ILP], idx[KM_QUERY_ILP];
+        uint32_t c0[KM_QUERY_ILP], c1[KM_QUERY_ILP];
+        const Line* lb[KM_QUERY_ILP];
+#pragma unroll
+        for (int i = 0; i < KM_QUERY_ILP; ++i) {
+            const uint64_t j = base + (uint64_t)i * n_quads;
+            const uint64_t v = (j < n ? kmers[j] : 0ull) & T.kmask;
+            key[i] = T.canonical ? canonical(v, T.k) : v;
+            lb[i] = locate_line(T, family_of_prefix(T, v), &idx[i]);
+            k0[i] = k1[i] = KM_EMPTY_KEY; c0[i] = c1[i] = 0;
+            if (j < n) load_sector(lb[i][idx[i]].s + 2 * sec, k0[i], c0[i], k1[i], c1[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < KM_QUERY_ILP; ++i) {
+            const uint64_t j = base + (uint64_t)i * n_quads;
+            // bits 0..31 count, 32 found, 33 the line has an empty slot
+            unsigned long long r = 0ull;
+            if (KM_KEY_OF(k0[i]) == key[i]) r = (1ull << 32) | c0[i];
+            if (KM_KEY_OF(k1[i]) == key[i]) r = (1ull << 32) | c1[i];
+            if (k0[i] == KM_EMPTY_KEY || k1[i] == KM_EMPTY_KEY) r |= 1ull << 33;
+            r |= __shfl_xor_sync(0xFFFFFFFFu, r, 1);
+            r |= __shfl_xor_sync(0xFFFFFFFFu, r, 2);
+            if (sec == 0 && j < n) {
+                uint32_t cnt = (uint32_t)r;
+                if (!(r >> 32)) {            // full line without the key: the next line, on this lane's own (rare)
+                    const uint64_t keys1[1] = {key[i]};
+                    uint32_t r1[1] = {0};
+                    line_find_from<1>(T, lb[i], idx[i] + 1 == T.n_buckets ? 0 : idx[i] + 1, keys1, 1u, r1);
+                    cnt = r1[0];
+                }
+                out[j] = cnt;
+            }
         }
     }
 }
@@ -154,7 +224,7 @@ __global__ void __launch_bounds__(256) km_get_child_kernel(TableView T, const ui
         uint64_t ck[4]; uint32_t cc[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) ck[c] = forward ? succ_kmer(v, c, T.kmask) : pred_kmer(v, c, T.k);
-        table_query_multi<4>(T, ck, cc);
+        table_query_family<4>(T, forward ? family_of_suffix(T, v) : family_of_prefix(T, v), ck, 15u, cc);
         const uint64_t sum = (uint64_t)cc[0] + cc[1] + cc[2] + cc[3];
         double thr = (double)sum * ratio;
         if (thr < (double)floor_count) thr = (double)floor_count;

@@ -40,6 +40,7 @@ struct TableView {
     int n_shards;
     int my_shard;
     const Bucket* shard[KM_MAX_SHARDS];   // shard[my_shard] == buckets; others null until peers are attached
+    int lines;                // 0: sector buckets (above); 1: family lines (below), n_buckets counts 128-byte lines
 };
 
 KM_HD uint64_t key_hash(uint64_t key) { return mix64(key + KM_GOLDEN_T); }
@@ -72,6 +73,190 @@ KM_HD void load_bucket(const Bucket* b, uint64_t& k0, uint64_t& k1, uint32_t& c0
 }
 #endif
 
+// ---- family lines (TableView::lines == 1) ---------------------------------------------------------------
+// Measured on B200: a random 32-byte read costs a whole 128-byte DRAM line (ncu: 4 L2 sectors, 129 B of DRAM
+// traffic per load, whatever cudaLimitMaxL2FetchGranularity says), and that line traffic -- not the request
+// count -- is what caps random probes.  So the table is laid out such that the k-mers the walk asks for
+// TOGETHER share a line: a line = 8 slots of (u64 key, u32 count, 4 spare bytes), addressed by a canonical
+// (k-1)-mer M, and holds the k-mers that contain M as their first or last k-1 bases -- the four successors
+// M+c and the four predecessors c+M.  Every k-mer is therefore stored twice (under its prefix and under
+// its suffix (k-1)-mer).  A reference k-mer X and its four successors X[1:]+c all live in the line of
+// canonical(X[1:]): get_child plus the k-mer's own count is ONE line instead of five sectors.  A line that
+// is full forwards to the next one (linear probing at line granularity).  Inside a line a k-mer prefers the
+// 32-byte sector chosen by its own hash, so an isolated query usually reads a single sector.
+#define KM_LINE_SLOTS 8
+// the two copies of a k-mer are told apart by the top bit of the stored key (k <= 31 uses 62 bits): the
+// copy under the suffix family carries it.  Without it an insertion whose two families share a line would
+// find its own first copy and count twice.
+#define KM_COPY_BIT 0x8000000000000000ull
+#define KM_KEY_OF(stored) ((stored) & ~KM_COPY_BIT)
+struct alignas(16) LineSlot { uint64_t key; uint32_t count; uint32_t pad; };
+struct alignas(128) Line { LineSlot s[KM_LINE_SLOTS]; };
+
+KM_HD uint64_t sub_canon(const TableView& t, uint64_t v) {         // v: a (k-1)-mer
+    return t.canonical ? canonical(v, t.k - 1) : v;
+}
+// the family in which a forward k-mer appears as a SUCCESSOR (shares its first k-1 bases with its siblings)
+KM_HD uint64_t family_of_prefix(const TableView& t, uint64_t fwd) { return sub_canon(t, (fwd & t.kmask) >> 2); }
+// the family in which a forward k-mer appears as the PARENT of its successors / as a predecessor
+KM_HD uint64_t family_of_suffix(const TableView& t, uint64_t fwd) { return sub_canon(t, fwd & (t.kmask >> 2)); }
+KM_HD int preferred_sector(uint64_t key) { return (int)((key * 0x9E3779B97F4A7C15ull) >> 62); }
+
+KM_HD const Line* locate_line(const TableView& t, uint64_t fam, uint64_t* idx) {
+    const uint64_t h = key_hash(fam ^ 0x5851F42D4C957F2Dull);
+    *idx = bucket_of_hash(h, t.n_shards, t.n_buckets);
+    const Bucket* base = t.n_shards > 1 ? t.shard[shard_of_hash(h, t.n_shards)] : t.buckets;
+    return reinterpret_cast<const Line*>(base);
+}
+KM_HD int family_owner(const TableView& t, uint64_t fam) { return shard_of_hash(key_hash(fam ^ 0x5851F42D4C957F2Dull), t.n_shards); }
+
+#if KM_DEVICE_BUILD
+KM_HD void load_sector(const LineSlot* p, uint64_t& k0, uint32_t& c0, uint64_t& k1, uint32_t& c1) {
+    uint64_t a, b;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(k0), "=l"(a), "=l"(k1), "=l"(b) : "l"(p));
+    c0 = (uint32_t)a; c1 = (uint32_t)b;
+}
+#else
+KM_HD void load_sector(const LineSlot* p, uint64_t& k0, uint32_t& c0, uint64_t& k1, uint32_t& c1) {
+    k0 = p[0].key; c0 = p[0].count; k1 = p[1].key; c1 = p[1].count;
+}
+#endif
+
+// counts of up to N canonical keys that all belong to one family, starting at line `idx` of `base`: the whole
+// line is fetched (four 32-byte loads in flight), then the rare forwarding to the next line
+template <int N>
+KM_HD void line_find_from(const TableView& t, const Line* base, uint64_t idx, const uint64_t (&key)[N], uint32_t pending,
+                          uint32_t (&out)[N]) {
+    while (pending) {
+        const LineSlot* p = base[idx].s;
+        uint64_t k[KM_LINE_SLOTS];
+        uint32_t c[KM_LINE_SLOTS];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) load_sector(p + 2 * h, k[2 * h], c[2 * h], k[2 * h + 1], c[2 * h + 1]);
+        bool has_empty = false;
+#pragma unroll
+        for (int s = 0; s < KM_LINE_SLOTS; ++s) {
+            has_empty |= k[s] == KM_EMPTY_KEY;
+#pragma unroll
+            for (int i = 0; i < N; ++i)
+                if (KM_KEY_OF(k[s]) == key[i] && (pending & (1u << i))) { out[i] = c[s]; pending &= ~(1u << i); }
+        }
+        if (has_empty) return;
+        if (++idx == t.n_buckets) idx = 0;
+    }
+}
+template <int N>
+KM_HD void line_find(const TableView& t, uint64_t fam, const uint64_t (&key)[N], uint32_t mask, uint32_t (&out)[N]) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) out[i] = 0;
+    uint64_t idx;
+    const Line* base = locate_line(t, fam, &idx);
+    line_find_from<N>(t, base, idx, key, mask, out);
+}
+
+#if KM_DEVICE_BUILD
+// The same for a whole warp, every lane with its own family: lanes fetch each other's lines FOUR LANES PER
+// LINE (lane j of a quad loads sector j), so a line is one coalesced 128-byte request instead of four
+// 32-byte ones, and the sectors are handed back to the owning lane by shuffle.  Four passes cover the 32
+// lanes; the loads of all passes are issued before any is consumed.  All 32 lanes must call.
+template <int N>
+__device__ __forceinline__ void warp_line_find(const TableView& t, uint64_t fam, const uint64_t (&key)[N], uint32_t mask,
+                                               uint32_t (&out)[N]) {
+    const int lane = threadIdx.x & 31, quad = lane >> 2, sec = lane & 3;
+    uint64_t idx;
+    const Line* base = locate_line(t, fam, &idx);
+    const unsigned long long mine = (unsigned long long)(base[idx].s);
+    uint64_t k0[4], k1[4], cc[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const LineSlot* line = (const LineSlot*)__shfl_sync(0xFFFFFFFFu, mine, 8 * p + quad);
+        uint32_t c0, c1;
+        load_sector(line + 2 * sec, k0[p], c0, k1[p], c1);
+        cc[p] = (uint64_t)c0 | ((uint64_t)c1 << 32);
+    }
+    uint64_t K[KM_LINE_SLOTS];
+    uint32_t C[KM_LINE_SLOTS];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            const int src = 4 * (lane & 7) + s;
+            const uint64_t a = __shfl_sync(0xFFFFFFFFu, (unsigned long long)k0[p], src);
+            const uint64_t b = __shfl_sync(0xFFFFFFFFu, (unsigned long long)k1[p], src);
+            const uint64_t c = __shfl_sync(0xFFFFFFFFu, (unsigned long long)cc[p], src);
+            if ((lane >> 3) == p) { K[2 * s] = a; K[2 * s + 1] = b; C[2 * s] = (uint32_t)c; C[2 * s + 1] = (uint32_t)(c >> 32); }
+        }
+    }
+    uint32_t pending = mask;
+    bool has_empty = false;
+#pragma unroll
+    for (int i = 0; i < N; ++i) out[i] = 0;
+#pragma unroll
+    for (int s = 0; s < KM_LINE_SLOTS; ++s) {
+        has_empty |= K[s] == KM_EMPTY_KEY;
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+            if (KM_KEY_OF(K[s]) == key[i] && (pending & (1u << i))) { out[i] = C[s]; pending &= ~(1u << i); }
+    }
+    // a full line that lacks a wanted key forwards to the next line: rare, finished by the lane on its own
+    if (pending && !has_empty) line_find_from<N>(t, base, idx + 1 == t.n_buckets ? 0 : idx + 1, key, pending, out);
+}
+#endif
+
+// one isolated k-mer: its preferred sector first, the rest of the line only if that sector is full without it
+KM_HD uint32_t line_lookup_one(const TableView& t, uint64_t fam, uint64_t key) {
+    uint64_t idx;
+    const Line* base = locate_line(t, fam, &idx);
+    const int pref = preferred_sector(key);
+    for (;;) {
+        const LineSlot* p = base[idx].s;
+        uint64_t k0, k1; uint32_t c0, c1;
+        load_sector(p + 2 * pref, k0, c0, k1, c1);
+        if (k0 != KM_EMPTY_KEY && KM_KEY_OF(k0) == key) return c0;
+        if (k1 != KM_EMPTY_KEY && KM_KEY_OF(k1) == key) return c1;
+        if (k0 == KM_EMPTY_KEY || k1 == KM_EMPTY_KEY) return 0;     // insertion fills the preferred sector first
+        bool has_empty = false;
+#pragma unroll
+        for (int h = 1; h < 4; ++h) {
+            load_sector(p + 2 * ((pref + h) & 3), k0, c0, k1, c1);
+            if (k0 != KM_EMPTY_KEY && KM_KEY_OF(k0) == key) return c0;
+            if (k1 != KM_EMPTY_KEY && KM_KEY_OF(k1) == key) return c1;
+            has_empty |= k0 == KM_EMPTY_KEY || k1 == KM_EMPTY_KEY;
+        }
+        if (has_empty) return 0;
+        if (++idx == t.n_buckets) idx = 0;
+    }
+}
+
+// one copy of the k-mer into the line of `fam` (`key` carries the copy bit): 1 newly inserted, 0 existed, -1 table full
+KM_HD int line_insert(const TableView& t, uint64_t fam, uint64_t key, uint32_t count, int mode) {
+    uint64_t idx;
+    Line* base = const_cast<Line*>(locate_line(t, fam, &idx));
+    const int pref = preferred_sector(KM_KEY_OF(key));
+    for (uint64_t tries = 0; tries < t.n_buckets; ++tries) {
+        LineSlot* p = base[idx].s;
+        for (int j = 0; j < KM_LINE_SLOTS; ++j) {
+            LineSlot* sl = p + ((2 * pref + j) & (KM_LINE_SLOTS - 1));
+            uint64_t cur = load_cg64(&sl->key);
+            if (cur == KM_EMPTY_KEY) {
+                cur = atomic_cas64(&sl->key, KM_EMPTY_KEY, key);
+                if (cur == KM_EMPTY_KEY) {
+                    if (mode == 2) atomic_add32(&sl->count, count);
+                    else sl->count = count;
+                    return 1;
+                }
+            }
+            if (cur == key) {
+                if (mode == 2) atomic_add32(&sl->count, count);
+                else if (mode == 1) sl->count = count;
+                return 0;
+            }
+        }
+        if (++idx == t.n_buckets) idx = 0;
+    }
+    return -1;
+}
+
 // canonical key -> count (0 when absent).  Read-only path: valid only while no kernel is
 // inserting into the table.
 KM_HD uint32_t table_lookup_key(const TableView& t, uint64_t key) {
@@ -90,7 +275,9 @@ KM_HD uint32_t table_lookup_key(const TableView& t, uint64_t key) {
 // forward-strand packed k-mer -> count: Jellyfish.query (km/utils/Jellyfish.py:47-53)
 KM_HD uint32_t table_query(const TableView& t, uint64_t fwd) {
     uint64_t v = fwd & t.kmask;
-    return table_lookup_key(t, t.canonical ? canonical(v, t.k) : v);
+    const uint64_t key = t.canonical ? canonical(v, t.k) : v;
+    if (t.lines) return line_lookup_one(t, family_of_prefix(t, v), key);
+    return table_lookup_key(t, key);
 }
 
 // N independent first probes in flight per thread (the walk issues the 4 successor
@@ -153,11 +340,87 @@ KM_HD void table_query_masked(const TableView& T, const uint64_t (&fwd)[N], uint
     }
 }
 
+// Lookups that belong together (the successors of one parent, plus the parent itself): `fam` is their
+// family (family_of_prefix of a successor == family_of_suffix of the parent).  With sector buckets this
+// is N independent probes; with family lines it is one line.
+template <int N>
+KM_HD void table_query_family(const TableView& T, uint64_t fam, const uint64_t (&fwd)[N], uint32_t mask, uint32_t (&out)[N]) {
+    if (T.lines) {
+        uint64_t key[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) { const uint64_t v = fwd[i] & T.kmask; key[i] = T.canonical ? canonical(v, T.k) : v; }
+        line_find<N>(T, fam, key, mask, out);
+    } else {
+        table_query_masked<N>(T, fwd, mask, out);
+    }
+}
+
+#if KM_DEVICE_BUILD
+// The four lanes of a quad each ask for one successor of the same parent (family `fam`): lane j loads sector j
+// of the family's line -- one coalesced 128-byte request for the quad -- and every lane then searches the
+// eight slots (handed round by shuffle) for its own key.  All 32 lanes must call; quads with `live` false
+// skip the load.
+__device__ __forceinline__ uint32_t quad_line_query(const TableView& t, uint64_t fam, uint64_t key, bool live) {
+    const int lane = threadIdx.x & 31, qbase = lane & 28, sec = lane & 3;
+    uint64_t idx = 0;
+    const Line* base = nullptr;
+    uint64_t k0 = KM_EMPTY_KEY, k1 = KM_EMPTY_KEY, cc = 0;
+    if (live) {
+        base = locate_line(t, fam, &idx);
+        uint32_t c0, c1;
+        load_sector(base[idx].s + 2 * sec, k0, c0, k1, c1);
+        cc = (uint64_t)c0 | ((uint64_t)c1 << 32);
+    }
+    uint32_t out = 0;
+    bool found = false, has_empty = false;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        const uint64_t a = __shfl_sync(0xFFFFFFFFu, (unsigned long long)k0, qbase + s);
+        const uint64_t b = __shfl_sync(0xFFFFFFFFu, (unsigned long long)k1, qbase + s);
+        const uint64_t c = __shfl_sync(0xFFFFFFFFu, (unsigned long long)cc, qbase + s);
+        has_empty |= a == KM_EMPTY_KEY || b == KM_EMPTY_KEY;
+        if (KM_KEY_OF(a) == key) { out = (uint32_t)c; found = true; }
+        if (KM_KEY_OF(b) == key) { out = (uint32_t)(c >> 32); found = true; }
+    }
+    if (live && !found && !has_empty) {          // full line without the key: the next line, on this lane's own
+        const uint64_t keys[1] = {key};
+        uint32_t r[1] = {0};
+        line_find_from<1>(t, base, idx + 1 == t.n_buckets ? 0 : idx + 1, keys, 1u, r);
+        out = r[0];
+    }
+    return out;
+}
+#endif
+
+// table_query_family for a converged warp (all 32 lanes call; lanes with nothing to ask pass mask 0)
+template <int N>
+KM_HD void table_query_family_warp(const TableView& T, uint64_t fam, const uint64_t (&fwd)[N], uint32_t mask, uint32_t (&out)[N]) {
+#if KM_DEVICE_BUILD
+    if (T.lines) {
+        uint64_t key[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) { const uint64_t v = fwd[i] & T.kmask; key[i] = T.canonical ? canonical(v, T.k) : v; }
+        warp_line_find<N>(T, fam, key, mask, out);
+        return;
+    }
+#endif
+    table_query_family<N>(T, fam, fwd, mask, out);
+}
+
 enum InsertMode { KM_INSERT_KEEP = 0, KM_INSERT_OVERWRITE = 1, KM_INSERT_ADD = 2 };
 
 // Returns 1 if the key was newly inserted, 0 if it already existed (or belongs to another shard),
 // -1 if the shard is full.  Only the owner inserts a key.
 KM_HD int table_insert(const TableView& t, uint64_t key, uint32_t count, int mode) {
+    if (t.lines) {
+        // two copies: under the k-mer's prefix (k-1)-mer and under its suffix (k-1)-mer; each goes to the
+        // shard that owns its family; "newly inserted" is reported for the prefix copy only
+        const uint64_t f1 = sub_canon(t, key >> 2), f2 = sub_canon(t, key & (t.kmask >> 2));
+        int r1 = 0, r2 = 0;
+        if (family_owner(t, f1) == t.my_shard) r1 = line_insert(t, f1, key, count, mode);
+        if (f2 != f1 && family_owner(t, f2) == t.my_shard) r2 = line_insert(t, f2, key | KM_COPY_BIT, count, mode);
+        return (r1 < 0 || r2 < 0) ? -1 : r1;
+    }
     const uint64_t h = key_hash(key);
     if (shard_of_hash(h, t.n_shards) != t.my_shard) return 0;
     uint64_t b = bucket_of_hash(h, t.n_shards, t.n_buckets);

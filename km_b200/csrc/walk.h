@@ -152,7 +152,7 @@ KM_HD void expand_node(const TableView& T, const WalkView& W, const TargetGeom& 
     uint64_t ck[4]; uint32_t cc[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) ck[c] = succ_kmer(kmer, c, T.kmask);
-    table_query_multi<4>(T, ck, cc);
+    table_query_family<4>(T, family_of_suffix(T, kmer), ck, 15u, cc);
     *n_lookups += 4;
     // Jellyfish.py:61-72 -- Python int * float, then max with the int floor, then >=
     const uint64_t sum = (uint64_t)cc[0] + cc[1] + cc[2] + cc[3];

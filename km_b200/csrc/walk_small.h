@@ -115,7 +115,7 @@ KM_HD void ref_probe_chunk(const Ctx& ctx, const TableView& T, const WalkView& W
             if (c != ref_c || lane == nl - 1) mask |= 2u << c;
         }
     }
-    table_query_masked<5>(T, q, mask, r);
+    table_query_family_warp<5>(T, family_of_suffix(T, q[0]), q, mask, r);
     const uint32_t next_own = (uint32_t)warp_shfl_down32((int)r[0], 1);
     if (active) {
         if (lane != nl - 1) {
@@ -155,7 +155,7 @@ KM_HD void ref_probe_chunk(const Ctx& ctx, const TableView& T, const WalkView& W
 KM_HD void ws_query_children(const TableView& T, uint64_t kmer, uint64_t (&ck)[4], uint32_t (&cc)[4]) {
 #pragma unroll
     for (int c = 0; c < 4; ++c) ck[c] = succ_kmer(kmer, c, T.kmask);
-    table_query_multi<4>(T, ck, cc);
+    table_query_family<4>(T, family_of_suffix(T, kmer), ck, 15u, cc);
 }
 
 // Children of one level, one successor letter per call: lanes holding the same child k-mer find each
@@ -266,17 +266,20 @@ KM_HD bool walk_small_target(const Ctx& ctx, const TableView& T, const WalkView&
             bool expand = false;
             uint64_t ck = 0;
             uint32_t cnt = 0, meta = 0;
+            uint64_t parent = 0;
             if (q < hi) {
                 meta = M.nmeta[q - L];
                 if ((int)(meta >> 8) > P.max_stack) st |= KM_ST_TOUCHED_LIMIT;                // MutationFinder.py:140-141
                 else {
                     expand = true;
-                    ck = succ_kmer(M.nk[q - L], c, T.kmask);
-                    cnt = table_query(T, ck);
+                    parent = M.nk[q - L];
+                    ck = succ_kmer(parent, c, T.kmask);
                     nlook += 1;
                 }
                 M.kid[q - L][c] = 0;
             }
+            if (T.lines) cnt = quad_line_query(T, family_of_suffix(T, parent), T.canonical ? canonical(ck, T.k) : ck, expand);
+            else if (expand) cnt = table_query(T, ck);
             // Jellyfish.py:61-72 over the group's four counts
             unsigned long long sum = cnt;
             sum += __shfl_xor_sync(0xFFFFFFFFu, sum, 1);

@@ -84,15 +84,21 @@ class Table:
         return cls(h)
 
     @classmethod
-    def create(cls, k=31, canonical=True, capacity=1 << 20, device=0):
+    def create(cls, k=31, canonical=True, capacity=1 << 20, device=0, layout=None):
+        """layout: None = library default (sector buckets, or family lines when KM_TABLE_LINES is set),
+        0 = sector buckets, 1 = family lines (include/km_b200.h)."""
         h = ctypes.c_void_p()
-        check(lib().km_table_create(int(device), int(k), int(bool(canonical)), int(capacity), ctypes.byref(h)))
+        if layout is None:
+            check(lib().km_table_create(int(device), int(k), int(bool(canonical)), int(capacity), ctypes.byref(h)))
+        else:
+            check(lib().km_table_create_layout(int(device), int(k), int(bool(canonical)), int(capacity), int(layout),
+                                               ctypes.byref(h)))
         return cls(h)
 
     def info(self):
         info = TableInfo()
         check(lib().km_table_get_info(self._h, ctypes.byref(info)))
-        return {"k": info.k, "canonical": bool(info.canonical), "device": info.device,
+        return {"k": info.k, "canonical": bool(info.canonical), "device": info.device, "layout": int(info.reserved),
                 "n_keys": int(info.n_keys), "n_buckets": int(info.n_buckets), "bytes": int(info.bytes)}
 
     def insert(self, keys, counts, mode="overwrite"):

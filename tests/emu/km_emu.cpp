@@ -16,19 +16,37 @@ using namespace km;
 
 struct EmuTable {
     TableView v;
-    std::vector<Bucket> store;
+    std::vector<Bucket> store;      // sector buckets, or family lines (4 buckets' worth of bytes each)
 };
 
 extern "C" {
 
-void* emu_table_create(int k, int canonical, uint64_t capacity) {
+void* emu_table_create_layout(int k, int canonical, uint64_t capacity, int lines) {
     EmuTable* t = new EmuTable();
     uint64_t nb = capacity < 64 ? 64 : capacity;
+    if (lines) {
+        nb = (capacity * 2 + 4) / 5 < 64 ? 64 : (capacity * 2 + 4) / 5;
+        t->store.resize(nb * 4 + 4);
+        // 128-byte alignment of the first line
+        char* raw = (char*)t->store.data();
+        char* al = raw + ((128 - ((uintptr_t)raw & 127)) & 127);
+        LineSlot* sl = (LineSlot*)al;
+        for (uint64_t i = 0; i < nb * KM_LINE_SLOTS; ++i) { sl[i].key = KM_EMPTY_KEY; sl[i].count = 0; sl[i].pad = 0; }
+        t->v.buckets = (Bucket*)al; t->v.n_buckets = nb; t->v.k = k; t->v.canonical = canonical; t->v.kmask = kmer_mask(k);
+        t->v.n_shards = 1; t->v.my_shard = 0; for (auto& sp : t->v.shard) sp = nullptr; t->v.shard[0] = t->v.buckets;
+        t->v.lines = 1;
+        return t;
+    }
+    t->v.lines = 0;
     t->store.resize(nb);
     for (auto& b : t->store) { b.key[0] = b.key[1] = KM_EMPTY_KEY; b.count[0] = b.count[1] = 0; b.pad[0] = b.pad[1] = 0; }
     t->v.buckets = t->store.data(); t->v.n_buckets = nb; t->v.k = k; t->v.canonical = canonical; t->v.kmask = kmer_mask(k);
     t->v.n_shards = 1; t->v.my_shard = 0; for (auto& sp : t->v.shard) sp = nullptr; t->v.shard[0] = t->v.buckets;
     return t;
+}
+void* emu_table_create(int k, int canonical, uint64_t capacity) {
+    const char* e = getenv("KM_TABLE_LINES");
+    return emu_table_create_layout(k, canonical, capacity, e && *e && *e != '0');
 }
 void emu_table_free(void* h) { delete (EmuTable*)h; }
 int emu_table_insert(void* h, const uint64_t* keys, const uint32_t* counts, uint64_t n, int mode) {

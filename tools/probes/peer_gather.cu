@@ -31,6 +31,10 @@ __global__ void gather(const uint4* __restrict__ buf, uint64_t n_sectors, uint64
                 asm volatile("ld.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(*(uint64_t*)&a[i].x), "=l"(*(uint64_t*)&a[i].z), "=l"(*(uint64_t*)&b[i].x), "=l"(*(uint64_t*)&b[i].z) : "l"(p));
             } else if (MODE == 5) {   // one 32-byte load, no L1 allocation
                 asm volatile("ld.global.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(*(uint64_t*)&a[i].x), "=l"(*(uint64_t*)&a[i].z), "=l"(*(uint64_t*)&b[i].x), "=l"(*(uint64_t*)&b[i].z) : "l"(p));
+            } else if (MODE == 6) {   // one 128-byte line per QUAD: lane j of the quad loads sector j (one coalesced request)
+                const uint64_t sq = __shfl_sync(0xFFFFFFFFu, s[i], threadIdx.x & 28);
+                const uint4* pl = buf + 2 * ((sq & ~3ull) + (threadIdx.x & 3));
+                asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(*(uint64_t*)&a[i].x), "=l"(*(uint64_t*)&a[i].z), "=l"(*(uint64_t*)&b[i].x), "=l"(*(uint64_t*)&b[i].z) : "l"(pl));
             } else {   // one 16-byte load only
                 asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a[i].x), "=r"(a[i].y), "=r"(a[i].z), "=r"(a[i].w) : "l"(p));
                 b[i] = a[i];
@@ -63,7 +67,7 @@ int main(int argc, char** argv) {
     const uint64_t n_loads = 1ull << 26;
     uint32_t* sink;
     CK(cudaSetDevice(0)); CK(cudaMalloc(&sink, 4));
-    const char* names[6] = {"ld.global.nc.L1::no_allocate 2x16B", "ld.global 2x16B", "ld.global.cg 2x16B", "ld.global 1x16B", "ld.global.v4.u64 1x32B", "ld.global.L1::no_allocate.v4.u64 1x32B"};
+    const char* names[7] = {"ld.global.nc.L1::no_allocate 2x16B", "ld.global 2x16B", "ld.global.cg 2x16B", "ld.global 1x16B", "ld.global.v4.u64 1x32B", "ld.global.L1::no_allocate.v4.u64 1x32B", "quad: 4 lanes x 32B = one 128B line (G lane-loads/s; lines/s = this / 4)"};
     if (n >= 2) CK(cudaDeviceEnablePeerAccess(1, 0));
     size_t gran = 0; cudaDeviceGetLimit(&gran, cudaLimitMaxL2FetchGranularity); printf("default L2 fetch granularity %zu\n", gran);
     if (argc > 1) { cudaError_t e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, atoi(argv[1])); cudaDeviceGetLimit(&gran, cudaLimitMaxL2FetchGranularity); printf("set %s -> %s, now %zu\n", argv[1], cudaGetErrorString(e), gran); }
@@ -74,9 +78,9 @@ int main(int argc, char** argv) {
             CK(cudaSetDevice(where)); CK(cudaMalloc(&buf, bytes)); CK(cudaMemset(buf, 1, bytes)); CK(cudaDeviceSynchronize());
             CK(cudaSetDevice(0));
             const int blocks = 148 * 8;
-            float t[6] = {run<0>(buf, n_sectors, n_loads, sink, blocks), run<1>(buf, n_sectors, n_loads, sink, blocks), run<2>(buf, n_sectors, n_loads, sink, blocks),
-                          run<3>(buf, n_sectors, n_loads, sink, blocks), run<4>(buf, n_sectors, n_loads, sink, blocks), run<5>(buf, n_sectors, n_loads, sink, blocks)};
-            for (int m = 0; m < 6; ++m) printf("%s %2llu GiB  %-40s %7.2f G loads/s\n", where ? "peer " : "local", (unsigned long long)gib, names[m], n_loads / t[m] / 1e6);
+            float t[7] = {run<0>(buf, n_sectors, n_loads, sink, blocks), run<1>(buf, n_sectors, n_loads, sink, blocks), run<2>(buf, n_sectors, n_loads, sink, blocks),
+                          run<3>(buf, n_sectors, n_loads, sink, blocks), run<4>(buf, n_sectors, n_loads, sink, blocks), run<5>(buf, n_sectors, n_loads, sink, blocks), run<6>(buf, n_sectors, n_loads, sink, blocks)};
+            for (int m = 0; m < 7; ++m) printf("%s %2llu GiB  %-40s %7.2f G loads/s\n", where ? "peer " : "local", (unsigned long long)gib, names[m], n_loads / t[m] / 1e6);
             CK(cudaSetDevice(where)); CK(cudaFree(buf));
         }
     return 0;
