@@ -26,6 +26,10 @@ def build(force=False, verbose=False):
     if os.environ.get("KM_PHASE_TIMERS") and "-DKM_PHASE_TIMERS" not in NVCC_FLAGS:
         NVCC_FLAGS.append("-DKM_PHASE_TIMERS")
         force = True
+    extra = os.environ.get("KM_NVCC_EXTRA", "").split()        # experiments: e.g. KM_NVCC_EXTRA=-DKM_WALK_WARPS=1
+    if extra and not set(extra) <= set(NVCC_FLAGS):
+        NVCC_FLAGS.extend(extra)
+        force = True
     if not force and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

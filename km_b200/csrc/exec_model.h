@@ -112,6 +112,8 @@ KM_HD uint8_t load_cg8(const uint8_t* p) { return __ldcg(p); }
 KM_HD int clz64(uint64_t x) { return __clzll((long long)x); }
 KM_HD int clz32(uint32_t x) { return __clz((int)x); }
 KM_HD int ffs32(uint32_t x) { return __ffs((int)x); }
+KM_HD int ffs64(uint64_t x) { return __ffsll((long long)x); }
+KM_HD uint64_t atomic_or64(uint64_t* p, uint64_t v) { return atomicOr(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v); }
 KM_HD uint64_t mulhi64(uint64_t a, uint64_t b) { return __umul64hi(a, b); }
 KM_HD float add_f32(float a, float b) { return __fadd_rn(a, b); }
 #else
@@ -150,6 +152,8 @@ KM_HD uint8_t load_cg8(const uint8_t* p) { return *p; }
 KM_HD int clz64(uint64_t x) { return x ? __builtin_clzll(x) : 64; }
 KM_HD int clz32(uint32_t x) { return x ? __builtin_clz(x) : 32; }
 KM_HD int ffs32(uint32_t x) { return __builtin_ffs((int)x); }
+KM_HD int ffs64(uint64_t x) { return __builtin_ffsll((long long)x); }
+KM_HD uint64_t atomic_or64(uint64_t* p, uint64_t v) { uint64_t o = *p; *p = o | v; return o; }
 KM_HD uint64_t mulhi64(uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)a * b) >> 64); }
 KM_HD float add_f32(float a, float b) { volatile float r = a + b; return r; }
 #endif

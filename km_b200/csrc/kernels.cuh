@@ -238,7 +238,9 @@ __global__ void __launch_bounds__(256) km_get_child_kernel(TableView T, const ui
 // ---- K3: walk, one WARP per target ----------------------------------------------------------
 // Two launches: the shared-memory walk takes every target of ordinary size (walk_small.h); the
 // general walk, whose per-target state lives in HBM, takes the targets the first one deferred.
+#ifndef KM_WALK_WARPS
 #define KM_WALK_WARPS 4
+#endif
 #define KM_PROBE_WARPS 8
 // K3a: level 0 of every walk, one warp per 32 reference k-mers, flat over the batch
 __global__ void __launch_bounds__(32 * KM_PROBE_WARPS, 4) km_ref_probe_kernel(TableView T, WalkView W, FindParams P) {

@@ -5,11 +5,17 @@
 // the smallest unit HBM3e delivers -- each holding two (key, count) records:
 //     +0  key[0]  u64      +16 count[0] u32     +24 8 bytes unused
 //     +8  key[1]  u64      +20 count[1] u32
-// A lookup reads ONE sector with one 256-bit load in the common case; only a
-// full bucket that does not hold the key forwards to the next bucket (linear probing at
-// bucket granularity).  Bucket = mulhi64(mix64(key), n_buckets): no power-of-two
-// constraint, so a 2e9-key table can sit at any load factor the HBM budget allows.
-// Empty key = ~0 (never a valid canonical k-mer for k <= 31).
+//     +24 hop u64: bit d (0..62) = "a key whose HOME is this bucket lives in bucket home+1+d";
+//                  bit 63 = "... lives further away" (never seen at load 0.5; linear scan)
+// A lookup reads ONE sector with one 256-bit load in the common case -- for an ABSENT key too: the
+// hop word of the home bucket names every other bucket that holds one of its keys (hopscotch-style),
+// so a full home bucket with hop == 0 answers "absent" at once, and otherwise exactly the named
+// buckets are read (92 % / 8 % one / two dependent reads at load 0.47; without the hop word a
+// full bucket forwarded to its neighbour 26 % of the time and chains of 3-4 dependent reads were
+// common -- that, not bandwidth, was what a walk level waited for).  Insertion is linear probing at
+// bucket granularity from the home bucket; placing a key away from home sets the home's hop bit.
+// Bucket = mulhi64(mix64(key), n_buckets): no power-of-two constraint, so a 2e9-key table can sit
+// at any load factor the HBM budget allows.  Empty key = ~0 (never a valid canonical k-mer for k <= 31).
 #pragma once
 #include "kmer.h"
 
@@ -22,8 +28,9 @@ namespace km {
 struct alignas(32) Bucket {
     uint64_t key[KM_BUCKET_SLOTS];
     uint32_t count[KM_BUCKET_SLOTS];
-    uint32_t pad[2];
+    uint32_t pad[2];          // the 64-bit hop word (see above), low half first
 };
+#define KM_HOP_FAR 0x8000000000000000ull
 
 #define KM_MAX_SHARDS 8
 
@@ -62,16 +69,52 @@ KM_HD const Bucket* locate(const TableView& t, uint64_t key, uint64_t* b) {
 // (tools/probes/peer_gather.cu): the memory system serves ~36 G random REQUESTS/s whatever their
 // size, so a bucket fetched as two 16-byte loads -- the L1-bypassing kind does not merge them -- tops
 // out at 18 G buckets/s, one 32-byte load at 36 G/s (and 6.6 vs 3.3 G/s from a peer GPU over NVLink).
-KM_HD void load_bucket(const Bucket* b, uint64_t& k0, uint64_t& k1, uint32_t& c0, uint32_t& c1) {
-    uint64_t cc, pad;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(k0), "=l"(k1), "=l"(cc), "=l"(pad) : "l"(b));
+KM_HD void load_bucket(const Bucket* b, uint64_t& k0, uint64_t& k1, uint32_t& c0, uint32_t& c1, uint64_t& hop) {
+    uint64_t cc;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(k0), "=l"(k1), "=l"(cc), "=l"(hop) : "l"(b));
     c0 = (uint32_t)cc; c1 = (uint32_t)(cc >> 32);
 }
 #else
-KM_HD void load_bucket(const Bucket* b, uint64_t& k0, uint64_t& k1, uint32_t& c0, uint32_t& c1) {
+KM_HD void load_bucket(const Bucket* b, uint64_t& k0, uint64_t& k1, uint32_t& c0, uint32_t& c1, uint64_t& hop) {
     k0 = b->key[0]; k1 = b->key[1]; c0 = b->count[0]; c1 = b->count[1];
+    hop = (uint64_t)b->pad[0] | ((uint64_t)b->pad[1] << 32);
 }
 #endif
+KM_HD void load_bucket(const Bucket* b, uint64_t& k0, uint64_t& k1, uint32_t& c0, uint32_t& c1) {
+    uint64_t hop;
+    load_bucket(b, k0, k1, c0, c1, hop);
+}
+
+// The rest of a lookup once the HOME bucket `b` of `key` has been read (k0..hop): the key is in the home
+// bucket, in one of the buckets its hop word names, or absent.
+KM_HD uint32_t finish_lookup(const Bucket* base, uint64_t n_buckets, uint64_t b, uint64_t key, uint64_t k0, uint64_t k1,
+                             uint32_t c0, uint32_t c1, uint64_t hop) {
+    if (k0 == key) return c0;
+    if (k1 == key) return c1;
+    if (hop & KM_HOP_FAR) {                      // a key of this home sits 64+ buckets away: linear scan from there
+        uint64_t bb = (b + 64) % n_buckets;
+        for (uint64_t tries = 0; tries < n_buckets; ++tries) {
+            uint64_t f0, f1; uint32_t d0, d1;
+            load_bucket(base + bb, f0, f1, d0, d1);
+            if (f0 == key) return d0;
+            if (f1 == key) return d1;
+            if (f0 == KM_EMPTY_KEY || f1 == KM_EMPTY_KEY) break;
+            if (++bb == n_buckets) bb = 0;
+        }
+        hop &= ~KM_HOP_FAR;
+    }
+    while (hop) {
+        const int d = ffs64(hop) - 1;
+        hop &= hop - 1;
+        uint64_t bb = b + 1 + (uint64_t)d;
+        if (bb >= n_buckets) bb -= n_buckets;
+        uint64_t f0, f1; uint32_t d0, d1;
+        load_bucket(base + bb, f0, f1, d0, d1);
+        if (f0 == key) return d0;
+        if (f1 == key) return d1;
+    }
+    return 0;
+}
 
 // ---- family lines (TableView::lines == 1) ---------------------------------------------------------------
 // Measured on B200: a random 32-byte read costs a whole 128-byte DRAM line (ncu: 4 L2 sectors, 129 B of DRAM
@@ -262,14 +305,9 @@ KM_HD int line_insert(const TableView& t, uint64_t fam, uint64_t key, uint32_t c
 KM_HD uint32_t table_lookup_key(const TableView& t, uint64_t key) {
     uint64_t b;
     const Bucket* base = locate(t, key, &b);
-    for (;;) {
-        uint64_t k0, k1; uint32_t c0, c1;
-        load_bucket(base + b, k0, k1, c0, c1);
-        if (k0 == key) return c0;
-        if (k1 == key) return c1;
-        if (k0 == KM_EMPTY_KEY || k1 == KM_EMPTY_KEY) return 0;
-        if (++b == t.n_buckets) b = 0;
-    }
+    uint64_t k0, k1, hop; uint32_t c0, c1;
+    load_bucket(base + b, k0, k1, c0, c1, hop);
+    return finish_lookup(base, t.n_buckets, b, key, k0, k1, c0, c1, hop);
 }
 
 // forward-strand packed k-mer -> count: Jellyfish.query (km/utils/Jellyfish.py:47-53)
@@ -284,7 +322,7 @@ KM_HD uint32_t table_query(const TableView& t, uint64_t fwd) {
 // lookups of Jellyfish.get_child this way), then the rare forwarding loop per query.
 template <int N>
 KM_HD void table_query_multi(const TableView& T, const uint64_t (&fwd)[N], uint32_t (&out)[N]) {
-    uint64_t key[N], b[N], k0[N], k1[N];
+    uint64_t key[N], b[N], k0[N], k1[N], hop[N];
     uint32_t c0[N], c1[N];
     const Bucket* base[N];
 #pragma unroll
@@ -294,25 +332,15 @@ KM_HD void table_query_multi(const TableView& T, const uint64_t (&fwd)[N], uint3
         base[i] = locate(T, key[i], &b[i]);
     }
 #pragma unroll
-    for (int i = 0; i < N; ++i) load_bucket(base[i] + b[i], k0[i], k1[i], c0[i], c1[i]);
+    for (int i = 0; i < N; ++i) load_bucket(base[i] + b[i], k0[i], k1[i], c0[i], c1[i], hop[i]);
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-        uint32_t r = 0;
-        for (;;) {
-            if (k0[i] == key[i]) { r = c0[i]; break; }
-            if (k1[i] == key[i]) { r = c1[i]; break; }
-            if (k0[i] == KM_EMPTY_KEY || k1[i] == KM_EMPTY_KEY) break;
-            if (++b[i] == T.n_buckets) b[i] = 0;      // rare: full bucket without the key
-            load_bucket(base[i] + b[i], k0[i], k1[i], c0[i], c1[i]);
-        }
-        out[i] = r;
-    }
+    for (int i = 0; i < N; ++i) out[i] = finish_lookup(base[i], T.n_buckets, b[i], key[i], k0[i], k1[i], c0[i], c1[i], hop[i]);
 }
 
 // N independent lookups in flight, only where `mask` has the bit set (others return 0).
 template <int N>
 KM_HD void table_query_masked(const TableView& T, const uint64_t (&fwd)[N], uint32_t mask, uint32_t (&out)[N]) {
-    uint64_t key[N], b[N], k0[N], k1[N];
+    uint64_t key[N], b[N], k0[N], k1[N], hop[N];
     uint32_t c0[N], c1[N];
     const Bucket* base[N];
 #pragma unroll
@@ -323,21 +351,10 @@ KM_HD void table_query_masked(const TableView& T, const uint64_t (&fwd)[N], uint
     }
 #pragma unroll
     for (int i = 0; i < N; ++i)
-        if (mask & (1u << i)) load_bucket(base[i] + b[i], k0[i], k1[i], c0[i], c1[i]);
+        if (mask & (1u << i)) load_bucket(base[i] + b[i], k0[i], k1[i], c0[i], c1[i], hop[i]);
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-        uint32_t r = 0;
-        if (mask & (1u << i)) {
-            for (;;) {
-                if (k0[i] == key[i]) { r = c0[i]; break; }
-                if (k1[i] == key[i]) { r = c1[i]; break; }
-                if (k0[i] == KM_EMPTY_KEY || k1[i] == KM_EMPTY_KEY) break;
-                if (++b[i] == T.n_buckets) b[i] = 0;      // rare: full bucket without the key
-                load_bucket(base[i] + b[i], k0[i], k1[i], c0[i], c1[i]);
-            }
-        }
-        out[i] = r;
-    }
+    for (int i = 0; i < N; ++i)
+        out[i] = (mask & (1u << i)) ? finish_lookup(base[i], T.n_buckets, b[i], key[i], k0[i], k1[i], c0[i], c1[i], hop[i]) : 0u;
 }
 
 // Lookups that belong together (the successors of one parent, plus the parent itself): `fam` is their
@@ -423,23 +440,31 @@ KM_HD int table_insert(const TableView& t, uint64_t key, uint32_t count, int mod
     }
     const uint64_t h = key_hash(key);
     if (shard_of_hash(h, t.n_shards) != t.my_shard) return 0;
-    uint64_t b = bucket_of_hash(h, t.n_shards, t.n_buckets);
+    const uint64_t home = bucket_of_hash(h, t.n_shards, t.n_buckets);
+    uint64_t b = home;
     for (uint64_t tries = 0; tries < t.n_buckets; ++tries) {
         Bucket* bk = t.buckets + b;
         for (int s = 0; s < KM_BUCKET_SLOTS; ++s) {
             uint64_t cur = load_cg64(&bk->key[s]);
+            int placed = -1;
             if (cur == KM_EMPTY_KEY) {
                 cur = atomic_cas64(&bk->key[s], KM_EMPTY_KEY, key);
                 if (cur == KM_EMPTY_KEY) {
                     if (mode == KM_INSERT_ADD) atomic_add32(&bk->count[s], count);
                     else bk->count[s] = count;
-                    return 1;
+                    placed = 1;
                 }
             }
-            if (cur == key) {
+            if (placed < 0 && cur == key) {
                 if (mode == KM_INSERT_ADD) atomic_add32(&bk->count[s], count);
                 else if (mode == KM_INSERT_OVERWRITE) bk->count[s] = count;
-                return 0;
+                placed = 0;
+            }
+            if (placed >= 0) {
+                // away from home: the home bucket's hop word must name this bucket (every inserter of the key sets
+                // the same bit, so whoever finishes last leaves it set)
+                if (tries) atomic_or64(reinterpret_cast<uint64_t*>(t.buckets[home].pad), tries <= 63 ? 1ull << (tries - 1) : KM_HOP_FAR);
+                return placed;
             }
         }
         if (++b == t.n_buckets) b = 0;

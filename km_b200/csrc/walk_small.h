@@ -193,6 +193,114 @@ KM_HD void ws_child(const Ctx& ctx, const WalkView& W, const TargetGeom& g, Walk
     }
 }
 
+#if KM_DEVICE_BUILD
+// node index of `key` or -1; *empty = the slot where the probe ended (where the key would go)
+KM_HD int ws_find_slot(const WalkSmall& M, uint64_t key, int L, int k, uint32_t* empty) {
+    uint32_t s = ws_hash(key);
+    for (;;) {
+        const uint32_t v = (load_shared_volatile32(&M.slot[s >> 1]) >> ((s & 1) * 16)) & 0xFFFFu;
+        if (v == 0) { *empty = s; return -1; }
+        if (ws_node_key(M, (int)v - 1, L, k) == key) return (int)v - 1;
+        s = (s + 1) & (KM_WS_HASH - 1);
+    }
+}
+
+// Counts prefetched one level ahead (ws_chain_level): valid on lanes 0..3 for the children of `node`.
+struct ChainPrefetch { int node; uint32_t cnt; };
+
+// One level whose frontier is a SINGLE novel node q -- what a walk looks like for most of its life (a
+// variant is a chain of novel k-mers).  Same rules as the general level below (Jellyfish.py:61-72,
+// MutationFinder.py:140-163), but with one node there is nothing to elect or to combine: every lane
+// follows the same control flow on the same shared-memory words, lane 0 does the stores, and no atomic,
+// match or fence is needed.  The table is asked one level AHEAD as well: lanes 0..3 fetch the four
+// children, lanes 4..19 the sixteen grandchildren in the same round trip, so when the level yields exactly
+// one new node the next level starts with its counts already in registers (`pf`) -- one HBM latency per
+// two levels of the chain.
+KM_HD void ws_chain_level(const TableView& T, const WalkView& W, const FindParams& P, const TargetGeom& g, WalkSmall& M,
+                          int novel_cap, int q, ChainPrefetch& pf, uint32_t& st, unsigned& nlook) {
+    const int lane = threadIdx.x & 31, L = g.L, k = T.k;
+    const uint32_t meta = M.nmeta[q - L];
+    const int depth = (int)(meta >> 8), breaks = (int)(meta & 255u);
+    if (depth > P.max_stack) {                                                   // MutationFinder.py:140-141
+        st |= KM_ST_TOUCHED_LIMIT;
+        if (lane < 4) M.kid[q - L][lane] = 0;
+        pf.node = -1;
+        return;
+    }
+    const uint64_t parent = M.nk[q - L];
+    const int c = lane & 3;
+    uint32_t cnt, ahead = 0;
+    const bool loaded = pf.node != q;
+    if (loaded) {
+        const bool live = lane < 20;
+        const uint64_t mine = lane < 4 ? parent : succ_kmer(parent, (lane - 4) >> 2, T.kmask);
+        const uint64_t ck = succ_kmer(mine, c, T.kmask);
+        uint32_t r = 0;
+        if (T.lines) r = quad_line_query(T, family_of_suffix(T, mine), T.canonical ? canonical(ck, T.k) : ck, live);
+        else if (live) r = table_query(T, ck);
+        nlook += live ? 1u : 0u;
+        cnt = r; ahead = r;
+    } else {
+        cnt = pf.cnt;
+    }
+    // Jellyfish.py:61-72 over the four counts (every lane computes the same)
+    uint32_t cc[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) cc[j] = (uint32_t)__shfl_sync(0xFFFFFFFFu, (int)cnt, j);
+    const uint64_t sum = (uint64_t)cc[0] + cc[1] + cc[2] + cc[3];
+    double thr = (double)sum * P.ratio;
+    if (thr < (double)P.count) thr = (double)P.count;
+    uint32_t pass = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) pass |= ((double)cc[j] >= thr) ? (1u << j) : 0u;
+    int nb = breaks;
+    if (popc32(pass) > 1) {                                                      // MutationFinder.py:153-156
+        nb += 1;
+        if (nb > P.max_break) { st |= KM_ST_TOUCHED_LIMIT; pass = 0; }
+    }
+    const uint32_t child_meta = pack_meta(depth + 1, nb);
+    int nn = (int)load_shared_volatile32(reinterpret_cast<const uint32_t*>(&M.n_nodes));
+    int n_new = 0, new_c = 0, new_idx = 0;
+    uint16_t kid[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (!((pass >> j) & 1u)) continue;
+        const uint64_t child = succ_kmer(parent, j, T.kmask);
+        uint32_t slot = 0;
+        int idx = ws_find_slot(M, child, L, k, &slot);
+        if (idx < 0) {
+            if (nn - L >= novel_cap) {                                           // as ws_child: the walk is redone elsewhere
+                if (lane == 0) M.flags |= 1u;
+                break;
+            }
+            idx = nn++;
+            if (lane == 0) {
+                M.nk[idx - L] = child;
+                M.nmeta[idx - L] = child_meta;
+                M.alive[idx - L] = 1;
+                M.slot[slot >> 1] |= (uint32_t)(idx + 1) << ((slot & 1) * 16);
+                W.node_kmer[g.nbase + idx] = child;
+                W.node_count[g.nbase + idx] = cc[j];
+            }
+            __syncwarp();
+            n_new += 1; new_c = j; new_idx = idx;
+        } else if (idx >= L) {
+            if (lane == 0 && child_meta < M.nmeta[idx - L]) M.nmeta[idx - L] = child_meta;
+            __syncwarp();
+        }
+        kid[j] = (uint16_t)(idx + 1);
+    }
+    if (lane == 0) {
+        M.kid[q - L][0] = kid[0]; M.kid[q - L][1] = kid[1]; M.kid[q - L][2] = kid[2]; M.kid[q - L][3] = kid[3];
+        M.n_nodes = nn;
+    }
+    // the counts of the new node's children came back with this level's loads
+    const uint32_t next = (uint32_t)__shfl_sync(0xFFFFFFFFu, (int)ahead, 4 + 4 * new_c + c);
+    if (loaded && n_new == 1) { pf.node = new_idx; pf.cnt = next; }
+    else pf.node = -1;
+}
+#endif
+
 // One warp walks target t.  Returns false when the target was deferred to the general kernel.
 template <class Ctx>
 KM_HD bool walk_small_target(const Ctx& ctx, const TableView& T, const WalkView& W, const FindParams& P, int t, WalkSmall& M) {
@@ -258,10 +366,15 @@ KM_HD bool walk_small_target(const Ctx& ctx, const TableView& T, const WalkView&
     int lo = L;
     int hi = (int)load_shared_volatile32(reinterpret_cast<const uint32_t*>(&M.n_nodes));
     if (hi - L > novel_cap) hi = L + novel_cap;
+#if KM_DEVICE_BUILD
+    ChainPrefetch pf;
+    pf.node = -1; pf.cnt = 0;
+#endif
     while (lo < hi && !(load_shared_volatile32(&M.flags) & 1u)) {
 #if KM_DEVICE_BUILD
+        if (hi - lo == 1) ws_chain_level(T, W, P, g, M, novel_cap, lo, pf, st, nlook);
         // four lanes per frontier node, one successor letter each: one lookup per lane
-        for (int base = lo; base < hi; base += 8) {
+        else for (int base = lo; base < hi; base += 8) {
             const int q = base + (lane >> 2), c = lane & 3;
             bool expand = false;
             uint64_t ck = 0;

@@ -355,7 +355,9 @@ def test_full_size_panel_properties(engine):
     n_ref = np.array([len(s) - 30 for s in panel.targets[:2000]])
     algorithmic = n_ref + 4 * (res.n_nodes.astype(np.int64) - 2)
     assert (res.lookups.astype(np.int64) >= algorithmic - (n_ref - 1)).all()
-    assert (res.lookups.astype(np.int64) <= algorithmic + 4 * 64).all()
+    # (a chain level asks for the sixteen grandchildren along with the four children: up to 20 per novel node)
+    n_novel = res.n_nodes.astype(np.int64) - 2 - n_ref
+    assert (res.lookups.astype(np.int64) <= algorithmic + 16 * n_novel + 4 * 64).all()
 
 
 def test_table_counted_from_reads_equals_host_count(engine):
