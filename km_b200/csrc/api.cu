@@ -16,6 +16,9 @@
 #include <string>
 #include <thread>
 #include <vector>
+#include <atomic>
+#include <tuple>
+#include <chrono>
 
 #include <cuda.h>        // driver-API TYPES only: the entry points are fetched at run time (vmm_load)
 #include <unistd.h>
@@ -666,6 +669,49 @@ extern "C" int km_get_child_batch(km_table* t, const uint64_t* kmers, uint64_t n
     return 0;
 }
 
+// Host byte buffers recycled between calls: a fresh 12 MB buffer costs more in first-touch page faults than
+// the text that goes into it costs to format.  Vectors keep their capacity while they sit in the cache.
+struct VecCache {
+    std::mutex m;
+    std::vector<std::vector<char>> idle;
+    size_t max_idle;
+    explicit VecCache(size_t n) : max_idle(n) {}
+    // the smallest idle vector that holds `want`, else the largest; `keep_size`: handed out as it came back
+    // (a text buffer is used as raw storage: growing it through resize() would zero-fill it on every call)
+    std::vector<char> get(size_t want, bool keep_size = false) {
+        std::lock_guard<std::mutex> g(m);
+        if (idle.empty()) return std::vector<char>();
+        size_t best = 0;
+        for (size_t i = 1; i < idle.size(); ++i) {
+            const size_t a = idle[i].capacity(), b = idle[best].capacity();
+            if ((a >= want && (b < want || a < b)) || (a < want && b < want && a > b)) best = i;
+        }
+        std::vector<char> v = std::move(idle[best]);
+        idle.erase(idle.begin() + (long)best);
+        if (!keep_size) v.clear();
+        return v;
+    }
+    void put(std::vector<char>&& v) {
+        if (!v.capacity() || v.capacity() > ((size_t)256 << 20)) return;
+        std::lock_guard<std::mutex> g(m);
+        if (idle.size() < max_idle) idle.push_back(std::move(v));
+    }
+};
+static VecCache& piece_cache() { static VecCache c(128); return c; }
+static VecCache& text_cache() { static VecCache c(8); return c; }
+// the text a result holds: a cached vector used as a plain buffer
+struct TextBuf {
+    std::vector<char> v;
+    char* get() { return v.data(); }
+    void reset() { if (v.capacity()) text_cache().put(std::move(v)); v = std::vector<char>(); }
+    void reset(size_t bytes) {
+        reset();
+        v = text_cache().get(bytes, true);
+        if (v.size() < bytes) v.resize(bytes + bytes / 8);     // first use of this size: the only time it is zero-filled
+    }
+    ~TextBuf() { reset(); }
+};
+
 // ---- find_mutation batch ------------------------------------------------------------------------
 struct km_result {
     int n_targets = 0, k = 31;
@@ -687,7 +733,7 @@ struct km_result {
     unsigned long long bytes_h2d = 0, bytes_d2h = 0;
     // the formatted text of all targets is built once and kept (km_result_format_all / km_result_text)
     mutable std::string fmt_key;
-    mutable std::unique_ptr<char[]> text;
+    mutable TextBuf text;
     mutable int64_t text_len = -1;
     // km_find_text: the result of a pipelined run keeps its sub-batches and the joined text
     std::vector<std::unique_ptr<km_result>> parts;
@@ -725,6 +771,7 @@ struct km_plan {
     int n_launches = 0, n_retries = 0;
     bool launched = false;
     unsigned long long bytes_h2d = 0;
+    size_t upload_bytes = 0;      // span of the input block on the device (plan_layout)
     cudaStream_t stream = nullptr, side = nullptr;      // the table's own unless the plan runs on a lane
     cudaEvent_t* ev = nullptr;
     cudaEvent_t fork = nullptr, join = nullptr;
@@ -779,9 +826,13 @@ static int plan_layout(km_plan* p) {
     WalkView& W = p->W;
     W.n_targets = n;
     W.codes = A.take<uint8_t>(n_code);
+    // codes .. chunk_start are taken in the order (and with the alignment) plan_upload uses for its pinned staging
+    // block, so the whole input goes up with ONE copy
     W.seq_off = A.take<int64_t>(n + 1); W.node_off = A.take<int64_t>(n + 1); W.hash_off = A.take<int64_t>(n + 1);
+    W.pack_off = A.take<int64_t>(n + 1);
     W.chunk_target = A.take<int32_t>(n_chunks); W.chunk_start = A.take<int32_t>(n_chunks); W.n_chunks = (int)n_chunks;
-    W.pack = A.take<uint32_t>((size_t)n_pack); W.pack_off = A.take<int64_t>(n + 1); W.pre_bad = A.take<uint8_t>(n);
+    p->upload_bytes = (size_t)((const char*)(W.chunk_start + n_chunks) - (const char*)W.codes);
+    W.pack = A.take<uint32_t>((size_t)n_pack); W.pre_bad = A.take<uint8_t>(n);
     W.node_kmer = A.take<uint64_t>(n_node); W.node_count = A.take<uint32_t>(n_node);
     W.node_slot = A.take<uint32_t>(n_node); W.node_kid = A.take<uint32_t>(4 * n_node);
     W.hkey = A.take<uint64_t>(n_hash); W.hval = A.take<uint32_t>(n_hash); W.hmeta = A.take<uint32_t>(n_hash);
@@ -829,15 +880,9 @@ static int plan_upload(km_plan* p, cudaStream_t s) {
     memcpy(h_node_off, p->node_off.data(), 8 * (n + 1));
     memcpy(h_hash_off, p->hash_off.data(), 8 * (n + 1));
     CU(cudaEventRecord(p->ev[0], s));
-    CU(cudaMemcpyAsync((void*)p->W.codes, h_codes, p->n_code, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync((void*)p->W.seq_off, h_seq_off, 8 * (n + 1), cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync((void*)p->W.node_off, h_node_off, 8 * (n + 1), cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync((void*)p->W.hash_off, h_hash_off, 8 * (n + 1), cudaMemcpyHostToDevice, s));
-    if (n_chunks) {
-        CU(cudaMemcpyAsync((void*)p->W.chunk_target, h_ct, 4 * n_chunks, cudaMemcpyHostToDevice, s));
-        CU(cudaMemcpyAsync((void*)p->W.chunk_start, h_cs, 4 * n_chunks, cudaMemcpyHostToDevice, s));
-    }
-    CU(cudaMemcpyAsync((void*)p->W.pack_off, h_pack_off, 8 * (n + 1), cudaMemcpyHostToDevice, s));
+    if ((size_t)((const char*)(h_cs + n_chunks) - (const char*)h_codes) != p->upload_bytes)
+        return fail(KM_E_ARG, "internal: staging block and device input block differ in layout");
+    CU(cudaMemcpyAsync((void*)p->W.codes, h_codes, p->upload_bytes, cudaMemcpyHostToDevice, s));
     if (n) {
         km_encode_kernel<<<(n + 7) / 8, 256, 0, s>>>(const_cast<uint8_t*>(p->W.codes), p->W.seq_off, const_cast<uint32_t*>(p->W.pack),
                                                      p->W.pack_off, const_cast<uint8_t*>(p->W.pre_bad), n);
@@ -893,22 +938,23 @@ static int plan_download(km_plan* p, cudaStream_t s, km_result* res, bool want_g
     const WalkView& W = p->W;
     const ResultView& R = p->R;
     res->n_targets = n; res->k = t->k;
-    if (int rc = res->head.reserve(t->pool, 36 * (size_t)n + 64 * 10)) return rc;
-    res->status = res->head.take<uint32_t>(n); res->n_nodes = res->head.take<int32_t>(n);
-    res->path_count = res->head.take<int32_t>(n); res->path_first = res->head.take<int32_t>(n);
-    res->row_count = res->head.take<int32_t>(n); res->row_first = res->head.take<int32_t>(n);
-    res->lookups = res->head.take<unsigned long long>(n); res->used = res->head.take<unsigned long long>(4);
+    // the per-target state and result ints sit back to back on the device (plan_layout): ONE copy brings the
+    // block into pinned memory and the result's arrays are views into it
+    if (int rc = res->head.reserve(t->pool, p->state_bytes + 512)) return rc;
+    Span<char> blk = res->head.take<char>(p->state_bytes);
+    auto view = [&](const void* dev_ptr) { return blk.data() + ((const char*)dev_ptr - p->state0); };
+    res->status.p = (uint32_t*)view(W.status); res->status.n = (size_t)n;
+    res->n_nodes.p = (int32_t*)view(R.t_n); res->n_nodes.n = (size_t)n;
+    res->path_count.p = (int32_t*)view(R.t_n_paths); res->path_count.n = (size_t)n;
+    res->path_first.p = (int32_t*)view(R.t_path_first); res->path_first.n = (size_t)n;
+    res->row_count.p = (int32_t*)view(R.t_n_rows); res->row_count.n = (size_t)n;
+    res->row_first.p = (int32_t*)view(R.t_row_first); res->row_first.n = (size_t)n;
+    res->lookups.p = (unsigned long long*)view(W.lookups); res->lookups.n = (size_t)n;
+    res->used = res->head.take<unsigned long long>(4);
     unsigned long long* used = res->used.data();
     used[0] = used[1] = used[2] = used[3] = 0;
     if (n) {
-        // per-target state and result ints sit back to back on the device (plan_layout)
-        CU(cudaMemcpyAsync(res->status.data(), W.status, 4 * n, cudaMemcpyDeviceToHost, s));
-        CU(cudaMemcpyAsync(res->n_nodes.data(), R.t_n, 4 * n, cudaMemcpyDeviceToHost, s));
-        CU(cudaMemcpyAsync(res->path_count.data(), R.t_n_paths, 4 * n, cudaMemcpyDeviceToHost, s));
-        CU(cudaMemcpyAsync(res->path_first.data(), R.t_path_first, 4 * n, cudaMemcpyDeviceToHost, s));
-        CU(cudaMemcpyAsync(res->row_count.data(), R.t_n_rows, 4 * n, cudaMemcpyDeviceToHost, s));
-        CU(cudaMemcpyAsync(res->row_first.data(), R.t_row_first, 4 * n, cudaMemcpyDeviceToHost, s));
-        CU(cudaMemcpyAsync(res->lookups.data(), W.lookups, 8 * n, cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(blk.data(), p->state0, p->state_bytes, cudaMemcpyDeviceToHost, s));
         CU(cudaMemcpyAsync(used, R.used, 32, cudaMemcpyDeviceToHost, s));
     }
     CU(cudaStreamSynchronize(s));
@@ -938,7 +984,7 @@ static int plan_download(km_plan* p, cudaStream_t s, km_result* res, bool want_g
         }
     }
     res->bytes_h2d = p->bytes_h2d;
-    res->bytes_d2h = 36ull * n + 32 + 20ull * n_paths + sizeof(Row) * n_rows + n_seq +
+    res->bytes_d2h = (unsigned long long)p->state_bytes + 32 + 20ull * n_paths + sizeof(Row) * n_rows + n_seq +
                      (want_graph ? 4ull * n_pool + 12ull * p->n_node : 0ull);
     res->text_len = -1; res->text.reset(); res->fmt_key.clear();
     CU(cudaEventRecord(p->ev[4], s));
@@ -1209,7 +1255,7 @@ static void format_rows_of(const km_result* r, int32_t tg, const char* db_name, 
         need += db_len + qn_len + 256 + (size_t)(w.del_len + w.ins_len) + (size_t)(w.var_end - w.var_begin + k) +
                 (size_t)(w.ref_end - w.ref_begin + k);
     }
-    arena.resize(need);
+    if (arena.size() < need) arena.resize(need + need / 2);
     char* o = arena.data();
     for (int i = 0; i < nrow; ++i) {
         const km_row& w = r->rows[r->row_first[tg] + i];
@@ -1252,7 +1298,7 @@ static void format_rows_of(const km_result* r, int32_t tg, const char* db_name, 
     // type, Min_coverage; a key that is a prefix of the other sorts first (vs_ref has one word, a
     // cluster three, but those never tie on the first word).
     if (nrow > 1) {
-        std::stable_sort(rows.begin(), rows.end(), [&](const FmtRow& x, const FmtRow& y) {
+        auto less = [&](const FmtRow& x, const FmtRow& y) {
             const km_row& a = *x.w; const km_row& b = *y.w;
             if (a.kind != b.kind) return a.kind < b.kind;                       // "vs_ref" > "cluster", reversed
             if (a.kind != 0) {
@@ -1265,7 +1311,17 @@ static void format_rows_of(const km_result* r, int32_t tg, const char* db_name, 
             if (c) return c < 0;
             // Min_coverage prints as a decimal integer; the counts are never negative
             return a.min_cov < b.min_cov;
-        });
+        };
+        if (nrow <= 16) {                   // stable insertion sort: no temporary buffer for the usual 2-3 rows
+            for (int i = 1; i < nrow; ++i) {
+                FmtRow cur = rows[(size_t)i];
+                int j = i;
+                while (j > 0 && less(cur, rows[(size_t)j - 1])) { rows[(size_t)j] = rows[(size_t)j - 1]; --j; }
+                rows[(size_t)j] = cur;
+            }
+        } else {
+            std::stable_sort(rows.begin(), rows.end(), less);
+        }
     }
     for (const FmtRow& f : rows) out.insert(out.end(), f.line, f.line + f.line_len);
 }
@@ -1316,7 +1372,7 @@ static int build_text(const km_result* r, const char* db_name, const char* names
     int64_t total = 0;
     std::vector<int64_t> at((size_t)nt);
     for (int i = 0; i < nt; ++i) { at[(size_t)i] = total; total += (int64_t)piece[(size_t)i].size(); }
-    r->text.reset(new char[(size_t)total + 1]);
+    r->text.reset((size_t)total + 1);
     char* dst = r->text.get();
     auto copy = [&](int w) { if (!piece[(size_t)w].empty()) memcpy(dst + at[(size_t)w], piece[(size_t)w].data(), piece[(size_t)w].size()); };
     if (nt == 1) copy(0);
@@ -1390,18 +1446,43 @@ struct Latch {
 // sub-batches that are all enqueued at once on their own streams; while the GPU works on the later
 // ones the host formats the rows of the earlier ones (pool threads), so copies, kernels and text
 // building overlap.  The text equals km_find_batch + km_result_format_all.
+// KM_TRACE=1: host-clock timeline of km_find_text on stderr (measurement aid)
+struct Trace {
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    std::mutex m;
+    std::vector<std::tuple<const char*, int, double>> ev;
+    Trace() : on(getenv("KM_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char* what, int sub = -1) {
+        if (!on) return;
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        std::lock_guard<std::mutex> g(m);
+        ev.emplace_back(what, sub, ms);
+    }
+    ~Trace() {
+        if (!on) return;
+        for (auto& e : ev) fprintf(stderr, "[km_trace] %8.3f ms  %s %d\n", std::get<2>(e), std::get<0>(e), std::get<1>(e));
+    }
+};
+
 extern "C" int km_find_text(km_table* t, const char* seqs, const int64_t* offsets, int32_t n, const km_find_params* params,
                             const char* db_name, const char* names, const int64_t* name_off, int32_t n_sub, km_result** out) {
     if (!t || !out || n < 0 || (n && (!seqs || !offsets || !names || !name_off)) || !params || !db_name)
         return fail(KM_E_ARG, "km_find_text: bad argument");
     CU(cudaSetDevice(t->device));
+    Trace tr;
     if (n_sub <= 0) n_sub = n >= 4096 ? 6 : n >= 1024 ? 2 : 1;
     n_sub = std::max(1, std::min(n_sub, std::max(1, n)));
     while ((int)t->lanes.size() < n_sub) {
         std::unique_ptr<km_table::Lane> L(new km_table::Lane());
         L->pin.host = true;
-        CU(cudaStreamCreateWithFlags(&L->stream, cudaStreamNonBlocking));
-        CU(cudaStreamCreateWithFlags(&L->side, cudaStreamNonBlocking));
+        // earlier sub-batches run at higher stream priority: they finish one after the other instead of all
+        // together at the end, so the host can format the first while the GPU works on the rest
+        int prio_lo = 0, prio_hi = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));          // lo = least urgent (0), hi = most urgent (negative)
+        const int prio = std::min(prio_lo, prio_hi + (int)t->lanes.size());
+        CU(cudaStreamCreateWithPriority(&L->stream, cudaStreamNonBlocking, prio));
+        CU(cudaStreamCreateWithPriority(&L->side, cudaStreamNonBlocking, prio));
         for (auto& e : L->ev) CU(cudaEventCreate(&e));
         CU(cudaEventCreateWithFlags(&L->fork, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&L->join, cudaEventDisableTiming));
@@ -1419,54 +1500,76 @@ extern "C" int km_find_text(km_table* t, const char* seqs, const int64_t* offset
     cut.push_back(n);
     km_result* res = new km_result();
     res->n_targets = n; res->k = t->k; res->has_graph = false;
-    std::vector<std::unique_ptr<km_plan>> plans;
-    std::vector<std::vector<int64_t>> offs((size_t)n_sub), noffs((size_t)n_sub);
     km_find_params prm = *params;
     prm.flags |= KM_FIND_NO_GRAPH;
-    // enqueue everything
-    for (int c = 0; c < n_sub; ++c) {
-        const int lo = cut[(size_t)c], hi = cut[(size_t)c + 1];
-        auto& o = offs[(size_t)c]; auto& no = noffs[(size_t)c];
-        o.resize((size_t)(hi - lo) + 1); no.resize((size_t)(hi - lo) + 1);
-        for (int i = lo; i <= hi; ++i) { o[(size_t)(i - lo)] = offsets[i] - offsets[lo]; no[(size_t)(i - lo)] = name_off[i] - name_off[lo]; }
-        std::unique_ptr<km_plan> p(new km_plan());
-        if (int rc = plan_init(t, seqs + offsets[lo], o.data(), hi - lo, &prm, p.get(), false, t->lanes[(size_t)c].get())) { delete res; return rc; }
-        if (int rc = plan_launch(p.get(), p->stream)) { delete res; return rc; }
-        plans.push_back(std::move(p));
-    }
-    // collect in order; the rows of each sub-batch are formatted in slices by the pool while the next
-    // sub-batch is awaited; the pieces are joined once at the end
-    const int n_slice = 4;
+    // One pool task per sub-batch: layout + upload + launch, then the fetch (which waits for that sub-batch's
+    // stream only), then its rows go to the pool in slices.  Nothing on the pool waits for another pool task; the
+    // caller waits for the last slice.  Enqueueing from several threads at once keeps the host off the critical
+    // path: done one after the other the six set-ups alone took as long as all the kernels.
+    const int n_slice = std::max(4, std::min(16, (int)host_pool().workers.size() / 2));
     std::vector<std::vector<char>> piece((size_t)n_sub * n_slice);
+    std::vector<std::unique_ptr<km_plan>> plans((size_t)n_sub);
+    std::vector<std::vector<int64_t>> offs((size_t)n_sub), noffs((size_t)n_sub);
+    res->parts.resize((size_t)n_sub);
+    std::vector<int> rcs((size_t)n_sub, 0);
+    std::vector<std::string> errs((size_t)n_sub);
     Latch latch(n_sub * n_slice);
-    int first_error = 0;
+    const int device = t->device;
+    std::atomic<int> next_lane(0);
     for (int c = 0; c < n_sub; ++c) {
-        const int lo = cut[(size_t)c];
-        std::unique_ptr<km_result> part(new km_result());
-        part->seq_off = plans[(size_t)c]->seq_off;
-        int rc = plan_fetch(plans[(size_t)c].get(), part.get(), false);
-        part->targets.swap(plans[(size_t)c]->targets);
-        km_result* pr = part.get();
-        res->parts.push_back(std::move(part));
-        if (rc) { if (!first_error) first_error = rc; for (int j = 0; j < n_slice; ++j) latch.done(); continue; }
-        const char* nm = names + name_off[lo];
-        const int64_t* no = noffs[(size_t)c].data();
-        const int m = pr->n_targets;
-        for (int j = 0; j < n_slice; ++j) {
-            std::vector<char>* dst = &piece[(size_t)c * n_slice + (size_t)j];
-            const int a = (int)((int64_t)m * j / n_slice), b = (int)((int64_t)m * (j + 1) / n_slice);
-            host_pool().submit([pr, db_name, nm, no, a, b, dst, &latch] {
-                format_range(pr, a, b, db_name, nm, no, *dst);
-                latch.done();
-            });
-        }
+        host_pool().submit([=, &next_lane, &cut, &piece, &plans, &offs, &noffs, &rcs, &errs, &latch, &prm, &tr] {
+            const int lo = cut[(size_t)c], hi = cut[(size_t)c + 1];
+            auto fail_all = [&](int rc) { rcs[(size_t)c] = rc; errs[(size_t)c] = g_err; for (int j = 0; j < n_slice; ++j) latch.done(); };
+            if (cudaSetDevice(device) != cudaSuccess) { fail(KM_E_CUDA, "cudaSetDevice failed"); return fail_all(KM_E_CUDA); }
+            auto& o = offs[(size_t)c]; auto& no = noffs[(size_t)c];
+            o.resize((size_t)(hi - lo) + 1); no.resize((size_t)(hi - lo) + 1);
+            for (int i = lo; i <= hi; ++i) { o[(size_t)(i - lo)] = offsets[i] - offsets[lo]; no[(size_t)(i - lo)] = name_off[i] - name_off[lo]; }
+            plans[(size_t)c].reset(new km_plan());
+            km_plan* p = plans[(size_t)c].get();
+            tr.mark("task start", c);
+            // lanes are handed out in the order the tasks get here: the first one to enqueue has the most urgent streams
+            const int lane_ix = next_lane.fetch_add(1);
+            if (int rc = plan_init(t, seqs + offsets[lo], o.data(), hi - lo, &prm, p, false, t->lanes[(size_t)lane_ix].get())) return fail_all(rc);
+            tr.mark("plan_init", c);
+            if (int rc = plan_launch(p, p->stream)) return fail_all(rc);
+            tr.mark("plan_launch", c);
+            std::unique_ptr<km_result> part(new km_result());
+            part->seq_off = p->seq_off;
+            if (int rc = plan_fetch(p, part.get(), false)) return fail_all(rc);
+            tr.mark("plan_fetch", c);
+            part->targets.swap(p->targets);
+            km_result* pr = part.get();
+            res->parts[(size_t)c] = std::move(part);
+            const char* nm = names + name_off[lo];
+            const int64_t* nop = no.data();
+            const int m = pr->n_targets;
+            for (int j = 0; j < n_slice; ++j) {
+                std::vector<char>* dst = &piece[(size_t)c * n_slice + (size_t)j];
+                const int a = (int)((int64_t)m * j / n_slice), b = (int)((int64_t)m * (j + 1) / n_slice);
+                host_pool().submit([pr, db_name, nm, nop, a, b, dst, &latch, &tr, c] {
+                    *dst = piece_cache().get(0);
+                    format_range(pr, a, b, db_name, nm, nop, *dst);
+                    tr.mark("slice", c);
+                    latch.done();
+                });
+            }
+        });
     }
+    tr.mark("all submitted");
     latch.wait();
-    if (first_error) { delete res; return first_error; }
+    tr.mark("formatted");
+    for (int c = 0; c < n_sub; ++c)
+        if (rcs[(size_t)c]) {
+            const int rc = rcs[(size_t)c];
+            fail(rc, "%s", errs[(size_t)c].c_str());
+            for (auto& pc : piece) piece_cache().put(std::move(pc));
+            delete res;
+            return rc;
+        }
     int64_t len = 0;
     std::vector<int64_t> at_of;
     for (auto& pc : piece) { at_of.push_back(len); len += (int64_t)pc.size(); }
-    res->text.reset(new char[(size_t)len + 1]);
+    res->text.reset((size_t)len + 1);
     {
         Latch joined((int)piece.size());
         char* dst = res->text.get();
@@ -1475,11 +1578,13 @@ extern "C" int km_find_text(km_table* t, const char* seqs, const int64_t* offset
             const int64_t at = at_of[c];
             host_pool().submit([pc, dst, at, &joined] {
                 if (!pc->empty()) memcpy(dst + at, pc->data(), pc->size());
+                piece_cache().put(std::move(*pc));
                 joined.done();
             });
         }
         joined.wait();
     }
+    tr.mark("joined");
     for (auto& part : res->parts) {
         res->all_status.insert(res->all_status.end(), part->status.data(), part->status.data() + part->status.size());
         res->ms_h2d += part->ms_h2d; res->ms_walk += part->ms_walk; res->ms_graph += part->ms_graph; res->ms_d2h += part->ms_d2h;
@@ -1490,6 +1595,7 @@ extern "C" int km_find_text(km_table* t, const char* seqs, const int64_t* offset
     res->text_len = len;
     res->fmt_key = std::string(db_name) + '\0' + (n ? std::string(names, (size_t)name_off[n]) : std::string());
     *out = res;
+    tr.mark("done");
     return 0;
 }
 
