@@ -158,6 +158,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-lookup", action="store_true")
     ap.add_argument("--n-sub", type=int, default=0, help="sub-batches in flight in km_find_text (0 = library default)")
+    ap.add_argument("--panel-offset", type=int, default=0, help="debug: use the panel rank R would get (seed offset)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "native":
         args.warmup = 3                       # timing rule: at least 3 warm-up steps
@@ -192,6 +193,11 @@ def main():
         return 0
 
     # ---- native arm ---------------------------------------------------------------------------
+    # the bench prints ONE line on stdout: everything else that writes to fd 1 (NCCL's version banner,
+    # library chatter) goes to stderr; the JSON line is written to the saved descriptor at the end
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     import torch
     import __graft_entry__ as ge
     ge.build()
@@ -202,7 +208,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = "WARN"         # NCCL's version banner goes to stdout: the bench prints ONE line
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -226,7 +232,7 @@ def main():
         return float(t.item())
 
     # every rank has its own panel; the planted k-mers of ALL panels go into every table (replicated)
-    panel = synth.make_panel(args.targets, seed=synth.PANEL_SEED + rank)
+    panel = synth.make_panel(args.targets, seed=synth.PANEL_SEED + rank + args.panel_offset)
     if dist is not None:
         gathered = [None] * world
         dist.all_gather_object(gathered, (panel.keys, panel.counts))
@@ -441,7 +447,8 @@ def main():
             lookup["sector_GBps"] = lookup["lookups_per_s"] / world * 32 / 1e9
             lookup["frac_of_random_gather"] = lookup["sector_GBps"] / gather["GBps"]
             lookup["frac_of_hbm_peak"] = lookup["sector_GBps"] / peak
-        print(json.dumps(out))
+        real_stdout.write(json.dumps(out) + "\n")
+        real_stdout.flush()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

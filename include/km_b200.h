@@ -59,6 +59,13 @@ int km_table_build_synthetic(km_table* t, uint64_t seed, uint64_t n_keys);
 int km_table_count_reads(km_table* t, const char* reads_host, const int64_t* offsets_host, int64_t n_reads);
 /* drop entries with count < min_count (jellyfish count -L); returns remaining through *n_left */
 int km_table_drop_below(km_table* t, uint32_t min_count, uint64_t* n_left);
+/* `jellyfish dump`: every (canonical key, count) record of the table (of this shard in cohort mode), in no
+ * particular order, into caller arrays of `cap` entries; *n_out = records in the table (may exceed cap). */
+int km_table_export(km_table* t, uint64_t* keys_host, uint32_t* counts_host, uint64_t cap, uint64_t* n_out);
+/* The table as a Jellyfish 2.x binary/sorted file -- what `jellyfish count -o` leaves on disk and
+ * Jellyfish(filename) opens (km/utils/Jellyfish.py:23-45; layout: SURVEY.md Appendix A): records sorted by the
+ * hash position M * key of the `matrix1` written into the header.  counter_len 0 = 4 bytes. */
+int km_table_write_jf(km_table* t, const char* path, uint32_t counter_len);
 
 typedef struct km_table_info {
     int32_t k;
@@ -229,7 +236,9 @@ int km_debug_nat_cmp(const char* a, const char* b);
 
 /* ---- measurement helpers (bench.py) --------------------------------------------------- */
 /* per-phase SM cycles of the graph pass (only in a -DKM_PHASE_TIMERS build; tools/phase_times.py) */
-int km_debug_phase_cycles(unsigned long long* out64, int reset);   /* 64 counters */
+int km_debug_phase_cycles(unsigned long long* out64, int reset);
+/* graph-pass SM cycles of targets 0..n-1 in the last launch (KM_PHASE_TIMERS builds only) */
+int km_debug_target_cycles(unsigned int* out, int n);   /* 64 counters */
 /* random 32-byte-sector gather over `bytes` of HBM: the ceiling for hash probes */
 int km_bench_random_gather(int device, uint64_t bytes, uint64_t n_loads, int iters, float* best_ms);
 /* device-resident lookup benchmark: n queries (config-4 mix) generated on device, timed `iters` times */

@@ -520,6 +520,108 @@ extern "C" int km_table_drop_below(km_table* t, uint32_t min_count, uint64_t* n_
     return rc;
 }
 
+
+
+// ---- export: `jellyfish dump` and a binary/sorted writer ---------------------------------------------
+extern "C" int km_table_export(km_table* t, uint64_t* keys, uint32_t* counts, uint64_t cap, uint64_t* n_out) {
+    if (!t || !n_out || (cap && (!keys || !counts))) return fail(KM_E_ARG, "km_table_export: bad argument");
+    CU(cudaSetDevice(t->device));
+    const uint64_t m = std::min<uint64_t>(cap, t->n_keys);
+    if (int rc = t->dev.reserve(m * 12 + 4096)) return rc;
+    t->dev.reset();
+    uint64_t* dk = t->dev.take<uint64_t>(m);
+    uint32_t* dc = t->dev.take<uint32_t>(m);
+    CU(cudaMemsetAsync(t->d_counter, 0, 16, t->stream));
+    km_table_export_kernel<<<t->sm_count * 8, 256, 0, t->stream>>>(t->view(), dk, dc, m, t->d_counter);
+    CU(cudaGetLastError());
+    unsigned long long found = 0;
+    CU(cudaMemcpyAsync(&found, t->d_counter, 8, cudaMemcpyDeviceToHost, t->stream));
+    CU(cudaStreamSynchronize(t->stream));
+    *n_out = found;
+    const uint64_t got = std::min<uint64_t>(found, m);
+    if (got) {
+        CU(cudaMemcpyAsync(keys, dk, got * 8, cudaMemcpyDeviceToHost, t->stream));
+        CU(cudaMemcpyAsync(counts, dc, got * 4, cudaMemcpyDeviceToHost, t->stream));
+        CU(cudaStreamSynchronize(t->stream));
+    }
+    return 0;
+}
+
+// Column i of the 32 x 62 binary matrix written into the header.  Any matrix works as long as the records are
+// sorted by it; this one is a fixed pseudo-random one.
+static uint32_t jf_matrix_column(int i) {
+    uint64_t z = 0x6B6D5F62323030ull + (uint64_t)i;          // splitmix64 finaliser (host copy)
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31;
+    return (uint32_t)(z >> 17);
+}
+
+// A Jellyfish 2.x `binary/sorted` file: "%09d" header length, JSON header (NUL-padded to 8 bytes), then
+// ceil(key_len/8)-byte LE key + counter_len-byte LE count per record.  Verified on the five files bundled with
+// km (tests/test_jf_writer.py): the records are sorted by pos = M * key over GF(2), masked to
+// `size`, where bit b of the key selects column c-1-b of `matrix1`.  Ties (unobserved in the bundled files)
+// are broken by key.  The writer emits its own matrix, so readers that binary-search by position stay consistent.
+extern "C" int km_table_write_jf(km_table* t, const char* path, uint32_t counter_len) {
+    if (!t || !path) return fail(KM_E_ARG, "km_table_write_jf: bad argument");
+    if (counter_len == 0) counter_len = 4;
+    if (counter_len > 8) return fail(KM_E_ARG, "km_table_write_jf: counter_len must be 1..8");
+    std::vector<uint64_t> keys((size_t)t->n_keys);
+    std::vector<uint32_t> counts((size_t)t->n_keys);
+    uint64_t n = 0;
+    if (int rc = km_table_export(t, keys.data(), counts.data(), t->n_keys, &n)) return rc;
+    if (n != t->n_keys) return fail(KM_E_ARG, "km_table_write_jf: table holds %llu records, expected %llu", (unsigned long long)n, (unsigned long long)t->n_keys);
+    const int kbits = 2 * t->k, kbytes = (kbits + 7) / 8;
+    int lsize = 10;
+    while (lsize < 32 && (1ull << lsize) < 2 * n) ++lsize;
+    const uint64_t size = 1ull << lsize, mask = size - 1;
+    // byte-sliced matrix-vector product: tab[j][v] = XOR of the columns selected by byte j of the key
+    std::vector<uint32_t> col((size_t)kbits);
+    for (int i = 0; i < kbits; ++i) col[(size_t)i] = jf_matrix_column(i);
+    std::vector<uint32_t> tab((size_t)8 * 256, 0);
+    for (int j = 0; j < 8; ++j)
+        for (int v = 0; v < 256; ++v) {
+            uint32_t x = 0;
+            for (int b = 0; b < 8; ++b) { const int bit = 8 * j + b; if (((v >> b) & 1) && bit < kbits) x ^= col[(size_t)(kbits - 1 - bit)]; }
+            tab[(size_t)j * 256 + (size_t)v] = x;
+        }
+    std::vector<uint64_t> order((size_t)n);      // pos << 32 | index would lose ties on the key: sort indices by (pos, key)
+    std::vector<uint32_t> pos((size_t)n);
+    for (uint64_t i = 0; i < n; ++i) {
+        uint32_t x = 0;
+        for (int j = 0; j < 8; ++j) x ^= tab[(size_t)j * 256 + ((keys[i] >> (8 * j)) & 0xFF)];
+        pos[i] = (uint32_t)(x & mask);
+        order[i] = i;
+    }
+    std::sort(order.begin(), order.end(), [&](uint64_t a, uint64_t b) { return pos[a] != pos[b] ? pos[a] < pos[b] : keys[a] < keys[b]; });
+    std::string js = "{\"alignment\":8,\"canonical\":";
+    js += t->canonical ? "true" : "false";
+    js += ",\"cmdline\":[\"km_b200\",\"count\"],\"counter_len\":" + std::to_string(counter_len) + ",\"format\":\"binary/sorted\",\"key_len\":" +
+          std::to_string(kbits) + ",\"matrix1\":{\"c\":" + std::to_string(kbits) + ",\"columns\":[";
+    for (int i = 0; i < kbits; ++i) { if (i) js += ','; js += std::to_string(col[(size_t)i]); }
+    js += "],\"r\":32},\"max_reprobe\":126,\"reprobes\":[1";
+    for (int i = 1; i <= 126; ++i) js += "," + std::to_string(i * (i + 1) / 2);
+    js += "],\"size\":" + std::to_string(size) + ",\"val_len\":" + std::to_string(8 * counter_len > 12 ? 12 : 8 * counter_len) + "}";
+    while ((9 + js.size()) % 8) js += '\0';
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(KM_E_IO, "cannot write %s", path);
+    char digits[16];
+    snprintf(digits, sizeof(digits), "%09zu", js.size());
+    bool ok = fwrite(digits, 1, 9, f) == 9 && fwrite(js.data(), 1, js.size(), f) == js.size();
+    const size_t rec = (size_t)kbytes + counter_len;
+    std::vector<unsigned char> buf;
+    buf.reserve(rec << 16);
+    const uint64_t cmax = counter_len >= 4 ? 0xFFFFFFFFull : ((1ull << (8 * counter_len)) - 1);
+    for (uint64_t i = 0; ok && i < n; ++i) {
+        const uint64_t key = keys[order[i]];
+        const uint64_t cnt = std::min<uint64_t>(counts[order[i]], cmax);       // a narrow counter saturates
+        for (int b = 0; b < kbytes; ++b) buf.push_back((unsigned char)(key >> (8 * b)));
+        for (uint32_t b = 0; b < counter_len; ++b) buf.push_back((unsigned char)(b < 8 ? cnt >> (8 * b) : 0));
+        if (buf.size() >= (rec << 16)) { ok = fwrite(buf.data(), 1, buf.size(), f) == buf.size(); buf.clear(); }
+    }
+    if (ok && !buf.empty()) ok = fwrite(buf.data(), 1, buf.size(), f) == buf.size();
+    if (fclose(f) != 0) ok = false;
+    if (!ok) return fail(KM_E_IO, "short write to %s", path);
+    return 0;
+}
 // ---- .jf loader (binary/sorted) ---------------------------------------
 static bool json_field(const std::string& js, const char* name, std::string* out) {
     std::string pat = std::string("\"") + name + "\"";
@@ -1615,6 +1717,17 @@ extern "C" int km_debug_phase_cycles(unsigned long long* out32, int reset) {
     return 0;
 #else
     (void)out32; (void)reset;
+    return fail(KM_E_ARG, "library built without KM_PHASE_TIMERS");
+#endif
+}
+
+extern "C" int km_debug_target_cycles(unsigned int* out, int n) {
+#ifdef KM_PHASE_TIMERS
+    if (!out || n < 0 || n > KM_DEBUG_TARGETS) return fail(KM_E_ARG, "km_debug_target_cycles: bad argument");
+    CU(cudaMemcpyFromSymbol(out, km_target_cycles, (size_t)n * sizeof(unsigned int)));
+    return 0;
+#else
+    (void)out; (void)n;
     return fail(KM_E_ARG, "library built without KM_PHASE_TIMERS");
 #endif
 }

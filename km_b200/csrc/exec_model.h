@@ -27,6 +27,8 @@ namespace km {
 // a global table, read back by km_debug_phase_cycles.  Compiled in when KM_PHASE_TIMERS is defined.
 #if KM_DEVICE_BUILD && defined(KM_PHASE_TIMERS)
 __device__ unsigned long long km_phase_cycles[64];
+#define KM_DEBUG_TARGETS 65536
+__device__ unsigned int km_target_cycles[KM_DEBUG_TARGETS];      // graph-pass cycles of each target (last launch)
 struct PhaseTimer {
     long long t0;
     __device__ __forceinline__ PhaseTimer() {

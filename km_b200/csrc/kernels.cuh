@@ -136,6 +136,28 @@ __global__ void km_encode_kernel(uint8_t* seq, const int64_t* seq_off, uint32_t*
     if (lane == 0) pre_bad[t] = bad ? 1 : 0;
 }
 
+// `jellyfish dump`: every (canonical key, count) record of this shard, compacted into two arrays in no
+// particular order (a family-line table holds two copies of most k-mers: only the one without the copy bit)
+__global__ void km_table_export_kernel(TableView T, uint64_t* keys, uint32_t* counts, unsigned long long cap, unsigned long long* n_out) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t n_slots = T.lines ? T.n_buckets * KM_LINE_SLOTS : T.n_buckets * KM_BUCKET_SLOTS;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += stride) {
+        uint64_t key; uint32_t cnt;
+        if (T.lines) {
+            const LineSlot* sl = reinterpret_cast<const LineSlot*>(T.buckets) + i;
+            key = sl->key; cnt = sl->count;
+            if (key == KM_EMPTY_KEY || (key & KM_COPY_BIT)) continue;
+        } else {
+            const Bucket* b = T.buckets + i / KM_BUCKET_SLOTS;
+            key = b->key[i % KM_BUCKET_SLOTS]; cnt = b->count[i % KM_BUCKET_SLOTS];
+            if (key == KM_EMPTY_KEY) continue;
+        }
+        const unsigned long long at = atomicAdd(n_out, 1ull);
+        if (at < cap) { keys[at] = key; counts[at] = cnt; }
+    }
+}
+
+
 // ---- K2: batched canonical probe (Jellyfish.query) ---------------------------------------
 #define KM_QUERY_ILP 4
 __global__ void __launch_bounds__(256) km_query_kernel(TableView T, const uint64_t* __restrict__ kmers, uint64_t n,
@@ -330,7 +352,7 @@ __global__ void __launch_bounds__(1024) km_schedule_kernel(WalkView W, ResultVie
 }
 
 template <int NODES>
-__global__ void __launch_bounds__(KM_CTA) km_graph_kernel(TableView T, WalkView W, ScratchLayout SL, ResultView R) {
+__global__ void __launch_bounds__(KM_CTA, NODES ? 8 : 4) km_graph_kernel(TableView T, WalkView W, ScratchLayout SL, ResultView R) {
     extern __shared__ __align__(16) char km_smem[];
     __shared__ int sh[32];
     CtaCtx ctx;
@@ -354,9 +376,15 @@ __global__ void __launch_bounds__(KM_CTA) km_graph_kernel(TableView T, WalkView 
         if (NODES == 0 && threadIdx.x == 0) atomicAnd(&W.status[t], ~KM_ST_RETRY_LARGE);
         GraphDims d;
         ctx.rot = t & 3;
+#ifdef KM_PHASE_TIMERS
+        const long long tc0 = clock64();
+#endif
         if (!graph_target(ctx, T, W, S, R, t, &d, sh)) continue;
         emit_rows(ctx, T, W, S, R, t, d, sh[2], sh[3], sh[6], sh);
         __syncthreads();
+#ifdef KM_PHASE_TIMERS
+        if (threadIdx.x == 0 && t < KM_DEBUG_TARGETS) km_target_cycles[t] = (unsigned int)(clock64() - tc0);
+#endif
     }
 }
 

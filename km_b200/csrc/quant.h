@@ -132,12 +132,103 @@ KM_HD double det2(double a, double b, double c, double d) {
     return f + e;
 }
 
-// refine_coef (PathQuant.py:120-136) + get_ratio (:144-149) on the normal equations, iterated
-// literally: fixed step 0.1, gradient / n_nodes, stop at max|grad| <= 0.01.
+// ---- refine_coef without its thousands of idle iterations ----------------------------------------------
+// The reference iterates coef += 0.1 * grad with grad = 2 (h - G coef) / n until max|grad| <= 0.01
+// (PathQuant.py:120-142).  When lstsq leaves a negative coefficient (a cluster whose second variant explains
+// nothing) the clamped problem converges along the slowest eigen-direction of G and the loop runs 5-10
+// thousand times -- one such target then takes longer than the rest of the batch.  Between two clamp
+// events the iteration is LINEAR in the free coefficients: x(t+1) = x(t) + a (h_F - G_FF x(t)), a = 0.2/n,
+// so in the eigenbasis of G_FF every component is y_i(t) = y_i(0) r_i^t + g_i (1 - r_i^t) / l_i with
+// r_i = 1 - a l_i.  chain_jump evaluates that closed form to (1) predict the step at which the stop test
+// will fire and (2) advance the state to 8 steps before it -- after checking at four points of the jump
+// that no free coefficient reaches zero and no clamped one is released.  The literal loop then runs the
+// last steps and decides the stop itself, so the result differs from the fully literal run only by the
+// rounding of the closed form (~1e-12 relative), and the first 32 iterations (every transient, every case
+// the reference's own tests hold) are literal.
+#define KM_REFINE_MAXF 4
+#if KM_DEVICE_BUILD
+#define KM_COLD __device__ __noinline__
+#else
+#define KM_COLD static
+#endif
+// (not inlined: it runs for a handful of targets per batch and must not cost the graph kernel its registers)
+KM_COLD int refine_jump(const double* G, const double* h, int m, int n_nodes, double* coef) {
+    int F[KM_REFINE_MAXF], mf = 0;
+    for (int a = 0; a < m; ++a)
+        if (coef[a] > 0.0) { if (mf == KM_REFINE_MAXF) return 0; F[mf++] = a; }
+    if (mf == 0) return 0;
+    double A[KM_REFINE_MAXF * KM_REFINE_MAXF], V[KM_REFINE_MAXF * KM_REFINE_MAXF];
+    double lam[KM_REFINE_MAXF], lg[KM_REFINE_MAXF], y0[KM_REFINE_MAXF], g[KM_REFINE_MAXF], x[KM_REFINE_MAXF];
+    for (int i = 0; i < mf; ++i)
+        for (int j = 0; j < mf; ++j) A[i * mf + j] = G[F[i] * m + F[j]];
+    jacobi_eigen(A, V, mf);
+    const double alpha = 0.2 / (double)n_nodes;
+    for (int e = 0; e < mf; ++e) {
+        lam[e] = A[e * mf + e] > 0.0 ? A[e * mf + e] : 0.0;
+        if (!(alpha * lam[e] < 1.0)) return 0;                 // an oscillating mode: leave it to the literal loop
+        lg[e] = log1p(-alpha * lam[e]);                        // log r_e <= 0
+        y0[e] = 0.0; g[e] = 0.0;
+        for (int i = 0; i < mf; ++i) { y0[e] += V[i * mf + e] * coef[F[i]]; g[e] += V[i * mf + e] * h[F[i]]; }
+    }
+    // state after t steps, and the stop test's quantity there; returns false if a clamp event lies at t
+    auto at = [&](double t, double* worst) -> bool {
+        double y[KM_REFINE_MAXF];
+        for (int e = 0; e < mf; ++e) {
+            const double tl = t * lg[e];
+            const double grow = lam[e] > 0.0 ? -expm1(tl) / lam[e] : alpha * t;      // (1 - r^t) / l
+            y[e] = y0[e] * exp(tl) + g[e] * grow;
+        }
+        bool ok = true;
+        for (int i = 0; i < mf; ++i) {
+            x[i] = 0.0;
+            for (int e = 0; e < mf; ++e) x[i] += V[i * mf + e] * y[e];
+            if (!(x[i] > 0.0)) ok = false;
+        }
+        double w = 0.0;
+        for (int a = 0; a < m; ++a) {
+            double fit = 0.0;
+            for (int i = 0; i < mf; ++i) fit += G[a * m + F[i]] * x[i];
+            const double gr = 2.0 * (h[a] - fit) / (double)n_nodes;
+            bool is_free = false;
+            for (int i = 0; i < mf; ++i) is_free |= F[i] == a;
+            if (is_free) { const double ag = fabs(gr); w = ag > w ? ag : w; }
+            else if (gr > 0.0) ok = false;                      // a clamped coefficient would be released
+        }
+        *worst = w;
+        return ok;
+    };
+    double w;
+    // first step at which the stop test fires, by doubling then bisection (the test quantity decays
+    // monotonically once the transients are gone: the caller has already run 32 literal steps)
+    double hi = 32.0;
+    while (hi < 16777216.0) { at(hi, &w); if (w <= 0.01) break; hi *= 2.0; }
+    if (!(w <= 0.01)) return 0;
+    double lo = hi * 0.5;
+    if (hi == 32.0) lo = 0.0;
+    while (hi - lo > 1.0) {
+        const double mid = floor(0.5 * (lo + hi));
+        at(mid, &w);
+        if (w <= 0.01) hi = mid; else lo = mid;
+    }
+    double J = hi - 8.0;
+    for (; J >= 32.0; J = floor(0.5 * J)) {
+        bool ok = true;
+        for (int q = 1; q <= 4 && ok; ++q) ok = at(floor(J * (double)q * 0.25), &w) && w > 0.01;
+        if (ok) break;
+    }
+    if (J < 32.0) return 0;
+    at(J, &w);
+    for (int i = 0; i < mf; ++i) coef[F[i]] = x[i];
+    return (int)J;
+}
+
+// refine_coef (PathQuant.py:120-136) + get_ratio (:144-149) on the normal equations: fixed step 0.1,
+// gradient / n_nodes, stop at max|grad| <= 0.01 -- literal steps, with refine_jump across the long
+// linear stretches.  Returns the number of iterations the literal loop would have run.
 KM_HD int refine_and_ratio(const double* G, const double* h, int m, int n_nodes, double* coef, double* rvaf, double* grad) {
     for (int a = 0; a < m; ++a) if (coef[a] < 0.0) coef[a] = 0.0;
     double worst = INFINITY;
-    int iters = 0;
+    int iters = 0, since = 0;
     while (worst > 0.01) {
         for (int a = 0; a < m; ++a) {
             double fit = 0.0;
@@ -152,6 +243,10 @@ KM_HD int refine_and_ratio(const double* G, const double* h, int m, int n_nodes,
             worst = ag > worst ? ag : worst;     // NaN never enters: counts are finite
         }
         if (++iters > 10000000) { iters = -1; break; }
+        if (++since >= 32 && worst > 0.01) {
+            iters += refine_jump(G, h, m, n_nodes, coef);
+            since = 0;
+        }
     }
     double cmax = coef[0], csum = 0.0;
     for (int a = 0; a < m; ++a) { cmax = coef[a] > cmax ? coef[a] : cmax; csum += coef[a]; }

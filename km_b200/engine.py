@@ -5,6 +5,7 @@ result arrays into the objects km's Python API exposes (km/utils/MutationFinder.
 km/utils/PathQuant.py).
 """
 import ctypes
+import os
 import sys
 
 import numpy as np
@@ -122,6 +123,20 @@ class Table:
         left = ctypes.c_uint64()
         check(lib().km_table_drop_below(self._h, int(min_count), ctypes.byref(left)))
         return int(left.value)
+
+    def export(self):
+        """`jellyfish dump`: (canonical keys uint64[n], counts uint32[n]) of every record, in no particular order."""
+        n = self.info()["n_keys"]
+        keys = np.empty(n, dtype=np.uint64)
+        counts = np.empty(n, dtype=np.uint32)
+        got = ctypes.c_uint64()
+        check(lib().km_table_export(self._h, keys.ctypes.data, counts.ctypes.data, n, ctypes.byref(got)))
+        m = min(n, int(got.value))
+        return keys[:m], counts[:m]
+
+    def write_jf(self, path, counter_len=4):
+        """The table as a Jellyfish binary/sorted file (what Jellyfish(filename) and Table.open_jf read)."""
+        check(lib().km_table_write_jf(self._h, os.fsencode(path), int(counter_len)))
 
     def query_packed(self, kmers):
         kmers = np.ascontiguousarray(kmers, dtype=np.uint64)

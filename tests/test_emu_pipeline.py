@@ -142,3 +142,43 @@ def test_both_scratch_passes_agree(synth_small, small):
     for i, rec in enumerate(synth_small["records"][:40]):
         assert int(res.status[i]) == 0
         _check(rec, record_of(res, i, "synth_small.jf", rec["target"]), rec["target"])
+
+
+def test_long_refinement_equals_literal_iteration():
+    """A tandem duplication of k-2..k-1 bases makes a cluster of two ITD paths of which lstsq gives one a
+    negative coefficient; the reference's projected-gradient loop (PathQuant.py:120-142) then runs for
+    thousands of iterations.  quant.h crosses the linear stretch in closed form (refine_jump): rows, raw
+    floats AND the iteration count must equal the literal loop's."""
+    from km_b200 import synth
+    panel = synth.make_panel(2000, seed=synth.PANEL_SEED + 5)
+    picks = [i for i, tr in enumerate(panel.truth) if tr["kind"] == "dup" and tr.get("size") in (28, 29, 30)][:5]
+    assert len(picks) >= 3
+    t = EmuTable.from_keys(panel.keys, panel.counts)
+    store = KmerStore(31, True, len(panel.keys))
+    store.insert(panel.keys, panel.counts)
+    jf = ko.OracleJellyfish(store, "p.jf", 0.05, 5)
+    seen = []
+    orig = ko.Quant.solve
+
+    def counting(self):
+        r = orig(self)
+        seen.append(self.n_iter)
+        return r
+    ko.Quant.solve = counting
+    try:
+        res = t.find_batch([panel.targets[i] for i in picks])
+        longest = 0
+        for j, i in enumerate(picks):
+            del seen[:]
+            f = ko.OracleFinder(ko.Target(panel.targets[i], panel.names[i], 31), jf).run()
+            want = f.get_paths()
+            got = record_of(res, j, "p.jf", panel.names[i])
+            errs, _ = compare_rows([str(r) for r in want], got["rows"],
+                                   [[float(r.rvaf), float(r.expr), float(r.ref_expr)] for r in want], got["raw"])
+            assert not errs, (panel.names[i], errs)
+            rows = res.rows[int(res.row_first[j]):int(res.row_first[j]) + int(res.row_count[j])]
+            assert max(seen) == int(rows["n_iter"].max()), (panel.names[i], max(seen), rows["n_iter"].tolist())
+            longest = max(longest, max(seen))
+        assert longest > 500           # the case this test is about did occur
+    finally:
+        ko.Quant.solve = orig
