@@ -119,6 +119,11 @@ class Table:
         np.cumsum([len(r) for r in reads], out=off[1:])
         check(lib().km_table_count_reads(self._h, blob, off.ctypes.data, len(reads)))
 
+    def count_reads_blob(self, blob, offsets):
+        """The same from one bytes object of concatenated reads and its int64 offsets [n_reads + 1]."""
+        off = np.ascontiguousarray(offsets, dtype=np.int64)
+        check(lib().km_table_count_reads(self._h, blob, off.ctypes.data, len(off) - 1))
+
     def drop_below(self, min_count):
         left = ctypes.c_uint64()
         check(lib().km_table_drop_below(self._h, int(min_count), ctypes.byref(left)))

@@ -1,12 +1,15 @@
 """Command line entry point: `km find_mutation | find_report | linear_kmin | min_cov`
-(same sub-commands and dispatch as km/km.py:17-67)."""
+(same sub-commands and dispatch as km/km.py:17-67), plus `count`, which stands in for the
+`jellyfish count` step of km's workflow (example/run_leucegene.sh:22)."""
 import argparse
 import sys
 
+from .argparser.count import get_argparser_count
 from .argparser.find_mutation import get_argparser_find_mut
 from .argparser.find_report import get_argparser_find_report
 from .argparser.linear_kmin import get_argparser_linear_kmin
 from .argparser.min_cov import get_argparser_min_cov
+from .tools.count import main_count
 from .tools.find_mutation import main_find_mut
 from .tools.find_report import main_find_report
 from .tools.linear_kmin import main_linear_kmin
@@ -20,6 +23,8 @@ COMMANDS = (
     ("linear_kmin", "Find min k-length to decompose a target sequence in a linear graph.",
      main_linear_kmin, get_argparser_linear_kmin),
     ("min_cov", "Compute coverage of target sequences.", main_min_cov, get_argparser_min_cov),
+    ("count", "Count k-mers of FASTA/FASTQ reads on the GPU into a Jellyfish binary/sorted database.",
+     main_count, get_argparser_count),
 )
 
 
