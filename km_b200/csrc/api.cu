@@ -25,6 +25,7 @@
 
 #include "../../include/km_b200.h"
 #include "kernels.cuh"
+#include "format.h"
 
 using namespace km;
 
@@ -804,8 +805,9 @@ static VecCache& text_cache() { static VecCache c(8); return c; }
 // the text a result holds: a cached vector used as a plain buffer
 struct TextBuf {
     std::vector<char> v;
-    char* get() { return v.data(); }
-    void reset() { if (v.capacity()) text_cache().put(std::move(v)); v = std::vector<char>(); }
+    PinBlock pin;                 // km_find_text with device-side formatting: the copies land here directly
+    char* get() { return pin.base ? pin.base : v.data(); }
+    void reset() { pin.drop(); if (v.capacity()) text_cache().put(std::move(v)); v = std::vector<char>(); }
     void reset(size_t bytes) {
         reset();
         v = text_cache().get(bytes, true);
@@ -837,6 +839,8 @@ struct km_result {
     mutable std::string fmt_key;
     mutable TextBuf text;
     mutable int64_t text_len = -1;
+    long long dev_text_len = 0;          // km_find_text: bytes of text the device wrote for this (sub-)batch
+    uint32_t dev_text_flags = 0;         // format.h flags: non-zero = the host must format this batch
     // km_find_text: the result of a pipelined run keeps its sub-batches and the joined text
     std::vector<std::unique_ptr<km_result>> parts;
     std::vector<uint32_t> all_status;
@@ -874,6 +878,12 @@ struct km_plan {
     bool launched = false;
     unsigned long long bytes_h2d = 0;
     size_t upload_bytes = 0;      // span of the input block on the device (plan_layout)
+    // device-side text (km_find_text): query names + database name go up with the input block, FormatView F
+    // describes the buffers of format.h
+    bool fmt = false;
+    const char* fmt_names = nullptr; const int64_t* fmt_name_off = nullptr; std::string fmt_db;
+    FormatView F{};
+    int64_t text_cap = 0;
     cudaStream_t stream = nullptr, side = nullptr;      // the table's own unless the plan runs on a lane
     cudaEvent_t* ev = nullptr;
     cudaEvent_t fork = nullptr, join = nullptr;
@@ -922,7 +932,14 @@ static int plan_layout(km_plan* p) {
     acc(8 * (size_t)path_cap); acc(4 * (size_t)path_cap); acc(8 * (size_t)path_cap); acc(4 * (size_t)pool_cap);
     acc(sizeof(Row) * (size_t)row_cap); acc((size_t)seq_cap); acc(64); acc(12 * (size_t)n + 64);
     acc(L0.stride * (size_t)p->grid_large);
-    if (int rc = p->dev->reserve(need + 8192)) return rc;
+    const size_t n_name = p->fmt ? (size_t)p->fmt_name_off[n] : 0;
+    if (p->fmt) {
+        // room for the text: rows carry two sequences of about the target's length each
+        p->text_cap = 16 * n_code + 512ll * n + (int64_t)row_cap * (int64_t)(p->fmt_db.size() + 64) + (1 << 16);
+        acc(n_name); acc(8 * (size_t)(n + 1)); acc(p->fmt_db.size() + 1);
+        acc(4 * (size_t)row_cap); acc(4 * (size_t)row_cap); acc(8 * (size_t)n); acc(8 * (size_t)(n + 1)); acc((size_t)p->text_cap); acc(64);
+    }
+    if (int rc = p->dev->reserve(need + 16384)) return rc;
     p->dev->reset();
     Arena& A = *p->dev;
     WalkView& W = p->W;
@@ -933,7 +950,15 @@ static int plan_layout(km_plan* p) {
     W.seq_off = A.take<int64_t>(n + 1); W.node_off = A.take<int64_t>(n + 1); W.hash_off = A.take<int64_t>(n + 1);
     W.pack_off = A.take<int64_t>(n + 1);
     W.chunk_target = A.take<int32_t>(n_chunks); W.chunk_start = A.take<int32_t>(n_chunks); W.n_chunks = (int)n_chunks;
-    p->upload_bytes = (size_t)((const char*)(W.chunk_start + n_chunks) - (const char*)W.codes);
+    const char* input_end = (const char*)(W.chunk_start + n_chunks);
+    if (p->fmt) {
+        char* dn = A.take<char>(n_name);
+        int64_t* dno = A.take<int64_t>(n + 1);
+        char* ddb = A.take<char>(p->fmt_db.size() + 1);
+        p->F.names = dn; p->F.name_off = dno; p->F.db_name = ddb; p->F.db_len = (int)p->fmt_db.size();
+        input_end = ddb + p->fmt_db.size() + 1;
+    }
+    p->upload_bytes = (size_t)(input_end - (const char*)W.codes);
     W.pack = A.take<uint32_t>((size_t)n_pack); W.pre_bad = A.take<uint8_t>(n);
     W.node_kmer = A.take<uint64_t>(n_node); W.node_count = A.take<uint32_t>(n_node);
     W.node_slot = A.take<uint32_t>(n_node); W.node_kid = A.take<uint32_t>(4 * n_node);
@@ -958,6 +983,12 @@ static int plan_layout(km_plan* p) {
     R.used = A.take<unsigned long long>(8);     // [0..3] pool cursors, [4..6] work counters of the three graph passes
     p->SL = L0;
     p->SL.base = A.take<char>(L0.stride * (size_t)p->grid_large);
+    if (p->fmt) {
+        p->F.row_len = A.take<int32_t>(row_cap); p->F.row_pos = A.take<int32_t>(row_cap);
+        p->F.t_len = A.take<int64_t>(n); p->F.t_off = A.take<int64_t>(n + 1);
+        p->F.text = A.take<char>((size_t)p->text_cap); p->F.text_cap = p->text_cap;
+        p->F.flags = A.take<uint32_t>(16);
+    }
     p->P.ratio = p->prm.ratio; p->P.count = p->prm.count; p->P.max_stack = p->prm.steps;
     p->P.max_break = p->prm.branchs; p->P.max_node = p->prm.nodes;
     return 0;
@@ -966,7 +997,8 @@ static int plan_layout(km_plan* p) {
 static int plan_upload(km_plan* p, cudaStream_t s) {
     const int n = p->n;
     const size_t n_chunks = p->chunk_target.size();
-    if (int rc = p->pin->reserve((size_t)p->n_code + 32 * (size_t)(n + 1) + 8 * n_chunks + 8192)) return rc;
+    const size_t n_name = p->fmt ? (size_t)p->fmt_name_off[n] : 0;
+    if (int rc = p->pin->reserve((size_t)p->n_code + 40 * (size_t)(n + 1) + 8 * n_chunks + n_name + p->fmt_db.size() + 16384)) return rc;
     p->pin->reset();
     uint8_t* h_codes = p->pin->take<uint8_t>(p->n_code);
     int64_t* h_seq_off = p->pin->take<int64_t>(n + 1);
@@ -982,7 +1014,17 @@ static int plan_upload(km_plan* p, cudaStream_t s) {
     memcpy(h_node_off, p->node_off.data(), 8 * (n + 1));
     memcpy(h_hash_off, p->hash_off.data(), 8 * (n + 1));
     CU(cudaEventRecord(p->ev[0], s));
-    if ((size_t)((const char*)(h_cs + n_chunks) - (const char*)h_codes) != p->upload_bytes)
+    const char* h_end = (const char*)(h_cs + n_chunks);
+    if (p->fmt) {
+        char* hn = p->pin->take<char>(n_name);
+        int64_t* hno = p->pin->take<int64_t>(n + 1);
+        char* hdb = p->pin->take<char>(p->fmt_db.size() + 1);
+        memcpy(hn, p->fmt_names, n_name);
+        memcpy(hno, p->fmt_name_off, 8 * (size_t)(n + 1));
+        memcpy(hdb, p->fmt_db.c_str(), p->fmt_db.size() + 1);
+        h_end = hdb + p->fmt_db.size() + 1;
+    }
+    if ((size_t)(h_end - (const char*)h_codes) != p->upload_bytes)
         return fail(KM_E_ARG, "internal: staging block and device input block differ in layout");
     CU(cudaMemcpyAsync((void*)p->W.codes, h_codes, p->upload_bytes, cudaMemcpyHostToDevice, s));
     if (n) {
@@ -990,7 +1032,7 @@ static int plan_upload(km_plan* p, cudaStream_t s) {
                                                      p->W.pack_off, const_cast<uint8_t*>(p->W.pre_bad), n);
         CU(cudaGetLastError());
     }
-    p->bytes_h2d = (unsigned long long)p->n_code + 32ull * (n + 1) + 8ull * n_chunks;
+    p->bytes_h2d = (unsigned long long)p->n_code + 32ull * (n + 1) + 8ull * n_chunks + (p->fmt ? n_name + 8ull * (n + 1) + p->fmt_db.size() : 0ull);
     return 0;
 }
 
@@ -1027,6 +1069,16 @@ static int plan_launch(km_plan* p, cudaStream_t s) {
     CU(cudaGetLastError());
     CU(cudaEventRecord(p->ev[3], s));
     p->n_launches += 7;
+    if (p->fmt) {
+        CU(cudaMemsetAsync(p->F.flags, 0, 64, s));
+        km_format_measure_kernel<<<(p->n + 3) / 4, 128, 0, s>>>(p->W, p->R, p->F, t->k);
+        CU(cudaGetLastError());
+        km_format_scan_kernel<<<1, 1024, 0, s>>>(p->F, p->n);
+        CU(cudaGetLastError());
+        km_format_write_kernel<<<(p->n + 3) / 4, 128, 0, s>>>(p->W, p->R, p->F, t->k);
+        CU(cudaGetLastError());
+        p->n_launches += 3;
+    }
     p->launched = true;
     return 0;
 }
@@ -1034,7 +1086,7 @@ static int plan_launch(km_plan* p, cudaStream_t s) {
 // D2H of per-target ints, then exactly the used extents.  `want_graph` also brings back the
 // node arrays and index paths (needed by the MutationFinder attribute views and the parity tests;
 // the TSV formatter only needs rows + spelled paths).
-static int plan_download(km_plan* p, cudaStream_t s, km_result* res, bool want_graph) {
+static int plan_download(km_plan* p, cudaStream_t s, km_result* res, bool want_graph, bool head_only = false) {
     km_table* t = p->t;
     const int n = p->n;
     const WalkView& W = p->W;
@@ -1042,7 +1094,7 @@ static int plan_download(km_plan* p, cudaStream_t s, km_result* res, bool want_g
     res->n_targets = n; res->k = t->k;
     // the per-target state and result ints sit back to back on the device (plan_layout): ONE copy brings the
     // block into pinned memory and the result's arrays are views into it
-    if (int rc = res->head.reserve(t->pool, p->state_bytes + 512)) return rc;
+    if (int rc = res->head.reserve(t->pool, p->state_bytes + 1024)) return rc;
     Span<char> blk = res->head.take<char>(p->state_bytes);
     auto view = [&](const void* dev_ptr) { return blk.data() + ((const char*)dev_ptr - p->state0); };
     res->status.p = (uint32_t*)view(W.status); res->status.n = (size_t)n;
@@ -1055,9 +1107,25 @@ static int plan_download(km_plan* p, cudaStream_t s, km_result* res, bool want_g
     res->used = res->head.take<unsigned long long>(4);
     unsigned long long* used = res->used.data();
     used[0] = used[1] = used[2] = used[3] = 0;
+    Span<long long> fmt_info = res->head.take<long long>(2);       // device text: total bytes, flags
+    fmt_info[0] = 0; fmt_info[1] = 0;
     if (n) {
         CU(cudaMemcpyAsync(blk.data(), p->state0, p->state_bytes, cudaMemcpyDeviceToHost, s));
         CU(cudaMemcpyAsync(used, R.used, 32, cudaMemcpyDeviceToHost, s));
+        if (p->fmt) {
+            CU(cudaMemcpyAsync(&fmt_info[0], p->F.t_off + n, 8, cudaMemcpyDeviceToHost, s));
+            CU(cudaMemcpyAsync(&fmt_info[1], p->F.flags, 4, cudaMemcpyDeviceToHost, s));
+        }
+    }
+    if (head_only) {
+        CU(cudaStreamSynchronize(s));
+        res->dev_text_len = fmt_info[0]; res->dev_text_flags = (uint32_t)fmt_info[1];
+        res->has_graph = false;
+        res->bytes_h2d = p->bytes_h2d;
+        res->bytes_d2h = (unsigned long long)p->state_bytes + 44;
+        res->text_len = -1; res->text.reset(); res->fmt_key.clear();
+        CU(cudaEventRecord(p->ev[4], s));
+        return 0;
     }
     CU(cudaStreamSynchronize(s));
     const size_t n_paths = std::min<unsigned long long>(used[0], p->path_cap), n_pool = std::min<unsigned long long>(used[1], p->pool_cap);
@@ -1132,11 +1200,11 @@ static int plan_init(km_table* t, const char* seqs, const int64_t* offsets, int3
 
 // fetch with the capacity-retry loop: targets whose exploration overflowed get 8x the node
 // capacity, exhausted pools grow 4x, and the batch is re-run
-static int plan_fetch(km_plan* p, km_result* res, bool want_graph) {
+static int plan_fetch(km_plan* p, km_result* res, bool want_graph, bool head_only = false) {
     km_table* t = p->t;
     for (int attempt = 0; attempt < 12; ++attempt) {
         if (!p->launched) if (int rc = plan_launch(p, p->stream)) return rc;
-        if (int rc = plan_download(p, p->stream, res, want_graph)) return rc;
+        if (int rc = plan_download(p, p->stream, res, want_graph, head_only)) return rc;
         bool again = false, pool_over = false;
         for (int i = 0; i < p->n; ++i) {
             if (res->status[i] & KM_ST_NODE_OVERFLOW) {
@@ -1604,6 +1672,131 @@ extern "C" int km_find_text(km_table* t, const char* seqs, const int64_t* offset
     res->n_targets = n; res->k = t->k; res->has_graph = false;
     km_find_params prm = *params;
     prm.flags |= KM_FIND_NO_GRAPH;
+    if (!getenv("KM_HOST_FORMAT")) {
+        // ---- the text is formatted on the device (format.h) --------------------------------------------------
+        // One pool task per sub-batch: set-up + upload + launches, a small fetch (per-target status, length of
+        // the text), then -- once the lengths of the sub-batches before it are known -- ONE copy of its text
+        // straight to its place in the result's pinned buffer.  The host formats nothing and joins nothing.
+        const std::string db(db_name);
+        std::vector<int64_t> caps((size_t)n_sub);
+        int64_t cap_total = 1;
+        for (int c = 0; c < n_sub; ++c) {
+            const int lo = cut[(size_t)c], hi = cut[(size_t)c + 1];
+            const int64_t rows = std::max(64, 16 * (hi - lo));
+            caps[(size_t)c] = 16 * (offsets[hi] - offsets[lo]) + 512ll * (hi - lo) + rows * (int64_t)(db.size() + 64) + (1 << 16);
+            cap_total += caps[(size_t)c];
+        }
+        if (int rc = res->text.pin.reserve(t->pool, (size_t)cap_total)) { delete res; return rc; }
+        char* final_text = res->text.pin.base;
+        std::vector<std::unique_ptr<km_plan>> plans((size_t)n_sub);
+        std::vector<std::vector<int64_t>> offs((size_t)n_sub), noffs((size_t)n_sub);
+        std::vector<std::vector<char>> spill((size_t)n_sub);            // text that did not go straight to its place
+        std::vector<char> spilled((size_t)n_sub, 0);
+        res->parts.resize((size_t)n_sub);
+        std::vector<int> rcs((size_t)n_sub, 0);
+        std::vector<std::string> errs((size_t)n_sub);
+        std::vector<long long> lens((size_t)n_sub, -1);
+        std::mutex lm; std::condition_variable lcv;
+        Latch latch(n_sub);
+        const int device = t->device;
+        std::atomic<int> next_lane(0);
+        for (int c = 0; c < n_sub; ++c) {
+            host_pool().submit([=, &db, &next_lane, &cut, &plans, &offs, &noffs, &spill, &spilled, &rcs, &errs, &lens, &lm, &lcv, &latch, &prm, &tr] {
+                const int lo = cut[(size_t)c], hi = cut[(size_t)c + 1];
+                auto publish = [&](long long len) { { std::lock_guard<std::mutex> g(lm); lens[(size_t)c] = len; } lcv.notify_all(); };
+                auto fail_all = [&](int rc) { rcs[(size_t)c] = rc; errs[(size_t)c] = g_err; publish(0); latch.done(); };
+                if (cudaSetDevice(device) != cudaSuccess) { fail(KM_E_CUDA, "cudaSetDevice failed"); return fail_all(KM_E_CUDA); }
+                auto& o = offs[(size_t)c]; auto& no = noffs[(size_t)c];
+                o.resize((size_t)(hi - lo) + 1); no.resize((size_t)(hi - lo) + 1);
+                for (int i = lo; i <= hi; ++i) { o[(size_t)(i - lo)] = offsets[i] - offsets[lo]; no[(size_t)(i - lo)] = name_off[i] - name_off[lo]; }
+                plans[(size_t)c].reset(new km_plan());
+                km_plan* p = plans[(size_t)c].get();
+                p->fmt = true; p->fmt_names = names + name_off[lo]; p->fmt_name_off = no.data(); p->fmt_db = db;
+                const int lane_ix = next_lane.fetch_add(1);
+                if (int rc = plan_init(t, seqs + offsets[lo], o.data(), hi - lo, &prm, p, false, t->lanes[(size_t)lane_ix].get())) return fail_all(rc);
+                if (int rc = plan_launch(p, p->stream)) return fail_all(rc);
+                tr.mark("plan_launch", c);
+                std::unique_ptr<km_result> part(new km_result());
+                part->seq_off = p->seq_off;
+                if (int rc = plan_fetch(p, part.get(), false, true)) return fail_all(rc);
+                tr.mark("head fetched", c);
+                km_result* pr = part.get();
+                res->parts[(size_t)c] = std::move(part);
+                long long len = pr->dev_text_len;
+                const bool host_format = pr->dev_text_flags != 0;
+                if (host_format) {        // the device declined (capacity, or a number it does not print): rows come back, host formats
+                    if (int rc = plan_download(p, p->stream, pr, false)) return fail_all(rc);
+                    pr->targets.swap(p->targets);
+                    format_range(pr, 0, pr->n_targets, db.c_str(), names + name_off[lo], no.data(), spill[(size_t)c]);
+                    len = (long long)spill[(size_t)c].size();
+                }
+                publish(len);
+                long long at = 0;
+                {
+                    std::unique_lock<std::mutex> lk(lm);
+                    lcv.wait(lk, [&] { for (int j = 0; j < c; ++j) if (lens[(size_t)j] < 0) return false; return true; });
+                    for (int j = 0; j < c; ++j) at += lens[(size_t)j];
+                }
+                const bool fits = at + len + 1 <= cap_total;
+                if (host_format) {
+                    if (fits) { memcpy(final_text + at, spill[(size_t)c].data(), (size_t)len); spill[(size_t)c].clear(); }
+                    else spilled[(size_t)c] = 1;
+                } else if (len) {
+                    char* dst = final_text + at;
+                    if (!fits) { spill[(size_t)c].resize((size_t)len); dst = spill[(size_t)c].data(); spilled[(size_t)c] = 1; }
+                    if (cudaMemcpyAsync(dst, p->F.text, (size_t)len, cudaMemcpyDeviceToHost, p->stream) != cudaSuccess ||
+                        cudaStreamSynchronize(p->stream) != cudaSuccess) {
+                        fail(KM_E_CUDA, "copy of the text failed: %s", cudaGetErrorString(cudaGetLastError()));
+                        rcs[(size_t)c] = KM_E_CUDA; errs[(size_t)c] = g_err;
+                    }
+                    pr->bytes_d2h += (unsigned long long)len;
+                }
+                tr.mark("text placed", c);
+                latch.done();
+            });
+        }
+        tr.mark("all submitted");
+        latch.wait();
+        tr.mark("all placed");
+        for (int c = 0; c < n_sub; ++c)
+            if (rcs[(size_t)c]) {
+                const int rc = rcs[(size_t)c];
+                fail(rc, "%s", errs[(size_t)c].c_str());
+                delete res;
+                return rc;
+            }
+        long long len = 0;
+        bool any_spill = false;
+        for (int c = 0; c < n_sub; ++c) { len += lens[(size_t)c]; any_spill |= spilled[(size_t)c] != 0; }
+        if (any_spill) {
+            // (only after capacity retries grew a sub-batch beyond the estimate) assemble in a buffer of the exact size
+            PinBlock exact;
+            if (int rc = exact.reserve(t->pool, (size_t)len + 1)) { delete res; return rc; }
+            long long at = 0;
+            for (int c = 0; c < n_sub; ++c) {
+                const long long l = lens[(size_t)c];
+                if (spilled[(size_t)c]) memcpy(exact.base + at, spill[(size_t)c].data(), (size_t)l);
+                else if (at + l + 1 <= cap_total) memcpy(exact.base + at, final_text + at, (size_t)l);
+                at += l;
+            }
+            res->text.pin.drop();
+            res->text.pin.pool = exact.pool; res->text.pin.base = exact.base; res->text.pin.cap = exact.cap;
+            exact.base = nullptr;
+        }
+        res->text.get()[len] = 0;
+        res->text_len = len;
+        for (auto& part : res->parts) {
+            res->all_status.insert(res->all_status.end(), part->status.data(), part->status.data() + part->status.size());
+            res->ms_h2d += part->ms_h2d; res->ms_walk += part->ms_walk; res->ms_graph += part->ms_graph; res->ms_d2h += part->ms_d2h;
+            res->n_launches += part->n_launches; res->n_retries += part->n_retries;
+            res->bytes_h2d += part->bytes_h2d; res->bytes_d2h += part->bytes_d2h;
+        }
+        res->fmt_key = std::string(db_name) + '\0' + (n ? std::string(names, (size_t)name_off[n]) : std::string());
+        *out = res;
+        tr.mark("done");
+        return 0;
+    }
+    // ---- KM_HOST_FORMAT: rows come back, host threads format them -------------------------------------------
     // One pool task per sub-batch: layout + upload + launch, then the fetch (which waits for that sub-batch's
     // stream only), then its rows go to the pool in slices.  Nothing on the pool waits for another pool task; the
     // caller waits for the last slice.  Enqueueing from several threads at once keeps the host off the critical

@@ -1,0 +1,272 @@
+// The text `km find_mutation` prints, built ON THE DEVICE: PathQuant.Path.__str__ (PathQuant.py:37-49) for
+// every row and MutationFinder.get_paths' sort (MutationFinder.py:813-833, common.natsortkey common.py:95-116)
+// inside every target.  km_find_text uses it so that the host neither formats nor joins anything: the text
+// of a sub-batch comes back with one copy, straight into its place in the caller's buffer.  (With the rows
+// formatted by host threads, eight ranks on one box spent 14 ms of CPU per 10,000-target panel each and the
+// end-to-end rate stopped scaling at ~11 M targets/s; the kernels themselves scale linearly.)
+//
+// Three launches: measure (one lane per row: exact length of the line, sort rank inside the target), scan
+// (exclusive prefix of the per-target lengths), write (one warp per target; numbers by every lane, sequences
+// copied 32 bytes at a time).  The same formatter runs in both, behind a counting and a storing emitter.
+// It is the device twin of format_rows_of / put_fixed / nat_cmp in api.cu; tests compare the two byte by byte.
+#pragma once
+#include "graph.h"
+
+namespace km {
+
+struct FormatView {
+    const char* db_name; int db_len;
+    const char* names; const int64_t* name_off;      // query names of the targets
+    int32_t* row_len;        // [row_cap] length of the row's line
+    int32_t* row_pos;        // [row_cap] offset of the line inside its target's block (sorted order)
+    int64_t* t_len;          // [n] bytes of the target's block
+    int64_t* t_off;          // [n + 1] exclusive prefix; t_off[n] = total
+    char* text; int64_t text_cap;
+    uint32_t* flags;         // bit 0: text_cap exceeded, bit 1: a value the device formatter does not print
+};
+
+#if KM_DEVICE_BUILD
+
+__device__ __forceinline__ int fmt_uint(char* buf, unsigned long long v) {       // digits into buf, returns their number
+    char tmp[24]; int n = 0;
+    do { tmp[n++] = (char)('0' + (int)(v % 10ull)); v /= 10ull; } while (v);
+    for (int i = 0; i < n; ++i) buf[i] = tmp[n - 1 - i];
+    return n;
+}
+__device__ __forceinline__ int fmt_int(char* buf, long long v) {
+    if (v < 0) { buf[0] = '-'; return 1 + fmt_uint(buf + 1, 0ull - (unsigned long long)v); }
+    return fmt_uint(buf, (unsigned long long)v);
+}
+// "%.{prec}f" (prec <= 3): the exact binary value rounded half-to-even at the last printed digit, decided on
+// integers (|v| = m * 2^e, m < 2^53, m * 10^prec fits 64 bits).  Returns -1 for magnitudes >= 2^52.
+__device__ __forceinline__ int fmt_fixed(char* buf, double v, int prec) {
+    if (isnan(v)) { buf[0] = 'n'; buf[1] = 'a'; buf[2] = 'n'; return 3; }
+    int n = 0;
+    if (isinf(v)) { if (v < 0) buf[n++] = '-'; buf[n++] = 'i'; buf[n++] = 'n'; buf[n++] = 'f'; return n; }
+    const double a = fabs(v);
+    if (a >= 4503599627370496.0) return -1;
+    if (signbit(v)) buf[n++] = '-';
+    const unsigned long long p10 = prec == 0 ? 1ull : prec == 1 ? 10ull : prec == 2 ? 100ull : 1000ull;
+    unsigned long long q = 0;
+    if (a != 0.0) {
+        int e;
+        const double fr = frexp(a, &e);
+        const unsigned long long m = (unsigned long long)ldexp(fr, 53);
+        const int sh = 53 - e;                       // a = m * 2^-sh
+        const unsigned long long scaled = m * p10;
+        if (sh <= 0) q = scaled << (-sh);
+        else if (sh >= 64) q = 0;
+        else {
+            q = scaled >> sh;
+            const unsigned long long rem = scaled & ((1ull << sh) - 1ull), half = 1ull << (sh - 1);
+            if (rem > half || (rem == half && (q & 1ull))) ++q;
+        }
+    }
+    n += fmt_uint(buf + n, q / p10);
+    if (prec > 0) {
+        buf[n++] = '.';
+        unsigned long long fp = q % p10;
+        for (unsigned long long d = p10 / 10ull; d; d /= 10ull) { buf[n++] = (char)('0' + (int)((fp / d) % 10ull)); }
+    }
+    return n;
+}
+
+__device__ const char km_type_name[6][16] = {"Reference", "Substitution", "ITD", "Indel", "Insertion", "Deletion"};
+__device__ const int km_type_len[6] = {9, 12, 3, 5, 9, 8};
+
+// emitters: where the formatter's output goes
+struct CountEmit {                       // one lane, nothing stored
+    long long n = 0;
+    __device__ __forceinline__ void small(const char*, int len) { n += len; }
+    __device__ __forceinline__ void ch(char) { n += 1; }
+    __device__ __forceinline__ void raw(const char*, int len) { n += len; }
+    __device__ __forceinline__ void codes(const uint8_t*, int len, bool) { n += len; }
+};
+struct WarpEmit {                        // the whole warp on one row: all lanes call with the same arguments
+    char* dst; long long n = 0; int lane;
+    __device__ __forceinline__ void small(const char* buf, int len) { if (lane < len) dst[n + lane] = buf[lane]; n += len; }   // len <= 32
+    __device__ __forceinline__ void ch(char c) { if (lane == 0) dst[n] = c; n += 1; }
+    __device__ __forceinline__ void raw(const char* src, int len) { for (int i = lane; i < len; i += 32) dst[n + i] = src[i]; n += len; }
+    __device__ __forceinline__ void codes(const uint8_t* src, int len, bool lower) {
+        for (int i = lane; i < len; i += 32) dst[n + i] = (char)((lower ? "acgt" : "ACGT")[src[i] & 3]);
+        n += len;
+    }
+};
+
+// one line: "{db}\t{query}\t{type}\t{name}\t{rVAF:.3f}\t{expr:.1f}\t{min_cov}\t{start_off}\t{seq}\t{ref_expr:.1f}\t{ref_seq}\t{info}\n"
+// Returns false if a number could not be printed here.
+template <class E>
+__device__ __forceinline__ bool format_row(E& e, const FormatView& F, const WalkView& W, const ResultView& R, int k, const Row& w) {
+    const int t = w.target;
+    const uint8_t* tcodes = W.codes + W.seq_off[t];
+    const char* pseq = R.seq_pool + R.path_seq_off[w.path_id];
+    char buf[40];
+    bool ok = true;
+    e.raw(F.db_name, F.db_len); e.ch('\t');
+    e.raw(F.names + F.name_off[t], (int)(F.name_off[t + 1] - F.name_off[t])); e.ch('\t');
+    e.small(km_type_name[w.type], km_type_len[w.type]); e.ch('\t');
+    if (w.type != 0) {                 // "{}:{}/{}:{}" (MutationFinder.py:483-488); Reference -> empty name
+        e.small(buf, fmt_int(buf, w.name_start)); e.ch(':');
+        e.codes(tcodes + w.del_begin + k - 1, w.del_len, true); e.ch('/');
+        e.raw(pseq + w.ins_begin + k - 1, w.ins_len); e.ch(':');
+        e.small(buf, fmt_int(buf, w.name_end));
+    }
+    e.ch('\t');
+    int n = fmt_fixed(buf, w.rvaf, 3); ok &= n >= 0; e.small(buf, n < 0 ? 0 : n); e.ch('\t');
+    n = fmt_fixed(buf, w.expr, 1); ok &= n >= 0; e.small(buf, n < 0 ? 0 : n); e.ch('\t');
+    e.small(buf, fmt_int(buf, (long long)w.min_cov)); e.ch('\t');
+    e.small(buf, fmt_int(buf, w.start_off)); e.ch('\t');
+    if (w.var_end > w.var_begin) e.raw(pseq + w.var_begin, w.var_end - w.var_begin + k - 1);
+    e.ch('\t');
+    n = fmt_fixed(buf, w.ref_expr, 1); ok &= n >= 0; e.small(buf, n < 0 ? 0 : n); e.ch('\t');
+    if (w.ref_end > w.ref_begin) e.codes(tcodes + w.ref_begin, w.ref_end - w.ref_begin + k - 1, false);
+    e.ch('\t');
+    if (w.kind == 0) e.small("vs_ref", 6);
+    else {
+        e.small("cluster ", 8); e.small(buf, fmt_int(buf, w.cluster_id));
+        e.small(" n=", 3); e.small(buf, fmt_int(buf, w.cluster_n));
+    }
+    e.ch('\n');
+    return ok;
+}
+
+// natsortkey of the variant name without spelling it: the name is "" (Reference) or
+// "<start>:<deleted, lower case>/<inserted>:<end>", whose token list is ["", start, ":del/ins:", end, ""] -- the
+// bases hold no digits.  Text compares lower-cased, numbers as integers, a prefix sorts first.
+__device__ __forceinline__ int name_text_at(const WalkView& W, const ResultView& R, int k, const Row& w, int i) {
+    // character i of ":<del>/<ins>:" lower-cased, -1 past its end
+    if (i == 0) return ':';
+    i -= 1;
+    if (i < w.del_len) return "acgt"[W.codes[W.seq_off[w.target] + w.del_begin + k - 1 + i] & 3];
+    i -= w.del_len;
+    if (i == 0) return '/';
+    i -= 1;
+    if (i < w.ins_len) {
+        const char c = R.seq_pool[R.path_seq_off[w.path_id] + w.ins_begin + k - 1 + i];
+        return c >= 'A' && c <= 'Z' ? c + 32 : c;
+    }
+    i -= w.ins_len;
+    return i == 0 ? ':' : -1;
+}
+__device__ __forceinline__ int name_cmp(const WalkView& W, const ResultView& R, int k, const Row& a, const Row& b) {
+    const bool ea = a.type == 0, eb = b.type == 0;
+    if (ea || eb) return ea == eb ? 0 : (ea ? -1 : 1);
+    if (a.name_start != b.name_start) return a.name_start < b.name_start ? -1 : 1;      // (never negative: start + k + offset)
+    for (int i = 0;; ++i) {
+        const int ca = name_text_at(W, R, k, a, i), cb = name_text_at(W, R, k, b, i);
+        if (ca != cb) return ca < cb ? -1 : 1;           // -1 (end) sorts first: the shorter text is a prefix
+        if (ca < 0) break;
+    }
+    if (a.name_end != b.name_end) return a.name_end < b.name_end ? -1 : 1;
+    return 0;
+}
+__device__ __forceinline__ int type_cmp(int ta, int tb) {           // natsort of the type names (no digits): lower-cased text
+    if (ta == tb) return 0;
+    const char* a = km_type_name[ta]; const char* b = km_type_name[tb];
+    for (int i = 0;; ++i) {
+        int ca = i < km_type_len[ta] ? a[i] : -1, cb = i < km_type_len[tb] ? b[i] : -1;
+        if (ca >= 'A' && ca <= 'Z') ca += 32;
+        if (cb >= 'A' && cb <= 'Z') cb += 32;
+        if (ca != cb) return ca < cb ? -1 : 1;
+        if (ca < 0) return 0;
+    }
+}
+// the order of MutationFinder.get_paths (:825-829): "vs_ref" rows first (first word reversed), clusters by
+// number then size, then variant name, type, Min_coverage
+__device__ __forceinline__ bool row_less(const WalkView& W, const ResultView& R, int k, const Row& a, const Row& b) {
+    if (a.kind != b.kind) return a.kind < b.kind;
+    if (a.kind != 0) {
+        if (a.cluster_id != b.cluster_id) return a.cluster_id < b.cluster_id;
+        if (a.cluster_n != b.cluster_n) return a.cluster_n < b.cluster_n;
+    }
+    int c = name_cmp(W, R, k, a, b);
+    if (c) return c < 0;
+    c = type_cmp(a.type, b.type);
+    if (c) return c < 0;
+    return a.min_cov < b.min_cov;
+}
+
+// one WARP per target: lane r measures row r and finds its place among the target's rows
+__global__ void __launch_bounds__(128) km_format_measure_kernel(WalkView W, ResultView R, FormatView F, int k) {
+    const int t = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (t >= W.n_targets) return;
+    int nrow = R.t_n_rows[t];
+    const int first = R.t_row_first[t];
+    long long total = 0;
+    bool ok = true;
+    // rows or spelled paths that did not fit their pools (the host grows the pools and runs the batch again)
+    if (first < 0 || nrow < 0 || (long long)first + nrow > (long long)R.row_cap) { nrow = 0; ok = false; }
+    for (int r = lane; r < nrow; r += 32) {
+        const Row w = R.rows[first + r];
+        if (w.path_id < 0 || w.path_id >= R.path_cap || R.path_seq_off[w.path_id] < 0 || w.type < 0 || w.type > 5 ||
+            (w.type != 0 && (w.name_start < 0 || w.name_end < 0))) { ok = false; F.row_len[first + r] = 0; continue; }
+        CountEmit e;
+        ok &= format_row(e, F, W, R, k, w);
+        F.row_len[first + r] = (int32_t)e.n;
+        total += e.n;
+    }
+    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xFFFFFFFFu, total, o);
+    ok = __all_sync(0xFFFFFFFFu, ok);
+    if (!ok) { if (lane == 0) { atomicOr(F.flags, 2u); F.t_len[t] = 0; } return; }
+    __syncwarp();
+    for (int r = lane; r < nrow; r += 32) {
+        const Row w = R.rows[first + r];
+        long long pos = 0;
+        for (int j = 0; j < nrow; ++j) {
+            if (j == r) continue;
+            const Row o = R.rows[first + j];
+            const bool before = row_less(W, R, k, o, w) || (!row_less(W, R, k, w, o) && j < r);      // stable
+            if (before) pos += F.row_len[first + j];
+        }
+        F.row_pos[first + r] = (int32_t)pos;
+    }
+    if (lane == 0) F.t_len[t] = total;
+}
+
+// exclusive prefix of t_len into t_off (one CTA; n is a few thousand)
+__global__ void __launch_bounds__(1024) km_format_scan_kernel(FormatView F, int n) {
+    __shared__ long long part[1024];
+    __shared__ long long carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + (int)threadIdx.x;
+        const long long v = i < n ? F.t_len[i] : 0;
+        part[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            const long long add = threadIdx.x >= (unsigned)o ? part[threadIdx.x - o] : 0;
+            __syncthreads();
+            part[threadIdx.x] += add;
+            __syncthreads();
+        }
+        if (i < n) F.t_off[i] = carry + part[threadIdx.x] - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry += part[1023];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        F.t_off[n] = carry;
+        if (carry > F.text_cap) atomicOr(F.flags, 1u);
+    }
+}
+
+// one WARP per target writes its rows, each at its place
+__global__ void __launch_bounds__(128) km_format_write_kernel(WalkView W, ResultView R, FormatView F, int k) {
+    const int t = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (t >= W.n_targets) return;
+    if (*F.flags) return;                            // the text does not fit / cannot be printed here: the host formats this batch
+    const int nrow = R.t_n_rows[t], first = R.t_row_first[t];
+    char* block = F.text + F.t_off[t];
+    for (int r = 0; r < nrow; ++r) {
+        const Row w = R.rows[first + r];
+        WarpEmit e;
+        e.dst = block + F.row_pos[first + r];
+        e.lane = lane;
+        format_row(e, F, W, R, k, w);
+    }
+}
+
+#endif  // KM_DEVICE_BUILD
+
+}  // namespace km
