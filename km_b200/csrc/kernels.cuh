@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(32 * KM_PROBE_WARPS, 4) km_ref_probe_kernel(Ta
     ref_probe_chunk(ctx, T, W, P, W.chunk_target[ch], W.chunk_start[ch]);
 }
 
-__global__ void __launch_bounds__(32 * KM_WALK_WARPS) km_walk_small_kernel(TableView T, WalkView W, FindParams P) {
+__global__ void __launch_bounds__(32 * KM_WALK_WARPS, 8) km_walk_small_kernel(TableView T, WalkView W, FindParams P) {
     __shared__ WalkSmall M[KM_WALK_WARPS];
     WarpCtx ctx;
     const int t = (int)blockIdx.x * KM_WALK_WARPS + (int)(threadIdx.x >> 5);

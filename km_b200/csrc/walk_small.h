@@ -23,7 +23,7 @@
 namespace km {
 
 #define KM_WS_HASH 1024      // visited-set slots per target (16 bit each)
-#define KM_WS_NOVEL 256      // novel nodes per target
+#define KM_WS_NOVEL 128      // novel nodes per target
 #define KM_WS_MAXL 448       // reference k-mers per target
 #define KM_WS_SEQW 32        // packed words: (KM_WS_MAXL + 31 + 15) / 16 + 2 of padding
 #define KM_ST_WALK_DEFER 0x20000000u   // internal: redo this target with the general walk kernel
