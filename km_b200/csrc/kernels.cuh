@@ -263,9 +263,15 @@ __global__ void __launch_bounds__(256) km_get_child_kernel(TableView T, const ui
 #ifndef KM_WALK_WARPS
 #define KM_WALK_WARPS 4
 #endif
-#define KM_PROBE_WARPS 8
+// (measured: 4 warps per CTA and room for ~100 registers -- no spills -- beat 8 warps at 64 registers, 0.307 vs 0.333 ms)
+#ifndef KM_PROBE_WARPS
+#define KM_PROBE_WARPS 4
+#endif
+#ifndef KM_PROBE_MINB
+#define KM_PROBE_MINB 5
+#endif
 // K3a: level 0 of every walk, one warp per 32 reference k-mers, flat over the batch
-__global__ void __launch_bounds__(32 * KM_PROBE_WARPS, 4) km_ref_probe_kernel(TableView T, WalkView W, FindParams P) {
+__global__ void __launch_bounds__(32 * KM_PROBE_WARPS, KM_PROBE_MINB) km_ref_probe_kernel(TableView T, WalkView W, FindParams P) {
     WarpCtx ctx;
     const int ch = (int)blockIdx.x * KM_PROBE_WARPS + (int)(threadIdx.x >> 5);
     if (ch >= W.n_chunks) return;
@@ -301,6 +307,13 @@ __global__ void __launch_bounds__(32 * KM_WALK_WARPS) km_walk_kernel(TableView T
 // per-CTA scratch in HBM and takes the rest, plus any target a shared-memory pass deferred
 // (KM_ST_RETRY_LARGE).
 #define KM_SMALL_NODES 512      // largest shared-memory class (graph nodes incl. the two caps)
+// resident CTAs per SM the register allocation aims at: the 512-node class is held to 5 by its shared memory
+#ifndef KM_GRAPH_SMALL_MINB
+#define KM_GRAPH_SMALL_MINB 5
+#endif
+#ifndef KM_GRAPH_TINY_MINB
+#define KM_GRAPH_TINY_MINB 8
+#endif
 #define KM_TINY_NODES 256
 #define KM_SMALL_CAND 64
 #define KM_SMALL_PATHS 64
@@ -352,7 +365,7 @@ __global__ void __launch_bounds__(1024) km_schedule_kernel(WalkView W, ResultVie
 }
 
 template <int NODES>
-__global__ void __launch_bounds__(KM_CTA, NODES ? 8 : 4) km_graph_kernel(TableView T, WalkView W, ScratchLayout SL, ResultView R) {
+__global__ void __launch_bounds__(KM_CTA, NODES == KM_SMALL_NODES ? KM_GRAPH_SMALL_MINB : (NODES ? KM_GRAPH_TINY_MINB : 4)) km_graph_kernel(TableView T, WalkView W, ScratchLayout SL, ResultView R) {
     extern __shared__ __align__(16) char km_smem[];
     __shared__ int sh[32];
     CtaCtx ctx;
