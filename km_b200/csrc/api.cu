@@ -971,6 +971,9 @@ static int plan_layout(km_plan* p) {
     ResultView& R = p->R;
     R.t_n = A.take<int32_t>(n); R.t_n_paths = A.take<int32_t>(n); R.t_path_first = A.take<int32_t>(n);
     R.t_n_rows = A.take<int32_t>(n); R.t_row_first = A.take<int32_t>(n);
+    // the pool cursors and the formatter's flags / total sit in the same block: one memset, one copy back
+    R.used = A.take<unsigned long long>(8);     // [0..3] pool cursors, [4..6] work counters of the three graph passes
+    p->F.flags = A.take<uint32_t>(16);          // [0] flags, [2..3] total bytes of text (64 bit)
     p->state_bytes = (size_t)(A.take<char>(0) - p->state0);
     R.out_kmer = A.take<uint64_t>(n_node); R.out_count = A.take<uint32_t>(n_node);
     R.path_off = A.take<int64_t>(path_cap); R.path_len = A.take<int32_t>(path_cap);
@@ -980,14 +983,12 @@ static int plan_layout(km_plan* p) {
     p->d_seq_pool = A.take<char>(seq_cap);
     R.seq_pool = p->d_seq_pool; R.path_seq_off = p->d_path_seq_off; R.seq_cap = seq_cap;
     R.sched_order = A.take<int32_t>(3 * (size_t)n); R.sched_count = A.take<int32_t>(4);
-    R.used = A.take<unsigned long long>(8);     // [0..3] pool cursors, [4..6] work counters of the three graph passes
     p->SL = L0;
     p->SL.base = A.take<char>(L0.stride * (size_t)p->grid_large);
     if (p->fmt) {
         p->F.row_len = A.take<int32_t>(row_cap); p->F.row_pos = A.take<int32_t>(row_cap);
         p->F.t_len = A.take<int64_t>(n); p->F.t_off = A.take<int64_t>(n + 1);
         p->F.text = A.take<char>((size_t)p->text_cap); p->F.text_cap = p->text_cap;
-        p->F.flags = A.take<uint32_t>(16);
     }
     p->P.ratio = p->prm.ratio; p->P.count = p->prm.count; p->P.max_stack = p->prm.steps;
     p->P.max_break = p->prm.branchs; p->P.max_node = p->prm.nodes;
@@ -1040,19 +1041,19 @@ static int plan_upload(km_plan* p, cudaStream_t s) {
 static int plan_launch(km_plan* p, cudaStream_t s) {
     km_table* t = p->t;
     if (p->n == 0) return 0;
-    CU(cudaEventRecord(p->ev[1], s));
+    const bool timed = !p->fmt;          // km_find_text enqueues as little as it can: no per-phase events
+    if (timed) CU(cudaEventRecord(p->ev[1], s));
     CU(cudaMemsetAsync(p->state0, 0, p->state_bytes, s));
-    CU(cudaMemsetAsync(p->R.used, 0, 64, s));
     if (p->W.n_chunks) {
         km_ref_probe_kernel<<<(p->W.n_chunks + KM_PROBE_WARPS - 1) / KM_PROBE_WARPS, 32 * KM_PROBE_WARPS, 0, s>>>(t->view(), p->W, p->P);
         CU(cudaGetLastError());
     }
-    CU(cudaEventRecord(p->ev[6], s));
+    if (timed) CU(cudaEventRecord(p->ev[6], s));
     km_walk_small_kernel<<<(p->n + KM_WALK_WARPS - 1) / KM_WALK_WARPS, 32 * KM_WALK_WARPS, 0, s>>>(t->view(), p->W, p->P);
     CU(cudaGetLastError());
     km_walk_kernel<<<(p->n + KM_WALK_WARPS - 1) / KM_WALK_WARPS, 32 * KM_WALK_WARPS, 0, s>>>(t->view(), p->W, p->P);
     CU(cudaGetLastError());
-    CU(cudaEventRecord(p->ev[2], s));
+    if (timed) CU(cudaEventRecord(p->ev[2], s));
     // shared-memory pass first, then the general pass for large or deferred targets
     km_schedule_kernel<<<1, 1024, 0, s>>>(p->W, p->R);
     CU(cudaGetLastError());
@@ -1067,10 +1068,9 @@ static int plan_launch(km_plan* p, cudaStream_t s) {
     CU(cudaStreamWaitEvent(s, p->join, 0));
     km_graph_kernel<0><<<p->grid_large, KM_CTA, 0, s>>>(t->view(), p->W, p->SL, p->R);
     CU(cudaGetLastError());
-    CU(cudaEventRecord(p->ev[3], s));
+    if (timed) CU(cudaEventRecord(p->ev[3], s));
     p->n_launches += 7;
     if (p->fmt) {
-        CU(cudaMemsetAsync(p->F.flags, 0, 64, s));
         km_format_measure_kernel<<<(p->n + 3) / 4, 128, 0, s>>>(p->W, p->R, p->F, t->k);
         CU(cudaGetLastError());
         km_format_scan_kernel<<<1, 1024, 0, s>>>(p->F, p->n);
@@ -1104,27 +1104,20 @@ static int plan_download(km_plan* p, cudaStream_t s, km_result* res, bool want_g
     res->row_count.p = (int32_t*)view(R.t_n_rows); res->row_count.n = (size_t)n;
     res->row_first.p = (int32_t*)view(R.t_row_first); res->row_first.n = (size_t)n;
     res->lookups.p = (unsigned long long*)view(W.lookups); res->lookups.n = (size_t)n;
-    res->used = res->head.take<unsigned long long>(4);
+    res->used.p = (unsigned long long*)view(R.used); res->used.n = 4;
     unsigned long long* used = res->used.data();
-    used[0] = used[1] = used[2] = used[3] = 0;
-    Span<long long> fmt_info = res->head.take<long long>(2);       // device text: total bytes, flags
-    fmt_info[0] = 0; fmt_info[1] = 0;
-    if (n) {
-        CU(cudaMemcpyAsync(blk.data(), p->state0, p->state_bytes, cudaMemcpyDeviceToHost, s));
-        CU(cudaMemcpyAsync(used, R.used, 32, cudaMemcpyDeviceToHost, s));
-        if (p->fmt) {
-            CU(cudaMemcpyAsync(&fmt_info[0], p->F.t_off + n, 8, cudaMemcpyDeviceToHost, s));
-            CU(cudaMemcpyAsync(&fmt_info[1], p->F.flags, 4, cudaMemcpyDeviceToHost, s));
-        }
-    }
+    const uint32_t* fmt_info = (const uint32_t*)view(p->F.flags);     // device text: [0] flags, [2..3] total bytes
+    if (n) CU(cudaMemcpyAsync(blk.data(), p->state0, p->state_bytes, cudaMemcpyDeviceToHost, s));
+    else memset(blk.data(), 0, p->state_bytes);
     if (head_only) {
         CU(cudaStreamSynchronize(s));
-        res->dev_text_len = fmt_info[0]; res->dev_text_flags = (uint32_t)fmt_info[1];
+        long long total = 0;
+        memcpy(&total, fmt_info + 2, 8);
+        res->dev_text_len = total; res->dev_text_flags = fmt_info[0];
         res->has_graph = false;
         res->bytes_h2d = p->bytes_h2d;
-        res->bytes_d2h = (unsigned long long)p->state_bytes + 44;
+        res->bytes_d2h = (unsigned long long)p->state_bytes;
         res->text_len = -1; res->text.reset(); res->fmt_key.clear();
-        CU(cudaEventRecord(p->ev[4], s));
         return 0;
     }
     CU(cudaStreamSynchronize(s));
@@ -1154,13 +1147,13 @@ static int plan_download(km_plan* p, cudaStream_t s, km_result* res, bool want_g
         }
     }
     res->bytes_h2d = p->bytes_h2d;
-    res->bytes_d2h = (unsigned long long)p->state_bytes + 32 + 20ull * n_paths + sizeof(Row) * n_rows + n_seq +
+    res->bytes_d2h = (unsigned long long)p->state_bytes + 20ull * n_paths + sizeof(Row) * n_rows + n_seq +
                      (want_graph ? 4ull * n_pool + 12ull * p->n_node : 0ull);
     res->text_len = -1; res->text.reset(); res->fmt_key.clear();
-    CU(cudaEventRecord(p->ev[4], s));
+    if (!p->fmt) CU(cudaEventRecord(p->ev[4], s));
     CU(cudaStreamSynchronize(s));
     float ms;
-    if (n) {
+    if (n && !p->fmt) {
         CU(cudaEventElapsedTime(&ms, p->ev[0], p->ev[1])); res->ms_h2d = ms;
         CU(cudaEventElapsedTime(&ms, p->ev[1], p->ev[2])); res->ms_walk = ms;
         CU(cudaEventElapsedTime(&ms, p->ev[2], p->ev[3])); res->ms_graph = ms;

@@ -22,7 +22,8 @@ struct FormatView {
     int64_t* t_len;          // [n] bytes of the target's block
     int64_t* t_off;          // [n + 1] exclusive prefix; t_off[n] = total
     char* text; int64_t text_cap;
-    uint32_t* flags;         // bit 0: text_cap exceeded, bit 1: a value the device formatter does not print
+    uint32_t* flags;         // [0] bit 0: text_cap exceeded, bit 1: a value the device formatter does not print;
+                             // [2..3] total bytes of text (64 bit), for the host
 };
 
 #if KM_DEVICE_BUILD
@@ -247,6 +248,7 @@ __global__ void __launch_bounds__(1024) km_format_scan_kernel(FormatView F, int 
     }
     if (threadIdx.x == 0) {
         F.t_off[n] = carry;
+        *reinterpret_cast<long long*>(F.flags + 2) = carry;
         if (carry > F.text_cap) atomicOr(F.flags, 1u);
     }
 }
