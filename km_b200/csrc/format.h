@@ -30,7 +30,9 @@ struct FormatView {
 
 __device__ __forceinline__ int fmt_uint(char* buf, unsigned long long v) {       // digits into buf, returns their number
     char tmp[24]; int n = 0;
-    do { tmp[n++] = (char)('0' + (int)(v % 10ull)); v /= 10ull; } while (v);
+    while (v > 0xFFFFFFFFull) { tmp[n++] = (char)('0' + (int)(v % 10ull)); v /= 10ull; }      // (rare: 64-bit division is emulated)
+    unsigned int x = (unsigned int)v;
+    do { tmp[n++] = (char)('0' + (int)(x % 10u)); x /= 10u; } while (x);
     for (int i = 0; i < n; ++i) buf[i] = tmp[n - 1 - i];
     return n;
 }
@@ -63,11 +65,13 @@ __device__ __forceinline__ int fmt_fixed(char* buf, double v, int prec) {
             if (rem > half || (rem == half && (q & 1ull))) ++q;
         }
     }
-    n += fmt_uint(buf + n, q / p10);
+    unsigned long long ip; unsigned int fp;
+    if (q <= 0xFFFFFFFFull) { const unsigned int q32 = (unsigned int)q, p32 = (unsigned int)p10; ip = q32 / p32; fp = q32 % p32; }
+    else { ip = q / p10; fp = (unsigned int)(q % p10); }
+    n += fmt_uint(buf + n, ip);
     if (prec > 0) {
         buf[n++] = '.';
-        unsigned long long fp = q % p10;
-        for (unsigned long long d = p10 / 10ull; d; d /= 10ull) { buf[n++] = (char)('0' + (int)((fp / d) % 10ull)); }
+        for (unsigned int d = (unsigned int)p10 / 10u; d; d /= 10u) { buf[n++] = (char)('0' + (int)((fp / d) % 10u)); }
     }
     return n;
 }
@@ -224,33 +228,32 @@ __global__ void __launch_bounds__(128) km_format_measure_kernel(WalkView W, Resu
     if (lane == 0) F.t_len[t] = total;
 }
 
-// exclusive prefix of t_len into t_off (one CTA; n is a few thousand)
+// exclusive prefix of t_len into t_off (one CTA: every thread sums a contiguous stretch, the 1024 partial sums
+// are scanned with shuffles, every thread writes its stretch back)
 __global__ void __launch_bounds__(1024) km_format_scan_kernel(FormatView F, int n) {
-    __shared__ long long part[1024];
-    __shared__ long long carry;
-    if (threadIdx.x == 0) carry = 0;
+    __shared__ long long warp_tot[32];
+    const int per = (n + 1023) / 1024;
+    const int lo = (int)threadIdx.x * per, hi = lo + per < n ? lo + per : n;
+    long long mine = 0;
+    for (int i = lo; i < hi; ++i) mine += F.t_len[i];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    long long incl = mine;
+    for (int o = 1; o < 32; o <<= 1) { const long long v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) warp_tot[wid] = incl;
     __syncthreads();
-    for (int base = 0; base < n; base += 1024) {
-        const int i = base + (int)threadIdx.x;
-        const long long v = i < n ? F.t_len[i] : 0;
-        part[threadIdx.x] = v;
-        __syncthreads();
-        for (int o = 1; o < 1024; o <<= 1) {
-            const long long add = threadIdx.x >= (unsigned)o ? part[threadIdx.x - o] : 0;
-            __syncthreads();
-            part[threadIdx.x] += add;
-            __syncthreads();
+    if (wid == 0) {
+        long long w = warp_tot[lane], wi = w;
+        for (int o = 1; o < 32; o <<= 1) { const long long v = __shfl_up_sync(0xFFFFFFFFu, wi, o); if (lane >= o) wi += v; }
+        warp_tot[lane] = wi - w;                                  // exclusive prefix of the warp totals
+        if (lane == 31) {
+            F.t_off[n] = wi;
+            *reinterpret_cast<long long*>(F.flags + 2) = wi;
+            if (wi > F.text_cap) atomicOr(F.flags, 1u);
         }
-        if (i < n) F.t_off[i] = carry + part[threadIdx.x] - v;
-        __syncthreads();
-        if (threadIdx.x == 1023) carry += part[1023];
-        __syncthreads();
     }
-    if (threadIdx.x == 0) {
-        F.t_off[n] = carry;
-        *reinterpret_cast<long long*>(F.flags + 2) = carry;
-        if (carry > F.text_cap) atomicOr(F.flags, 1u);
-    }
+    __syncthreads();
+    long long at = warp_tot[wid] + incl - mine;
+    for (int i = lo; i < hi; ++i) { F.t_off[i] = at; at += F.t_len[i]; }
 }
 
 // one WARP per target writes its rows, each at its place
