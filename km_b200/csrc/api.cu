@@ -318,7 +318,8 @@ extern "C" int km_table_create_shard(int device, int k, int canonical, uint64_t 
     if (km_device_count() <= 0) return fail(KM_E_NOGPU, "no CUDA device visible: km_b200 has no CPU fallback");
     // the ordinary constructor with a token allocation, then the bucket array is replaced by a
     // shareable one of the real size
-    if (int rc = km_table_create(device, k, canonical, 64, out)) return rc;      // layout from KM_TABLE_LINES
+    // shards always use sector buckets: the experimental family-line layout (KM_TABLE_LINES) is single-GPU only
+    if (int rc = km_table_create_layout(device, k, canonical, 64, 0, out)) return rc;
     km_table* t = *out;
     t->n_shards = n_shards; t->my_shard = rank;
     if (int rc = vmm_load()) { km_table_close(t); *out = nullptr; return rc; }
