@@ -282,7 +282,9 @@ KM_HD bool bit_at(const uint32_t* bits, int u) { return (bits[u >> 5] >> (u & 31
 // Settling order = ascending (distance, index) and a node is re-parented only on a strictly smaller
 // float32 sum (Graph.py:103), exactly as in the reference.
 // dist/prev must be pre-filled with +inf / -1.
-#if KM_DEVICE_BUILD && defined(KM_PHASE_TIMERS)
+// (KM_TREE_TIMERS: per-step ticks inside the tree pass -- they cost more than the steps they time, so they are
+// separate from the per-phase marks)
+#if KM_DEVICE_BUILD && defined(KM_PHASE_TIMERS) && defined(KM_TREE_TIMERS)
 #define KM_DBG_DECL long long dbg_t0 = 0;
 #define KM_DBG_TICK(p) dbg_t0 = clock64();
 #define KM_DBG_TOCK(p, n) { atomicAdd(&km_phase_cycles[p], (unsigned long long)(clock64() - dbg_t0)); atomicAdd(&km_phase_cycles[(p) + 8], (unsigned long long)(n)); }

@@ -495,7 +495,11 @@ KM_HD void emit_rows(const Ctx& ctx, const TableView& T, const WalkView& W, cons
     const int lane = wctx.tid();
     const int64_t nbase = W.node_off[t];
     const uint64_t* kmers = R.out_kmer + nbase;
-    const uint32_t* counts = R.out_count + nbase;  // caps are not stored: rows never touch them
+    // the counts are read several times per row by every solver pass: a copy in the scratch (shared memory in
+    // the small passes) in place of the distance array, which is dead once the paths are materialised
+    uint32_t* cnt_s = reinterpret_cast<uint32_t*>(S.dist);
+    for (int i = tid; i < d.N - 2; i += ctx.nt()) cnt_s[i] = R.out_count[nbase + i];
+    const uint32_t* counts = cnt_s;                  // caps are not stored: rows never touch them
     int* slot = sh + 8;                              // CTA-wide reduction scratch
     int* wslot = sh + 16 + wid;                      // this warp's reduction scratch
     const PathView ref = {nullptr, 0, d.L};
