@@ -67,14 +67,15 @@ KM_HD Diff diff_paths(const Ctx& ctx, const PathView& ref, const PathView& alt, 
 
 enum { KM_T_REFERENCE = 0, KM_T_SUBSTITUTION = 1, KM_T_ITD = 2, KM_T_INDEL = 3, KM_T_INSERTION = 4, KM_T_DELETION = 5 };
 
-// get_name: type + trimmed deleted / inserted runs.  kmers are the canonical node array.
-KM_HD int classify(const uint64_t* kmers, const PathView& ref, const PathView& alt, const Diff& d,
+// get_name: type + trimmed deleted / inserted runs.  kmers[i] = last base of canonical node i (all the naming
+// needs of a k-mer: the scan below is serial, one lane, and used to wait for an L2 round trip per step).
+KM_HD int classify(const uint8_t* kmers, const PathView& ref, const PathView& alt, const Diff& d,
                    int* del_len, int* ins_len) {
     int gone = d.end_ref - d.start, fresh = d.end_var - d.start;
     int cut = 0;
     if (gone > 0) {     // strip the suffix both strings share (:446-456)
         while (cut < gone && cut < fresh &&
-               (kmers[pv_at(ref, d.end_ref - 1 - cut)] & 3ull) == (kmers[pv_at(alt, d.end_var - 1 - cut)] & 3ull))
+               kmers[pv_at(ref, d.end_ref - 1 - cut)] == kmers[pv_at(alt, d.end_var - 1 - cut)])
             ++cut;
     }
     gone -= cut; fresh -= cut;
@@ -430,7 +431,7 @@ KM_HD Quant2 quant_pair(const WCtx& wctx, const GraphScratch& S, const uint32_t*
 }
 
 // One output row.  `variant` is the (possibly clipped) path, `refv` the (possibly clipped) reference.
-KM_HD void write_row(const ResultView& R, const WalkView& W, const uint64_t* kmers, int t, int k, int row_index, int kind,
+KM_HD void write_row(const ResultView& R, const WalkView& W, const uint8_t* kmers, int t, int k, int row_index, int kind,
                      const PathView& refv, const PathView& variant, const Diff& df, int path_id, int offset, int cluster_id,
                      int cluster_n, int iters, int64_t mc, double rvaf, double expr, double ref_rvaf, double ref_expr) {
     int dl, il;
@@ -494,7 +495,9 @@ KM_HD void emit_rows(const Ctx& ctx, const TableView& T, const WalkView& W, cons
     const WarpCtx wctx;
     const int lane = wctx.tid();
     const int64_t nbase = W.node_off[t];
-    const uint64_t* kmers = R.out_kmer + nbase;
+    uint8_t* last_s = reinterpret_cast<uint8_t*>(S.dist2);           // (dead like S.dist, see below)
+    for (int i = tid; i < d.N - 2; i += ctx.nt()) last_s[i] = (uint8_t)(R.out_kmer[nbase + i] & 3ull);
+    const uint8_t* kmers = last_s;
     // the counts are read several times per row by every solver pass: a copy in the scratch (shared memory in
     // the small passes) in place of the distance array, which is dead once the paths are materialised
     uint32_t* cnt_s = reinterpret_cast<uint32_t*>(S.dist);
