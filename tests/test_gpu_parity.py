@@ -414,3 +414,68 @@ def test_repeated_runs_print_the_same_text(engine):
     for _ in range(5):
         plan.launch()
         assert plan.fetch(want_graph=False).format_all("panel.jf", packed) == first
+
+
+@pytest.mark.gpu
+def test_long_insertions_overflow_the_shared_memory_walk(engine):
+    """An insertion of 120-300 bases is a chain of 150-330 novel k-mers: more than the shared-memory walk holds
+    per target (KM_WS_NOVEL = 128), so its chain level raises the overflow flag half-way and the general walk
+    kernel redoes the target.  Same records as the oracle."""
+    from km_b200 import synth
+    rng = np.random.default_rng(77)
+    k = 31
+    targets, names, keys, counts = [], [], [], []
+    for i in range(12):
+        L = int(rng.integers(150, 260))
+        while True:
+            ref = rng.integers(0, 4, size=L, dtype=np.uint8)
+            ins = rng.integers(0, 4, size=int(rng.integers(120, 301)), dtype=np.uint8)
+            pos = int(rng.integers(k, L - k + 1))
+            alt = np.concatenate([ref[:pos], ins, ref[pos:]])
+            ka, kr = synth.pack_kmers(alt, k), synth.pack_kmers(ref, k)
+            if len(np.unique(ka)) == len(ka) and len(np.unique(kr)) == len(kr):
+                break
+        keys += [synth.canonical(kr, k), synth.canonical(ka, k)]
+        counts += [np.full(len(kr), 300, dtype=np.int64), np.full(len(ka), 120, dtype=np.int64)]
+        targets.append(synth.decode(ref))
+        names.append("longins_%02d" % i)
+    uk, inv = np.unique(np.concatenate(keys), return_inverse=True)
+    uc = np.zeros(len(uk), dtype=np.int64)
+    np.add.at(uc, inv, np.concatenate(counts))
+    t = engine.Table.create(capacity=len(uk) + 100000)
+    t.build_synthetic(synth.TABLE_SEED, 100000)
+    t.insert(uk, uc.astype(np.uint32), mode="overwrite")
+    res = t.find_batch(targets)
+    assert (res.status & ~np.uint32(16) == 0).all()
+    store = KmerStore(31, True, len(uk))
+    store.set_background(synth.TABLE_SEED, 100000)
+    store.insert(uk, uc.astype(np.uint32))
+    jf = ko.OracleJellyfish(store, "long.jf", 0.05, 5)
+    novel_max = 0
+    for i, (name, seq) in enumerate(zip(names, targets)):
+        f = ko.OracleFinder(ko.Target(seq, name, 31), jf).run()
+        want = f.get_paths()
+        got = record_of(res, i, "long.jf", name)
+        errs, _ = compare_rows([str(r) for r in want], got["rows"],
+                               [[float(r.rvaf), float(r.expr), float(r.ref_expr)] for r in want], got["raw"])
+        assert not errs, (name, errs)
+        assert got["nodes"] == sorted([kk, int(v)] for kk, v in f.node_data.items())
+        novel_max = max(novel_max, f.num_k - 2 - (len(seq) - 30))
+        assert any(r.split("\t")[2] in ("Insertion", "ITD") for r in got["rows"]), name
+    assert novel_max > 128
+    # the one-call path prints the same rows
+    text, _ = t.find_text(engine.PackedTargets(targets, names), "long.jf")
+    assert text == "".join(res.format_target(i, "long.jf", names[i]) for i in range(len(targets)))
+
+
+@pytest.mark.gpu
+def test_text_call_survives_capacity_retries(engine, synth_small):
+    """km_find_text with node capacities far too small at first: the fetch loop grows them and runs the
+    sub-batch again (layout, upload, kernels AND the device formatter); the text is the same."""
+    t = engine.Table.create(capacity=len(synth_small["keys"]) + 1024)
+    t.insert(synth_small["keys"], synth_small["counts"].astype(np.uint32))
+    packed = engine.PackedTargets(synth_small["targets"], synth_small["names"])
+    want, _ = t.find_text(packed, "synth_small.jf")
+    got, status = t.find_text(packed, "synth_small.jf", extra_nodes=2, n_sub=3)
+    assert got == want and (status & ~np.uint32(16) == 0).all()
+    assert t.last_timing["retries"] > 0
