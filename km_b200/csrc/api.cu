@@ -938,7 +938,8 @@ static int plan_layout(km_plan* p) {
         // room for the text: rows carry two sequences of about the target's length each
         p->text_cap = 16 * n_code + 512ll * n + (int64_t)row_cap * (int64_t)(p->fmt_db.size() + 64) + (1 << 16);
         acc(n_name); acc(8 * (size_t)(n + 1)); acc(p->fmt_db.size() + 1);
-        acc(4 * (size_t)row_cap); acc(4 * (size_t)row_cap); acc(8 * (size_t)n); acc(8 * (size_t)(n + 1)); acc((size_t)p->text_cap); acc(64);
+        acc(4 * (size_t)row_cap); acc(4 * (size_t)row_cap); acc((size_t)KM_FMT_ROW_BYTES * (size_t)row_cap);
+        acc(8 * (size_t)n); acc(8 * (size_t)(n + 1)); acc((size_t)p->text_cap); acc(64);
     }
     if (int rc = p->dev->reserve(need + 16384)) return rc;
     p->dev->reset();
@@ -988,6 +989,7 @@ static int plan_layout(km_plan* p) {
     p->SL.base = A.take<char>(L0.stride * (size_t)p->grid_large);
     if (p->fmt) {
         p->F.row_len = A.take<int32_t>(row_cap); p->F.row_pos = A.take<int32_t>(row_cap);
+        p->F.row_num = A.take<char>((size_t)KM_FMT_ROW_BYTES * (size_t)row_cap);
         p->F.t_len = A.take<int64_t>(n); p->F.t_off = A.take<int64_t>(n + 1);
         p->F.text = A.take<char>((size_t)p->text_cap); p->F.text_cap = p->text_cap;
     }

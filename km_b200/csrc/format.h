@@ -19,6 +19,7 @@ struct FormatView {
     const char* names; const int64_t* name_off;      // query names of the targets
     int32_t* row_len;        // [row_cap] length of the row's line
     int32_t* row_pos;        // [row_cap] offset of the line inside its target's block (sorted order)
+    char* row_num;           // [row_cap * KM_FMT_ROW_BYTES] the row's numbers as text (measure writes, write copies)
     int64_t* t_len;          // [n] bytes of the target's block
     int64_t* t_off;          // [n + 1] exclusive prefix; t_off[n] = total
     char* text; int64_t text_cap;
@@ -26,14 +27,26 @@ struct FormatView {
                              // [2..3] total bytes of text (64 bit), for the host
 };
 
+// per-row scratch: 9 numeric fields of up to 24 characters + their lengths
+#define KM_FMT_FIELDS 9
+#define KM_FMT_FIELD_BYTES 24
+#define KM_FMT_ROW_BYTES 256
+
 #if KM_DEVICE_BUILD
 
-__device__ __forceinline__ int fmt_uint(char* buf, unsigned long long v) {       // digits into buf, returns their number
-    char tmp[24]; int n = 0;
-    while (v > 0xFFFFFFFFull) { tmp[n++] = (char)('0' + (int)(v % 10ull)); v /= 10ull; }      // (rare: 64-bit division is emulated)
-    unsigned int x = (unsigned int)v;
-    do { tmp[n++] = (char)('0' + (int)(x % 10u)); x /= 10u; } while (x);
-    for (int i = 0; i < n; ++i) buf[i] = tmp[n - 1 - i];
+// decimal digits of v straight into buf (no temporary: a local array indexed by a loop counter lives in local
+// memory, and every digit then costs a round trip to L1); returns their number
+__device__ __forceinline__ int fmt_uint(char* buf, unsigned long long v) {
+    if (v <= 0xFFFFFFFFull) {
+        unsigned int x = (unsigned int)v;
+        const int n = x < 10u ? 1 : x < 100u ? 2 : x < 1000u ? 3 : x < 10000u ? 4 : x < 100000u ? 5 : x < 1000000u ? 6 :
+                      x < 10000000u ? 7 : x < 100000000u ? 8 : x < 1000000000u ? 9 : 10;
+        for (int i = n - 1; i >= 0; --i) { buf[i] = (char)('0' + (int)(x % 10u)); x /= 10u; }
+        return n;
+    }
+    int n = 0;
+    for (unsigned long long t = v; t; t /= 10ull) ++n;            // (rare: 64-bit division is emulated)
+    for (int i = n - 1; i >= 0; --i) { buf[i] = (char)('0' + (int)(v % 10ull)); v /= 10ull; }
     return n;
 }
 __device__ __forceinline__ int fmt_int(char* buf, long long v) {
@@ -91,48 +104,102 @@ struct WarpEmit {                        // the whole warp on one row: all lanes
     char* dst; long long n = 0; int lane;
     __device__ __forceinline__ void small(const char* buf, int len) { if (lane < len) dst[n + lane] = buf[lane]; n += len; }   // len <= 32
     __device__ __forceinline__ void ch(char c) { if (lane == 0) dst[n] = c; n += 1; }
-    __device__ __forceinline__ void raw(const char* src, int len) { for (int i = lane; i < len; i += 32) dst[n + i] = src[i]; n += len; }
-    __device__ __forceinline__ void codes(const uint8_t* src, int len, bool lower) {
-        for (int i = lane; i < len; i += 32) dst[n + i] = (char)((lower ? "acgt" : "ACGT")[src[i] & 3]);
+    // four loads in flight per lane: a copy is a chain of global round trips otherwise
+    __device__ __forceinline__ void raw(const char* src, int len) {
+        for (int i = lane; i < len; i += 128) {
+            char v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = i + 32 * u < len ? src[i + 32 * u] : (char)0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (i + 32 * u < len) dst[n + i + 32 * u] = v[u];
+        }
         n += len;
+    }
+    __device__ __forceinline__ void codes(const uint8_t* src, int len, bool lower) {
+        const char* alphabet = lower ? "acgt" : "ACGT";
+        for (int i = lane; i < len; i += 128) {
+            uint8_t v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = i + 32 * u < len ? src[i + 32 * u] : (uint8_t)0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (i + 32 * u < len) dst[n + i + 32 * u] = alphabet[v[u] & 3];
+        }
+        n += len;
+    }
+};
+
+// The numbers of a row as text.  The measure pass (one lane per row) prints them once -- into the row's scratch --
+// and the write pass (a whole warp per row) only copies: printing them there again would be the same work done
+// by 32 lanes at once.  Fields: 0 name_start, 1 name_end, 2 rVAF, 3 expression, 4 min_cov, 5 start_off,
+// 6 ref_expression, 7 cluster id, 8 cluster size.
+struct PrintNums {
+    char* store;                 // the row's scratch, or nullptr
+    bool ok = true;
+    __device__ __forceinline__ int get(int field, const Row& w, char* buf, const char** out) {
+        int n;
+        char* dst = store ? store + KM_FMT_FIELD_BYTES * field : buf;       // (the longest: '-' + 16 digits + ".ddd" = 21)
+        switch (field) {
+            case 0: n = fmt_int(dst, w.name_start); break;
+            case 1: n = fmt_int(dst, w.name_end); break;
+            case 2: n = fmt_fixed(dst, w.rvaf, 3); break;
+            case 3: n = fmt_fixed(dst, w.expr, 1); break;
+            case 4: n = fmt_int(dst, (long long)w.min_cov); break;
+            case 5: n = fmt_int(dst, w.start_off); break;
+            case 6: n = fmt_fixed(dst, w.ref_expr, 1); break;
+            case 7: n = fmt_int(dst, w.cluster_id); break;
+            default: n = fmt_int(dst, w.cluster_n); break;
+        }
+        if (n < 0) { ok = false; n = 0; }
+        if (store) store[KM_FMT_FIELD_BYTES * KM_FMT_FIELDS + field] = (char)n;
+        *out = dst;
+        return n;
+    }
+};
+struct StoredNums {
+    const char* store;
+    bool ok = true;
+    __device__ __forceinline__ int get(int field, const Row&, char*, const char** out) {
+        *out = store + KM_FMT_FIELD_BYTES * field;
+        return (int)store[KM_FMT_FIELD_BYTES * KM_FMT_FIELDS + field];
     }
 };
 
 // one line: "{db}\t{query}\t{type}\t{name}\t{rVAF:.3f}\t{expr:.1f}\t{min_cov}\t{start_off}\t{seq}\t{ref_expr:.1f}\t{ref_seq}\t{info}\n"
 // Returns false if a number could not be printed here.
-template <class E>
-__device__ __forceinline__ bool format_row(E& e, const FormatView& F, const WalkView& W, const ResultView& R, int k, const Row& w) {
+template <class E, class N>
+__device__ __forceinline__ bool format_row(E& e, N& nums, const FormatView& F, const WalkView& W, const ResultView& R, int k, const Row& w) {
     const int t = w.target;
     const uint8_t* tcodes = W.codes + W.seq_off[t];
     const char* pseq = R.seq_pool + R.path_seq_off[w.path_id];
     char buf[40];
-    bool ok = true;
+    const char* s;
+    int n;
     e.raw(F.db_name, F.db_len); e.ch('\t');
     e.raw(F.names + F.name_off[t], (int)(F.name_off[t + 1] - F.name_off[t])); e.ch('\t');
     e.small(km_type_name[w.type], km_type_len[w.type]); e.ch('\t');
     if (w.type != 0) {                 // "{}:{}/{}:{}" (MutationFinder.py:483-488); Reference -> empty name
-        e.small(buf, fmt_int(buf, w.name_start)); e.ch(':');
+        n = nums.get(0, w, buf, &s); e.small(s, n); e.ch(':');
         e.codes(tcodes + w.del_begin + k - 1, w.del_len, true); e.ch('/');
         e.raw(pseq + w.ins_begin + k - 1, w.ins_len); e.ch(':');
-        e.small(buf, fmt_int(buf, w.name_end));
+        n = nums.get(1, w, buf, &s); e.small(s, n);
     }
     e.ch('\t');
-    int n = fmt_fixed(buf, w.rvaf, 3); ok &= n >= 0; e.small(buf, n < 0 ? 0 : n); e.ch('\t');
-    n = fmt_fixed(buf, w.expr, 1); ok &= n >= 0; e.small(buf, n < 0 ? 0 : n); e.ch('\t');
-    e.small(buf, fmt_int(buf, (long long)w.min_cov)); e.ch('\t');
-    e.small(buf, fmt_int(buf, w.start_off)); e.ch('\t');
+    n = nums.get(2, w, buf, &s); e.small(s, n); e.ch('\t');
+    n = nums.get(3, w, buf, &s); e.small(s, n); e.ch('\t');
+    n = nums.get(4, w, buf, &s); e.small(s, n); e.ch('\t');
+    n = nums.get(5, w, buf, &s); e.small(s, n); e.ch('\t');
     if (w.var_end > w.var_begin) e.raw(pseq + w.var_begin, w.var_end - w.var_begin + k - 1);
     e.ch('\t');
-    n = fmt_fixed(buf, w.ref_expr, 1); ok &= n >= 0; e.small(buf, n < 0 ? 0 : n); e.ch('\t');
+    n = nums.get(6, w, buf, &s); e.small(s, n); e.ch('\t');
     if (w.ref_end > w.ref_begin) e.codes(tcodes + w.ref_begin, w.ref_end - w.ref_begin + k - 1, false);
     e.ch('\t');
     if (w.kind == 0) e.small("vs_ref", 6);
     else {
-        e.small("cluster ", 8); e.small(buf, fmt_int(buf, w.cluster_id));
-        e.small(" n=", 3); e.small(buf, fmt_int(buf, w.cluster_n));
+        e.small("cluster ", 8); n = nums.get(7, w, buf, &s); e.small(s, n);
+        e.small(" n=", 3); n = nums.get(8, w, buf, &s); e.small(s, n);
     }
     e.ch('\n');
-    return ok;
+    return nums.ok;
 }
 
 // natsortkey of the variant name without spelling it: the name is "" (Reference) or
@@ -157,7 +224,10 @@ __device__ __forceinline__ int name_cmp(const WalkView& W, const ResultView& R, 
     const bool ea = a.type == 0, eb = b.type == 0;
     if (ea || eb) return ea == eb ? 0 : (ea ? -1 : 1);
     if (a.name_start != b.name_start) return a.name_start < b.name_start ? -1 : 1;      // (never negative: start + k + offset)
-    for (int i = 0;; ++i) {
+    // the vs_ref row and the cluster row of one variant spell the same bases: no need to walk them
+    const bool same_text = a.target == b.target && a.path_id == b.path_id && a.del_begin == b.del_begin && a.del_len == b.del_len &&
+                           a.ins_begin == b.ins_begin && a.ins_len == b.ins_len;
+    if (!same_text) for (int i = 0;; ++i) {
         const int ca = name_text_at(W, R, k, a, i), cb = name_text_at(W, R, k, b, i);
         if (ca != cb) return ca < cb ? -1 : 1;           // -1 (end) sorts first: the shorter text is a prefix
         if (ca < 0) break;
@@ -206,7 +276,9 @@ __global__ void __launch_bounds__(128) km_format_measure_kernel(WalkView W, Resu
         if (w.path_id < 0 || w.path_id >= R.path_cap || R.path_seq_off[w.path_id] < 0 || w.type < 0 || w.type > 5 ||
             (w.type != 0 && (w.name_start < 0 || w.name_end < 0))) { ok = false; F.row_len[first + r] = 0; continue; }
         CountEmit e;
-        ok &= format_row(e, F, W, R, k, w);
+        PrintNums nums;
+        nums.store = F.row_num + (size_t)KM_FMT_ROW_BYTES * (size_t)(first + r);
+        ok &= format_row(e, nums, F, W, R, k, w);
         F.row_len[first + r] = (int32_t)e.n;
         total += e.n;
     }
@@ -268,7 +340,9 @@ __global__ void __launch_bounds__(128) km_format_write_kernel(WalkView W, Result
         WarpEmit e;
         e.dst = block + F.row_pos[first + r];
         e.lane = lane;
-        format_row(e, F, W, R, k, w);
+        StoredNums nums;
+        nums.store = F.row_num + (size_t)KM_FMT_ROW_BYTES * (size_t)(first + r);
+        format_row(e, nums, F, W, R, k, w);
     }
 }
 
