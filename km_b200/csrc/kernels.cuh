@@ -306,7 +306,9 @@ __global__ void __launch_bounds__(32 * KM_WALK_WARPS) km_walk_kernel(TableView T
 // larger ones (the pass is latency-bound: resident CTAs are throughput).  The GENERAL pass uses
 // per-CTA scratch in HBM and takes the rest, plus any target a shared-memory pass deferred
 // (KM_ST_RETRY_LARGE).
+#ifndef KM_SMALL_NODES
 #define KM_SMALL_NODES 512      // largest shared-memory class (graph nodes incl. the two caps)
+#endif
 // resident CTAs per SM the register allocation aims at: the 512-node class is held to 5 by its shared memory
 #ifndef KM_GRAPH_SMALL_MINB
 #define KM_GRAPH_SMALL_MINB 5
@@ -314,7 +316,9 @@ __global__ void __launch_bounds__(32 * KM_WALK_WARPS) km_walk_kernel(TableView T
 #ifndef KM_GRAPH_TINY_MINB
 #define KM_GRAPH_TINY_MINB 8
 #endif
+#ifndef KM_TINY_NODES
 #define KM_TINY_NODES 256
+#endif
 #define KM_SMALL_CAND 64
 #define KM_SMALL_PATHS 64
 #define KM_SMALL_COLS 8
