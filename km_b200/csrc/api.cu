@@ -921,8 +921,8 @@ static int plan_layout(km_plan* p) {
     }
     const size_t n_chunks = p->chunk_target.size();
     const int64_t n_node = p->n_node = p->node_off[n], n_hash = p->n_hash = p->hash_off[n], n_code = p->n_code = p->seq_off[n];
-    p->grid_tiny = std::max(1, std::min(n, t->sm_count * 10));
-    p->grid_graph = std::max(1, std::min(n, t->sm_count * 5));
+    p->grid_tiny = std::max(1, std::min(n, t->sm_count * KM_GRAPH_TINY_GRID));
+    p->grid_graph = std::max(1, std::min(n, t->sm_count * KM_GRAPH_SMALL_GRID));
     p->grid_large = std::max(1, std::min(n, t->sm_count * 2));
     const ScratchLayout L0 = make_layout(maxcap, KM_MAX_PATHS, KM_MAX_PATHS, KM_MAX_COLS, 0);
     const int32_t path_cap = p->path_cap, row_cap = p->row_cap;

@@ -316,6 +316,13 @@ __global__ void __launch_bounds__(32 * KM_WALK_WARPS) km_walk_kernel(TableView T
 #ifndef KM_GRAPH_TINY_MINB
 #define KM_GRAPH_TINY_MINB 8
 #endif
+// persistent CTAs per SM launched for each class (they take targets from a shared cursor)
+#ifndef KM_GRAPH_SMALL_GRID
+#define KM_GRAPH_SMALL_GRID 5
+#endif
+#ifndef KM_GRAPH_TINY_GRID
+#define KM_GRAPH_TINY_GRID 10
+#endif
 #ifndef KM_TINY_NODES
 #define KM_TINY_NODES 256
 #endif
