@@ -57,6 +57,10 @@ int km_table_build_synthetic(km_table* t, uint64_t seed, uint64_t n_keys);
 /* C19 / config 5: count canonical k-mers of `n_reads` reads (ASCII, concatenated, offsets
  * [n_reads+1]) on device; k-mers containing a non-ACGT letter are skipped. */
 int km_table_count_reads(km_table* t, const char* reads_host, const int64_t* offsets_host, int64_t n_reads);
+/* The same straight from a FASTA / FASTQ file, plain or .gz (zlib is looked up at run time), "-" = stdin: the
+ * input side of `jellyfish count` (example/run_leucegene.sh:22).  min_qual_char > 0: bases whose FASTQ quality
+ * character is below it count as N (`-Q`).  Reads and bases seen come back through the two counters. */
+int km_table_count_file(km_table* t, const char* path, int min_qual_char, uint64_t* n_reads, uint64_t* n_bases);
 /* drop entries with count < min_count (jellyfish count -L); returns remaining through *n_left */
 int km_table_drop_below(km_table* t, uint32_t min_count, uint64_t* n_left);
 /* `jellyfish dump`: every (canonical key, count) record of the table (of this shard in cohort mode), in no

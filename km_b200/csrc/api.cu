@@ -529,6 +529,131 @@ extern "C" int km_table_drop_below(km_table* t, uint32_t min_count, uint64_t* n_
 
 
 
+// ---- counting straight from FASTA / FASTQ files (plain or .gz) ------------------------------------------
+// zlib is looked up at run time (dlopen), like the driver's virtual-memory entry points: the library loads on
+// a machine without it and only .gz input is refused there.
+#include <dlfcn.h>
+struct ZLib {
+    void* (*open)(const char*, const char*) = nullptr;
+    int (*read)(void*, void*, unsigned) = nullptr;
+    int (*close)(void*) = nullptr;
+    int (*buffer)(void*, unsigned) = nullptr;
+    bool tried = false, ok = false;
+};
+static ZLib g_z;
+static bool zlib_load() {
+    if (g_z.tried) return g_z.ok;
+    g_z.tried = true;
+    void* h = dlopen("libz.so.1", RTLD_NOW | RTLD_LOCAL);
+    if (!h) h = dlopen("libz.so", RTLD_NOW | RTLD_LOCAL);
+    if (!h) return false;
+    g_z.open = (void* (*)(const char*, const char*))dlsym(h, "gzopen");
+    g_z.read = (int (*)(void*, void*, unsigned))dlsym(h, "gzread");
+    g_z.close = (int (*)(void*))dlsym(h, "gzclose");
+    g_z.buffer = (int (*)(void*, unsigned))dlsym(h, "gzbuffer");
+    g_z.ok = g_z.open && g_z.read && g_z.close;
+    return g_z.ok;
+}
+struct LineReader {                 // lines of a plain or gzip file, without their line ends
+    FILE* f = nullptr; void* gz = nullptr;
+    std::vector<char> buf; size_t pos = 0, end = 0; bool eof = false;
+    bool fill() {
+        if (eof) return false;
+        if (pos > 0) { memmove(buf.data(), buf.data() + pos, end - pos); end -= pos; pos = 0; }
+        if (end == buf.size()) buf.resize(buf.size() * 2);
+        const size_t room = buf.size() - end;
+        long got = gz ? (long)g_z.read(gz, buf.data() + end, (unsigned)std::min<size_t>(room, 1u << 30)) : (long)fread(buf.data() + end, 1, room, f);
+        if (got <= 0) { eof = true; return false; }
+        end += (size_t)got;
+        return true;
+    }
+    // next line into (*p, *n); false at end of file
+    bool next(const char** p, size_t* n) {
+        for (;;) {
+            const char* nl = (const char*)memchr(buf.data() + pos, '\n', end - pos);
+            if (nl) {
+                *p = buf.data() + pos; *n = (size_t)(nl - *p);
+                pos = (size_t)(nl - buf.data()) + 1;
+                if (*n && (*p)[*n - 1] == '\r') --*n;
+                return true;
+            }
+            if (!fill()) {
+                if (pos < end) { *p = buf.data() + pos; *n = end - pos; pos = end; if (*n && (*p)[*n - 1] == '\r') --*n; return true; }
+                return false;
+            }
+        }
+    }
+};
+
+// `jellyfish count` input side: every sequence of the file goes through km_table_count_reads in batches of ~64 M
+// bases.  FASTQ records are four lines; with min_qual_char > 0 a base whose quality character is below it
+// counts as N (jellyfish count -Q).  FASTA sequences may span lines.
+extern "C" int km_table_count_file(km_table* t, const char* path, int min_qual_char, uint64_t* n_reads_out, uint64_t* n_bases_out) {
+    if (!t || !path) return fail(KM_E_ARG, "km_table_count_file: bad argument");
+    LineReader R;
+    const size_t plen = strlen(path);
+    const bool gz = plen > 3 && strcmp(path + plen - 3, ".gz") == 0;
+    if (gz) {
+        if (!zlib_load()) return fail(KM_E_IO, "%s: libz.so.1 not found, decompress the file first", path);
+        R.gz = g_z.open(path, "rb");
+        if (!R.gz) return fail(KM_E_IO, "cannot open %s", path);
+        if (g_z.buffer) g_z.buffer(R.gz, 1u << 20);
+    } else {
+        R.f = strcmp(path, "-") == 0 ? stdin : fopen(path, "rb");
+        if (!R.f) return fail(KM_E_IO, "cannot open %s", path);
+    }
+    R.buf.resize((size_t)8 << 20);
+    std::vector<char> blob;
+    std::vector<int64_t> off(1, 0);
+    blob.reserve((size_t)80 << 20);
+    uint64_t n_reads = 0, n_bases = 0;
+    int rc = 0;
+    auto flush = [&]() -> int {
+        if (off.size() <= 1) return 0;
+        const int r = km_table_count_reads(t, blob.data(), off.data(), (int64_t)off.size() - 1);
+        blob.clear(); off.assign(1, 0);
+        return r;
+    };
+    auto end_read = [&]() -> int {
+        if ((int64_t)blob.size() == off.back()) return 0;          // empty sequence
+        n_reads += 1; n_bases += (uint64_t)((int64_t)blob.size() - off.back());
+        off.push_back((int64_t)blob.size());
+        return blob.size() >= ((size_t)64 << 20) ? flush() : 0;
+    };
+    const char* ln; size_t n;
+    bool first = true, fastq = false;
+    while (!rc && R.next(&ln, &n)) {
+        if (first) {
+            if (!n) continue;
+            first = false;
+            if (ln[0] == '@') fastq = true;
+            else if (ln[0] != '>') { rc = fail(KM_E_IO, "%s: neither FASTA nor FASTQ", path); break; }
+        }
+        if (fastq) {
+            if (!n) continue;                              // stray blank line between records
+            // ln is the header; then sequence, '+', quality
+            const char* sq; size_t sn;
+            if (!R.next(&sq, &sn)) break;
+            const size_t at = blob.size();
+            blob.insert(blob.end(), sq, sq + sn);          // (sq stays valid until the next call of next())
+            const char* pl; size_t pn; const char* ql; size_t qn;
+            if (!R.next(&pl, &pn) || !R.next(&ql, &qn)) { rc = end_read(); break; }
+            if (min_qual_char > 0 && qn == sn)
+                for (size_t i = 0; i < sn; ++i) if ((unsigned char)ql[i] < (unsigned)min_qual_char) blob[at + i] = 'N';
+            rc = end_read();
+        } else {
+            if (n && ln[0] == '>') rc = end_read();
+            else blob.insert(blob.end(), ln, ln + n);
+        }
+    }
+    if (!rc) rc = end_read();
+    if (!rc) rc = flush();
+    if (R.gz) g_z.close(R.gz); else if (R.f && R.f != stdin) fclose(R.f);
+    if (n_reads_out) *n_reads_out = n_reads;
+    if (n_bases_out) *n_bases_out = n_bases;
+    return rc;
+}
+
 // ---- export: `jellyfish dump` and a binary/sorted writer ---------------------------------------------
 extern "C" int km_table_export(km_table* t, uint64_t* keys, uint32_t* counts, uint64_t cap, uint64_t* n_out) {
     if (!t || !n_out || (cap && (!keys || !counts))) return fail(KM_E_ARG, "km_table_export: bad argument");

@@ -119,6 +119,14 @@ class Table:
         np.cumsum([len(r) for r in reads], out=off[1:])
         check(lib().km_table_count_reads(self._h, blob, off.ctypes.data, len(reads)))
 
+    def count_file(self, path, min_qual=None):
+        """Counts the k-mers of a FASTA / FASTQ file (plain or .gz) read by the library itself; min_qual = the
+        `-Q` quality character (or its byte value).  Returns (reads, bases)."""
+        q = 0 if min_qual is None else (ord(min_qual[0]) if isinstance(min_qual, str) else int(min_qual))
+        nr, nb = ctypes.c_uint64(), ctypes.c_uint64()
+        check(lib().km_table_count_file(self._h, os.fsencode(path), q, ctypes.byref(nr), ctypes.byref(nb)))
+        return int(nr.value), int(nb.value)
+
     def count_reads_blob(self, blob, offsets):
         """The same from one bytes object of concatenated reads and its int64 offsets [n_reads + 1]."""
         off = np.ascontiguousarray(offsets, dtype=np.int64)

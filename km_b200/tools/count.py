@@ -65,8 +65,9 @@ def read_sequences(fn, min_qual=None):
             raise ValueError("%s: neither FASTA nor FASTQ" % fn)
 
 
-def count_into(table, files, min_qual=None, batch_bases=64 << 20):
-    """Streams the reads of `files` through km_table_count_reads in batches; returns (reads, bases)."""
+def count_into(table, files, min_qual=None, batch_bases=64 << 20, native=True):
+    """Counts the reads of `files` into `table`; returns (reads, bases).  native: the library's own reader
+    (km_table_count_file); otherwise the files are parsed here and handed over in batches."""
     n_reads = n_bases = 0
     chunk, size = [], 0
 
@@ -78,6 +79,12 @@ def count_into(table, files, min_qual=None, batch_bases=64 << 20):
             table.count_reads_blob(b"".join(chunk), off)
             chunk, size = [], 0
     for fn in files:
+        if native:
+            flush()
+            r, b = table.count_file(fn, min_qual)          # the library reads and parses the file itself
+            n_reads += r
+            n_bases += b
+            continue
         for seq in read_sequences(fn, min_qual):
             chunk.append(seq)
             size += len(seq)

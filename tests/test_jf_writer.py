@@ -155,3 +155,32 @@ def test_km_count_cli_equals_host_count(engine, tmp_path):
     h, k2, c2 = jf_format.read_jf(out)
     assert dict(zip(k2.tolist(), c2.tolist())) == {k: v for k, v in host.items() if v >= 2}
     assert h["canonical"] is True and h["key_len"] == 62
+
+
+@pytest.mark.gpu
+def test_native_reader_equals_python_reader(engine, tmp_path):
+    """km_table_count_file (FASTA with wrapped lines and CRLF, FASTQ, .gz, quality mask) == the same sequences
+    parsed by tools/count.read_sequences and counted through count_reads."""
+    from km_b200.tools.count import count_into
+    rng = np.random.default_rng(3)
+    seqs = ["".join("ACGT"[i] for i in rng.integers(0, 4, size=int(n))) for n in rng.integers(40, 400, size=60)]
+    fa = tmp_path / "wrapped.fa"
+    with open(fa, "w", newline="") as f:
+        for i, s in enumerate(seqs):
+            f.write(">s%d some text\r\n" % i)
+            for j in range(0, len(s), 60):
+                f.write(s[j:j + 60] + "\r\n")
+            f.write("\r\n" if i % 7 == 0 else "")
+    quals = ["".join(rng.choice(list("#+5I"), size=len(s), p=[0.01, 0.01, 0.01, 0.97])) for s in seqs]
+    fq = str(tmp_path / "r.fq.gz")
+    _write_fastq(fq, seqs, quals, gz=True)
+    for files, q in (([str(fa)], None), ([fq], None), ([fq], ord("+")), ([str(fa), fq], ord("5"))):
+        a = engine.Table.create(capacity=1 << 16)
+        b = engine.Table.create(capacity=1 << 16)
+        ra = count_into(a, files, q, native=True)
+        rb = count_into(b, files, q, native=False)
+        assert ra == rb and ra[0] == 60 * len(files)
+        ka, ca = a.export()
+        kb, cb = b.export()
+        oa, ob = np.argsort(ka), np.argsort(kb)
+        assert (ka[oa] == kb[ob]).all() and (ca[oa] == cb[ob]).all() and len(ka) > 500
