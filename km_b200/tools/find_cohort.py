@@ -1,0 +1,53 @@
+"""`km find_cohort -t <target(s)> <db.jf> [<db.jf> ...]` -- one invocation over MANY samples.
+
+km's users loop `km find_mutation` over their .jf files in the shell (example/run_leucegene.sh:29-35) and
+concatenate; here the targets are read and packed once, every database is loaded into HBM in turn, and each
+sample is ONE km_find_text call (text formatted on the device).  The output is what that loop prints: one header,
+then for every sample the rows of every target -- the Database column tells the samples apart, which is what
+`km find_report -f table` aggregates (find_report.py:290-327).  The reference has no such sub-command."""
+import os
+import sys
+import time
+
+from .. import engine
+from ..utils import MutationFinder as umf
+from ..utils import Sequence as us
+from ..utils import common as uc
+
+
+def _jf_files(args):
+    out = []
+    for p in args:
+        if os.path.isdir(p):
+            out.extend(sorted(os.path.join(p, f) for f in os.listdir(p) if f.endswith(".jf")))
+        else:
+            out.append(p)
+    return out
+
+
+def main_find_cohort(args, argparser):
+    time_start = time.time()
+    for name, value in vars(args).items():
+        sys.stdout.write("#" + str(name) + ":" + str(value) + "\n")
+    umf.MutationFinder.output_header()
+    seq_files = []
+    for tgt in args.target_fn:
+        seq_files.extend(uc.target_2_seqfiles([tgt]))
+    packed, k_seen = None, None
+    for jf_fn in _jf_files(args.jellyfish_fn):
+        table = engine.Table.open_jf(jf_fn, device=args.device)
+        if packed is None or table.k != k_seen:
+            names, seqs = [], []
+            for seq_f in seq_files:
+                ref_seqs, _ = uc.file_2_seq(seq_f)
+                ref = us.RefSeq("".join(ref_seqs), os.path.splitext(os.path.basename(seq_f))[0], table.k)   # raises on a non-linear target
+                names.append(ref.name)
+                seqs.append(ref.seq)
+            packed, k_seen = engine.PackedTargets(seqs, names), table.k
+        text, status = table.find_text(packed, jf_fn, count=args.count, ratio=args.ratio, steps=args.steps,
+                                       branchs=args.branchs, nodes=args.nodes)
+        sys.stdout.write(text)
+        for i, st in enumerate(status.tolist()):
+            engine.raise_for_status(st, packed.names[i], args.nodes)
+        table.close()
+    sys.stdout.write("#Elapsed time:" + str(time.time() - time_start) + "\n")

@@ -479,3 +479,41 @@ def test_text_call_survives_capacity_retries(engine, synth_small):
     got, status = t.find_text(packed, "synth_small.jf", extra_nodes=2, n_sub=3)
     assert got == want and (status & ~np.uint32(16) == 0).all()
     assert t.last_timing["retries"] > 0
+
+
+@pytest.mark.gpu
+def test_find_cohort_equals_find_mutation_per_sample(engine, bundled):
+    """`km find_cohort -t <catalog dir> <all .jf>`: the rows printed for every sample are the rows
+    `km find_mutation <catalog dir> <that .jf>` prints, in the order of the databases on the command line."""
+    import io
+    import sys
+    from argparse import Namespace
+    from km_b200.tools import find_cohort as fc
+    from km_b200.tools import find_mutation as fm
+    cwd = os.getcwd()
+    os.chdir(bundled)
+    try:
+        samples = sorted(f for f in os.listdir("./data/jf") if f.endswith(".jf"))
+        assert len(samples) == 5
+        catalog = "./data/catalog/GRCh38"
+
+        def run(main, args):
+            old = sys.stdout
+            sys.stdout = buf = io.StringIO()
+            try:
+                main(args, None)
+            finally:
+                sys.stdout = old
+            return [l for l in buf.getvalue().split("\n") if l and not l.startswith("#")]
+        base = dict(count=5, ratio=0.05, steps=500, branchs=10, nodes=10000)
+        cohort = run(fc.main_find_cohort, Namespace(target_fn=[catalog], jellyfish_fn=["./data/jf"], device=0, **base))
+        want = [cohort[0]]
+        for s in samples:
+            rows = run(fm.main_find_mut, Namespace(target_fn=[catalog], jellyfish_fn="./data/jf/" + s, graphical=False,
+                                                   verbose=False, debug=False, **base))
+            assert rows[0] == cohort[0]
+            want += rows[1:]
+        assert cohort == want
+        assert len(cohort) > 5 * 9
+    finally:
+        os.chdir(cwd)
