@@ -227,8 +227,10 @@ int64_t km_result_text(const km_result* r, const char* db_name, const char* name
 /* `km find_mutation` for a whole batch as ONE call: host buffers in (sequences + offsets, query names +
  * offsets), the sorted TSV text out (read it with km_result_text, same db_name / names; km_result_get
  * gives the per-target status).  The batch runs as n_sub sub-batches in flight at once (0 = choose), so
- * copies, kernels and the host-side text building overlap.  Same text as km_find_batch +
- * km_result_format_all. */
+ * copies and kernels overlap; the text itself is formatted ON THE DEVICE (csrc/format.h) and every sub-batch's
+ * share comes back with one copy, straight into its place in the result's pinned buffer.  Byte for byte the
+ * text of km_find_batch + km_result_format_all (the host formatter, which a sub-batch falls back to when the
+ * device declines: text capacity, a magnitude >= 2^52; KM_HOST_FORMAT=1 forces it). */
 int km_find_text(km_table* t, const char* seqs_host, const int64_t* offsets, int32_t n_targets, const km_find_params* params,
                  const char* db_name, const char* names_host, const int64_t* name_off, int32_t n_sub, km_result** out);
 
