@@ -9,13 +9,14 @@ SNV/insertion/deletion/tandem-duplication variants) against the ~2e9-distinct-31
 Targets shard across ranks (each rank works on its own 10,000-target panel -> weak scaling), the
 table is replicated, there is no collective on the data path.
 
-  value   targets/s, whole job, inputs resident in HBM: K launches of the two kernels
-          (km_find_plan_launch), CUDA events on the launch stream, max over ranks
-  e2e     the same through the reference-facing call with HOST buffers: km_find_batch (H2D of
-          the sequences, kernels, D2H of rows and spelled paths) + km_result_format_all (the TSV
-          text `km find_mutation` prints), wall clock bracketed by barriers + synchronize
-  roofline      walk kernel: algorithmic lookups (n_ref_kmers + 4*n_nodes per target)
-                x 32 B / its CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs
+  value   targets/s, whole job, inputs resident in HBM: K launches of the resident plan (seven kernels per
+          launch: reference probe, two walks, schedule, three graph passes; km_find_plan_launch), CUDA events
+          on the launch stream, max over ranks
+  e2e     the same through the reference-facing call with HOST buffers: km_find_text (H2D of sequences and
+          names, kernels, the text `km find_mutation` prints formatted on the device, D2H of that text), wall
+          clock bracketed by barriers + synchronize; its text is compared with the host formatter's every run
+  roofline      reference-probe kernel: the lookups it issues x 32 B / its CUDA-event duration, against
+                MEASURED_PEAKS.json hbm_gbs and against the random-gather rate measured in the same run
   lookup        2^30 device-resident canonical k-mer lookups (km_query_batch_device)
   cpu_baseline  oracle/ (the CPU restatement of the reference) on a bounded sample, all host cores
 """
