@@ -159,7 +159,9 @@ struct km_table {
     Arena dev_find, pin_find;  // km_find_batch workspace, reused across calls
     // km_find_text runs a batch as several sub-batches in flight at once: each has its own workspace,
     // stream and events, kept across calls
-    struct Lane { Arena dev, pin; cudaStream_t stream = nullptr, side = nullptr; cudaEvent_t ev[8] = {}, fork = nullptr, join = nullptr; };
+    // (the host vectors of a lane's last plan are kept too: their capacity saves the next plan its allocations)
+    struct PlanVecs { std::vector<int64_t> seq_off, node_off, hash_off, pack_off; std::vector<int32_t> chunk_target, chunk_start, extra; };
+    struct Lane { Arena dev, pin; cudaStream_t stream = nullptr, side = nullptr; cudaEvent_t ev[8] = {}, fork = nullptr, join = nullptr; PlanVecs vecs; };
     std::vector<std::unique_ptr<Lane>> lanes;
     std::shared_ptr<PinPool> pool = std::make_shared<PinPool>();   // result buffers (outlive the table if a result does)
     int sm_count = 148;
@@ -1010,6 +1012,7 @@ struct km_plan {
     unsigned long long bytes_h2d = 0;
     size_t upload_bytes = 0;      // span of the input block on the device (plan_layout)
     const void* h_stage = nullptr;   // the staged copy of that block in pinned memory (plan_stage)
+    const char* targets_ext = nullptr;   // km_find_text: the caller's sequences, valid for the whole call -- no private copy
     bool defer_upload = false;    // plan_init stops after staging: the caller enqueues (km_find_text, one thread at a time)
     // device-side text (km_find_text): query names + database name go up with the input block, FormatView F
     // describes the buffers of format.h
@@ -1146,7 +1149,7 @@ static int plan_stage(km_plan* p, cudaStream_t s) {
     int32_t* h_ct = p->pin->take<int32_t>(n_chunks);
     int32_t* h_cs = p->pin->take<int32_t>(n_chunks);
     if (n_chunks) { memcpy(h_ct, p->chunk_target.data(), 4 * n_chunks); memcpy(h_cs, p->chunk_start.data(), 4 * n_chunks); }
-    memcpy(h_codes, p->targets.data(), p->n_code);          // letters; km_encode_kernel turns them into codes on the device
+    memcpy(h_codes, p->targets_ext ? p->targets_ext : p->targets.data(), p->n_code);   // letters; km_encode_kernel turns them into codes on the device
     memcpy(h_seq_off, p->seq_off.data(), 8 * (n + 1));
     memcpy(h_node_off, p->node_off.data(), 8 * (n + 1));
     memcpy(h_hash_off, p->hash_off.data(), 8 * (n + 1));
@@ -1311,8 +1314,15 @@ static int plan_download(km_plan* p, cudaStream_t s, km_result* res, bool want_g
     return 0;
 }
 
+// a plan on a lane borrows the lane's host vectors (and hands them back, km_find_text) for their capacity
+static void plan_swap_vecs(km_plan* p, km_table::PlanVecs& v) {
+    p->seq_off.swap(v.seq_off); p->node_off.swap(v.node_off); p->hash_off.swap(v.hash_off); p->pack_off.swap(v.pack_off);
+    p->chunk_target.swap(v.chunk_target); p->chunk_start.swap(v.chunk_start); p->extra.swap(v.extra);
+}
+
 static int plan_init(km_table* t, const char* seqs, const int64_t* offsets, int32_t n, const km_find_params* params, km_plan* p,
                      bool borrow_arena, km_table::Lane* lane = nullptr) {
+    if (lane) plan_swap_vecs(p, lane->vecs);
     p->t = t; p->n = n; p->prm = *params;
     p->stream = lane ? lane->stream : t->stream;
     p->side = lane ? lane->side : t->side;
@@ -1321,7 +1331,7 @@ static int plan_init(km_table* t, const char* seqs, const int64_t* offsets, int3
     p->join = lane ? lane->join : t->join;
     if (p->prm.steps > 60000 || p->prm.branchs > 250) return fail(KM_E_ARG, "steps must be <= 60000 and branchs <= 250");
     const int64_t total = n ? offsets[n] : 0;
-    p->targets.assign(seqs ? seqs : "", (size_t)total);
+    if (!p->targets_ext) p->targets.assign(seqs ? seqs : "", (size_t)total);
     p->seq_off.assign(1, 0);
     if (n) p->seq_off.assign(offsets, offsets + n + 1);
     int64_t n_ref = 0;
@@ -1857,6 +1867,7 @@ extern "C" int km_find_text(km_table* t, const char* seqs, const int64_t* offset
                 plans[(size_t)c].reset(new km_plan());
                 km_plan* p = plans[(size_t)c].get();
                 p->fmt = true; p->fmt_names = names + name_off[lo]; p->fmt_name_off = no.data(); p->fmt_db = db;
+                p->targets_ext = seqs + offsets[lo];
                 const int lane_ix = next_lane.fetch_add(1);
                 g_trace_obj = &tr; g_trace_sub = c;
                 g_trace_mark = tr.on ? +[](void* o, const char* w, int sub) { static_cast<Trace*>(o)->mark(w, sub); } : nullptr;
@@ -1884,7 +1895,7 @@ extern "C" int km_find_text(km_table* t, const char* seqs, const int64_t* offset
                 const bool host_format = pr->dev_text_flags != 0;
                 if (host_format) {        // the device declined (capacity, or a number it does not print): rows come back, host formats
                     if (int rc = plan_download(p, p->stream, pr, false)) return fail_all(rc);
-                    pr->targets.swap(p->targets);
+                    pr->targets.assign(p->targets_ext, (size_t)p->n_code);
                     format_range(pr, 0, pr->n_targets, db.c_str(), names + name_off[lo], no.data(), spill[(size_t)c]);
                     len = (long long)spill[(size_t)c].size();
                 }
@@ -1910,6 +1921,7 @@ extern "C" int km_find_text(km_table* t, const char* seqs, const int64_t* offset
                     pr->bytes_d2h += (unsigned long long)len;
                 }
                 tr.mark("text placed", c);
+                plan_swap_vecs(p, t->lanes[(size_t)lane_ix]->vecs);
                 latch.done();
             });
         }
