@@ -263,6 +263,9 @@ __global__ void __launch_bounds__(256) km_get_child_kernel(TableView T, const ui
 #ifndef KM_WALK_WARPS
 #define KM_WALK_WARPS 4
 #endif
+#ifndef KM_WALK_MINB
+#define KM_WALK_MINB 9       // (measured: 7 -> 0.271, 8 -> 0.262, 9 -> 0.256, 10 -> 0.296 ms) CTAs per SM the shared-memory walk's registers are budgeted for
+#endif
 // (measured: 4 warps per CTA and room for ~100 registers -- no spills -- beat 8 warps at 64 registers, 0.307 vs 0.333 ms)
 #ifndef KM_PROBE_WARPS
 #define KM_PROBE_WARPS 4
@@ -278,7 +281,7 @@ __global__ void __launch_bounds__(32 * KM_PROBE_WARPS, KM_PROBE_MINB) km_ref_pro
     ref_probe_chunk(ctx, T, W, P, W.chunk_target[ch], W.chunk_start[ch]);
 }
 
-__global__ void __launch_bounds__(32 * KM_WALK_WARPS, 8) km_walk_small_kernel(TableView T, WalkView W, FindParams P) {
+__global__ void __launch_bounds__(32 * KM_WALK_WARPS, KM_WALK_MINB) km_walk_small_kernel(TableView T, WalkView W, FindParams P) {
     __shared__ WalkSmall M[KM_WALK_WARPS];
     WarpCtx ctx;
     const int t = (int)blockIdx.x * KM_WALK_WARPS + (int)(threadIdx.x >> 5);
