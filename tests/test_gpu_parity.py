@@ -517,3 +517,24 @@ def test_find_cohort_equals_find_mutation_per_sample(engine, bundled):
         assert len(cohort) > 5 * 9
     finally:
         os.chdir(cwd)
+
+
+@pytest.mark.gpu
+def test_empty_and_single_target_batches(engine, synth_small):
+    """Edge sizes of the one-call path: no target at all, one target, and more sub-batches asked for than
+    there are targets."""
+    t = engine.Table.create(capacity=len(synth_small["keys"]) + 1024)
+    t.insert(synth_small["keys"], synth_small["counts"].astype(np.uint32))
+    text, status = t.find_text(engine.PackedTargets([], []), "x.jf")
+    assert text == "" and len(status) == 0
+    res = t.find_batch([])
+    assert len(res.status) == 0
+    one = engine.PackedTargets(synth_small["targets"][:1], synth_small["names"][:1])
+    want = t.find_batch(one.sequences).format_target(0, "x.jf", synth_small["names"][0])
+    for n_sub in (0, 1, 6):
+        got, status = t.find_text(one, "x.jf", n_sub=n_sub)
+        assert got == want and len(status) == 1
+    three = engine.PackedTargets(synth_small["targets"][:3], synth_small["names"][:3])
+    a, _ = t.find_text(three, "x.jf", n_sub=1)
+    b, _ = t.find_text(three, "x.jf", n_sub=8)
+    assert a == b and a.count("\n") >= 3
