@@ -32,7 +32,8 @@ struct FormatView {
 #define KM_FMT_FIELD_BYTES 24
 #define KM_FMT_ROW_BYTES 256
 
-#if KM_DEVICE_BUILD
+// (the device code below is compiled by format_kernels.cu only; the other translation units see FormatView)
+#if KM_DEVICE_BUILD && defined(KM_FORMAT_KERNELS)
 
 // decimal digits of v straight into buf (no temporary: a local array indexed by a loop counter lives in local
 // memory, and every digit then costs a round trip to L1); returns their number
@@ -346,6 +347,6 @@ __global__ void __launch_bounds__(128) km_format_write_kernel(WalkView W, Result
     }
 }
 
-#endif  // KM_DEVICE_BUILD
+#endif  // KM_DEVICE_BUILD && KM_FORMAT_KERNELS
 
 }  // namespace km

@@ -1,0 +1,147 @@
+// Kernels of stages 2 and 3 of find_mutation (sm_100a): the scheduler that sorts targets into work lists and the
+// per-target graph / paths / FP64 quantification pass (graph.h, quant.h) -- MutationFinder.graph_analysis,
+// quantify_paths, quantify_clusters (km/utils/MutationFinder.py:496-811), Graph.py, PathQuant.py.
+#include <cuda_runtime.h>
+
+#include "quant.h"
+#include "find_config.h"
+#include "find_launch.h"
+#include "../../include/km_b200.h"
+
+namespace km {
+
+// ---- K4 + K5: graph, paths, FP64 quantification; persistent CTAs over targets -----------------
+// Three passes share one body.  The two SHARED-MEMORY passes keep the whole per-target working set
+// (adjacency, both shortest-path trees, candidate edges, solver matrices) on chip; a target goes to the
+// smallest class its graph fits, so the many small graphs run with twice the CTAs per SM of the
+// larger ones (the pass is latency-bound: resident CTAs are throughput).  The GENERAL pass uses
+// per-CTA scratch in HBM and takes the rest, plus any target a shared-memory pass deferred
+// (KM_ST_RETRY_LARGE).
+#define KM_ST_FATAL (KM_ST_BAD_BASE | KM_ST_DUP_KMER | KM_ST_NODE_OVERFLOW | KM_ST_NODE_LIMIT | KM_ST_TOO_SHORT)
+
+// NODES = node capacity of a shared-memory class, 0 = the general pass
+// Work lists of the three graph passes: every target whose walk succeeded goes to the smallest class
+// its graph fits, each list ordered by descending node count (64 size bins; a counting sort in one CTA).
+__global__ void __launch_bounds__(1024) km_schedule_kernel(WalkView W, ResultView R) {
+    __shared__ int hist[3][64], start[3][64];
+    const int n = W.n_targets;
+    for (int i = threadIdx.x; i < 3 * 64; i += blockDim.x) (&hist[0][0])[i] = 0;
+    __syncthreads();
+    auto classify = [&](int t, int* bin) -> int {
+        if (W.status[t] & KM_ST_FATAL) return -1;
+        const int cap = (int)(W.node_off[t + 1] - W.node_off[t]);
+        const int n_all = W.n_nodes[t] < cap ? W.n_nodes[t] : cap;
+        const int kept2 = W.n_kept[t] + 2;
+        const int b = 63 - (kept2 >> 3);
+        *bin = b < 0 ? 0 : b;                                         // bin 0 = the largest graphs
+        if (n_all <= KM_TINY_NODES - 2 && kept2 <= KM_TINY_NODES) return 0;
+        if (n_all <= KM_SMALL_NODES - 2 && kept2 <= KM_SMALL_NODES) return 1;
+        return 2;
+    };
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+        int b;
+        const int c = classify(t, &b);
+        if (c < 0) { R.t_n[t] = 0; R.t_n_paths[t] = 0; R.t_path_first[t] = 0; R.t_n_rows[t] = 0; R.t_row_first[t] = 0; }
+        else atomicAdd(&hist[c][b], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        int at = 0;
+        for (int b = 0; b < 64; ++b) { start[threadIdx.x][b] = at; at += hist[threadIdx.x][b]; }
+        R.sched_count[threadIdx.x] = at;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+        int b;
+        const int c = classify(t, &b);
+        if (c >= 0) R.sched_order[(size_t)c * n + atomicAdd(&start[c][b], 1)] = t;
+    }
+}
+
+template <int NODES>
+__global__ void __launch_bounds__(KM_CTA, NODES == KM_SMALL_NODES ? KM_GRAPH_SMALL_MINB : (NODES ? KM_GRAPH_TINY_MINB : 4)) km_graph_kernel(TableView T, WalkView W, ScratchLayout SL, ResultView R) {
+    extern __shared__ __align__(16) char km_smem[];
+    __shared__ int sh[32];
+    CtaCtx ctx;
+    const GraphScratch S = NODES ? carve(class_layout(NODES ? NODES : 4), km_smem, 1)
+                                 : carve(SL, SL.base + (size_t)blockIdx.x * SL.stride, 0);
+    // Targets come from this pass's work list (km_schedule_kernel: largest graphs first), handed out one
+    // at a time from a global cursor: their cost varies several-fold (a tandem duplication has six times
+    // the novel nodes of a substitution), a fixed deal leaves most CTAs idle behind the unluckiest one.
+    const int cls = NODES == KM_TINY_NODES ? 0 : NODES == KM_SMALL_NODES ? 1 : 2;
+    unsigned long long* next = R.used + 4 + cls;
+    const int32_t* order = R.sched_order + (size_t)cls * W.n_targets;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int i = (int)atomicAdd(next, 1ull);
+            sh[12] = i < R.sched_count[cls] ? order[i] : -1;
+        }
+        __syncthreads();
+        const int t = sh[12];
+        if (t < 0) break;
+        if (NODES == 0 && threadIdx.x == 0) atomicAnd(&W.status[t], ~KM_ST_RETRY_LARGE);
+        GraphDims d;
+        ctx.rot = t & 3;
+#ifdef KM_PHASE_TIMERS
+        const long long tc0 = clock64();
+#endif
+        if (!graph_target(ctx, T, W, S, R, t, &d, sh)) continue;
+        emit_rows(ctx, T, W, S, R, t, d, sh[2], sh[3], sh[6], sh);
+        __syncthreads();
+#ifdef KM_PHASE_TIMERS
+        if (threadIdx.x == 0 && t < KM_DEBUG_TARGETS) km_target_cycles[t] = (unsigned int)(clock64() - tc0);
+#endif
+    }
+}
+
+
+}  // namespace km
+
+using namespace km;
+
+cudaError_t km_find_kernels_init() {
+    cudaError_t e = cudaFuncSetAttribute(km_graph_kernel<KM_TINY_NODES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)class_layout(KM_TINY_NODES).stride);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(km_graph_kernel<KM_SMALL_NODES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)class_layout(KM_SMALL_NODES).stride);
+}
+cudaError_t km_launch_schedule(const WalkView& W, const ResultView& R, cudaStream_t s) {
+    km_schedule_kernel<<<1, 1024, 0, s>>>(W, R);
+    return cudaGetLastError();
+}
+cudaError_t km_launch_graph(int cls, int grid, const TableView& T, const WalkView& W, const ScratchLayout& SL, const ResultView& R,
+                            cudaStream_t s) {
+    if (cls == 0) km_graph_kernel<KM_TINY_NODES><<<grid, KM_CTA, class_layout(KM_TINY_NODES).stride, s>>>(T, W, SL, R);
+    else if (cls == 1) km_graph_kernel<KM_SMALL_NODES><<<grid, KM_CTA, class_layout(KM_SMALL_NODES).stride, s>>>(T, W, SL, R);
+    else km_graph_kernel<0><<<grid, KM_CTA, 0, s>>>(T, W, SL, R);
+    return cudaGetLastError();
+}
+
+// ---- measurement helpers (the phase timers live in this translation unit) -----------------------------------
+static int dbg_fail(const char*) { return KM_E_ARG; }
+#define fail(code, ...) dbg_fail("")
+#define CU(call) do { if ((call) != cudaSuccess) return KM_E_CUDA; } while (0)
+extern "C" int km_debug_phase_cycles(unsigned long long* out32, int reset) {
+#ifdef KM_PHASE_TIMERS
+    if (out32) CU(cudaMemcpyFromSymbol(out32, km_phase_cycles, 64 * sizeof(unsigned long long)));
+    if (reset) { unsigned long long z[64] = {0}; CU(cudaMemcpyToSymbol(km_phase_cycles, z, sizeof(z))); }
+    return 0;
+#else
+    (void)out32; (void)reset;
+    return fail(KM_E_ARG, "library built without KM_PHASE_TIMERS");
+#endif
+}
+
+extern "C" int km_debug_target_cycles(unsigned int* out, int n) {
+#ifdef KM_PHASE_TIMERS
+    if (!out || n < 0 || n > KM_DEBUG_TARGETS) return fail(KM_E_ARG, "km_debug_target_cycles: bad argument");
+    CU(cudaMemcpyFromSymbol(out, km_target_cycles, (size_t)n * sizeof(unsigned int)));
+    return 0;
+#else
+    (void)out; (void)n;
+    return fail(KM_E_ARG, "library built without KM_PHASE_TIMERS");
+#endif
+}
+

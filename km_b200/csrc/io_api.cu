@@ -1,0 +1,264 @@
+// C ABI of libkm_b200.so, part 2: the files either side of the table -- FASTA / FASTQ reads in
+// (km_table_count_file, the input side of `jellyfish count`, example/run_leucegene.sh:22), Jellyfish
+// binary/sorted databases in and out (km_table_open_jf: km/utils/Jellyfish.py:23-45; km_table_write_jf).
+#include "host_common.h"
+
+// ---- counting straight from FASTA / FASTQ files (plain or .gz) ------------------------------------------
+// zlib is looked up at run time (dlopen), like the driver's virtual-memory entry points: the library loads on
+// a machine without it and only .gz input is refused there.
+#include <dlfcn.h>
+struct ZLib {
+    void* (*open)(const char*, const char*) = nullptr;
+    int (*read)(void*, void*, unsigned) = nullptr;
+    int (*close)(void*) = nullptr;
+    int (*buffer)(void*, unsigned) = nullptr;
+    bool tried = false, ok = false;
+};
+static ZLib g_z;
+static bool zlib_load() {
+    if (g_z.tried) return g_z.ok;
+    g_z.tried = true;
+    void* h = dlopen("libz.so.1", RTLD_NOW | RTLD_LOCAL);
+    if (!h) h = dlopen("libz.so", RTLD_NOW | RTLD_LOCAL);
+    if (!h) return false;
+    g_z.open = (void* (*)(const char*, const char*))dlsym(h, "gzopen");
+    g_z.read = (int (*)(void*, void*, unsigned))dlsym(h, "gzread");
+    g_z.close = (int (*)(void*))dlsym(h, "gzclose");
+    g_z.buffer = (int (*)(void*, unsigned))dlsym(h, "gzbuffer");
+    g_z.ok = g_z.open && g_z.read && g_z.close;
+    return g_z.ok;
+}
+struct LineReader {                 // lines of a plain or gzip file, without their line ends
+    FILE* f = nullptr; void* gz = nullptr;
+    std::vector<char> buf; size_t pos = 0, end = 0; bool eof = false;
+    bool fill() {
+        if (eof) return false;
+        if (pos > 0) { memmove(buf.data(), buf.data() + pos, end - pos); end -= pos; pos = 0; }
+        if (end == buf.size()) buf.resize(buf.size() * 2);
+        const size_t room = buf.size() - end;
+        long got = gz ? (long)g_z.read(gz, buf.data() + end, (unsigned)std::min<size_t>(room, 1u << 30)) : (long)fread(buf.data() + end, 1, room, f);
+        if (got <= 0) { eof = true; return false; }
+        end += (size_t)got;
+        return true;
+    }
+    // next line into (*p, *n); false at end of file
+    bool next(const char** p, size_t* n) {
+        for (;;) {
+            const char* nl = (const char*)memchr(buf.data() + pos, '\n', end - pos);
+            if (nl) {
+                *p = buf.data() + pos; *n = (size_t)(nl - *p);
+                pos = (size_t)(nl - buf.data()) + 1;
+                if (*n && (*p)[*n - 1] == '\r') --*n;
+                return true;
+            }
+            if (!fill()) {
+                if (pos < end) { *p = buf.data() + pos; *n = end - pos; pos = end; if (*n && (*p)[*n - 1] == '\r') --*n; return true; }
+                return false;
+            }
+        }
+    }
+};
+
+// `jellyfish count` input side: every sequence of the file goes through km_table_count_reads in batches of ~64 M
+// bases.  FASTQ records are four lines; with min_qual_char > 0 a base whose quality character is below it
+// counts as N (jellyfish count -Q).  FASTA sequences may span lines.
+extern "C" int km_table_count_file(km_table* t, const char* path, int min_qual_char, uint64_t* n_reads_out, uint64_t* n_bases_out) {
+    if (!t || !path) return fail(KM_E_ARG, "km_table_count_file: bad argument");
+    LineReader R;
+    const size_t plen = strlen(path);
+    const bool gz = plen > 3 && strcmp(path + plen - 3, ".gz") == 0;
+    if (gz) {
+        if (!zlib_load()) return fail(KM_E_IO, "%s: libz.so.1 not found, decompress the file first", path);
+        R.gz = g_z.open(path, "rb");
+        if (!R.gz) return fail(KM_E_IO, "cannot open %s", path);
+        if (g_z.buffer) g_z.buffer(R.gz, 1u << 20);
+    } else {
+        R.f = strcmp(path, "-") == 0 ? stdin : fopen(path, "rb");
+        if (!R.f) return fail(KM_E_IO, "cannot open %s", path);
+    }
+    R.buf.resize((size_t)8 << 20);
+    std::vector<char> blob;
+    std::vector<int64_t> off(1, 0);
+    blob.reserve((size_t)80 << 20);
+    uint64_t n_reads = 0, n_bases = 0;
+    int rc = 0;
+    auto flush = [&]() -> int {
+        if (off.size() <= 1) return 0;
+        const int r = km_table_count_reads(t, blob.data(), off.data(), (int64_t)off.size() - 1);
+        blob.clear(); off.assign(1, 0);
+        return r;
+    };
+    auto end_read = [&]() -> int {
+        if ((int64_t)blob.size() == off.back()) return 0;          // empty sequence
+        n_reads += 1; n_bases += (uint64_t)((int64_t)blob.size() - off.back());
+        off.push_back((int64_t)blob.size());
+        return blob.size() >= ((size_t)64 << 20) ? flush() : 0;
+    };
+    const char* ln; size_t n;
+    bool first = true, fastq = false;
+    while (!rc && R.next(&ln, &n)) {
+        if (first) {
+            if (!n) continue;
+            first = false;
+            if (ln[0] == '@') fastq = true;
+            else if (ln[0] != '>') { rc = fail(KM_E_IO, "%s: neither FASTA nor FASTQ", path); break; }
+        }
+        if (fastq) {
+            if (!n) continue;                              // stray blank line between records
+            // ln is the header; then sequence, '+', quality
+            const char* sq; size_t sn;
+            if (!R.next(&sq, &sn)) break;
+            const size_t at = blob.size();
+            blob.insert(blob.end(), sq, sq + sn);          // (sq stays valid until the next call of next())
+            const char* pl; size_t pn; const char* ql; size_t qn;
+            if (!R.next(&pl, &pn) || !R.next(&ql, &qn)) { rc = end_read(); break; }
+            if (min_qual_char > 0 && qn == sn)
+                for (size_t i = 0; i < sn; ++i) if ((unsigned char)ql[i] < (unsigned)min_qual_char) blob[at + i] = 'N';
+            rc = end_read();
+        } else {
+            if (n && ln[0] == '>') rc = end_read();
+            else blob.insert(blob.end(), ln, ln + n);
+        }
+    }
+    if (!rc) rc = end_read();
+    if (!rc) rc = flush();
+    if (R.gz) g_z.close(R.gz); else if (R.f && R.f != stdin) fclose(R.f);
+    if (n_reads_out) *n_reads_out = n_reads;
+    if (n_bases_out) *n_bases_out = n_bases;
+    return rc;
+}
+
+// Column i of the 32 x 62 binary matrix written into the header.  Any matrix works as long as the records are
+// sorted by it; this one is a fixed pseudo-random one.
+static uint32_t jf_matrix_column(int i) {
+    uint64_t z = 0x6B6D5F62323030ull + (uint64_t)i;          // splitmix64 finaliser (host copy)
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31;
+    return (uint32_t)(z >> 17);
+}
+
+// A Jellyfish 2.x `binary/sorted` file: "%09d" header length, JSON header (NUL-padded to 8 bytes), then
+// ceil(key_len/8)-byte LE key + counter_len-byte LE count per record.  Verified on the five files bundled with
+// km (tests/test_jf_writer.py): the records are sorted by pos = M * key over GF(2), masked to
+// `size`, where bit b of the key selects column c-1-b of `matrix1`.  Ties (unobserved in the bundled files)
+// are broken by key.  The writer emits its own matrix, so readers that binary-search by position stay consistent.
+extern "C" int km_table_write_jf(km_table* t, const char* path, uint32_t counter_len) {
+    if (!t || !path) return fail(KM_E_ARG, "km_table_write_jf: bad argument");
+    if (counter_len == 0) counter_len = 4;
+    if (counter_len > 8) return fail(KM_E_ARG, "km_table_write_jf: counter_len must be 1..8");
+    std::vector<uint64_t> keys((size_t)t->n_keys);
+    std::vector<uint32_t> counts((size_t)t->n_keys);
+    uint64_t n = 0;
+    if (int rc = km_table_export(t, keys.data(), counts.data(), t->n_keys, &n)) return rc;
+    if (n != t->n_keys) return fail(KM_E_ARG, "km_table_write_jf: table holds %llu records, expected %llu", (unsigned long long)n, (unsigned long long)t->n_keys);
+    const int kbits = 2 * t->k, kbytes = (kbits + 7) / 8;
+    int lsize = 10;
+    while (lsize < 32 && (1ull << lsize) < 2 * n) ++lsize;
+    const uint64_t size = 1ull << lsize, mask = size - 1;
+    // byte-sliced matrix-vector product: tab[j][v] = XOR of the columns selected by byte j of the key
+    std::vector<uint32_t> col((size_t)kbits);
+    for (int i = 0; i < kbits; ++i) col[(size_t)i] = jf_matrix_column(i);
+    std::vector<uint32_t> tab((size_t)8 * 256, 0);
+    for (int j = 0; j < 8; ++j)
+        for (int v = 0; v < 256; ++v) {
+            uint32_t x = 0;
+            for (int b = 0; b < 8; ++b) { const int bit = 8 * j + b; if (((v >> b) & 1) && bit < kbits) x ^= col[(size_t)(kbits - 1 - bit)]; }
+            tab[(size_t)j * 256 + (size_t)v] = x;
+        }
+    std::vector<uint64_t> order((size_t)n);      // pos << 32 | index would lose ties on the key: sort indices by (pos, key)
+    std::vector<uint32_t> pos((size_t)n);
+    for (uint64_t i = 0; i < n; ++i) {
+        uint32_t x = 0;
+        for (int j = 0; j < 8; ++j) x ^= tab[(size_t)j * 256 + ((keys[i] >> (8 * j)) & 0xFF)];
+        pos[i] = (uint32_t)(x & mask);
+        order[i] = i;
+    }
+    std::sort(order.begin(), order.end(), [&](uint64_t a, uint64_t b) { return pos[a] != pos[b] ? pos[a] < pos[b] : keys[a] < keys[b]; });
+    std::string js = "{\"alignment\":8,\"canonical\":";
+    js += t->canonical ? "true" : "false";
+    js += ",\"cmdline\":[\"km_b200\",\"count\"],\"counter_len\":" + std::to_string(counter_len) + ",\"format\":\"binary/sorted\",\"key_len\":" +
+          std::to_string(kbits) + ",\"matrix1\":{\"c\":" + std::to_string(kbits) + ",\"columns\":[";
+    for (int i = 0; i < kbits; ++i) { if (i) js += ','; js += std::to_string(col[(size_t)i]); }
+    js += "],\"r\":32},\"max_reprobe\":126,\"reprobes\":[1";
+    for (int i = 1; i <= 126; ++i) js += "," + std::to_string(i * (i + 1) / 2);
+    js += "],\"size\":" + std::to_string(size) + ",\"val_len\":" + std::to_string(8 * counter_len > 12 ? 12 : 8 * counter_len) + "}";
+    while ((9 + js.size()) % 8) js += '\0';
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(KM_E_IO, "cannot write %s", path);
+    char digits[16];
+    snprintf(digits, sizeof(digits), "%09zu", js.size());
+    bool ok = fwrite(digits, 1, 9, f) == 9 && fwrite(js.data(), 1, js.size(), f) == js.size();
+    const size_t rec = (size_t)kbytes + counter_len;
+    std::vector<unsigned char> buf;
+    buf.reserve(rec << 16);
+    const uint64_t cmax = counter_len >= 4 ? 0xFFFFFFFFull : ((1ull << (8 * counter_len)) - 1);
+    for (uint64_t i = 0; ok && i < n; ++i) {
+        const uint64_t key = keys[order[i]];
+        const uint64_t cnt = std::min<uint64_t>(counts[order[i]], cmax);       // a narrow counter saturates
+        for (int b = 0; b < kbytes; ++b) buf.push_back((unsigned char)(key >> (8 * b)));
+        for (uint32_t b = 0; b < counter_len; ++b) buf.push_back((unsigned char)(b < 8 ? cnt >> (8 * b) : 0));
+        if (buf.size() >= (rec << 16)) { ok = fwrite(buf.data(), 1, buf.size(), f) == buf.size(); buf.clear(); }
+    }
+    if (ok && !buf.empty()) ok = fwrite(buf.data(), 1, buf.size(), f) == buf.size();
+    if (fclose(f) != 0) ok = false;
+    if (!ok) return fail(KM_E_IO, "short write to %s", path);
+    return 0;
+}
+// ---- .jf loader (binary/sorted) ---------------------------------------
+static bool json_field(const std::string& js, const char* name, std::string* out) {
+    std::string pat = std::string("\"") + name + "\"";
+    size_t p = js.find(pat);
+    if (p == std::string::npos) return false;
+    p = js.find(':', p + pat.size());
+    if (p == std::string::npos) return false;
+    ++p;
+    while (p < js.size() && isspace((unsigned char)js[p])) ++p;
+    size_t e = p;
+    if (js[p] == '"') { e = js.find('"', p + 1); if (e == std::string::npos) return false; *out = js.substr(p + 1, e - p - 1); return true; }
+    while (e < js.size() && js[e] != ',' && js[e] != '}' && !isspace((unsigned char)js[e])) ++e;
+    *out = js.substr(p, e - p);
+    return true;
+}
+
+extern "C" int km_table_open_jf(const char* path, int device, km_table** out) {
+    if (!path || !out) return fail(KM_E_ARG, "km_table_open_jf: null argument");
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(KM_E_IO, "cannot open %s", path);
+    char digits[10] = {0};
+    if (fread(digits, 1, 9, f) != 9) { fclose(f); return fail(KM_E_IO, "%s: truncated header", path); }
+    for (int i = 0; i < 9; ++i) if (!isdigit((unsigned char)digits[i])) { fclose(f); return fail(KM_E_IO, "%s: not a Jellyfish file (no header length)", path); }
+    const long hlen = atol(digits);
+    std::string js((size_t)hlen, '\0');
+    if (fread(&js[0], 1, (size_t)hlen, f) != (size_t)hlen) { fclose(f); return fail(KM_E_IO, "%s: truncated header", path); }
+    std::string fmt, canon, key_len, counter_len;
+    if (!json_field(js, "format", &fmt) || !json_field(js, "canonical", &canon) || !json_field(js, "key_len", &key_len) ||
+        !json_field(js, "counter_len", &counter_len)) { fclose(f); return fail(KM_E_IO, "%s: header lacks format/canonical/key_len/counter_len", path); }
+    if (fmt != "binary/sorted") { fclose(f); return fail(KM_E_IO, "%s: unsupported format '%s' (only binary/sorted)", path, fmt.c_str()); }
+    const int kbits = atoi(key_len.c_str()), cbytes = atoi(counter_len.c_str());
+    if (kbits < 2 || kbits > 62 || (kbits & 1) || cbytes < 1 || cbytes > 8) { fclose(f); return fail(KM_E_IO, "%s: key_len %d / counter_len %d not supported", path, kbits, cbytes); }
+    const int kbytes = (kbits + 7) / 8, rec = kbytes + cbytes;
+    fseek(f, 0, SEEK_END);
+    const long fsize = ftell(f);
+    const long payload = fsize - 9 - hlen;
+    if (payload < 0 || payload % rec) { fclose(f); return fail(KM_E_IO, "%s: payload of %ld bytes is not a multiple of %d", path, payload, rec); }
+    const uint64_t n = (uint64_t)(payload / rec);
+    std::vector<unsigned char> raw((size_t)payload);
+    fseek(f, 9 + hlen, SEEK_SET);
+    if (payload && fread(raw.data(), 1, (size_t)payload, f) != (size_t)payload) { fclose(f); return fail(KM_E_IO, "%s: short read", path); }
+    fclose(f);
+    std::vector<uint64_t> keys(n);
+    std::vector<uint32_t> counts(n);
+    for (uint64_t i = 0; i < n; ++i) {
+        const unsigned char* p = raw.data() + i * rec;
+        uint64_t key = 0, cnt = 0;
+        for (int b = 0; b < kbytes; ++b) key |= (uint64_t)p[b] << (8 * b);
+        for (int b = 0; b < cbytes; ++b) cnt |= (uint64_t)p[kbytes + b] << (8 * b);
+        keys[i] = key;
+        counts[i] = cnt > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)cnt;
+    }
+    km_table* t = nullptr;
+    if (int rc = km_table_create(device, kbits / 2, canon == "true", std::max<uint64_t>(n, 1024), &t)) return rc;
+    if (int rc = km_table_insert(t, keys.data(), counts.data(), n, KM_INSERT_OVERWRITE)) { km_table_close(t); return rc; }
+    *out = t;
+    return 0;
+}
+

@@ -1,15 +1,13 @@
-// __global__ entry points of libkm_b200.so (sm_100a).  Each kernel is a thin wrapper over
-// the stage functions in table.h / walk.h / graph.h / quant.h.
+// __global__ entry points of the k-mer table (sm_100a): maintenance, counting from reads, export, the batched
+// probe (Jellyfish.query / get_child, km/utils/Jellyfish.py:47-72) and the measurement kernels.  Thin wrappers
+// over the device functions of table.h.
 #pragma once
 #include <cuda_runtime.h>
 
-#include "quant.h"
-#include "walk_small.h"
+#include "table.h"
 #include "synth.h"
 
 namespace km {
-
-#define KM_CTA 128
 
 // ---- table maintenance ----------------------------------------------------------------
 __global__ void km_table_clear_kernel(Bucket* buckets, uint64_t n) {
@@ -105,35 +103,6 @@ __global__ void km_table_filter_kernel(TableView src, TableView dst, uint32_t mi
         mine += r > 0;
     }
     if (mine) atomicAdd(n_new, mine);
-}
-
-// Once per upload, one warp per target: letters -> codes in place (A0 C1 G2 T3, anything else 255; the
-// general walk reads these) and the 2-bit packed copy the probe and shared-memory walk kernels read
-// (16 bases per word, first base in the top bits, >= 2 zero words after each target).
-__global__ void km_encode_kernel(uint8_t* seq, const int64_t* seq_off, uint32_t* pack, const int64_t* pack_off, uint8_t* pre_bad,
-                                 int n_targets) {
-    const int t = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
-    if (t >= n_targets) return;
-    const int64_t s0 = seq_off[t], w0 = pack_off[t];
-    const int len = (int)(seq_off[t + 1] - s0), nw = (int)(pack_off[t + 1] - w0);
-    bool bad = false;
-    for (int w = lane; w < nw; w += 32) {
-        uint32_t word = 0;
-        for (int j = 0; j < 16; ++j) {
-            const int pos = 16 * w + j;
-            uint32_t c = 0;
-            if (pos < len) {
-                const uint8_t ch = seq[s0 + pos];
-                c = ch == 'A' ? 0u : ch == 'C' ? 1u : ch == 'G' ? 2u : ch == 'T' ? 3u : 255u;
-                seq[s0 + pos] = (uint8_t)c;
-                if (c > 3u) { bad = true; c = 0u; }
-            }
-            word = (word << 2) | c;
-        }
-        pack[w0 + w] = word;
-    }
-    bad = __any_sync(0xFFFFFFFFu, bad);
-    if (lane == 0) pre_bad[t] = bad ? 1 : 0;
 }
 
 // `jellyfish dump`: every (canonical key, count) record of this shard, compacted into two arrays in no
@@ -257,164 +226,6 @@ __global__ void __launch_bounds__(256) km_get_child_kernel(TableView T, const ui
     }
 }
 
-// ---- K3: walk, one WARP per target ----------------------------------------------------------
-// Two launches: the shared-memory walk takes every target of ordinary size (walk_small.h); the
-// general walk, whose per-target state lives in HBM, takes the targets the first one deferred.
-#ifndef KM_WALK_WARPS
-#define KM_WALK_WARPS 4
-#endif
-#ifndef KM_WALK_MINB
-#define KM_WALK_MINB 9       // (measured: 7 -> 0.271, 8 -> 0.262, 9 -> 0.256, 10 -> 0.296 ms) CTAs per SM the shared-memory walk's registers are budgeted for
-#endif
-// (measured: 4 warps per CTA and room for ~100 registers -- no spills -- beat 8 warps at 64 registers, 0.307 vs 0.333 ms)
-#ifndef KM_PROBE_WARPS
-#define KM_PROBE_WARPS 4
-#endif
-#ifndef KM_PROBE_MINB
-#define KM_PROBE_MINB 5
-#endif
-// K3a: level 0 of every walk, one warp per 32 reference k-mers, flat over the batch
-__global__ void __launch_bounds__(32 * KM_PROBE_WARPS, KM_PROBE_MINB) km_ref_probe_kernel(TableView T, WalkView W, FindParams P) {
-    WarpCtx ctx;
-    const int ch = (int)blockIdx.x * KM_PROBE_WARPS + (int)(threadIdx.x >> 5);
-    if (ch >= W.n_chunks) return;
-    ref_probe_chunk(ctx, T, W, P, W.chunk_target[ch], W.chunk_start[ch]);
-}
-
-__global__ void __launch_bounds__(32 * KM_WALK_WARPS, KM_WALK_MINB) km_walk_small_kernel(TableView T, WalkView W, FindParams P) {
-    __shared__ WalkSmall M[KM_WALK_WARPS];
-    WarpCtx ctx;
-    const int t = (int)blockIdx.x * KM_WALK_WARPS + (int)(threadIdx.x >> 5);
-    if (t >= W.n_targets) return;
-    const TargetGeom g = target_geom(W, t, T.k);
-    if (!walk_small_fits(g)) { if ((threadIdx.x & 31) == 0) W.status[t] = KM_ST_WALK_DEFER; return; }   // also drops the probe's limit flag
-    walk_small_target(ctx, T, W, P, t, M[threadIdx.x >> 5]);
-}
-
-__global__ void __launch_bounds__(32 * KM_WALK_WARPS) km_walk_kernel(TableView T, WalkView W, FindParams P) {
-    WarpCtx ctx;
-    const int t = (int)blockIdx.x * KM_WALK_WARPS + (int)(threadIdx.x >> 5);
-    if (t >= W.n_targets) return;
-    if (!(W.status[t] & KM_ST_WALK_DEFER)) return;
-    __syncwarp();
-    if ((threadIdx.x & 31) == 0) { W.status[t] = 0; W.lookups[t] = 0; W.n_kept[t] = 0; }
-    __syncwarp();
-    walk_target(ctx, T, W, P, t);
-}
-
-// ---- K4 + K5: graph, paths, FP64 quantification; persistent CTAs over targets -----------------
-// Three passes share one body.  The two SHARED-MEMORY passes keep the whole per-target working set
-// (adjacency, both shortest-path trees, candidate edges, solver matrices) on chip; a target goes to the
-// smallest class its graph fits, so the many small graphs run with twice the CTAs per SM of the
-// larger ones (the pass is latency-bound: resident CTAs are throughput).  The GENERAL pass uses
-// per-CTA scratch in HBM and takes the rest, plus any target a shared-memory pass deferred
-// (KM_ST_RETRY_LARGE).
-#ifndef KM_SMALL_NODES
-#define KM_SMALL_NODES 512      // largest shared-memory class (graph nodes incl. the two caps)
-#endif
-// resident CTAs per SM the register allocation aims at: the 512-node class is held to 5 by its shared memory
-#ifndef KM_GRAPH_SMALL_MINB
-#define KM_GRAPH_SMALL_MINB 5
-#endif
-#ifndef KM_GRAPH_TINY_MINB
-#define KM_GRAPH_TINY_MINB 8
-#endif
-// persistent CTAs per SM launched for each class (they take targets from a shared cursor)
-#ifndef KM_GRAPH_SMALL_GRID
-#define KM_GRAPH_SMALL_GRID 5
-#endif
-#ifndef KM_GRAPH_TINY_GRID
-#define KM_GRAPH_TINY_GRID 10
-#endif
-#ifndef KM_TINY_NODES
-#define KM_TINY_NODES 256
-#endif
-#define KM_SMALL_CAND 64
-#define KM_SMALL_PATHS 64
-#define KM_SMALL_COLS 8
-
-__host__ __device__ inline ScratchLayout class_layout(int nodes) {
-    return make_layout(nodes - 2, KM_SMALL_CAND, KM_SMALL_PATHS, KM_SMALL_COLS, 1);
-}
-
-#define KM_ST_FATAL (KM_ST_BAD_BASE | KM_ST_DUP_KMER | KM_ST_NODE_OVERFLOW | KM_ST_NODE_LIMIT | KM_ST_TOO_SHORT)
-
-// NODES = node capacity of a shared-memory class, 0 = the general pass
-// Work lists of the three graph passes: every target whose walk succeeded goes to the smallest class
-// its graph fits, each list ordered by descending node count (64 size bins; a counting sort in one CTA).
-__global__ void __launch_bounds__(1024) km_schedule_kernel(WalkView W, ResultView R) {
-    __shared__ int hist[3][64], start[3][64];
-    const int n = W.n_targets;
-    for (int i = threadIdx.x; i < 3 * 64; i += blockDim.x) (&hist[0][0])[i] = 0;
-    __syncthreads();
-    auto classify = [&](int t, int* bin) -> int {
-        if (W.status[t] & KM_ST_FATAL) return -1;
-        const int cap = (int)(W.node_off[t + 1] - W.node_off[t]);
-        const int n_all = W.n_nodes[t] < cap ? W.n_nodes[t] : cap;
-        const int kept2 = W.n_kept[t] + 2;
-        const int b = 63 - (kept2 >> 3);
-        *bin = b < 0 ? 0 : b;                                         // bin 0 = the largest graphs
-        if (n_all <= KM_TINY_NODES - 2 && kept2 <= KM_TINY_NODES) return 0;
-        if (n_all <= KM_SMALL_NODES - 2 && kept2 <= KM_SMALL_NODES) return 1;
-        return 2;
-    };
-    for (int t = threadIdx.x; t < n; t += blockDim.x) {
-        int b;
-        const int c = classify(t, &b);
-        if (c < 0) { R.t_n[t] = 0; R.t_n_paths[t] = 0; R.t_path_first[t] = 0; R.t_n_rows[t] = 0; R.t_row_first[t] = 0; }
-        else atomicAdd(&hist[c][b], 1);
-    }
-    __syncthreads();
-    if (threadIdx.x < 3) {
-        int at = 0;
-        for (int b = 0; b < 64; ++b) { start[threadIdx.x][b] = at; at += hist[threadIdx.x][b]; }
-        R.sched_count[threadIdx.x] = at;
-    }
-    __syncthreads();
-    for (int t = threadIdx.x; t < n; t += blockDim.x) {
-        int b;
-        const int c = classify(t, &b);
-        if (c >= 0) R.sched_order[(size_t)c * n + atomicAdd(&start[c][b], 1)] = t;
-    }
-}
-
-template <int NODES>
-__global__ void __launch_bounds__(KM_CTA, NODES == KM_SMALL_NODES ? KM_GRAPH_SMALL_MINB : (NODES ? KM_GRAPH_TINY_MINB : 4)) km_graph_kernel(TableView T, WalkView W, ScratchLayout SL, ResultView R) {
-    extern __shared__ __align__(16) char km_smem[];
-    __shared__ int sh[32];
-    CtaCtx ctx;
-    const GraphScratch S = NODES ? carve(class_layout(NODES ? NODES : 4), km_smem, 1)
-                                 : carve(SL, SL.base + (size_t)blockIdx.x * SL.stride, 0);
-    // Targets come from this pass's work list (km_schedule_kernel: largest graphs first), handed out one
-    // at a time from a global cursor: their cost varies several-fold (a tandem duplication has six times
-    // the novel nodes of a substitution), a fixed deal leaves most CTAs idle behind the unluckiest one.
-    const int cls = NODES == KM_TINY_NODES ? 0 : NODES == KM_SMALL_NODES ? 1 : 2;
-    unsigned long long* next = R.used + 4 + cls;
-    const int32_t* order = R.sched_order + (size_t)cls * W.n_targets;
-    for (;;) {
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const int i = (int)atomicAdd(next, 1ull);
-            sh[12] = i < R.sched_count[cls] ? order[i] : -1;
-        }
-        __syncthreads();
-        const int t = sh[12];
-        if (t < 0) break;
-        if (NODES == 0 && threadIdx.x == 0) atomicAnd(&W.status[t], ~KM_ST_RETRY_LARGE);
-        GraphDims d;
-        ctx.rot = t & 3;
-#ifdef KM_PHASE_TIMERS
-        const long long tc0 = clock64();
-#endif
-        if (!graph_target(ctx, T, W, S, R, t, &d, sh)) continue;
-        emit_rows(ctx, T, W, S, R, t, d, sh[2], sh[3], sh[6], sh);
-        __syncthreads();
-#ifdef KM_PHASE_TIMERS
-        if (threadIdx.x == 0 && t < KM_DEBUG_TARGETS) km_target_cycles[t] = (unsigned int)(clock64() - tc0);
-#endif
-    }
-}
-
 // ---- measurement kernels -------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) km_gather_kernel(const uint4* __restrict__ buf, uint64_t n_sectors, uint64_t n_loads,
                                                         uint64_t seed, uint32_t* sink) {
@@ -459,3 +270,4 @@ __global__ void km_count_nonzero_kernel(const uint32_t* c, uint64_t n, unsigned 
 }
 
 }  // namespace km
+

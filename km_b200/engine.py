@@ -212,7 +212,7 @@ class Table:
         out = TextResult(h, db, targets)
         self.last_timing = out.timing
         view = out.text_view()
-        return ((view if as_bytes else view.tobytes().decode("ascii")), out.status)
+        return ((view if as_bytes else view.tobytes().decode()), out.status)
 
     def plan(self, sequences, count=5, ratio=0.05, steps=500, branchs=10, nodes=10000, extra_nodes=0):
         """Upload a batch once; launch it any number of times (FindPlan)."""
@@ -426,7 +426,7 @@ class BatchResult:
             check(int(need))
         buf = ctypes.create_string_buffer(int(need) + 1)
         lib().km_result_format_target(self._h, int(t), db_name.encode(), query_name.encode(), buf, int(need) + 1)
-        return buf.raw[:int(need)].decode("ascii")
+        return buf.raw[:int(need)].decode()
 
     def format_all(self, db_name, names, threads=0, as_bytes=False):
         """Sorted TSV text of every target, in target order, formatted on host threads.
@@ -442,7 +442,7 @@ class BatchResult:
         view = _view(ptr.value, np.uint8, int(need))      # the library's own buffer, valid while the result lives
         if as_bytes:
             return view
-        return view.tobytes().decode("ascii")
+        return view.tobytes().decode()
 
     def close(self):
         if getattr(self, "_h", None):
@@ -474,5 +474,8 @@ def raise_for_status(status, name, max_node):
         raise ValueError("a k-mer occurs multiple times in reference %s" % name)
     if status & ST_TOO_SHORT:
         raise AssertionError("target %s is shorter than k" % name)      # Sequence.py:45 `assert len(self.ref_mer)`
-    if status & (ST_TOO_MANY_COLS | ST_SOLVER_WATCHDOG | ST_NAME_MISMATCH | ST_NODE_OVERFLOW | ST_PATH_OVERFLOW):
+    if status & ST_NODE_OVERFLOW:
+        raise RuntimeError("km_b200: target %s visits more nodes off the reference than max_node + 4 * max_stack + 4096 "
+                           "allows (the reference bounds only the nodes it keeps; its own walk would not end here)" % name)
+    if status & (ST_TOO_MANY_COLS | ST_SOLVER_WATCHDOG | ST_NAME_MISMATCH | ST_PATH_OVERFLOW):
         raise RuntimeError("km_b200: target %s could not be processed (status 0x%x)" % (name, status))
