@@ -93,56 +93,150 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------
-# CPU arm: the oracle port, one process per core
+# CPU arm: the reference's own Python (baseline/_ref, unmodified km 2.2.2) one process per core, each running
+# main_find_mut (km/tools/find_mutation.py:17-60) over a contiguous slice of the targets; Jellyfish -- absent from
+# the reference tree -- is oracle/jellyfish_standin over oracle/kmer_store.c with the analytic 2e9-key background.
+# kind "port" runs oracle/km_oracle.py (the CPU restatement) over the same slices instead.
 # ---------------------------------------------------------------------------------------------
-_W = {}
+def _cpu_worker(conn, job, keys, counts, bg_seed, bg_n, kind, workdir):
+    """One process = one core = one contiguous slice of the targets, for the life of the measurement."""
+    try:
+        import warnings
+        warnings.simplefilter("ignore")                  # the reference's own SyntaxWarnings (Graph.py docstring)
+        from oracle import km_oracle as ko
+        from oracle.store import KmerStore
+        store = KmerStore(31, True, len(keys))
+        store.set_background(bg_seed, bg_n)
+        store.insert(keys, counts)
+        names, seqs = [n for n, _ in job], [s for _, s in job]
+        if kind == "reference":
+            from oracle import reference_runner as rr
+            session = rr.ReferenceSession(store, os.path.join(workdir, "w%d" % os.getpid()))
+            files = session.write_targets(names, seqs)   # untimed: the reference reads its targets from disk
+        else:
+            jf = ko.OracleJellyfish(store, "panel.jf", 0.05, 5)
+        conn.send("ready")
+        while True:
+            n_take = conn.recv()
+            if n_take is None:
+                break
+            if kind == "reference":
+                rows, issued = session.find_mutation(files[:n_take]) if n_take else ([], 0)
+            else:
+                q0 = jf.n_queries
+                rows = []
+                for name, seq in job[:n_take]:
+                    f = ko.OracleFinder(ko.Target(seq, name, 31), jf).run()
+                    rows.extend(str(r) for r in f.get_paths())
+                issued = jf.n_queries - q0
+            conn.send((min(n_take, len(job)), issued, rows))
+    except Exception as e:                               # surfaces in the parent instead of a hang
+        import traceback
+        conn.send(("error", "%s\n%s" % (e, traceback.format_exc())))
 
 
-def _cpu_init(keys, counts, bg_seed, bg_n):
-    from oracle import km_oracle as ko
-    from oracle.store import KmerStore
-    store = KmerStore(31, True, len(keys))
-    store.set_background(bg_seed, bg_n)
-    store.insert(keys, counts)
-    _W["jf"] = ko.OracleJellyfish(store, "panel.jf", 0.05, 5)
-    _W["ko"] = ko
-
-
-def _cpu_work(job):
-    ko, jf = _W["ko"], _W["jf"]
-    q0 = jf.n_queries
-    nodes = 0
-    text = []
-    for name, seq in job:
-        f = ko.OracleFinder(ko.Target(seq, name, 31), jf).run()
-        text.extend(str(r) for r in f.get_paths())
-        nodes += len(f.refpath.ref_mer) + 4 * (f.num_k - 2)
-    return len(job), jf.n_queries - q0, nodes, len(text)
-
-
-def cpu_arm(panel, bg_seed, bg_n, n_sample, steps, warmup, cores=None):
-    """Times the oracle port over `n_sample` targets of the panel with one process per core.
-    Returns (targets/s, cores, sample text, issued lookups/s, ms per step)."""
+def cpu_arm(panel, bg_seed, bg_n, n_sample, steps, warmup, cores=None, kind="reference", budget_s=None, table_keys=None):
+    """Times find_mutation on the CPU over `n_sample` targets of the panel, one process per core, each over a
+    contiguous 1/P slice.  budget_s: if the warm-up predicts that `steps` passes exceed it,
+    every slice shrinks.  Returns a dict: value (targets/s), cores, sample, issued_lookups_per_s, ms_per_step, rows
+    (of the last step: one list per slice), names (targets of each slice that were run)."""
     import multiprocessing as mp
+    import shutil
+    import tempfile
     cores = cores or os.cpu_count() or 1
     n_sample = min(n_sample, len(panel.targets))
     jobs_targets = list(zip(panel.names[:n_sample], panel.targets[:n_sample]))
-    chunks = [jobs_targets[i::cores] for i in range(cores)]
-    chunks = [c for c in chunks if c]
+    per = (n_sample + cores - 1) // cores
+    chunks = [jobs_targets[i:i + per] for i in range(0, n_sample, per)]
+    keys, counts = table_keys if table_keys is not None else (panel.keys, panel.counts)
+    workdir = tempfile.mkdtemp(prefix="km_ref_")
     ctx = mp.get_context("fork")
-    with ctx.Pool(len(chunks), initializer=_cpu_init, initargs=(panel.keys, panel.counts, bg_seed, bg_n)) as pool:
-        for _ in range(warmup):
-            pool.map(_cpu_work, [c[:1] for c in chunks])
-        times, issued = [], 0
-        for _ in range(steps):
+    procs, conns = [], []
+    try:
+        for c in chunks:
+            a, b = ctx.Pipe()
+            pr = ctx.Process(target=_cpu_worker, args=(b, c, keys, counts, bg_seed, bg_n, kind, workdir), daemon=True)
+            pr.start()
+            procs.append(pr)
+            conns.append(a)
+
+        def gather():
+            out = [c.recv() for c in conns]
+            for o in out:
+                if o and o[0] == "error":
+                    raise RuntimeError("CPU arm worker failed: " + o[1])
+            return out
+        gather()                                          # "ready"
+
+        def step(takes):
             t0 = time.perf_counter()
-            out = pool.map(_cpu_work, chunks)
-            times.append(time.perf_counter() - t0)
+            for c, n in zip(conns, takes):
+                c.send(n)
+            out = gather()
+            return time.perf_counter() - t0, out
+        takes = [len(c) for c in chunks]
+        probe = [min(8, t) for t in takes]
+        warm = 0.0
+        for _ in range(max(1, warmup)):
+            warm, _o = step(probe)
+        if budget_s is not None:
+            predicted = warm * (max(takes) / max(1, max(probe))) * steps
+            if predicted > budget_s:
+                scale = budget_s / predicted
+                takes = [max(8, int(t * scale)) for t in takes]
+        times, issued, rows, done = [], 0, [], 0
+        for _ in range(steps):
+            dt, out = step(takes)
+            times.append(dt)
             issued = sum(o[1] for o in out)
+            done = sum(o[0] for o in out)
+            rows = [o[2] for o in out]
+        for c in conns:
+            c.send(None)
+        for pr in procs:
+            pr.join(timeout=10)
+    finally:
+        for pr in procs:
+            if pr.is_alive():
+                pr.terminate()
+        shutil.rmtree(workdir, ignore_errors=True)
     total = sum(times)
-    sample = "%d of %d panel targets, %d processes, oracle port (Python + C k-mer store, analytic %d-key background)" % (
-        n_sample, len(panel.targets), len(chunks), bg_n)
-    return n_sample * steps / total, len(chunks), sample, issued * steps / total, 1e3 * total / steps
+    what = ("unmodified reference Python (km 2.2.2 main_find_mut, baseline/_ref) + stand-in k-mer store"
+            if kind == "reference" else "oracle port (Python restatement + C k-mer store)")
+    sample = "%d of %d panel targets per step, %d processes (contiguous slices), %s, analytic %d-key background" % (
+        done, len(panel.targets), len(chunks), what, bg_n)
+    return {"value": done * steps / total, "cores": len(chunks), "sample": sample, "issued_lookups_per_s": issued * steps / total,
+            "ms_per_step": 1e3 * total / steps, "rows": rows, "names": [[n for n, _ in c[:t]] for c, t in zip(chunks, takes)],
+            "n_done": done, "kind": kind}
+
+
+def reference_available():
+    from oracle import reference_runner as rr
+    return rr.locate_reference() is not None
+
+
+def compare_with_cpu_rows(cpu, text):
+    """Rows the CPU arm produced (per slice, per target) against the GPU arm's text: every target the CPU ran."""
+    from oracle.compare import compare_rows
+    by_target = {}
+    for ln in text.split("\n"):
+        if ln:
+            by_target.setdefault(ln.split("\t")[1], []).append(ln)
+    bad, flips, checked, bad_names = 0, 0, 0, []
+    for rows, names in zip(cpu["rows"], cpu["names"]):
+        mine = {}
+        for r in rows:
+            mine.setdefault(r.split("\t")[1], []).append(r)
+        for n in names:
+            errs, fl = compare_rows(mine.get(n, []), by_target.get(n, []))
+            checked += 1
+            flips += fl
+            if errs:
+                bad += 1
+                if len(bad_names) < 8:
+                    bad_names.append(n)
+    return {"targets_checked": checked, "mismatching": bad, "printed_digit_flips": flips, "mismatching_names": bad_names,
+            "against": cpu["kind"]}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -155,9 +249,12 @@ def main():
     ap.add_argument("--targets", type=int, default=10000)
     ap.add_argument("--table-keys", type=int, default=2_000_000_000)
     ap.add_argument("--lookup-queries", type=int, default=1 << 30)
-    ap.add_argument("--cpu-sample", type=int, default=0, help="targets in the CPU sample (0 = 640 per core, at most the panel: ~5-10 s of CPU work)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="targets in the CPU sample (0 = the whole panel, shrunk if it would take minutes)")
+    ap.add_argument("--cpu-kind", default="reference", choices=["reference", "port"],
+                    help="CPU arm: the unmodified reference Python from baseline/_ref (default) or the oracle port")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-lookup", action="store_true")
+    ap.add_argument("--no-tier2", action="store_true")
     ap.add_argument("--n-sub", type=int, default=0, help="sub-batches in flight in km_find_text (0 = library default)")
     ap.add_argument("--panel-offset", type=int, default=0, help="debug: use the panel rank R would get (seed offset)")
     args = ap.parse_args()
@@ -175,21 +272,27 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        import __graft_entry__ as ge
         from oracle import store
         store.build()
+        try:
+            from tools import stage_reference
+            stage_reference.stage()
+        except Exception:
+            pass
         panel = synth.make_panel(args.targets, seed=synth.PANEL_SEED)
         cores = os.cpu_count() or 1
-        n_sample = args.cpu_sample or 640 * cores
-        v, used, sample, lps, ms = cpu_arm(panel, synth.TABLE_SEED, args.table_keys, n_sample, max(1, args.steps),
-                                           min(args.warmup, 1), cores)
+        kind = "reference" if reference_available() and args.cpu_kind != "port" else "port"
+        # every step = the whole panel unless the warm-up predicts that K steps would take more than ~2.5 minutes
+        r = cpu_arm(panel, synth.TABLE_SEED, args.table_keys, args.cpu_sample or args.targets, max(1, args.steps),
+                    min(max(args.warmup, 1), 2), cores, kind=kind, budget_s=150.0)
+        v = r["value"]
         print(json.dumps({
             "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u64 keys / u32 counts / f64 solver",
-            "data": "synthetic", "config": {"workload": workload, "step": "bounded sample: " + sample},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": used, "kind": "port", "sample": sample,
-                             "issued_lookups_per_s": lps},
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u64 keys / u32 counts / f32 graph weights / f64 solver",
+            "data": "synthetic", "config": {"workload": workload},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": r["cores"], "kind": kind, "sample": r["sample"],
+                             "issued_lookups_per_s": r["issued_lookups_per_s"]},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return 0
 
@@ -345,7 +448,30 @@ def main():
     e2e_breakdown = {k: res.timing[k] for k in ("h2d_ms", "walk_ms", "graph_ms", "d2h_ms")}
     e2e_breakdown.update({k: v / args.steps for k, v in e2e_split.items()})
     e2e_breakdown["text_identical_to_one_call"] = bool(np.array_equal(text, text2))
-    text = text.tobytes().decode("ascii")
+    text = text.tobytes().decode()
+
+    # ---- tier 2: the same panel against a REDUCED background (the first 1e7 keys of the same
+    # stream, so full is a superset).  A target's text may differ only if its walk touched a background key the
+    # reduced table lacks (chance ~ queried k-mers x 2e9 / 2^61 per panel); such targets are counted and listed.
+    tier2 = None
+    if rank == 0 and not args.no_tier2:
+        n_small = min(10_000_000, table_keys)
+        small = engine.Table.create(k=31, canonical=True, capacity=n_small + len(all_keys), device=local)
+        small.build_synthetic(synth.TABLE_SEED, n_small)
+        small.insert(all_keys, all_counts, mode="overwrite")
+        text_small, _ = small.find_text(packed, "panel.jf")
+        small.close()
+
+        def per_target(tx):
+            d = {}
+            for ln in tx.split("\n"):
+                if ln:
+                    d.setdefault(ln.split("\t")[1], []).append(ln)
+            return d
+        full_rows, small_rows = per_target(text), per_target(text_small)
+        differing = [n for n in panel.names if full_rows.get(n) != small_rows.get(n)]
+        tier2 = {"reduced_background_keys": n_small, "full_background_keys": table_keys,
+                 "targets_compared": len(panel.names), "targets_differing": len(differing), "names": differing[:16]}
 
     # ---- lookup microbenchmark (device-resident queries) ---------------------------------------
     lookup = None
@@ -368,35 +494,32 @@ def main():
                       "span_gb": span / 1e9}
     clocks = sampler.stop()
 
-    # ---- parity spot check against the oracle (not timed) ----------------------------------------
+    # ---- parity against the CPU arm (not timed): EVERY target of rank 0's panel --------------------------------
+    # N=1: the rows are those of the cpu_baseline run itself (the unmodified reference Python when it is staged);
+    # N>1: the oracle port over the whole panel on rank 0's host cores.  The 2e9-key background is decided
+    # analytically on the CPU, so the comparison is exact at full scale (tier 1).
     parity = None
     cpu = None
     if rank == 0:
-        from oracle import km_oracle as ko
-        from oracle.compare import compare_rows
-        from oracle.store import KmerStore
-        store = KmerStore(31, True, len(panel.keys))
-        store.set_background(synth.TABLE_SEED, table_keys)
-        store.insert(all_keys, all_counts)
-        jf = ko.OracleJellyfish(store, "panel.jf", 0.05, 5)
-        lines = text.split("\n")
-        by_target = {}
-        for ln in lines:
-            if ln:
-                by_target.setdefault(ln.split("\t")[1], []).append(ln)
-        bad = flips = checked = 0
-        for i in range(0, args.targets, max(1, args.targets // 64)):
-            f = ko.OracleFinder(ko.Target(panel.targets[i], panel.names[i], 31), jf).run()
-            errs, fl = compare_rows([str(r) for r in f.get_paths()], by_target.get(panel.names[i], []))
-            bad += 1 if errs else 0
-            flips += fl
-            checked += 1
-        parity = {"targets_checked": checked, "mismatching": bad, "printed_digit_flips": flips}
+        cores = os.cpu_count() or 1
+        kind = "reference" if reference_available() and args.cpu_kind != "port" else "port"
         if world == 1 and not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
-            v, used, sample, lps, _ = cpu_arm(panel, synth.TABLE_SEED, table_keys, args.cpu_sample or 640 * cores, 1, 1, cores)
-            cpu = {"value": v, "unit": UNIT, "cores": used, "kind": "port", "sample": sample,
-                   "issued_lookups_per_s": lps}
+            r = cpu_arm(panel, synth.TABLE_SEED, table_keys, args.cpu_sample or args.targets, 1, 1, cores, kind=kind,
+                        budget_s=30.0, table_keys=(all_keys, all_counts))
+            cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": kind, "sample": r["sample"],
+                   "issued_lookups_per_s": r["issued_lookups_per_s"]}
+            parity = compare_with_cpu_rows(r, text)
+            if kind == "reference":        # the oracle port beside it: a second, labelled figure
+                r2 = cpu_arm(panel, synth.TABLE_SEED, table_keys, args.cpu_sample or args.targets, 1, 1, cores, kind="port",
+                             budget_s=30.0, table_keys=(all_keys, all_counts))
+                cpu["oracle_port_value"] = r2["value"]
+                cpu["oracle_port_parity"] = {k: v for k, v in compare_with_cpu_rows(r2, text).items() if k != "against"}
+        elif not args.no_cpu_baseline:
+            r = cpu_arm(panel, synth.TABLE_SEED, table_keys, args.targets, 1, 1, max(1, cores // 2), kind="port",
+                        budget_s=20.0, table_keys=(all_keys, all_counts))
+            parity = compare_with_cpu_rows(r, text)
+        if parity is not None and tier2 is not None:
+            parity["tier2_full_vs_reduced_background"] = tier2
 
     peak, peak_src = load_peaks()
     achieved = probe_lookups * 32 / (probe_ms / 1e3) / 1e9

@@ -126,6 +126,9 @@ typedef struct km_find_params {
     int32_t reserved;
 } km_find_params;
 #define KM_FIND_NO_GRAPH 1   /* do not copy node arrays / index paths back (rows and text only) */
+#define KM_FIND_NO_REFINE_JUMP 2   /* iterate PathQuant.refine_coef (PathQuant.py:120-142) literally from start to end: no
+                                      closed-form jump across its long linear stretches (A/B switch; the environment
+                                      variable KM_NO_REFINE_JUMP does the same) */
 
 /* per-target status bits */
 #define KM_ST_BAD_BASE 1

@@ -81,7 +81,9 @@ struct ResultView {
     // first; sched_count[c] entries in sched_order[c * n_targets ...]
     int32_t* sched_order;
     int32_t* sched_count;
+    int32_t flags;           // KM_RESULT_*
 };
+#define KM_RESULT_NO_REFINE_JUMP 1   // refine_coef is iterated literally from start to end (A/B switch, KM_FIND_NO_REFINE_JUMP)
 
 // Per-target working set of the CTA: shared memory in the small pass, per-CTA HBM scratch
 // (L2 resident in practice) in the general pass.  Arrays whose lifetimes do not overlap share

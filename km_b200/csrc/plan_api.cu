@@ -111,6 +111,8 @@ int plan_layout(km_plan* p) {
         p->F.t_len = A.take<int64_t>(n); p->F.t_off = A.take<int64_t>(n + 1);
         p->F.text = A.take<char>((size_t)p->text_cap); p->F.text_cap = p->text_cap;
     }
+    { const char* e = getenv("KM_NO_REFINE_JUMP");
+      R.flags = ((p->prm.flags & KM_FIND_NO_REFINE_JUMP) || (e && *e && *e != '0')) ? KM_RESULT_NO_REFINE_JUMP : 0; }
     p->P.ratio = p->prm.ratio; p->P.count = p->prm.count; p->P.max_stack = p->prm.steps;
     p->P.max_break = p->prm.branchs; p->P.max_node = p->prm.nodes;
     return 0;

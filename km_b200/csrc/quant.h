@@ -136,16 +136,23 @@ KM_HD double det2(double a, double b, double c, double d) {
 // ---- refine_coef without its thousands of idle iterations ----------------------------------------------
 // The reference iterates coef += 0.1 * grad with grad = 2 (h - G coef) / n until max|grad| <= 0.01
 // (PathQuant.py:120-142).  When lstsq leaves a negative coefficient (a cluster whose second variant explains
-// nothing) the clamped problem converges along the slowest eigen-direction of G and the loop runs 5-10
-// thousand times -- one such target then takes longer than the rest of the batch.  Between two clamp
+// nothing) the clamped problem converges along the slowest eigen-direction of G and the loop runs hundreds to
+// thousands of times -- one such target then takes longer than the rest of the batch.  Between two clamp
 // events the iteration is LINEAR in the free coefficients: x(t+1) = x(t) + a (h_F - G_FF x(t)), a = 0.2/n,
-// so in the eigenbasis of G_FF every component is y_i(t) = y_i(0) r_i^t + g_i (1 - r_i^t) / l_i with
-// r_i = 1 - a l_i.  chain_jump evaluates that closed form to (1) predict the step at which the stop test
-// will fire and (2) advance the state to 8 steps before it -- after checking at four points of the jump
-// that no free coefficient reaches zero and no clamped one is released.  The literal loop then runs the
-// last steps and decides the stop itself, so the result differs from the fully literal run only by the
-// rounding of the closed form (~1e-12 relative), and the first 32 iterations (every transient, every case
-// the reference's own tests hold) are literal.
+// so in the eigenbasis of G_FF every component is y_e(t) = y_e(0) r_e^t + g_e (1 - r_e^t) / l_e with
+// r_e = 1 - a l_e in (0, 1], and the gradient component is d_e(t) = (g_e - l_e y_e(0)) r_e^t.  refine_jump
+// evaluates that closed form to (1) predict the step at which the stop test will fire and (2) advance the
+// state to 8 steps before it -- but only over a stretch [0, J] on which it can PROVE that the literal loop
+// does nothing else: every y_e(t) and d_e(t) is monotone in t, so on a segment [t0, t1] each term V_ie y_e(t)
+// lies between its two end values and
+//     min over the segment of x_i(t)   >=  sum_e min(V_ie y_e(t0), V_ie y_e(t1))          (no free coefficient is clamped)
+//     max over the segment of grad_a(t) <=  c_a - sum_e min(w_ae y_e(t0), w_ae y_e(t1))    (no clamped one is released)
+//     min over the segment of |grad_i|  >=  the same bound on sum_e V_ie d_e(t)            (the stop test does not fire)
+// hold for every real t in the segment, hence for every step.  [0, J] is cut adaptively (a segment whose bounds
+// are inconclusive is halved, down to single steps); if the proof fails, J is halved; below 32 steps the literal
+// loop simply goes on.  The literal loop then runs the last steps and decides the stop itself, so the result
+// differs from the fully literal run only by the rounding of the closed form (~1e-12 relative), and the first 32
+// iterations (every transient, every case the reference's own tests hold) are literal.
 #define KM_REFINE_MAXF 4
 #if KM_DEVICE_BUILD
 #define KM_COLD __device__ __noinline__
@@ -157,9 +164,9 @@ KM_COLD int refine_jump(const double* G, const double* h, int m, int n_nodes, do
     int F[KM_REFINE_MAXF], mf = 0;
     for (int a = 0; a < m; ++a)
         if (coef[a] > 0.0) { if (mf == KM_REFINE_MAXF) return 0; F[mf++] = a; }
-    if (mf == 0) return 0;
+    if (mf == 0 || m > 2 * KM_REFINE_MAXF) return 0;
     double A[KM_REFINE_MAXF * KM_REFINE_MAXF], V[KM_REFINE_MAXF * KM_REFINE_MAXF];
-    double lam[KM_REFINE_MAXF], lg[KM_REFINE_MAXF], y0[KM_REFINE_MAXF], g[KM_REFINE_MAXF], x[KM_REFINE_MAXF];
+    double lam[KM_REFINE_MAXF], lg[KM_REFINE_MAXF], y0[KM_REFINE_MAXF], g[KM_REFINE_MAXF], d0[KM_REFINE_MAXF];
     for (int i = 0; i < mf; ++i)
         for (int j = 0; j < mf; ++j) A[i * mf + j] = G[F[i] * m + F[j]];
     jacobi_eigen(A, V, mf);
@@ -170,63 +177,129 @@ KM_COLD int refine_jump(const double* G, const double* h, int m, int n_nodes, do
         lg[e] = log1p(-alpha * lam[e]);                        // log r_e <= 0
         y0[e] = 0.0; g[e] = 0.0;
         for (int i = 0; i < mf; ++i) { y0[e] += V[i * mf + e] * coef[F[i]]; g[e] += V[i * mf + e] * h[F[i]]; }
+        d0[e] = g[e] - lam[e] * y0[e];
     }
-    // state after t steps, and the stop test's quantity there; returns false if a clamp event lies at t
-    auto at = [&](double t, double* worst) -> bool {
-        double y[KM_REFINE_MAXF];
+    // clamped coefficients: grad_a(t) * n / 2 = h_a - sum_e w_ae y_e(t)
+    int Cl[2 * KM_REFINE_MAXF], mc = 0;
+    double wc[2 * KM_REFINE_MAXF * KM_REFINE_MAXF];
+    for (int a = 0; a < m; ++a) {
+        bool is_free = false;
+        for (int i = 0; i < mf; ++i) is_free |= F[i] == a;
+        if (is_free) continue;
+        for (int e = 0; e < mf; ++e) {
+            double w = 0.0;
+            for (int i = 0; i < mf; ++i) w += G[a * m + F[i]] * V[i * mf + e];
+            wc[mc * KM_REFINE_MAXF + e] = w;
+        }
+        Cl[mc++] = a;
+    }
+    // y_e and d_e after t steps
+    auto eval = [&](double t, double* y, double* d) {
         for (int e = 0; e < mf; ++e) {
             const double tl = t * lg[e];
+            const double rt = exp(tl);
             const double grow = lam[e] > 0.0 ? -expm1(tl) / lam[e] : alpha * t;      // (1 - r^t) / l
-            y[e] = y0[e] * exp(tl) + g[e] * grow;
+            y[e] = y0[e] * rt + g[e] * grow;
+            d[e] = d0[e] * rt;
         }
-        bool ok = true;
-        for (int i = 0; i < mf; ++i) {
-            x[i] = 0.0;
-            for (int e = 0; e < mf; ++e) x[i] += V[i * mf + e] * y[e];
-            if (!(x[i] > 0.0)) ok = false;
-        }
-        double w = 0.0;
-        for (int a = 0; a < m; ++a) {
-            double fit = 0.0;
-            for (int i = 0; i < mf; ++i) fit += G[a * m + F[i]] * x[i];
-            const double gr = 2.0 * (h[a] - fit) / (double)n_nodes;
-            bool is_free = false;
-            for (int i = 0; i < mf; ++i) is_free |= F[i] == a;
-            if (is_free) { const double ag = fabs(gr); w = ag > w ? ag : w; }
-            else if (gr > 0.0) ok = false;                      // a clamped coefficient would be released
-        }
-        *worst = w;
-        return ok;
     };
-    double w;
-    // first step at which the stop test fires, by doubling then bisection (the test quantity decays
-    // monotonically once the transients are gone: the caller has already run 32 literal steps)
-    double hi = 32.0;
-    while (hi < 16777216.0) { at(hi, &w); if (w <= 0.01) break; hi *= 2.0; }
+    const double gscale = 2.0 / (double)n_nodes;
+    // max |grad| over the free coefficients at the state (y, d)
+    auto worst_at = [&](const double* d) {
+        double w = 0.0;
+        for (int i = 0; i < mf; ++i) {
+            double gi = 0.0;
+            for (int e = 0; e < mf; ++e) gi += V[i * mf + e] * d[e];
+            const double ag = fabs(gi) * gscale;
+            w = ag > w ? ag : w;
+        }
+        return w;
+    };
+    // the three interval bounds on [tA, tB] from the end states; true = nothing but linear steps in between
+    auto segment_clean = [&](const double* yA, const double* dA, const double* yB, const double* dB) {
+        for (int i = 0; i < mf; ++i) {
+            double lo = 0.0, mag = 0.0;
+            for (int e = 0; e < mf; ++e) {
+                const double a = V[i * mf + e] * yA[e], b = V[i * mf + e] * yB[e];
+                lo += a < b ? a : b;
+                mag += fabs(a) > fabs(b) ? fabs(a) : fabs(b);
+            }
+            if (!(lo > 1e-9 * mag)) return false;
+        }
+        for (int c = 0; c < mc; ++c) {
+            double lo = 0.0, mag = fabs(h[Cl[c]]);
+            for (int e = 0; e < mf; ++e) {
+                const double a = wc[c * KM_REFINE_MAXF + e] * yA[e], b = wc[c * KM_REFINE_MAXF + e] * yB[e];
+                lo += a < b ? a : b;
+                mag += fabs(a) > fabs(b) ? fabs(a) : fabs(b);
+            }
+            if (!(h[Cl[c]] - lo < -1e-9 * mag)) return false;
+        }
+        bool loud = false;                       // some free coefficient's |grad| stays above the stop threshold
+        for (int i = 0; i < mf && !loud; ++i) {
+            double lo = 0.0, hi = 0.0;
+            for (int e = 0; e < mf; ++e) {
+                const double a = V[i * mf + e] * dA[e], b = V[i * mf + e] * dB[e];
+                lo += a < b ? a : b;
+                hi += a < b ? b : a;
+            }
+            loud = lo * gscale > 0.01 * (1.0 + 1e-9) || hi * gscale < -0.01 * (1.0 + 1e-9);
+        }
+        return loud;
+    };
+    // [0, J] proven clean by adaptive bisection (explicit stack; at most ~64 leaves are ever needed: the terms
+    // are exponentials that have shed their fast modes during the 32 literal steps before the call)
+    auto stretch_clean = [&](double J) {
+        double st_lo[24], st_hi[24];
+        int sp = 0, work = 0;
+        st_lo[0] = 0.0; st_hi[0] = J; sp = 1;
+        while (sp) {
+            --sp;
+            const double a = st_lo[sp], b = st_hi[sp];
+            double yA[KM_REFINE_MAXF], dA[KM_REFINE_MAXF], yB[KM_REFINE_MAXF], dB[KM_REFINE_MAXF];
+            eval(a, yA, dA); eval(b, yB, dB);
+            if (segment_clean(yA, dA, yB, dB)) continue;
+            if (b - a <= 1.0 || sp + 2 > 24 || ++work > 256) return false;
+            const double mid = floor(0.5 * (a + b));
+            st_lo[sp] = mid; st_hi[sp] = b; ++sp;
+            st_lo[sp] = a; st_hi[sp] = mid; ++sp;
+        }
+        return true;
+    };
+    double y[KM_REFINE_MAXF], d[KM_REFINE_MAXF];
+    // first step at which the stop test fires, by doubling then bisection (only a PREDICTION: whatever it says,
+    // the stretch actually jumped is proven clean below and the literal loop decides the stop)
+    double hi = 32.0, w = INFINITY;
+    while (hi < 16777216.0) { eval(hi, y, d); w = worst_at(d); if (w <= 0.01) break; hi *= 2.0; }
     if (!(w <= 0.01)) return 0;
     double lo = hi * 0.5;
     if (hi == 32.0) lo = 0.0;
     while (hi - lo > 1.0) {
         const double mid = floor(0.5 * (lo + hi));
-        at(mid, &w);
-        if (w <= 0.01) hi = mid; else lo = mid;
+        eval(mid, y, d);
+        if (worst_at(d) <= 0.01) hi = mid; else lo = mid;
     }
     double J = hi - 8.0;
-    for (; J >= 32.0; J = floor(0.5 * J)) {
-        bool ok = true;
-        for (int q = 1; q <= 4 && ok; ++q) ok = at(floor(J * (double)q * 0.25), &w) && w > 0.01;
-        if (ok) break;
-    }
+    for (; J >= 32.0; J = floor(0.5 * J))
+        if (stretch_clean(J)) break;
+#if defined(KM_HOST_EMU) && defined(KM_RJ_DEBUG)
+    fprintf(stderr, "refine_jump: mf=%d predicted stop %.0f, proven stretch %.0f\n", mf, hi, J);
+#endif
     if (J < 32.0) return 0;
-    at(J, &w);
-    for (int i = 0; i < mf; ++i) coef[F[i]] = x[i];
+    eval(J, y, d);
+    for (int i = 0; i < mf; ++i) {
+        double x = 0.0;
+        for (int e = 0; e < mf; ++e) x += V[i * mf + e] * y[e];
+        coef[F[i]] = x;
+    }
     return (int)J;
 }
 
 // refine_coef (PathQuant.py:120-136) + get_ratio (:144-149) on the normal equations: fixed step 0.1,
 // gradient / n_nodes, stop at max|grad| <= 0.01 -- literal steps, with refine_jump across the long
 // linear stretches.  Returns the number of iterations the literal loop would have run.
-KM_HD int refine_and_ratio(const double* G, const double* h, int m, int n_nodes, double* coef, double* rvaf, double* grad) {
+KM_HD int refine_and_ratio(const double* G, const double* h, int m, int n_nodes, double* coef, double* rvaf, double* grad,
+                            bool allow_jump) {
     for (int a = 0; a < m; ++a) if (coef[a] < 0.0) coef[a] = 0.0;
     double worst = INFINITY;
     int iters = 0, since = 0;
@@ -244,7 +317,7 @@ KM_HD int refine_and_ratio(const double* G, const double* h, int m, int n_nodes,
             worst = ag > worst ? ag : worst;     // NaN never enters: counts are finite
         }
         if (++iters > 10000000) { iters = -1; break; }
-        if (++since >= 32 && worst > 0.01) {
+        if (allow_jump && ++since >= 32 && worst > 0.01) {
             iters += refine_jump(G, h, m, n_nodes, coef);
             since = 0;
         }
@@ -260,7 +333,7 @@ KM_HD int refine_and_ratio(const double* G, const double* h, int m, int n_nodes,
 // entry and is all zero again on return.
 template <class Ctx>
 KM_HD int solve_columns(const Ctx& ctx, const GraphScratch& S, const uint32_t* counts, int n_nodes,
-                        const PathView* cols, int m, double* coef, double* rvaf, int* sh) {
+                        const PathView* cols, int m, double* coef, double* rvaf, int* sh, bool allow_jump) {
     const int tid = ctx.tid(), nt = ctx.nt();
     unsigned long long* acc = S.acc;   // [m*m + m] exact integer accumulators
     for (int i = tid; i < m * m + m; i += nt) acc[i] = 0ull;
@@ -316,7 +389,7 @@ KM_HD int solve_columns(const Ctx& ctx, const GraphScratch& S, const uint32_t* c
             const double s = (v0 * h[0] + v1 * h[1]) / ((v0 * v0 + v1 * v1) * (G[0] + G[3]));
             c[0] = v0 * s; c[1] = v1 * s;
         }
-        sh[4] = refine_and_ratio(G, h, 2, n_nodes, c, r, grad);
+        sh[4] = refine_and_ratio(G, h, 2, n_nodes, c, r, grad, allow_jump);
         coef[0] = c[0]; coef[1] = c[1]; rvaf[0] = r[0]; rvaf[1] = r[1];
     } else if (tid == 0) {
         double* G = S.G;
@@ -344,7 +417,7 @@ KM_HD int solve_columns(const Ctx& ctx, const GraphScratch& S, const uint32_t* c
             proj /= lam;
             for (int a = 0; a < m; ++a) coef[a] += V[a * m + e] * proj;
         }
-        sh[4] = refine_and_ratio(G, h, m, n_nodes, coef, rvaf, S.vec + 2 * S.max_cols);
+        sh[4] = refine_and_ratio(G, h, m, n_nodes, coef, rvaf, S.vec + 2 * S.max_cols, allow_jump);
     }
     ctx.sync();
     return sh[4];
@@ -380,7 +453,7 @@ struct Quant2 {
 
 template <class WCtx>
 KM_HD Quant2 quant_pair(const WCtx& wctx, const GraphScratch& S, const uint32_t* counts, int n_nodes, const PathView& path,
-                        const PathView& range, bool path_first, int lane8) {
+                        const PathView& range, bool path_first, int lane8, bool allow_jump) {
     const int lane = wctx.tid(), nl = wctx.nt();
     const uint32_t one = 1u << (8 * lane8);
     uint32_t* occ = reinterpret_cast<uint32_t*>(S.occ);
@@ -424,7 +497,7 @@ KM_HD Quant2 quant_pair(const WCtx& wctx, const GraphScratch& S, const uint32_t*
             const double sc = (v0 * h[0] + v1 * h[1]) / ((v0 * v0 + v1 * v1) * (G[0] + G[3]));
             c[0] = v0 * sc; c[1] = v1 * sc;
         }
-        q.iters = refine_and_ratio(G, h, 2, n_nodes, c, q.rvaf, grad);
+        q.iters = refine_and_ratio(G, h, 2, n_nodes, c, q.rvaf, grad, allow_jump);
         q.min_cov = (int64_t)mn;
     }
     return q;
@@ -491,6 +564,7 @@ KM_HD void emit_rows(const Ctx& ctx, const TableView& T, const WalkView& W, cons
                      const ResultView& R, int t, const GraphDims& d, int n_paths, int first_path, int first_row, int* sh) {
     const int k = T.k;
     const int tid = ctx.tid();
+    const bool allow_jump = !(R.flags & KM_RESULT_NO_REFINE_JUMP);
     const int wid = warp_index(ctx), nw = warp_count(ctx);
     const WarpCtx wctx;
     const int lane = wctx.tid();
@@ -571,7 +645,7 @@ KM_HD void emit_rows(const Ctx& ctx, const TableView& T, const WalkView& W, cons
         if (j < n_paths) {
             const int p = j;
             const PathView alt = {R.pool + R.path_off[first_path + p], 0, R.path_len[first_path + p]};
-            const Quant2 q = quant_pair(wctx, S, counts, d.N, alt, ref, true, wid);
+            const Quant2 q = quant_pair(wctx, S, counts, d.N, alt, ref, true, wid, allow_jump);
             if (lane == 0) {
                 const Diff df = {S.pdiff[4 * p], S.pdiff[4 * p + 1], S.pdiff[4 * p + 2], S.pdiff[4 * p + 3]};
                 const bool is_ref = alt.len == d.L && df.start == d.L;      // alt_index == ref_index (:627)
@@ -603,7 +677,7 @@ KM_HD void emit_rows(const Ctx& ctx, const TableView& T, const WalkView& W, cons
             stop = stop < plen ? stop : plen;
             const int beg = off0 < plen ? off0 : plen;
             const PathView clip = {R.pool + R.path_off[first_path + p], beg, stop - beg > 0 ? stop - beg : 0};
-            const Quant2 q = quant_pair(wctx, S, counts, d.N, clip, ref_clip, false, wid);
+            const Quant2 q = quant_pair(wctx, S, counts, d.N, clip, ref_clip, false, wid, allow_jump);
             const Diff df = diff_paths(wctx, ref_clip, clip, k, wslot);
             if (lane == 0)
                 write_row(R, W, kmers, t, k, crec[4 * c + 3], 1, ref_clip, clip, df, first_path + p, off0, c + 1, 1, q.iters,
@@ -632,7 +706,7 @@ KM_HD void emit_rows(const Ctx& ctx, const TableView& T, const WalkView& W, cons
         ctx.sync();
         const int offset = cols[0].begin;
         const PathView ref_clip = cols[0];
-        const int iters = solve_columns(ctx, S, counts, d.N, cols, size + 1, coef, rvaf, sh);
+        const int iters = solve_columns(ctx, S, counts, d.N, cols, size + 1, coef, rvaf, sh, allow_jump);
         for (int j = 0; j < size; ++j) {
             const PathView clip = cols[1 + j];
             const Diff df = diff_paths(ctx, ref_clip, clip, k, slot);

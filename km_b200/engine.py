@@ -183,7 +183,7 @@ class Table:
         return blob, off
 
     def find_batch(self, sequences, count=5, ratio=0.05, steps=500, branchs=10, nodes=10000, extra_nodes=0,
-                   want_graph=True):
+                   want_graph=True, no_refine_jump=False):
         """Run the whole find_mutation path for a list of target sequences in one call.
         want_graph=False skips copying node arrays / index paths back (rows and text only)."""
         if isinstance(sequences, PackedTargets):
@@ -192,7 +192,7 @@ class Table:
             seqs = list(sequences)
             blob, off = self._pack_targets(seqs)
         prm = FindParams(float(ratio), int(count), int(steps), int(branchs), int(nodes), int(extra_nodes),
-                         0 if want_graph else 1, 0)
+                         (0 if want_graph else 1) | (2 if no_refine_jump else 0), 0)
         h = ctypes.c_void_p()
         check(lib().km_find_batch(self._h, blob, off.ctypes.data, len(seqs), ctypes.byref(prm), ctypes.byref(h)))
         return BatchResult.from_handle(h, seqs, self.k)

@@ -126,6 +126,7 @@ int emu_find_target(void* h, const uint8_t* codes, int len, double ratio, int64_
     int32_t t_n = 0, t_np = 0, t_pf = 0, t_nr = 0, t_rf = 0;
     unsigned long long used[4] = {0, 0, 0, 0};
     ResultView R;
+    R.flags = getenv("KM_NO_REFINE_JUMP") ? KM_RESULT_NO_REFINE_JUMP : 0;
     R.t_n = &t_n; R.t_n_paths = &t_np; R.t_path_first = &t_pf; R.t_n_rows = &t_nr; R.t_row_first = &t_rf;
     R.out_kmer = okmer.data(); R.out_count = ocount.data();
     R.path_off = path_off.data(); R.path_len = out_path_len; R.pool = out_pool; R.path_cap = path_cap; R.pool_cap = pool_cap;

@@ -1,0 +1,176 @@
+"""GPU parity tests added in round 2 (run with -m gpu on a B200): the cases VERDICT r1 found untested on the
+device -- long refine_coef runs, one overflowing target in a batch, .jf files with k != 31 or canonical:false."""
+import numpy as np
+import pytest
+
+from oracle import jf_format, km_oracle as ko
+from oracle.compare import compare_rows
+from oracle.store import KmerStore
+
+from helpers import record_of
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine():
+    import __graft_entry__ as ge
+    ge.build()
+    from km_b200 import engine as e
+    from km_b200._lib import lib
+    assert lib().km_device_count() > 0, "these tests need a CUDA device"
+    return e
+
+
+def test_long_refinement_on_device_equals_literal_loop(engine):
+    """PathQuant.refine_coef (PathQuant.py:120-142) has no iteration cap; a tandem duplication of k-3..k-1 bases
+    gives a cluster in which lstsq leaves a negative coefficient and the loop runs for hundreds of steps.  The
+    device crosses the linear stretch in closed form (quant.h refine_jump): iteration count and raw floats must
+    equal the oracle's LITERAL loop, and the device's own literal run (KM_FIND_NO_REFINE_JUMP)."""
+    from km_b200 import synth
+    panel = synth.make_panel(2000, seed=synth.PANEL_SEED + 5)
+    picks = [i for i, tr in enumerate(panel.truth) if tr["kind"] == "dup" and tr.get("size") in (27, 28, 29, 30)][:12]
+    assert len(picks) >= 3
+    t = engine.Table.create(capacity=len(panel.keys) + 1024)
+    t.insert(panel.keys, panel.counts)
+    store = KmerStore(31, True, len(panel.keys))
+    store.insert(panel.keys, panel.counts)
+    jf = ko.OracleJellyfish(store, "p.jf", 0.05, 5)
+    seen = []
+    orig = ko.Quant.solve
+
+    def counting(self):
+        r = orig(self)
+        seen.append(self.n_iter)
+        return r
+    ko.Quant.solve = counting
+    try:
+        seqs = [panel.targets[i] for i in picks]
+        res = t.find_batch(seqs)
+        lit = t.find_batch(seqs, no_refine_jump=True)
+        longest = 0
+        for j, i in enumerate(picks):
+            del seen[:]
+            f = ko.OracleFinder(ko.Target(panel.targets[i], panel.names[i], 31), jf).run()
+            want = f.get_paths()
+            want_raw = [[float(r.rvaf), float(r.expr), float(r.ref_expr)] for r in want]
+            for run in (res, lit):
+                got = record_of(run, j, "p.jf", panel.names[i])
+                errs, _ = compare_rows([str(r) for r in want], got["rows"], want_raw, got["raw"])
+                assert not errs, (panel.names[i], errs)
+                rows = run.rows[int(run.row_first[j]):int(run.row_first[j]) + int(run.row_count[j])]
+                assert max(seen) == int(rows["n_iter"].max()), (panel.names[i], max(seen), rows["n_iter"].tolist())
+            a = res.rows[int(res.row_first[j]):int(res.row_first[j]) + int(res.row_count[j])]
+            b = lit.rows[int(lit.row_first[j]):int(lit.row_first[j]) + int(lit.row_count[j])]
+            assert a["n_iter"].tolist() == b["n_iter"].tolist()
+            for col in ("rvaf", "expr", "ref_rvaf", "ref_expr"):
+                assert np.allclose(a[col], b[col], rtol=1e-9, atol=1e-12, equal_nan=True), (panel.names[i], col)
+            longest = max(longest, max(seen))
+        assert longest >= 400           # the case this test is about did occur
+    finally:
+        ko.Quant.solve = orig
+
+
+def test_overflowing_target_fails_alone(engine):
+    """A target whose walk visits more nodes than max_node + 4 * max_stack + 4096 keeps KM_ST_NODE_OVERFLOW as ITS
+    status; the targets before and after it are processed (the reference prints every earlier target's rows
+    before it stops on one, km/tools/find_mutation.py:47-58)."""
+    rng = np.random.default_rng(11)
+    good = ["".join("ACGT"[i] for i in rng.integers(0, 4, size=90)) for _ in range(2)]
+    bad = "".join("ACGT"[i] for i in rng.integers(0, 4, size=70))
+    # a complete 4-ary tree of depth 8 hanging off the k-mer at position 20 of `bad`: 87,380 visited nodes, none of
+    # which leads back to the reference
+    root = bad[20:51]
+    level = [root]
+    keys = set()
+    for _ in range(8):
+        nxt = []
+        for s in level:
+            for c in "ACGT":
+                ch = s[1:] + c
+                v = jf_format.pack(ch)
+                keys.add(min(v, jf_format.revcomp_packed(v, 31)))
+                nxt.append(ch)
+        level = nxt
+    for s in good + [bad]:
+        for i in range(len(s) - 30):
+            v = jf_format.pack(s[i:i + 31])
+            keys.add(min(v, jf_format.revcomp_packed(v, 31)))
+    keys = np.array(sorted(keys), dtype=np.uint64)
+    t = engine.Table.create(capacity=2 * len(keys) + 1024)
+    t.insert(keys, np.full(len(keys), 100, np.uint32))
+    res = t.find_batch([good[0], bad, good[1]], branchs=20)
+    st = [int(s) for s in res.status]
+    assert st[1] & engine.ST_NODE_OVERFLOW and not (st[0] & ~16) and not (st[2] & ~16), st
+    assert int(res.row_count[0]) >= 1 and int(res.row_count[2]) >= 1 and int(res.row_count[1]) == 0
+    packed = engine.PackedTargets([good[0], bad, good[1]], ["g0", "bad", "g1"])
+    text, status = t.find_text(packed, "o.jf", branchs=20)
+    assert int(status[1]) & engine.ST_NODE_OVERFLOW
+    assert [ln.split("\t")[1] for ln in text.strip().split("\n")].count("g0") >= 1 and "\tg1\t" in text and "\tbad\t" not in text
+    with pytest.raises(RuntimeError):
+        engine.raise_for_status(status[1], "bad", 10000)
+
+
+def _two_allele_sample(rng, n_targets, k, canonical):
+    """targets with one SNV allele each; keys as stored by `jellyfish count` with or without -C"""
+    targets, table = [], {}
+    for _ in range(n_targets):
+        while True:
+            L = int(rng.integers(3 * k, 6 * k))
+            ref = "".join("ACGT"[i] for i in rng.integers(0, 4, size=L))
+            km = [ref[i:i + k] for i in range(L - k + 1)]
+            if len(set(km)) == len(km):
+                break
+        pos = int(rng.integers(k, L - k))
+        alt = ref[:pos] + "ACGT"[("ACGT".index(ref[pos]) + 1 + int(rng.integers(0, 3))) % 4] + ref[pos + 1:]
+        for seq, c in ((ref, 60), (alt, 25)):
+            for i in range(len(seq) - k + 1):
+                v = jf_format.pack(seq[i:i + k])
+                if canonical:
+                    v = min(v, jf_format.revcomp_packed(v, k))
+                table[v] = table.get(v, 0) + c
+        targets.append(ref)
+    keys = np.array(list(table.keys()), dtype=np.uint64)
+    counts = np.array(list(table.values()), dtype=np.uint32)
+    return targets, keys, counts
+
+
+@pytest.mark.parametrize("k,canonical,counter_len", [(21, True, 4), (31, False, 4), (25, False, 2), (21, True, 3)])
+def test_jf_files_with_other_k_and_strandedness(engine, tmp_path, k, canonical, counter_len):
+    """key_len != 62, canonical:false and counter_len != 4 through the writer, the loader, the probe
+    kernels and the whole find_mutation path (parity unpinned at the Jellyfish boundary: there is no reference file
+    of this kind; the oracle's store follows the same published rules)."""
+    rng = np.random.default_rng(100 * k + canonical)
+    targets, keys, counts = _two_allele_sample(rng, 24, k, canonical)
+    t = engine.Table.create(k=k, canonical=canonical, capacity=2 * len(keys) + 1024)
+    t.insert(keys, counts)
+    out = str(tmp_path / "s.jf")
+    t.write_jf(out, counter_len=counter_len)
+    header, k2, c2 = jf_format.read_jf(out)
+    assert header["key_len"] == 2 * k and header["canonical"] is canonical and header["counter_len"] == counter_len
+    assert dict(zip(k2.tolist(), c2.tolist())) == dict(zip(keys.tolist(), counts.tolist()))
+    t2 = engine.Table.open_jf(out)
+    assert t2.k == k and t2.canonical is canonical and t2.info()["n_keys"] == len(keys)
+    store = KmerStore.from_jf(out)
+    probes = np.concatenate([keys, np.array([jf_format.revcomp_packed(int(v), k) for v in keys[:400]], dtype=np.uint64),
+                             rng.integers(0, 1 << (2 * k), size=3000, dtype=np.uint64)])
+    got = t2.query_packed(probes)
+    assert (got == store.query_batch(probes)).all()
+    if not canonical:          # the other strand is a different k-mer in a stranded database
+        rc = np.array([jf_format.revcomp_packed(int(v), k) for v in keys[:400]], dtype=np.uint64)
+        present = np.isin(rc, keys)
+        assert (got[len(keys):len(keys) + 400][~present] == 0).all()
+    jf = ko.OracleJellyfish(store, "s.jf", 0.05, 5)
+    res = t2.find_batch(targets)
+    n_variant_rows = 0
+    for i, seq in enumerate(targets):
+        name = "t%d" % i
+        f = ko.OracleFinder(ko.Target(seq, name, k), jf).run()
+        want = f.get_paths()
+        got_rec = record_of(res, i, "s.jf", name)
+        errs, _ = compare_rows([str(r) for r in want], got_rec["rows"],
+                               [[float(r.rvaf), float(r.expr), float(r.ref_expr)] for r in want], got_rec["raw"])
+        assert not errs, (name, errs)
+        assert got_rec["nodes"] == sorted([kk, int(v)] for kk, v in f.node_data.items())
+        n_variant_rows += sum(1 for r in want if "Substitution" in str(r))
+    assert n_variant_rows >= 20
