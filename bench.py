@@ -240,6 +240,233 @@ def compare_with_cpu_rows(cpu, text):
 
 
 # ---------------------------------------------------------------------------------------------
+# N > 1 only: strong scaling through the product's sharded call, and cohort mode (BASELINE.json config 5)
+# ---------------------------------------------------------------------------------------------
+def strong_leg(args, table, dist, dev, rank, world, panel, text_rank0, barrier, max_over_ranks, stream):
+    """The SAME 10,000-target panel (rank 0's) dealt over the N ranks in contiguous shares, through
+    cohort.find_mutation_sharded: one km_find_text per rank (host buffers in), the texts gathered on rank 0
+    -- gather included in the timed region.  Also the device-only time of each rank's share."""
+    import torch
+    from km_b200 import cohort, engine
+    box = [(panel.targets, panel.names)] if rank == 0 else [None]
+    dist.broadcast_object_list(box, src=0)
+    targets0, names0 = box[0]
+    packed0 = engine.PackedTargets(targets0, names0)
+    plan = cohort.ShardPlan(packed0, world, rank, 31)
+    for _ in range(max(3, args.warmup)):
+        text, status = cohort.find_mutation_sharded(table, plan, "panel.jf", dist)
+    barrier()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        text, status = cohort.find_mutation_sharded(table, plan, "panel.jf", dist)
+    torch.cuda.synchronize(dev)
+    barrier()
+    e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - t0)) / args.steps
+    same = bool(np.array_equal(text, text_rank0)) if rank == 0 else None
+    # device-only: every rank's share resident in HBM, K launches, CUDA events, max over ranks
+    share = table.plan(plan.mine.sequences)
+    for _ in range(3):
+        share.launch(stream.cuda_stream)
+    torch.cuda.synchronize(dev)
+    share.fetch(want_graph=False)
+    share.launch(stream.cuda_stream)
+    barrier()
+    torch.cuda.synchronize(dev)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        share.launch(stream.cuda_stream)
+    ev1.record(stream)
+    torch.cuda.synchronize(dev)
+    barrier()
+    dev_ms = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
+    km = [max_over_ranks(x) for x in share.kernel_ms()]
+    share.close()
+    n = len(targets0)
+    worst = max(range(3), key=lambda i: km[i])
+    return {"what": "the same %d-target panel dealt over %d ranks in contiguous shares (cohort.find_mutation_sharded: one "
+                    "km_find_text per rank, texts gathered on rank 0 with 2 collectives)" % (n, world),
+            "targets": n, "e2e_ms_per_step": e2e_ms, "e2e_value": n / (e2e_ms / 1e3), "device_ms_per_step": dev_ms,
+            "device_value": n / (dev_ms / 1e3), "unit": UNIT, "text_equals_single_gpu_text": same,
+            "kernel_ms_max_over_ranks": {"ref_probe": km[0], "walks": km[1], "graph": km[2]},
+            "limited_by": ("e2e: per-call host work (enqueue, staging, the gather's two collectives) on a share of %d targets; "
+                           "device: the %s, whose tail is a handful of long dependent chains per share"
+                           % (plan.hi - plan.lo, ("reference-probe kernel", "walk kernels", "graph kernels")[worst]))}
+
+
+def cohort_leg(args, table, dist, dev, rank, world, local, panel, table_keys, barrier, max_over_ranks, sum_over_ranks, stream):
+    """BASELINE.json config 5: N synthetic samples (one per rank) -> reads -> canonical 31-mers counted ON THE DEVICE
+    into ONE table hash-sharded over the N GPUs, every k-mer sent to its owner by atomics over NVLink from inside the
+    counting kernel (`jellyfish count -m 31 -C`), counts < 2 dropped (-L 2); then a ~2e9-key synthetic background is
+    added (the 'huge table'), and the table is queried through (a) peer loads inside the probe kernel, (b) the explicit
+    exchange with device-side routing + NCCL all-to-all, (c) the panel's find_mutation; each checked."""
+    import torch
+    from km_b200 import cohort, engine
+    from km_b200._lib import lib, check
+    n_t = min(args.cohort_targets, len(panel.targets))
+    sub = synth.make_panel(n_t, seed=synth.PANEL_SEED + rank + args.panel_offset)        # the first n_t targets of this rank's panel
+    assert sub.targets == panel.targets[:n_t]
+    t0 = time.perf_counter()
+    reads = synth.sample_reads(sub)
+    gen_s = time.perf_counter() - t0
+    n_reads = reads.count(b"\n")
+    n_kmers = len(reads) - 31 * n_reads
+    counted_keys_total = int(sum_over_ranks(len(sub.keys)))
+    cap = (table_keys + 2 * counted_keys_total) // world + (1 << 20)
+    shard = cohort.ShardedTable.create(rank, world, capacity_per_shard=cap, device=local)
+    shard.attach(dist)
+    shard.set_routing(True)
+    barrier()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    shard.count_text(reads)                          # host buffer in: H2D + count kernel with routed inserts, chunks overlapped
+    torch.cuda.synchronize(dev)
+    barrier()
+    count_s = max_over_ranks(time.perf_counter() - t0)
+    kmers_total = sum_over_ranks(n_kmers)
+    bytes_total = sum_over_ranks(len(reads))
+    shard.drop_below(2)                              # -L 2 (also recounts this shard's keys)
+    barrier()
+    shard.set_routing(False)
+    kept_total = int(sum_over_ranks(shard.info()["n_keys"]))
+    # the sample's analytic content (what the reads must have produced) through peer loads -- every rank, every key
+    got = shard.query_packed(sub.keys)
+    analytic_ok = bool(sum_over_ranks(int(not (got == sub.counts).all())) == 0)
+    # the huge-table filler: the config-4 background, every rank keeps what it owns (insert-if-absent)
+    t0 = time.perf_counter()
+    shard.build_synthetic(synth.TABLE_SEED, table_keys)
+    barrier()
+    fill_s = time.perf_counter() - t0
+    keys_total = int(sum_over_ranks(shard.info()["n_keys"]))
+    # host recount of the actual read bytes of a few targets (rank 0): the counting kernel against a plain numpy count
+    recount = None
+    if rank == 0:
+        from oracle import count_oracle
+        some = list(range(min(6, n_t)))
+        hk, hc = count_oracle.count_stream(synth.sample_reads(sub, some))
+        keep = hc >= 2
+        gk = shard.query_packed(hk)
+        # (keys below 2 were dropped; a background key may sit there instead -- decided by the analytic background)
+        from oracle.store import KmerStore
+        st = KmerStore(31, True, 16)
+        st.set_background(synth.TABLE_SEED, table_keys)
+        want = np.where(keep, hc, st.query_batch(hk).astype(np.int64))
+        recount = {"targets": len(some), "kmers_distinct": int(len(hk)), "equal": bool((gk.astype(np.int64) == want).all())}
+    # ---- (a) lookups through peer loads, (b) through the device-side exchange --------------------------------------
+    nq = args.cohort_queries
+    q = torch.empty(nq, dtype=torch.int64, device=dev)
+    check(lib().km_bench_make_queries(shard._h, ctypes.c_void_p(q.data_ptr()), nq, synth.TABLE_SEED, table_keys,
+                                      synth.QUERY_SEED + 17 * rank, ctypes.c_void_p(stream.cuda_stream)))
+    out_peer = torch.empty(nq, dtype=torch.int32, device=dev)
+    out_repl = torch.empty(nq, dtype=torch.int32, device=dev)
+    sp = ctypes.c_void_p(stream.cuda_stream)
+
+    def peer():
+        check(lib().km_query_batch_device(shard._h, ctypes.c_void_p(q.data_ptr()), nq, ctypes.c_void_p(out_peer.data_ptr()), sp))
+    for _ in range(3):
+        peer()
+    barrier()
+    torch.cuda.synchronize(dev)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        peer()
+    ev1.record(stream)
+    torch.cuda.synchronize(dev)
+    barrier()
+    peer_ms = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
+    # the replicated table holds the same background (+ planted keys the query mix never asks for): equal answers expected
+    check(lib().km_query_batch_device(table._h, ctypes.c_void_p(q.data_ptr()), nq, ctypes.c_void_p(out_repl.data_ptr()), sp))
+    torch.cuda.synchronize(dev)
+    equals_unsharded = bool(sum_over_ranks(int(not torch.equal(out_peer, out_repl))) == 0)
+    hit_frac = float((out_peer != 0).sum().item()) / nq
+    with torch.cuda.stream(stream):
+        for _ in range(2):
+            out_a2a = shard.query_routed_device(q, dist)
+        barrier()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            out_a2a = shard.query_routed_device(q, dist)
+        torch.cuda.synchronize(dev)
+        barrier()
+    a2a_ms = max_over_ranks(1e3 * (time.perf_counter() - t0)) / args.steps
+    a2a_equal = bool(sum_over_ranks(int(not torch.equal(out_a2a, out_peer))) == 0)
+    del q, out_peer, out_repl, out_a2a
+    # ---- (c) the panel against the sharded table ------------------------------------------------------------------
+    packed = engine.PackedTargets(sub.targets, sub.names)
+    text_sh, _ = shard.find_text(packed, "cohort.jf", as_bytes=True)
+    text_rep, _ = table.find_text(packed, "cohort.jf", as_bytes=True)
+    text_equal = bool(sum_over_ranks(int(not np.array_equal(text_sh, text_rep))) == 0)
+    plan = shard.plan(sub.targets)
+    for _ in range(3):
+        plan.launch(stream.cuda_stream)
+    torch.cuda.synchronize(dev)
+    plan.fetch(want_graph=False)
+    plan.launch(stream.cuda_stream)
+    barrier()
+    torch.cuda.synchronize(dev)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        plan.launch(stream.cuda_stream)
+    ev1.record(stream)
+    torch.cuda.synchronize(dev)
+    barrier()
+    panel_ms = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
+    km = [max_over_ranks(x) for x in plan.kernel_ms()]
+    plan.close()
+    oracle = None
+    if rank == 0:
+        from oracle import km_oracle as ko
+        from oracle.compare import compare_rows
+        from oracle.store import KmerStore
+        st = KmerStore(31, True, len(sub.keys))
+        st.set_background(synth.TABLE_SEED, table_keys)
+        st.insert(sub.keys, sub.counts)
+        jf = ko.OracleJellyfish(st, "cohort.jf", 0.05, 5)
+        by_target = {}
+        for ln in text_sh.tobytes().decode().split("\n"):
+            if ln:
+                by_target.setdefault(ln.split("\t")[1], []).append(ln)
+        bad = 0
+        picks = list(range(0, n_t, max(1, n_t // 48)))
+        for i in picks:
+            f = ko.OracleFinder(ko.Target(sub.targets[i], sub.names[i], 31), jf).run()
+            errs, _ = compare_rows([str(r) for r in f.get_paths()], by_target.get(sub.names[i], []))
+            bad += 1 if errs else 0
+        oracle = {"targets_checked": len(picks), "mismatching": bad}
+    barrier()
+    shard.close()
+    remote = (world - 1) / world
+    return {
+        "what": "config 5: %d samples' reads counted on device into one table hash-sharded over %d GPUs (owner = top bits of the "
+                "key's hash), k-mers routed to their owner by system-scope atomics over NVLink inside the counting kernel; "
+                "+ %.3g-key synthetic background" % (world, world, table_keys),
+        "samples": world, "targets_per_sample": n_t, "reads_per_sample": n_reads, "read_bytes_total": int(bytes_total),
+        "read_generation_s_host": gen_s,
+        "count": {"kmers_total": int(kmers_total), "seconds": count_s, "kmers_per_s_whole_job": kmers_total / count_s,
+                  "read_GBps_whole_job": bytes_total / count_s / 1e9,
+                  "what": "km_table_count_text from HOST buffers on every rank at once: H2D + km_count_text_kernel, inserts routed to the owner shard",
+                  "distinct_keys_kept_after_L2": kept_total, "counts_equal_analytic_model": analytic_ok, "host_recount_of_read_bytes": recount},
+        "background_fill_s": fill_s, "table_keys_total": keys_total,
+        "peer_loads": {"queries_per_rank": nq, "ms": peer_ms, "lookups_per_s_whole_job": world * nq / (peer_ms / 1e3),
+                       "lookups_per_s_per_gpu": nq / (peer_ms / 1e3), "hit_frac": hit_frac, "equals_unsharded": equals_unsharded,
+                       "nvlink_bytes_per_lookup": 32 * remote, "remote_fraction": remote,
+                       "peer_gather_ceiling_per_gpu": 6.6e9,
+                       "frac_of_peer_gather_ceiling": (nq * remote / (peer_ms / 1e3)) / 6.6e9 if remote else None},
+        "all_to_all": {"queries_per_rank": nq, "ms": a2a_ms, "lookups_per_s_whole_job": world * nq / (a2a_ms / 1e3),
+                       "equals_peer_loads": a2a_equal, "nvlink_bytes_per_lookup": 12 * remote,
+                       "what": "km_route_partition (owner + grouping on the device) -> NCCL all_to_all_single of keys -> "
+                               "km_query_batch_device at the owner -> all_to_all_single of counts -> km_route_unpermute; only the "
+                               "per-owner counts visit the host"},
+        "panel": {"targets_per_rank": n_t, "ms_per_step": panel_ms, "targets_per_s_whole_job": world * n_t / (panel_ms / 1e3),
+                  "kernel_ms_max_over_ranks": {"ref_probe": km[0], "walks": km[1], "graph": km[2]},
+                  "text_equals_replicated_table": text_equal, "equals_oracle": oracle},
+    }
+
+
+# ---------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -255,6 +482,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-lookup", action="store_true")
     ap.add_argument("--no-tier2", action="store_true")
+    ap.add_argument("--no-cohort", action="store_true", help="skip the cohort (config 5) and strong-scaling legs at N > 1")
+    ap.add_argument("--cohort-targets", type=int, default=1000, help="targets per sample whose reads are counted in the cohort leg")
+    ap.add_argument("--cohort-queries", type=int, default=1 << 26)
     ap.add_argument("--n-sub", type=int, default=0, help="sub-batches in flight in km_find_text (0 = library default)")
     ap.add_argument("--panel-offset", type=int, default=0, help="debug: use the panel rank R would get (seed offset)")
     args = ap.parse_args()
@@ -448,6 +678,7 @@ def main():
     e2e_breakdown = {k: res.timing[k] for k in ("h2d_ms", "walk_ms", "graph_ms", "d2h_ms")}
     e2e_breakdown.update({k: v / args.steps for k, v in e2e_split.items()})
     e2e_breakdown["text_identical_to_one_call"] = bool(np.array_equal(text, text2))
+    text_bytes_rank0 = np.array(text)
     text = text.tobytes().decode()
 
     # ---- tier 2: the same panel against a REDUCED background (the first 1e7 keys of the same
@@ -492,6 +723,11 @@ def main():
             check(lib().km_bench_random_gather(local, span, 1 << 28, 3, ctypes.byref(ms)))
             gather = {"gsectors_per_s": (1 << 28) / ms.value / 1e6, "GBps": (1 << 28) * 32 / ms.value / 1e6,
                       "span_gb": span / 1e9}
+    strong = cohort_out = None
+    if world > 1 and not args.no_cohort:
+        strong = strong_leg(args, table, dist, dev, rank, world, panel, text_bytes_rank0, barrier, max_over_ranks, stream)
+        cohort_out = cohort_leg(args, table, dist, dev, rank, world, local, panel, table_keys, barrier, max_over_ranks,
+                                sum_over_ranks, stream)
     clocks = sampler.stop()
 
     # ---- parity against the CPU arm (not timed): EVERY target of rank 0's panel --------------------------------
@@ -563,7 +799,7 @@ def main():
                                    "GBps_over_whole_step": algorithmic * 32 / (ms_per_step / 1e3) / 1e9,
                                    "frac_of_random_gather_over_whole_step":
                                        (algorithmic * 32 / (ms_per_step / 1e3) / 1e9 / gather["GBps"]) if gather else None}},
-            "lookup": lookup, "random_gather": gather,
+            "lookup": lookup, "random_gather": gather, "strong": strong, "cohort": cohort_out,
             "lookups_per_s_in_panel": issued_total / (ms_per_step / 1e3),
             "clocks": clocks, "parity": parity, "cpu_baseline": cpu,
         }

@@ -61,6 +61,11 @@ int km_table_count_reads(km_table* t, const char* reads_host, const int64_t* off
  * input side of `jellyfish count` (example/run_leucegene.sh:22).  min_qual_char > 0: bases whose FASTQ quality
  * character is below it count as N (`-Q`).  Reads and bases seen come back through the two counters. */
 int km_table_count_file(km_table* t, const char* path, int min_qual_char, uint64_t* n_reads, uint64_t* n_bases);
+/* The same from a BYTE STREAM: sequences separated by any byte outside ACGTacgt (a newline between reads), n_bytes
+ * long; qual_host (may be NULL) = the FASTQ quality character of every byte, same length: with min_qual_char > 0 a
+ * base whose quality is below it ends the k-mers that contain it (`jellyfish count -Q`), decided on the device.
+ * The stream goes up in chunks through two pinned buffers, copies and kernels overlapping. */
+int km_table_count_text(km_table* t, const char* text_host, const char* qual_host, uint64_t n_bytes, int min_qual_char);
 /* drop entries with count < min_count (jellyfish count -L); returns remaining through *n_left */
 int km_table_drop_below(km_table* t, uint32_t min_count, uint64_t* n_left);
 /* `jellyfish dump`: every (canonical key, count) record of the table (of this shard in cohort mode), in no
@@ -98,6 +103,21 @@ int km_table_shard_attach_fd(km_table* t, int rank, int fd);      /* takes owner
 /* owner shard of each k-mer (forward-strand, packed): host arithmetic only, no GPU needed.  This is what
  * routes a query in the explicit all-to-all exchange (km_b200/cohort.py). */
 int km_shard_owner(const uint64_t* kmers, uint64_t n, int k, int canonical, int n_shards, int32_t* owner);
+/* Routed inserts (every peer attached first): with routing on, a key given to km_table_insert / km_table_count_* on
+ * ANY rank is inserted into its OWNER's shard by system-scope atomics over NVLink -- extraction and exchange are one
+ * kernel -- so every rank feeds its own part of the stream (its sample's reads).  With routing off (the default) a
+ * shard keeps only the keys it owns and every rank must stream everything.  After routed inserts call
+ * km_table_recount (behind a barrier): the keys of a shard were created by other ranks. */
+int km_table_set_routing(km_table* t, int on);
+int km_table_recount(km_table* t, uint64_t* n_keys);
+/* The explicit exchange on the device: owner of each k-mer; a batch of queries grouped by owner with the permutation
+ * that brings the answers back (counts_dev: 24 uint64 of scratch, [0..8) = queries per owner afterwards); the
+ * inverse permutation of the answers.  All asynchronous on `cuda_stream` (NULL = the table's). */
+int km_shard_owner_device(km_table* t, const uint64_t* kmers_dev, uint64_t n, int32_t* owner_dev, void* cuda_stream);
+int km_route_partition(km_table* t, const uint64_t* kmers_dev, uint64_t n, uint64_t* sorted_dev, uint32_t* perm_dev,
+                       uint64_t* counts_dev, void* cuda_stream);
+int km_route_unpermute(km_table* t, const uint32_t* answers_dev, const uint32_t* perm_dev, uint64_t n, uint32_t* out_dev,
+                       void* cuda_stream);
 
 /* ---- lookups: Jellyfish.query (Jellyfish.py:47-53) ---------------------------------- */
 int km_query_batch(km_table* t, const uint64_t* kmers_host, uint64_t n, uint32_t* counts_host);
@@ -250,6 +270,9 @@ int km_debug_phase_cycles(unsigned long long* out64, int reset);
 int km_debug_target_cycles(unsigned int* out, int n);   /* 64 counters */
 /* random 32-byte-sector gather over `bytes` of HBM: the ceiling for hash probes */
 int km_bench_random_gather(int device, uint64_t bytes, uint64_t n_loads, int iters, float* best_ms);
+/* the config-4 query mix (50 % background keys on a random strand, 50 % random k-mers) into a caller's device buffer */
+int km_bench_make_queries(km_table* t, uint64_t* queries_dev, uint64_t n, uint64_t table_seed, uint64_t table_n,
+                          uint64_t query_seed, void* cuda_stream);
 /* device-resident lookup benchmark: n queries (config-4 mix) generated on device, timed `iters` times */
 int km_bench_lookup(km_table* t, uint64_t table_seed, uint64_t table_n, uint64_t n_queries, uint64_t query_seed,
                     int iters, float* best_ms, float* mean_ms, uint64_t* n_hits);

@@ -74,6 +74,15 @@ def lib():
     L.km_table_build_synthetic.argtypes = [vp, u64, u64]
     L.km_table_count_reads.argtypes = [vp, cp, vp, i64]
     L.km_table_count_file.argtypes = [vp, cp, ci, P(u64), P(u64)]
+    L.km_table_count_text.argtypes = [vp, vp, vp, u64, ci]
+    L.km_table_set_routing.argtypes = [vp, ci]
+    L.km_table_recount.argtypes = [vp, P(u64)]
+    L.km_shard_owner_device.argtypes = [vp, vp, u64, vp, vp]
+    L.km_route_partition.argtypes = [vp, vp, u64, vp, vp, vp, vp]
+    L.km_route_unpermute.argtypes = [vp, vp, vp, u64, vp, vp]
+    for _n in ("km_table_count_text", "km_table_set_routing", "km_table_recount", "km_shard_owner_device", "km_route_partition",
+               "km_route_unpermute"):
+        getattr(L, _n).restype = ci
     L.km_table_drop_below.argtypes = [vp, u32, P(u64)]
     L.km_table_get_info.argtypes = [vp, P(TableInfo)]
     L.km_table_close.argtypes = [vp]
@@ -113,6 +122,8 @@ def lib():
     L.km_find_plan_free.argtypes = [vp]
     L.km_find_plan_free.restype = None
     L.km_bench_random_gather.argtypes = [ci, u64, u64, ci, P(cf)]
+    L.km_bench_make_queries.argtypes = [vp, vp, u64, u64, u64, u64, vp]
+    L.km_bench_make_queries.restype = ci
     L.km_bench_lookup.argtypes = [vp, u64, u64, u64, u64, ci, P(cf), P(cf), P(u64)]
     for name in ("km_table_open_jf", "km_table_create", "km_table_insert", "km_table_build_synthetic",
                  "km_table_count_reads", "km_table_count_file", "km_table_drop_below", "km_table_get_info", "km_query_batch",
@@ -133,5 +144,6 @@ EXPORTS = ["km_last_error", "km_device_count", "km_version", "km_table_open_jf",
            "km_table_insert", "km_table_build_synthetic", "km_table_count_reads", "km_table_count_file", "km_table_drop_below",
            "km_table_get_info", "km_table_close", "km_query_batch", "km_query_batch_device", "km_query_ascii",
            "km_get_child_batch", "km_find_batch", "km_result_get", "km_result_free", "km_result_format_target", "km_result_format_all", "km_result_text", "km_find_text", "km_table_create_layout", "km_table_export", "km_table_write_jf", "km_table_create_shard", "km_table_shard_export_fd", "km_table_shard_attach_fd", "km_shard_owner", "km_debug_format_fixed", "km_debug_nat_cmp",
+           "km_table_count_text", "km_table_set_routing", "km_table_recount", "km_shard_owner_device", "km_route_partition", "km_route_unpermute",
            "km_find_plan_create", "km_find_plan_launch", "km_find_plan_fetch", "km_find_plan_free", "km_find_plan_last_ms", "km_find_plan_kernel_ms",
-           "km_bench_random_gather", "km_bench_lookup", "km_debug_phase_cycles", "km_debug_target_cycles"]
+           "km_bench_random_gather", "km_bench_lookup", "km_bench_make_queries", "km_debug_phase_cycles", "km_debug_target_cycles"]

@@ -21,5 +21,8 @@ def get_argparser_find_mut(parser):
     parser.add_argument("-g", "--graphical", help="Display coverage graph.", action="store_true")
     parser.add_argument("-v", "--verbose", help="Get more information.", action="store_true")
     parser.add_argument("-vv", "--debug", help="Get much more information.", action="store_true")
+    # km_b200 only: the targets are dealt to this many GPUs of the box (the table is loaded on each); echoed as
+    # `#gpus:N` only when it is not 1, so that the default output stays the reference's byte for byte
+    parser.add_argument("--gpus", type=int, default=1, help="GPUs to spread the targets over (default: 1)")
     parser.add_argument("target_fn", help="Filename of the target sequence file or directory.", nargs="*")
     parser.add_argument("jellyfish_fn", help="Filename of the jellyfish database.")

@@ -62,18 +62,87 @@ def gather_in_order(local_items, local_index, n_total, dist=None, dst=0):
     return out
 
 
-def find_mutation_sharded(table, sequences, names, db_name, dist=None, **params):
-    """`km find_mutation` for a list of targets on all ranks of `dist`: every rank holds a replica of
-    the table, takes its share of the targets and formats their rows; rank 0 receives one text block
-    per target in input order (what the CLI prints)."""
+def shard_ranges(lengths, world, k=31):
+    """CONTIGUOUS ranges of targets, one per rank, balanced by reference-k-mer count: rank r gets [cut[r], cut[r+1]).
+    With contiguous ranges the text of the whole run is the ranks' texts one after the other -- rank 0 joins
+    buffers, nothing is re-ordered per target."""
+    lengths = np.asarray(lengths, dtype=np.int64)
+    weight = np.maximum(lengths - k + 1, 1)
+    csum = np.concatenate([[0], np.cumsum(weight)])
+    total = int(csum[-1])
+    cuts = [0]
+    for r in range(1, world):
+        i = int(np.searchsorted(csum, total * r / world, side="left"))
+        cuts.append(max(cuts[-1], min(i, len(lengths))))
+    cuts.append(len(lengths))
+    return cuts
+
+
+class ShardPlan:
+    """This rank's share of a batch of targets (a contiguous range) packed once, for repeated sharded runs."""
+
+    def __init__(self, packed, world, rank, k=31):
+        if not isinstance(packed, engine.PackedTargets) or packed.names is None:
+            raise TypeError("ShardPlan takes PackedTargets(sequences, names)")
+        self.n_total = len(packed)
+        self.cuts = shard_ranges([len(s) for s in packed.sequences], world, k)
+        self.lo, self.hi = self.cuts[rank], self.cuts[rank + 1]
+        self.mine = packed.slice(self.lo, self.hi)
+        self.world, self.rank = world, rank
+
+
+def find_mutation_sharded(table, targets, db_name, dist=None, device=None, raise_errors=True, **params):
+    """`km find_mutation` for a batch of targets on all ranks of `dist` (the per-target loop of
+    km/tools/find_mutation.py:47-58 dealt to the GPUs): every rank holds a replica of the table (or a shard of a
+    peer-mapped cohort table), runs ONE km_find_text call on its contiguous share, and rank 0 receives the ranks'
+    texts and per-target statuses with two collectives (sizes, then one padded gather of byte buffers) and joins
+    them in rank order = input order.  `targets`: a ShardPlan, or PackedTargets(sequences, names).
+
+    Returns (text: uint8 array, status: uint32 array over all targets) on rank 0, (None, None) elsewhere.
+    A rank whose call fails still takes part in both collectives, so nobody hangs; the error then surfaces on
+    every rank (raise_errors) after the gather, like the reference's -- which prints the rows of the targets
+    before the failing one first (the statuses of targets that failed on their own are returned, not raised:
+    callers print the text, then engine.raise_for_status in target order)."""
+    import torch
     world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
     rank = dist.get_rank() if world > 1 else 0
-    mine = shard_targets([len(s) for s in sequences], world, table.k)[rank]
-    res = table.find_batch([sequences[i] for i in mine], want_graph=False, **params)
-    for j, i in enumerate(mine.tolist()):
-        engine.raise_for_status(res.status[j], names[i], params.get("nodes", 10000))
-    texts = [res.format_target(j, db_name, names[i]) for j, i in enumerate(mine.tolist())]
-    return gather_in_order(texts, mine, len(sequences), dist)
+    plan = targets if isinstance(targets, ShardPlan) else ShardPlan(targets, world, rank, table.k)
+    err = None
+    text = np.zeros(0, dtype=np.uint8)
+    status = np.zeros(0, dtype=np.uint32)
+    try:
+        text, status = table.find_text(plan.mine, db_name, as_bytes=True, **params)
+    except Exception as e:                         # a failing CALL (not a failing target): reported after the collectives
+        err = "rank %d: %s" % (rank, e)
+    if world == 1:
+        if err and raise_errors:
+            raise RuntimeError(err)
+        return np.array(text), np.array(status)
+    dev = device if device is not None else (torch.device("cuda", table.device) if dist.get_backend() == "nccl" else torch.device("cpu"))
+    n_text, n_stat = int(text.size), int(status.size)
+    sizes = torch.tensor([n_text, n_stat, 1 if err else 0], dtype=torch.int64, device=dev)
+    all_sizes = [torch.empty_like(sizes) for _ in range(world)]
+    dist.all_gather(all_sizes, sizes)
+    all_sizes = torch.stack(all_sizes).cpu().numpy()
+    width = int((all_sizes[:, 0] + 4 * all_sizes[:, 1]).max())
+    payload = np.zeros(max(width, 1), dtype=np.uint8)
+    payload[:n_text] = text
+    payload[n_text:n_text + 4 * n_stat] = np.asarray(status, dtype=np.uint32).view(np.uint8)
+    mine = torch.from_numpy(payload).to(dev, non_blocking=True)
+    parts = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
+    dist.gather(mine, parts, dst=0)
+    any_err = bool(all_sizes[:, 2].any())
+    if any_err:
+        msgs = [None] * world
+        dist.all_gather_object(msgs, err)
+        if raise_errors:
+            raise RuntimeError("; ".join(m for m in msgs if m))
+    if rank != 0:
+        return None, None
+    host = torch.stack(parts).cpu().numpy()              # one copy back
+    texts = [h[:int(all_sizes[r, 0])] for r, h in enumerate(host)]
+    stats = [h[int(all_sizes[r, 0]):int(all_sizes[r, 0]) + 4 * int(all_sizes[r, 1])].view(np.uint32) for r, h in enumerate(host)]
+    return np.concatenate(texts), np.concatenate(stats)
 
 
 # ---- table sharded -----------------------------------------------------------------------------------
@@ -160,6 +229,46 @@ class ShardedTable(engine.Table):
                 check(lib().km_table_shard_attach_fd(self._h, server, fds[0]))
             dist.barrier()
         os.close(fd.value)
+
+    def set_routing(self, on=True):
+        """Routed inserts: every key given to insert / count_* on this rank goes to its OWNER's shard by atomics over
+        NVLink (all peers attached).  Each rank then feeds its own part of the stream -- its sample's reads."""
+        check(lib().km_table_set_routing(self._h, int(bool(on))))
+
+    def query_routed_device(self, kmers_dev, dist):
+        """The explicit exchange with everything on the device: `kmers_dev` is a CUDA int64 tensor of packed k-mers;
+        owners are computed and the batch is grouped by owner by the library's kernels (km_route_partition), the keys
+        travel with one NCCL all_to_all_single, the owner answers from its shard (km_query_batch_device), the counts
+        travel back and are put in the caller's order (km_route_unpermute).  Only the per-owner counts (8 numbers)
+        visit the host, because NCCL wants its split sizes there.  Returns a CUDA int32 tensor (uint32 bit patterns)."""
+        import torch
+        dev = kmers_dev.device
+        n = kmers_dev.numel()
+        s = torch.cuda.current_stream(dev)
+        sp = ctypes.c_void_p(s.cuda_stream)
+        sorted_k = torch.empty(n, dtype=torch.int64, device=dev)
+        perm = torch.empty(n, dtype=torch.int32, device=dev)
+        scratch = torch.empty(24, dtype=torch.int64, device=dev)
+        check(lib().km_route_partition(self._h, ctypes.c_void_p(kmers_dev.data_ptr()), n, ctypes.c_void_p(sorted_k.data_ptr()),
+                                       ctypes.c_void_p(perm.data_ptr()), ctypes.c_void_p(scratch.data_ptr()), sp))
+        send_counts_dev = scratch[:self.world].clone()
+        recv_counts_dev = torch.empty(self.world, dtype=torch.int64, device=dev)
+        dist.all_to_all_single(recv_counts_dev, send_counts_dev)
+        both = torch.stack([send_counts_dev, recv_counts_dev]).cpu()          # the one host round trip: 2 x world integers
+        send_counts, recv_counts = both[0].tolist(), both[1].tolist()
+        recv = torch.empty(int(sum(recv_counts)), dtype=torch.int64, device=dev)
+        dist.all_to_all_single(recv, sorted_k, recv_counts, send_counts)
+        answers = torch.empty(recv.numel(), dtype=torch.int32, device=dev)
+        if recv.numel():
+            check(lib().km_query_batch_device(self._h, ctypes.c_void_p(recv.data_ptr()), recv.numel(),
+                                              ctypes.c_void_p(answers.data_ptr()), sp))
+        back = torch.empty(n, dtype=torch.int32, device=dev)
+        dist.all_to_all_single(back, answers, send_counts, recv_counts)
+        out = torch.empty(n, dtype=torch.int32, device=dev)
+        check(lib().km_route_unpermute(self._h, ctypes.c_void_p(back.data_ptr()), ctypes.c_void_p(perm.data_ptr()), n,
+                                       ctypes.c_void_p(out.data_ptr()), sp))
+        self.last_route = {"send_counts": send_counts, "recv_counts": recv_counts}
+        return out
 
     def query_routed(self, kmers, dist):
         """Counts of `kmers` through the explicit all-to-all exchange (no peer mapping needed)."""

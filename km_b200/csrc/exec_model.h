@@ -118,6 +118,19 @@ KM_HD int ffs64(uint64_t x) { return __ffsll((long long)x); }
 KM_HD uint64_t atomic_or64(uint64_t* p, uint64_t v) { return atomicOr(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v); }
 KM_HD uint64_t mulhi64(uint64_t a, uint64_t b) { return __umul64hi(a, b); }
 KM_HD float add_f32(float a, float b) { return __fadd_rn(a, b); }
+// system-scope atomics: the target may be a PEER GPU's memory (a cohort shard mapped over NVLink); they are
+// carried out at the home GPU's L2, so all GPUs inserting into one shard see one another
+KM_HD uint64_t atomic_cas64_sys(uint64_t* p, uint64_t cmp, uint64_t val) {
+    return atomicCAS_system(reinterpret_cast<unsigned long long*>(p), (unsigned long long)cmp, (unsigned long long)val);
+}
+KM_HD void atomic_add32_sys(uint32_t* p, uint32_t v) { atomicAdd_system(p, v); }
+KM_HD void atomic_or64_sys(uint64_t* p, uint64_t v) { atomicOr_system(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v); }
+KM_HD void store32_sys(uint32_t* p, uint32_t v) { asm volatile("st.relaxed.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
+KM_HD uint64_t load64_sys(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
 #else
 struct CtaCtx {
     int tid() const { return 0; }
@@ -158,6 +171,11 @@ KM_HD int ffs64(uint64_t x) { return __builtin_ffsll((long long)x); }
 KM_HD uint64_t atomic_or64(uint64_t* p, uint64_t v) { uint64_t o = *p; *p = o | v; return o; }
 KM_HD uint64_t mulhi64(uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)a * b) >> 64); }
 KM_HD float add_f32(float a, float b) { volatile float r = a + b; return r; }
+KM_HD uint64_t atomic_cas64_sys(uint64_t* p, uint64_t cmp, uint64_t val) { uint64_t o = *p; if (o == cmp) *p = val; return o; }
+KM_HD void atomic_add32_sys(uint32_t* p, uint32_t v) { *p += v; }
+KM_HD void atomic_or64_sys(uint64_t* p, uint64_t v) { *p |= v; }
+KM_HD void store32_sys(uint32_t* p, uint32_t v) { *p = v; }
+KM_HD uint64_t load64_sys(const uint64_t* p) { return *p; }
 #endif
 
 }  // namespace km

@@ -149,6 +149,7 @@ struct km_table {
     int n_shards = 1, my_shard = 0;
     const Bucket* peer[KM_MAX_SHARDS] = {};
     bool attached = false;
+    int route = 0;             // km_table_set_routing: inserts go to the owner shard (peer atomics over NVLink)
     // a shard is allocated through the virtual-memory API so that peers can map it with its own 2 MiB
     // pages (a legacy cudaIpc mapping gets small pages: random probes of a 32 GB peer shard then run
     // ~70x slower, all TLB misses -- measured, profiles/README.md)
@@ -158,7 +159,7 @@ struct km_table {
     TableView view() const {
         TableView v;
         v.buckets = buckets; v.n_buckets = n_buckets; v.kmask = (1ull << (2 * k)) - 1ull; v.k = k; v.canonical = canonical;
-        v.n_shards = n_shards; v.my_shard = my_shard; v.lines = lines;
+        v.n_shards = n_shards; v.my_shard = my_shard; v.lines = lines; v.route = route;
         for (int r = 0; r < KM_MAX_SHARDS; ++r) v.shard[r] = peer[r];
         v.shard[my_shard] = buckets;
         return v;
@@ -173,3 +174,23 @@ static inline int grid_for(const km_table* t, uint64_t n, int block, int per_sm)
     if (want < 1) want = 1;
     return (int)std::min(want, cap);
 }
+
+// A byte stream of sequences on its way into the table (km_table_count_text / _reads / _file): two pinned staging
+// buffers and their device twins, so that the host fills one while the GPU copies and counts the other.
+struct CountStream {
+    km_table* t = nullptr;
+    size_t cap = 0;
+    bool want_qual = false;
+    char* pin_seq[2] = {nullptr, nullptr}; char* pin_q[2] = {nullptr, nullptr};
+    char* dev_seq[2] = {nullptr, nullptr}; char* dev_q[2] = {nullptr, nullptr};
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    bool busy[2] = {false, false};
+    int slot = 0;
+    uint64_t bytes_in = 0;
+    int open(km_table* table, size_t cap_bytes, bool with_qual);
+    char* seq() const { return pin_seq[slot]; }
+    char* qual() const { return pin_q[slot]; }
+    int submit(size_t n_bytes, int min_qual);      // asynchronous; afterwards seq()/qual() are the OTHER buffer, free to fill
+    int close();                                   // waits for the GPU, updates the table's key count, frees everything
+    ~CountStream();
+};

@@ -59,11 +59,14 @@ struct LineReader {                 // lines of a plain or gzip file, without th
     }
 };
 
-// `jellyfish count` input side: every sequence of the file goes through km_table_count_reads in batches of ~64 M
-// bases.  FASTQ records are four lines; with min_qual_char > 0 a base whose quality character is below it
-// counts as N (jellyfish count -Q).  FASTA sequences may span lines.
+// `jellyfish count` input side.  The file's sequence lines are copied ONCE, straight into a pinned staging buffer
+// (a newline between sequences), FASTQ quality lines into a parallel buffer at the same offsets; the -Q mask, the
+// 2-bit packing and the counting all happen on the device (km_count_text_kernel).  Two staging buffers: while the
+// GPU copies and counts one, this thread parses the next (CountStream).  FASTQ records are four lines; FASTA
+// sequences may span lines.
 extern "C" int km_table_count_file(km_table* t, const char* path, int min_qual_char, uint64_t* n_reads_out, uint64_t* n_bases_out) {
     if (!t || !path) return fail(KM_E_ARG, "km_table_count_file: bad argument");
+    if (t->lines) return fail(KM_E_ARG, "km_table_count_file: counting needs the sector-bucket layout");
     LineReader R;
     const size_t plen = strlen(path);
     const bool gz = plen > 3 && strcmp(path + plen - 3, ".gz") == 0;
@@ -77,25 +80,34 @@ extern "C" int km_table_count_file(km_table* t, const char* path, int min_qual_c
         if (!R.f) return fail(KM_E_IO, "cannot open %s", path);
     }
     R.buf.resize((size_t)8 << 20);
-    std::vector<char> blob;
-    std::vector<int64_t> off(1, 0);
-    blob.reserve((size_t)80 << 20);
+    CountStream cs;
+    const bool want_q = min_qual_char > 0;
+    int rc = cs.open(t, (size_t)32 << 20, want_q);
+    size_t fill = 0;
+    const size_t k1 = (size_t)t->k - 1;
     uint64_t n_reads = 0, n_bases = 0;
-    int rc = 0;
-    auto flush = [&]() -> int {
-        if (off.size() <= 1) return 0;
-        const int r = km_table_count_reads(t, blob.data(), off.data(), (int64_t)off.size() - 1);
-        blob.clear(); off.assign(1, 0);
-        return r;
+    // append `n` bases (and their qualities) to the stream; a piece that does not fit goes out and the sequence
+    // continues k - 1 bases back in the next buffer, so no k-mer is lost or counted twice
+    auto put = [&](const char* sq, const char* ql, size_t n) -> int {
+        while (n) {
+            const size_t room = fill + 1 < cs.cap ? cs.cap - fill - 1 : 0;
+            if (n <= room) {
+                memcpy(cs.seq() + fill, sq, n);
+                if (want_q) { if (ql) memcpy(cs.qual() + fill, ql, n); else memset(cs.qual() + fill, 0x7F, n); }
+                fill += n; n = 0;
+            } else if (fill == 0) {
+                memcpy(cs.seq(), sq, room);
+                if (want_q) { if (ql) memcpy(cs.qual(), ql, room); else memset(cs.qual(), 0x7F, room); }
+                if (int r = cs.submit(room, min_qual_char)) return r;
+                sq += room - k1; if (ql) ql += room - k1; n -= room - k1;
+            } else { if (int r = cs.submit(fill, min_qual_char)) return r; fill = 0; }
+        }
+        return 0;
     };
-    auto end_read = [&]() -> int {
-        if ((int64_t)blob.size() == off.back()) return 0;          // empty sequence
-        n_reads += 1; n_bases += (uint64_t)((int64_t)blob.size() - off.back());
-        off.push_back((int64_t)blob.size());
-        return blob.size() >= ((size_t)64 << 20) ? flush() : 0;
-    };
+    auto end_seq = [&]() { cs.seq()[fill] = '\n'; if (want_q) cs.qual()[fill] = 0x7F; ++fill; };
     const char* ln; size_t n;
-    bool first = true, fastq = false;
+    bool first = true, fastq = false, open_seq = false;
+    std::vector<char> held;                       // FASTQ: the sequence line, kept while its quality line is fetched
     while (!rc && R.next(&ln, &n)) {
         if (first) {
             if (!n) continue;
@@ -108,24 +120,30 @@ extern "C" int km_table_count_file(km_table* t, const char* path, int min_qual_c
             // ln is the header; then sequence, '+', quality
             const char* sq; size_t sn;
             if (!R.next(&sq, &sn)) break;
-            const size_t at = blob.size();
-            blob.insert(blob.end(), sq, sq + sn);          // (sq stays valid until the next call of next())
-            const char* pl; size_t pn; const char* ql; size_t qn;
-            if (!R.next(&pl, &pn) || !R.next(&ql, &qn)) { rc = end_read(); break; }
-            if (min_qual_char > 0 && qn == sn)
-                for (size_t i = 0; i < sn; ++i) if ((unsigned char)ql[i] < (unsigned)min_qual_char) blob[at + i] = 'N';
-            rc = end_read();
+            held.assign(sq, sq + sn);                      // (a line stays valid only until the next call of next())
+            const char* pl; size_t pn; const char* ql = nullptr; size_t qn = 0;
+            const bool whole = R.next(&pl, &pn) && R.next(&ql, &qn);
+            if (sn) {
+                rc = put(held.data(), whole && want_q && qn == sn ? ql : nullptr, sn);
+                if (!rc) { end_seq(); n_reads += 1; n_bases += sn; }
+            }
+            if (!whole) break;
         } else {
-            if (n && ln[0] == '>') rc = end_read();
-            else blob.insert(blob.end(), ln, ln + n);
+            if (n && ln[0] == '>') { if (open_seq) { end_seq(); open_seq = false; } }
+            else if (n) {
+                rc = put(ln, nullptr, n);
+                if (!open_seq) { n_reads += 1; open_seq = true; }
+                n_bases += n;
+            }
         }
     }
-    if (!rc) rc = end_read();
-    if (!rc) rc = flush();
+    if (!rc && open_seq) end_seq();
+    if (!rc && fill) rc = cs.submit(fill, min_qual_char);
+    const int rc2 = cs.close();
     if (R.gz) g_z.close(R.gz); else if (R.f && R.f != stdin) fclose(R.f);
     if (n_reads_out) *n_reads_out = n_reads;
     if (n_bases_out) *n_bases_out = n_bases;
-    return rc;
+    return rc ? rc : rc2;
 }
 
 // Column i of the 32 x 62 binary matrix written into the header.  Any matrix works as long as the records are

@@ -48,6 +48,9 @@ struct TableView {
     int my_shard;
     const Bucket* shard[KM_MAX_SHARDS];   // shard[my_shard] == buckets; others null until peers are attached
     int lines;                // 0: sector buckets (above); 1: family lines (below), n_buckets counts 128-byte lines
+    int route;                // cohort: 1 = an insert goes to the key's OWNER shard, wherever it is (peer atomics over NVLink:
+                              // every rank gives its own part of the stream); 0 = only owned keys are kept (every rank
+                              // streams everything)
 };
 
 KM_HD uint64_t key_hash(uint64_t key) { return mix64(key + KM_GOLDEN_T); }
@@ -426,8 +429,67 @@ KM_HD void table_query_family_warp(const TableView& T, uint64_t fam, const uint6
 
 enum InsertMode { KM_INSERT_KEEP = 0, KM_INSERT_OVERWRITE = 1, KM_INSERT_ADD = 2 };
 
-// Returns 1 if the key was newly inserted, 0 if it already existed (or belongs to another shard),
-// -1 if the shard is full.  Only the owner inserts a key.
+// One key into the bucket array `base` (this process's shard, or a peer's mapped over NVLink when `sys`): linear
+// probing at bucket granularity from `home`; placing a key away from home sets the home's hop bit.  Returns 1 if the
+// key was newly inserted, 0 if it already existed, -1 if the shard is full.  With `sys` every atomic has system
+// scope -- it is carried out at the home GPU's L2, which is what makes inserts from several GPUs into one shard
+// safe; plain loads of a peer's slot may be stale only in the harmless direction (a slot read as empty is then
+// claimed with a CAS, which returns what is really there; a slot once filled never changes its key).
+KM_HD int bucket_insert(Bucket* base, uint64_t n_buckets, uint64_t home, uint64_t key, uint32_t count, int mode, bool sys) {
+    uint64_t b = home;
+    for (uint64_t tries = 0; tries < n_buckets; ++tries) {
+        Bucket* bk = base + b;
+        for (int s = 0; s < KM_BUCKET_SLOTS; ++s) {
+            uint64_t cur = sys ? load64_sys(&bk->key[s]) : load_cg64(&bk->key[s]);
+            int placed = -1;
+            if (cur == KM_EMPTY_KEY) {
+                cur = sys ? atomic_cas64_sys(&bk->key[s], KM_EMPTY_KEY, key) : atomic_cas64(&bk->key[s], KM_EMPTY_KEY, key);
+                if (cur == KM_EMPTY_KEY) {
+                    if (mode == 2) { if (sys) atomic_add32_sys(&bk->count[s], count); else atomic_add32(&bk->count[s], count); }
+                    else if (sys) store32_sys(&bk->count[s], count);
+                    else bk->count[s] = count;
+                    placed = 1;
+                }
+            }
+            if (placed < 0 && cur == key) {
+                if (mode == 2) { if (sys) atomic_add32_sys(&bk->count[s], count); else atomic_add32(&bk->count[s], count); }
+                else if (mode == 1) { if (sys) store32_sys(&bk->count[s], count); else bk->count[s] = count; }
+                placed = 0;
+            }
+            if (placed >= 0) {
+                // away from home: the home bucket's hop word must name this bucket (every inserter of the key sets
+                // the same bit, so whoever finishes last leaves it set)
+                if (tries) {
+                    uint64_t* hop = reinterpret_cast<uint64_t*>(base[home].pad);
+                    const uint64_t bit = tries <= 63 ? 1ull << (tries - 1) : KM_HOP_FAR;
+                    if (sys) atomic_or64_sys(hop, bit); else atomic_or64(hop, bit);
+                }
+                return placed;
+            }
+        }
+        if (++b == n_buckets) b = 0;
+    }
+    return -1;
+}
+
+// Counting (mode add) of a key that is usually there already: ONE load of the home bucket's two keys finds it, one
+// reduction adds to it; anything else (absent, displaced) takes bucket_insert.
+KM_HD int bucket_count(Bucket* base, uint64_t n_buckets, uint64_t home, uint64_t key, uint32_t count, bool sys) {
+#if KM_DEVICE_BUILD
+    uint64_t k0, k1;               // both keys of the home bucket with one 128-bit load (at L2: the slot may have just been claimed)
+    asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(k0), "=l"(k1) : "l"(base + home) : "memory");
+    if (k0 == key || k1 == key) {
+        uint32_t* c = &base[home].count[k0 == key ? 0 : 1];
+        if (sys) atomic_add32_sys(c, count); else atomic_add32(c, count);
+        return 0;
+    }
+#endif
+    return bucket_insert(base, n_buckets, home, key, count, 2, sys);
+}
+
+// Returns 1 if the key was newly inserted, 0 if it already existed (or was left to its owner), -1 if the shard
+// is full.  Without routing only the owner inserts a key; with routing (TableView::route, peers attached) the key
+// goes to its owner's shard from wherever it was seen.
 KM_HD int table_insert(const TableView& t, uint64_t key, uint32_t count, int mode) {
     if (t.lines) {
         // two copies: under the k-mer's prefix (k-1)-mer and under its suffix (k-1)-mer; each goes to the
@@ -439,37 +501,15 @@ KM_HD int table_insert(const TableView& t, uint64_t key, uint32_t count, int mod
         return (r1 < 0 || r2 < 0) ? -1 : r1;
     }
     const uint64_t h = key_hash(key);
-    if (shard_of_hash(h, t.n_shards) != t.my_shard) return 0;
+    const int owner = shard_of_hash(h, t.n_shards);
     const uint64_t home = bucket_of_hash(h, t.n_shards, t.n_buckets);
-    uint64_t b = home;
-    for (uint64_t tries = 0; tries < t.n_buckets; ++tries) {
-        Bucket* bk = t.buckets + b;
-        for (int s = 0; s < KM_BUCKET_SLOTS; ++s) {
-            uint64_t cur = load_cg64(&bk->key[s]);
-            int placed = -1;
-            if (cur == KM_EMPTY_KEY) {
-                cur = atomic_cas64(&bk->key[s], KM_EMPTY_KEY, key);
-                if (cur == KM_EMPTY_KEY) {
-                    if (mode == KM_INSERT_ADD) atomic_add32(&bk->count[s], count);
-                    else bk->count[s] = count;
-                    placed = 1;
-                }
-            }
-            if (placed < 0 && cur == key) {
-                if (mode == KM_INSERT_ADD) atomic_add32(&bk->count[s], count);
-                else if (mode == KM_INSERT_OVERWRITE) bk->count[s] = count;
-                placed = 0;
-            }
-            if (placed >= 0) {
-                // away from home: the home bucket's hop word must name this bucket (every inserter of the key sets
-                // the same bit, so whoever finishes last leaves it set)
-                if (tries) atomic_or64(reinterpret_cast<uint64_t*>(t.buckets[home].pad), tries <= 63 ? 1ull << (tries - 1) : KM_HOP_FAR);
-                return placed;
-            }
-        }
-        if (++b == t.n_buckets) b = 0;
+    if (owner != t.my_shard) {
+        if (!t.route) return 0;
+        Bucket* base = const_cast<Bucket*>(t.shard[owner]);
+        return mode == 2 ? bucket_count(base, t.n_buckets, home, key, count, true) : bucket_insert(base, t.n_buckets, home, key, count, mode, true);
     }
-    return -1;
+    const bool sys = t.route != 0;                 // peers may be inserting into this shard at the same time
+    return mode == 2 ? bucket_count(t.buckets, t.n_buckets, home, key, count, sys) : bucket_insert(t.buckets, t.n_buckets, home, key, count, mode, sys);
 }
 
 }  // namespace km

@@ -225,6 +225,47 @@ extern "C" int km_shard_owner(const uint64_t* kmers, uint64_t n, int k, int cano
     return 0;
 }
 
+// the same on the device, and the two-pass partition of a query batch by owner (explicit all-to-all exchange,
+// km_b200/cohort.py query_routed_device): nothing but the per-owner counts ever visits the host
+extern "C" int km_shard_owner_device(km_table* t, const uint64_t* kmers_dev, uint64_t n, int32_t* owner_dev, void* stream) {
+    if (!t || (n && (!kmers_dev || !owner_dev))) return fail(KM_E_ARG, "km_shard_owner_device: bad argument");
+    if (!n) return 0;
+    cudaStream_t s = stream ? (cudaStream_t)stream : t->stream;
+    km_owner_kernel<<<grid_for(t, n, 256, 8), 256, 0, s>>>(t->view(), kmers_dev, n, owner_dev);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// counts_dev: KM_MAX_SHARDS * 3 uint64 of device scratch; on return (stream order) [0..8) holds the number of queries
+// per owner, sorted_dev the k-mers grouped by owner (owner 0 first), perm_dev[i] the position sorted_dev[i] came from
+extern "C" int km_route_partition(km_table* t, const uint64_t* kmers_dev, uint64_t n, uint64_t* sorted_dev, uint32_t* perm_dev,
+                                  uint64_t* counts_dev, void* stream) {
+    if (!t || !counts_dev || (n && (!kmers_dev || !sorted_dev || !perm_dev)) || n >= (1ull << 32))
+        return fail(KM_E_ARG, "km_route_partition: bad argument");
+    cudaStream_t s = stream ? (cudaStream_t)stream : t->stream;
+    unsigned long long* c = reinterpret_cast<unsigned long long*>(counts_dev);
+    CU(cudaMemsetAsync(c, 0, sizeof(unsigned long long) * 3 * KM_MAX_SHARDS, s));
+    if (!n) return 0;
+    const int grid = grid_for(t, n, 256, 8);
+    km_route_hist_kernel<<<grid, 256, 0, s>>>(t->view(), kmers_dev, n, c);
+    CU(cudaGetLastError());
+    km_route_prefix_kernel<<<1, 32, 0, s>>>(c);
+    CU(cudaGetLastError());
+    km_route_scatter_kernel<<<grid, 256, 0, s>>>(t->view(), kmers_dev, n, c + KM_MAX_SHARDS, c + 2 * KM_MAX_SHARDS, sorted_dev, perm_dev);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int km_route_unpermute(km_table* t, const uint32_t* answers_dev, const uint32_t* perm_dev, uint64_t n, uint32_t* out_dev,
+                                  void* stream) {
+    if (!t || (n && (!answers_dev || !perm_dev || !out_dev))) return fail(KM_E_ARG, "km_route_unpermute: bad argument");
+    if (!n) return 0;
+    cudaStream_t s = stream ? (cudaStream_t)stream : t->stream;
+    km_route_unpermute_kernel<<<grid_for(t, n, 256, 8), 256, 0, s>>>(answers_dev, perm_dev, n, out_dev);
+    CU(cudaGetLastError());
+    return 0;
+}
+
 extern "C" void km_table_close(km_table* t) {
     if (!t) return;
     cudaSetDevice(t->device);
@@ -309,22 +350,136 @@ extern "C" int km_table_build_synthetic(km_table* t, uint64_t seed, uint64_t n_k
     return finish_insert(t, "km_table_build_synthetic");
 }
 
+// ---- counting: a byte stream of sequences into the table ------------------------------------------------------
+int CountStream::open(km_table* table, size_t cap_bytes, bool with_qual) {
+    t = table; want_qual = with_qual;
+    cap = align_up_sz(std::max<size_t>(cap_bytes, 4096), 256);
+    CU(cudaSetDevice(t->device));
+    for (int b = 0; b < 2; ++b) {
+        CU(cudaMallocHost((void**)&pin_seq[b], cap));
+        CU(cudaMalloc((void**)&dev_seq[b], cap + 256));
+        if (want_qual) {
+            CU(cudaMallocHost((void**)&pin_q[b], cap));
+            CU(cudaMalloc((void**)&dev_q[b], cap + 256));
+        }
+        CU(cudaEventCreateWithFlags(&done[b], cudaEventDisableTiming));
+    }
+    CU(cudaMemsetAsync(t->d_counter, 0, 16, t->stream));
+    return 0;
+}
+int CountStream::submit(size_t n_bytes, int min_qual) {
+    if (n_bytes > cap) return fail(KM_E_ARG, "internal: count chunk of %zu bytes exceeds the staging buffer", n_bytes);
+    if (n_bytes) {
+        const bool q = want_qual && min_qual > 0;
+        CU(cudaMemcpyAsync(dev_seq[slot], pin_seq[slot], n_bytes, cudaMemcpyHostToDevice, t->stream));
+        if (q) CU(cudaMemcpyAsync(dev_q[slot], pin_q[slot], n_bytes, cudaMemcpyHostToDevice, t->stream));
+        const uint64_t n_tiles = (n_bytes + KM_COUNT_TILE - 1) / KM_COUNT_TILE;
+        const int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)t->sm_count * 8);
+        km_count_text_kernel<<<grid, KM_COUNT_CTA, 0, t->stream>>>(t->view(), (const uint32_t*)dev_seq[slot], q ? (const uint32_t*)dev_q[slot] : nullptr,
+                                                                  min_qual, n_bytes, t->d_counter, reinterpret_cast<uint32_t*>(t->d_counter + 1));
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(done[slot], t->stream));
+        busy[slot] = true;
+        bytes_in += n_bytes;
+    }
+    slot ^= 1;
+    if (busy[slot]) { CU(cudaEventSynchronize(done[slot])); busy[slot] = false; }
+    return 0;
+}
+int CountStream::close() {
+    if (!t) return 0;
+    km_table* table = t;
+    const int rc = finish_insert(table, "counting k-mers");      // synchronises the stream; with routing on, the number of new
+    for (int b = 0; b < 2; ++b) {                                // keys it adds is what THIS rank created anywhere: km_table_recount
+        if (pin_seq[b]) cudaFreeHost(pin_seq[b]);
+        if (pin_q[b]) cudaFreeHost(pin_q[b]);
+        if (dev_seq[b]) cudaFree(dev_seq[b]);
+        if (dev_q[b]) cudaFree(dev_q[b]);
+        if (done[b]) cudaEventDestroy(done[b]);
+        pin_seq[b] = pin_q[b] = dev_seq[b] = dev_q[b] = nullptr; done[b] = nullptr;
+    }
+    t = nullptr;
+    return rc;
+}
+CountStream::~CountStream() { if (t) { cudaSetDevice(t->device); cudaStreamSynchronize(t->stream); close(); } }
+
+#define KM_COUNT_CHUNK ((size_t)32 << 20)
+
+extern "C" int km_table_count_text(km_table* t, const char* text, const char* qual, uint64_t n_bytes, int min_qual_char) {
+    if (!t || (n_bytes && !text)) return fail(KM_E_ARG, "km_table_count_text: bad argument");
+    if (t->lines) return fail(KM_E_ARG, "km_table_count_text: counting needs the sector-bucket layout");
+    if (!n_bytes) return 0;
+    const bool q = qual && min_qual_char > 0;
+    CountStream cs;
+    if (int rc = cs.open(t, std::min<size_t>(KM_COUNT_CHUNK, n_bytes + 64), q)) return rc;
+    // chunks overlap by k - 1 bytes: a k-mer that straddles the cut is counted by the chunk it STARTS in, which
+    // therefore sees k - 1 bytes more than it owns; the kernel is told how many start positions are its own
+    const size_t k1 = (size_t)t->k - 1;
+    const size_t step = cs.cap - k1;
+    for (uint64_t at = 0; at < n_bytes; at += step) {
+        const size_t own = (size_t)std::min<uint64_t>(step, n_bytes - at);
+        const size_t take = (size_t)std::min<uint64_t>(own + k1, n_bytes - at);
+        memcpy(cs.seq(), text + at, take);
+        if (q) memcpy(cs.qual(), qual + at, take);
+        // bytes past `own` must not START a k-mer here (the next chunk owns them): cut the stream at own + k - 1 and
+        // blank the tail's ability to start k-mers by ending the chunk there -- a k-mer starting at p >= own needs the byte
+        // at p + k - 1 >= own + k - 1 = take, which is past the end
+        if (int rc = cs.submit(take, min_qual_char)) return rc;
+    }
+    return cs.close();
+}
+
+// the same from reads given as one concatenated buffer + offsets (reads are staged with a separator between them)
 extern "C" int km_table_count_reads(km_table* t, const char* reads, const int64_t* off, int64_t n_reads) {
     if (!t || !reads || !off || n_reads < 0) return fail(KM_E_ARG, "km_table_count_reads: bad argument");
+    if (t->lines) return fail(KM_E_ARG, "km_table_count_reads: counting needs the sector-bucket layout");
     if (n_reads == 0) return 0;
+    const uint64_t total = (uint64_t)(off[n_reads] - off[0]) + (uint64_t)n_reads;
+    CountStream cs;
+    if (int rc = cs.open(t, std::min<size_t>(KM_COUNT_CHUNK, total + 64), false)) return rc;
+    size_t fill = 0;
+    const size_t k1 = (size_t)t->k - 1;
+    for (int64_t r = 0; r < n_reads; ++r) {
+        const char* p = reads + off[r];
+        size_t len = (size_t)(off[r + 1] - off[r]);
+        while (len) {                                             // a read longer than the buffer goes in overlapping pieces
+            const size_t room = fill + 1 < cs.cap ? cs.cap - fill - 1 : 0;
+            if (len <= room) { memcpy(cs.seq() + fill, p, len); fill += len; len = 0; }
+            else if (fill == 0) {                                 // fill the whole buffer, continue k - 1 bytes back
+                memcpy(cs.seq(), p, room); fill = room;
+                if (int rc = cs.submit(fill, 0)) return rc;
+                fill = 0; p += room - k1; len -= room - k1;
+            } else { if (int rc = cs.submit(fill, 0)) return rc; fill = 0; }
+        }
+        cs.seq()[fill++] = '\n';
+    }
+    if (fill) if (int rc = cs.submit(fill, 0)) return rc;
+    return cs.close();
+}
+
+// cohort mode: route inserts to the owner shard (every peer attached); 0 switches back
+extern "C" int km_table_set_routing(km_table* t, int on) {
+    if (!t) return fail(KM_E_ARG, "null table");
+    if (on) {
+        if (t->lines) return fail(KM_E_ARG, "km_table_set_routing: shards use the sector-bucket layout");
+        for (int r = 0; r < t->n_shards; ++r)
+            if (r != t->my_shard && !t->peer[r]) return fail(KM_E_ARG, "km_table_set_routing: shard %d is not attached", r);
+    }
+    t->route = on ? 1 : 0;
+    return 0;
+}
+
+extern "C" int km_table_recount(km_table* t, uint64_t* n_keys) {
+    if (!t) return fail(KM_E_ARG, "null table");
+    if (t->lines) return fail(KM_E_ARG, "km_table_recount: sector-bucket layout only");
     CU(cudaSetDevice(t->device));
-    const int64_t total = off[n_reads];
-    if (int rc = t->dev.reserve((size_t)total + (size_t)(n_reads + 1) * 8 + 1024)) return rc;
-    t->dev.reset();
-    char* dr = t->dev.take<char>(total);
-    int64_t* doff = t->dev.take<int64_t>(n_reads + 1);
     CU(cudaMemsetAsync(t->d_counter, 0, 16, t->stream));
-    CU(cudaMemcpyAsync(dr, reads, total, cudaMemcpyHostToDevice, t->stream));
-    CU(cudaMemcpyAsync(doff, off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, t->stream));
-    km_count_reads_kernel<<<grid_for(t, total, 256, 8), 256, 0, t->stream>>>(t->view(), dr, doff, n_reads, total, t->d_counter,
-                                                                            reinterpret_cast<uint32_t*>(t->d_counter + 1));
+    km_table_recount_kernel<<<t->sm_count * 8, 256, 0, t->stream>>>(t->view(), t->d_counter);
     CU(cudaGetLastError());
-    return finish_insert(t, "km_table_count_reads");
+    t->n_keys = 0;
+    if (int rc = finish_insert(t, "km_table_recount")) return rc;
+    if (n_keys) *n_keys = t->n_keys;
+    return 0;
 }
 
 extern "C" int km_table_drop_below(km_table* t, uint32_t min_count, uint64_t* n_left) {
@@ -497,6 +652,18 @@ extern "C" int km_bench_random_gather(int device, uint64_t bytes, uint64_t n_loa
     CU(cudaGetLastError());
     cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(buf); cudaFree(sink);
     *best_ms = best;
+    return 0;
+}
+
+// the config-4 lookup mix (50 % background keys on a random strand / 50 % random k-mers) into a caller's device buffer
+extern "C" int km_bench_make_queries(km_table* t, uint64_t* queries_dev, uint64_t n, uint64_t table_seed, uint64_t table_n,
+                                     uint64_t query_seed, void* stream) {
+    if (!t || (n && !queries_dev)) return fail(KM_E_ARG, "km_bench_make_queries: bad argument");
+    if (!n) return 0;
+    CU(cudaSetDevice(t->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : t->stream;
+    km_make_queries_kernel<<<t->sm_count * 8, 256, 0, s>>>(queries_dev, n, table_seed, table_n, query_seed, t->k);
+    CU(cudaGetLastError());
     return 0;
 }
 

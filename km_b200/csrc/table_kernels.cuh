@@ -6,6 +6,7 @@
 
 #include "table.h"
 #include "synth.h"
+#include "exec_model.h"
 
 namespace km {
 
@@ -43,32 +44,156 @@ __global__ void km_table_synth_kernel(TableView T, uint64_t seed, uint64_t n, un
     if (mine) atomicAdd(n_new, mine);
 }
 
-// K1': canonical k-mer counting from reads (jellyfish count -C; run_leucegene.sh:22)
-__global__ void km_count_reads_kernel(TableView T, const char* reads, const int64_t* off, int64_t n_reads, int64_t total,
-                                      unsigned long long* n_new, uint32_t* full) {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+// K1': canonical k-mer counting from reads (jellyfish count -m k -C [-Q c]; example/run_leucegene.sh:22).
+// The input is a BYTE STREAM: sequences separated by any byte outside ACGTacgt (the reader puts a newline between
+// reads), optionally with a parallel stream of FASTQ quality characters; a k-mer is counted when its k bases are
+// letters of one sequence and -- with -Q -- none of them has a quality below min_qual.  No offsets, no search:
+// every thread owns KM_COUNT_SPAN consecutive start positions, reads the KM_COUNT_SPAN + k - 1 bytes they cover
+// ONCE from a shared-memory copy of the CTA's tile (global loads coalesced; the copy is padded one word in eight,
+// so thread t's word c sits in bank 9t + c: no conflicts) and rolls the forward and the reverse-complement k-mer
+// base by base (2 shifts, 2 ors each).  With TableView::route the insert goes to the key's owner shard over NVLink.
+#define KM_COUNT_SPAN 32
+#define KM_COUNT_CTA 256
+#define KM_COUNT_TILE (KM_COUNT_SPAN * KM_COUNT_CTA)             // start positions per CTA tile
+#define KM_COUNT_WORDS (KM_COUNT_TILE / 4 + 16)                  // words staged per tile (64 bytes past the last span's start)
+__global__ void __launch_bounds__(KM_COUNT_CTA) km_count_text_kernel(TableView T, const uint32_t* __restrict__ text,
+                                                                     const uint32_t* __restrict__ qual, int min_qual, uint64_t n_bytes,
+                                                                     unsigned long long* n_new, uint32_t* full) {
+    __shared__ uint32_t s_txt[KM_COUNT_WORDS + KM_COUNT_WORDS / 8 + 1];
+    __shared__ uint32_t s_q[KM_COUNT_WORDS + KM_COUNT_WORDS / 8 + 1];
+    const int k = T.k;
+    const uint64_t n_tiles = (n_bytes + KM_COUNT_TILE - 1) / KM_COUNT_TILE;
+    const uint64_t n_words = (n_bytes + 3) / 4;
+    const int shift_top = 2 * (k - 1);
     unsigned long long mine = 0;
-    for (int64_t pos = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pos < total; pos += stride) {
-        // binary search the read that owns this position
-        int64_t lo = 0, hi = n_reads;
-        while (hi - lo > 1) { const int64_t mid = (lo + hi) >> 1; if (off[mid] <= pos) lo = mid; else hi = mid; }
-        if (pos + T.k > off[lo + 1]) continue;
-        uint64_t v = 0; bool ok = true;
-        for (int j = 0; j < T.k; ++j) {
-            uint64_t c;
-            switch (reads[pos + j]) {
-                case 'A': case 'a': c = 0; break; case 'C': case 'c': c = 1; break;
-                case 'G': case 'g': c = 2; break; case 'T': case 't': c = 3; break;
-                default: c = 0; ok = false;
-            }
-            v = (v << 2) | c;
+    bool is_full = false;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint64_t w0 = tile * (KM_COUNT_TILE / 4);
+        __syncthreads();
+        for (int i = threadIdx.x; i < KM_COUNT_WORDS; i += KM_COUNT_CTA) {
+            const uint64_t w = w0 + (uint64_t)i;
+            s_txt[i + (i >> 3)] = w < n_words ? text[w] : 0x0A0A0A0Au;
+            if (qual) s_q[i + (i >> 3)] = w < n_words ? qual[w] : 0u;
         }
-        if (!ok) continue;
-        const int r = table_insert(T, T.canonical ? canonical(v, T.k) : v, 1u, KM_INSERT_ADD);
-        if (r < 0) *full = 1;
-        mine += r > 0;
+        __syncthreads();
+        const uint64_t p0 = tile * KM_COUNT_TILE + (uint64_t)threadIdx.x * KM_COUNT_SPAN;
+        if (p0 >= n_bytes) continue;
+        uint64_t fwd = 0, rc = 0;
+        int len = 0;
+        const int wbase = 8 * (int)threadIdx.x;
+        const int n_scan = KM_COUNT_SPAN + k - 1;                   // bytes this thread looks at (<= 62)
+        uint32_t word = 0, qword = 0;
+#pragma unroll 1
+        for (int j = 0; j < n_scan; ++j) {
+            if ((j & 3) == 0) {
+                const int wi = wbase + (j >> 2);
+                word = s_txt[wi + (wi >> 3)];
+                if (qual) qword = s_q[wi + (wi >> 3)];
+            }
+            const uint32_t b = (word >> (8 * (j & 3))) & 0xFFu;
+            const uint32_t up = (b & 0xDFu) - 65u;                   // 'A' -> 0 ... 'T' -> 19, lower case folded
+            bool ok = up < 20u && ((0x80045u >> up) & 1u) && p0 + (uint64_t)j < n_bytes;
+            if (qual) ok = ok && (int)((qword >> (8 * (j & 3))) & 0xFFu) >= min_qual;
+            const uint32_t x = (b >> 1) & 3u;                        // A0 C1 T2 G3
+            const uint64_t code = (uint64_t)(x ^ (x >> 1));          // A0 C1 G2 T3
+            fwd = ((fwd << 2) | code) & T.kmask;
+            rc = (rc >> 2) | ((3ull - code) << shift_top);
+            len = ok ? len + 1 : 0;
+            if (len >= k) {
+                const uint64_t key = T.canonical ? (rc < fwd ? rc : fwd) : fwd;
+                const int r = table_insert(T, key, 1u, KM_INSERT_ADD);
+                is_full |= r < 0;
+                mine += r > 0;
+            }
+        }
     }
-    if (mine) atomicAdd(n_new, mine);
+    if (is_full) *full = 1;
+    mine = warp_sum64(mine);
+    if (warp_leader() && mine) atomicAdd(n_new, mine);
+}
+
+// every record of the table counted again (after routed inserts the creators of a key sit on other GPUs)
+__global__ void km_table_recount_kernel(TableView T, unsigned long long* n_keys) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    unsigned long long mine = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < T.n_buckets; i += stride) {
+        uint64_t k0, k1; uint32_t c0, c1;
+        load_bucket(T.buckets + i, k0, k1, c0, c1);
+        mine += (k0 != KM_EMPTY_KEY) + (k1 != KM_EMPTY_KEY);
+    }
+    mine = warp_sum64(mine);
+    if (warp_leader() && mine) atomicAdd(n_keys, mine);
+}
+
+// ---- cohort mode, explicit exchange: route a batch of queries to their owners ON THE DEVICE ------------------
+// owner of each forward-strand k-mer (the arithmetic of locate(): canonical form, hash, top bits)
+KM_HD int owner_of(const TableView& T, uint64_t fwd) {
+    const uint64_t v = fwd & T.kmask;
+    return shard_of_hash(key_hash(T.canonical ? canonical(v, T.k) : v), T.n_shards);
+}
+__global__ void km_owner_kernel(TableView T, const uint64_t* __restrict__ kmers, uint64_t n, int32_t* __restrict__ owner) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) owner[i] = owner_of(T, kmers[i]);
+}
+// pass 1: how many queries go to each owner
+__global__ void __launch_bounds__(256) km_route_hist_kernel(TableView T, const uint64_t* __restrict__ kmers, uint64_t n,
+                                                            unsigned long long* __restrict__ counts) {
+    __shared__ unsigned int h[KM_MAX_SHARDS];
+    if (threadIdx.x < KM_MAX_SHARDS) h[threadIdx.x] = 0;
+    __syncthreads();
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < n; base += stride) {
+        const uint64_t i = base + threadIdx.x;
+        const int o = i < n ? owner_of(T, kmers[i]) : -1;
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, o);
+        if (o >= 0 && (int)(threadIdx.x & 31) == __ffs((int)peers) - 1) atomicAdd(&h[o], (unsigned int)__popc(peers));
+    }
+    __syncthreads();
+    if (threadIdx.x < KM_MAX_SHARDS && h[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)h[threadIdx.x]);
+}
+// exclusive prefix of the per-owner counts: counts[8..16) = start of each owner's range, counts[16..24) = cursors (zero)
+__global__ void km_route_prefix_kernel(unsigned long long* counts) {
+    if (threadIdx.x == 0) {
+        unsigned long long at = 0;
+        for (int o = 0; o < KM_MAX_SHARDS; ++o) { counts[KM_MAX_SHARDS + o] = at; at += counts[o]; counts[2 * KM_MAX_SHARDS + o] = 0; }
+    }
+}
+// pass 2: keys grouped by owner (start[o] = exclusive prefix of the counts; cursor[o] starts at 0), with the
+// permutation that brings the answers back.  A CTA reserves one range per owner for each chunk of 256 keys.
+__global__ void __launch_bounds__(256) km_route_scatter_kernel(TableView T, const uint64_t* __restrict__ kmers, uint64_t n,
+                                                               const unsigned long long* __restrict__ start,
+                                                               unsigned long long* __restrict__ cursor, uint64_t* __restrict__ sorted,
+                                                               uint32_t* __restrict__ perm) {
+    __shared__ unsigned int h[KM_MAX_SHARDS];
+    __shared__ unsigned long long at[KM_MAX_SHARDS];
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < n; base += stride) {
+        if (threadIdx.x < KM_MAX_SHARDS) h[threadIdx.x] = 0;
+        __syncthreads();
+        const uint64_t i = base + threadIdx.x;
+        const uint64_t key = i < n ? kmers[i] : 0ull;
+        const int o = i < n ? owner_of(T, key) : -1;
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, o);
+        const int leader = __ffs((int)peers) - 1, lane = threadIdx.x & 31;
+        unsigned int rank = 0;
+        if (o >= 0 && lane == leader) rank = atomicAdd(&h[o], (unsigned int)__popc(peers));
+        rank = __shfl_sync(0xFFFFFFFFu, rank, leader) + (unsigned int)__popc(peers & ((1u << lane) - 1u));
+        __syncthreads();
+        if (threadIdx.x < KM_MAX_SHARDS && h[threadIdx.x])
+            at[threadIdx.x] = start[threadIdx.x] + atomicAdd(&cursor[threadIdx.x], (unsigned long long)h[threadIdx.x]);
+        __syncthreads();
+        if (o >= 0) {
+            const unsigned long long dst = at[o] + rank;
+            sorted[dst] = key;
+            perm[dst] = (uint32_t)i;
+        }
+        __syncthreads();
+    }
+}
+__global__ void km_route_unpermute_kernel(const uint32_t* __restrict__ answers, const uint32_t* __restrict__ perm, uint64_t n,
+                                          uint32_t* __restrict__ out) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[perm[i]] = answers[i];
 }
 
 __global__ void km_table_clear_lines_kernel(Line* lines, uint64_t n) {

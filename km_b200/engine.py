@@ -56,6 +56,18 @@ class PackedTargets:
     def __len__(self):
         return len(self.sequences)
 
+    def slice(self, lo, hi):
+        """Targets [lo, hi) as a PackedTargets of their own (buffers cut, not re-encoded)."""
+        sub = PackedTargets.__new__(PackedTargets)
+        sub.sequences = self.sequences[lo:hi]
+        sub.blob = self.blob[int(self.off[lo]):int(self.off[hi])]
+        sub.off = (self.off[lo:hi + 1] - self.off[lo]).copy()
+        sub.names = self.names[lo:hi] if self.names is not None else None
+        if self.names is not None:
+            sub.name_blob = self.name_blob[int(self.name_off[lo]):int(self.name_off[hi])]
+            sub.name_off = (self.name_off[lo:hi + 1] - self.name_off[lo]).copy()
+        return sub
+
 
 def _pack_names(names):
     blob = "".join(names).encode()
@@ -118,6 +130,26 @@ class Table:
         off = np.zeros(len(reads) + 1, dtype=np.int64)
         np.cumsum([len(r) for r in reads], out=off[1:])
         check(lib().km_table_count_reads(self._h, blob, off.ctypes.data, len(reads)))
+
+    def count_text(self, text, qual=None, min_qual=None):
+        """Counts the k-mers of a byte stream of sequences separated by any non-ACGT byte (bytes / bytearray / uint8
+        array); `qual` = the FASTQ quality character of every byte (same length) and `min_qual` the `-Q` threshold,
+        applied on the device."""
+        buf = np.frombuffer(text, dtype=np.uint8) if not isinstance(text, np.ndarray) else np.ascontiguousarray(text, dtype=np.uint8)
+        q = 0 if min_qual is None else (ord(min_qual[0]) if isinstance(min_qual, str) else int(min_qual))
+        qp = None
+        if qual is not None and q > 0:
+            qbuf = np.frombuffer(qual, dtype=np.uint8) if not isinstance(qual, np.ndarray) else np.ascontiguousarray(qual, dtype=np.uint8)
+            if qbuf.size != buf.size:
+                raise ValueError("qual and text differ in length")
+            qp = qbuf.ctypes.data
+        check(lib().km_table_count_text(self._h, buf.ctypes.data, qp, buf.size, q))
+
+    def recount(self):
+        """Number of records in this table (this shard), counted on the device."""
+        n = ctypes.c_uint64()
+        check(lib().km_table_recount(self._h, ctypes.byref(n)))
+        return int(n.value)
 
     def count_file(self, path, min_qual=None):
         """Counts the k-mers of a FASTA / FASTQ file (plain or .gz) read by the library itself; min_qual = the

@@ -97,6 +97,7 @@ class Panel:
         self.targets = []
         self.names = []
         self.truth = []
+        self.alleles = []          # per target: [(codes uint8[], depth), ...], the reference allele first
         self.keys = np.zeros(0, dtype=np.uint64)
         self.counts = np.zeros(0, dtype=np.uint32)
 
@@ -186,6 +187,7 @@ def make_panel(n_targets, seed=PANEL_SEED, k=31, len_lo=62, len_hi=400, two_vari
             cn.append(np.full(len(ka), c_alt, dtype=np.int64))
         all_keys.append(canonical(np.concatenate(km), k))
         all_counts.append(np.concatenate(cn))
+        p.alleles.append([(ref, c_ref)] + [(a, c_alt) for a in alleles])
         p.targets.append(decode(ref))
         p.names.append("synth_%05d" % t)
         p.truth.append(info)
@@ -215,3 +217,46 @@ def lookup_queries(n, table_seed, table_n, seed=QUERY_SEED, k=31):
     q = np.concatenate([hit, miss])
     rng.shuffle(q)
     return q
+
+
+# ---- config 5: the reads a sample carrying the panel's alleles would produce ------------------------------------
+READ_LEN = 100
+
+
+def allele_reads(codes, depth, k=31, read_len=READ_LEN):
+    """The reads of one allele sequenced to `depth`: `depth` tiling passes, pass j cut at phase (37 j) mod S with
+    S = read_len - k + 1, so that every pass covers every k-mer of the allele exactly once (reads of one pass
+    overlap by k - 1 bases) and a k-mer's count is the sum of the depths of the alleles that contain it -- the
+    two-allele model of make_panel, now as actual reads.  Returns (blocks, multiplicities): blocks[phi] = the
+    newline-terminated reads of a pass with phase phi (bytes), multiplicities[phi] = how many passes have it."""
+    S = read_len - k + 1
+    seq = decode(codes).encode("ascii")
+    n_k = len(seq) - k + 1
+    if n_k <= 0 or depth <= 0:
+        return [], []
+    blocks, mult = [], []
+    full, rest = divmod(depth, S)
+    inv = pow(37, -1, S)                       # pass j has phase (37 j) mod S  <=>  j = inv * phase mod S
+    for phi in range(S):
+        m = full + (1 if (inv * phi) % S < rest else 0)
+        if m == 0:
+            continue
+        cuts = ([0] if phi > 0 else []) + list(range(phi, n_k, S)) + [n_k]
+        reads = [seq[a:b + k - 1] for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
+        blocks.append(b"\n".join(reads) + b"\n")
+        mult.append(m)
+    return blocks, mult
+
+
+def sample_reads(panel, targets=None, read_len=READ_LEN):
+    """Byte stream (reads separated by newlines) of the sample that carries `targets` (indices; default all) of the
+    panel.  Counting its canonical k-mers and dropping counts < 2 (`jellyfish count -C -L 2`) gives exactly
+    panel.keys / panel.counts restricted to those targets."""
+    idx = range(len(panel.targets)) if targets is None else targets
+    parts = []
+    for t in idx:
+        for codes, depth in panel.alleles[t]:
+            blocks, mult = allele_reads(codes, int(depth), panel.k, read_len)
+            for b, m in zip(blocks, mult):
+                parts.append(b * m)
+    return b"".join(parts)

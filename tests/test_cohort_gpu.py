@@ -70,13 +70,39 @@ def _worker(rank, world, port, out_dir):
     a = shard.find_batch(seqs, want_graph=False).format_all("panel.jf", names)
     b = whole.find_batch(seqs, want_graph=False).format_all("panel.jf", names)
     assert a == b and a.count("\n") >= len(seqs)
-    # default regime through the same ranks: targets dealt to the ranks, replicated table, rows gathered in order
-    texts = cohort.find_mutation_sharded(whole, panel.targets, panel.names, "panel.jf", dist)
+    # default regime through the same ranks: contiguous shares of the targets, replicated table, ONE km_find_text per
+    # rank, the byte buffers gathered on rank 0 in rank order = input order
+    packed = engine.PackedTargets(panel.targets, panel.names)
+    text, status = cohort.find_mutation_sharded(whole, packed, "panel.jf", dist)
     if rank == 0:
-        one = whole.find_batch(panel.targets, want_graph=False)
-        assert texts == [one.format_target(i, "panel.jf", panel.names[i]) for i in range(len(panel.targets))]
+        one, st1 = whole.find_text(packed, "panel.jf", as_bytes=True)
+        assert np.array_equal(text, one) and np.array_equal(status, st1)
     else:
-        assert texts is None
+        assert text is None and status is None
+    # the same against the SHARDED table (peer loads inside the kernels)
+    text2, _ = cohort.find_mutation_sharded(shard, packed, "panel.jf", dist)
+    if rank == 0:
+        assert np.array_equal(text2, one)
+    # routed counting: every rank feeds ITS OWN reads, keys travel to their owner by atomics over NVLink
+    counted = cohort.ShardedTable.create(rank, world, capacity_per_shard=(len(panel.keys) * 2) // world + (1 << 16))
+    counted.attach(dist)
+    counted.set_routing(True)
+    share = list(range(rank, len(panel.targets), world))
+    counted.count_text(synth.sample_reads(panel, share))
+    torch.cuda.synchronize()
+    dist.barrier()
+    counted.drop_below(2)
+    dist.barrier()
+    n_here = torch.tensor([counted.info()["n_keys"]], dtype=torch.int64, device="cuda")
+    dist.all_reduce(n_here)
+    assert int(n_here.item()) == len(panel.keys)
+    assert (counted.query_packed(panel.keys) == panel.counts).all()          # peer loads: every key, wherever it lives
+    # device-side explicit exchange == peer loads
+    qd = torch.from_numpy(q.view(np.int64)).cuda()
+    routed_dev = shard.query_routed_device(qd, dist).cpu().numpy().view(np.uint32)
+    assert (routed_dev == want).all()
+    dist.barrier()
+    counted.close()
     _say(rank, "sharded targets done")
     dist.barrier()
     with open(os.path.join(out_dir, "ok%d" % rank), "w") as f:

@@ -101,6 +101,66 @@ def test_rows_come_back_in_order_and_all_to_all_routing_equals_direct_lookup():
     _spawn(_both_worker, 57)
 
 
+class _FakeTable:
+    """stands in for engine.Table on a machine without a GPU: find_text prints one line per target"""
+    k = 31
+    device = 0
+
+    def __init__(self, fail_on_rank=None, rank=0):
+        self.fail = fail_on_rank == rank
+
+    def find_text(self, packed, db_name, as_bytes=False, **params):
+        if self.fail:
+            raise RuntimeError("boom")
+        text = "".join("%s\t%s\t%d\n" % (db_name, n, len(s)) for n, s in zip(packed.names, packed.sequences)).encode()
+        status = np.array([len(s) % 3 for s in packed.sequences], dtype=np.uint32)
+        return np.frombuffer(text, dtype=np.uint8), status
+
+
+def _sharded_worker(rank, world, port):
+    from km_b200 import engine
+    dist = _init(rank, world, port)
+    rng = np.random.default_rng(5)
+    seqs = ["A" * int(n) for n in rng.integers(62, 400, size=41)]
+    names = ["t%03d" % i for i in range(41)]
+    packed = engine.PackedTargets(seqs, names)
+    text, status = cohort.find_mutation_sharded(_FakeTable(), packed, "db.jf", dist)
+    if rank == 0:
+        want, st = _FakeTable().find_text(packed, "db.jf")
+        assert text.tobytes() == want.tobytes() and status.tolist() == st.tolist()
+    else:
+        assert text is None and status is None
+    # a rank whose call fails must not leave the others waiting in the collective: everybody raises afterwards
+    try:
+        cohort.find_mutation_sharded(_FakeTable(fail_on_rank=1, rank=rank), packed, "db.jf", dist)
+        raised = False
+    except RuntimeError as e:
+        raised = "rank 1: boom" in str(e)
+    assert raised
+    # an empty share (more ranks than targets)
+    tiny = engine.PackedTargets(seqs[:1], names[:1])
+    text, status = cohort.find_mutation_sharded(_FakeTable(), tiny, "db.jf", dist)
+    if rank == 0:
+        assert text.tobytes().count(b"\n") == 1 and len(status) == 1
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_find_mutation_gathers_text_in_input_order_and_survives_a_failing_rank():
+    _spawn(_sharded_worker)
+
+
+def test_shard_ranges_are_contiguous_and_balanced():
+    rng = np.random.default_rng(3)
+    lengths = rng.integers(62, 401, size=1000)
+    for world in (1, 2, 4, 8):
+        cuts = cohort.shard_ranges(lengths, world)
+        assert cuts[0] == 0 and cuts[-1] == 1000 and len(cuts) == world + 1 and all(b >= a for a, b in zip(cuts, cuts[1:]))
+        loads = [int((lengths[a:b] - 30).sum()) for a, b in zip(cuts, cuts[1:])]
+        assert max(loads) - min(loads) <= 800
+    assert cohort.shard_ranges([100], 4) in ([0, 0, 0, 0, 1], [0, 1, 1, 1, 1], [0, 0, 0, 1, 1], [0, 0, 1, 1, 1])
+
+
 def test_owner_is_strand_independent_for_canonical_tables():
     kb.build()
     from km_b200.engine import pack_kmer
