@@ -247,7 +247,7 @@ def strong_leg(args, table, dist, dev, rank, world, panel, text_rank0, barrier, 
     cohort.find_mutation_sharded: one km_find_text per rank (host buffers in), the texts gathered on rank 0
     -- gather included in the timed region.  Also the device-only time of each rank's share."""
     import torch
-    from km_b200 import cohort, engine
+    from km_b200 import cohort, engine, synth
     box = [(panel.targets, panel.names)] if rank == 0 else [None]
     dist.broadcast_object_list(box, src=0)
     targets0, names0 = box[0]
@@ -302,7 +302,7 @@ def cohort_leg(args, table, dist, dev, rank, world, local, panel, table_keys, ba
     added (the 'huge table'), and the table is queried through (a) peer loads inside the probe kernel, (b) the explicit
     exchange with device-side routing + NCCL all-to-all, (c) the panel's find_mutation; each checked."""
     import torch
-    from km_b200 import cohort, engine
+    from km_b200 import cohort, engine, synth
     from km_b200._lib import lib, check
     n_t = min(args.cohort_targets, len(panel.targets))
     sub = synth.make_panel(n_t, seed=synth.PANEL_SEED + rank + args.panel_offset)        # the first n_t targets of this rank's panel

@@ -76,6 +76,13 @@ int km_table_export(km_table* t, uint64_t* keys_host, uint32_t* counts_host, uin
  * hash position M * key of the `matrix1` written into the header.  counter_len 0 = 4 bytes. */
 int km_table_write_jf(km_table* t, const char* path, uint32_t counter_len);
 
+/* Writes the NEIGHBOUR MASKS: for every stored k-mer, which of its 4 successors and 4 predecessors are stored too
+ * (csrc/table.h).  km_find_* use them to answer "absent" for a successor without reading memory -- MutationFinder asks
+ * for four successors per k-mer (Jellyfish.get_child, Jellyfish.py:61-66) and three of them are absent almost everywhere.
+ * Called on demand by km_find_* after the table's content changed; call it yourself to keep that cost out of a timed
+ * region.  No-op for cohort shards and the family-line layout. */
+int km_table_link(km_table* t);
+
 typedef struct km_table_info {
     int32_t k;
     int32_t canonical;
@@ -270,6 +277,11 @@ int km_debug_phase_cycles(unsigned long long* out64, int reset);
 int km_debug_target_cycles(unsigned int* out, int n);   /* 64 counters */
 /* random 32-byte-sector gather over `bytes` of HBM: the ceiling for hash probes */
 int km_bench_random_gather(int device, uint64_t bytes, uint64_t n_loads, int iters, float* best_ms);
+/* device-resident counting benchmark: n_reads reads of read_len bases drawn from a pseudo-random genome of `genome` bases
+ * are generated on the device and counted iters + 1 times (km_count_text_kernel alone, CUDA events): best_ms2[0] = best
+ * pass over existing keys, best_ms2[1] = the first pass, which creates them */
+int km_bench_count(km_table* t, uint64_t n_reads, int read_len, uint64_t genome, uint64_t seed, int iters, float* best_ms2,
+                   uint64_t* n_kmers);
 /* the config-4 query mix (50 % background keys on a random strand, 50 % random k-mers) into a caller's device buffer */
 int km_bench_make_queries(km_table* t, uint64_t* queries_dev, uint64_t n, uint64_t table_seed, uint64_t table_n,
                           uint64_t query_seed, void* cuda_stream);

@@ -6,7 +6,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libkm_b200.so")
+# KM_B200_LIB: an alternative build of the same library (tuning experiments: tools/build_variant.py)
+LIB_PATH = os.environ.get("KM_B200_LIB") or os.path.join(HERE, "libkm_b200.so")
 
 u64, u32, i64, i32, u8 = ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int64, ctypes.c_int32, ctypes.c_uint8
 vp, cp, ci, cd, cf = ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_double, ctypes.c_float
@@ -75,12 +76,14 @@ def lib():
     L.km_table_count_reads.argtypes = [vp, cp, vp, i64]
     L.km_table_count_file.argtypes = [vp, cp, ci, P(u64), P(u64)]
     L.km_table_count_text.argtypes = [vp, vp, vp, u64, ci]
+    L.km_table_link.argtypes = [vp]
+    L.km_table_link.restype = ci
     L.km_table_set_routing.argtypes = [vp, ci]
     L.km_table_recount.argtypes = [vp, P(u64)]
     L.km_shard_owner_device.argtypes = [vp, vp, u64, vp, vp]
     L.km_route_partition.argtypes = [vp, vp, u64, vp, vp, vp, vp]
     L.km_route_unpermute.argtypes = [vp, vp, vp, u64, vp, vp]
-    for _n in ("km_table_count_text", "km_table_set_routing", "km_table_recount", "km_shard_owner_device", "km_route_partition",
+    for _n in ("km_table_link", "km_table_count_text", "km_table_set_routing", "km_table_recount", "km_shard_owner_device", "km_route_partition",
                "km_route_unpermute"):
         getattr(L, _n).restype = ci
     L.km_table_drop_below.argtypes = [vp, u32, P(u64)]
@@ -122,6 +125,8 @@ def lib():
     L.km_find_plan_free.argtypes = [vp]
     L.km_find_plan_free.restype = None
     L.km_bench_random_gather.argtypes = [ci, u64, u64, ci, P(cf)]
+    L.km_bench_count.argtypes = [vp, u64, ci, u64, u64, ci, P(cf), P(u64)]
+    L.km_bench_count.restype = ci
     L.km_bench_make_queries.argtypes = [vp, vp, u64, u64, u64, u64, vp]
     L.km_bench_make_queries.restype = ci
     L.km_bench_lookup.argtypes = [vp, u64, u64, u64, u64, ci, P(cf), P(cf), P(u64)]
@@ -140,10 +145,10 @@ def check(rc):
         raise KmError(rc, lib().km_last_error().decode("utf-8", "replace"))
 
 
-EXPORTS = ["km_last_error", "km_device_count", "km_version", "km_table_open_jf", "km_table_create",
+EXPORTS = ["km_table_link", "km_last_error", "km_device_count", "km_version", "km_table_open_jf", "km_table_create",
            "km_table_insert", "km_table_build_synthetic", "km_table_count_reads", "km_table_count_file", "km_table_drop_below",
            "km_table_get_info", "km_table_close", "km_query_batch", "km_query_batch_device", "km_query_ascii",
            "km_get_child_batch", "km_find_batch", "km_result_get", "km_result_free", "km_result_format_target", "km_result_format_all", "km_result_text", "km_find_text", "km_table_create_layout", "km_table_export", "km_table_write_jf", "km_table_create_shard", "km_table_shard_export_fd", "km_table_shard_attach_fd", "km_shard_owner", "km_debug_format_fixed", "km_debug_nat_cmp",
            "km_table_count_text", "km_table_set_routing", "km_table_recount", "km_shard_owner_device", "km_route_partition", "km_route_unpermute",
            "km_find_plan_create", "km_find_plan_launch", "km_find_plan_fetch", "km_find_plan_free", "km_find_plan_last_ms", "km_find_plan_kernel_ms",
-           "km_bench_random_gather", "km_bench_lookup", "km_bench_make_queries", "km_debug_phase_cycles", "km_debug_target_cycles"]
+           "km_bench_random_gather", "km_bench_lookup", "km_bench_make_queries", "km_bench_count", "km_debug_phase_cycles", "km_debug_target_cycles"]

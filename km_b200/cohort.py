@@ -89,6 +89,17 @@ class ShardPlan:
         self.lo, self.hi = self.cuts[rank], self.cuts[rank + 1]
         self.mine = packed.slice(self.lo, self.hi)
         self.world, self.rank = world, rank
+        self._bufs = {}
+
+    def buffer(self, name, n_bytes, device, pinned=False):
+        """A byte buffer of at least n_bytes kept across calls (device or pinned host memory)."""
+        import torch
+        cur = self._bufs.get(name)
+        if cur is None or cur.numel() < n_bytes or cur.device != device:
+            cur = torch.empty(max(64, n_bytes + n_bytes // 4), dtype=torch.uint8, device=device,
+                              pin_memory=bool(pinned and torch.cuda.is_available()))
+            self._bufs[name] = cur
+        return cur
 
 
 def find_mutation_sharded(table, targets, db_name, dist=None, device=None, raise_errors=True, **params):
@@ -119,18 +130,25 @@ def find_mutation_sharded(table, targets, db_name, dist=None, device=None, raise
             raise RuntimeError(err)
         return np.array(text), np.array(status)
     dev = device if device is not None else (torch.device("cuda", table.device) if dist.get_backend() == "nccl" else torch.device("cpu"))
+    on_gpu = dev.type == "cuda"
     n_text, n_stat = int(text.size), int(status.size)
+    mine_bytes = n_text + 4 * n_stat
     sizes = torch.tensor([n_text, n_stat, 1 if err else 0], dtype=torch.int64, device=dev)
-    all_sizes = [torch.empty_like(sizes) for _ in range(world)]
-    dist.all_gather(all_sizes, sizes)
-    all_sizes = torch.stack(all_sizes).cpu().numpy()
-    width = int((all_sizes[:, 0] + 4 * all_sizes[:, 1]).max())
-    payload = np.zeros(max(width, 1), dtype=np.uint8)
-    payload[:n_text] = text
-    payload[n_text:n_text + 4 * n_stat] = np.asarray(status, dtype=np.uint32).view(np.uint8)
-    mine = torch.from_numpy(payload).to(dev, non_blocking=True)
-    parts = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
-    dist.gather(mine, parts, dst=0)
+    all_sizes = torch.empty(3 * world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(all_sizes, sizes)
+    all_sizes = all_sizes.cpu().numpy().reshape(world, 3)
+    per_rank = (all_sizes[:, 0] + 4 * all_sizes[:, 1]).tolist()
+    # ONE collective moves every rank's bytes (text, then statuses) to rank 0: all_to_all_single with everything
+    # addressed to rank 0.  The text is read where the library left it (pinned memory) -- no host-side packing.
+    buf = plan.buffer("send", mine_bytes, dev)
+    if n_text:
+        buf[:n_text].copy_(torch.from_numpy(text), non_blocking=on_gpu)
+    if n_stat:
+        buf[n_text:mine_bytes].copy_(torch.from_numpy(np.ascontiguousarray(status, dtype=np.uint32).view(np.uint8)), non_blocking=on_gpu)
+    total = int(sum(per_rank)) if rank == 0 else 0
+    out = plan.buffer("recv", total, dev)
+    dist.all_to_all_single(out[:total], buf[:mine_bytes], per_rank if rank == 0 else [0] * world,
+                           [mine_bytes] + [0] * (world - 1))
     any_err = bool(all_sizes[:, 2].any())
     if any_err:
         msgs = [None] * world
@@ -138,11 +156,23 @@ def find_mutation_sharded(table, targets, db_name, dist=None, device=None, raise
         if raise_errors:
             raise RuntimeError("; ".join(m for m in msgs if m))
     if rank != 0:
+        if on_gpu:
+            torch.cuda.current_stream(dev).synchronize()      # the send buffer is reused by the next call
         return None, None
-    host = torch.stack(parts).cpu().numpy()              # one copy back
-    texts = [h[:int(all_sizes[r, 0])] for r, h in enumerate(host)]
-    stats = [h[int(all_sizes[r, 0]):int(all_sizes[r, 0]) + 4 * int(all_sizes[r, 1])].view(np.uint32) for r, h in enumerate(host)]
-    return np.concatenate(texts), np.concatenate(stats)
+    if on_gpu:
+        host = plan.buffer("host", total, torch.device("cpu"), pinned=True)
+        host[:total].copy_(out[:total], non_blocking=True)    # one copy back, into pinned memory
+        torch.cuda.current_stream(dev).synchronize()
+        host = host[:total].numpy()
+    else:
+        host = out[:total].numpy()
+    texts, stats, at = [], [], 0
+    for r in range(world):
+        nt, ns = int(all_sizes[r, 0]), int(all_sizes[r, 1])
+        texts.append(host[at:at + nt])
+        stats.append(host[at + nt:at + nt + 4 * ns])
+        at += nt + 4 * ns
+    return np.concatenate(texts), np.concatenate(stats).view(np.uint32)
 
 
 # ---- table sharded -----------------------------------------------------------------------------------
@@ -243,8 +273,20 @@ class ShardedTable(engine.Table):
         visit the host, because NCCL wants its split sizes there.  Returns a CUDA int32 tensor (uint32 bit patterns)."""
         import torch
         dev = kmers_dev.device
+        cur = torch.cuda.current_stream(dev)
+        if cur.cuda_stream == 0:
+            # the legacy default stream has a null handle, which the library reads as "the table's own stream": run on
+            # a real stream of ours instead, ordered after and before the caller's
+            if getattr(self, "_stream", None) is None:
+                self._stream = torch.cuda.Stream(dev)
+            self._stream.wait_stream(cur)
+            with torch.cuda.stream(self._stream):
+                out = self.query_routed_device(kmers_dev, dist)
+            cur.wait_stream(self._stream)
+            out.record_stream(cur)
+            return out
         n = kmers_dev.numel()
-        s = torch.cuda.current_stream(dev)
+        s = cur
         sp = ctypes.c_void_p(s.cuda_stream)
         sorted_k = torch.empty(n, dtype=torch.int64, device=dev)
         perm = torch.empty(n, dtype=torch.int32, device=dev)

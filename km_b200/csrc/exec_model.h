@@ -26,9 +26,9 @@ namespace km {
 // Phase timer (measurement only): lane 0 of each CTA adds the SM cycles it spent between marks to
 // a global table, read back by km_debug_phase_cycles.  Compiled in when KM_PHASE_TIMERS is defined.
 #if KM_DEVICE_BUILD && defined(KM_PHASE_TIMERS)
-__device__ unsigned long long km_phase_cycles[64];
+static __device__ unsigned long long km_phase_cycles[64];      // (one copy per translation unit: graph_kernels.cu reads its own)
 #define KM_DEBUG_TARGETS 65536
-__device__ unsigned int km_target_cycles[KM_DEBUG_TARGETS];      // graph-pass cycles of each target (last launch)
+static __device__ unsigned int km_target_cycles[KM_DEBUG_TARGETS];      // graph-pass cycles of each target (last launch)
 struct PhaseTimer {
     long long t0;
     __device__ __forceinline__ PhaseTimer() {

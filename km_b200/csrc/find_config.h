@@ -5,7 +5,9 @@
 
 namespace km {
 
+#ifndef KM_CTA
 #define KM_CTA 128
+#endif
 
 #ifndef KM_WALK_WARPS
 #define KM_WALK_WARPS 4

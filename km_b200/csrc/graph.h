@@ -22,6 +22,9 @@ namespace km {
 // hands a target over to the general pass when it exceeds them
 #define KM_MAX_PATHS 1024       // unique alternative paths per target
 #define KM_MAX_COLS 64          // columns of one least-squares problem (1 + cluster size)
+#ifndef KM_PCACHE
+#define KM_PCACHE 2048          // 16-bit node numbers of a target's paths kept in shared memory (shared-memory passes)
+#endif
 #define KM_ST_RETRY_LARGE 0x40000000u   // internal: redo this target in the general pass
 
 // a (possibly clipped) path: idx == nullptr means the reference path, whose node at
@@ -30,6 +33,7 @@ struct PathView {
     const int32_t* idx;
     int begin;
     int len;
+    const uint16_t* c16;     // the same node numbers in shared memory (16 bit), or nullptr: see GraphScratch::pcache
 };
 
 // One output row (PathQuant.Path, km/utils/PathQuant.py:10-49) in numeric form; the host
@@ -121,6 +125,12 @@ struct GraphScratch {
     unsigned long long* acc;  // [max_cols*max_cols + max_cols] exact integer accumulators of G and h
     PathView* cols;    // [max_cols] columns of the current least-squares problem
     int32_t* members;  // [max_cols]
+    // The paths' node numbers, 16 bit, in shared memory (shared-memory passes only; pcache_cap = 0 otherwise).  Every scan
+    // of a path -- ordering, diffs, the three passes of each row's solver, naming -- used to read R.pool, i.e. L2, one
+    // dependent round trip per step of its loop; from here a step costs a shared-memory load.  Paths are cached in
+    // order until the cache is full; ce_b[p] = offset of path p (rank order) in it, or -1.
+    uint16_t* pcache;
+    int pcache_cap;
     int maxN;
     int hcap;          // capacity of hk/hv (a power of two >= 2*maxN)
     int max_cand;      // capacity of the ce_* arrays
@@ -140,8 +150,8 @@ struct ScratchLayout {
     size_t stride;          // bytes per CTA
     size_t o_newidx, o_kept, o_keptk, o_hk, o_hv, o_succ, o_pred, o_deg, o_dist, o_dist2, o_before, o_after, o_hopF, o_hopB,
         o_cand, o_cand2, o_bitsF, o_bitsB, o_eflag, o_occ;
-    size_t o_ce_a, o_ce_b, o_ce_len, o_upath, o_pdiff, o_grp, o_G, o_V, o_vec, o_acc, o_cols, o_members;
-    int maxN, hcap, max_cand, max_paths, max_cols;
+    size_t o_ce_a, o_ce_b, o_ce_len, o_upath, o_pdiff, o_grp, o_G, o_V, o_vec, o_acc, o_cols, o_members, o_pcache;
+    int maxN, hcap, max_cand, max_paths, max_cols, pcache_cap;
 };
 
 KM_HOSTDEV ScratchLayout make_layout(int maxcap, int max_cand, int max_paths, int max_cols, int compact) {
@@ -165,6 +175,8 @@ KM_HOSTDEV ScratchLayout make_layout(int maxcap, int max_cand, int max_paths, in
     L.o_acc = put(8 * (nc * nc + nc));
     const size_t quant_end = o;
     L.o_cols = put(sizeof(PathView) * nc); L.o_members = put(4 * nc);
+    L.pcache_cap = compact ? KM_PCACHE : 0;
+    L.o_pcache = put(2 * (size_t)L.pcache_cap);
     if (compact) { L.o_kept = L.o_cand; L.o_keptk = L.o_succ; }
     else { L.o_kept = put(4 * maxN); L.o_keptk = put(8 * maxN); }
     if (compact && 12 * hcap <= tree_end - L.o_dist) { L.o_hk = L.o_dist; L.o_hv = L.o_dist + 8 * hcap; }
@@ -192,6 +204,7 @@ KM_HOSTDEV GraphScratch carve(const ScratchLayout& L, char* p, int retry) {
     S.G = (double*)(p + L.o_G); S.V = (double*)(p + L.o_V); S.vec = (double*)(p + L.o_vec);
     S.acc = (unsigned long long*)(p + L.o_acc);
     S.cols = (PathView*)(p + L.o_cols); S.members = (int32_t*)(p + L.o_members);
+    S.pcache = (uint16_t*)(p + L.o_pcache); S.pcache_cap = L.pcache_cap;
     S.maxN = L.maxN; S.hcap = L.hcap; S.max_cand = L.max_cand; S.max_paths = L.max_paths; S.max_cols = L.max_cols; S.retry = retry;
     return S;
 }
@@ -737,6 +750,24 @@ KM_HD bool graph_target(const Ctx& ctx, const TableView& T, const WalkView& W, c
     ctx.sync();
 
     pt.mark(6);
+    // ---- the paths once more in shared memory, 16 bit (GraphScratch::pcache): ce_a[u] = offset of path u, -1 = not cached
+    if (tid == 0) {
+        int at = 0;
+        for (int u = 0; u < nu; ++u) {
+            const int len = S.ce_len[u] - 2;
+            if (at + len <= S.pcache_cap) { S.ce_a[u] = at; at += len; }
+            else S.ce_a[u] = -1;
+        }
+    }
+    ctx.sync();
+    for (int u = 0; u < nu; ++u) {
+        const int at = S.ce_a[u];
+        if (at < 0) continue;
+        const int32_t* src = R.pool + R.path_off[first + u];
+        const int len = S.ce_len[u] - 2;
+        for (int i = tid; i < len; i += nt) S.pcache[at + i] = (uint16_t)src[i];
+    }
+    ctx.sync();
     // ---- lexicographic order (sorted(set of tuples)): rank by pairwise CTA-parallel compares ----
     if (nu > 1) {
         int* slot = sh + 8;
@@ -744,50 +775,65 @@ KM_HD bool graph_target(const Ctx& ctx, const TableView& T, const WalkView& W, c
         ctx.sync();
         for (int x = 0; x < nu - 1; ++x)
             for (int y = x + 1; y < nu; ++y) {
-                const int32_t* px = R.pool + R.path_off[first + x];
-                const int32_t* py = R.pool + R.path_off[first + y];
-                const int lx = R.path_len[first + x], ly = R.path_len[first + y], m = lx < ly ? lx : ly;
+                const int lx = S.ce_len[x] - 2, ly = S.ce_len[y] - 2, m = lx < ly ? lx : ly;
+                const int cx = S.ce_a[x], cy = S.ce_a[y];
+                const bool cached = cx >= 0 && cy >= 0;
+                const int32_t* px = R.pool + (cached ? 0 : R.path_off[first + x]);
+                const int32_t* py = R.pool + (cached ? 0 : R.path_off[first + y]);
                 if (tid == 0) *slot = m;
                 ctx.sync();
-                for (int q = tid; q < m; q += nt)
-                    if (px[q] != py[q]) { atomic_mini32(slot, q); break; }
+                if (cached) {
+                    for (int q = tid; q < m; q += nt)
+                        if (S.pcache[cx + q] != S.pcache[cy + q]) { atomic_mini32(slot, q); break; }
+                } else {
+                    for (int q = tid; q < m; q += nt)
+                        if (px[q] != py[q]) { atomic_mini32(slot, q); break; }
+                }
                 ctx.sync();
                 if (tid == 0) {
                     const int q = *slot;
-                    const bool x_less = q < m ? px[q] < py[q] : lx < ly;
+                    const bool x_less = q < m ? (cached ? S.pcache[cx + q] < S.pcache[cy + q] : px[q] < py[q]) : lx < ly;
                     S.upath[x_less ? y : x] += 1;
                 }
                 ctx.sync();
             }
         if (tid == 0) {
-            // permute (offset, length) into rank order; pdiff / ce_len serve as temporaries
+            // permute (offset, length, cache offset) into rank order; pdiff / ce_b serve as temporaries
             for (int u = 0; u < nu; ++u) {
                 const int64_t off = R.path_off[first + u];
-                S.pdiff[2 * u] = (int32_t)(off & 0x7FFFFFFF); S.pdiff[2 * u + 1] = (int32_t)(off >> 31);
-                S.ce_len[u] = R.path_len[first + u];
+                S.pdiff[4 * u] = (int32_t)(off & 0x7FFFFFFF); S.pdiff[4 * u + 1] = (int32_t)(off >> 31);
+                S.pdiff[4 * u + 2] = S.ce_len[u] - 2; S.pdiff[4 * u + 3] = S.ce_a[u];
             }
             for (int u = 0; u < nu; ++u) {
-                R.path_off[first + S.upath[u]] = ((int64_t)S.pdiff[2 * u + 1] << 31) | (int64_t)S.pdiff[2 * u];
-                R.path_len[first + S.upath[u]] = S.ce_len[u];
+                const int r = S.upath[u];
+                R.path_off[first + r] = ((int64_t)S.pdiff[4 * u + 1] << 31) | (int64_t)S.pdiff[4 * u];
+                R.path_len[first + r] = S.pdiff[4 * u + 2];
+                S.ce_len[r] = S.pdiff[4 * u + 2];
+                S.ce_b[r] = S.pdiff[4 * u + 3];
             }
         }
         ctx.sync();
+    } else if (nu == 1) {
+        if (tid == 0) { S.ce_b[0] = S.ce_a[0]; S.ce_len[0] = S.ce_len[0] - 2; }
+        ctx.sync();
     }
+    // from here on: ce_len[p] = length and ce_b[p] = cache offset of path p in rank order
     pt.mark(7);
     // ---- spell every unique path once (MutationFinder.get_seq, :375-403): first k-mer, then the last
     // base of each following node; rows print slices of these strings
     if (R.seq_pool) {
         int64_t soff = ((int64_t)sh[11] << 31) | (int64_t)sh[10];
         for (int p = 0; p < nu; ++p) {
-            const int len = R.path_len[first + p];
-            const int32_t* idx = R.pool + R.path_off[first + p];
+            const int len = S.ce_len[p];
+            const int cat = S.ce_b[p];
+            const int32_t* idx = R.pool + (cat >= 0 ? 0 : R.path_off[first + p]);
             if (tid == 0) R.path_seq_off[first + p] = soff;
             if (len > 0) {
-                const uint64_t k0 = R.out_kmer[g.nbase + idx[0]];
+                const uint64_t k0 = R.out_kmer[g.nbase + (cat >= 0 ? (int)S.pcache[cat] : idx[0])];
                 for (int c = tid; c < len + k - 1; c += nt) {
                     int code;
                     if (c < k) code = (int)((k0 >> (2 * (k - 1 - c))) & 3ull);
-                    else code = (int)(R.out_kmer[g.nbase + idx[c - k + 1]] & 3ull);
+                    else code = (int)(R.out_kmer[g.nbase + (cat >= 0 ? (int)S.pcache[cat + c - k + 1] : idx[c - k + 1])] & 3ull);
                     R.seq_pool[soff + c] = "ACGT"[code];
                 }
             }

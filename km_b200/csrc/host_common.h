@@ -32,6 +32,8 @@ using namespace km;
 
 extern thread_local char g_err[512];
 int fail(int code, const char* fmt, ...);
+struct km_table;
+int km_ensure_linked(km_table* t);      // writes the neighbour masks if the table's content changed since (table_api.cu)
 
 #define CU(call)                                                                                  \
     do {                                                                                          \
@@ -150,6 +152,7 @@ struct km_table {
     const Bucket* peer[KM_MAX_SHARDS] = {};
     bool attached = false;
     int route = 0;             // km_table_set_routing: inserts go to the owner shard (peer atomics over NVLink)
+    bool linked = false;       // the neighbour masks (table.h) are current; any change of content clears this
     // a shard is allocated through the virtual-memory API so that peers can map it with its own 2 MiB
     // pages (a legacy cudaIpc mapping gets small pages: random probes of a 32 GB peer shard then run
     // ~70x slower, all TLB misses -- measured, profiles/README.md)
@@ -160,6 +163,7 @@ struct km_table {
         TableView v;
         v.buckets = buckets; v.n_buckets = n_buckets; v.kmask = (1ull << (2 * k)) - 1ull; v.k = k; v.canonical = canonical;
         v.n_shards = n_shards; v.my_shard = my_shard; v.lines = lines; v.route = route;
+        v.linked = (linked && n_shards == 1 && !lines) ? 1 : 0;
         for (int r = 0; r < KM_MAX_SHARDS; ++r) v.shard[r] = peer[r];
         v.shard[my_shard] = buckets;
         return v;

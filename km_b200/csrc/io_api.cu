@@ -2,6 +2,9 @@
 // (km_table_count_file, the input side of `jellyfish count`, example/run_leucegene.sh:22), Jellyfish
 // binary/sorted databases in and out (km_table_open_jf: km/utils/Jellyfish.py:23-45; km_table_write_jf).
 #include "host_common.h"
+#include "table.h"
+#include "exec_model.h"
+#include <sys/types.h>
 
 // ---- counting straight from FASTA / FASTQ files (plain or .gz) ------------------------------------------
 // zlib is looked up at run time (dlopen), like the driver's virtual-memory entry points: the library loads on
@@ -237,6 +240,30 @@ static bool json_field(const std::string& js, const char* name, std::string* out
     return true;
 }
 
+// records of `rec` bytes (kbytes of key, little-endian, then cbytes of count) decoded and inserted on the device
+__global__ void __launch_bounds__(256) km_jf_insert_kernel(TableView T, const uint8_t* __restrict__ raw, uint64_t n_rec, int kbytes,
+                                                            int cbytes, unsigned long long* n_new, uint32_t* full) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const int rec = kbytes + cbytes;
+    unsigned long long mine = 0;
+    bool is_full = false;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_rec; i += stride) {
+        const uint8_t* p = raw + i * (uint64_t)rec;
+        uint64_t key = 0, cnt = 0;
+        for (int b = 0; b < kbytes; ++b) key |= (uint64_t)p[b] << (8 * b);
+        for (int b = 0; b < cbytes; ++b) cnt |= (uint64_t)p[kbytes + b] << (8 * b);
+        const int r = table_insert(T, key & T.kmask, cnt > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)cnt, KM_INSERT_OVERWRITE);
+        is_full |= r < 0;
+        mine += r > 0;
+    }
+    if (is_full) *full = 1;
+    mine = warp_sum64(mine);
+    if (warp_leader() && mine) atomicAdd(n_new, mine);
+}
+
+// Jellyfish(filename) (km/utils/Jellyfish.py:23-45): the header is parsed on the host, the records -- gigabytes for a real
+// sample (example/README.rst:47-48) -- stream through two pinned buffers (pread of the next chunk overlaps the copy and the
+// decode + insert kernel of the previous one); nothing is decoded or staged per record on the host.
 extern "C" int km_table_open_jf(const char* path, int device, km_table** out) {
     if (!path || !out) return fail(KM_E_ARG, "km_table_open_jf: null argument");
     FILE* f = fopen(path, "rb");
@@ -254,29 +281,63 @@ extern "C" int km_table_open_jf(const char* path, int device, km_table** out) {
     const int kbits = atoi(key_len.c_str()), cbytes = atoi(counter_len.c_str());
     if (kbits < 2 || kbits > 62 || (kbits & 1) || cbytes < 1 || cbytes > 8) { fclose(f); return fail(KM_E_IO, "%s: key_len %d / counter_len %d not supported", path, kbits, cbytes); }
     const int kbytes = (kbits + 7) / 8, rec = kbytes + cbytes;
-    fseek(f, 0, SEEK_END);
-    const long fsize = ftell(f);
-    const long payload = fsize - 9 - hlen;
-    if (payload < 0 || payload % rec) { fclose(f); return fail(KM_E_IO, "%s: payload of %ld bytes is not a multiple of %d", path, payload, rec); }
+    fseeko(f, 0, SEEK_END);
+    const int64_t fsize = (int64_t)ftello(f);
+    const int64_t payload = fsize - 9 - hlen;
+    if (payload < 0 || payload % rec) { fclose(f); return fail(KM_E_IO, "%s: payload of %lld bytes is not a multiple of %d", path, (long long)payload, rec); }
     const uint64_t n = (uint64_t)(payload / rec);
-    std::vector<unsigned char> raw((size_t)payload);
-    fseek(f, 9 + hlen, SEEK_SET);
-    if (payload && fread(raw.data(), 1, (size_t)payload, f) != (size_t)payload) { fclose(f); return fail(KM_E_IO, "%s: short read", path); }
-    fclose(f);
-    std::vector<uint64_t> keys(n);
-    std::vector<uint32_t> counts(n);
-    for (uint64_t i = 0; i < n; ++i) {
-        const unsigned char* p = raw.data() + i * rec;
-        uint64_t key = 0, cnt = 0;
-        for (int b = 0; b < kbytes; ++b) key |= (uint64_t)p[b] << (8 * b);
-        for (int b = 0; b < cbytes; ++b) cnt |= (uint64_t)p[kbytes + b] << (8 * b);
-        keys[i] = key;
-        counts[i] = cnt > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)cnt;
-    }
     km_table* t = nullptr;
-    if (int rc = km_table_create(device, kbits / 2, canon == "true", std::max<uint64_t>(n, 1024), &t)) return rc;
-    if (int rc = km_table_insert(t, keys.data(), counts.data(), n, KM_INSERT_OVERWRITE)) { km_table_close(t); return rc; }
+    if (int rc = km_table_create(device, kbits / 2, canon == "true", std::max<uint64_t>(n, 1024), &t)) { fclose(f); return rc; }
+    // two pinned chunks of whole records
+    const size_t chunk_rec = std::max<size_t>(1, std::min<size_t>(((size_t)64 << 20) / (size_t)rec, (size_t)std::max<uint64_t>(n, 1)));
+    const size_t chunk_bytes = chunk_rec * (size_t)rec;
+    char* pin[2] = {nullptr, nullptr}; char* dev[2] = {nullptr, nullptr};
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    bool busy[2] = {false, false};
+    int rc = 0;
+    auto cleanup = [&]() {
+        for (int b = 0; b < 2; ++b) { if (pin[b]) cudaFreeHost(pin[b]); if (dev[b]) cudaFree(dev[b]); if (done[b]) cudaEventDestroy(done[b]); }
+        fclose(f);
+    };
+    for (int b = 0; b < 2 && !rc; ++b) {
+        if (cudaMallocHost((void**)&pin[b], chunk_bytes) != cudaSuccess || cudaMalloc((void**)&dev[b], chunk_bytes) != cudaSuccess ||
+            cudaEventCreateWithFlags(&done[b], cudaEventDisableTiming) != cudaSuccess)
+            rc = fail(KM_E_CUDA, "km_table_open_jf: staging buffers of %zu bytes: %s", chunk_bytes, cudaGetErrorString(cudaGetLastError()));
+    }
+    if (!rc && cudaMemsetAsync(t->d_counter, 0, 16, t->stream) != cudaSuccess) rc = fail(KM_E_CUDA, "memset failed");
+    const int fd = fileno(f);
+    int64_t at = 9 + hlen;
+    int slot = 0;
+    for (uint64_t left = n; !rc && left; slot ^= 1) {
+        const size_t m = (size_t)std::min<uint64_t>(left, chunk_rec), bytes = m * (size_t)rec;
+        if (busy[slot]) { if (cudaEventSynchronize(done[slot]) != cudaSuccess) { rc = fail(KM_E_CUDA, "event sync failed"); break; } busy[slot] = false; }
+        size_t got = 0;
+        while (got < bytes) {
+            const ssize_t r = pread(fd, pin[slot] + got, bytes - got, (off_t)(at + (int64_t)got));
+            if (r <= 0) break;
+            got += (size_t)r;
+        }
+        if (got != bytes) { rc = fail(KM_E_IO, "%s: short read", path); break; }
+        if (cudaMemcpyAsync(dev[slot], pin[slot], bytes, cudaMemcpyHostToDevice, t->stream) != cudaSuccess) { rc = fail(KM_E_CUDA, "copy failed"); break; }
+        km_jf_insert_kernel<<<(int)std::min<uint64_t>((m + 255) / 256, (uint64_t)t->sm_count * 8), 256, 0, t->stream>>>(
+            t->view(), (const uint8_t*)dev[slot], (uint64_t)m, kbytes, cbytes, t->d_counter, reinterpret_cast<uint32_t*>(t->d_counter + 1));
+        if (cudaGetLastError() != cudaSuccess || cudaEventRecord(done[slot], t->stream) != cudaSuccess) { rc = fail(KM_E_CUDA, "launch failed"); break; }
+        busy[slot] = true;
+        at += (int64_t)bytes;
+        left -= m;
+    }
+    if (!rc) {
+        unsigned long long host[2] = {0, 0};
+        if (cudaMemcpyAsync(host, t->d_counter, 16, cudaMemcpyDeviceToHost, t->stream) != cudaSuccess || cudaStreamSynchronize(t->stream) != cudaSuccess)
+            rc = fail(KM_E_CUDA, "km_table_open_jf: %s", cudaGetErrorString(cudaGetLastError()));
+        else {
+            t->n_keys += host[0];
+            t->linked = false;
+            if ((uint32_t)host[1]) rc = fail(KM_E_FULL, "km_table_open_jf: table full");
+        }
+    } else cudaStreamSynchronize(t->stream);
+    cleanup();
+    if (rc) { km_table_close(t); return rc; }
     *out = t;
     return 0;
 }
-

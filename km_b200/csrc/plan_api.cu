@@ -359,6 +359,7 @@ extern "C" int km_find_plan_create(km_table* t, const char* seqs, const int64_t*
                                    km_plan** out) {
     if (!t || !out || n < 0 || (n && (!seqs || !offsets)) || !params) return fail(KM_E_ARG, "km_find_plan_create: bad argument");
     CU(cudaSetDevice(t->device));
+    if (int rc = km_ensure_linked(t)) return rc;
     km_plan* p = new km_plan();
     if (int rc = plan_init(t, seqs, offsets, n, params, p, false)) { delete p; return rc; }
     CU(cudaStreamSynchronize(t->stream));
@@ -369,6 +370,7 @@ extern "C" int km_find_plan_create(km_table* t, const char* seqs, const int64_t*
 extern "C" int km_find_plan_launch(km_plan* p, void* stream) {
     if (!p) return fail(KM_E_ARG, "null plan");
     CU(cudaSetDevice(p->t->device));
+    if (int rc = km_ensure_linked(p->t)) return rc;
     return plan_launch(p, stream ? (cudaStream_t)stream : p->stream);
 }
 
@@ -415,6 +417,7 @@ extern "C" int km_find_batch(km_table* t, const char* seqs, const int64_t* offse
                              km_result** out) {
     if (!t || !out || n < 0 || (n && (!seqs || !offsets)) || !params) return fail(KM_E_ARG, "km_find_batch: bad argument");
     CU(cudaSetDevice(t->device));
+    if (int rc = km_ensure_linked(t)) return rc;
     km_plan plan;
     if (int rc = plan_init(t, seqs, offsets, n, params, &plan, true)) return rc;
     km_result* res = new km_result();

@@ -22,7 +22,20 @@
 
 namespace km {
 
-KM_HD int pv_at(const PathView& p, int i) { return p.idx ? p.idx[p.begin + i] : p.begin + i; }
+KM_HD int pv_at(const PathView& p, int i) {
+    return p.c16 ? (int)p.c16[p.begin + i] : (p.idx ? p.idx[p.begin + i] : p.begin + i);
+}
+// path p of the target (rank order) as a view: its node numbers come from the shared-memory cache when it holds them
+// (graph_target leaves ce_len[p] = length and ce_b[p] = cache offset or -1)
+KM_HD PathView path_view(const GraphScratch& S, const ResultView& R, int first_path, int p) {
+    PathView v;
+    const int at = S.ce_b[p];
+    v.c16 = (S.pcache_cap > 0 && at >= 0) ? S.pcache + at : nullptr;
+    v.idx = R.pool + R.path_off[first_path + p];
+    v.begin = 0;
+    v.len = S.ce_len[p];
+    return v;
+}
 // Python indexing: a negative position counts from the end (the reference's third scan can run
 // its alt cursor below zero, MutationFinder.py:362-369); beyond that Python raises -> no match
 KM_HD int pv_at_wrap(const PathView& p, int i) {
@@ -543,16 +556,17 @@ KM_HD void cluster_columns(const GraphScratch& S, const ResultView& R, const Gra
     const int off0 = lo - span > 0 ? lo - span : 0;             // (:713)
     // Python slices clamp to the sequence (:714, :720)
     const int ref_stop = hi < d.L ? hi : d.L;
-    cols[0].idx = nullptr; cols[0].begin = off0; cols[0].len = ref_stop - off0 > 0 ? ref_stop - off0 : 0;
+    cols[0].idx = nullptr; cols[0].c16 = nullptr; cols[0].begin = off0; cols[0].len = ref_stop - off0 > 0 ? ref_stop - off0 : 0;
     for (int j = 0; j < size; ++j) {
         const int p = members[j];
-        const int plen = R.path_len[first_path + p];
+        PathView v = path_view(S, R, first_path, p);
+        const int plen = v.len;
         int stop = S.pdiff[4 * p + 2] + hi - S.pdiff[4 * p + 1];   // (:719)
         stop = stop < plen ? stop : plen;
         const int beg = off0 < plen ? off0 : plen;
-        cols[1 + j].idx = R.pool + R.path_off[first_path + p];
-        cols[1 + j].begin = beg;
-        cols[1 + j].len = stop - beg > 0 ? stop - beg : 0;
+        v.begin = beg;
+        v.len = stop - beg > 0 ? stop - beg : 0;
+        cols[1 + j] = v;
     }
 }
 
@@ -585,7 +599,7 @@ KM_HD void emit_rows(const Ctx& ctx, const TableView& T, const WalkView& W, cons
     for (int i = tid; i < d.N; i += ctx.nt()) S.occ[i] = 0;     // held nxtF during the tree phase; the solvers need zeros
     // ---- per-path diffs against the whole reference: one warp per path ---------
     for (int p = wid; p < n_paths; p += nw) {
-        const PathView alt = {R.pool + R.path_off[first_path + p], 0, R.path_len[first_path + p]};
+        const PathView alt = path_view(S, R, first_path, p);
         const Diff df = diff_paths(wctx, ref, alt, k, wslot);
         if (lane == 0) {
             S.pdiff[4 * p + 0] = df.start; S.pdiff[4 * p + 1] = df.end_ref;
@@ -626,7 +640,7 @@ KM_HD void emit_rows(const Ctx& ctx, const TableView& T, const WalkView& W, cons
             }
             // a lone path equal to the reference forms no cluster (:703-707): the path IS the
             // reference exactly when the common prefix covers both completely
-            if (size == 1 && R.path_len[first_path + seed] == d.L && S.pdiff[4 * seed] == d.L) { S.grp[seed] = -1; continue; }
+            if (size == 1 && S.ce_len[seed] == d.L && S.pdiff[4 * seed] == d.L) { S.grp[seed] = -1; continue; }
             crec[4 * cid + 0] = lo; crec[4 * cid + 1] = hi; crec[4 * cid + 2] = size; crec[4 * cid + 3] = first_row + n_rows;
             ++n_clusters;
             n_rows += size;
@@ -644,7 +658,7 @@ KM_HD void emit_rows(const Ctx& ctx, const TableView& T, const WalkView& W, cons
     for (int j = wid; j < n_paths + n_clusters; j += nw) {
         if (j < n_paths) {
             const int p = j;
-            const PathView alt = {R.pool + R.path_off[first_path + p], 0, R.path_len[first_path + p]};
+            const PathView alt = path_view(S, R, first_path, p);
             const Quant2 q = quant_pair(wctx, S, counts, d.N, alt, ref, true, wid, allow_jump);
             if (lane == 0) {
                 const Diff df = {S.pdiff[4 * p], S.pdiff[4 * p + 1], S.pdiff[4 * p + 2], S.pdiff[4 * p + 3]};
@@ -672,11 +686,12 @@ KM_HD void emit_rows(const Ctx& ctx, const TableView& T, const WalkView& W, cons
             const int off0 = lo - span > 0 ? lo - span : 0;                  // (:713)
             const int ref_stop = hi < d.L ? hi : d.L;
             const PathView ref_clip = {nullptr, off0, ref_stop - off0 > 0 ? ref_stop - off0 : 0};
-            const int plen = R.path_len[first_path + p];
+            PathView clip = path_view(S, R, first_path, p);
+            const int plen = clip.len;
             int stop = S.pdiff[4 * p + 2] + hi - S.pdiff[4 * p + 1];         // (:719)
             stop = stop < plen ? stop : plen;
             const int beg = off0 < plen ? off0 : plen;
-            const PathView clip = {R.pool + R.path_off[first_path + p], beg, stop - beg > 0 ? stop - beg : 0};
+            clip.begin = beg; clip.len = stop - beg > 0 ? stop - beg : 0;
             const Quant2 q = quant_pair(wctx, S, counts, d.N, clip, ref_clip, false, wid, allow_jump);
             const Diff df = diff_paths(wctx, ref_clip, clip, k, wslot);
             if (lane == 0)

@@ -30,7 +30,19 @@ struct alignas(32) Bucket {
     uint32_t count[KM_BUCKET_SLOTS];
     uint32_t pad[2];          // the 64-bit hop word (see above), low half first
 };
-#define KM_HOP_FAR 0x8000000000000000ull
+// The hop word, refined: bits 0..46 hop distances 1..47, bit 47 "further away", and -- new -- bits 48..55 / 56..63 the
+// NEIGHBOUR MASK of the key in slot 0 / slot 1: bit c (0..3) = "the k-mer key[1:] + c is in the table", bit 4 + c =
+// "c + key[:-1] is in the table" (letters A C G T, on the strand the canonical key is written in).  MutationFinder asks
+// for a k-mer's count and at once for its four successors (Jellyfish.get_child, Jellyfish.py:61-66), and three of those
+// four are absent on every reference k-mer outside a variant: with the mask riding along with the k-mer's own record,
+// "absent" is known without touching memory -- the reference-probe kernel reads ~1 line per reference k-mer instead of
+// ~4 (every random 32-byte read costs a 128-byte DRAM line; that traffic was 4.6x the algorithmic bytes).  The masks are
+// written by km_table_link_kernel after the table's content has changed (TableView::linked says they are current);
+// a set bit is always verified by the lookup it allows, a clear bit IS the answer "count 0".
+#define KM_HOP_DIST 47
+#define KM_HOP_FAR (1ull << 47)
+#define KM_HOP_MASK ((1ull << 48) - 1ull)
+#define KM_LINK_SHIFT(slot) (48 + 8 * (slot))
 
 #define KM_MAX_SHARDS 8
 
@@ -48,6 +60,7 @@ struct TableView {
     int my_shard;
     const Bucket* shard[KM_MAX_SHARDS];   // shard[my_shard] == buckets; others null until peers are attached
     int lines;                // 0: sector buckets (above); 1: family lines (below), n_buckets counts 128-byte lines
+    int linked;               // 1: the neighbour masks in the hop words are current (km_table_link); sector layout, one shard
     int route;                // cohort: 1 = an insert goes to the key's OWNER shard, wherever it is (peer atomics over NVLink:
                               // every rank gives its own part of the stream); 0 = only owned keys are kept (every rank
                               // streams everything)
@@ -94,8 +107,9 @@ KM_HD uint32_t finish_lookup(const Bucket* base, uint64_t n_buckets, uint64_t b,
                              uint32_t c0, uint32_t c1, uint64_t hop) {
     if (k0 == key) return c0;
     if (k1 == key) return c1;
-    if (hop & KM_HOP_FAR) {                      // a key of this home sits 64+ buckets away: linear scan from there
-        uint64_t bb = (b + 64) % n_buckets;
+    hop &= KM_HOP_MASK;                          // (the top 16 bits are the slots' neighbour masks)
+    if (hop & KM_HOP_FAR) {                      // a key of this home sits 48+ buckets away: linear scan from there
+        uint64_t bb = (b + KM_HOP_DIST + 1) % n_buckets;
         for (uint64_t tries = 0; tries < n_buckets; ++tries) {
             uint64_t f0, f1; uint32_t d0, d1;
             load_bucket(base + bb, f0, f1, d0, d1);
@@ -313,6 +327,57 @@ KM_HD uint32_t table_lookup_key(const TableView& t, uint64_t key) {
     return finish_lookup(base, t.n_buckets, b, key, k0, k1, c0, c1, hop);
 }
 
+// The same, also telling WHERE the key was found: *at = its bucket, *slot = its slot; false when absent.
+KM_HD bool table_find_key(const TableView& t, uint64_t key, const Bucket** at, int* slot, uint32_t* count, uint64_t* word) {
+    uint64_t b;
+    const Bucket* base = locate(t, key, &b);
+    uint64_t k0, k1, hop; uint32_t c0, c1;
+    load_bucket(base + b, k0, k1, c0, c1, hop);
+    if (k0 == key) { *at = base + b; *slot = 0; *count = c0; *word = hop; return true; }
+    if (k1 == key) { *at = base + b; *slot = 1; *count = c1; *word = hop; return true; }
+    uint64_t h = hop & KM_HOP_MASK;
+    if (h & KM_HOP_FAR) {
+        uint64_t bb = (b + KM_HOP_DIST + 1) % t.n_buckets;
+        for (uint64_t tries = 0; tries < t.n_buckets; ++tries) {
+            uint64_t f0, f1, w; uint32_t d0, d1;
+            load_bucket(base + bb, f0, f1, d0, d1, w);
+            if (f0 == key) { *at = base + bb; *slot = 0; *count = d0; *word = w; return true; }
+            if (f1 == key) { *at = base + bb; *slot = 1; *count = d1; *word = w; return true; }
+            if (f0 == KM_EMPTY_KEY || f1 == KM_EMPTY_KEY) break;
+            if (++bb == t.n_buckets) bb = 0;
+        }
+        h &= ~KM_HOP_FAR;
+    }
+    while (h) {
+        const int d = ffs64(h) - 1;
+        h &= h - 1;
+        uint64_t bb = b + 1 + (uint64_t)d;
+        if (bb >= t.n_buckets) bb -= t.n_buckets;
+        uint64_t f0, f1, w; uint32_t d0, d1;
+        load_bucket(base + bb, f0, f1, d0, d1, w);
+        if (f0 == key) { *at = base + bb; *slot = 0; *count = d0; *word = w; return true; }
+        if (f1 == key) { *at = base + bb; *slot = 1; *count = d1; *word = w; return true; }
+    }
+    return false;
+}
+
+KM_HD uint32_t rev_nibble(uint32_t x) { return ((x & 1u) << 3) | ((x & 2u) << 1) | ((x & 4u) >> 1) | ((x & 8u) >> 3); }
+
+// Jellyfish.query of a forward-strand k-mer PLUS which of its four successors fwd[1:] + c exist (bit c of *succ), from the
+// neighbour mask stored with the key (valid only while TableView::linked).  Returns false when the k-mer itself is
+// absent: then nothing is known about its successors (*succ = 15: ask for all of them).
+KM_HD bool table_query_links(const TableView& t, uint64_t fwd, uint32_t* count, uint32_t* succ) {
+    const uint64_t v = fwd & t.kmask;
+    const uint64_t rc = revcomp(v, t.k);
+    const bool flip = t.canonical && rc < v;
+    const Bucket* at; int slot; uint64_t word;
+    if (!table_find_key(t, flip ? rc : v, &at, &slot, count, &word)) { *count = 0; *succ = 15u; return false; }
+    const uint32_t m = (uint32_t)(word >> KM_LINK_SHIFT(slot)) & 0xFFu;
+    // on the other strand the successors of the query are the predecessors of the stored key, letters complemented
+    *succ = flip ? rev_nibble(m >> 4) : (m & 15u);
+    return true;
+}
+
 // forward-strand packed k-mer -> count: Jellyfish.query (km/utils/Jellyfish.py:47-53)
 KM_HD uint32_t table_query(const TableView& t, uint64_t fwd) {
     uint64_t v = fwd & t.kmask;
@@ -461,7 +526,7 @@ KM_HD int bucket_insert(Bucket* base, uint64_t n_buckets, uint64_t home, uint64_
                 // the same bit, so whoever finishes last leaves it set)
                 if (tries) {
                     uint64_t* hop = reinterpret_cast<uint64_t*>(base[home].pad);
-                    const uint64_t bit = tries <= 63 ? 1ull << (tries - 1) : KM_HOP_FAR;
+                    const uint64_t bit = tries <= KM_HOP_DIST ? 1ull << (tries - 1) : KM_HOP_FAR;
                     if (sys) atomic_or64_sys(hop, bit); else atomic_or64(hop, bit);
                 }
                 return placed;

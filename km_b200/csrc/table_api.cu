@@ -311,6 +311,7 @@ extern "C" int km_table_get_info(km_table* t, km_table_info* info) {
 }
 
 static int finish_insert(km_table* t, const char* what) {
+    t->linked = false;                     // the content changed: the neighbour masks are stale until km_table_link
     unsigned long long host[2] = {0, 0};
     CU(cudaMemcpyAsync(host, t->d_counter, 16, cudaMemcpyDeviceToHost, t->stream));
     CU(cudaStreamSynchronize(t->stream));
@@ -467,6 +468,26 @@ extern "C" int km_table_set_routing(km_table* t, int on) {
     }
     t->route = on ? 1 : 0;
     return 0;
+}
+
+// The neighbour masks (table.h): which successors / predecessors of every stored k-mer are in the table too.  The
+// find_mutation kernels use them to skip the lookups of absent successors; they are rebuilt here, on demand, after any
+// change of the table's content (one shard, sector layout only -- a shard of a cohort table answers without them).
+extern "C" int km_table_link(km_table* t) {
+    if (!t) return fail(KM_E_ARG, "null table");
+    if (t->lines || t->n_shards > 1) { t->linked = false; return 0; }
+    if (t->linked) return 0;
+    CU(cudaSetDevice(t->device));
+    km_table_link_kernel<<<t->sm_count * 8, 256, 0, t->stream>>>(t->view());
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(t->stream));
+    t->linked = true;
+    return 0;
+}
+int km_ensure_linked(km_table* t) {
+    const char* e = getenv("KM_NO_LINKS");            // A/B switch: every successor is looked up, as before
+    if (e && *e && *e != '0') { t->linked = false; return 0; }
+    return km_table_link(t);
 }
 
 extern "C" int km_table_recount(km_table* t, uint64_t* n_keys) {
@@ -653,6 +674,41 @@ extern "C" int km_bench_random_gather(int device, uint64_t bytes, uint64_t n_loa
     cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(buf); cudaFree(sink);
     *best_ms = best;
     return 0;
+}
+
+// device-resident counting benchmark: n_reads reads of read_len bases drawn from a pseudo-random genome of `genome` bases
+// (coverage = n_reads * read_len / genome) are generated on the device, then counted `iters` times into the table
+// (km_count_text_kernel alone, CUDA events); the table is left holding the counts of all passes
+extern "C" int km_bench_count(km_table* t, uint64_t n_reads, int read_len, uint64_t genome, uint64_t seed, int iters, float* best_ms,
+                              uint64_t* n_kmers) {
+    if (!t || !n_reads || read_len < t->k || genome <= (uint64_t)read_len || iters < 1 || !best_ms) return fail(KM_E_ARG, "km_bench_count: bad argument");
+    if (t->lines) return fail(KM_E_ARG, "km_bench_count: sector-bucket layout only");
+    CU(cudaSetDevice(t->device));
+    const uint64_t n_bytes = n_reads * (uint64_t)(read_len + 1);
+    uint8_t* text = nullptr;
+    CU(cudaMalloc((void**)&text, n_bytes + 256));
+    cudaStream_t s = t->stream;
+    km_make_reads_kernel<<<t->sm_count * 8, 256, 0, s>>>(text, n_reads, read_len, genome, seed);
+    CU(cudaGetLastError());
+    CU(cudaMemsetAsync(t->d_counter, 0, 16, s));
+    const uint64_t n_tiles = (n_bytes + KM_COUNT_TILE - 1) / KM_COUNT_TILE;
+    const int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)t->sm_count * 8);
+    float best = 1e30f;
+    for (int it = 0; it < iters + 1; ++it) {                    // the first pass creates the keys, the timed ones add to them
+        CU(cudaEventRecord(t->ev[0], s));
+        km_count_text_kernel<<<grid, KM_COUNT_CTA, 0, s>>>(t->view(), (const uint32_t*)text, nullptr, 0, n_bytes, t->d_counter,
+                                                          reinterpret_cast<uint32_t*>(t->d_counter + 1));
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(t->ev[1], s));
+        CU(cudaEventSynchronize(t->ev[1]));
+        float ms; CU(cudaEventElapsedTime(&ms, t->ev[0], t->ev[1]));
+        if (it == 0 && best_ms) best_ms[1] = ms;                // [1] = the pass that inserts new keys
+        if (it > 0) best = std::min(best, ms);
+    }
+    cudaFree(text);
+    best_ms[0] = best;
+    if (n_kmers) *n_kmers = n_reads * (uint64_t)(read_len - t->k + 1);
+    return finish_insert(t, "km_bench_count");
 }
 
 // the config-4 lookup mix (50 % background keys on a random strand / 50 % random k-mers) into a caller's device buffer

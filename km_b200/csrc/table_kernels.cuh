@@ -112,6 +112,63 @@ __global__ void __launch_bounds__(KM_COUNT_CTA) km_count_text_kernel(TableView T
     if (warp_leader() && mine) atomicAdd(n_new, mine);
 }
 
+// The neighbour masks (table.h): one thread per bucket asks the table for the 4 successors and 4 predecessors of each
+// of its keys -- 8 independent probes in flight per key -- and stores the two masks into the top 16 bits of the bucket's
+// hop word.  Runs when nothing else writes the table; the low 48 bits (hop distances) are left as they are.
+__global__ void __launch_bounds__(256) km_table_link_kernel(TableView T) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < T.n_buckets; i += stride) {
+        Bucket* bk = T.buckets + i;
+        uint64_t k0, k1, word; uint32_t c0, c1;
+        load_bucket(bk, k0, k1, c0, c1, word);
+        uint64_t masks = 0;
+#pragma unroll
+        for (int s = 0; s < KM_BUCKET_SLOTS; ++s) {
+            const uint64_t key = s ? k1 : k0;
+            if (key == KM_EMPTY_KEY) continue;
+            uint64_t nb[8], b[8], f0[8], f1[8], hop[8];
+            uint32_t d0, d1;
+            const Bucket* base[8];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const uint64_t su = succ_kmer(key, c, T.kmask), pr = pred_kmer(key, c, T.k);
+                nb[c] = T.canonical ? canonical(su, T.k) : su;
+                nb[4 + c] = T.canonical ? canonical(pr, T.k) : pr;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { base[j] = locate(T, nb[j], &b[j]); load_bucket(base[j] + b[j], f0[j], f1[j], d0, d1, hop[j]); }
+            uint32_t m = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                bool found = f0[j] == nb[j] || f1[j] == nb[j];
+                if (!found && (hop[j] & KM_HOP_MASK)) {             // displaced: follow the hop word (rare)
+                    const Bucket* at; int slot; uint32_t cnt; uint64_t w;
+                    found = table_find_key(T, nb[j], &at, &slot, &cnt, &w);
+                }
+                m |= found ? (1u << j) : 0u;
+            }
+            masks |= (uint64_t)m << KM_LINK_SHIFT(s);
+        }
+        const uint64_t fresh = (word & KM_HOP_MASK) | masks;
+        if (fresh != word) *reinterpret_cast<uint64_t*>(bk->pad) = fresh;
+    }
+}
+
+// measurement: reads of `read_len` bases sampled from a pseudo-random "genome" of `genome` bases (base i = two bits of a
+// hash of i), one newline after each -- a device-resident byte stream for timing km_count_text_kernel on its own
+__global__ void km_make_reads_kernel(uint8_t* text, uint64_t n_reads, int read_len, uint64_t genome, uint64_t seed) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t total = n_reads * (uint64_t)(read_len + 1);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const uint64_t r = i / (uint64_t)(read_len + 1);
+        const int j = (int)(i - r * (uint64_t)(read_len + 1));
+        if (j == read_len) { text[i] = '\n'; continue; }
+        const uint64_t start = mulhi64(mix64(seed + (r + 1) * KM_GOLDEN), genome - (uint64_t)read_len);
+        const uint64_t g = start + (uint64_t)j;
+        text[i] = "ACGT"[(mix64(g / 32 + 0x5DEECE66Dull * seed) >> (2 * (g & 31))) & 3ull];
+    }
+}
+
 // every record of the table counted again (after routed inserts the creators of a key sit on other GPUs)
 __global__ void km_table_recount_kernel(TableView T, unsigned long long* n_keys) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;

@@ -332,6 +332,7 @@ extern "C" int km_find_text(km_table* t, const char* seqs, const int64_t* offset
         *out = res;
         return 0;
     }
+    if (int rc = km_ensure_linked(t)) return rc;
     Trace tr;
     if (n_sub <= 0) n_sub = n >= 4096 ? 6 : n >= 1024 ? 2 : 1;
     n_sub = std::max(1, std::min(n_sub, std::max(1, n)));

@@ -115,7 +115,21 @@ KM_HD void ref_probe_chunk(const Ctx& ctx, const TableView& T, const WalkView& W
             if (c != ref_c || lane == nl - 1) mask |= 2u << c;
         }
     }
-    table_query_family_warp<5>(T, family_of_suffix(T, q[0]), q, mask, r);
+    uint32_t n_issued = (uint32_t)popc32(mask);
+    if (T.linked) {
+        // the k-mer's own record says which of its successors exist at all (neighbour mask, table.h): an absent one is
+        // count 0 without a read, so a reference k-mer costs ~1 table read instead of ~4
+        uint32_t own = 0, succ = 15u;
+        if (active) table_query_links(T, q[0], &own, &succ);
+        const uint32_t need = (mask >> 1) & succ;
+        const uint64_t ck[4] = {q[1], q[2], q[3], q[4]};
+        uint32_t cr[4];
+        table_query_masked<4>(T, ck, need, cr);
+        r[0] = own; r[1] = cr[0]; r[2] = cr[1]; r[3] = cr[2]; r[4] = cr[3];
+        n_issued = active ? 1u + (uint32_t)popc32(need) : 0u;
+    } else {
+        table_query_family_warp<5>(T, family_of_suffix(T, q[0]), q, mask, r);
+    }
     const uint32_t next_own = (uint32_t)warp_shfl_down32((int)r[0], 1);
     if (active) {
         if (lane != nl - 1) {
@@ -146,7 +160,7 @@ KM_HD void ref_probe_chunk(const Ctx& ctx, const TableView& T, const WalkView& W
             }
         }
     }
-    unsigned long long n = (unsigned long long)popc32(mask);
+    unsigned long long n = (unsigned long long)n_issued;
     n = warp_sum64(n);
     if (lane == 0 && n) atomic_add64(&W.lookups[t], n);
 }

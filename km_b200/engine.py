@@ -145,6 +145,10 @@ class Table:
             qp = qbuf.ctypes.data
         check(lib().km_table_count_text(self._h, buf.ctypes.data, qp, buf.size, q))
 
+    def link(self):
+        """Write the neighbour masks now (km_table_link) instead of at the next find call."""
+        check(lib().km_table_link(self._h))
+
     def recount(self):
         """Number of records in this table (this shard), counted on the device."""
         n = ctypes.c_uint64()

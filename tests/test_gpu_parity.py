@@ -157,8 +157,9 @@ def test_panel_against_oracle_with_full_background(engine):
                                 [[float(r.rvaf), float(r.expr), float(r.ref_expr)] for r in want], got["raw"])
         assert not errs, (panel.names[i], errs)
         assert got["nodes"] == sorted([k, int(v)] for k, v in f.node_data.items())
-        # the reference-probe kernel reuses a neighbour's count for the successor along the reference
-        assert int(res.lookups[i]) >= ko.algorithmic_lookups(f) - (len(panel.targets[i]) - 31)
+        # table reads actually issued: at least one per reference k-mer; the neighbour masks (km_table_link) answer
+        # "absent" for most successors without a read, so the reference's 5 per k-mer is an upper bound only
+        assert int(res.lookups[i]) >= len(panel.targets[i]) - 30
         flips += fl
     assert flips <= 4
 
@@ -354,7 +355,7 @@ def test_full_size_panel_properties(engine):
     res = t.find_batch(engine.PackedTargets(panel.targets[:2000]), want_graph=False)
     n_ref = np.array([len(s) - 30 for s in panel.targets[:2000]])
     algorithmic = n_ref + 4 * (res.n_nodes.astype(np.int64) - 2)
-    assert (res.lookups.astype(np.int64) >= algorithmic - (n_ref - 1)).all()
+    assert (res.lookups.astype(np.int64) >= n_ref).all()          # (the neighbour masks answer most absent successors without a read)
     # (a chain level asks for the sixteen grandchildren along with the four children: up to 20 per novel node)
     n_novel = res.n_nodes.astype(np.int64) - 2 - n_ref
     assert (res.lookups.astype(np.int64) <= algorithmic + 16 * n_novel + 4 * 64).all()

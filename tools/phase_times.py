@@ -4,10 +4,11 @@ import ctypes
 import os
 import sys
 
-os.environ["KM_PHASE_TIMERS"] = "1"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from km_b200 import build as kb     # noqa: E402
-kb.build(force=True)
+if not os.environ.get("KM_B200_LIB"):      # else: a variant built with -DKM_PHASE_TIMERS (tools/build_variant.py)
+    os.environ["KM_PHASE_TIMERS"] = "1"
+    from km_b200 import build as kb     # noqa: E402
+    kb.build(force=True)
 from km_b200 import engine, synth   # noqa: E402
 from km_b200._lib import lib        # noqa: E402
 
