@@ -273,6 +273,8 @@ int km_debug_nat_cmp(const char* a, const char* b);
 /* ---- measurement helpers (bench.py) --------------------------------------------------- */
 /* per-phase SM cycles of the graph pass (only in a -DKM_PHASE_TIMERS build; tools/phase_times.py) */
 int km_debug_phase_cycles(unsigned long long* out64, int reset);
+/* the same for the walk kernels (their counters live in their own translation unit) */
+int km_debug_walk_cycles(unsigned long long* out64, int reset);
 /* graph-pass SM cycles of targets 0..n-1 in the last launch (KM_PHASE_TIMERS builds only) */
 int km_debug_target_cycles(unsigned int* out, int n);   /* 64 counters */
 /* random 32-byte-sector gather over `bytes` of HBM: the ceiling for hash probes */

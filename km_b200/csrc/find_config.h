@@ -22,6 +22,9 @@ namespace km {
 #ifndef KM_PROBE_MINB
 #define KM_PROBE_MINB 5
 #endif
+#ifndef KM_PROBE_MINB_LINKED
+#define KM_PROBE_MINB_LINKED 10
+#endif
 #ifndef KM_SMALL_NODES
 #define KM_SMALL_NODES 512      // largest shared-memory class (graph nodes incl. the two caps)
 #endif

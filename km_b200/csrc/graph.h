@@ -23,7 +23,9 @@ namespace km {
 #define KM_MAX_PATHS 1024       // unique alternative paths per target
 #define KM_MAX_COLS 64          // columns of one least-squares problem (1 + cluster size)
 #ifndef KM_PCACHE
-#define KM_PCACHE 2048          // 16-bit node numbers of a target's paths kept in shared memory (shared-memory passes)
+#define KM_PCACHE 0             // 16-bit node numbers of a target's paths kept in shared memory (shared-memory passes);
+                                // measured: 2048 saves 8 % of the pass's cycles per target but costs co-residency of the two
+                                // classes' CTAs -- 0.717 ms against 0.695 without (profiles/r2g_variants.txt) -- so it is off
 #endif
 #define KM_ST_RETRY_LARGE 0x40000000u   // internal: redo this target in the general pass
 

@@ -141,7 +141,14 @@ struct km_table {
     // stream and events, kept across calls
     // (the host vectors of a lane's last plan are kept too: their capacity saves the next plan its allocations)
     struct PlanVecs { std::vector<int64_t> seq_off, node_off, hash_off, pack_off; std::vector<int32_t> chunk_target, chunk_start, extra; };
-    struct Lane { Arena dev, pin; cudaStream_t stream = nullptr, side = nullptr; cudaEvent_t ev[8] = {}, fork = nullptr, join = nullptr; PlanVecs vecs; };
+    struct Lane {
+        Arena dev, pin; cudaStream_t stream = nullptr, side = nullptr; cudaEvent_t ev[8] = {}, fork = nullptr, join = nullptr; PlanVecs vecs;
+        // the enqueue of a sub-batch as ONE driver call: when two consecutive calls give this lane a sub-batch of the very
+        // same layout (a fixed panel of targets against sample after sample is km's workflow), the sequence copy +
+        // ~16 kernels is captured into a CUDA graph and replayed from then on (text_api.cu)
+        cudaGraphExec_t gexec = nullptr;
+        std::string gkey, last_key;
+    };
     std::vector<std::unique_ptr<Lane>> lanes;
     std::shared_ptr<PinPool> pool = std::make_shared<PinPool>();   // result buffers (outlive the table if a result does)
     int sm_count = 148;
@@ -160,7 +167,7 @@ struct km_table {
     CUmemGenericAllocationHandle vmm_handle = 0, peer_handle[KM_MAX_SHARDS] = {};
     size_t vmm_size = 0;
     TableView view() const {
-        TableView v;
+        TableView v{};
         v.buckets = buckets; v.n_buckets = n_buckets; v.kmask = (1ull << (2 * k)) - 1ull; v.k = k; v.canonical = canonical;
         v.n_shards = n_shards; v.my_shard = my_shard; v.lines = lines; v.route = route;
         v.linked = (linked && n_shards == 1 && !lines) ? 1 : 0;

@@ -143,3 +143,6 @@ void plan_swap_vecs(km_plan* p, km_table::PlanVecs& v);
 int plan_init(km_table* t, const char* seqs, const int64_t* offsets, int32_t n, const km_find_params* params, km_plan* p,
               bool borrow_arena, km_table::Lane* lane = nullptr);
 int plan_fetch(km_plan* p, km_result* res, bool want_graph, bool head_only = false);
+// everything the enqueue of a staged plan depends on (pointers, sizes, grids, parameters), as bytes: two plans with equal
+// keys enqueue identical work, whatever the letters of their targets
+std::string plan_graph_key(const km_plan* p);

@@ -319,6 +319,19 @@ int plan_init(km_table* t, const char* seqs, const int64_t* offsets, int32_t n, 
     return rc_up;
 }
 
+std::string plan_graph_key(const km_plan* p) {
+    std::string k;
+    auto add = [&](const void* ptr, size_t n) { k.append((const char*)ptr, n); };
+    const TableView T = p->t->view();
+    add(&T, sizeof(T)); add(&p->W, sizeof(p->W)); add(&p->R, sizeof(p->R)); add(&p->F, sizeof(p->F)); add(&p->P, sizeof(p->P));
+    add(&p->SL, sizeof(p->SL));
+    const int64_t misc[] = {p->n, p->grid_tiny, p->grid_graph, p->grid_large, (int64_t)p->state_bytes, (int64_t)p->upload_bytes,
+                            (int64_t)(intptr_t)p->state0, (int64_t)(intptr_t)p->h_stage, (int64_t)(intptr_t)p->stream,
+                            (int64_t)(intptr_t)p->side, p->fmt ? 1 : 0};
+    add(misc, sizeof(misc));
+    return k;
+}
+
 // fetch with the capacity-retry loop: targets whose exploration overflowed get 8x the node
 // capacity, exhausted pools grow 4x, and the batch is re-run
 int plan_fetch(km_plan* p, km_result* res, bool want_graph, bool head_only) {

@@ -293,6 +293,7 @@ extern "C" void km_table_close(km_table* t) {
         if (L->side) cudaStreamDestroy(L->side);
         if (L->fork) cudaEventDestroy(L->fork);
         if (L->join) cudaEventDestroy(L->join);
+        if (L->gexec) cudaGraphExecDestroy(L->gexec);
     }
     for (auto& ev : t->ev) if (ev) cudaEventDestroy(ev);
     if (t->stream) cudaStreamDestroy(t->stream);

@@ -406,7 +406,10 @@ extern "C" int km_find_text(km_table* t, const char* seqs, const int64_t* offset
                 km_plan* p = plans[(size_t)c].get();
                 p->fmt = true; p->fmt_names = names + name_off[lo]; p->fmt_name_off = no.data(); p->fmt_db = db;
                 p->targets_ext = seqs + offsets[lo];
-                const int lane_ix = next_lane.fetch_add(1);
+                // sub-batch c always runs on lane c: the same streams (earlier sub-batches more urgent), the same arenas --
+                // and therefore, for a batch of the same layout, the same enqueue, which is what makes the graph replay below
+                const int lane_ix = c;
+                (void)next_lane;
                 g_trace_obj = &tr; g_trace_sub = c;
                 g_trace_mark = tr.on ? +[](void* o, const char* w, int sub) { static_cast<Trace*>(o)->mark(w, sub); } : nullptr;
                 tr.mark("task start", c);
@@ -414,11 +417,37 @@ extern "C" int km_find_text(km_table* t, const char* seqs, const int64_t* offset
                 if (int rc = plan_init(t, seqs + offsets[lo], o.data(), hi - lo, &prm, p, false, t->lanes[(size_t)lane_ix].get())) return fail_all(rc);
                 tr.mark("plan_init", c);
                 {
-                    // ~17 driver calls per sub-batch, ~6 us each whether one thread issues them or six do at once
-                    // (measured both ways: taking turns under a mutex put the last sub-batch on the GPU at 0.71 ms
-                    // instead of 0.54 and gained nothing for the first)
-                    int rc = plan_upload_enqueue(p, p->stream);
-                    if (!rc) rc = plan_launch(p, p->stream);
+                    // Enqueued directly this is ~17 driver calls per sub-batch, ~6 us each whether one thread issues them or
+                    // six do at once.  When the lane saw the very same layout in the previous call, the sequence is captured
+                    // into a CUDA graph (once) and from then on replayed with ONE call.
+                    km_table::Lane* lane = t->lanes[(size_t)lane_ix].get();
+                    static const bool use_graph = !getenv("KM_NO_GRAPH");
+                    const std::string key = use_graph ? plan_graph_key(p) : std::string();
+                    int rc = 0;
+                    bool done = false;
+                    if (use_graph && lane->gexec && lane->gkey == key) {
+                        if (cudaGraphLaunch(lane->gexec, p->stream) == cudaSuccess) { done = true; p->launched = true; p->n_launches += 10; tr.mark("graph replay", c); }
+                        else { cudaGetLastError(); cudaGraphExecDestroy(lane->gexec); lane->gexec = nullptr; }
+                    } else if (use_graph && lane->last_key == key) {
+                        if (lane->gexec) { cudaGraphExecDestroy(lane->gexec); lane->gexec = nullptr; }
+                        cudaGraph_t graph = nullptr;
+                        if (cudaStreamBeginCapture(p->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                            rc = plan_upload_enqueue(p, p->stream);
+                            if (!rc) rc = plan_launch(p, p->stream);
+                            const cudaError_t ce = cudaStreamEndCapture(p->stream, &graph);
+                            if (!rc && ce == cudaSuccess && graph && cudaGraphInstantiate(&lane->gexec, graph, 0) == cudaSuccess) {
+                                lane->gkey = key;
+                                if (cudaGraphLaunch(lane->gexec, p->stream) == cudaSuccess) { done = true; tr.mark("graph captured", c); }
+                            }
+                            if (graph) cudaGraphDestroy(graph);
+                            if (!done) { cudaGetLastError(); if (lane->gexec) { cudaGraphExecDestroy(lane->gexec); lane->gexec = nullptr; } rc = 0; p->launched = false; }
+                        } else cudaGetLastError();
+                    }
+                    if (use_graph) lane->last_key = key;
+                    if (!done) {
+                        rc = plan_upload_enqueue(p, p->stream);
+                        if (!rc) rc = plan_launch(p, p->stream);
+                    }
                     if (rc) return fail_all(rc);
                 }
                 p->defer_upload = false;

@@ -43,11 +43,14 @@ __global__ void km_encode_kernel(uint8_t* seq, const int64_t* seq_off, uint32_t*
 // Two launches: the shared-memory walk takes every target of ordinary size (walk_small.h); the
 // general walk, whose per-target state lives in HBM, takes the targets the first one deferred.
 // K3a: level 0 of every walk, one warp per 32 reference k-mers, flat over the batch
-__global__ void __launch_bounds__(32 * KM_PROBE_WARPS, KM_PROBE_MINB) km_ref_probe_kernel(TableView T, WalkView W, FindParams P) {
+// (two instances: with the neighbour masks a lane makes ONE table read and almost never a second, so that instance is
+// compiled for twice the warps per SM; without them five reads are in flight per lane and registers buy more than warps)
+template <bool LINKED>
+__global__ void __launch_bounds__(32 * KM_PROBE_WARPS, LINKED ? KM_PROBE_MINB_LINKED : KM_PROBE_MINB) km_ref_probe_kernel(TableView T, WalkView W, FindParams P) {
     WarpCtx ctx;
     const int ch = (int)blockIdx.x * KM_PROBE_WARPS + (int)(threadIdx.x >> 5);
     if (ch >= W.n_chunks) return;
-    ref_probe_chunk(ctx, T, W, P, W.chunk_target[ch], W.chunk_start[ch]);
+    ref_probe_chunk<WarpCtx, LINKED>(ctx, T, W, P, W.chunk_target[ch], W.chunk_start[ch]);
 }
 
 __global__ void __launch_bounds__(32 * KM_WALK_WARPS, KM_WALK_MINB) km_walk_small_kernel(TableView T, WalkView W, FindParams P) {
@@ -83,7 +86,9 @@ cudaError_t km_launch_encode(const WalkView& W, cudaStream_t s) {
     return cudaGetLastError();
 }
 cudaError_t km_launch_ref_probe(const TableView& T, const WalkView& W, const FindParams& P, cudaStream_t s) {
-    if (W.n_chunks) km_ref_probe_kernel<<<(W.n_chunks + KM_PROBE_WARPS - 1) / KM_PROBE_WARPS, 32 * KM_PROBE_WARPS, 0, s>>>(T, W, P);
+    const int grid = (W.n_chunks + KM_PROBE_WARPS - 1) / KM_PROBE_WARPS;
+    if (W.n_chunks && T.linked) km_ref_probe_kernel<true><<<grid, 32 * KM_PROBE_WARPS, 0, s>>>(T, W, P);
+    else if (W.n_chunks) km_ref_probe_kernel<false><<<grid, 32 * KM_PROBE_WARPS, 0, s>>>(T, W, P);
     return cudaGetLastError();
 }
 cudaError_t km_launch_walks(const TableView& T, const WalkView& W, const FindParams& P, cudaStream_t s) {
@@ -93,4 +98,16 @@ cudaError_t km_launch_walks(const TableView& T, const WalkView& W, const FindPar
     if (e != cudaSuccess) return e;
     km_walk_kernel<<<(n + KM_WALK_WARPS - 1) / KM_WALK_WARPS, 32 * KM_WALK_WARPS, 0, s>>>(T, W, P);
     return cudaGetLastError();
+}
+
+// per-phase SM cycles of the walk kernels (KM_PHASE_TIMERS builds only; the counters are per translation unit)
+extern "C" int km_debug_walk_cycles(unsigned long long* out64, int reset) {
+#ifdef KM_PHASE_TIMERS
+    if (out64 && cudaMemcpyFromSymbol(out64, km_phase_cycles, 64 * sizeof(unsigned long long)) != cudaSuccess) return -3;
+    if (reset) { unsigned long long z[64] = {0}; if (cudaMemcpyToSymbol(km_phase_cycles, z, sizeof(z)) != cudaSuccess) return -3; }
+    return 0;
+#else
+    (void)out64; (void)reset;
+    return -1;
+#endif
 }

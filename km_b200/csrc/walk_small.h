@@ -92,7 +92,7 @@ KM_HD int ws_insert(WalkSmall& M, uint64_t key, int idx, int L, int k) {
 // for every reference k-mer with an accepted successor off the reference, one entry of the target's
 // EXIT LIST: node_slot[0 .. n_kept) = position | accepted letters << 16 | branching << 20 (n_kept
 // counts the entries until the walk kernel replaces it with the kept-node count).
-template <class Ctx>
+template <class Ctx, bool LINKED>
 KM_HD void ref_probe_chunk(const Ctx& ctx, const TableView& T, const WalkView& W, const FindParams& P, int t, int i0) {
     const int k = T.k;
     const TargetGeom g = target_geom(W, t, k);
@@ -116,16 +116,16 @@ KM_HD void ref_probe_chunk(const Ctx& ctx, const TableView& T, const WalkView& W
         }
     }
     uint32_t n_issued = (uint32_t)popc32(mask);
-    if (T.linked) {
+    if (LINKED) {
         // the k-mer's own record says which of its successors exist at all (neighbour mask, table.h): an absent one is
         // count 0 without a read, so a reference k-mer costs ~1 table read instead of ~4
         uint32_t own = 0, succ = 15u;
         if (active) table_query_links(T, q[0], &own, &succ);
         const uint32_t need = (mask >> 1) & succ;
-        const uint64_t ck[4] = {q[1], q[2], q[3], q[4]};
-        uint32_t cr[4];
-        table_query_masked<4>(T, ck, need, cr);
-        r[0] = own; r[1] = cr[0]; r[2] = cr[1]; r[3] = cr[2]; r[4] = cr[3];
+        r[0] = own;
+        // (a successor that exists off the reference is rare -- a variant site: no key is even formed for the others)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) r[1 + c] = ((need >> c) & 1u) ? table_query(T, q[1 + c]) : 0u;
         n_issued = active ? 1u + (uint32_t)popc32(need) : 0u;
     } else {
         table_query_family_warp<5>(T, family_of_suffix(T, q[0]), q, mask, r);
@@ -139,7 +139,11 @@ KM_HD void ref_probe_chunk(const Ctx& ctx, const TableView& T, const WalkView& W
         W.node_kmer[g.nbase + i] = q[0];
         W.node_count[g.nbase + i] = r[0];
         uint32_t* cc = W.node_kid + 4 * (g.nbase + i);
+#if KM_DEVICE_BUILD
+        *reinterpret_cast<uint4*>(cc) = make_uint4(r[1], r[2], r[3], r[4]);          // (node_kid is 256-byte aligned, 16 bytes per node)
+#else
         cc[0] = r[1]; cc[1] = r[2]; cc[2] = r[3]; cc[3] = r[4];
+#endif
         // Jellyfish.py:61-72 -- Python int * float, then max with the int floor, then >=
         const uint64_t sum = (uint64_t)r[1] + r[2] + r[3] + r[4];
         double thr = (double)sum * P.ratio;

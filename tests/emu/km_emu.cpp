@@ -109,7 +109,7 @@ int emu_find_target(void* h, const uint8_t* codes, int len, double ratio, int64_
         const TargetGeom g = target_geom(W, 0, k);
         if (walk_small_fits(g)) {
             W.chunk_target = nullptr; W.chunk_start = nullptr; W.n_chunks = 0;
-            for (int i0 = 0; i0 < g.L; i0 += ctx.nt()) ref_probe_chunk(ctx, t->v, W, P, 0, i0);     // km_ref_probe_kernel
+            for (int i0 = 0; i0 < g.L; i0 += ctx.nt()) ref_probe_chunk<CtaCtx, false>(ctx, t->v, W, P, 0, i0);     // km_ref_probe_kernel
             static WalkSmall M;
             memset(&M, 0x5A, sizeof(M));
             walked = walk_small_target(ctx, t->v, W, P, 0, M);

@@ -516,6 +516,30 @@ def test_find_cohort_equals_find_mutation_per_sample(engine, bundled):
             want += rows[1:]
         assert cohort == want
         assert len(cohort) > 5 * 9
+        # every table resident in HBM at once: the same rows
+        resident = run(fc.main_find_cohort, Namespace(target_fn=[catalog], jellyfish_fn=["./data/jf"], device=0, resident=True, **base))
+        assert resident == cohort
+        # -f table: per target, what `km find_report -t <target> -f table` makes of ALL samples' rows (find_report.py:290-327)
+        from km_b200.tools import find_report as fr
+        table = run(fc.main_find_cohort, Namespace(target_fn=[catalog], jellyfish_fn=["./data/jf"], device=0, resident=True,
+                                                   format="table", min_cov=1, **base))
+        npm1 = "NPM1_4ins_exons_10-11utr"
+        at = table.index("## " + npm1)
+        block = []
+        for ln in table[at + 1:]:
+            if ln.startswith("## "):
+                break
+            block.append(ln)
+        rows = [r for r in cohort[1:] if r.split("\t")[1] == npm1]
+        want_tab = run(lambda a, _p: fr.create_report(a),
+                       Namespace(target="./data/catalog/GRCh38/%s.fa" % npm1, infile=io.StringIO("".join(r + "\n" for r in rows)),
+                                 info="vs_ref", min_cov=1, exclu="", format="table"))
+        assert block == want_tab and block[0].startswith("Sample\t") and len(block) == 1 + 5
+        # the NPM1 insertion is seen in the NPM1 sample only
+        cells = {ln.split("\t")[0]: ln.split("\t")[1:] for ln in block[1:]}
+        hdr = block[0].split("\t")[1:]
+        ins_col = [i for i, h in enumerate(hdr) if "171410544" in h]
+        assert ins_col and cells["./data/jf/02H025_NPM1.jf"][ins_col[0]] not in (".", "")
     finally:
         os.chdir(cwd)
 

@@ -19,8 +19,9 @@ def main():
     ncu_name = sys.argv[5] if len(sys.argv) > 5 else kern      # demangled base name for ncu -k
     with tempfile.TemporaryDirectory() as d:
         subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=d, check=True, capture_output=True)
-        cubin = [f for f in os.listdir(d) if f.endswith(".cubin")][0]
-        sass = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(d, cubin)], capture_output=True, text=True).stdout
+        # one cubin per translation unit: disassemble them all (the kernel is in one of them)
+        sass = "".join(subprocess.run(["nvdisasm", "-g", "-c", os.path.join(d, f)], capture_output=True, text=True).stdout
+                       for f in sorted(os.listdir(d)) if f.endswith(".cubin"))
     # offset -> (file, line) for the wanted kernel
     line_of = {}
     inside = False

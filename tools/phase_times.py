@@ -27,10 +27,16 @@ plan.last_ms()
 L = lib()
 L.km_debug_phase_cycles.argtypes = [ctypes.c_void_p, ctypes.c_int]
 buf = (ctypes.c_ulonglong * 64)()
+L.km_debug_walk_cycles.argtypes = [ctypes.c_void_p, ctypes.c_int]
+wbuf = (ctypes.c_ulonglong * 64)()
 L.km_debug_phase_cycles(buf, 1)
+L.km_debug_walk_cycles(wbuf, 1)
 plan.launch()
 w, g = plan.last_ms()
 L.km_debug_phase_cycles(buf, 0)
+L.km_debug_walk_cycles(wbuf, 0)
+for i in range(32, 40):
+    buf[i] = wbuf[i]
 tot = sum(buf[:16])
 print("walk %.3f ms  graph %.3f ms   targets %d   (probe %.3f, walks %.3f, graph %.3f)" % ((w, g, n) + tuple(plan.kernel_ms())))
 WALK = {32: "walk: set-up", 33: "walk: phase 1 (ref k-mers)", 34: "walk: level 0", 35: "walk: later levels", 36: "walk: peel", 37: "walk: results"}

@@ -19,6 +19,17 @@ text = res.format_all("s.jf", names)
 packed = engine.PackedTargets(targets, names)
 text2, status = t.find_text(packed, "s.jf", n_sub=3)
 assert text == text2 and not (status & (0xFFFFFFFF ^ 16)).any()
+text3, _ = t.find_text(packed, "s.jf", n_sub=3)          # the same layout again: captured into a CUDA graph ...
+text4, _ = t.find_text(packed, "s.jf", n_sub=3)          # ... and replayed
+assert text3 == text and text4 == text
 q = synth.lookup_queries(4096, synth.TABLE_SEED, 20000)
 t.query_packed(q)
+# counting from reads (rolling kernel, -Q mask on the device), -L 2, neighbour masks, and the walk over the counted table
+reads = synth.sample_reads(panel, range(12))
+c = engine.Table.create(capacity=1 << 16)
+c.count_text(reads, qual=bytes([60]) * len(reads), min_qual="+")
+c.drop_below(2)
+c.link()
+res2 = c.find_batch(panel.targets[:12])
+assert not (res2.status & (0xFFFFFFFF ^ 16)).any() and int(res2.row_count.sum()) >= 12
 print("ok", len(text), "bytes of rows")
