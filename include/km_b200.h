@@ -233,7 +233,7 @@ typedef struct km_result_view {
     int32_t n_launches;            /* kernels launched for this result */
     int32_t n_retries;
     int32_t has_graph;             /* 0: node_kmer/node_count/path_pool were not copied back */
-    int32_t reserved;
+    int32_t reserved;              /* measurement: targets whose graph was a "simple bubble" (closed-form paths, csrc/graph.h) */
     uint64_t bytes_h2d, bytes_d2h; /* bytes copied host->device / device->host for this result */
 } km_result_view;
 int km_result_get(const km_result* r, km_result_view* view);

@@ -509,6 +509,81 @@ KM_HD bool graph_target(const Ctx& ctx, const TableView& T, const WalkView& W, c
         S.deg[i] = (uint8_t)(od | (id << 4));
     }
     ctx.sync();
+    // ---- SIMPLE BUBBLE (most targets): the reference chain plus ONE chain of novel nodes that leaves it at node a and
+    // rejoins it at node b > a -- a substitution, an insertion, a deletion -- or no novel node at all.  Every non-reference
+    // edge then lies on that one chain, so Graph.all_shortest (Graph.py:220-240) can only stitch two paths: the reference
+    // (from the source cap's edge, which init_paths keeps, Graph.py:184-198) and 0..a + chain + b..L-1; both shortest-path
+    // trees, the chain strip and the candidate edges are known without being computed, provided the trees would follow
+    // the reference wherever there is a choice -- true while the by-passed stretch costs less than the chain
+    // (0.01 per reference edge against 1.0 per other edge; the test below keeps a factor 2 clear of the inversion that
+    // Graph.py:153-163 documents).  Anything else -- branching, a chain that rejoins upstream (a duplication), extra
+    // overlaps between reference k-mers -- takes the general path below.
+    {
+        int* bub = sh + 24;                  // [0] branch nodes, [1] a, [2] head, [3] join nodes, [4] b, [5] tail, [6] violations
+        if (tid < 8) bub[tid] = 0;
+        ctx.sync();
+        for (int i = tid; i < n_real; i += nt) {
+            const int dg = S.deg[i], od = dg & 15, id = dg >> 4;
+            const Slot4 s4 = *reinterpret_cast<const Slot4*>(S.succ + 4 * i);
+            int bad = 0;
+            if (i < L) {
+                int novel_succ = -1, n_next = 0;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int j = s4.v[c];
+                    if (j < 0) continue;
+                    if (j == i + 1) n_next += 1;
+                    else if (j >= L) novel_succ = j;
+                    else bad = 1;                                       // an overlap between two reference k-mers that are not neighbours
+                }
+                if (i < L - 1 && n_next != 1) bad = 1;
+                if (od == 2 && novel_succ >= 0 && !bad) { atomic_addi32(&bub[0], 1); bub[1] = i; bub[2] = novel_succ; }
+                else if (od != 1) bad = 1;
+                if (id == 2) {
+                    const Slot4 p4 = *reinterpret_cast<const Slot4*>(S.pred + 4 * i);
+                    int novel_pred = -1;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) if (p4.v[c] >= L) novel_pred = p4.v[c];
+                    if (novel_pred >= 0) { atomic_addi32(&bub[3], 1); bub[4] = i; bub[5] = novel_pred; }
+                    else bad = 1;
+                } else if (id != 1) bad = 1;
+            } else if (od != 1 || id != 1) bad = 1;                     // a novel node inside a simple chain
+            if (bad) bub[6] = 1;
+        }
+        ctx.sync();
+        if (tid == 0) {
+            int simple = 0;
+            if (!bub[6] && bub[0] == 0 && bub[3] == 0 && nk == 0) simple = 1;                 // the reference alone
+            else if (!bub[6] && bub[0] == 1 && bub[3] == 1 && nk >= 1 && bub[1] < bub[4] && nk + 2 <= S.maxN &&
+                     (bub[4] - bub[1]) < 50 * (nk + 1)) {
+                // follow the chain: it must visit every novel node once and end in the join's predecessor
+                int cur = bub[2], n = 0;
+                while (cur >= L && n < nk) {
+                    S.cand[n++] = cur;
+                    const Slot4 s4 = *reinterpret_cast<const Slot4*>(S.succ + 4 * cur);
+                    int nx = -1;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) if (s4.v[c] >= 0) nx = s4.v[c];
+                    if (nx == bub[4] && cur == bub[5]) { cur = -2; break; }
+                    cur = nx;
+                }
+                if (cur == -2 && n == nk) simple = 2;
+            }
+            bub[7] = simple;
+            if (simple) atomic_add64(&R.used[7], 1ull);                // (measurement: how many targets took this path)
+        }
+        ctx.sync();
+    }
+    const int simple = sh[24 + 7];
+    const int bub_a = sh[24 + 1], bub_b = sh[24 + 4];
+    if (simple) {
+        if (tid == 0) {
+            S.ce_len[0] = L + 2;                                              // nodes incl. both caps, like the general path
+            if (simple == 2) S.ce_len[1] = (bub_a + 1) + nk + (L - bub_b) + 2;
+            sh[1] = simple;                                                   // candidate count = number of paths
+        }
+        ctx.sync();
+    } else {
     // simple edges: (u, j) with u's only out-edge and j's only in-edge (see shortest_tree)
     int32_t* nxtF = S.occ;
     int32_t* nxtB = S.newidx;
@@ -645,6 +720,7 @@ KM_HD bool graph_target(const Ctx& ctx, const TableView& T, const WalkView& W, c
         });
     }
     ctx.sync();
+    }
     const int n_cand = sh[1];
     if (n_cand > S.max_cand || n_cand > S.max_paths) {
         if (tid == 0) {
@@ -698,6 +774,24 @@ KM_HD bool graph_target(const Ctx& ctx, const TableView& T, const WalkView& W, c
     if (nu < 0) return false;
 
     pt.mark(5);
+    if (simple) {
+        // the two paths written in place: the reference, and 0..a + chain (S.cand, in chain order) + b..L-1; they ARE in
+        // lexicographic order (the chain's first node is numbered >= L > a + 1)
+        int32_t* p0 = R.pool + R.path_off[first];
+        for (int i = tid; i < L; i += nt) p0[i] = i;
+        if (simple == 2) {
+            int32_t* p1 = R.pool + R.path_off[first + 1];
+            const int n1 = (bub_a + 1) + nk + (L - bub_b);
+            for (int i = tid; i < n1; i += nt)
+                p1[i] = i <= bub_a ? i : (i <= bub_a + nk ? S.cand[i - bub_a - 1] : bub_b + (i - bub_a - 1 - nk));
+        }
+        ctx.sync();
+        if (tid == 0) {
+            S.ce_len[0] = L; S.ce_b[0] = -1;
+            if (simple == 2) { S.ce_len[1] = (bub_a + 1) + nk + (L - bub_b); S.ce_b[1] = -1; }
+        }
+        ctx.sync();
+    } else {
     // ---- materialise: two lanes per unique path, one per chain; positions come from the hop counts.
     // A lane steps through novel nodes one dependent load at a time but crosses a reference run in
     // one go (the run bitmaps give its length); long runs are only recorded and then written by the
@@ -818,6 +912,7 @@ KM_HD bool graph_target(const Ctx& ctx, const TableView& T, const WalkView& W, c
     } else if (nu == 1) {
         if (tid == 0) { S.ce_b[0] = S.ce_a[0]; S.ce_len[0] = S.ce_len[0] - 2; }
         ctx.sync();
+    }
     }
     // from here on: ce_len[p] = length and ce_b[p] = cache offset of path p in rank order
     pt.mark(7);

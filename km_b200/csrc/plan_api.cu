@@ -220,7 +220,7 @@ int plan_download(km_plan* p, cudaStream_t s, km_result* res, bool want_graph, b
     res->row_count.p = (int32_t*)view(R.t_n_rows); res->row_count.n = (size_t)n;
     res->row_first.p = (int32_t*)view(R.t_row_first); res->row_first.n = (size_t)n;
     res->lookups.p = (unsigned long long*)view(W.lookups); res->lookups.n = (size_t)n;
-    res->used.p = (unsigned long long*)view(R.used); res->used.n = 4;
+    res->used.p = (unsigned long long*)view(R.used); res->used.n = 8;
     unsigned long long* used = res->used.data();
     const uint32_t* fmt_info = (const uint32_t*)view(p->F.flags);     // device text: [0] flags, [2..3] total bytes
     if (n) CU(cudaMemcpyAsync(blk.data(), p->state0, p->state_bytes, cudaMemcpyDeviceToHost, s));
@@ -460,6 +460,7 @@ extern "C" int km_result_get(const km_result* r, km_result_view* v) {
     v->lookups = reinterpret_cast<const uint64_t*>(r->lookups.data());
     v->ms_h2d = r->ms_h2d; v->ms_walk = r->ms_walk; v->ms_graph = r->ms_graph; v->ms_d2h = r->ms_d2h; v->ms_total = r->ms_total;
     v->n_launches = r->n_launches; v->n_retries = r->n_retries; v->has_graph = r->has_graph ? 1 : 0;
+    v->reserved = r->used.size() >= 8 ? (int32_t)r->used[7] : 0;       // targets whose graph was a simple bubble (graph.h)
     v->bytes_h2d = r->bytes_h2d; v->bytes_d2h = r->bytes_d2h;
     return 0;
 }

@@ -389,7 +389,7 @@ class BatchResult:
         r.lookups = _view(v.lookups, np.uint64, n)
         r.timing = {"h2d_ms": v.ms_h2d, "walk_ms": v.ms_walk, "graph_ms": v.ms_graph, "d2h_ms": v.ms_d2h,
                     "total_ms": v.ms_total, "launches": v.n_launches, "retries": v.n_retries,
-                    "h2d_bytes": int(v.bytes_h2d), "d2h_bytes": int(v.bytes_d2h)}
+                    "h2d_bytes": int(v.bytes_h2d), "d2h_bytes": int(v.bytes_d2h), "simple_graphs": int(v.reserved)}
         return r
 
     # ---- per-target accessors ------------------------------------------------------------

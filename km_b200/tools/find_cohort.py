@@ -34,7 +34,7 @@ def _cohort_table(seq_files, names, header, rows_by_query, min_cov):
     from . import find_report as fr
     for seq_f, name in zip(seq_files, names):
         rows = rows_by_query.get(name, [])
-        sys.stdout.write("## %s\n" % name)
+        sys.stdout.write("Target\t%s\n" % name)
         if not rows:
             continue
         rep = argparse.Namespace(target=seq_f, infile=io.StringIO(header + "".join(r + "\n" for r in rows)), info="vs_ref",

@@ -4,6 +4,7 @@
 // no-ops, atomics plain) so the kernel LOGIC can be compared with the oracle on a machine
 // without a GPU (tests/test_emu_pipeline.py).  Never loaded by km_b200/: the product library
 // contains no host copy of these functions and fails with KM_E_NOGPU when there is no device.
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -124,7 +125,7 @@ int emu_find_target(void* h, const uint8_t* codes, int len, double ratio, int64_
     std::vector<uint32_t> ocount(cap);
     std::vector<int64_t> path_off(path_cap);
     int32_t t_n = 0, t_np = 0, t_pf = 0, t_nr = 0, t_rf = 0;
-    unsigned long long used[4] = {0, 0, 0, 0};
+    unsigned long long used[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     ResultView R;
     R.flags = getenv("KM_NO_REFINE_JUMP") ? KM_RESULT_NO_REFINE_JUMP : 0;
     R.t_n = &t_n; R.t_n_paths = &t_np; R.t_path_first = &t_pf; R.t_n_rows = &t_nr; R.t_row_first = &t_rf;
@@ -157,6 +158,7 @@ int emu_find_target(void* h, const uint8_t* codes, int len, double ratio, int64_
         run_pass(cap, KM_MAX_PATHS, KM_MAX_PATHS, KM_MAX_COLS, 0);
     }
     *out_pass = done ? 1 : 2;
+    if (getenv("KM_EMU_VERBOSE")) fprintf(stderr, "emu: pass %d simple %llu\n", *out_pass, used[7]);
     if (t_n - 2 > node_cap_out) return -1;
     *out_n = t_n;
     memcpy(out_kmer, okmer.data(), sizeof(uint64_t) * (size_t)(t_n - 2));

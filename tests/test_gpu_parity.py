@@ -524,10 +524,10 @@ def test_find_cohort_equals_find_mutation_per_sample(engine, bundled):
         table = run(fc.main_find_cohort, Namespace(target_fn=[catalog], jellyfish_fn=["./data/jf"], device=0, resident=True,
                                                    format="table", min_cov=1, **base))
         npm1 = "NPM1_4ins_exons_10-11utr"
-        at = table.index("## " + npm1)
+        at = table.index("Target\t" + npm1)
         block = []
         for ln in table[at + 1:]:
-            if ln.startswith("## "):
+            if ln.startswith("Target\t"):
                 break
             block.append(ln)
         rows = [r for r in cohort[1:] if r.split("\t")[1] == npm1]
