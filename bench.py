@@ -785,14 +785,17 @@ def main():
                     "ms_per_step": e2e_ms, "device_ms": e2e_breakdown,
                     "what": "km_find_text(host buffers: sequences + offsets, names) -> the TSV text km find_mutation prints; "
                             "device_ms = the same work as two calls (km_find_batch, km_result_text), not pipelined"},
-            "gpu_launches": 7 * args.steps,
+            "gpu_launches": 7 * args.steps,              # per step: reference probe, two walks, schedule, three graph passes
             "kernels": {"km_ref_probe_kernel_ms": probe_ms, "km_walk_kernels_ms": walk_ms, "km_graph_kernels_ms": graph_ms,
                         "what": "reference probe (HBM-bound: ~87% of the panel's lookups), shared-memory + general walk "
                                 "(latency-bound tails), graph/paths/quantification (shared memory, latency-bound)"},
             "roofline": {"kernel": "km_ref_probe_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "units_per_launch": probe_lookups, "bytes_per_unit": 32,
-                         "unit_is": "one canonical k-mer lookup = one 32-byte HBM sector (SURVEY.md 8d)",
+                         "unit_is": "one canonical k-mer lookup ANSWERED = one 32-byte HBM sector (SURVEY.md 8d): per reference "
+                                    "k-mer its own count + the successors off the reference; with the table's neighbour masks "
+                                    "most 'absent' answers need no read (issued_table_reads)",
+                         "traffic_over_algorithmic": (traffic / (probe_lookups * 32.0)) if traffic else None,
                          "random_gather_GBps": gather["GBps"] if gather else None,
                          "frac_of_random_gather": (achieved / gather["GBps"]) if gather else None,
                          "panel": {"algorithmic_lookups": algorithmic, "issued_lookups": issued,

@@ -510,14 +510,15 @@ KM_HD bool graph_target(const Ctx& ctx, const TableView& T, const WalkView& W, c
     }
     ctx.sync();
     // ---- SIMPLE BUBBLE (most targets): the reference chain plus ONE chain of novel nodes that leaves it at node a and
-    // rejoins it at node b > a -- a substitution, an insertion, a deletion -- or no novel node at all.  Every non-reference
+    // rejoins it at node b -- downstream for a substitution, an insertion, a deletion; upstream (b <= a, the path then runs
+    // through b..a twice) for a tandem duplication -- or no novel node at all.  Every non-reference
     // edge then lies on that one chain, so Graph.all_shortest (Graph.py:220-240) can only stitch two paths: the reference
     // (from the source cap's edge, which init_paths keeps, Graph.py:184-198) and 0..a + chain + b..L-1; both shortest-path
     // trees, the chain strip and the candidate edges are known without being computed, provided the trees would follow
     // the reference wherever there is a choice -- true while the by-passed stretch costs less than the chain
     // (0.01 per reference edge against 1.0 per other edge; the test below keeps a factor 2 clear of the inversion that
-    // Graph.py:153-163 documents).  Anything else -- branching, a chain that rejoins upstream (a duplication), extra
-    // overlaps between reference k-mers -- takes the general path below.
+    // Graph.py:153-163 documents; upstream of a the reference is always the cheaper way).  Anything else -- branching, two
+    // variants, extra overlaps between reference k-mers -- takes the general path below.
     {
         int* bub = sh + 24;                  // [0] branch nodes, [1] a, [2] head, [3] join nodes, [4] b, [5] tail, [6] violations
         if (tid < 8) bub[tid] = 0;
@@ -554,8 +555,7 @@ KM_HD bool graph_target(const Ctx& ctx, const TableView& T, const WalkView& W, c
         if (tid == 0) {
             int simple = 0;
             if (!bub[6] && bub[0] == 0 && bub[3] == 0 && nk == 0) simple = 1;                 // the reference alone
-            else if (!bub[6] && bub[0] == 1 && bub[3] == 1 && nk >= 1 && bub[1] < bub[4] && nk + 2 <= S.maxN &&
-                     (bub[4] - bub[1]) < 50 * (nk + 1)) {
+            else if (!bub[6] && bub[0] == 1 && bub[3] == 1 && nk >= 1 && nk + 2 <= S.maxN && (bub[4] - bub[1]) < 50 * (nk + 1)) {
                 // follow the chain: it must visit every novel node once and end in the join's predecessor
                 int cur = bub[2], n = 0;
                 while (cur >= L && n < nk) {

@@ -12,7 +12,7 @@ from km_b200._lib import ROW_DTYPE
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "emu", "km_emu.cpp")
-SO = os.path.join(HERE, "emu", "libkm_emu_test.so")
+SO = os.path.join(HERE, "emu", "libkm_emu_test_asan.so" if os.environ.get("KM_EMU_SANITIZE") else "libkm_emu_test.so")
 CSRC = os.path.join(os.path.dirname(HERE), "km_b200", "csrc")
 _L = None
 
@@ -22,7 +22,11 @@ def lib():
     if _L is None:
         deps = [SRC] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".h")]
         if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
-            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas",
+            # KM_EMU_SANITIZE=1: the same stage functions under AddressSanitizer + UBSan (run pytest with
+            # LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0); compute-sanitizer is closed on
+            # this GPU pool, so this is where out-of-bounds scratch / shared-memory indexing gets caught
+            extra = ["-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-g", "-O1"] if os.environ.get("KM_EMU_SANITIZE") else ["-O2"]
+            subprocess.check_call(["g++", *extra, "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas",
                                    "-o", SO, SRC])
         L = ctypes.CDLL(SO)
         vp, u64, u32, ci = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int
