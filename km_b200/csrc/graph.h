@@ -36,7 +36,14 @@ struct PathView {
     int begin;
     int len;
     const uint16_t* c16;     // the same node numbers in shared memory (16 bit), or nullptr: see GraphScratch::pcache
+    // a SIMPLE BUBBLE's alternative path needs no memory at all outside its chain: position q holds q up to node a, then
+    // the chain's nodes (`idx` points at them, in shared memory), then b, b+1, ...   (bub_nk < 0: not such a path)
+    int bub_a, bub_nk, bub_b;
 };
+KM_HD PathView range_view(int begin, int len) {
+    PathView v; v.idx = nullptr; v.begin = begin; v.len = len; v.c16 = nullptr; v.bub_a = 0; v.bub_nk = -1; v.bub_b = 0;
+    return v;
+}
 
 // One output row (PathQuant.Path, km/utils/PathQuant.py:10-49) in numeric form; the host
 // spells the strings from the node k-mers.  Mirrored by km_row in include/km_b200.h.
@@ -787,8 +794,10 @@ KM_HD bool graph_target(const Ctx& ctx, const TableView& T, const WalkView& W, c
         }
         ctx.sync();
         if (tid == 0) {
-            S.ce_len[0] = L; S.ce_b[0] = -1;
-            if (simple == 2) { S.ce_len[1] = (bub_a + 1) + nk + (L - bub_b); S.ce_b[1] = -1; }
+            // ce_b codes for path_view (quant.h): -2 = the identity path 0..L-1, -3 = the bubble path (a, nk, b in ce_a[0..2],
+            // its chain in S.cand, which nothing overwrites before the rows are done)
+            S.ce_len[0] = L; S.ce_b[0] = -2;
+            if (simple == 2) { S.ce_len[1] = (bub_a + 1) + nk + (L - bub_b); S.ce_b[1] = -3; S.ce_a[0] = bub_a; S.ce_a[1] = nk; S.ce_a[2] = bub_b; }
         }
         ctx.sync();
     } else {

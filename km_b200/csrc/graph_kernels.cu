@@ -71,15 +71,42 @@ __global__ void __launch_bounds__(KM_CTA, NODES == KM_SMALL_NODES ? KM_GRAPH_SMA
     const int cls = NODES == KM_TINY_NODES ? 0 : NODES == KM_SMALL_NODES ? 1 : 2;
     unsigned long long* next = R.used + 4 + cls;
     const int32_t* order = R.sched_order + (size_t)cls * W.n_targets;
+    // Work items are taken ONE AHEAD: while target t is processed, the node arrays the walk left for the next one (evicted
+    // from L2 by the table traffic in between) are prefetched into L2, so its numbering phase starts on L2 hits instead
+    // of ~4 dependent DRAM round trips.
+    bool primed = false;
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) {
-            const int i = (int)atomicAdd(next, 1ull);
-            sh[12] = i < R.sched_count[cls] ? order[i] : -1;
+            int cur;
+            if (!primed) { const int i = (int)atomicAdd(next, 1ull); cur = i < R.sched_count[cls] ? order[i] : -1; }
+            else cur = sh[13];
+            int nxt = -1;
+            if (cur >= 0) { const int j = (int)atomicAdd(next, 1ull); nxt = j < R.sched_count[cls] ? order[j] : -1; }
+            sh[12] = cur; sh[13] = nxt;
         }
+        primed = true;
         __syncthreads();
         const int t = sh[12];
         if (t < 0) break;
+        {
+            const int tn = sh[13];
+            const int lane = (int)threadIdx.x - (KM_CTA - 32);
+            if (tn >= 0 && lane >= 0) {
+                const int64_t nb = W.node_off[tn];
+                const int cap = (int)(W.node_off[tn + 1] - nb);
+                int n = W.n_nodes[tn];
+                n = n < cap ? n : cap;
+                const char* a0 = reinterpret_cast<const char*>(W.node_kmer + nb);
+                const char* a1 = reinterpret_cast<const char*>(W.node_count + nb);
+                const char* a2 = reinterpret_cast<const char*>(W.node_slot + nb);
+                for (int o = lane * 128; o < 8 * n; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" :: "l"(a0 + o));
+                for (int o = lane * 128; o < 4 * n; o += 32 * 128) {
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(a1 + o));
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(a2 + o));
+                }
+            }
+        }
         if (NODES == 0 && threadIdx.x == 0) atomicAnd(&W.status[t], ~KM_ST_RETRY_LARGE);
         GraphDims d;
         ctx.rot = t & 3;

@@ -33,7 +33,11 @@ using namespace km;
 extern thread_local char g_err[512];
 int fail(int code, const char* fmt, ...);
 struct km_table;
-int km_ensure_linked(km_table* t);      // writes the neighbour masks if the table's content changed since (table_api.cu)
+int km_ensure_linked(km_table* t);
+// Wait for `s`.  With several processes per box (one per GPU, six pool threads each) spinning waits oversubscribe the
+// host cores in principle; with KM_BLOCKING_SYNC=1 the wait sleeps on a blocking-sync event instead (off by default: measured
+// slower at 8 ranks per box).
+cudaError_t km_wait_stream(cudaStream_t s, cudaEvent_t* blocking_ev);      // writes the neighbour masks if the table's content changed since (table_api.cu)
 
 #define CU(call)                                                                                  \
     do {                                                                                          \
@@ -148,6 +152,8 @@ struct km_table {
         // ~16 kernels is captured into a CUDA graph and replayed from then on (text_api.cu)
         cudaGraphExec_t gexec = nullptr;
         std::string gkey, last_key;
+        bool vecs_pristine = false; int vecs_k = 0, vecs_extra0 = 0, vecs_maxcap = 1;     // what `vecs` describes (plan_return_vecs)
+        cudaEvent_t wait_ev = nullptr;        // blocking-sync event: a waiting pool thread sleeps instead of spinning (km_wait_stream)
     };
     std::vector<std::unique_ptr<Lane>> lanes;
     std::shared_ptr<PinPool> pool = std::make_shared<PinPool>();   // result buffers (outlive the table if a result does)

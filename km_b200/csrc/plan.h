@@ -130,6 +130,9 @@ struct km_plan {
     cudaStream_t stream = nullptr, side = nullptr;      // the table's own unless the plan runs on a lane
     cudaEvent_t* ev = nullptr;
     cudaEvent_t fork = nullptr, join = nullptr;
+    cudaEvent_t* wait_ev = nullptr;      // the lane's blocking-sync event (km_wait_stream), or null: spin
+    bool layout_reusable = false;        // plan_init: the borrowed vectors already hold this batch's layout
+    int maxcap = 1;
 };
 
 
@@ -140,6 +143,7 @@ int plan_upload(km_plan* p, cudaStream_t s);
 int plan_launch(km_plan* p, cudaStream_t s);
 int plan_download(km_plan* p, cudaStream_t s, km_result* res, bool want_graph, bool head_only = false);
 void plan_swap_vecs(km_plan* p, km_table::PlanVecs& v);
+void plan_return_vecs(km_plan* p, km_table::Lane* lane);
 int plan_init(km_table* t, const char* seqs, const int64_t* offsets, int32_t n, const km_find_params* params, km_plan* p,
               bool borrow_arena, km_table::Lane* lane = nullptr);
 int plan_fetch(km_plan* p, km_result* res, bool want_graph, bool head_only = false);

@@ -11,25 +11,33 @@ thread_local int g_trace_sub = -1;
 int plan_layout(km_plan* p) {
     km_table* t = p->t;
     const int k = t->k, n = p->n;
-    p->node_off.assign(n + 1, 0);
-    p->hash_off.assign(n + 1, 0);
     int maxcap = 1;
-    for (int i = 0; i < n; ++i) {
-        const int64_t len = p->seq_off[i + 1] - p->seq_off[i];
-        const int L = (int)std::max<int64_t>(0, len - k + 1);
-        const int cap = L + p->extra[i];
-        maxcap = std::max(maxcap, cap);
-        p->node_off[i + 1] = p->node_off[i] + cap;
-        p->hash_off[i + 1] = p->hash_off[i] + pow2_at_least(2 * (uint64_t)cap + 256);
+    if (p->layout_reusable) {
+        // the lane's previous plan had the very same target lengths and default capacities: its offset and chunk vectors
+        // (borrowed through plan_swap_vecs) ARE this plan's
+        maxcap = p->maxcap;
+        p->layout_reusable = false;                     // (a capacity retry changes `extra`: it lays out afresh)
+    } else {
+        p->node_off.assign(n + 1, 0);
+        p->hash_off.assign(n + 1, 0);
+        for (int i = 0; i < n; ++i) {
+            const int64_t len = p->seq_off[i + 1] - p->seq_off[i];
+            const int L = (int)std::max<int64_t>(0, len - k + 1);
+            const int cap = L + p->extra[i];
+            maxcap = std::max(maxcap, cap);
+            p->node_off[i + 1] = p->node_off[i] + cap;
+            p->hash_off[i + 1] = p->hash_off[i] + pow2_at_least(2 * (uint64_t)cap + 256);
+        }
+        p->pack_off.assign(n + 1, 0);
+        for (int i = 0; i < n; ++i) p->pack_off[i + 1] = p->pack_off[i] + (p->seq_off[i + 1] - p->seq_off[i] + 15) / 16 + 2;
+        p->chunk_target.clear(); p->chunk_start.clear();
+        for (int i = 0; i < n; ++i) {
+            const int L = (int)std::max<int64_t>(0, p->seq_off[i + 1] - p->seq_off[i] - k + 1);
+            for (int s0 = 0; s0 < L; s0 += 32) { p->chunk_target.push_back(i); p->chunk_start.push_back(s0); }
+        }
+        p->maxcap = maxcap;
     }
-    p->pack_off.assign(n + 1, 0);
-    for (int i = 0; i < n; ++i) p->pack_off[i + 1] = p->pack_off[i] + (p->seq_off[i + 1] - p->seq_off[i] + 15) / 16 + 2;
     const int64_t n_pack = p->pack_off[n];
-    p->chunk_target.clear(); p->chunk_start.clear();
-    for (int i = 0; i < n; ++i) {
-        const int L = (int)std::max<int64_t>(0, p->seq_off[i + 1] - p->seq_off[i] - k + 1);
-        for (int s0 = 0; s0 < L; s0 += 32) { p->chunk_target.push_back(i); p->chunk_start.push_back(s0); }
-    }
     const size_t n_chunks = p->chunk_target.size();
     const int64_t n_node = p->n_node = p->node_off[n], n_hash = p->n_hash = p->hash_off[n], n_code = p->n_code = p->seq_off[n];
     p->grid_tiny = std::max(1, std::min(n, t->sm_count * KM_GRAPH_TINY_GRID));
@@ -226,7 +234,7 @@ int plan_download(km_plan* p, cudaStream_t s, km_result* res, bool want_graph, b
     if (n) CU(cudaMemcpyAsync(blk.data(), p->state0, p->state_bytes, cudaMemcpyDeviceToHost, s));
     else memset(blk.data(), 0, p->state_bytes);
     if (head_only) {
-        CU(cudaStreamSynchronize(s));
+        CU(km_wait_stream(s, p->wait_ev));
         long long total = 0;
         memcpy(&total, fmt_info + 2, 8);
         res->dev_text_len = total; res->dev_text_flags = fmt_info[0];
@@ -280,6 +288,14 @@ int plan_download(km_plan* p, cudaStream_t s, km_result* res, bool want_graph, b
 }
 
 // a plan on a lane borrows the lane's host vectors (and hands them back, km_find_text) for their capacity
+// hand the plan's vectors back to its lane, remembering whether they still describe the default layout
+void plan_return_vecs(km_plan* p, km_table::Lane* lane) {
+    const int32_t extra0 = p->prm.extra_nodes > 0 ? p->prm.extra_nodes : 256;
+    lane->vecs_pristine = p->n_retries == 0;
+    lane->vecs_k = p->t->k; lane->vecs_extra0 = extra0; lane->vecs_maxcap = p->maxcap;
+    plan_swap_vecs(p, lane->vecs);
+}
+
 void plan_swap_vecs(km_plan* p, km_table::PlanVecs& v) {
     p->seq_off.swap(v.seq_off); p->node_off.swap(v.node_off); p->hash_off.swap(v.hash_off); p->pack_off.swap(v.pack_off);
     p->chunk_target.swap(v.chunk_target); p->chunk_start.swap(v.chunk_start); p->extra.swap(v.extra);
@@ -294,14 +310,24 @@ int plan_init(km_table* t, const char* seqs, const int64_t* offsets, int32_t n, 
     p->ev = lane ? lane->ev : t->ev;
     p->fork = lane ? lane->fork : t->fork;
     p->join = lane ? lane->join : t->join;
+    p->wait_ev = lane ? &lane->wait_ev : nullptr;
     if (p->prm.steps > 60000 || p->prm.branchs > 250) return fail(KM_E_ARG, "steps must be <= 60000 and branchs <= 250");
     const int64_t total = n ? offsets[n] : 0;
     if (!p->targets_ext) p->targets.assign(seqs ? seqs : "", (size_t)total);
-    p->seq_off.assign(1, 0);
-    if (n) p->seq_off.assign(offsets, offsets + n + 1);
+    const int32_t extra0 = p->prm.extra_nodes > 0 ? p->prm.extra_nodes : 256;
+    // a lane's previous plan leaves its vectors behind: when the target lengths are the same again (a fixed panel, sample
+    // after sample) and no capacity was grown, the whole layout is reused
+    p->layout_reusable = lane && n > 0 && lane->vecs_k == t->k && lane->vecs_extra0 == extra0 && lane->vecs_pristine &&
+                         p->seq_off.size() == (size_t)n + 1 && p->node_off.size() == (size_t)n + 1 && p->extra.size() == (size_t)n &&
+                         memcmp(p->seq_off.data(), offsets, sizeof(int64_t) * ((size_t)n + 1)) == 0;
+    if (lane) p->maxcap = lane->vecs_maxcap;
+    if (!p->layout_reusable) {
+        p->seq_off.assign(1, 0);
+        if (n) p->seq_off.assign(offsets, offsets + n + 1);
+        p->extra.assign((size_t)n, extra0);
+    }
     int64_t n_ref = 0;
     for (int i = 0; i < n; ++i) n_ref += std::max<int64_t>(0, offsets[i + 1] - offsets[i] - t->k + 1);
-    p->extra.assign((size_t)n, p->prm.extra_nodes > 0 ? p->prm.extra_nodes : 256);
     p->gave_up.assign((size_t)n, 0);
     p->path_cap = std::max(64, 8 * n);
     p->row_cap = std::max(64, 16 * n);

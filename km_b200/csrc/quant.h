@@ -23,17 +23,19 @@
 namespace km {
 
 KM_HD int pv_at(const PathView& p, int i) {
-    return p.c16 ? (int)p.c16[p.begin + i] : (p.idx ? p.idx[p.begin + i] : p.begin + i);
+    const int q = p.begin + i;
+    if (p.bub_nk >= 0) return q <= p.bub_a ? q : (q <= p.bub_a + p.bub_nk ? p.idx[q - p.bub_a - 1] : p.bub_b + (q - p.bub_a - 1 - p.bub_nk));
+    return p.c16 ? (int)p.c16[q] : (p.idx ? p.idx[q] : q);
 }
 // path p of the target (rank order) as a view: its node numbers come from the shared-memory cache when it holds them
 // (graph_target leaves ce_len[p] = length and ce_b[p] = cache offset or -1)
 KM_HD PathView path_view(const GraphScratch& S, const ResultView& R, int first_path, int p) {
-    PathView v;
     const int at = S.ce_b[p];
+    PathView v = range_view(0, S.ce_len[p]);
+    if (at == -2) return v;                              // the reference path of a simple bubble: position q holds node q
+    if (at == -3) { v.idx = S.cand; v.bub_a = S.ce_a[0]; v.bub_nk = S.ce_a[1]; v.bub_b = S.ce_a[2]; return v; }
     v.c16 = (S.pcache_cap > 0 && at >= 0) ? S.pcache + at : nullptr;
     v.idx = R.pool + R.path_off[first_path + p];
-    v.begin = 0;
-    v.len = S.ce_len[p];
     return v;
 }
 // Python indexing: a negative position counts from the end (the reference's third scan can run
@@ -556,7 +558,7 @@ KM_HD void cluster_columns(const GraphScratch& S, const ResultView& R, const Gra
     const int off0 = lo - span > 0 ? lo - span : 0;             // (:713)
     // Python slices clamp to the sequence (:714, :720)
     const int ref_stop = hi < d.L ? hi : d.L;
-    cols[0].idx = nullptr; cols[0].c16 = nullptr; cols[0].begin = off0; cols[0].len = ref_stop - off0 > 0 ? ref_stop - off0 : 0;
+    cols[0] = range_view(off0, ref_stop - off0 > 0 ? ref_stop - off0 : 0);
     for (int j = 0; j < size; ++j) {
         const int p = members[j];
         PathView v = path_view(S, R, first_path, p);
@@ -593,7 +595,7 @@ KM_HD void emit_rows(const Ctx& ctx, const TableView& T, const WalkView& W, cons
     const uint32_t* counts = cnt_s;                  // caps are not stored: rows never touch them
     int* slot = sh + 8;                              // CTA-wide reduction scratch
     int* wslot = sh + 16 + wid;                      // this warp's reduction scratch
-    const PathView ref = {nullptr, 0, d.L};
+    const PathView ref = range_view(0, d.L);
 
     PhaseTimer pt;
     for (int i = tid; i < d.N; i += ctx.nt()) S.occ[i] = 0;     // held nxtF during the tree phase; the solvers need zeros
@@ -685,7 +687,7 @@ KM_HD void emit_rows(const Ctx& ctx, const TableView& T, const WalkView& W, cons
             span = span < 0 ? -span : span;
             const int off0 = lo - span > 0 ? lo - span : 0;                  // (:713)
             const int ref_stop = hi < d.L ? hi : d.L;
-            const PathView ref_clip = {nullptr, off0, ref_stop - off0 > 0 ? ref_stop - off0 : 0};
+            const PathView ref_clip = range_view(off0, ref_stop - off0 > 0 ? ref_stop - off0 : 0);
             PathView clip = path_view(S, R, first_path, p);
             const int plen = clip.len;
             int stop = S.pdiff[4 * p + 2] + hi - S.pdiff[4 * p + 1];         // (:719)

@@ -334,7 +334,9 @@ extern "C" int km_find_text(km_table* t, const char* seqs, const int64_t* offset
     }
     if (int rc = km_ensure_linked(t)) return rc;
     Trace tr;
-    if (n_sub <= 0) n_sub = n >= 4096 ? 6 : n >= 1024 ? 2 : 1;
+    // (measured, 10,000 targets: 4 and 6 sub-batches tie on one GPU -- 1.407 / 1.408 ms -- and 4 wins when eight ranks share a
+    // 32-core box, 1.91 vs 2.18 ms: fewer pool threads per process; profiles/r2m_nsub.txt, r2o_nsub_n8.txt)
+    if (n_sub <= 0) n_sub = n >= 4096 ? 4 : n >= 1024 ? 2 : 1;
     n_sub = std::max(1, std::min(n_sub, std::max(1, n)));
     while ((int)t->lanes.size() < n_sub) {
         std::unique_ptr<km_table::Lane> L(new km_table::Lane());
@@ -481,14 +483,14 @@ extern "C" int km_find_text(km_table* t, const char* seqs, const int64_t* offset
                     char* dst = final_text + at;
                     if (!fits) { spill[(size_t)c].resize((size_t)len); dst = spill[(size_t)c].data(); spilled[(size_t)c] = 1; }
                     if (cudaMemcpyAsync(dst, p->F.text, (size_t)len, cudaMemcpyDeviceToHost, p->stream) != cudaSuccess ||
-                        cudaStreamSynchronize(p->stream) != cudaSuccess) {
+                        km_wait_stream(p->stream, p->wait_ev) != cudaSuccess) {
                         fail(KM_E_CUDA, "copy of the text failed: %s", cudaGetErrorString(cudaGetLastError()));
                         rcs[(size_t)c] = KM_E_CUDA; errs[(size_t)c] = g_err;
                     }
                     pr->bytes_d2h += (unsigned long long)len;
                 }
                 tr.mark("text placed", c);
-                plan_swap_vecs(p, t->lanes[(size_t)lane_ix]->vecs);
+                plan_return_vecs(p, t->lanes[(size_t)lane_ix].get());
                 latch.done();
             });
         }
