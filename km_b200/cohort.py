@@ -109,7 +109,8 @@ def find_mutation_sharded(table, targets, db_name, dist=None, device=None, raise
     texts and per-target statuses with two collectives (sizes, then one padded gather of byte buffers) and joins
     them in rank order = input order.  `targets`: a ShardPlan, or PackedTargets(sequences, names).
 
-    Returns (text: uint8 array, status: uint32 array over all targets) on rank 0, (None, None) elsewhere.
+    Returns (text: uint8 array, status: uint32 array over all targets) on rank 0, (None, None) elsewhere; when `targets`
+    is a ShardPlan the two arrays are views of buffers the plan keeps (valid until its next call).
     A rank whose call fails still takes part in both collectives, so nobody hangs; the error then surfaces on
     every rank (raise_errors) after the gather, like the reference's -- which prints the rows of the targets
     before the failing one first (the statuses of targets that failed on their own are returned, not raised:
@@ -132,23 +133,28 @@ def find_mutation_sharded(table, targets, db_name, dist=None, device=None, raise
     dev = device if device is not None else (torch.device("cuda", table.device) if dist.get_backend() == "nccl" else torch.device("cpu"))
     on_gpu = dev.type == "cuda"
     n_text, n_stat = int(text.size), int(status.size)
-    mine_bytes = n_text + 4 * n_stat
     sizes = torch.tensor([n_text, n_stat, 1 if err else 0], dtype=torch.int64, device=dev)
     all_sizes = torch.empty(3 * world, dtype=torch.int64, device=dev)
     dist.all_gather_into_tensor(all_sizes, sizes)
     all_sizes = all_sizes.cpu().numpy().reshape(world, 3)
-    per_rank = (all_sizes[:, 0] + 4 * all_sizes[:, 1]).tolist()
-    # ONE collective moves every rank's bytes (text, then statuses) to rank 0: all_to_all_single with everything
-    # addressed to rank 0.  The text is read where the library left it (pinned memory) -- no host-side packing.
-    buf = plan.buffer("send", mine_bytes, dev)
+    text_sizes = all_sizes[:, 0].tolist()
+    stat_sizes = (4 * all_sizes[:, 1]).tolist()
+    # TWO collectives move every rank's bytes to rank 0 (all_to_all_single with everything addressed to rank 0): the
+    # texts, which land one after the other in rank order -- that IS the text of the whole run, nothing is joined or
+    # copied again on the host -- and the (small) statuses.  The text is read where the library left it (pinned memory).
+    send_t = plan.buffer("send_text", n_text, dev)
+    send_s = plan.buffer("send_stat", 4 * n_stat, dev)
     if n_text:
-        buf[:n_text].copy_(torch.from_numpy(text), non_blocking=on_gpu)
+        send_t[:n_text].copy_(torch.from_numpy(text), non_blocking=on_gpu)
     if n_stat:
-        buf[n_text:mine_bytes].copy_(torch.from_numpy(np.ascontiguousarray(status, dtype=np.uint32).view(np.uint8)), non_blocking=on_gpu)
-    total = int(sum(per_rank)) if rank == 0 else 0
-    out = plan.buffer("recv", total, dev)
-    dist.all_to_all_single(out[:total], buf[:mine_bytes], per_rank if rank == 0 else [0] * world,
-                           [mine_bytes] + [0] * (world - 1))
+        send_s[:4 * n_stat].copy_(torch.from_numpy(np.ascontiguousarray(status, dtype=np.uint32).view(np.uint8)), non_blocking=on_gpu)
+    total_t = int(sum(text_sizes)) if rank == 0 else 0
+    total_s = int(sum(stat_sizes)) if rank == 0 else 0
+    recv_t = plan.buffer("recv_text", total_t, dev)
+    recv_s = plan.buffer("recv_stat", total_s, dev)
+    zeros = [0] * world
+    dist.all_to_all_single(recv_t[:total_t], send_t[:n_text], text_sizes if rank == 0 else zeros, [n_text] + [0] * (world - 1))
+    dist.all_to_all_single(recv_s[:total_s], send_s[:4 * n_stat], stat_sizes if rank == 0 else zeros, [4 * n_stat] + [0] * (world - 1))
     any_err = bool(all_sizes[:, 2].any())
     if any_err:
         msgs = [None] * world
@@ -157,22 +163,18 @@ def find_mutation_sharded(table, targets, db_name, dist=None, device=None, raise
             raise RuntimeError("; ".join(m for m in msgs if m))
     if rank != 0:
         if on_gpu:
-            torch.cuda.current_stream(dev).synchronize()      # the send buffer is reused by the next call
+            torch.cuda.current_stream(dev).synchronize()      # the send buffers are reused by the next call
         return None, None
     if on_gpu:
-        host = plan.buffer("host", total, torch.device("cpu"), pinned=True)
-        host[:total].copy_(out[:total], non_blocking=True)    # one copy back, into pinned memory
+        # one copy back each, into pinned memory that lives on the plan: the returned text is a VIEW of it, valid until the
+        # next call with this plan
+        host_t = plan.buffer("host_text", total_t, torch.device("cpu"), pinned=True)
+        host_s = plan.buffer("host_stat", total_s, torch.device("cpu"), pinned=True)
+        host_t[:total_t].copy_(recv_t[:total_t], non_blocking=True)
+        host_s[:total_s].copy_(recv_s[:total_s], non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
-        host = host[:total].numpy()
-    else:
-        host = out[:total].numpy()
-    texts, stats, at = [], [], 0
-    for r in range(world):
-        nt, ns = int(all_sizes[r, 0]), int(all_sizes[r, 1])
-        texts.append(host[at:at + nt])
-        stats.append(host[at + nt:at + nt + 4 * ns])
-        at += nt + 4 * ns
-    return np.concatenate(texts), np.concatenate(stats).view(np.uint32)
+        return host_t[:total_t].numpy(), host_s[:total_s].numpy().view(np.uint32)
+    return recv_t[:total_t].numpy(), recv_s[:total_s].numpy().view(np.uint32)
 
 
 # ---- table sharded -----------------------------------------------------------------------------------

@@ -131,6 +131,10 @@ struct km_plan {
     cudaEvent_t* ev = nullptr;
     cudaEvent_t fork = nullptr, join = nullptr;
     cudaEvent_t* wait_ev = nullptr;      // the lane's blocking-sync event (km_wait_stream), or null: spin
+    // a plan made by km_find_plan_create owns its side stream and events, so that several plans of one table can be in
+    // flight at once on different streams (bench.py launches the panel as parts that overlap each other's phases)
+    cudaStream_t own_side = nullptr;
+    cudaEvent_t own_ev[8] = {}, own_fork = nullptr, own_join = nullptr;
     bool layout_reusable = false;        // plan_init: the borrowed vectors already hold this batch's layout
     int maxcap = 1;
 };

@@ -402,6 +402,13 @@ extern "C" int km_find_plan_create(km_table* t, const char* seqs, const int64_t*
     km_plan* p = new km_plan();
     if (int rc = plan_init(t, seqs, offsets, n, params, p, false)) { delete p; return rc; }
     CU(cudaStreamSynchronize(t->stream));
+    // its own side stream and events (the table's are shared by km_find_batch and by other plans)
+    CU(cudaStreamCreateWithFlags(&p->own_side, cudaStreamNonBlocking));
+    for (auto& e : p->own_ev) CU(cudaEventCreate(&e));
+    CU(cudaEventCreateWithFlags(&p->own_fork, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&p->own_join, cudaEventDisableTiming));
+    p->side = p->own_side; p->ev = p->own_ev; p->fork = p->own_fork; p->join = p->own_join;
+    CU(cudaEventRecord(p->ev[0], t->stream));          // (the upload's start mark was taken on the table's event)
     *out = p;
     return 0;
 }
@@ -449,6 +456,10 @@ extern "C" void km_find_plan_free(km_plan* p) {
     cudaSetDevice(p->t->device);
     p->own_dev.release();
     p->own_pin.release();
+    for (auto& e : p->own_ev) if (e) cudaEventDestroy(e);
+    if (p->own_fork) cudaEventDestroy(p->own_fork);
+    if (p->own_join) cudaEventDestroy(p->own_join);
+    if (p->own_side) cudaStreamDestroy(p->own_side);
     delete p;
 }
 
