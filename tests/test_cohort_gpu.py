@@ -117,3 +117,21 @@ def test_sharded_table_equals_unsharded(tmp_path):
     kb.build()
     mp.spawn(_worker, args=(WORLD, _free_port(), str(tmp_path)), nprocs=WORLD, join=True)
     assert all(os.path.exists(os.path.join(str(tmp_path), "ok%d" % r)) for r in range(WORLD))
+
+
+@pytest.mark.skipif(_n_gpus() < WORLD, reason="needs %d GPUs" % WORLD)
+def test_cli_find_mutation_gpus_switch_prints_the_single_gpu_text(synth_small):
+    """`km find_mutation --gpus 2 <targets> <db.jf>`: the targets dealt to two GPUs (one process each, table loaded on
+    both), rank 0 prints -- byte for byte what one GPU prints, minus the volatile lines and the `#gpus:2` echo."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+    def run(extra):
+        out = subprocess.run([sys.executable, "-m", "km_b200", "find_mutation", *extra, *synth_small["files"][:40], synth_small["jf"]],
+                             cwd=root, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        return [l for l in out.stdout.split("\n") if l and not l.startswith("#Elapsed") and not l.startswith("#func:") and not l.startswith("#gpus:")]
+    one = run([])
+    two = run(["--gpus", "2"])
+    assert one == two and sum(1 for l in one if not l.startswith("#")) > 40
