@@ -27,12 +27,14 @@ namespace km {
 #define KM_WS_MAXL 448       // reference k-mers per target
 #define KM_WS_SEQW 32        // packed words: (KM_WS_MAXL + 31 + 15) / 16 + 2 of padding
 #define KM_ST_WALK_DEFER 0x20000000u   // internal: redo this target with the general walk kernel
+#define KM_WS_KID_REF 255u
 
 struct alignas(16) WalkSmall {
     uint64_t nk[KM_WS_NOVEL];          // novel k-mers, index = node - L
     uint32_t slot[KM_WS_HASH / 2];     // two 16-bit slots per word: node index + 1, 0 = empty
     uint32_t nmeta[KM_WS_NOVEL];       // (depth << 8) | breaks of novel nodes
-    uint16_t kid[KM_WS_NOVEL][4];      // node index + 1 of each accepted child of a novel node, 0 = none
+    uint8_t kid[KM_WS_NOVEL][4];       // each accepted child of a novel node: 0 = none, KM_WS_KID_REF = a reference k-mer
+                                       // (never peeled), else novel index + 1
     uint8_t alive[KM_WS_NOVEL];
     uint32_t seq2[KM_WS_SEQW];         // the target, 16 bases per word, first base in the top bits
     int32_t n_nodes;                   // next node index
@@ -40,6 +42,7 @@ struct alignas(16) WalkSmall {
 };
 
 KM_HD bool walk_small_fits(const TargetGeom& g) { return g.L >= 1 && g.L <= KM_WS_MAXL; }
+KM_HD uint8_t ws_kid_code(int idx, int L) { return (uint8_t)(idx < L ? KM_WS_KID_REF : (uint32_t)(idx - L + 1)); }
 
 // reference k-mer i from the packed target (k <= 31)
 KM_HD uint64_t ws_ref_kmer(const WalkSmall& M, int i, int k) { return packed_kmer(M.seq2, i, k); }
@@ -207,7 +210,7 @@ KM_HD void ws_child(const Ctx& ctx, const WalkView& W, const TargetGeom& g, Walk
     idx = warp_shfl32(idx, leader);
     if (has && idx >= 0) {
         if (idx >= L) atomic_min32(&M.nmeta[idx - L], child_meta);
-        if (parent >= L) M.kid[parent - L][c] = (uint16_t)(idx + 1);
+        if (parent >= L) M.kid[parent - L][c] = ws_kid_code(idx, L);
     }
 }
 
@@ -279,7 +282,7 @@ KM_HD void ws_chain_level(const TableView& T, const WalkView& W, const FindParam
     const uint32_t child_meta = pack_meta(depth + 1, nb);
     int nn = (int)load_shared_volatile32(reinterpret_cast<const uint32_t*>(&M.n_nodes));
     int n_new = 0, new_c = 0, new_idx = 0;
-    uint16_t kid[4] = {0, 0, 0, 0};
+    uint8_t kid[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         if (!((pass >> j) & 1u)) continue;
@@ -306,7 +309,7 @@ KM_HD void ws_chain_level(const TableView& T, const WalkView& W, const FindParam
             if (lane == 0 && child_meta < M.nmeta[idx - L]) M.nmeta[idx - L] = child_meta;
             __syncwarp();
         }
-        kid[j] = (uint16_t)(idx + 1);
+        kid[j] = ws_kid_code(idx, L);
     }
     if (lane == 0) {
         M.kid[q - L][0] = kid[0]; M.kid[q - L][1] = kid[1]; M.kid[q - L][2] = kid[2]; M.kid[q - L][3] = kid[3];
@@ -319,19 +322,19 @@ KM_HD void ws_chain_level(const TableView& T, const WalkView& W, const FindParam
 }
 #endif
 
-// One warp walks target t.  Returns false when the target was deferred to the general kernel.
+// The start of a target's walk, by one warp: clears the set, registers the reference k-mers (phase 1) and inserts the
+// successors that leave the reference from the exit list ref_probe_chunk wrote (level 0).  Returns false when the
+// target is finished already (malformed: its status is written and nothing is walked).
 template <class Ctx>
-KM_HD bool walk_small_target(const Ctx& ctx, const TableView& T, const WalkView& W, const FindParams& P, int t, WalkSmall& M) {
+KM_HD bool ws_begin(const Ctx& ctx, const TableView& T, const WalkView& W, const FindParams& P, int t, const TargetGeom& g,
+                    WalkSmall& M, int novel_cap, PhaseTimer& pt) {
     const int k = T.k;
-    const TargetGeom g = target_geom(W, t, k);
     const int lane = ctx.tid(), nl = ctx.nt();
     const int L = g.L;
-    const int novel_cap = g.cap - L < KM_WS_NOVEL ? g.cap - L : KM_WS_NOVEL;
     const int n_exits = W.n_kept[t];               // entries of the exit list (ref_probe_chunk)
-    unsigned nlook = 0;
     uint32_t st = 0;
+    (void)P;
 
-    PhaseTimer pt;
     // ---- set-up: clear the set, pack the target ---------------------------------------------
     for (int s = lane; s < KM_WS_HASH / 2; s += nl) M.slot[s] = 0u;
     {
@@ -353,7 +356,7 @@ KM_HD bool walk_small_target(const Ctx& ctx, const TableView& T, const WalkView&
         if (st) atomic_or32(&W.status[t], st);
         ctx.sync();
         if (lane == 0) { W.n_nodes[t] = L; W.n_kept[t] = 0; }
-        return true;
+        return false;
     }
     ctx.sync();
     pt.mark_warp(33);
@@ -379,6 +382,80 @@ KM_HD bool walk_small_target(const Ctx& ctx, const TableView& T, const WalkView&
     }
     ctx.sync();
     pt.mark_warp(34);
+    return true;
+}
+
+// The end of a target's walk, by one warp: the peel (commit rule, MutationFinder.py:159-163) over the n_all nodes the
+// levels discovered, then the per-target results.  `st` / `nlook`: lane-private status bits and lookup counts.
+// Returns false when the target was deferred to the general kernel (more novel nodes than fit here).
+template <class Ctx>
+KM_HD bool ws_finish(const Ctx& ctx, const WalkView& W, const FindParams& P, int t, const TargetGeom& g, WalkSmall& M,
+                     int novel_cap, int n_all, uint32_t st, unsigned nlook, PhaseTimer& pt) {
+    const int lane = ctx.tid(), nl = ctx.nt();
+    const int L = g.L;
+    if (load_shared_volatile32(&M.flags) & 1u) {
+        // more novel nodes than fit here: a capacity the host can raise, or the general kernel's job
+        if (lane == 0) {
+            if (novel_cap < KM_WS_NOVEL) { atomic_or32(&W.status[t], KM_ST_NODE_OVERFLOW); W.n_nodes[t] = g.cap + 1; W.n_kept[t] = 0; }
+            else atomic_or32(&W.status[t], KM_ST_WALK_DEFER);
+        }
+        return novel_cap < KM_WS_NOVEL;
+    }
+
+    // ---- phase 3: peel novel nodes with no surviving accepted child (commit rule, :159-163) -----------
+    int changed = 1;
+    while (changed) {
+        int mine = 0;
+        for (int q = L + lane; q < n_all; q += nl) {
+            if (!load_shared_volatile8(&M.alive[q - L])) continue;
+            bool ok = false;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const uint32_t kd = M.kid[q - L][c];
+                if (kd && (kd == KM_WS_KID_REF || load_shared_volatile8(&M.alive[kd - 1]))) ok = true;
+            }
+            if (!ok) { M.alive[q - L] = 0; mine = 1; }
+        }
+        changed = ctx.sync_or(mine);
+    }
+
+    pt.mark_warp(36);
+    // ---- results: kept / dropped per node, counts, status ---------------------------------------------
+    int kept = 0;
+    for (int q = L + lane; q < n_all; q += nl) {
+        const bool a = M.alive[q - L] != 0;
+        W.node_slot[g.nbase + q] = a ? 0u : KM_NO_SLOT;
+        kept += a ? 1 : 0;
+    }
+    kept = (int)warp_sum64((unsigned long long)kept);
+    st = warp_or32(st);
+    nlook = (unsigned)warp_sum64((unsigned long long)nlook);
+    if (lane == 0) {
+        const int total = L + kept;
+        W.n_nodes[t] = n_all;
+        W.n_kept[t] = total;
+        if (total > P.max_node) st |= KM_ST_NODE_LIMIT;                          // MutationFinder.py:143-148
+        if (st) atomic_or32(&W.status[t], st);
+        if (nlook) atomic_add64(&W.lookups[t], nlook);
+    }
+    pt.mark_warp(37);
+    return true;
+}
+
+// One warp walks target t.  Returns false when the target was deferred to the general kernel.
+template <class Ctx>
+KM_HD bool walk_small_target(const Ctx& ctx, const TableView& T, const WalkView& W, const FindParams& P, int t, WalkSmall& M) {
+    const int k = T.k;
+    const TargetGeom g = target_geom(W, t, k);
+    const int lane = ctx.tid(), nl = ctx.nt();
+    const int L = g.L;
+    const int novel_cap = g.cap - L < KM_WS_NOVEL ? g.cap - L : KM_WS_NOVEL;
+    unsigned nlook = 0;
+    uint32_t st = 0;
+    (void)k; (void)nl; (void)lane;
+
+    PhaseTimer pt;
+    if (!ws_begin(ctx, T, W, P, t, g, M, novel_cap, pt)) return true;
 
     // ---- later levels: novel nodes only, level-synchronous ---------------------------------------------
     int lo = L;
@@ -465,54 +542,7 @@ KM_HD bool walk_small_target(const Ctx& ctx, const TableView& T, const WalkView&
         const int n = (int)load_shared_volatile32(reinterpret_cast<const uint32_t*>(&M.n_nodes));
         hi = n - L > novel_cap ? L + novel_cap : n;
     }
-    if (load_shared_volatile32(&M.flags) & 1u) {
-        // more novel nodes than fit here: a capacity the host can raise, or the general kernel's job
-        if (lane == 0) {
-            if (novel_cap < KM_WS_NOVEL) { atomic_or32(&W.status[t], KM_ST_NODE_OVERFLOW); W.n_nodes[t] = g.cap + 1; W.n_kept[t] = 0; }
-            else atomic_or32(&W.status[t], KM_ST_WALK_DEFER);
-        }
-        return novel_cap < KM_WS_NOVEL;
-    }
-    const int n_all = hi;
-
-    // ---- phase 3: peel novel nodes with no surviving accepted child (commit rule, :159-163) -----------
-    int changed = 1;
-    while (changed) {
-        int mine = 0;
-        for (int q = L + lane; q < n_all; q += nl) {
-            if (!load_shared_volatile8(&M.alive[q - L])) continue;
-            bool ok = false;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const int kd = M.kid[q - L][c];
-                if (kd && (kd - 1 < L || load_shared_volatile8(&M.alive[kd - 1 - L]))) ok = true;
-            }
-            if (!ok) { M.alive[q - L] = 0; mine = 1; }
-        }
-        changed = ctx.sync_or(mine);
-    }
-
-    pt.mark_warp(36);
-    // ---- results: kept / dropped per node, counts, status ---------------------------------------------
-    int kept = 0;
-    for (int q = L + lane; q < n_all; q += nl) {
-        const bool a = M.alive[q - L] != 0;
-        W.node_slot[g.nbase + q] = a ? 0u : KM_NO_SLOT;
-        kept += a ? 1 : 0;
-    }
-    kept = (int)warp_sum64((unsigned long long)kept);
-    st = warp_or32(st);
-    nlook = (unsigned)warp_sum64((unsigned long long)nlook);
-    if (lane == 0) {
-        const int total = L + kept;
-        W.n_nodes[t] = n_all;
-        W.n_kept[t] = total;
-        if (total > P.max_node) st |= KM_ST_NODE_LIMIT;                          // MutationFinder.py:143-148
-        if (st) atomic_or32(&W.status[t], st);
-        if (nlook) atomic_add64(&W.lookups[t], nlook);
-    }
-    pt.mark_warp(37);
-    return true;
+    return ws_finish(ctx, W, P, t, g, M, novel_cap, hi, st, nlook, pt);
 }
 
 }  // namespace km
