@@ -98,6 +98,8 @@ KM_HD uint8_t load_shared_volatile8(const uint8_t* p) { return *reinterpret_cast
 KM_HD uint32_t atomic_cas32(uint32_t* p, uint32_t cmp, uint32_t val) { return atomicCAS(p, cmp, val); }
 KM_HD int warp_index(const CtaCtx& c) { return c.tid() >> 5; }
 KM_HD int warp_count(const CtaCtx&) { return blockDim.x >> 5; }
+KM_HD int warp_index(const WarpCtx&) { return 0; }
+KM_HD int warp_count(const WarpCtx&) { return 1; }
 KM_HD uint64_t atomic_cas64(uint64_t* p, uint64_t cmp, uint64_t val) {
     return atomicCAS(reinterpret_cast<unsigned long long*>(p), (unsigned long long)cmp, (unsigned long long)val);
 }

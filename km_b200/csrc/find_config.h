@@ -45,6 +45,21 @@ namespace km {
 #ifndef KM_TINY_NODES
 #define KM_TINY_NODES 256
 #endif
+// the bubble pass (graph_bubble.h): warps per CTA, and the CTAs per SM its registers are budgeted for / that are launched
+// (a warp's scratch is 8 KB in the 256-node class, 16 KB in the 512-node class)
+#ifndef KM_BUBBLE_THREADS
+#define KM_BUBBLE_THREADS 64     // threads per target: 32 = a warp (KM_BUBBLE_WARPS targets per CTA), 64 / 128 = a CTA
+#endif
+#ifndef KM_BUBBLE_WARPS
+#define KM_BUBBLE_WARPS 4
+#endif
+#define KM_BUBBLE_SLOTS (KM_BUBBLE_THREADS == 32 ? KM_BUBBLE_WARPS : 1)      // targets (scratch areas) per CTA
+#ifndef KM_BUBBLE_TINY_MINB
+#define KM_BUBBLE_TINY_MINB 16
+#endif
+#ifndef KM_BUBBLE_SMALL_MINB
+#define KM_BUBBLE_SMALL_MINB 10
+#endif
 #define KM_SMALL_CAND 64
 #define KM_SMALL_PATHS 64
 #define KM_SMALL_COLS 8

@@ -3,7 +3,9 @@
 // quantify_paths, quantify_clusters (km/utils/MutationFinder.py:496-811), Graph.py, PathQuant.py.
 #include <cuda_runtime.h>
 
-#include "quant.h"
+#include <cstdlib>
+
+#include "graph_bubble.h"
 #include "find_config.h"
 #include "find_launch.h"
 #include "../../include/km_b200.h"
@@ -20,22 +22,26 @@ namespace km {
 #define KM_ST_FATAL (KM_ST_BAD_BASE | KM_ST_DUP_KMER | KM_ST_NODE_OVERFLOW | KM_ST_NODE_LIMIT | KM_ST_TOO_SHORT)
 
 // NODES = node capacity of a shared-memory class, 0 = the general pass
-// Work lists of the three graph passes: every target whose walk succeeded goes to the smallest class
-// its graph fits, each list ordered by descending node count (64 size bins; a counting sort in one CTA).
-__global__ void __launch_bounds__(1024) km_schedule_kernel(WalkView W, ResultView R) {
-    __shared__ int hist[3][64], start[3][64];
+// Work lists of the graph passes: every target whose walk succeeded goes to the smallest size class its graph fits, each
+// list ordered by descending node count (64 size bins; a counting sort in one CTA).  Lists 0 / 1: the 256- / 512-node
+// classes of the CTA-per-target pass, 2: the general pass, 3 / 4: the same two classes for the bubble pass -- a target
+// goes there when its walk never branched (KM_ST_BRANCHED, cleared here), i.e. when it is almost surely a simple bubble.
+__global__ void __launch_bounds__(1024) km_schedule_kernel(WalkView W, ResultView R, int bubbles) {
+    __shared__ int hist[5][64], start[5][64];
     const int n = W.n_targets;
-    for (int i = threadIdx.x; i < 3 * 64; i += blockDim.x) (&hist[0][0])[i] = 0;
+    for (int i = threadIdx.x; i < 5 * 64; i += blockDim.x) (&hist[0][0])[i] = 0;
     __syncthreads();
     auto classify = [&](int t, int* bin) -> int {
-        if (W.status[t] & KM_ST_FATAL) return -1;
+        const uint32_t st = W.status[t];
+        if (st & KM_ST_FATAL) return -1;
         const int cap = (int)(W.node_off[t + 1] - W.node_off[t]);
         const int n_all = W.n_nodes[t] < cap ? W.n_nodes[t] : cap;
         const int kept2 = W.n_kept[t] + 2;
         const int b = 63 - (kept2 >> 3);
         *bin = b < 0 ? 0 : b;                                         // bin 0 = the largest graphs
-        if (n_all <= KM_TINY_NODES - 2 && kept2 <= KM_TINY_NODES) return 0;
-        if (n_all <= KM_SMALL_NODES - 2 && kept2 <= KM_SMALL_NODES) return 1;
+        const int lean = bubbles && !(st & KM_ST_BRANCHED) ? 3 : 0;
+        if (n_all <= KM_TINY_NODES - 2 && kept2 <= KM_TINY_NODES) return 0 + lean;
+        if (n_all <= KM_SMALL_NODES - 2 && kept2 <= KM_SMALL_NODES) return 1 + lean;
         return 2;
     };
     for (int t = threadIdx.x; t < n; t += blockDim.x) {
@@ -45,21 +51,91 @@ __global__ void __launch_bounds__(1024) km_schedule_kernel(WalkView W, ResultVie
         else atomicAdd(&hist[c][b], 1);
     }
     __syncthreads();
-    if (threadIdx.x < 3) {
+    if (threadIdx.x < 5) {
         int at = 0;
         for (int b = 0; b < 64; ++b) { start[threadIdx.x][b] = at; at += hist[threadIdx.x][b]; }
         R.sched_count[threadIdx.x] = at;
-    }
+    } else if (threadIdx.x < 8) R.sched_count[threadIdx.x] = 0;      // [5], [6]: cursors of the bubble pass
     __syncthreads();
     for (int t = threadIdx.x; t < n; t += blockDim.x) {
         int b;
         const int c = classify(t, &b);
         if (c >= 0) R.sched_order[(size_t)c * n + atomicAdd(&start[c][b], 1)] = t;
+        if (W.status[t] & KM_ST_BRANCHED) W.status[t] &= ~KM_ST_BRANCHED;
     }
 }
 
+// The simple bubbles (graph_bubble.h): a small group of threads per target -- KM_BUBBLE_THREADS = 32: one warp, several
+// targets per CTA; 64 / 128: one CTA per target -- takes the targets of its size class from the scheduler's list 3 / 4; what
+// turns out not to be a simple bubble goes to the general pass.
 template <int NODES>
-__global__ void __launch_bounds__(KM_CTA, NODES == KM_SMALL_NODES ? KM_GRAPH_SMALL_MINB : (NODES ? KM_GRAPH_TINY_MINB : 4)) km_graph_kernel(TableView T, WalkView W, ScratchLayout SL, ResultView R) {
+__global__ void __launch_bounds__(KM_BUBBLE_THREADS == 32 ? 32 * KM_BUBBLE_WARPS : KM_BUBBLE_THREADS,
+                                  NODES == KM_SMALL_NODES ? KM_BUBBLE_SMALL_MINB : KM_BUBBLE_TINY_MINB)
+km_graph_bubble_kernel(TableView T, WalkView W, ResultView R) {
+    extern __shared__ __align__(16) char km_smem[];
+    const int cls = NODES == KM_TINY_NODES ? 0 : 1;
+    const int32_t* order = R.sched_order + (size_t)(3 + cls) * W.n_targets;
+    const int count = R.sched_count[3 + cls];
+#if KM_BUBBLE_THREADS == 32
+    BubbleScratch<NODES>& B = reinterpret_cast<BubbleScratch<NODES>*>(km_smem)[threadIdx.x >> 5];
+    WarpCtx ctx;
+    for (;;) {
+        int i = 0;
+        if ((threadIdx.x & 31) == 0) i = atomicAdd(&R.sched_count[5 + cls], 1);
+        i = __shfl_sync(0xFFFFFFFFu, i, 0);
+        if (i >= count) break;
+        bubble_target<NODES>(ctx, T, W, R, order[i], B);
+        __syncwarp();
+    }
+#else
+    BubbleScratch<NODES>& B = *reinterpret_cast<BubbleScratch<NODES>*>(km_smem);
+    __shared__ int next_item[2];
+    CtaCtx ctx;
+    // work items are taken ONE AHEAD, as in km_graph_kernel: while target t is processed the node arrays the walk left for
+    // the next one (evicted from L2 by the table traffic in between) are prefetched into L2
+    bool primed = false;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int cur;
+            if (!primed) { const int i = atomicAdd(&R.sched_count[5 + cls], 1); cur = i < count ? order[i] : -1; }
+            else cur = next_item[1];
+            int nxt = -1;
+            if (cur >= 0) { const int j = atomicAdd(&R.sched_count[5 + cls], 1); nxt = j < count ? order[j] : -1; }
+            next_item[0] = cur; next_item[1] = nxt;
+        }
+        primed = true;
+        __syncthreads();
+        const int t = next_item[0];
+        if (t < 0) break;
+        {
+            const int tn = next_item[1];
+            const int lane = (int)threadIdx.x - (KM_BUBBLE_THREADS - 32);
+            if (tn >= 0 && lane >= 0) {
+                const int64_t nb = W.node_off[tn];
+                const int cap = (int)(W.node_off[tn + 1] - nb);
+                int n = W.n_nodes[tn];
+                n = n < cap ? n : cap;
+                const char* a0 = reinterpret_cast<const char*>(W.node_kmer + nb);
+                const char* a1 = reinterpret_cast<const char*>(W.node_count + nb);
+                const char* a2 = reinterpret_cast<const char*>(W.node_slot + nb);
+                for (int o = lane * 128; o < 8 * n; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" :: "l"(a0 + o));
+                for (int o = lane * 128; o < 4 * n; o += 32 * 128) {
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(a1 + o));
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(a2 + o));
+                }
+            }
+        }
+        ctx.rot = t & ((KM_BUBBLE_THREADS >> 5) - 1);
+        bubble_target<NODES>(ctx, T, W, R, t, B);
+    }
+#endif
+}
+
+// `list`: which work list of the scheduler the pass takes its targets from (its own class's, or the one the bubble pass
+// filled with what it handed on)
+template <int NODES>
+__global__ void __launch_bounds__(KM_CTA, NODES == KM_SMALL_NODES ? KM_GRAPH_SMALL_MINB : (NODES ? KM_GRAPH_TINY_MINB : 4)) km_graph_kernel(TableView T, WalkView W, ScratchLayout SL, ResultView R, int list) {
     extern __shared__ __align__(16) char km_smem[];
     __shared__ int sh[32];
     CtaCtx ctx;
@@ -70,7 +146,7 @@ __global__ void __launch_bounds__(KM_CTA, NODES == KM_SMALL_NODES ? KM_GRAPH_SMA
     // the novel nodes of a substitution), a fixed deal leaves most CTAs idle behind the unluckiest one.
     const int cls = NODES == KM_TINY_NODES ? 0 : NODES == KM_SMALL_NODES ? 1 : 2;
     unsigned long long* next = R.used + 4 + cls;
-    const int32_t* order = R.sched_order + (size_t)cls * W.n_targets;
+    const int32_t* order = R.sched_order + (size_t)list * W.n_targets;
     // Work items are taken ONE AHEAD: while target t is processed, the node arrays the walk left for the next one (evicted
     // from L2 by the table traffic in between) are prefetched into L2, so its numbering phase starts on L2 hits instead
     // of ~4 dependent DRAM round trips.
@@ -79,10 +155,10 @@ __global__ void __launch_bounds__(KM_CTA, NODES == KM_SMALL_NODES ? KM_GRAPH_SMA
         __syncthreads();
         if (threadIdx.x == 0) {
             int cur;
-            if (!primed) { const int i = (int)atomicAdd(next, 1ull); cur = i < R.sched_count[cls] ? order[i] : -1; }
+            if (!primed) { const int i = (int)atomicAdd(next, 1ull); cur = i < R.sched_count[list] ? order[i] : -1; }
             else cur = sh[13];
             int nxt = -1;
-            if (cur >= 0) { const int j = (int)atomicAdd(next, 1ull); nxt = j < R.sched_count[cls] ? order[j] : -1; }
+            if (cur >= 0) { const int j = (int)atomicAdd(next, 1ull); nxt = j < R.sched_count[list] ? order[j] : -1; }
             sh[12] = cur; sh[13] = nxt;
         }
         primed = true;
@@ -131,18 +207,35 @@ cudaError_t km_find_kernels_init() {
     cudaError_t e = cudaFuncSetAttribute(km_graph_kernel<KM_TINY_NODES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)class_layout(KM_TINY_NODES).stride);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(km_graph_kernel<KM_SMALL_NODES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)class_layout(KM_SMALL_NODES).stride);
+    e = cudaFuncSetAttribute(km_graph_kernel<KM_SMALL_NODES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)class_layout(KM_SMALL_NODES).stride);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(km_graph_bubble_kernel<KM_TINY_NODES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(KM_BUBBLE_SLOTS * sizeof(BubbleScratch<KM_TINY_NODES>)));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(km_graph_bubble_kernel<KM_SMALL_NODES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(KM_BUBBLE_SLOTS * sizeof(BubbleScratch<KM_SMALL_NODES>)));
+}
+// KM_NO_BUBBLE_KERNEL=1 (environment) = A/B switch: every target through the CTA-per-target passes
+bool km_bubble_pass_enabled() {
+    static const bool on = [] { const char* e = getenv("KM_NO_BUBBLE_KERNEL"); return !(e && *e && *e != '0'); }();
+    return on;
 }
 cudaError_t km_launch_schedule(const WalkView& W, const ResultView& R, cudaStream_t s) {
-    km_schedule_kernel<<<1, 1024, 0, s>>>(W, R);
+    km_schedule_kernel<<<1, 1024, 0, s>>>(W, R, km_bubble_pass_enabled() ? 1 : 0);
     return cudaGetLastError();
 }
-cudaError_t km_launch_graph(int cls, int grid, const TableView& T, const WalkView& W, const ScratchLayout& SL, const ResultView& R,
+cudaError_t km_launch_bubble(int cls, int grid, const TableView& T, const WalkView& W, const ResultView& R, cudaStream_t s) {
+    const int threads = KM_BUBBLE_THREADS == 32 ? 32 * KM_BUBBLE_WARPS : KM_BUBBLE_THREADS;
+    if (cls == 0) km_graph_bubble_kernel<KM_TINY_NODES><<<grid, threads, KM_BUBBLE_SLOTS * sizeof(BubbleScratch<KM_TINY_NODES>), s>>>(T, W, R);
+    else km_graph_bubble_kernel<KM_SMALL_NODES><<<grid, threads, KM_BUBBLE_SLOTS * sizeof(BubbleScratch<KM_SMALL_NODES>), s>>>(T, W, R);
+    return cudaGetLastError();
+}
+cudaError_t km_launch_graph(int cls, int list, int grid, const TableView& T, const WalkView& W, const ScratchLayout& SL, const ResultView& R,
                             cudaStream_t s) {
-    if (cls == 0) km_graph_kernel<KM_TINY_NODES><<<grid, KM_CTA, class_layout(KM_TINY_NODES).stride, s>>>(T, W, SL, R);
-    else if (cls == 1) km_graph_kernel<KM_SMALL_NODES><<<grid, KM_CTA, class_layout(KM_SMALL_NODES).stride, s>>>(T, W, SL, R);
-    else km_graph_kernel<0><<<grid, KM_CTA, 0, s>>>(T, W, SL, R);
+    if (cls == 0) km_graph_kernel<KM_TINY_NODES><<<grid, KM_CTA, class_layout(KM_TINY_NODES).stride, s>>>(T, W, SL, R, list);
+    else if (cls == 1) km_graph_kernel<KM_SMALL_NODES><<<grid, KM_CTA, class_layout(KM_SMALL_NODES).stride, s>>>(T, W, SL, R, list);
+    else km_graph_kernel<0><<<grid, KM_CTA, 0, s>>>(T, W, SL, R, list);
     return cudaGetLastError();
 }
 

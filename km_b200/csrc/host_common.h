@@ -139,6 +139,7 @@ struct km_table {
     unsigned long long* d_counter = nullptr;   // [0] new keys, then a u32 "full" flag at +8
     cudaStream_t stream = nullptr, side = nullptr;   // side: the second shared-memory graph pass runs beside the first
     cudaEvent_t ev[8] = {}, fork = nullptr, join = nullptr;
+    cudaStream_t side2 = nullptr, side3 = nullptr; cudaEvent_t join2 = nullptr, join3 = nullptr;     // the graph passes run four abreast
     Arena dev, pin;            // lookups / inserts
     Arena dev_find, pin_find;  // km_find_batch workspace, reused across calls
     // km_find_text runs a batch as several sub-batches in flight at once: each has its own workspace,
@@ -146,7 +147,8 @@ struct km_table {
     // (the host vectors of a lane's last plan are kept too: their capacity saves the next plan its allocations)
     struct PlanVecs { std::vector<int64_t> seq_off, node_off, hash_off, pack_off; std::vector<int32_t> chunk_target, chunk_start, extra; };
     struct Lane {
-        Arena dev, pin; cudaStream_t stream = nullptr, side = nullptr; cudaEvent_t ev[8] = {}, fork = nullptr, join = nullptr; PlanVecs vecs;
+        Arena dev, pin; cudaStream_t stream = nullptr, side = nullptr, side2 = nullptr, side3 = nullptr;
+        cudaEvent_t ev[8] = {}, fork = nullptr, join = nullptr, join2 = nullptr, join3 = nullptr; PlanVecs vecs;
         // the enqueue of a sub-batch as ONE driver call: when two consecutive calls give this lane a sub-batch of the very
         // same layout (a fixed panel of targets against sample after sample is km's workflow), the sequence copy +
         // ~16 kernels is captured into a CUDA graph and replayed from then on (text_api.cu)

@@ -102,7 +102,7 @@ struct km_plan {
     std::vector<uint8_t> gave_up;     // 1: the target explored more nodes than extra_max allows; it keeps KM_ST_NODE_OVERFLOW
     int64_t pool_cap = 0, seq_cap = 0, n_node = 0, n_hash = 0, n_code = 0;
     int32_t path_cap = 0, row_cap = 0, extra_max = 0;
-    int grid_tiny = 1, grid_graph = 1, grid_large = 1;
+    int grid_tiny = 1, grid_graph = 1, grid_large = 1, grid_bubble_tiny = 1, grid_bubble_small = 1;
     Arena own_dev, own_pin;
     Arena* dev = nullptr;
     Arena* pin = nullptr;
@@ -127,14 +127,14 @@ struct km_plan {
     const char* fmt_names = nullptr; const int64_t* fmt_name_off = nullptr; std::string fmt_db;
     FormatView F{};
     int64_t text_cap = 0;
-    cudaStream_t stream = nullptr, side = nullptr;      // the table's own unless the plan runs on a lane
+    cudaStream_t stream = nullptr, side = nullptr, side2 = nullptr, side3 = nullptr;      // the table's own unless the plan runs on a lane
     cudaEvent_t* ev = nullptr;
-    cudaEvent_t fork = nullptr, join = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr, join2 = nullptr, join3 = nullptr;
     cudaEvent_t* wait_ev = nullptr;      // the lane's blocking-sync event (km_wait_stream), or null: spin
     // a plan made by km_find_plan_create owns its side stream and events, so that several plans of one table can be in
     // flight at once on different streams (bench.py launches the panel as parts that overlap each other's phases)
-    cudaStream_t own_side = nullptr;
-    cudaEvent_t own_ev[8] = {}, own_fork = nullptr, own_join = nullptr;
+    cudaStream_t own_side = nullptr, own_side2 = nullptr, own_side3 = nullptr;
+    cudaEvent_t own_ev[8] = {}, own_fork = nullptr, own_join = nullptr, own_join2 = nullptr, own_join3 = nullptr;
     bool layout_reusable = false;        // plan_init: the borrowed vectors already hold this batch's layout
     int maxcap = 1;
 };

@@ -43,6 +43,8 @@ int plan_layout(km_plan* p) {
     p->grid_tiny = std::max(1, std::min(n, t->sm_count * KM_GRAPH_TINY_GRID));
     p->grid_graph = std::max(1, std::min(n, t->sm_count * KM_GRAPH_SMALL_GRID));
     p->grid_large = std::max(1, std::min(n, t->sm_count * 2));
+    p->grid_bubble_tiny = std::max(1, std::min((n + KM_BUBBLE_SLOTS - 1) / KM_BUBBLE_SLOTS, t->sm_count * KM_BUBBLE_TINY_MINB));
+    p->grid_bubble_small = std::max(1, std::min((n + KM_BUBBLE_SLOTS - 1) / KM_BUBBLE_SLOTS, t->sm_count * KM_BUBBLE_SMALL_MINB));
     const ScratchLayout L0 = make_layout(maxcap, KM_MAX_PATHS, KM_MAX_PATHS, KM_MAX_COLS, 0);
     const int32_t path_cap = p->path_cap, row_cap = p->row_cap;
     const int64_t pool_cap = p->pool_cap, seq_cap = p->seq_cap;
@@ -57,7 +59,7 @@ int plan_layout(km_plan* p) {
     for (int i = 0; i < 5; ++i) acc(4 * n);                                        // per-target result ints
     acc(8 * n_node); acc(4 * n_node);                                              // canonical nodes
     acc(8 * (size_t)path_cap); acc(4 * (size_t)path_cap); acc(8 * (size_t)path_cap); acc(4 * (size_t)pool_cap);
-    acc(sizeof(Row) * (size_t)row_cap); acc((size_t)seq_cap); acc(64); acc(12 * (size_t)n + 64);
+    acc(sizeof(Row) * (size_t)row_cap); acc((size_t)seq_cap); acc(64); acc(20 * (size_t)n + 64);
     acc(L0.stride * (size_t)p->grid_large);
     const size_t n_name = p->fmt ? (size_t)p->fmt_name_off[n] : 0;
     if (p->fmt) {
@@ -110,7 +112,7 @@ int plan_layout(km_plan* p) {
     R.rows = A.take<Row>(row_cap); R.row_cap = row_cap;
     p->d_seq_pool = A.take<char>(seq_cap);
     R.seq_pool = p->d_seq_pool; R.path_seq_off = p->d_path_seq_off; R.seq_cap = seq_cap;
-    R.sched_order = A.take<int32_t>(3 * (size_t)n); R.sched_count = A.take<int32_t>(4);
+    R.sched_order = A.take<int32_t>(5 * (size_t)n); R.sched_count = A.take<int32_t>(8);
     p->SL = L0;
     p->SL.base = A.take<char>(L0.stride * (size_t)p->grid_large);
     if (p->fmt) {
@@ -189,16 +191,28 @@ int plan_launch(km_plan* p, cudaStream_t s) {
     if (timed) CU(cudaEventRecord(p->ev[2], s));
     // shared-memory passes first, then the general pass for large or deferred targets
     CU(km_launch_schedule(p->W, p->R, s));
-    // the two shared-memory passes side by side (their CTAs co-reside; each pass's tail fills with the other)
+    // The passes run side by side (each pass's tail fills with the others' CTAs): the simple bubbles of the two size classes,
+    // a small group of threads per target (graph_bubble.h), and -- for the targets whose walk branched -- the two
+    // shared-memory classes of the CTA-per-target pass; then the general pass for what any of them handed on.
+    const bool bubbles = km_bubble_pass_enabled();
     CU(cudaEventRecord(p->fork, s));
     CU(cudaStreamWaitEvent(p->side, p->fork, 0));
-    CU(km_launch_graph(1, p->grid_graph, t->view(), p->W, p->SL, p->R, p->side));
+    CU(km_launch_graph(1, 1, p->grid_graph, t->view(), p->W, p->SL, p->R, p->side));
     CU(cudaEventRecord(p->join, p->side));
-    CU(km_launch_graph(0, p->grid_tiny, t->view(), p->W, p->SL, p->R, s));
+    if (bubbles) {
+        CU(cudaStreamWaitEvent(p->side2, p->fork, 0));
+        CU(km_launch_bubble(1, p->grid_bubble_small, t->view(), p->W, p->R, p->side2));
+        CU(cudaEventRecord(p->join2, p->side2));
+        CU(cudaStreamWaitEvent(p->side3, p->fork, 0));
+        CU(km_launch_bubble(0, p->grid_bubble_tiny, t->view(), p->W, p->R, p->side3));
+        CU(cudaEventRecord(p->join3, p->side3));
+    }
+    CU(km_launch_graph(0, 0, p->grid_tiny, t->view(), p->W, p->SL, p->R, s));
     CU(cudaStreamWaitEvent(s, p->join, 0));
-    CU(km_launch_graph(2, p->grid_large, t->view(), p->W, p->SL, p->R, s));
+    if (bubbles) { CU(cudaStreamWaitEvent(s, p->join2, 0)); CU(cudaStreamWaitEvent(s, p->join3, 0)); }
+    CU(km_launch_graph(2, 2, p->grid_large, t->view(), p->W, p->SL, p->R, s));
     if (timed) CU(cudaEventRecord(p->ev[3], s));
-    p->n_launches += 7;
+    p->n_launches += bubbles ? 9 : 7;
     if (p->fmt) {
         CU(km_launch_format(p->W, p->R, p->F, t->k, s));
         p->n_launches += 3;
@@ -307,6 +321,8 @@ int plan_init(km_table* t, const char* seqs, const int64_t* offsets, int32_t n, 
     p->t = t; p->n = n; p->prm = *params;
     p->stream = lane ? lane->stream : t->stream;
     p->side = lane ? lane->side : t->side;
+    p->side2 = lane ? lane->side2 : t->side2; p->side3 = lane ? lane->side3 : t->side3;
+    p->join2 = lane ? lane->join2 : t->join2; p->join3 = lane ? lane->join3 : t->join3;
     p->ev = lane ? lane->ev : t->ev;
     p->fork = lane ? lane->fork : t->fork;
     p->join = lane ? lane->join : t->join;
@@ -351,9 +367,9 @@ std::string plan_graph_key(const km_plan* p) {
     const TableView T = p->t->view();
     add(&T, sizeof(T)); add(&p->W, sizeof(p->W)); add(&p->R, sizeof(p->R)); add(&p->F, sizeof(p->F)); add(&p->P, sizeof(p->P));
     add(&p->SL, sizeof(p->SL));
-    const int64_t misc[] = {p->n, p->grid_tiny, p->grid_graph, p->grid_large, (int64_t)p->state_bytes, (int64_t)p->upload_bytes,
+    const int64_t misc[] = {p->n, p->grid_tiny, p->grid_graph, p->grid_large, p->grid_bubble_tiny, p->grid_bubble_small, km_bubble_pass_enabled() ? 1 : 0, (int64_t)p->state_bytes, (int64_t)p->upload_bytes,
                             (int64_t)(intptr_t)p->state0, (int64_t)(intptr_t)p->h_stage, (int64_t)(intptr_t)p->stream,
-                            (int64_t)(intptr_t)p->side, p->fmt ? 1 : 0};
+                            (int64_t)(intptr_t)p->side, (int64_t)(intptr_t)p->side2, (int64_t)(intptr_t)p->side3, p->fmt ? 1 : 0};
     add(misc, sizeof(misc));
     return k;
 }
@@ -404,10 +420,15 @@ extern "C" int km_find_plan_create(km_table* t, const char* seqs, const int64_t*
     CU(cudaStreamSynchronize(t->stream));
     // its own side stream and events (the table's are shared by km_find_batch and by other plans)
     CU(cudaStreamCreateWithFlags(&p->own_side, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&p->own_side2, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&p->own_side3, cudaStreamNonBlocking));
     for (auto& e : p->own_ev) CU(cudaEventCreate(&e));
     CU(cudaEventCreateWithFlags(&p->own_fork, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&p->own_join, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&p->own_join2, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&p->own_join3, cudaEventDisableTiming));
     p->side = p->own_side; p->ev = p->own_ev; p->fork = p->own_fork; p->join = p->own_join;
+    p->side2 = p->own_side2; p->side3 = p->own_side3; p->join2 = p->own_join2; p->join3 = p->own_join3;
     CU(cudaEventRecord(p->ev[0], t->stream));          // (the upload's start mark was taken on the table's event)
     *out = p;
     return 0;
@@ -459,7 +480,11 @@ extern "C" void km_find_plan_free(km_plan* p) {
     for (auto& e : p->own_ev) if (e) cudaEventDestroy(e);
     if (p->own_fork) cudaEventDestroy(p->own_fork);
     if (p->own_join) cudaEventDestroy(p->own_join);
+    if (p->own_join2) cudaEventDestroy(p->own_join2);
+    if (p->own_join3) cudaEventDestroy(p->own_join3);
     if (p->own_side) cudaStreamDestroy(p->own_side);
+    if (p->own_side2) cudaStreamDestroy(p->own_side2);
+    if (p->own_side3) cudaStreamDestroy(p->own_side3);
     delete p;
 }
 

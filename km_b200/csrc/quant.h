@@ -574,25 +574,18 @@ KM_HD void cluster_columns(const GraphScratch& S, const ResultView& R, const Gra
 
 // quantify_paths + quantify_clusters for target t.  `dims`, `n_paths`, `first_path` come from
 // graph_target, which also reserved rows [first_row, first_row + 2*n_paths).  `sh` = 32 ints of
-// CTA-shared memory.  All threads of the CTA must call this.
+// CTA-shared memory.  `kmers` = last base of every canonical node, `counts` = their counts (caps are not stored: rows
+// never touch them), both in the group's fast memory.  All threads of the group must call this.
 template <class Ctx>
-KM_HD void emit_rows(const Ctx& ctx, const TableView& T, const WalkView& W, const GraphScratch& S,
-                     const ResultView& R, int t, const GraphDims& d, int n_paths, int first_path, int first_row, int* sh) {
+KM_HD void emit_rows_prepared(const Ctx& ctx, const TableView& T, const WalkView& W, const GraphScratch& S,
+                              const ResultView& R, int t, const GraphDims& d, int n_paths, int first_path, int first_row, int* sh,
+                              const uint8_t* kmers, const uint32_t* counts) {
     const int k = T.k;
     const int tid = ctx.tid();
     const bool allow_jump = !(R.flags & KM_RESULT_NO_REFINE_JUMP);
     const int wid = warp_index(ctx), nw = warp_count(ctx);
     const WarpCtx wctx;
     const int lane = wctx.tid();
-    const int64_t nbase = W.node_off[t];
-    uint8_t* last_s = reinterpret_cast<uint8_t*>(S.dist2);           // (dead like S.dist, see below)
-    for (int i = tid; i < d.N - 2; i += ctx.nt()) last_s[i] = (uint8_t)(R.out_kmer[nbase + i] & 3ull);
-    const uint8_t* kmers = last_s;
-    // the counts are read several times per row by every solver pass: a copy in the scratch (shared memory in
-    // the small passes) in place of the distance array, which is dead once the paths are materialised
-    uint32_t* cnt_s = reinterpret_cast<uint32_t*>(S.dist);
-    for (int i = tid; i < d.N - 2; i += ctx.nt()) cnt_s[i] = R.out_count[nbase + i];
-    const uint32_t* counts = cnt_s;                  // caps are not stored: rows never touch them
     int* slot = sh + 8;                              // CTA-wide reduction scratch
     int* wslot = sh + 16 + wid;                      // this warp's reduction scratch
     const PathView ref = range_view(0, d.L);
@@ -735,6 +728,21 @@ KM_HD void emit_rows(const Ctx& ctx, const TableView& T, const WalkView& W, cons
         ctx.sync();
     }
     pt.mark(13);
+}
+
+// The same for the CTA-per-target passes: last bases and counts are first copied from the canonical node arrays into the
+// scratch (shared memory in the small passes), in place of the two distance arrays, which are dead once the paths are
+// materialised -- every solver pass reads the counts, naming is a serial scan over last bases.
+template <class Ctx>
+KM_HD void emit_rows(const Ctx& ctx, const TableView& T, const WalkView& W, const GraphScratch& S,
+                     const ResultView& R, int t, const GraphDims& d, int n_paths, int first_path, int first_row, int* sh) {
+    const int tid = ctx.tid();
+    const int64_t nbase = W.node_off[t];
+    uint8_t* last_s = reinterpret_cast<uint8_t*>(S.dist2);
+    for (int i = tid; i < d.N - 2; i += ctx.nt()) last_s[i] = (uint8_t)(R.out_kmer[nbase + i] & 3ull);
+    uint32_t* cnt_s = reinterpret_cast<uint32_t*>(S.dist);
+    for (int i = tid; i < d.N - 2; i += ctx.nt()) cnt_s[i] = R.out_count[nbase + i];
+    emit_rows_prepared(ctx, T, W, S, R, t, d, n_paths, first_path, first_row, sh, last_s, cnt_s);
 }
 
 }  // namespace km

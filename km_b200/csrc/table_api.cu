@@ -65,9 +65,13 @@ extern "C" int km_table_create_layout(int device, int k, int canonical, uint64_t
     }
     CU(cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&t->side, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&t->side2, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&t->side3, cudaStreamNonBlocking));
     for (auto& ev : t->ev) CU(cudaEventCreate(&ev));
     CU(cudaEventCreateWithFlags(&t->fork, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&t->join, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&t->join2, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&t->join3, cudaEventDisableTiming));
     CU(cudaMalloc((void**)&t->d_counter, 16));
     t->pin.host = true;
     t->pin_find.host = true;
@@ -291,16 +295,24 @@ extern "C" void km_table_close(km_table* t) {
         for (auto& e : L->ev) if (e) cudaEventDestroy(e);
         if (L->stream) cudaStreamDestroy(L->stream);
         if (L->side) cudaStreamDestroy(L->side);
+        if (L->side2) cudaStreamDestroy(L->side2);
+        if (L->side3) cudaStreamDestroy(L->side3);
         if (L->fork) cudaEventDestroy(L->fork);
         if (L->join) cudaEventDestroy(L->join);
+        if (L->join2) cudaEventDestroy(L->join2);
+        if (L->join3) cudaEventDestroy(L->join3);
         if (L->gexec) cudaGraphExecDestroy(L->gexec);
         if (L->wait_ev) cudaEventDestroy(L->wait_ev);
     }
     for (auto& ev : t->ev) if (ev) cudaEventDestroy(ev);
     if (t->stream) cudaStreamDestroy(t->stream);
     if (t->side) cudaStreamDestroy(t->side);
+    if (t->side2) cudaStreamDestroy(t->side2);
+    if (t->side3) cudaStreamDestroy(t->side3);
     if (t->fork) cudaEventDestroy(t->fork);
     if (t->join) cudaEventDestroy(t->join);
+    if (t->join2) cudaEventDestroy(t->join2);
+    if (t->join3) cudaEventDestroy(t->join3);
     delete t;
 }
 

@@ -348,9 +348,13 @@ extern "C" int km_find_text(km_table* t, const char* seqs, const int64_t* offset
         const int prio = std::min(prio_lo, prio_hi + (int)t->lanes.size());
         CU(cudaStreamCreateWithPriority(&L->stream, cudaStreamNonBlocking, prio));
         CU(cudaStreamCreateWithPriority(&L->side, cudaStreamNonBlocking, prio));
+        CU(cudaStreamCreateWithPriority(&L->side2, cudaStreamNonBlocking, prio));
+        CU(cudaStreamCreateWithPriority(&L->side3, cudaStreamNonBlocking, prio));
         for (auto& e : L->ev) CU(cudaEventCreate(&e));
         CU(cudaEventCreateWithFlags(&L->fork, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&L->join, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&L->join2, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&L->join3, cudaEventDisableTiming));
         t->lanes.push_back(std::move(L));
     }
     // sub-batches balanced by sequence length (contiguous ranges)
@@ -428,7 +432,7 @@ extern "C" int km_find_text(km_table* t, const char* seqs, const int64_t* offset
                     int rc = 0;
                     bool done = false;
                     if (use_graph && lane->gexec && lane->gkey == key) {
-                        if (cudaGraphLaunch(lane->gexec, p->stream) == cudaSuccess) { done = true; p->launched = true; p->n_launches += 10; tr.mark("graph replay", c); }
+                        if (cudaGraphLaunch(lane->gexec, p->stream) == cudaSuccess) { done = true; p->launched = true; p->n_launches += km_bubble_pass_enabled() ? 12 : 10; tr.mark("graph replay", c); }
                         else { cudaGetLastError(); cudaGraphExecDestroy(lane->gexec); lane->gexec = nullptr; }
                     } else if (use_graph && lane->last_key == key) {
                         if (lane->gexec) { cudaGraphExecDestroy(lane->gexec); lane->gexec = nullptr; }

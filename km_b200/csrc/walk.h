@@ -34,6 +34,10 @@ namespace km {
 #define KM_ST_NAME_MISMATCH 512   // MutationFinder.py:431-440 length check failed
 #endif
 
+// internal, for the scheduler of the graph passes (cleared there): the walk saw more than one way off the reference, or a
+// novel node with several accepted children -- the target's graph is probably not a simple bubble (graph_bubble.h)
+#define KM_ST_BRANCHED 0x10000000u
+
 struct FindParams {
     double ratio;       // -p / Jellyfish cutoff
     int64_t count;      // -c / Jellyfish n_cutoff
@@ -276,6 +280,7 @@ KM_HD void walk_target(const Ctx& ctx, const TableView& T, const WalkView& W, co
         else W.node_slot[g.nbase + q] = KM_NO_SLOT;
     }
     if (kept) atomic_addi32(&W.n_kept[t], kept);
+    st |= KM_ST_BRANCHED;                           // what needed this kernel is no simple bubble
     if (st) atomic_or32(&W.status[t], st);
     if (nlook) atomic_add64(&W.lookups[t], nlook);
     ctx.sync();

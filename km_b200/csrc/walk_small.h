@@ -276,6 +276,7 @@ KM_HD void ws_chain_level(const TableView& T, const WalkView& W, const FindParam
     for (int j = 0; j < 4; ++j) pass |= ((double)cc[j] >= thr) ? (1u << j) : 0u;
     int nb = breaks;
     if (popc32(pass) > 1) {                                                      // MutationFinder.py:153-156
+        st |= KM_ST_BRANCHED;
         nb += 1;
         if (nb > P.max_break) { st |= KM_ST_TOUCHED_LIMIT; pass = 0; }
     }
@@ -343,7 +344,10 @@ KM_HD bool ws_begin(const Ctx& ctx, const TableView& T, const WalkView& W, const
         for (int w = lane; w < KM_WS_SEQW; w += nl) M.seq2[w] = w < nw ? W.pack[w0 + w] : 0u;
     }
     if (W.pre_bad[t]) st |= KM_ST_BAD_BASE;
-    if (lane == 0) { M.n_nodes = L; M.flags = 0; }
+    if (lane == 0) {
+        M.n_nodes = L; M.flags = 0;
+        if (n_exits > 1 || (n_exits == 1 && popc32((W.node_slot[g.nbase] >> 16) & 15u) > 1)) atomic_or32(&W.status[t], KM_ST_BRANCHED);
+    }
     ctx.sync();
 
     pt.mark_warp(32);
@@ -470,6 +474,7 @@ KM_HD bool walk_small_target(const Ctx& ctx, const TableView& T, const WalkView&
         if (hi - lo == 1) ws_chain_level(T, W, P, g, M, novel_cap, lo, pf, st, nlook);
         // four lanes per frontier node, one successor letter each: one lookup per lane
         else for (int base = lo; base < hi; base += 8) {
+            st |= KM_ST_BRANCHED;                      // (two live nodes in one level)
             const int q = base + (lane >> 2), c = lane & 3;
             bool expand = false;
             uint64_t ck = 0;
@@ -505,6 +510,7 @@ KM_HD bool walk_small_target(const Ctx& ctx, const TableView& T, const WalkView&
         }
 #else
         for (int base = lo; base < hi; base += nl) {
+            if (hi - lo > 1) st |= KM_ST_BRANCHED;
             const int q = base + lane;
             const bool active = q < hi;
             bool pass[4] = {false, false, false, false};
@@ -526,6 +532,7 @@ KM_HD bool walk_small_target(const Ctx& ctx, const TableView& T, const WalkView&
                     for (int c = 0; c < 4; ++c) { pass[c] = (double)cc[c] >= thr; nkid += pass[c] ? 1 : 0; }
                     int nb = breaks;
                     if (nkid > 1) {                                                 // MutationFinder.py:153-156
+                        st |= KM_ST_BRANCHED;
                         nb = breaks + 1;
                         if (nb > P.max_break) { st |= KM_ST_TOUCHED_LIMIT; pass[0] = pass[1] = pass[2] = pass[3] = false; }
                     }

@@ -43,6 +43,12 @@ WALK = {32: "walk: set-up", 33: "walk: phase 1 (ref k-mers)", 34: "walk: level 0
 for i in range(32, 40):
     if buf[i]:
         print("%2d %-28s %8.1f cycles/target" % (i, WALK[i], buf[i] / n))
+BUB = {40: "bubble: numbering", 41: "bubble: k-mer map", 42: "bubble: edges", 43: "bubble: test + chain", 44: "bubble: alloc",
+       45: "bubble: paths + spelling", 46: "bubble: rows"}
+for i in range(40, 47):
+    if buf[i]:
+        print("%2d %-28s %8.1f cycles/target" % (i, BUB[i], buf[i] / n))
+print("simple graphs:", plan.fetch(want_graph=False).timing.get("simple_graphs"))
 TREE = {16: "fwd tree: all iterations", 17: "fwd run", 18: "fwd simple step", 19: "fwd general", 20: "bwd all", 21: "bwd run", 22: "bwd simple step", 23: "bwd general"}
 for i in range(16, 24):
     if buf[i]:
