@@ -577,7 +577,7 @@ KM_HD bool graph_target(const Ctx& ctx, const TableView& T, const WalkView& W, c
                 if (cur == -2 && n == nk) simple = 2;
             }
             bub[7] = simple;
-            if (simple) atomic_add64(&R.used[7], 100000ull);
+            if (simple) atomic_add64(&R.used[7], 1ull);                // (measurement: how many targets took this path)
         }
         ctx.sync();
     }

@@ -288,7 +288,7 @@ KM_HD bool bubble_target(const Ctx& ctx, const TableView& T, const WalkView& W, 
     S.cols = reinterpret_cast<PathView*>(B.km); S.members = reinterpret_cast<int32_t*>(B.km);
     S.pcache = nullptr; S.pcache_cap = 0;
     S.maxN = NODES; S.hcap = 0; S.max_cand = 2; S.max_paths = 2; S.max_cols = 2; S.retry = 1;
-    emit_rows_prepared(ctx, T, W, S, R, t, d, nu, first, first_row, sh, B.last, B.cnt);
+    emit_rows_prepared<Ctx, false>(ctx, T, W, S, R, t, d, nu, first, first_row, sh, B.last, B.cnt);
     pt.mark_warp(46);
     return true;
 }

@@ -26,29 +26,36 @@ namespace km {
 // list ordered by descending node count (64 size bins; a counting sort in one CTA).  Lists 0 / 1: the 256- / 512-node
 // classes of the CTA-per-target pass, 2: the general pass, 3 / 4: the same two classes for the bubble pass -- a target
 // goes there when its walk never branched (KM_ST_BRANCHED, cleared here), i.e. when it is almost surely a simple bubble.
+#define KM_SCHED_CACHE 12288          // targets whose (list, bin) code is kept in shared memory between the two passes
 __global__ void __launch_bounds__(1024) km_schedule_kernel(WalkView W, ResultView R, int bubbles) {
     __shared__ int hist[5][64], start[5][64];
+    __shared__ uint16_t code_s[KM_SCHED_CACHE];
     const int n = W.n_targets;
     for (int i = threadIdx.x; i < 5 * 64; i += blockDim.x) (&hist[0][0])[i] = 0;
     __syncthreads();
-    auto classify = [&](int t, int* bin) -> int {
+    // list | bin << 3, or 0xFFFF for a target without a graph
+    auto classify = [&](int t) -> uint32_t {
         const uint32_t st = W.status[t];
-        if (st & KM_ST_FATAL) return -1;
         const int cap = (int)(W.node_off[t + 1] - W.node_off[t]);
-        const int n_all = W.n_nodes[t] < cap ? W.n_nodes[t] : cap;
+        const int nn = W.n_nodes[t];
         const int kept2 = W.n_kept[t] + 2;
-        const int b = 63 - (kept2 >> 3);
-        *bin = b < 0 ? 0 : b;                                         // bin 0 = the largest graphs
+        if (st & KM_ST_FATAL) return 0xFFFFu;
+        const int n_all = nn < cap ? nn : cap;
+        int b = 63 - (kept2 >> 3);
+        b = b < 0 ? 0 : b;                                            // bin 0 = the largest graphs
         const int lean = bubbles && !(st & KM_ST_BRANCHED) ? 3 : 0;
-        if (n_all <= KM_TINY_NODES - 2 && kept2 <= KM_TINY_NODES) return 0 + lean;
-        if (n_all <= KM_SMALL_NODES - 2 && kept2 <= KM_SMALL_NODES) return 1 + lean;
-        return 2;
+        int c = 2;
+        if (n_all <= KM_TINY_NODES - 2 && kept2 <= KM_TINY_NODES) c = 0 + lean;
+        else if (n_all <= KM_SMALL_NODES - 2 && kept2 <= KM_SMALL_NODES) c = 1 + lean;
+        return (uint32_t)(c | (b << 3));
     };
+    // pass 1: the loads of a thread's targets are independent of one another (the histogram comes after)
+#pragma unroll 4
     for (int t = threadIdx.x; t < n; t += blockDim.x) {
-        int b;
-        const int c = classify(t, &b);
-        if (c < 0) { R.t_n[t] = 0; R.t_n_paths[t] = 0; R.t_path_first[t] = 0; R.t_n_rows[t] = 0; R.t_row_first[t] = 0; }
-        else atomicAdd(&hist[c][b], 1);
+        const uint32_t code = classify(t);
+        if (t < KM_SCHED_CACHE) code_s[t] = (uint16_t)code;
+        if (code == 0xFFFFu) { R.t_n[t] = 0; R.t_n_paths[t] = 0; R.t_path_first[t] = 0; R.t_n_rows[t] = 0; R.t_row_first[t] = 0; }
+        else atomicAdd(&hist[code & 7u][code >> 3], 1);
     }
     __syncthreads();
     if (threadIdx.x < 5) {
@@ -58,11 +65,12 @@ __global__ void __launch_bounds__(1024) km_schedule_kernel(WalkView W, ResultVie
     } else if (threadIdx.x < 8) R.sched_count[threadIdx.x] = 0;      // [5], [6]: cursors of the bubble pass
     __syncthreads();
     for (int t = threadIdx.x; t < n; t += blockDim.x) {
-        int b;
-        const int c = classify(t, &b);
-        if (c >= 0) R.sched_order[(size_t)c * n + atomicAdd(&start[c][b], 1)] = t;
-        if (W.status[t] & KM_ST_BRANCHED) W.status[t] &= ~KM_ST_BRANCHED;
+        const uint32_t code = t < KM_SCHED_CACHE ? (uint32_t)code_s[t] : classify(t);
+        if (code != 0xFFFFu) R.sched_order[(size_t)(code & 7u) * n + atomicAdd(&start[code & 7u][code >> 3], 1)] = t;
     }
+    // the scheduler's hint is internal: the host never sees it
+    for (int t = threadIdx.x; t < n; t += blockDim.x)
+        if (W.status[t] & KM_ST_BRANCHED) W.status[t] &= ~KM_ST_BRANCHED;
 }
 
 // The simple bubbles (graph_bubble.h): a small group of threads per target -- KM_BUBBLE_THREADS = 32: one warp, several

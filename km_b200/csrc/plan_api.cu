@@ -212,7 +212,7 @@ int plan_launch(km_plan* p, cudaStream_t s) {
     if (bubbles) { CU(cudaStreamWaitEvent(s, p->join2, 0)); CU(cudaStreamWaitEvent(s, p->join3, 0)); }
     CU(km_launch_graph(2, 2, p->grid_large, t->view(), p->W, p->SL, p->R, s));
     if (timed) CU(cudaEventRecord(p->ev[3], s));
-    p->n_launches += bubbles ? 9 : 7;
+    p->n_launches += bubbles ? 8 : 6;
     if (p->fmt) {
         CU(km_launch_format(p->W, p->R, p->F, t->k, s));
         p->n_launches += 3;

@@ -65,6 +65,12 @@ KM_HD int first_true(const Ctx& ctx, int n, F f, int* slot) {
 template <class Ctx>
 KM_HD Diff diff_paths(const Ctx& ctx, const PathView& ref, const PathView& alt, int k, int* slot) {
     const int nr = ref.len, na = alt.len, m = nr < na ? nr : na;
+    if (!alt.idx && alt.bub_nk < 0 && !ref.idx && ref.bub_nk < 0 && alt.begin == ref.begin && na == nr) {
+        // the reference against itself: the prefix scan runs to the end, the two suffix scans have no room
+        Diff same;
+        same.start = nr; same.end_ref = nr; same.end_var = nr; same.end_ref_overlap = nr;
+        return same;
+    }
     // common prefix (:321-331)
     const int i = first_true(ctx, m, [&](int p) { return pv_at(ref, p) != pv_at(alt, p); }, slot);
     // common suffix, keeping k positions clear of the prefix (:334-356): the loop runs while
@@ -84,11 +90,13 @@ enum { KM_T_REFERENCE = 0, KM_T_SUBSTITUTION = 1, KM_T_ITD = 2, KM_T_INDEL = 3, 
 
 // get_name: type + trimmed deleted / inserted runs.  kmers[i] = last base of canonical node i (all the naming
 // needs of a k-mer: the scan below is serial, one lane, and used to wait for an L2 round trip per step).
+// (`cut` = length of the suffix the deleted and the inserted string share, when the caller has it already: shared_suffix)
 KM_HD int classify(const uint8_t* kmers, const PathView& ref, const PathView& alt, const Diff& d,
-                   int* del_len, int* ins_len) {
+                   int* del_len, int* ins_len, int cut_known = -1) {
     int gone = d.end_ref - d.start, fresh = d.end_var - d.start;
     int cut = 0;
-    if (gone > 0) {     // strip the suffix both strings share (:446-456)
+    if (cut_known >= 0) cut = cut_known;
+    else if (gone > 0) {     // strip the suffix both strings share (:446-456)
         while (cut < gone && cut < fresh &&
                kmers[pv_at(ref, d.end_ref - 1 - cut)] == kmers[pv_at(alt, d.end_var - 1 - cut)])
             ++cut;
@@ -101,9 +109,23 @@ KM_HD int classify(const uint8_t* kmers, const PathView& ref, const PathView& al
     return fresh == 0 ? KM_T_DELETION : KM_T_INDEL;
 }
 
+// The scan of classify by a whole warp (all lanes call): lanes compare strided positions, the first mismatch wins.
+template <class WCtx>
+KM_HD int shared_suffix(const WCtx& wctx, const uint8_t* kmers, const PathView& ref, const PathView& alt, const Diff& d, int* slot) {
+    const int gone = d.end_ref - d.start, fresh = d.end_var - d.start;
+    const int m = gone > 0 ? (gone < fresh ? gone : fresh) : 0;
+    return first_true(wctx, m, [&](int s) { return kmers[pv_at(ref, d.end_ref - 1 - s)] != kmers[pv_at(alt, d.end_var - 1 - s)]; }, slot);
+}
+
+#if KM_DEVICE_BUILD
+#define KM_COLD __device__ __noinline__
+#else
+#define KM_COLD static
+#endif
+
 // cyclic Jacobi on the symmetric m x m matrix A (destroyed); V receives the eigenvectors
 // (columns), the diagonal of A the eigenvalues.
-KM_HD void jacobi_eigen(double* A, double* V, int m) {
+KM_COLD void jacobi_eigen(double* A, double* V, int m) {
     for (int i = 0; i < m; ++i)
         for (int j = 0; j < m; ++j) V[i * m + j] = i == j ? 1.0 : 0.0;
     for (int sweep = 0; sweep < 60; ++sweep) {
@@ -169,11 +191,6 @@ KM_HD double det2(double a, double b, double c, double d) {
 // differs from the fully literal run only by the rounding of the closed form (~1e-12 relative), and the first 32
 // iterations (every transient, every case the reference's own tests hold) are literal.
 #define KM_REFINE_MAXF 4
-#if KM_DEVICE_BUILD
-#define KM_COLD __device__ __noinline__
-#else
-#define KM_COLD static
-#endif
 // (not inlined: it runs for a handful of targets per batch and must not cost the graph kernel its registers)
 KM_COLD int refine_jump(const double* G, const double* h, int m, int n_nodes, double* coef) {
     int F[KM_REFINE_MAXF], mf = 0;
@@ -470,24 +487,57 @@ template <class WCtx>
 KM_HD Quant2 quant_pair(const WCtx& wctx, const GraphScratch& S, const uint32_t* counts, int n_nodes, const PathView& path,
                         const PathView& range, bool path_first, int lane8, bool allow_jump) {
     const int lane = wctx.tid(), nl = wctx.nt();
-    const uint32_t one = 1u << (8 * lane8);
-    uint32_t* occ = reinterpret_cast<uint32_t*>(S.occ);
     unsigned long long h_p = 0ull, h_r = 0ull, g_pr = 0ull, g_pp = 0ull;
     uint32_t mn = 0xFFFFFFFFu;
-    for (int p = lane; p < path.len; p += nl) {
-        const int node = pv_at(path, p);
-        const uint32_t c = counts[node];
-        atomic_add32(&occ[node], one);
-        h_p += (unsigned long long)(float)c;                    // counts -> float32 (PathQuant.py:99), an integer
-        g_pr += (unsigned long long)(node >= range.begin && node < range.begin + range.len);
-        mn = c < mn ? c : mn;
+    if (path.bub_nk >= 0 || !path.idx) {
+        // The identity path or a simple bubble's path (graph.h): which node sits where is known in closed form -- nodes
+        // [x0, x1) once in position order, then the chain (novel nodes, each once, none of them in the reference), then
+        // nodes [y0, y1) -- so the occurrence counts are interval arithmetic: a node occurs twice exactly when both runs
+        // hold it (a tandem duplication), and the only pass left is the one that sums the counts.
+        const int e = path.begin + path.len;
+        int x0 = path.begin, x1 = e, y0 = 0, y1 = 0;
+        if (path.bub_nk >= 0) {
+            const int a1 = path.bub_a + 1, tail = a1 + path.bub_nk;          // first position of the chain / after it
+            x1 = e < a1 ? e : a1;
+            if (x0 > x1) x0 = x1;
+            const int s0 = path.begin > tail ? path.begin : tail;
+            if (e > s0) { y0 = path.bub_b + (s0 - tail); y1 = path.bub_b + (e - tail); }
+        }
+        auto overlap = [](int p0, int p1, int q0, int q1) { const int lo = p0 > q0 ? p0 : q0, hi = p1 < q1 ? p1 : q1; return hi > lo ? hi - lo : 0; };
+        const int r0 = range.begin, r1 = range.begin + range.len;
+        g_pp = (unsigned long long)(path.len + 2 * overlap(x0, x1, y0, y1));
+        g_pr = (unsigned long long)(overlap(x0, x1, r0, r1) + overlap(y0, y1, r0, r1));
+        // the counts are summed run by run (counts -> float32, PathQuant.py:99: an integer)
+        auto take = [&](uint32_t c) { h_p += (unsigned long long)(float)c; mn = c < mn ? c : mn; };
+        for (int i = x0 + lane; i < x1; i += nl) take(counts[i]);
+        if (path.bub_nk >= 0) {
+            const int a1 = path.bub_a + 1;
+            int c0 = path.begin - a1, c1 = e - a1;
+            c0 = c0 < 0 ? 0 : c0; c1 = c1 > path.bub_nk ? path.bub_nk : c1;
+            for (int j = c0 + lane; j < c1; j += nl) take(counts[path.idx[j]]);
+            for (int i = y0 + lane; i < y1; i += nl) take(counts[i]);
+        }
+        const bool same = path.bub_nk < 0 && x0 == r0 && x1 == r1;        // the reference against itself: one sum serves both
+        if (!same) for (int p = lane; p < range.len; p += nl) h_r += (unsigned long long)(float)counts[range.begin + p];
+        h_p = warp_sum64(h_p); h_r = same ? h_p : warp_sum64(h_r);
+    } else {
+        const uint32_t one = 1u << (8 * lane8);
+        uint32_t* occ = reinterpret_cast<uint32_t*>(S.occ);
+        for (int p = lane; p < path.len; p += nl) {
+            const int node = pv_at(path, p);
+            const uint32_t c = counts[node];
+            atomic_add32(&occ[node], one);
+            h_p += (unsigned long long)(float)c;                    // counts -> float32 (PathQuant.py:99), an integer
+            g_pr += (unsigned long long)(node >= range.begin && node < range.begin + range.len);
+            mn = c < mn ? c : mn;
+        }
+        for (int p = lane; p < range.len; p += nl) h_r += (unsigned long long)(float)counts[range.begin + p];
+        wctx.sync();
+        for (int p = lane; p < path.len; p += nl) g_pp += (unsigned long long)((occ[pv_at(path, p)] >> (8 * lane8)) & 255u);
+        wctx.sync();
+        for (int p = lane; p < path.len; p += nl) atomic_add32(&occ[pv_at(path, p)], 0u - one);
+        h_p = warp_sum64(h_p); h_r = warp_sum64(h_r); g_pr = warp_sum64(g_pr); g_pp = warp_sum64(g_pp);
     }
-    for (int p = lane; p < range.len; p += nl) h_r += (unsigned long long)(float)counts[range.begin + p];
-    wctx.sync();
-    for (int p = lane; p < path.len; p += nl) g_pp += (unsigned long long)((occ[pv_at(path, p)] >> (8 * lane8)) & 255u);
-    wctx.sync();
-    for (int p = lane; p < path.len; p += nl) atomic_add32(&occ[pv_at(path, p)], 0u - one);
-    h_p = warp_sum64(h_p); h_r = warp_sum64(h_r); g_pr = warp_sum64(g_pr); g_pp = warp_sum64(g_pp);
     mn = warp_min32(mn);
     Quant2 q;
     q.iters = 0; q.min_cov = 0; q.coef[0] = q.coef[1] = q.rvaf[0] = q.rvaf[1] = 0.0;
@@ -521,9 +571,9 @@ KM_HD Quant2 quant_pair(const WCtx& wctx, const GraphScratch& S, const uint32_t*
 // One output row.  `variant` is the (possibly clipped) path, `refv` the (possibly clipped) reference.
 KM_HD void write_row(const ResultView& R, const WalkView& W, const uint8_t* kmers, int t, int k, int row_index, int kind,
                      const PathView& refv, const PathView& variant, const Diff& df, int path_id, int offset, int cluster_id,
-                     int cluster_n, int iters, int64_t mc, double rvaf, double expr, double ref_rvaf, double ref_expr) {
+                     int cluster_n, int iters, int64_t mc, double rvaf, double expr, double ref_rvaf, double ref_expr, int cut_known = -1) {
     int dl, il;
-    const int type = classify(kmers, refv, variant, df, &dl, &il);
+    const int type = classify(kmers, refv, variant, df, &dl, &il, cut_known);
     Row& row = R.rows[row_index];
     row.target = t; row.kind = kind; row.type = type;
     row.name_start = df.start + k + offset; row.name_end = df.end_ref + 1 + offset;
@@ -576,7 +626,9 @@ KM_HD void cluster_columns(const GraphScratch& S, const ResultView& R, const Gra
 // graph_target, which also reserved rows [first_row, first_row + 2*n_paths).  `sh` = 32 ints of
 // CTA-shared memory.  `kmers` = last base of every canonical node, `counts` = their counts (caps are not stored: rows
 // never touch them), both in the group's fast memory.  All threads of the group must call this.
-template <class Ctx>
+// WIDE = false compiles the solver for clusters of several variants out (the bubble pass: such a target goes to the
+// general pass instead).
+template <class Ctx, bool WIDE = true>
 KM_HD void emit_rows_prepared(const Ctx& ctx, const TableView& T, const WalkView& W, const GraphScratch& S,
                               const ResultView& R, int t, const GraphDims& d, int n_paths, int first_path, int first_row, int* sh,
                               const uint8_t* kmers, const uint32_t* counts) {
@@ -654,9 +706,12 @@ KM_HD void emit_rows_prepared(const Ctx& ctx, const TableView& T, const WalkView
         if (j < n_paths) {
             const int p = j;
             const PathView alt = path_view(S, R, first_path, p);
+            PhaseTimer jt;
             const Quant2 q = quant_pair(wctx, S, counts, d.N, alt, ref, true, wid, allow_jump);
+            jt.mark_warp(51);
+            const Diff df = {S.pdiff[4 * p], S.pdiff[4 * p + 1], S.pdiff[4 * p + 2], S.pdiff[4 * p + 3]};
+            const int cut = shared_suffix(wctx, kmers, ref, alt, df, wslot);
             if (lane == 0) {
-                const Diff df = {S.pdiff[4 * p], S.pdiff[4 * p + 1], S.pdiff[4 * p + 2], S.pdiff[4 * p + 3]};
                 const bool is_ref = alt.len == d.L && df.start == d.L;      // alt_index == ref_index (:627)
                 double c0 = q.coef[0], c1 = q.coef[1], r0 = q.rvaf[0], r1 = q.rvaf[1];
                 if (is_ref) {
@@ -667,8 +722,9 @@ KM_HD void emit_rows_prepared(const Ctx& ctx, const TableView& T, const WalkView
                     if (aliased) { c0 = c1 = NAN; }
                     else { if (c0 >= 0.0) c0 = -1.0; if (c1 >= 0.0) c1 = -1.0; }   // min(counts) is the cap's -1
                 }
-                write_row(R, W, kmers, t, k, first_row + p, 0, ref, alt, df, first_path + p, 0, 0, 0, q.iters, q.min_cov, r0, c0, r1, c1);
+                write_row(R, W, kmers, t, k, first_row + p, 0, ref, alt, df, first_path + p, 0, 0, 0, q.iters, q.min_cov, r0, c0, r1, c1, cut);
             }
+            jt.mark_warp(52);
         } else {
             const int c = j - n_paths;
             if (crec[4 * c + 2] != 1) continue;                  // wider clusters: whole CTA, below
@@ -687,11 +743,16 @@ KM_HD void emit_rows_prepared(const Ctx& ctx, const TableView& T, const WalkView
             stop = stop < plen ? stop : plen;
             const int beg = off0 < plen ? off0 : plen;
             clip.begin = beg; clip.len = stop - beg > 0 ? stop - beg : 0;
+            PhaseTimer jt;
             const Quant2 q = quant_pair(wctx, S, counts, d.N, clip, ref_clip, false, wid, allow_jump);
+            jt.mark_warp(48);
             const Diff df = diff_paths(wctx, ref_clip, clip, k, wslot);
+            jt.mark_warp(49);
+            const int cut = shared_suffix(wctx, kmers, ref_clip, clip, df, wslot);
             if (lane == 0)
                 write_row(R, W, kmers, t, k, crec[4 * c + 3], 1, ref_clip, clip, df, first_path + p, off0, c + 1, 1, q.iters,
-                          q.min_cov, q.rvaf[1], q.coef[1], q.rvaf[0], q.coef[0]);
+                          q.min_cov, q.rvaf[1], q.coef[1], q.rvaf[0], q.coef[0], cut);
+            jt.mark_warp(50);
         }
     }
     ctx.sync();
@@ -705,13 +766,14 @@ KM_HD void emit_rows_prepared(const Ctx& ctx, const TableView& T, const WalkView
     for (int c = 0; c < n_clusters; ++c) {
         const int size = crec[4 * c + 2];
         if (size == 1) continue;
-        if (size + 1 > S.max_cols) {
+        if (!WIDE || size + 1 > S.max_cols) {
             if (tid == 0) {
                 const uint32_t before = atomic_or32(&W.status[t], S.retry ? KM_ST_RETRY_LARGE : (uint32_t)KM_ST_TOO_MANY_COLS);
                 if (S.retry && !(before & KM_ST_RETRY_LARGE)) defer_to_general(R, W, t);
             }
             continue;          // rows stay unset; the general pass redoes the target, or the host refuses it
         }
+        if (!WIDE) continue;
         if (tid == 0) cluster_columns(S, R, d, n_paths, first_path, c, crec, cols, members);
         ctx.sync();
         const int offset = cols[0].begin;

@@ -432,7 +432,7 @@ extern "C" int km_find_text(km_table* t, const char* seqs, const int64_t* offset
                     int rc = 0;
                     bool done = false;
                     if (use_graph && lane->gexec && lane->gkey == key) {
-                        if (cudaGraphLaunch(lane->gexec, p->stream) == cudaSuccess) { done = true; p->launched = true; p->n_launches += km_bubble_pass_enabled() ? 12 : 10; tr.mark("graph replay", c); }
+                        if (cudaGraphLaunch(lane->gexec, p->stream) == cudaSuccess) { done = true; p->launched = true; p->n_launches += km_bubble_pass_enabled() ? 11 : 9; tr.mark("graph replay", c); }
                         else { cudaGetLastError(); cudaGraphExecDestroy(lane->gexec); lane->gexec = nullptr; }
                     } else if (use_graph && lane->last_key == key) {
                         if (lane->gexec) { cudaGraphExecDestroy(lane->gexec); lane->gexec = nullptr; }

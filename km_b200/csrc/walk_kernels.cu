@@ -59,21 +59,14 @@ __global__ void __launch_bounds__(32 * KM_WALK_WARPS, KM_WALK_MINB) km_walk_smal
     const int t = (int)blockIdx.x * KM_WALK_WARPS + (int)(threadIdx.x >> 5);
     if (t >= W.n_targets) return;
     const TargetGeom g = target_geom(W, t, T.k);
-    if (!walk_small_fits(g)) { if ((threadIdx.x & 31) == 0) W.status[t] = KM_ST_WALK_DEFER; return; }   // also drops the probe's limit flag
-    walk_small_target(ctx, T, W, P, t, M[threadIdx.x >> 5]);
-}
-
-__global__ void __launch_bounds__(32 * KM_WALK_WARPS) km_walk_kernel(TableView T, WalkView W, FindParams P) {
-    WarpCtx ctx;
-    const int t = (int)blockIdx.x * KM_WALK_WARPS + (int)(threadIdx.x >> 5);
-    if (t >= W.n_targets) return;
-    if (!(W.status[t] & KM_ST_WALK_DEFER)) return;
+    if (walk_small_fits(g) && walk_small_target(ctx, T, W, P, t, M[threadIdx.x >> 5])) return;
+    // too long for the shared-memory state, or more novel nodes than it holds: the general walk, state in HBM, by the same
+    // warp (rare; a kernel of its own for these cost 7 us per batch whether or not there was one)
     __syncwarp();
-    if ((threadIdx.x & 31) == 0) { W.status[t] = 0; W.lookups[t] = 0; W.n_kept[t] = 0; }
+    if ((threadIdx.x & 31) == 0) { W.status[t] = 0; W.lookups[t] = 0; W.n_kept[t] = 0; }     // (also drops the probe's limit flag)
     __syncwarp();
     walk_target(ctx, T, W, P, t);
 }
-
 
 }  // namespace km
 
@@ -94,9 +87,6 @@ cudaError_t km_launch_ref_probe(const TableView& T, const WalkView& W, const Fin
 cudaError_t km_launch_walks(const TableView& T, const WalkView& W, const FindParams& P, cudaStream_t s) {
     const int n = W.n_targets;
     km_walk_small_kernel<<<(n + KM_WALK_WARPS - 1) / KM_WALK_WARPS, 32 * KM_WALK_WARPS, 0, s>>>(T, W, P);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    km_walk_kernel<<<(n + KM_WALK_WARPS - 1) / KM_WALK_WARPS, 32 * KM_WALK_WARPS, 0, s>>>(T, W, P);
     return cudaGetLastError();
 }
 

@@ -117,6 +117,7 @@ int emu_find_target(void* h, const uint8_t* codes, int len, double ratio, int64_
         }
     }
     if (!walked) { status = 0; lookups = 0; n_kept = 0; walk_target(ctx, t->v, W, P, 0); }
+    status &= ~KM_ST_BRANCHED;                 // the scheduler's hint (km_schedule_kernel clears it)
     *out_lookups = lookups;
     *out_n = 0; *out_n_paths = 0; *out_n_rows = 0;
     if (status & (KM_ST_BAD_BASE | KM_ST_DUP_KMER | KM_ST_NODE_OVERFLOW | KM_ST_NODE_LIMIT | KM_ST_TOO_SHORT)) return (int)status;

@@ -44,8 +44,9 @@ for i in range(32, 40):
     if buf[i]:
         print("%2d %-28s %8.1f cycles/target" % (i, WALK[i], buf[i] / n))
 BUB = {40: "bubble: numbering", 41: "bubble: k-mer map", 42: "bubble: edges", 43: "bubble: test + chain", 44: "bubble: alloc",
-       45: "bubble: paths + spelling", 46: "bubble: rows"}
-for i in range(40, 47):
+       45: "bubble: paths + spelling", 46: "bubble: rows", 48: "  cluster row: quant_pair", 49: "  cluster row: diff_paths",
+       50: "  cluster row: write_row", 51: "  vs_ref row: quant_pair", 52: "  vs_ref row: write_row"}
+for i in range(40, 53):
     if buf[i]:
         print("%2d %-28s %8.1f cycles/target" % (i, BUB[i], buf[i] / n))
 print("simple graphs:", plan.fetch(want_graph=False).timing.get("simple_graphs"))
