@@ -47,11 +47,18 @@ struct PhaseTimer {
         if ((threadIdx.x & 31) == 0) { const long long t1 = clock64(); atomicAdd(&km_phase_cycles[phase], (unsigned long long)(t1 - t0)); t0 = t1; }
 #endif
     }
+    // one warp of a CTA-per-target kernel reports (the caller passes its lane)
+    __device__ __forceinline__ void mark_warp0(int phase, int lane) {
+#ifdef __CUDA_ARCH__
+        if (lane == 0) { const long long t1 = clock64(); atomicAdd(&km_phase_cycles[phase], (unsigned long long)(t1 - t0)); t0 = t1; }
+#endif
+    }
 };
 #else
 struct PhaseTimer {
     KM_HD void mark(int) {}
     KM_HD void mark_warp(int) {}
+    KM_HD void mark_warp0(int, int) {}
 };
 #endif
 
@@ -85,6 +92,7 @@ KM_HD unsigned long long warp_sum64(unsigned long long v) {
     return v;
 }
 KM_HD bool warp_leader() { return (threadIdx.x & 31) == 0; }
+KM_HD unsigned long long warp_bcast64(unsigned long long v) { return __shfl_sync(0xFFFFFFFFu, v, 0); }      // lane 0's value
 KM_HD uint32_t warp_min32(uint32_t v) { return __reduce_min_sync(0xFFFFFFFFu, v); }
 KM_HD uint32_t warp_or32(uint32_t v) { return __reduce_or_sync(0xFFFFFFFFu, v); }
 // lanes holding the same 64-bit value (all 32 lanes must call)
@@ -144,6 +152,7 @@ struct CtaCtx {
 typedef CtaCtx WarpCtx;
 KM_HD unsigned long long warp_sum64(unsigned long long v) { return v; }
 KM_HD bool warp_leader() { return true; }
+KM_HD unsigned long long warp_bcast64(unsigned long long v) { return v; }
 KM_HD uint32_t warp_min32(uint32_t v) { return v; }
 KM_HD uint32_t warp_or32(uint32_t v) { return v; }
 KM_HD uint32_t warp_match64(uint64_t) { return 1u; }

@@ -12,6 +12,23 @@
 
 namespace km {
 
+// (measurement builds) wall-clock extent of every kernel of the graph phase: [id][0] = earliest CTA start, [1] = latest CTA
+// end, in %globaltimer ns; ids: 0 scheduler, 1 / 2 / 3 CTA-per-target 256 / 512 / general, 4 / 5 bubbles 256 / 512;
+// [8 + i] = start / end of the i-th target a CTA-per-target pass took (first 8)
+#if defined(KM_PHASE_TIMERS) || defined(KM_TIMELINE)
+#define KM_HAVE_TIMELINE 1
+static __device__ unsigned long long km_timeline[16][2];
+static __device__ unsigned int km_timeline_targets;
+__device__ __forceinline__ unsigned long long km_now_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+struct KernelSpan {
+    int id;
+    __device__ __forceinline__ explicit KernelSpan(int i) : id(i) { if (threadIdx.x == 0) atomicMin(&km_timeline[id][0], km_now_ns()); }
+    __device__ __forceinline__ ~KernelSpan() { if (threadIdx.x == 0) atomicMax(&km_timeline[id][1], km_now_ns()); }
+};
+#else
+struct KernelSpan { __device__ __forceinline__ explicit KernelSpan(int) {} };
+#endif
+
 // ---- K4 + K5: graph, paths, FP64 quantification; persistent CTAs over targets -----------------
 // Three passes share one body.  The two SHARED-MEMORY passes keep the whole per-target working set
 // (adjacency, both shortest-path trees, candidate edges, solver matrices) on chip; a target goes to the
@@ -30,6 +47,7 @@ namespace km {
 __global__ void __launch_bounds__(1024) km_schedule_kernel(WalkView W, ResultView R, int bubbles) {
     __shared__ int hist[5][64], start[5][64];
     __shared__ uint16_t code_s[KM_SCHED_CACHE];
+    KernelSpan span(0);
     const int n = W.n_targets;
     for (int i = threadIdx.x; i < 5 * 64; i += blockDim.x) (&hist[0][0])[i] = 0;
     __syncthreads();
@@ -82,6 +100,7 @@ __global__ void __launch_bounds__(KM_BUBBLE_THREADS == 32 ? 32 * KM_BUBBLE_WARPS
 km_graph_bubble_kernel(TableView T, WalkView W, ResultView R) {
     extern __shared__ __align__(16) char km_smem[];
     const int cls = NODES == KM_TINY_NODES ? 0 : 1;
+    KernelSpan span(4 + cls);
     const int32_t* order = R.sched_order + (size_t)(3 + cls) * W.n_targets;
     const int count = R.sched_count[3 + cls];
 #if KM_BUBBLE_THREADS == 32
@@ -153,6 +172,7 @@ __global__ void __launch_bounds__(KM_CTA, NODES == KM_SMALL_NODES ? KM_GRAPH_SMA
     // at a time from a global cursor: their cost varies several-fold (a tandem duplication has six times
     // the novel nodes of a substitution), a fixed deal leaves most CTAs idle behind the unluckiest one.
     const int cls = NODES == KM_TINY_NODES ? 0 : NODES == KM_SMALL_NODES ? 1 : 2;
+    KernelSpan span(1 + cls);
     unsigned long long* next = R.used + 4 + cls;
     const int32_t* order = R.sched_order + (size_t)list * W.n_targets;
     // Work items are taken ONE AHEAD: while target t is processed, the node arrays the walk left for the next one (evicted
@@ -197,11 +217,17 @@ __global__ void __launch_bounds__(KM_CTA, NODES == KM_SMALL_NODES ? KM_GRAPH_SMA
 #ifdef KM_PHASE_TIMERS
         const long long tc0 = clock64();
 #endif
+#ifdef KM_HAVE_TIMELINE
+        const unsigned long long tn0 = km_now_ns();
+#endif
         if (!graph_target(ctx, T, W, S, R, t, &d, sh)) continue;
         emit_rows(ctx, T, W, S, R, t, d, sh[2], sh[3], sh[6], sh);
         __syncthreads();
 #ifdef KM_PHASE_TIMERS
         if (threadIdx.x == 0 && t < KM_DEBUG_TARGETS) km_target_cycles[t] = (unsigned int)(clock64() - tc0);
+#endif
+#ifdef KM_HAVE_TIMELINE
+        if (threadIdx.x == 0) { const unsigned int i = atomicAdd(&km_timeline_targets, 1u); if (i < 8) { km_timeline[8 + i][0] = tn0; km_timeline[8 + i][1] = km_now_ns(); } }
 #endif
     }
 }
@@ -221,8 +247,10 @@ cudaError_t km_find_kernels_init() {
     e = cudaFuncSetAttribute(km_graph_bubble_kernel<KM_TINY_NODES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)(KM_BUBBLE_SLOTS * sizeof(BubbleScratch<KM_TINY_NODES>)));
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(km_graph_bubble_kernel<KM_SMALL_NODES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)(KM_BUBBLE_SLOTS * sizeof(BubbleScratch<KM_SMALL_NODES>)));
+    e = cudaFuncSetAttribute(km_graph_bubble_kernel<KM_SMALL_NODES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(KM_BUBBLE_SLOTS * sizeof(BubbleScratch<KM_SMALL_NODES>)));
+    if (e != cudaSuccess) return e;
+    return e;
 }
 // KM_NO_BUBBLE_KERNEL=1 (environment) = A/B switch: every target through the CTA-per-target passes
 bool km_bubble_pass_enabled() {
@@ -255,6 +283,24 @@ extern "C" int km_debug_phase_cycles(unsigned long long* out32, int reset) {
 #ifdef KM_PHASE_TIMERS
     if (out32) CU(cudaMemcpyFromSymbol(out32, km_phase_cycles, 64 * sizeof(unsigned long long)));
     if (reset) { unsigned long long z[64] = {0}; CU(cudaMemcpyToSymbol(km_phase_cycles, z, sizeof(z))); }
+    return 0;
+#else
+    (void)out32; (void)reset;
+    return fail(KM_E_ARG, "library built without KM_PHASE_TIMERS");
+#endif
+}
+
+// out32: 16 x (start, end) in ns; reset: the next launch starts a new record
+extern "C" int km_debug_timeline(unsigned long long* out32, int reset) {
+#ifdef KM_HAVE_TIMELINE
+    if (out32) CU(cudaMemcpyFromSymbol(out32, km_timeline, sizeof(unsigned long long) * 32));
+    if (reset) {
+        unsigned long long z[32];
+        for (int i = 0; i < 16; ++i) { z[2 * i] = ~0ull; z[2 * i + 1] = 0ull; }
+        CU(cudaMemcpyToSymbol(km_timeline, z, sizeof(z)));
+        const unsigned int zero = 0;
+        CU(cudaMemcpyToSymbol(km_timeline_targets, &zero, sizeof(zero)));
+    }
     return 0;
 #else
     (void)out32; (void)reset;

@@ -182,7 +182,7 @@ int plan_upload(km_plan* p, cudaStream_t s) {
 int plan_launch(km_plan* p, cudaStream_t s) {
     km_table* t = p->t;
     if (p->n == 0) return 0;
-    const bool timed = !p->fmt;          // km_find_text enqueues as little as it can: no per-phase events
+    const bool timed = !p->fmt || p->trace_events;          // km_find_text enqueues as little as it can: no per-phase events
     if (timed) CU(cudaEventRecord(p->ev[1], s));
     CU(cudaMemsetAsync(p->state0, 0, p->state_bytes, s));
     CU(km_launch_ref_probe(t->view(), p->W, p->P, s));
@@ -196,6 +196,11 @@ int plan_launch(km_plan* p, cudaStream_t s) {
     // shared-memory classes of the CTA-per-target pass; then the general pass for what any of them handed on.
     const bool bubbles = km_bubble_pass_enabled();
     CU(cudaEventRecord(p->fork, s));
+    // The CTA-per-target classes go FIRST: with the bubble pass in front of them they hold the few targets whose walk
+    // branched, among them the one or two whose wide cluster keeps a lane busy for 0.1-0.2 ms -- launched behind the
+    // bubble kernels (persistent CTAs that fill every SM until their lists are empty) such a target only STARTED when the
+    // bubbles were done, and the pass took both times one after the other.
+    CU(km_launch_graph(0, 0, p->grid_tiny, t->view(), p->W, p->SL, p->R, s));
     CU(cudaStreamWaitEvent(p->side, p->fork, 0));
     CU(km_launch_graph(1, 1, p->grid_graph, t->view(), p->W, p->SL, p->R, p->side));
     CU(cudaEventRecord(p->join, p->side));
@@ -207,7 +212,6 @@ int plan_launch(km_plan* p, cudaStream_t s) {
         CU(km_launch_bubble(0, p->grid_bubble_tiny, t->view(), p->W, p->R, p->side3));
         CU(cudaEventRecord(p->join3, p->side3));
     }
-    CU(km_launch_graph(0, 0, p->grid_tiny, t->view(), p->W, p->SL, p->R, s));
     CU(cudaStreamWaitEvent(s, p->join, 0));
     if (bubbles) { CU(cudaStreamWaitEvent(s, p->join2, 0)); CU(cudaStreamWaitEvent(s, p->join3, 0)); }
     CU(km_launch_graph(2, 2, p->grid_large, t->view(), p->W, p->SL, p->R, s));
@@ -215,6 +219,7 @@ int plan_launch(km_plan* p, cudaStream_t s) {
     p->n_launches += bubbles ? 8 : 6;
     if (p->fmt) {
         CU(km_launch_format(p->W, p->R, p->F, t->k, s));
+        if (p->trace_events) CU(cudaEventRecord(p->ev[4], s));
         p->n_launches += 3;
     }
     p->launched = true;

@@ -190,10 +190,17 @@ KM_HD double det2(double a, double b, double c, double d) {
 // loop simply goes on.  The literal loop then runs the last steps and decides the stop itself, so the result
 // differs from the fully literal run only by the rounding of the closed form (~1e-12 relative), and the first 32
 // iterations (every transient, every case the reference's own tests hold) are literal.
+//
+// WARP-COLLECTIVE: all `nl` lanes of the calling warp pass the same arguments (each its own copy, or memory nobody
+// writes during the call) and get the same result.  The closed form costs two exponentials per mode, and on one lane
+// the search for the stop (doubling + bisection) and the proof were ~20 evaluations one after the other -- the longest
+// serial stretch of a whole batch.  Here 32 candidate steps are evaluated at once, one per lane (a 33-ary search), and
+// the proof runs on 32 sub-stretches side by side.  (The CPU emulation's single lane takes the candidates in turn.)
 #define KM_REFINE_MAXF 4
 // (not inlined: it runs for a handful of targets per batch and must not cost the graph kernel its registers)
-KM_COLD int refine_jump(const double* G, const double* h, int m, int n_nodes, double* coef) {
+KM_COLD int refine_jump(int lane, int nl, const double* G, const double* h, int m, int n_nodes, const double* coef, double* coef_new) {
     int F[KM_REFINE_MAXF], mf = 0;
+    for (int a = 0; a < m; ++a) coef_new[a] = coef[a];
     for (int a = 0; a < m; ++a)
         if (coef[a] > 0.0) { if (mf == KM_REFINE_MAXF) return 0; F[mf++] = a; }
     if (mf == 0 || m > 2 * KM_REFINE_MAXF) return 0;
@@ -226,7 +233,13 @@ KM_COLD int refine_jump(const double* G, const double* h, int m, int n_nodes, do
         Cl[mc++] = a;
     }
     // y_e and d_e after t steps
+#if defined(KM_HOST_EMU) && defined(KM_RJ_DEBUG)
+    int n_eval = 0;
+#endif
     auto eval = [&](double t, double* y, double* d) {
+#if defined(KM_HOST_EMU) && defined(KM_RJ_DEBUG)
+        ++n_eval;
+#endif
         for (int e = 0; e < mf; ++e) {
             const double tl = t * lg[e];
             const double rt = exp(tl);
@@ -236,8 +249,10 @@ KM_COLD int refine_jump(const double* G, const double* h, int m, int n_nodes, do
         }
     };
     const double gscale = 2.0 / (double)n_nodes;
-    // max |grad| over the free coefficients at the state (y, d)
-    auto worst_at = [&](const double* d) {
+    // does the stop test fire at step t?  (max |grad| over the free coefficients <= 0.01)
+    auto quiet_at = [&](double t) {
+        double y[KM_REFINE_MAXF], d[KM_REFINE_MAXF];
+        eval(t, y, d);
         double w = 0.0;
         for (int i = 0; i < mf; ++i) {
             double gi = 0.0;
@@ -245,7 +260,7 @@ KM_COLD int refine_jump(const double* G, const double* h, int m, int n_nodes, do
             const double ag = fabs(gi) * gscale;
             w = ag > w ? ag : w;
         }
-        return w;
+        return w <= 0.01;
     };
     // the three interval bounds on [tA, tB] from the end states; true = nothing but linear steps in between
     auto segment_clean = [&](const double* yA, const double* dA, const double* yB, const double* dB) {
@@ -279,50 +294,68 @@ KM_COLD int refine_jump(const double* G, const double* h, int m, int n_nodes, do
         }
         return loud;
     };
-    // [0, J] proven clean by adaptive bisection (explicit stack; at most ~64 leaves are ever needed: the terms
-    // are exponentials that have shed their fast modes during the 32 literal steps before the call)
-    auto stretch_clean = [&](double J) {
+    // [t0, t1] proven clean by adaptive bisection (explicit stack; the terms are exponentials that have shed their fast
+    // modes during the 32 literal steps before the call, so a handful of leaves is the rule)
+    auto stretch_clean = [&](double t0, double t1) {
         double st_lo[24], st_hi[24];
         int sp = 0, work = 0;
-        st_lo[0] = 0.0; st_hi[0] = J; sp = 1;
+        st_lo[0] = t0; st_hi[0] = t1; sp = 1;
         while (sp) {
             --sp;
             const double a = st_lo[sp], b = st_hi[sp];
             double yA[KM_REFINE_MAXF], dA[KM_REFINE_MAXF], yB[KM_REFINE_MAXF], dB[KM_REFINE_MAXF];
             eval(a, yA, dA); eval(b, yB, dB);
             if (segment_clean(yA, dA, yB, dB)) continue;
-            if (b - a <= 1.0 || sp + 2 > 24 || ++work > 256) return false;
+            if (b - a <= 1.0 || sp + 2 > 24 || ++work > 64) return false;
             const double mid = floor(0.5 * (a + b));
             st_lo[sp] = mid; st_hi[sp] = b; ++sp;
             st_lo[sp] = a; st_hi[sp] = mid; ++sp;
         }
         return true;
     };
-    double y[KM_REFINE_MAXF], d[KM_REFINE_MAXF];
-    // first step at which the stop test fires, by doubling then bisection (only a PREDICTION: whatever it says,
-    // the stretch actually jumped is proven clean below and the literal loop decides the stop)
-    double hi = 32.0, w = INFINITY;
-    while (hi < 16777216.0) { eval(hi, y, d); w = worst_at(d); if (w <= 0.01) break; hi *= 2.0; }
-    if (!(w <= 0.01)) return 0;
-    double lo = hi * 0.5;
-    if (hi == 32.0) lo = 0.0;
+    // (1) the first power-of-two multiple of 32 steps at which the stop test fires: 32 * 2^v, v = 0..18, a lane each.
+    // (Only a PREDICTION: whatever it says, the stretch actually jumped is proven clean below and the literal loop
+    // decides the stop.)
+    uint32_t quiet = 0;
+    for (int v = lane; v < 19; v += nl)
+        if (quiet_at(ldexp(32.0, v))) { quiet |= 1u << v; if (nl == 1) break; }
+    quiet = warp_or32(quiet);
+    if (!quiet) return 0;
+    const int v0 = ffs32(quiet) - 1;
+    double hi = ldexp(32.0, v0), lo = v0 ? 0.5 * hi : 0.0;
+    // (2) the first step in (lo, hi] at which it fires, 32 candidates per round
     while (hi - lo > 1.0) {
-        const double mid = floor(0.5 * (lo + hi));
-        eval(mid, y, d);
-        if (worst_at(d) <= 0.01) hi = mid; else lo = mid;
+        const double width = hi - lo;
+        const double stride = width <= 33.0 ? 1.0 : ceil(width / 33.0);
+        uint32_t fired = 0, asked = 0;
+        for (int v = lane; v < 32; v += nl) {
+            const double t = lo + stride * (double)(v + 1);
+            if (t < hi) { asked |= 1u << v; if (quiet_at(t)) fired |= 1u << v; }
+        }
+        fired = warp_or32(fired); asked = warp_or32(asked);
+        if (fired) { const int v = ffs32(fired) - 1; hi = lo + stride * (double)(v + 1); lo = hi - stride; }
+        else lo = lo + stride * (double)popc32(asked);
     }
+    // (3) the longest stretch [0, J], J = hi - 8, hi/2 - 4, ... that is provably clean: 32 sub-stretches side by side
     double J = hi - 8.0;
-    for (; J >= 32.0; J = floor(0.5 * J))
-        if (stretch_clean(J)) break;
+    for (; J >= 32.0; J = floor(0.5 * J)) {
+        bool clean = true;
+        for (int v = lane; v < 32 && clean; v += nl) {
+            const double a = floor(J * (double)v / 32.0), b = v == 31 ? J : floor(J * (double)(v + 1) / 32.0);
+            if (b > a) clean = stretch_clean(a, b);
+        }
+        if (!warp_or32(clean ? 0u : 1u)) break;
+    }
 #if defined(KM_HOST_EMU) && defined(KM_RJ_DEBUG)
-    fprintf(stderr, "refine_jump: mf=%d predicted stop %.0f, proven stretch %.0f\n", mf, hi, J);
+    fprintf(stderr, "refine_jump: mf=%d predicted stop %.0f, proven stretch %.0f, %d closed-form evaluations\n", mf, hi, J, n_eval);
 #endif
     if (J < 32.0) return 0;
+    double y[KM_REFINE_MAXF], d[KM_REFINE_MAXF];
     eval(J, y, d);
     for (int i = 0; i < mf; ++i) {
         double x = 0.0;
         for (int e = 0; e < mf; ++e) x += V[i * mf + e] * y[e];
-        coef[F[i]] = x;
+        coef_new[F[i]] = x;
     }
     return (int)J;
 }
@@ -330,33 +363,231 @@ KM_COLD int refine_jump(const double* G, const double* h, int m, int n_nodes, do
 // refine_coef (PathQuant.py:120-136) + get_ratio (:144-149) on the normal equations: fixed step 0.1,
 // gradient / n_nodes, stop at max|grad| <= 0.01 -- literal steps, with refine_jump across the long
 // linear stretches.  Returns the number of iterations the literal loop would have run.
-KM_HD int refine_and_ratio(const double* G, const double* h, int m, int n_nodes, double* coef, double* rvaf, double* grad,
+// M columns, known at compile time: the whole state lives in registers (in shared memory one step of a 3-column
+// problem was a 1,650-cycle chain of dependent loads, stores and divisions; in registers the rows are independent).
+// WARP-COLLECTIVE like refine_jump: every lane computes the same thing, which costs nothing and lets the jump use them.
+// G_in / h_in must stay valid and unchanged during the call.
+template <int M>
+KM_HD int refine_and_ratio(int lane, int nl, const double* G_in, const double* h_in, int n_nodes, double* coef_io, double* rvaf,
                             bool allow_jump) {
-    for (int a = 0; a < m; ++a) if (coef[a] < 0.0) coef[a] = 0.0;
+    double G[M * M], h[M], c[M], grad[M];
+#pragma unroll
+    for (int i = 0; i < M * M; ++i) G[i] = G_in[i];
+#pragma unroll
+    for (int a = 0; a < M; ++a) { h[a] = h_in[a]; c[a] = coef_io[a] < 0.0 ? 0.0 : coef_io[a]; }
     double worst = INFINITY;
     int iters = 0, since = 0;
     while (worst > 0.01) {
-        for (int a = 0; a < m; ++a) {
+#pragma unroll
+        for (int a = 0; a < M; ++a) {
             double fit = 0.0;
-            for (int b = 0; b < m; ++b) fit += G[a * m + b] * coef[b];
+#pragma unroll
+            for (int b = 0; b < M; ++b) fit += G[a * M + b] * c[b];
             grad[a] = 2.0 * (h[a] - fit) / (double)n_nodes;
         }
         worst = 0.0;
-        for (int a = 0; a < m; ++a) {
-            coef[a] += 0.1 * grad[a];
-            if (coef[a] < 0.0) { grad[a] = 0.0; coef[a] = 0.0; }
+#pragma unroll
+        for (int a = 0; a < M; ++a) {
+            c[a] += 0.1 * grad[a];
+            if (c[a] < 0.0) { grad[a] = 0.0; c[a] = 0.0; }
             const double ag = fabs(grad[a]);
             worst = ag > worst ? ag : worst;     // NaN never enters: counts are finite
         }
         if (++iters > 10000000) { iters = -1; break; }
         if (allow_jump && ++since >= 32 && worst > 0.01) {
-            iters += refine_jump(G, h, m, n_nodes, coef);
+#if KM_DEVICE_BUILD && defined(KM_PHASE_TIMERS)
+            const long long j0 = clock64();
+#endif
+            double cur[M], nxt[M];
+#pragma unroll
+            for (int a = 0; a < M; ++a) cur[a] = c[a];
+            const int J = refine_jump(lane, nl, G_in, h_in, M, n_nodes, cur, nxt);
+            if (J) {
+#pragma unroll
+                for (int a = 0; a < M; ++a) c[a] = nxt[a];
+            }
+            iters += J;
+#if KM_DEVICE_BUILD && defined(KM_PHASE_TIMERS)
+            if (lane == 0) atomicAdd(&km_phase_cycles[56], (unsigned long long)(clock64() - j0));
+#endif
             since = 0;
         }
     }
-    double cmax = coef[0], csum = 0.0;
-    for (int a = 0; a < m; ++a) { cmax = coef[a] > cmax ? coef[a] : cmax; csum += coef[a]; }
-    for (int a = 0; a < m; ++a) rvaf[a] = cmax == 0.0 ? coef[a] : coef[a] / csum;
+    double cmax = c[0], csum = 0.0;
+#pragma unroll
+    for (int a = 0; a < M; ++a) { cmax = c[a] > cmax ? c[a] : cmax; csum += c[a]; }
+#pragma unroll
+    for (int a = 0; a < M; ++a) { coef_io[a] = c[a]; rvaf[a] = cmax == 0.0 ? c[a] : c[a] / csum; }
+    return iters;
+}
+
+// The same for any number of columns, state in memory (clusters of four variants and more): lane 0 iterates, the warp
+// meets for the jumps.  coef / rvaf / grad: m doubles each, written by lane 0 only.
+KM_HD int refine_and_ratio_any(int lane, int nl, const double* G, const double* h, int m, int n_nodes, double* coef, double* rvaf,
+                                double* grad, bool allow_jump) {
+    if (lane == 0) for (int a = 0; a < m; ++a) if (coef[a] < 0.0) coef[a] = 0.0;
+    int iters = 0;
+    bool more = true;
+    while (more) {
+        // literal steps until the stop, or until 32 of them have passed without it
+        int go = 0;                                           // 0: stopped, 1: try a jump, 2: watchdog
+        if (lane == 0) {
+            double worst = INFINITY;
+            int since = 0;
+            while (worst > 0.01) {
+                for (int a = 0; a < m; ++a) {
+                    double fit = 0.0;
+                    for (int b = 0; b < m; ++b) fit += G[a * m + b] * coef[b];
+                    grad[a] = 2.0 * (h[a] - fit) / (double)n_nodes;
+                }
+                worst = 0.0;
+                for (int a = 0; a < m; ++a) {
+                    coef[a] += 0.1 * grad[a];
+                    if (coef[a] < 0.0) { grad[a] = 0.0; coef[a] = 0.0; }
+                    const double ag = fabs(grad[a]);
+                    worst = ag > worst ? ag : worst;
+                }
+                if (++iters > 10000000) { go = 2; break; }
+                if (allow_jump && m <= 2 * KM_REFINE_MAXF && ++since >= 32 && worst > 0.01) { go = 1; break; }
+            }
+        }
+#if KM_DEVICE_BUILD
+        __syncwarp();
+#endif
+        go = warp_shfl32(go, 0);
+        iters = warp_shfl32(iters, 0);
+        if (go == 2) { iters = -1; break; }
+        more = go == 1;
+        if (more) {
+            double cur[2 * KM_REFINE_MAXF], nxt[2 * KM_REFINE_MAXF];
+            for (int a = 0; a < m; ++a) cur[a] = coef[a];
+            const int J = refine_jump(lane, nl, G, h, m, n_nodes, cur, nxt);
+#if KM_DEVICE_BUILD
+            __syncwarp();
+#endif
+            if (J && lane == 0) for (int a = 0; a < m; ++a) coef[a] = nxt[a];
+            iters += J;
+        }
+    }
+    if (lane == 0) {
+        double cmax = coef[0], csum = 0.0;
+        for (int a = 0; a < m; ++a) { cmax = coef[a] > cmax ? coef[a] : cmax; csum += coef[a]; }
+        for (int a = 0; a < m; ++a) rvaf[a] = cmax == 0.0 ? coef[a] : coef[a] / csum;
+    }
+#if KM_DEVICE_BUILD
+    __syncwarp();
+#endif
+    return iters;
+}
+
+// a + b exactly as a double-double (hi, lo)
+KM_HD void two_sum(double a, double b, double* hi, double* lo) {
+    const double s = a + b, bb = s - a;
+    *hi = s; *lo = (a - (s - bb)) + (b - bb);
+}
+// sum_j c_j * x_j of three products to (almost) the last bit: products and partial sums carry their rounding errors along
+KM_HD double dot3_compensated(const double* c, const double* x) {
+    double hi = 0.0, lo = 0.0;
+    for (int j = 0; j < 3; ++j) {
+        const double p = c[j] * x[j];
+        const double e = fma(c[j], x[j], -p);
+        double s, r;
+        two_sum(hi, p, &s, &r);
+        hi = s; lo += r + e;
+    }
+    return hi + lo;
+}
+
+// The serial part of a wide cluster's quantification, by warp 0 of the CTA (all its lanes call): G and h from the exact
+// integer sums, the minimum-norm solution, refine_coef, get_ratio.  coef / rvaf (m doubles each, shared memory) are
+// written by lane 0; returns the iteration count on every lane.  Not inlined: it runs for a handful of targets.
+KM_COLD int solve_wide(int lane, int nl, const GraphScratch& S, int m, int n_nodes, double* coef, double* rvaf, bool allow_jump) {
+    const unsigned long long* acc = S.acc;
+    double* G = S.G;
+    double* h = S.vec;   // [m]
+    if (lane == 0) {
+        for (int a = 0; a < m; ++a) {
+            h[a] = (double)acc[m * m + a];
+            for (int b = 0; b <= a; ++b) G[a * m + b] = G[b * m + a] = (double)acc[a * m + b];
+        }
+    }
+#if KM_DEVICE_BUILD
+    __syncwarp();
+#endif
+    PhaseTimer st;
+    bool solved = false;
+    if (m == 3) {
+        // Three columns (a cluster of two variants, the common wide case): G is an exact integer matrix, so its rank is
+        // decided exactly; at full rank the solution is unique and the adjugate gives it from exact integer cofactors
+        // (no eigen-decomposition: 33,000 cycles of one lane's square roots and divisions otherwise).
+        long long a[9];
+        bool small = true;
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) {
+                const unsigned long long v = acc[(i >= j ? i : j) * 3 + (i >= j ? j : i)];
+                small &= v < (1ull << 20);
+                a[i * 3 + j] = (long long)v;
+            }
+        if (small) {
+            long long C[9];                       // cofactors (the matrix is symmetric, so is its adjugate)
+            C[0] = a[4] * a[8] - a[5] * a[7]; C[1] = a[5] * a[6] - a[3] * a[8]; C[2] = a[3] * a[7] - a[4] * a[6];
+            C[3] = C[1];                      C[4] = a[0] * a[8] - a[2] * a[6]; C[5] = a[1] * a[6] - a[0] * a[7];
+            C[6] = C[2];                      C[7] = C[5];                      C[8] = a[0] * a[4] - a[1] * a[3];
+            const long long det = a[0] * C[0] + a[1] * C[1] + a[2] * C[2];
+            if (det != 0) {
+                const double hh[3] = {(double)acc[9], (double)acc[10], (double)acc[11]};
+                double c3[3];
+                for (int i = 0; i < 3; ++i) {
+                    const double ci[3] = {(double)C[i * 3], (double)C[i * 3 + 1], (double)C[i * 3 + 2]};
+                    c3[i] = dot3_compensated(ci, hh) / (double)det;
+                }
+                if (lane == 0) { coef[0] = c3[0]; coef[1] = c3[1]; coef[2] = c3[2]; }
+                solved = true;
+            }
+        }
+    }
+    if (!solved) {
+        if (lane == 0) {
+            double* A = S.V;                 // working copy for the eigen solver
+            double* V = S.V + m * m;         // needs 2*m*m doubles: S.V is sized for that
+            for (int i = 0; i < m * m; ++i) A[i] = G[i];
+            jacobi_eigen(A, V, m);
+            double lmax = 0.0;
+            for (int i = 0; i < m; ++i) lmax = A[i * m + i] > lmax ? A[i * m + i] : lmax;
+            // singular values below eps*max(M,N)*s_max are dropped by lstsq(rcond=None); in
+            // eigenvalue terms that is far below FP64 resolution of G, so the cut is placed where
+            // an exactly rank-deficient integer G leaves its rounding noise.
+            const double cut = lmax * 1e-11;
+            for (int a = 0; a < m; ++a) coef[a] = 0.0;
+            for (int e = 0; e < m; ++e) {
+                const double lam = A[e * m + e];
+                if (!(lam > cut)) continue;
+                double proj = 0.0;
+                for (int a = 0; a < m; ++a) proj += V[a * m + e] * h[a];
+                proj /= lam;
+                for (int a = 0; a < m; ++a) coef[a] += V[a * m + e] * proj;
+            }
+        }
+    }
+#if KM_DEVICE_BUILD
+    __syncwarp();
+#endif
+    st.mark_warp0(54, lane);
+    int iters;
+    if (m == 3 || m == 4) {
+        // state in registers, every lane the same
+        double c[4], r[4];
+        for (int a = 0; a < m; ++a) c[a] = coef[a];
+#if KM_DEVICE_BUILD
+        __syncwarp();
+#endif
+        iters = m == 3 ? refine_and_ratio<3>(lane, nl, G, h, n_nodes, c, r, allow_jump)
+                       : refine_and_ratio<4>(lane, nl, G, h, n_nodes, c, r, allow_jump);
+        if (lane == 0) for (int a = 0; a < m; ++a) { coef[a] = c[a]; rvaf[a] = r[a]; }
+    } else {
+        iters = refine_and_ratio_any(lane, nl, G, h, m, n_nodes, coef, rvaf, S.vec + 2 * S.max_cols, allow_jump);
+    }
+    st.mark_warp0(55, lane);
     return iters;
 }
 
@@ -367,6 +598,7 @@ template <class Ctx>
 KM_HD int solve_columns(const Ctx& ctx, const GraphScratch& S, const uint32_t* counts, int n_nodes,
                         const PathView* cols, int m, double* coef, double* rvaf, int* sh, bool allow_jump) {
     const int tid = ctx.tid(), nt = ctx.nt();
+    PhaseTimer st;                     // (measurement builds: 53 Gram sums, 54 eigen solve, 55 refine)
     unsigned long long* acc = S.acc;   // [m*m + m] exact integer accumulators
     for (int i = tid; i < m * m + m; i += nt) acc[i] = 0ull;
     ctx.sync();
@@ -402,54 +634,12 @@ KM_HD int solve_columns(const Ctx& ctx, const GraphScratch& S, const uint32_t* c
             ctx.sync();
         }
     }
-    if (tid == 0 && m == 2) {
-        // 2 x 2 (every vs_ref row and every single-variant cluster): G is an exact integer matrix,
-        // so its rank is decided exactly, and the minimum-norm solution (what lstsq returns,
-        // PathQuant.py:116) has a closed form in either case.
-        double G[4], h[2], c[2], r[2], grad[2];
-        G[0] = (double)acc[0]; G[1] = G[2] = (double)acc[2]; G[3] = (double)acc[3];
-        h[0] = (double)acc[4]; h[1] = (double)acc[5];
-        const long long det = (long long)acc[0] * (long long)acc[3] - (long long)acc[2] * (long long)acc[2];
-        if (det != 0) {
-            c[0] = det2(h[0], h[1], G[1], G[3]) / (double)det;       // Cramer
-            c[1] = det2(G[0], G[1], h[0], h[1]) / (double)det;
-        } else if (acc[0] + acc[3] == 0ull) {
-            c[0] = c[1] = 0.0;
-        } else {
-            // rank 1: G = lambda u u^T, lambda = trace; any non-zero column v of G is parallel to u
-            const double v0 = acc[0] >= acc[3] ? G[0] : G[1], v1 = acc[0] >= acc[3] ? G[1] : G[3];
-            const double s = (v0 * h[0] + v1 * h[1]) / ((v0 * v0 + v1 * v1) * (G[0] + G[3]));
-            c[0] = v0 * s; c[1] = v1 * s;
-        }
-        sh[4] = refine_and_ratio(G, h, 2, n_nodes, c, r, grad, allow_jump);
-        coef[0] = c[0]; coef[1] = c[1]; rvaf[0] = r[0]; rvaf[1] = r[1];
-    } else if (tid == 0) {
-        double* G = S.G;
-        double* h = S.vec;   // [m]
-        for (int a = 0; a < m; ++a) {
-            h[a] = (double)acc[m * m + a];
-            for (int b = 0; b <= a; ++b) G[a * m + b] = G[b * m + a] = (double)acc[a * m + b];
-        }
-        double* A = S.V;                 // working copy for the eigen solver
-        double* V = S.V + m * m;         // needs 2*m*m doubles: S.V is sized for that
-        for (int i = 0; i < m * m; ++i) A[i] = G[i];
-        jacobi_eigen(A, V, m);
-        double lmax = 0.0;
-        for (int i = 0; i < m; ++i) lmax = A[i * m + i] > lmax ? A[i * m + i] : lmax;
-        // singular values below eps*max(M,N)*s_max are dropped by lstsq(rcond=None); in
-        // eigenvalue terms that is far below FP64 resolution of G, so the cut is placed where
-        // an exactly rank-deficient integer G leaves its rounding noise.
-        const double cut = lmax * 1e-11;
-        for (int a = 0; a < m; ++a) coef[a] = 0.0;
-        for (int e = 0; e < m; ++e) {
-            const double lam = A[e * m + e];
-            if (!(lam > cut)) continue;
-            double proj = 0.0;
-            for (int a = 0; a < m; ++a) proj += V[a * m + e] * h[a];
-            proj /= lam;
-            for (int a = 0; a < m; ++a) coef[a] += V[a * m + e] * proj;
-        }
-        sh[4] = refine_and_ratio(G, h, m, n_nodes, coef, rvaf, S.vec + 2 * S.max_cols, allow_jump);
+    st.mark(53);
+    // the serial part, by the warp that holds thread 0 (solve_wide): exact solve, refine_coef with its jumps, ratios
+    if (warp_index(ctx) == 0) {
+        const int nl = nt < 32 ? nt : 32;
+        const int iters = solve_wide(tid & 31, nl, S, m, n_nodes, coef, rvaf, allow_jump);
+        if ((tid & 31) == 0) sh[4] = iters;
     }
     ctx.sync();
     return sh[4];
@@ -539,13 +729,15 @@ KM_HD Quant2 quant_pair(const WCtx& wctx, const GraphScratch& S, const uint32_t*
         h_p = warp_sum64(h_p); h_r = warp_sum64(h_r); g_pr = warp_sum64(g_pr); g_pp = warp_sum64(g_pp);
     }
     mn = warp_min32(mn);
+    // every lane solves (the sums are broadcast): redundant lanes cost nothing, and a long refinement can use them
+    // (refine_jump evaluates its closed form at 32 steps at once)
+    h_p = warp_bcast64(h_p); h_r = warp_bcast64(h_r); g_pr = warp_bcast64(g_pr); g_pp = warp_bcast64(g_pp);
     Quant2 q;
-    q.iters = 0; q.min_cov = 0; q.coef[0] = q.coef[1] = q.rvaf[0] = q.rvaf[1] = 0.0;
-    if (lane == 0) {
+    {
         // exact integer normal equations in the reference's column order
         const unsigned long long g_rr = (unsigned long long)range.len;
         const unsigned long long a00 = path_first ? g_pp : g_rr, a11 = path_first ? g_rr : g_pp, a01 = g_pr;
-        double G[4], h[2], grad[2];
+        double G[4], h[2];
         G[0] = (double)a00; G[1] = G[2] = (double)a01; G[3] = (double)a11;
         h[0] = (double)(path_first ? h_p : h_r); h[1] = (double)(path_first ? h_r : h_p);
         const long long det = (long long)a00 * (long long)a11 - (long long)a01 * (long long)a01;
@@ -562,7 +754,7 @@ KM_HD Quant2 quant_pair(const WCtx& wctx, const GraphScratch& S, const uint32_t*
             const double sc = (v0 * h[0] + v1 * h[1]) / ((v0 * v0 + v1 * v1) * (G[0] + G[3]));
             c[0] = v0 * sc; c[1] = v1 * sc;
         }
-        q.iters = refine_and_ratio(G, h, 2, n_nodes, c, q.rvaf, grad, allow_jump);
+        q.iters = refine_and_ratio<2>(lane, nl, G, h, n_nodes, c, q.rvaf, allow_jump);
         q.min_cov = (int64_t)mn;
     }
     return q;

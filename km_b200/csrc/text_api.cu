@@ -299,11 +299,11 @@ struct Latch {
 // building overlap.  The text equals km_find_batch + km_result_format_all.
 // KM_TRACE=1: host-clock timeline of km_find_text on stderr (measurement aid)
 struct Trace {
-    bool on;
+    bool on, device;         // device (KM_TRACE=2): per-phase CUDA events on every lane as well (and no graph replay)
     std::chrono::steady_clock::time_point t0;
     std::mutex m;
     std::vector<std::tuple<const char*, int, double>> ev;
-    Trace() : on(getenv("KM_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    Trace() : on(getenv("KM_TRACE") != nullptr), device(on && atoi(getenv("KM_TRACE")) >= 2), t0(std::chrono::steady_clock::now()) {}
     void mark(const char* what, int sub = -1) {
         if (!on) return;
         const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -427,7 +427,9 @@ extern "C" int km_find_text(km_table* t, const char* seqs, const int64_t* offset
                     // six do at once.  When the lane saw the very same layout in the previous call, the sequence is captured
                     // into a CUDA graph (once) and from then on replayed with ONE call.
                     km_table::Lane* lane = t->lanes[(size_t)lane_ix].get();
-                    static const bool use_graph = !getenv("KM_NO_GRAPH");
+                    static const bool graphs_on = !getenv("KM_NO_GRAPH");
+                    const bool use_graph = graphs_on && !tr.device;
+                    p->trace_events = tr.device;
                     const std::string key = use_graph ? plan_graph_key(p) : std::string();
                     int rc = 0;
                     bool done = false;
@@ -493,6 +495,7 @@ extern "C" int km_find_text(km_table* t, const char* seqs, const int64_t* offset
                     }
                     pr->bytes_d2h += (unsigned long long)len;
                 }
+                if (tr.device) cudaEventRecord(p->ev[5], p->stream);
                 tr.mark("text placed", c);
                 plan_return_vecs(p, t->lanes[(size_t)lane_ix].get());
                 latch.done();
@@ -501,6 +504,26 @@ extern "C" int km_find_text(km_table* t, const char* seqs, const int64_t* offset
         tr.mark("all submitted");
         latch.wait();
         tr.mark("all placed");
+        if (tr.device) {
+            // device timeline: every lane's phase events against the earliest upload
+            cudaDeviceSynchronize();
+            static const char* what[] = {"upload", "probe", "walks", "graph passes", "format", "text copied"};
+            static const int evi[] = {0, 1, 6, 2, 3, 4, 5};
+            int first = 0;
+            for (int c = 1; c < n_sub; ++c) {
+                float ms = 0.f;
+                if (cudaEventElapsedTime(&ms, t->lanes[(size_t)first]->ev[0], t->lanes[(size_t)c]->ev[0]) == cudaSuccess && ms < 0.f) first = c;
+            }
+            for (int c = 0; c < n_sub; ++c) {
+                fprintf(stderr, "[km_trace] device, sub-batch %d:", c);
+                for (int j = 0; j < 7; ++j) {
+                    float ms = 0.f;
+                    if (cudaEventElapsedTime(&ms, t->lanes[(size_t)first]->ev[0], t->lanes[(size_t)c]->ev[evi[j]]) != cudaSuccess) { cudaGetLastError(); ms = -1.f; }
+                    if (j == 0) fprintf(stderr, " start %.3f", ms); else fprintf(stderr, " | %s done %.3f", what[j - 1], ms);
+                }
+                fprintf(stderr, " ms\n");
+            }
+        }
         for (int c = 0; c < n_sub; ++c)
             if (rcs[(size_t)c]) {
                 const int rc = rcs[(size_t)c];

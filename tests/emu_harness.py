@@ -12,7 +12,7 @@ from km_b200._lib import ROW_DTYPE
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "emu", "km_emu.cpp")
-SO = os.path.join(HERE, "emu", "libkm_emu_test_asan.so" if os.environ.get("KM_EMU_SANITIZE") else "libkm_emu_test.so")
+SO = os.environ.get("KM_EMU_SO") or os.path.join(HERE, "emu", "libkm_emu_test_asan.so" if os.environ.get("KM_EMU_SANITIZE") else "libkm_emu_test.so")
 CSRC = os.path.join(os.path.dirname(HERE), "km_b200", "csrc")
 _L = None
 

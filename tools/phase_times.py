@@ -1,5 +1,5 @@
 """Per-phase SM cycles of the graph pass (build with KM_PHASE_TIMERS=1).  Run on a GPU box:
-    KM_PHASE_TIMERS=1 python tools/phase_times.py [n_targets]"""
+    KM_PHASE_TIMERS=1 python tools/phase_times.py [n_targets]          (KM_ONLY=i,j,...: only those targets of the panel)"""
 import ctypes
 import os
 import sys
@@ -17,6 +17,10 @@ NAMES = {0: "numbering", 1: "adjacency", 2: "shortest trees", 3: "strip chain", 
          13: "cluster rows tail", 14: "solve_columns", 15: "min_count"}
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 10000
 panel = synth.make_panel(n, seed=synth.PANEL_SEED)
+only = [int(x) for x in os.environ.get("KM_ONLY", "").split(",") if x]      # KM_ONLY=794: the phases of that one target
+if only:
+    panel.targets = [panel.targets[i] for i in only]
+    n = len(only)
 t = engine.Table.create(capacity=50_000_000 + len(panel.keys))
 t.build_synthetic(synth.TABLE_SEED, 50_000_000)
 t.insert(panel.keys, panel.counts)
@@ -46,7 +50,8 @@ for i in range(32, 40):
 BUB = {40: "bubble: numbering", 41: "bubble: k-mer map", 42: "bubble: edges", 43: "bubble: test + chain", 44: "bubble: alloc",
        45: "bubble: paths + spelling", 46: "bubble: rows", 48: "  cluster row: quant_pair", 49: "  cluster row: diff_paths",
        50: "  cluster row: write_row", 51: "  vs_ref row: quant_pair", 52: "  vs_ref row: write_row"}
-for i in range(40, 53):
+BUB.update({53: "  wide cluster: Gram sums", 54: "  wide cluster: eigen solve", 55: "  wide cluster: refine (all)", 56: "  refine_jump calls (every row)"})
+for i in range(40, 57):
     if buf[i]:
         print("%2d %-28s %8.1f cycles/target" % (i, BUB[i], buf[i] / n))
 print("simple graphs:", plan.fetch(want_graph=False).timing.get("simple_graphs"))

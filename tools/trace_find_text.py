@@ -4,7 +4,7 @@ import os
 import sys
 import time
 
-os.environ["KM_TRACE"] = "1"
+os.environ.setdefault("KM_TRACE", "1")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from km_b200 import engine, synth   # noqa: E402
 
