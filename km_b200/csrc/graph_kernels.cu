@@ -36,7 +36,6 @@ struct KernelSpan { __device__ __forceinline__ explicit KernelSpan(int) {} };
 // larger ones (the pass is latency-bound: resident CTAs are throughput).  The GENERAL pass uses
 // per-CTA scratch in HBM and takes the rest, plus any target a shared-memory pass deferred
 // (KM_ST_RETRY_LARGE).
-#define KM_ST_FATAL (KM_ST_BAD_BASE | KM_ST_DUP_KMER | KM_ST_NODE_OVERFLOW | KM_ST_NODE_LIMIT | KM_ST_TOO_SHORT)
 
 // NODES = node capacity of a shared-memory class, 0 = the general pass
 // Work lists of the graph passes: every target whose walk succeeded goes to the smallest size class its graph fits, each
@@ -51,27 +50,30 @@ __global__ void __launch_bounds__(1024) km_schedule_kernel(WalkView W, ResultVie
     const int n = W.n_targets;
     for (int i = threadIdx.x; i < 5 * 64; i += blockDim.x) (&hist[0][0])[i] = 0;
     __syncthreads();
-    // list | bin << 3, or 0xFFFF for a target without a graph
+    // list | bin << 3, or 0xFFFF for a target without a graph, from the walk's code (walk.h sched_code_of: class, "the walk
+    // branched", size bin).  The shared-memory walk leaves the code of every target it finishes; for the others (the general
+    // walk, malformed targets) the scheduler reads the target's state itself.
     auto classify = [&](int t) -> uint32_t {
-        const uint32_t st = W.status[t];
-        const int cap = (int)(W.node_off[t + 1] - W.node_off[t]);
-        const int nn = W.n_nodes[t];
-        const int kept2 = W.n_kept[t] + 2;
-        if (st & KM_ST_FATAL) return 0xFFFFu;
-        const int n_all = nn < cap ? nn : cap;
-        int b = 63 - (kept2 >> 3);
-        b = b < 0 ? 0 : b;                                            // bin 0 = the largest graphs
-        const int lean = bubbles && !(st & KM_ST_BRANCHED) ? 3 : 0;
-        int c = 2;
-        if (n_all <= KM_TINY_NODES - 2 && kept2 <= KM_TINY_NODES) c = 0 + lean;
-        else if (n_all <= KM_SMALL_NODES - 2 && kept2 <= KM_SMALL_NODES) c = 1 + lean;
-        return (uint32_t)(c | (b << 3));
+        uint32_t code = W.sched_code[t];
+        if (code == 0) {
+            const uint32_t st = W.status[t];
+            const int cap = (int)(W.node_off[t + 1] - W.node_off[t]);
+            const int nn = W.n_nodes[t];
+            code = sched_code_of(st, nn < cap ? nn : cap, W.n_kept[t], KM_TINY_NODES, KM_SMALL_NODES) + 1u;
+            if (st & KM_ST_BRANCHED) W.status[t] = st & ~KM_ST_BRANCHED;      // the walk's hint is internal: the host never sees it
+        }
+        code -= 1u;
+        if (code == 0xFFFFu) return code;
+        const int c = (int)(code & 3u);
+        const int lean = bubbles && !(code & 4u) && c < 2 ? 3 : 0;
+        return (uint32_t)(c + lean) | (code & ~7u);
     };
     // pass 1: the loads of a thread's targets are independent of one another (the histogram comes after)
 #pragma unroll 4
     for (int t = threadIdx.x; t < n; t += blockDim.x) {
         const uint32_t code = classify(t);
         if (t < KM_SCHED_CACHE) code_s[t] = (uint16_t)code;
+        else W.sched_code[t] = (uint16_t)(code == 0xFFFFu ? 0xFFFFu : 0x8000u | code);      // (beyond the cache: final list kept for pass 2)
         if (code == 0xFFFFu) { R.t_n[t] = 0; R.t_n_paths[t] = 0; R.t_path_first[t] = 0; R.t_n_rows[t] = 0; R.t_row_first[t] = 0; }
         else atomicAdd(&hist[code & 7u][code >> 3], 1);
     }
@@ -83,12 +85,11 @@ __global__ void __launch_bounds__(1024) km_schedule_kernel(WalkView W, ResultVie
     } else if (threadIdx.x < 8) R.sched_count[threadIdx.x] = 0;      // [5], [6]: cursors of the bubble pass
     __syncthreads();
     for (int t = threadIdx.x; t < n; t += blockDim.x) {
-        const uint32_t code = t < KM_SCHED_CACHE ? (uint32_t)code_s[t] : classify(t);
+        uint32_t code;
+        if (t < KM_SCHED_CACHE) code = (uint32_t)code_s[t];
+        else { code = (uint32_t)W.sched_code[t]; code = code == 0xFFFFu ? code : code & 0x7FFFu; }
         if (code != 0xFFFFu) R.sched_order[(size_t)(code & 7u) * n + atomicAdd(&start[code & 7u][code >> 3], 1)] = t;
     }
-    // the scheduler's hint is internal: the host never sees it
-    for (int t = threadIdx.x; t < n; t += blockDim.x)
-        if (W.status[t] & KM_ST_BRANCHED) W.status[t] &= ~KM_ST_BRANCHED;
 }
 
 // The simple bubbles (graph_bubble.h): a small group of threads per target -- KM_BUBBLE_THREADS = 32: one warp, several

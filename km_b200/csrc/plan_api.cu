@@ -57,6 +57,7 @@ int plan_layout(km_plan* p) {
     acc(8 * n_hash); acc(4 * n_hash); acc(4 * n_hash); acc(n_hash);                // visited sets
     acc(4 * n); acc(4 * n); acc(4 * n); acc(8 * n);                                // n_nodes n_kept status lookups
     for (int i = 0; i < 5; ++i) acc(4 * n);                                        // per-target result ints
+    acc(2 * (size_t)n);                                                            // the walk's codes for the scheduler
     acc(8 * n_node); acc(4 * n_node);                                              // canonical nodes
     acc(8 * (size_t)path_cap); acc(4 * (size_t)path_cap); acc(8 * (size_t)path_cap); acc(4 * (size_t)pool_cap);
     acc(sizeof(Row) * (size_t)row_cap); acc((size_t)seq_cap); acc(64); acc(20 * (size_t)n + 64);
@@ -105,6 +106,9 @@ int plan_layout(km_plan* p) {
     R.used = A.take<unsigned long long>(8);     // [0..3] pool cursors, [4..6] work counters of the three graph passes
     p->F.flags = A.take<uint32_t>(16);          // [0] flags, [2..3] total bytes of text (64 bit)
     p->state_bytes = (size_t)(A.take<char>(0) - p->state0);
+    // (cleared with the state, but not part of what comes back: the memset covers it, the copy does not)
+    W.sched_code = A.take<uint16_t>(n);
+    p->clear_bytes = (size_t)(A.take<char>(0) - p->state0);
     R.out_kmer = A.take<uint64_t>(n_node); R.out_count = A.take<uint32_t>(n_node);
     R.path_off = A.take<int64_t>(path_cap); R.path_len = A.take<int32_t>(path_cap);
     p->d_path_seq_off = A.take<int64_t>(path_cap);
@@ -184,7 +188,7 @@ int plan_launch(km_plan* p, cudaStream_t s) {
     if (p->n == 0) return 0;
     const bool timed = !p->fmt || p->trace_events;          // km_find_text enqueues as little as it can: no per-phase events
     if (timed) CU(cudaEventRecord(p->ev[1], s));
-    CU(cudaMemsetAsync(p->state0, 0, p->state_bytes, s));
+    CU(cudaMemsetAsync(p->state0, 0, p->clear_bytes, s));
     CU(km_launch_ref_probe(t->view(), p->W, p->P, s));
     if (timed) CU(cudaEventRecord(p->ev[6], s));
     CU(km_launch_walks(t->view(), p->W, p->P, s));

@@ -3,7 +3,7 @@
 //
 //   diff_paths      MutationFinder.diff_path_without_overlap   (MutationFinder.py:321-373)
 //   classify        MutationFinder.get_name                     (:429-488)
-//   solve_columns   PathQuant.__init__/compute_coef/refine_coef/get_ratio (PathQuant.py:94-149)
+//   gram_columns, solve_wide, quant_pair   PathQuant.__init__/compute_coef/refine_coef/get_ratio (PathQuant.py:94-149)
 //   emit_rows       quantify_paths (:613-648), _find_clusters (:651-723),
 //                   quantify_clusters (:749-811)
 //
@@ -498,6 +498,62 @@ KM_HD double dot3_compensated(const double* c, const double* x) {
     return hi + lo;
 }
 
+// The minimum-norm solution of the 3 x 3 normal equations G x = h from their exact integer sums (acc: lower triangle of G at
+// [a * 3 + b], b <= a; h at [9..11]).  G = A^T A is positive semi-definite and h = A^T b lies in its range.
+//   rank 3: x = adj(G) h / det(G), cofactors and determinant exact integers
+//   rank 2: adj(G) = alpha n n^T with n spanning the null space (any non-zero column of the cofactor matrix); a particular
+//           solution from the largest principal 2 x 2 minor (third unknown 0), minus its component along n
+//   rank 1: G = lambda u u^T, lambda = trace; x = v (v.h) / (|v|^2 lambda) for any non-zero column v of G
+// false: entries too large for exact 64-bit cofactors (the caller falls back to the eigen-decomposition).
+KM_HD bool solve3_exact(const unsigned long long* acc, double* x) {
+    long long a[9];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            const unsigned long long v = acc[(i >= j ? i : j) * 3 + (i >= j ? j : i)];
+            if (v >= (1ull << 20)) return false;
+            a[i * 3 + j] = (long long)v;
+        }
+    const double hh[3] = {(double)acc[9], (double)acc[10], (double)acc[11]};
+    long long C[9];                       // cofactors (the matrix is symmetric, so is its adjugate)
+    C[0] = a[4] * a[8] - a[5] * a[7]; C[1] = a[5] * a[6] - a[3] * a[8]; C[2] = a[3] * a[7] - a[4] * a[6];
+    C[3] = C[1];                      C[4] = a[0] * a[8] - a[2] * a[6]; C[5] = a[1] * a[6] - a[0] * a[7];
+    C[6] = C[2];                      C[7] = C[5];                      C[8] = a[0] * a[4] - a[1] * a[3];
+    const long long det = a[0] * C[0] + a[1] * C[1] + a[2] * C[2];
+    if (det != 0) {
+        for (int i = 0; i < 3; ++i) {
+            const double ci[3] = {(double)C[i * 3], (double)C[i * 3 + 1], (double)C[i * 3 + 2]};
+            x[i] = dot3_compensated(ci, hh) / (double)det;
+        }
+        return true;
+    }
+    // the largest principal 2 x 2 minor (C[kk] = the minor that leaves row and column k out; >= 0 for a PSD matrix)
+    int k = 0;
+    if (C[4] > C[k * 4]) k = 1;
+    if (C[8] > C[k * 4]) k = 2;
+    if (C[k * 4] != 0) {
+        const int i = k == 0 ? 1 : 0, j = k == 2 ? 1 : 2;
+        const double gii = (double)a[i * 3 + i], gij = (double)a[i * 3 + j], gjj = (double)a[j * 3 + j], minor = (double)C[k * 4];
+        double xp[3];
+        xp[i] = det2(hh[i], hh[j], gij, gjj) / minor;            // Cramer on exact integers
+        xp[j] = det2(gii, gij, hh[i], hh[j]) / minor;
+        xp[k] = 0.0;
+        const double n[3] = {(double)C[k * 3], (double)C[k * 3 + 1], (double)C[k * 3 + 2]};      // column k of the adjugate: null vector
+        const double nn = n[0] * n[0] + n[1] * n[1] + n[2] * n[2];
+        const double along = dot3_compensated(n, xp) / nn;
+        for (int q = 0; q < 3; ++q) x[q] = xp[q] - n[q] * along;
+        return true;
+    }
+    const long long trace = a[0] + a[4] + a[8];
+    if (trace == 0) { x[0] = x[1] = x[2] = 0.0; return true; }
+    int col = 0;
+    if (a[4] > a[col * 4]) col = 1;
+    if (a[8] > a[col * 4]) col = 2;
+    const double v[3] = {(double)a[col], (double)a[3 + col], (double)a[6 + col]};
+    const double sc = dot3_compensated(v, hh) / ((v[0] * v[0] + v[1] * v[1] + v[2] * v[2]) * (double)trace);
+    for (int q = 0; q < 3; ++q) x[q] = v[q] * sc;
+    return true;
+}
+
 // The serial part of a wide cluster's quantification, by warp 0 of the CTA (all its lanes call): G and h from the exact
 // integer sums, the minimum-norm solution, refine_coef, get_ratio.  coef / rvaf (m doubles each, shared memory) are
 // written by lane 0; returns the iteration count on every lane.  Not inlined: it runs for a handful of targets.
@@ -518,33 +574,12 @@ KM_COLD int solve_wide(int lane, int nl, const GraphScratch& S, int m, int n_nod
     bool solved = false;
     if (m == 3) {
         // Three columns (a cluster of two variants, the common wide case): G is an exact integer matrix, so its rank is
-        // decided exactly; at full rank the solution is unique and the adjugate gives it from exact integer cofactors
-        // (no eigen-decomposition: 33,000 cycles of one lane's square roots and divisions otherwise).
-        long long a[9];
-        bool small = true;
-        for (int i = 0; i < 3; ++i)
-            for (int j = 0; j < 3; ++j) {
-                const unsigned long long v = acc[(i >= j ? i : j) * 3 + (i >= j ? j : i)];
-                small &= v < (1ull << 20);
-                a[i * 3 + j] = (long long)v;
-            }
-        if (small) {
-            long long C[9];                       // cofactors (the matrix is symmetric, so is its adjugate)
-            C[0] = a[4] * a[8] - a[5] * a[7]; C[1] = a[5] * a[6] - a[3] * a[8]; C[2] = a[3] * a[7] - a[4] * a[6];
-            C[3] = C[1];                      C[4] = a[0] * a[8] - a[2] * a[6]; C[5] = a[1] * a[6] - a[0] * a[7];
-            C[6] = C[2];                      C[7] = C[5];                      C[8] = a[0] * a[4] - a[1] * a[3];
-            const long long det = a[0] * C[0] + a[1] * C[1] + a[2] * C[2];
-            if (det != 0) {
-                const double hh[3] = {(double)acc[9], (double)acc[10], (double)acc[11]};
-                double c3[3];
-                for (int i = 0; i < 3; ++i) {
-                    const double ci[3] = {(double)C[i * 3], (double)C[i * 3 + 1], (double)C[i * 3 + 2]};
-                    c3[i] = dot3_compensated(ci, hh) / (double)det;
-                }
-                if (lane == 0) { coef[0] = c3[0]; coef[1] = c3[1]; coef[2] = c3[2]; }
-                solved = true;
-            }
-        }
+        // decided exactly and the minimum-norm solution (what lstsq returns, PathQuant.py:116) has a closed form at every
+        // rank -- no eigen-decomposition (33,000 cycles of one lane's square roots and divisions).  Two tandem copies of a
+        // duplication next to one make the columns linearly dependent (2 * once - reference = twice): rank 2 is the rule.
+        double c3[3];
+        solved = solve3_exact(acc, c3);
+        if (solved && lane == 0) { coef[0] = c3[0]; coef[1] = c3[1]; coef[2] = c3[2]; }
     }
     if (!solved) {
         if (lane == 0) {
@@ -591,12 +626,10 @@ KM_COLD int solve_wide(int lane, int nl, const GraphScratch& S, int m, int n_nod
     return iters;
 }
 
-// Quantify m columns.  coef/rvaf receive m values each.  Returns refine iterations, or
-// -1 when the watchdog fired.  All threads of the CTA must call this; S.occ must be all zero on
-// entry and is all zero again on return.
+// The exact integer sums of m columns' normal equations into S.acc (solve_wide turns them into coefficients).  All threads
+// of the CTA must call this; S.occ must be all zero on entry and is all zero again on return.
 template <class Ctx>
-KM_HD int solve_columns(const Ctx& ctx, const GraphScratch& S, const uint32_t* counts, int n_nodes,
-                        const PathView* cols, int m, double* coef, double* rvaf, int* sh, bool allow_jump) {
+KM_HD void gram_columns(const Ctx& ctx, const GraphScratch& S, const uint32_t* counts, const PathView* cols, int m) {
     const int tid = ctx.tid(), nt = ctx.nt();
     PhaseTimer st;                     // (measurement builds: 53 Gram sums, 54 eigen solve, 55 refine)
     unsigned long long* acc = S.acc;   // [m*m + m] exact integer accumulators
@@ -635,14 +668,6 @@ KM_HD int solve_columns(const Ctx& ctx, const GraphScratch& S, const uint32_t* c
         }
     }
     st.mark(53);
-    // the serial part, by the warp that holds thread 0 (solve_wide): exact solve, refine_coef with its jumps, ratios
-    if (warp_index(ctx) == 0) {
-        const int nl = nt < 32 ? nt : 32;
-        const int iters = solve_wide(tid & 31, nl, S, m, n_nodes, coef, rvaf, allow_jump);
-        if ((tid & 31) == 0) sh[4] = iters;
-    }
-    ctx.sync();
-    return sh[4];
 }
 
 // min(counts over the path) by the whole group; `slot` is shared by the group.  An empty path gives 2^32-1.
@@ -679,6 +704,7 @@ KM_HD Quant2 quant_pair(const WCtx& wctx, const GraphScratch& S, const uint32_t*
     const int lane = wctx.tid(), nl = wctx.nt();
     unsigned long long h_p = 0ull, h_r = 0ull, g_pr = 0ull, g_pp = 0ull;
     uint32_t mn = 0xFFFFFFFFu;
+    bool twin = false;                 // both columns are the same slice of the reference
     if (path.bub_nk >= 0 || !path.idx) {
         // The identity path or a simple bubble's path (graph.h): which node sits where is known in closed form -- nodes
         // [x0, x1) once in position order, then the chain (novel nodes, each once, none of them in the reference), then
@@ -708,6 +734,7 @@ KM_HD Quant2 quant_pair(const WCtx& wctx, const GraphScratch& S, const uint32_t*
             for (int i = y0 + lane; i < y1; i += nl) take(counts[i]);
         }
         const bool same = path.bub_nk < 0 && x0 == r0 && x1 == r1;        // the reference against itself: one sum serves both
+        twin = same;
         if (!same) for (int p = lane; p < range.len; p += nl) h_r += (unsigned long long)(float)counts[range.begin + p];
         h_p = warp_sum64(h_p); h_r = same ? h_p : warp_sum64(h_r);
     } else {
@@ -733,7 +760,17 @@ KM_HD Quant2 quant_pair(const WCtx& wctx, const GraphScratch& S, const uint32_t*
     // (refine_jump evaluates its closed form at 32 steps at once)
     h_p = warp_bcast64(h_p); h_r = warp_bcast64(h_r); g_pr = warp_bcast64(g_pr); g_pp = warp_bcast64(g_pp);
     Quant2 q;
-    {
+    if (twin) {
+        // Two identical columns of len ones: G = len * [[1, 1], [1, 1]], h = S * [1, 1].  The minimum-norm solution is
+        // S / (2 len) for both; the first refine_coef step finds a zero gradient (to rounding) and stops.  Written down
+        // instead of computed: this is the Reference row of every target (whose numbers adjust_for_reference then
+        // replaces, PathQuant.py:151-154 -- only "all zero or not" survives), a third of all rows.
+        const double c = range.len > 0 ? (double)h_p / (2.0 * (double)range.len) : 0.0;
+        q.coef[0] = q.coef[1] = c;
+        q.rvaf[0] = q.rvaf[1] = c == 0.0 ? 0.0 : 0.5;
+        q.iters = 1;
+        q.min_cov = (int64_t)mn;
+    } else {
         // exact integer normal equations in the reference's column order
         const unsigned long long g_rr = (unsigned long long)range.len;
         const unsigned long long a00 = path_first ? g_pp : g_rr, a11 = path_first ? g_rr : g_pp, a01 = g_pr;
@@ -970,14 +1007,41 @@ KM_HD void emit_rows_prepared(const Ctx& ctx, const TableView& T, const WalkView
         ctx.sync();
         const int offset = cols[0].begin;
         const PathView ref_clip = cols[0];
-        const int iters = solve_columns(ctx, S, counts, d.N, cols, size + 1, coef, rvaf, sh, allow_jump);
-        for (int j = 0; j < size; ++j) {
+        gram_columns(ctx, S, counts, cols, size + 1);
+        // The solve is one long dependent chain (solve_wide: warp 0); what each member's row needs besides -- its diff
+        // against the clipped reference, its minimum count, the suffix its two strings share -- does not depend on it and
+        // is found by the other warps meanwhile, a member each (it used to follow the solve, 38,000 cycles later).
+        int32_t* mdiff = reinterpret_cast<int32_t*>(S.vec + 6 * S.max_cols);       // [4 per member]   (free parts of S.vec)
+        long long* mmc = reinterpret_cast<long long*>(S.vec + S.max_cols);         // [member]
+        int32_t* mcut = reinterpret_cast<int32_t*>(S.vec + 3 * S.max_cols);        // [member]
+        auto member_job = [&](int j) {
             const PathView clip = cols[1 + j];
-            const Diff df = diff_paths(ctx, ref_clip, clip, k, slot);
-            const int64_t mc = min_count(ctx, counts, clip, slot);
-            if (tid == 0)
-                write_row(R, W, kmers, t, k, crec[4 * c + 3] + j, 1, ref_clip, clip, df, first_path + members[j], offset, c + 1, size,
-                          iters, mc, rvaf[1 + j], coef[1 + j], rvaf[0], coef[0]);
+            const Diff df = diff_paths(wctx, ref_clip, clip, k, wslot);
+            const int64_t mc = min_count(wctx, counts, clip, wslot);
+            const int cut = shared_suffix(wctx, kmers, ref_clip, clip, df, wslot);
+            if (lane == 0) {
+                mdiff[4 * j] = df.start; mdiff[4 * j + 1] = df.end_ref; mdiff[4 * j + 2] = df.end_var; mdiff[4 * j + 3] = df.end_ref_overlap;
+                mmc[j] = mc; mcut[j] = cut;
+            }
+        };
+        if (nw > 1) {
+            if (wid == 0) {
+                const int it = solve_wide(lane, wctx.nt(), S, size + 1, d.N, coef, rvaf, allow_jump);
+                if (lane == 0) sh[4] = it;
+            } else {
+                for (int j = wid - 1; j < size; j += nw - 1) member_job(j);
+            }
+        } else {
+            const int it = solve_wide(lane, wctx.nt(), S, size + 1, d.N, coef, rvaf, allow_jump);
+            if (lane == 0) sh[4] = it;
+            for (int j = 0; j < size; ++j) member_job(j);
+        }
+        ctx.sync();
+        const int iters = sh[4];
+        for (int j = tid; j < size; j += ctx.nt()) {
+            const Diff df = {mdiff[4 * j], mdiff[4 * j + 1], mdiff[4 * j + 2], mdiff[4 * j + 3]};
+            write_row(R, W, kmers, t, k, crec[4 * c + 3] + j, 1, ref_clip, cols[1 + j], df, first_path + members[j], offset, c + 1, size,
+                      iters, mmc[j], rvaf[1 + j], coef[1 + j], rvaf[0], coef[0], mcut[j]);
         }
         ctx.sync();
     }

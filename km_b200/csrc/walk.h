@@ -73,11 +73,29 @@ struct WalkView {
     int32_t* n_kept;          // kept nodes (excludes the two caps)
     uint32_t* status;
     unsigned long long* lookups;  // [n] table lookups issued (measurement only)
+    // [n] what the walk already knows about the target's graph pass, + 1 (0 = not said: the scheduler works it out):
+    // bits 0-1 size class (0 / 1 the shared-memory classes, 2 general), bit 2 the walk branched, bits 3.. size bin;
+    // 0xFFFF = no graph.  May be null (the CPU emulation has no scheduler).
+    uint16_t* sched_code;
     // chunks of <= 32 consecutive reference k-mers, flat over all targets (ref_probe_chunk)
     const int32_t* chunk_target;
     const int32_t* chunk_start;
     int n_chunks;
 };
+
+#define KM_ST_FATAL (KM_ST_BAD_BASE | KM_ST_DUP_KMER | KM_ST_NODE_OVERFLOW | KM_ST_NODE_LIMIT | KM_ST_TOO_SHORT)
+// The graph pass's work-list code of a target (km_schedule_kernel): `st` its final status, `n_all` explored nodes (capped),
+// `kept` kept nodes without the caps.
+KM_HD uint32_t sched_code_of(uint32_t st, int n_all, int kept, int tiny_nodes, int small_nodes) {
+    if (st & KM_ST_FATAL) return 0xFFFFu;
+    const int kept2 = kept + 2;
+    int b = 63 - (kept2 >> 3);
+    b = b < 0 ? 0 : b;                                            // bin 0 = the largest graphs
+    int c = 2;
+    if (n_all <= tiny_nodes - 2 && kept2 <= tiny_nodes) c = 0;
+    else if (n_all <= small_nodes - 2 && kept2 <= small_nodes) c = 1;
+    return (uint32_t)(c | ((st & KM_ST_BRANCHED) ? 4 : 0) | (b << 3));
+}
 
 KM_HD uint32_t pack_meta(int depth, int breaks) { return ((uint32_t)depth << 8) | (uint32_t)(breaks > 255 ? 255 : breaks); }
 

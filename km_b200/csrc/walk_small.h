@@ -19,6 +19,7 @@
 // kernel: KM_ST_WALK_DEFER.
 #pragma once
 #include "walk.h"
+#include "find_config.h"
 
 namespace km {
 
@@ -439,7 +440,14 @@ KM_HD bool ws_finish(const Ctx& ctx, const WalkView& W, const FindParams& P, int
         W.n_nodes[t] = n_all;
         W.n_kept[t] = total;
         if (total > P.max_node) st |= KM_ST_NODE_LIMIT;                          // MutationFinder.py:143-148
-        if (st) atomic_or32(&W.status[t], st);
+        // the status is final here (the probe kernel is done, the other lanes' bits are in `st`): the walk's internal hint
+        // goes to the scheduler's code instead of the status, and the scheduler need not read five arrays per target
+        const uint32_t all = atomic_or32(&W.status[t], st) | st;
+        if (W.sched_code) {
+            const int cap_all = n_all < g.cap ? n_all : g.cap;
+            W.sched_code[t] = (uint16_t)(sched_code_of(all, cap_all, total, KM_TINY_NODES, KM_SMALL_NODES) + 1u);
+            if (all & KM_ST_BRANCHED) W.status[t] = all & ~KM_ST_BRANCHED;
+        }
         if (nlook) atomic_add64(&W.lookups[t], nlook);
     }
     pt.mark_warp(37);

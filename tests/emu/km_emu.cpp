@@ -86,7 +86,7 @@ int emu_find_target(void* h, const uint8_t* codes, int len, double ratio, int64_
     int32_t n_nodes = 0, n_kept = 0;
     uint32_t status = 0;
     unsigned long long lookups = 0;
-    WalkView W;
+    WalkView W{};
     W.n_targets = 1; W.codes = codes; W.seq_off = seq_off; W.node_off = node_off; W.hash_off = hash_off;
     W.node_kmer = node_kmer.data(); W.node_count = node_count.data(); W.node_slot = node_slot.data(); W.node_kid = node_kid.data();
     W.hkey = hkey.data(); W.hval = hval.data(); W.hmeta = hmeta.data(); W.hflag = hflag.data();
@@ -177,5 +177,8 @@ int emu_find_target(void* h, const uint8_t* codes, int len, double ratio, int64_
     for (int r = 0; r < t_nr; ++r) { out_rows[r] = out_rows[t_rf + r]; out_rows[r].path_id -= t_pf; }
     return (int)status;
 }
+
+// quant.h solve3_exact on its own: acc = lower triangle of G at [a * 3 + b] (b <= a) + h at [9..11]; 1 = solved
+int emu_solve3(const unsigned long long* acc, double* x) { return solve3_exact(acc, x) ? 1 : 0; }
 
 }  // extern "C"

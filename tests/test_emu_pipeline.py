@@ -182,3 +182,42 @@ def test_long_refinement_equals_literal_iteration():
         assert longest > 500           # the case this test is about did occur
     finally:
         ko.Quant.solve = orig
+
+
+def test_exact_three_column_solve_matches_lstsq_at_every_rank():
+    """quant.h solve3_exact (clusters of two variants): the minimum-norm solution np.linalg.lstsq returns
+    (PathQuant.py:116), from exact integer sums, for contribution matrices of rank 3, 2 (two tandem copies next to
+    one: twice = 2 * once - reference), 1 and 0."""
+    import ctypes
+    L = elib()
+    L.emu_solve3.restype = ctypes.c_int
+    L.emu_solve3.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    rng = np.random.default_rng(7)
+    cases = []
+    for _ in range(200):
+        n = int(rng.integers(20, 400))
+        ref = rng.integers(0, 2, n)
+        once = np.clip(ref + rng.integers(0, 2, n) * rng.integers(-1, 2, n), 0, 2)
+        third = rng.integers(0, 3, n)
+        cases.append(np.stack([ref, once, third], 1))                      # rank 3 (almost surely)
+        cases.append(np.stack([ref, once, 2 * once - ref + 0 * third], 1).clip(min=-5))   # rank 2, signed entries excluded below
+        cases.append(np.stack([ref, 2 * ref, ref], 1))                      # rank 1
+    cases.append(np.zeros((50, 3), dtype=np.int64))                         # rank 0
+    ranks = set()
+    for A in cases:
+        if (A < 0).any():
+            continue
+        b = rng.integers(0, 5000, A.shape[0]).astype(np.float64)
+        G = A.T @ A
+        h = (A.T @ b).astype(np.int64)
+        acc = np.zeros(12, dtype=np.uint64)
+        for i in range(3):
+            for j in range(i + 1):
+                acc[i * 3 + j] = G[i, j]
+        acc[9:12] = h
+        x = np.zeros(3)
+        assert L.emu_solve3(acc.ctypes.data, x.ctypes.data) == 1
+        want = np.linalg.lstsq(A.astype(np.float64), b, rcond=None)[0]
+        ranks.add(int(np.linalg.matrix_rank(A)))
+        assert np.allclose(x, want, rtol=1e-9, atol=1e-9 * max(1.0, float(np.abs(want).max()))), (A.shape, x, want)
+    assert ranks == {0, 1, 2, 3}
