@@ -33,6 +33,9 @@ def _gpu_worker(rank, world, port, opts):
     from .. import cohort, engine
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
+    # stdout is the report (km's callers parse it): whatever NCCL has to say at NCCL_DEBUG=VERSION / WARN / INFO -- its
+    # "NCCL version ..." banner goes to stdout by default -- belongs on stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
