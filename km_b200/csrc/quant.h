@@ -367,12 +367,17 @@ KM_COLD int refine_jump(int lane, int nl, const double* G, const double* h, int 
 // problem was a 1,650-cycle chain of dependent loads, stores and divisions; in registers the rows are independent).
 // WARP-COLLECTIVE like refine_jump: every lane computes the same thing, which costs nothing and lets the jump use them.
 // G_in / h_in must stay valid and unchanged during the call.
+// (G is symmetric: its M (M + 1) / 2 distinct entries are kept, which is what lets three columns run without spills in a
+// 64-register kernel)
+KM_HD constexpr int sym_index(int a, int b) { return a >= b ? a * (a + 1) / 2 + b : b * (b + 1) / 2 + a; }
 template <int M>
 KM_HD int refine_and_ratio(int lane, int nl, const double* G_in, const double* h_in, int n_nodes, double* coef_io, double* rvaf,
                             bool allow_jump) {
-    double G[M * M], h[M], c[M], grad[M];
+    double G[M * (M + 1) / 2], h[M], c[M], grad[M];
 #pragma unroll
-    for (int i = 0; i < M * M; ++i) G[i] = G_in[i];
+    for (int a = 0; a < M; ++a)
+#pragma unroll
+        for (int b = 0; b <= a; ++b) G[sym_index(a, b)] = G_in[a * M + b];
 #pragma unroll
     for (int a = 0; a < M; ++a) { h[a] = h_in[a]; c[a] = coef_io[a] < 0.0 ? 0.0 : coef_io[a]; }
     double worst = INFINITY;
@@ -382,7 +387,7 @@ KM_HD int refine_and_ratio(int lane, int nl, const double* G_in, const double* h
         for (int a = 0; a < M; ++a) {
             double fit = 0.0;
 #pragma unroll
-            for (int b = 0; b < M; ++b) fit += G[a * M + b] * c[b];
+            for (int b = 0; b < M; ++b) fit += G[sym_index(a, b)] * c[b];
             grad[a] = 2.0 * (h[a] - fit) / (double)n_nodes;
         }
         worst = 0.0;
@@ -419,6 +424,14 @@ KM_HD int refine_and_ratio(int lane, int nl, const double* G_in, const double* h
 #pragma unroll
     for (int a = 0; a < M; ++a) { coef_io[a] = c[a]; rvaf[a] = cmax == 0.0 ? c[a] : c[a] / csum; }
     return iters;
+}
+
+// (a function of its own for three and four columns: inside solve_wide the loop's state competed with everything else that
+// is live there and spilled -- 700 bytes in the 64-register kernel, a local-memory round trip on every operand)
+template <int M>
+KM_COLD int refine_and_ratio_cold(int lane, int nl, const double* G_in, const double* h_in, int n_nodes, double* coef_io, double* rvaf,
+                                  bool allow_jump) {
+    return refine_and_ratio<M>(lane, nl, G_in, h_in, n_nodes, coef_io, rvaf, allow_jump);
 }
 
 // The same for any number of columns, state in memory (clusters of four variants and more): lane 0 iterates, the warp
@@ -616,8 +629,8 @@ KM_COLD int solve_wide(int lane, int nl, const GraphScratch& S, int m, int n_nod
 #if KM_DEVICE_BUILD
         __syncwarp();
 #endif
-        iters = m == 3 ? refine_and_ratio<3>(lane, nl, G, h, n_nodes, c, r, allow_jump)
-                       : refine_and_ratio<4>(lane, nl, G, h, n_nodes, c, r, allow_jump);
+        iters = m == 3 ? refine_and_ratio_cold<3>(lane, nl, G, h, n_nodes, c, r, allow_jump)
+                       : refine_and_ratio_cold<4>(lane, nl, G, h, n_nodes, c, r, allow_jump);
         if (lane == 0) for (int a = 0; a < m; ++a) { coef[a] = c[a]; rvaf[a] = r[a]; }
     } else {
         iters = refine_and_ratio_any(lane, nl, G, h, m, n_nodes, coef, rvaf, S.vec + 2 * S.max_cols, allow_jump);
