@@ -60,7 +60,7 @@ int plan_layout(km_plan* p) {
     acc(2 * (size_t)n);                                                            // the walk's codes for the scheduler
     acc(8 * n_node); acc(4 * n_node);                                              // canonical nodes
     acc(8 * (size_t)path_cap); acc(4 * (size_t)path_cap); acc(8 * (size_t)path_cap); acc(4 * (size_t)pool_cap);
-    acc(sizeof(Row) * (size_t)row_cap); acc((size_t)seq_cap); acc(64); acc(20 * (size_t)n + 64);
+    acc(sizeof(Row) * (size_t)row_cap); acc((size_t)seq_cap); acc(64); acc(64); acc(20 * (size_t)n + 64);
     acc(L0.stride * (size_t)p->grid_large);
     const size_t n_name = p->fmt ? (size_t)p->fmt_name_off[n] : 0;
     if (p->fmt) {
@@ -105,6 +105,7 @@ int plan_layout(km_plan* p) {
     // the pool cursors and the formatter's flags / total sit in the same block: one memset, one copy back
     R.used = A.take<unsigned long long>(8);     // [0..3] pool cursors, [4..6] work counters of the three graph passes
     p->F.flags = A.take<uint32_t>(16);          // [0] flags, [2..3] total bytes of text (64 bit)
+    W.walk_cursor = A.take<uint32_t>(4);
     p->state_bytes = (size_t)(A.take<char>(0) - p->state0);
     // (cleared with the state, but not part of what comes back: the memset covers it, the copy does not)
     W.sched_code = A.take<uint16_t>(n);

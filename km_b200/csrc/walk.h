@@ -77,6 +77,7 @@ struct WalkView {
     // bits 0-1 size class (0 / 1 the shared-memory classes, 2 general), bit 2 the walk branched, bits 3.. size bin;
     // 0xFFFF = no graph.  May be null (the CPU emulation has no scheduler).
     uint16_t* sched_code;
+    uint32_t* walk_cursor;        // next target of the persistent walk warps (cleared with the per-target state)
     // chunks of <= 32 consecutive reference k-mers, flat over all targets (ref_probe_chunk)
     const int32_t* chunk_target;
     const int32_t* chunk_start;

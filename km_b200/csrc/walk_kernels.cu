@@ -53,19 +53,28 @@ __global__ void __launch_bounds__(32 * KM_PROBE_WARPS, LINKED ? KM_PROBE_MINB_LI
     ref_probe_chunk<WarpCtx, LINKED>(ctx, T, W, P, W.chunk_target[ch], W.chunk_start[ch]);
 }
 
+// Persistent warps: each takes the next target from a cursor until none is left.  (One CTA per four targets held its slot
+// until the LONGEST of its four walks was over -- walks differ several-fold, 30 to 180 levels -- and the slots of the three
+// finished warps sat idle meanwhile.)
 __global__ void __launch_bounds__(32 * KM_WALK_WARPS, KM_WALK_MINB) km_walk_small_kernel(TableView T, WalkView W, FindParams P) {
     __shared__ WalkSmall M[KM_WALK_WARPS];
     WarpCtx ctx;
-    const int t = (int)blockIdx.x * KM_WALK_WARPS + (int)(threadIdx.x >> 5);
-    if (t >= W.n_targets) return;
-    const TargetGeom g = target_geom(W, t, T.k);
-    if (walk_small_fits(g) && walk_small_target(ctx, T, W, P, t, M[threadIdx.x >> 5])) return;
-    // too long for the shared-memory state, or more novel nodes than it holds: the general walk, state in HBM, by the same
-    // warp (rare; a kernel of its own for these cost 7 us per batch whether or not there was one)
-    __syncwarp();
-    if ((threadIdx.x & 31) == 0) { W.status[t] = 0; W.lookups[t] = 0; W.n_kept[t] = 0; }     // (also drops the probe's limit flag)
-    __syncwarp();
-    walk_target(ctx, T, W, P, t);
+    for (;;) {
+        int t = 0;
+        if ((threadIdx.x & 31) == 0) t = (int)atomicAdd(W.walk_cursor, 1u);
+        t = __shfl_sync(0xFFFFFFFFu, t, 0);
+        if (t >= W.n_targets) return;
+        const TargetGeom g = target_geom(W, t, T.k);
+        if (!(walk_small_fits(g) && walk_small_target(ctx, T, W, P, t, M[threadIdx.x >> 5]))) {
+            // too long for the shared-memory state, or more novel nodes than it holds: the general walk, state in HBM, by the
+            // same warp (rare; a kernel of its own for these cost 7 us per batch whether or not there was one)
+            __syncwarp();
+            if ((threadIdx.x & 31) == 0) { W.status[t] = 0; W.lookups[t] = 0; W.n_kept[t] = 0; }     // (also drops the probe's limit flag)
+            __syncwarp();
+            walk_target(ctx, T, W, P, t);
+        }
+        __syncwarp();
+    }
 }
 
 }  // namespace km
@@ -86,7 +95,18 @@ cudaError_t km_launch_ref_probe(const TableView& T, const WalkView& W, const Fin
 }
 cudaError_t km_launch_walks(const TableView& T, const WalkView& W, const FindParams& P, cudaStream_t s) {
     const int n = W.n_targets;
-    km_walk_small_kernel<<<(n + KM_WALK_WARPS - 1) / KM_WALK_WARPS, 32 * KM_WALK_WARPS, 0, s>>>(T, W, P);
+    static int sm_count[64] = {0};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!sm_count[dev]) {
+        int v = 0;
+        if ((e = cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+        sm_count[dev] = v > 0 ? v : 1;
+    }
+    const int want = (n + KM_WALK_WARPS - 1) / KM_WALK_WARPS, resident = sm_count[dev] * KM_WALK_MINB;
+    km_walk_small_kernel<<<want < resident ? want : resident, 32 * KM_WALK_WARPS, 0, s>>>(T, W, P);
     return cudaGetLastError();
 }
 
