@@ -135,6 +135,11 @@ struct km_plan {
     // flight at once on different streams (bench.py launches the panel as parts that overlap each other's phases)
     cudaStream_t own_side = nullptr, own_side2 = nullptr, own_side3 = nullptr;
     cudaEvent_t own_ev[8] = {}, own_fork = nullptr, own_join = nullptr, own_join2 = nullptr, own_join3 = nullptr;
+    // a resident plan (km_find_plan_create) launched again and again: the launch sequence as a CUDA graph (plan_api.cu)
+    cudaGraphExec_t gexec = nullptr;
+    std::string gkey;
+    int direct_launches = 0;
+    bool capturing = false;              // plan_launch is being captured: phase events are recorded as external event nodes
     size_t clear_bytes = 0;              // state_bytes + what is cleared with the state but not fetched (the scheduler's codes)
     bool trace_events = false;           // KM_TRACE=2: per-phase events also on the km_find_text path (device timeline)
     bool layout_reusable = false;        // plan_init: the borrowed vectors already hold this batch's layout

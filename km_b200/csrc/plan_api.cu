@@ -188,12 +188,14 @@ int plan_launch(km_plan* p, cudaStream_t s) {
     km_table* t = p->t;
     if (p->n == 0) return 0;
     const bool timed = !p->fmt || p->trace_events;          // km_find_text enqueues as little as it can: no per-phase events
-    if (timed) CU(cudaEventRecord(p->ev[1], s));
+    // (inside a capture a phase event becomes an EXTERNAL record node: it is recorded when the graph runs and can be timed)
+    auto mark = [&](cudaEvent_t ev) { return cudaEventRecordWithFlags(ev, s, p->capturing ? cudaEventRecordExternal : cudaEventRecordDefault); };
+    if (timed) CU(mark(p->ev[1]));
     CU(cudaMemsetAsync(p->state0, 0, p->clear_bytes, s));
     CU(km_launch_ref_probe(t->view(), p->W, p->P, s));
-    if (timed) CU(cudaEventRecord(p->ev[6], s));
+    if (timed) CU(mark(p->ev[6]));
     CU(km_launch_walks(t->view(), p->W, p->P, s));
-    if (timed) CU(cudaEventRecord(p->ev[2], s));
+    if (timed) CU(mark(p->ev[2]));
     // shared-memory passes first, then the general pass for large or deferred targets
     CU(km_launch_schedule(p->W, p->R, s));
     // The passes run side by side (each pass's tail fills with the others' CTAs): the simple bubbles of the two size classes,
@@ -220,11 +222,11 @@ int plan_launch(km_plan* p, cudaStream_t s) {
     CU(cudaStreamWaitEvent(s, p->join, 0));
     if (bubbles) { CU(cudaStreamWaitEvent(s, p->join2, 0)); CU(cudaStreamWaitEvent(s, p->join3, 0)); }
     CU(km_launch_graph(2, 2, p->grid_large, t->view(), p->W, p->SL, p->R, s));
-    if (timed) CU(cudaEventRecord(p->ev[3], s));
+    if (timed) CU(mark(p->ev[3]));
     p->n_launches += bubbles ? 8 : 6;
     if (p->fmt) {
         CU(km_launch_format(p->W, p->R, p->F, t->k, s));
-        if (p->trace_events) CU(cudaEventRecord(p->ev[4], s));
+        if (p->trace_events) CU(mark(p->ev[4]));
         p->n_launches += 3;
     }
     p->launched = true;
@@ -448,7 +450,36 @@ extern "C" int km_find_plan_launch(km_plan* p, void* stream) {
     if (!p) return fail(KM_E_ARG, "null plan");
     CU(cudaSetDevice(p->t->device));
     if (int rc = km_ensure_linked(p->t)) return rc;
-    return plan_launch(p, stream ? (cudaStream_t)stream : p->stream);
+    cudaStream_t s = stream ? (cudaStream_t)stream : p->stream;
+    // A resident plan is launched again and again (a fixed panel against sample after sample): from its third launch on the
+    // sequence -- memset, nine kernels on four streams, their events -- is ONE graph launch; the gaps between dependent
+    // kernels (4 us on a stream, 10-14 us across streams through an event) shrink to what the hardware needs.
+    // KM_NO_GRAPH=1 = A/B switch.
+    static const bool graphs_on = !getenv("KM_NO_GRAPH");
+    if (!graphs_on) return plan_launch(p, s);
+    const std::string key = plan_graph_key(p);
+    if (p->gexec && p->gkey == key) {
+        if (cudaGraphLaunch(p->gexec, s) == cudaSuccess) { p->launched = true; p->n_launches += km_bubble_pass_enabled() ? 8 : 6; return 0; }
+        cudaGetLastError();
+        cudaGraphExecDestroy(p->gexec); p->gexec = nullptr;
+    }
+    if (p->gkey != key) { p->gkey = key; p->direct_launches = 0; if (p->gexec) { cudaGraphExecDestroy(p->gexec); p->gexec = nullptr; } }
+    if (p->direct_launches++ >= 2 && !p->gexec) {
+        cudaGraph_t graph = nullptr;
+        if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            p->capturing = true;
+            const int rc = plan_launch(p, s);
+            p->capturing = false;
+            const cudaError_t ce = cudaStreamEndCapture(s, &graph);
+            bool ok = !rc && ce == cudaSuccess && graph && cudaGraphInstantiate(&p->gexec, graph, 0) == cudaSuccess;
+            if (graph) cudaGraphDestroy(graph);
+            if (ok && cudaGraphLaunch(p->gexec, s) == cudaSuccess) return 0;
+            cudaGetLastError();
+            if (p->gexec) { cudaGraphExecDestroy(p->gexec); p->gexec = nullptr; }
+            p->direct_launches = -1000000;          // do not try again for this layout
+        } else cudaGetLastError();
+    }
+    return plan_launch(p, s);
 }
 
 extern "C" int km_find_plan_last_ms(km_plan* p, float* walk_ms, float* graph_ms) {
@@ -492,6 +523,7 @@ extern "C" void km_find_plan_free(km_plan* p) {
     if (p->own_join) cudaEventDestroy(p->own_join);
     if (p->own_join2) cudaEventDestroy(p->own_join2);
     if (p->own_join3) cudaEventDestroy(p->own_join3);
+    if (p->gexec) cudaGraphExecDestroy(p->gexec);
     if (p->own_side) cudaStreamDestroy(p->own_side);
     if (p->own_side2) cudaStreamDestroy(p->own_side2);
     if (p->own_side3) cudaStreamDestroy(p->own_side3);

@@ -451,6 +451,11 @@ extern "C" int km_find_text(km_table* t, const char* seqs, const int64_t* offset
                         if (cudaGraphLaunch(lane->gexec, p->stream) == cudaSuccess) { done = true; p->launched = true; p->n_launches += km_bubble_pass_enabled() ? 11 : 9; tr.mark("graph replay", c); }
                         else { cudaGetLastError(); cudaGraphExecDestroy(lane->gexec); lane->gexec = nullptr; }
                     } else if (use_graph && lane->last_key == key) {
+                        // (one capture at a time: it happens once per layout, and four threads capturing and instantiating at
+                        // once is the one thing this call does that profilers and the driver see rarely -- an ncu run of
+                        // bench.py once died there)
+                        static std::mutex capture_mutex;
+                        std::lock_guard<std::mutex> capture_lock(capture_mutex);
                         if (lane->gexec) { cudaGraphExecDestroy(lane->gexec); lane->gexec = nullptr; }
                         cudaGraph_t graph = nullptr;
                         if (cudaStreamBeginCapture(p->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
