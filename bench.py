@@ -9,8 +9,8 @@ SNV/insertion/deletion/tandem-duplication variants) against the ~2e9-distinct-31
 Targets shard across ranks (each rank works on its own 10,000-target panel -> weak scaling), the
 table is replicated, there is no collective on the data path.
 
-  value   targets/s, whole job, inputs resident in HBM: K launches of the resident plan (seven kernels per
-          launch: reference probe, two walks, schedule, three graph passes; km_find_plan_launch), CUDA events
+  value   targets/s, whole job, inputs resident in HBM: K launches of the resident plan (eight kernels per
+          launch: reference probe, walk, scheduler, two bubble passes, three graph passes; one CUDA graph), CUDA events
           on the launch stream, max over ranks
   e2e     the same through the reference-facing call with HOST buffers: km_find_text (H2D of sequences and
           names, kernels, the text `km find_mutation` prints formatted on the device, D2H of that text), wall
@@ -826,7 +826,9 @@ def main():
                     "ms_per_step": e2e_ms, "device_ms": e2e_breakdown,
                     "what": "km_find_text(host buffers: sequences + offsets, names) -> the TSV text km find_mutation prints; "
                             "device_ms = the same work as two calls (km_find_batch, km_result_text), not pipelined"},
-            "gpu_launches": 7 * args.steps * best_parts,  # per step and part: reference probe, two walks, schedule, three graph passes
+            # per step and part: reference probe, walk, scheduler, the two bubble passes, the three CTA-per-target graph
+            # passes (plan_launch; replayed as one CUDA graph from a plan's third launch on)
+            "gpu_launches": (6 if os.environ.get("KM_NO_BUBBLE_KERNEL", "0") not in ("", "0") else 8) * args.steps * best_parts,
             "kernels": {"km_ref_probe_kernel_ms": probe_ms, "km_walk_kernels_ms": walk_ms, "km_graph_kernels_ms": graph_ms,
                         "what": "reference probe (HBM-bound: ~87% of the panel's lookups), shared-memory + general walk "
                                 "(latency-bound tails), graph/paths/quantification (shared memory, latency-bound)"},
