@@ -33,9 +33,12 @@ def _gpu_worker(rank, world, port, opts):
     from .. import cohort, engine
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
-    # stdout is the report (km's callers parse it): whatever NCCL has to say at NCCL_DEBUG=VERSION / WARN / INFO -- its
-    # "NCCL version ..." banner goes to stdout by default -- belongs on stderr
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    # stdout is the report (km's callers parse it).  Whatever a library has to say on file descriptor 1 -- NCCL prints its
+    # "NCCL version ..." banner there at NCCL_DEBUG=VERSION / WARN -- goes to stderr: the worker keeps a private copy of
+    # the real stdout for the report and points descriptor 1 at descriptor 2.
+    sys.stdout.flush()
+    report = os.fdopen(os.dup(1), "wb")
+    os.dup2(2, 1)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
@@ -56,11 +59,11 @@ def _gpu_worker(rank, world, port, opts):
                         break
                     if ln:
                         keep.append(ln)
-                sys.stdout.buffer.write(b"\n".join(keep) + (b"\n" if keep else b""))
-                sys.stdout.flush()
+                report.write(b"\n".join(keep) + (b"\n" if keep else b""))
+                report.flush()
                 engine.raise_for_status(status[bad[0]], refpaths[bad[0]].name, opts["nodes"])
-            sys.stdout.buffer.write(text.tobytes())
-            sys.stdout.flush()
+            report.write(text.tobytes())
+            report.flush()
     finally:
         dist.barrier()
         dist.destroy_process_group()
