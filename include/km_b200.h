@@ -277,6 +277,11 @@ int km_debug_phase_cycles(unsigned long long* out64, int reset);
 int km_debug_walk_cycles(unsigned long long* out64, int reset);
 /* graph-pass SM cycles of targets 0..n-1 in the last launch (KM_PHASE_TIMERS builds only) */
 int km_debug_target_cycles(unsigned int* out, int n);   /* 64 counters */
+/* wall-clock extent (%globaltimer ns) of every kernel of the graph phase in the launches since the last reset
+ * (-DKM_TIMELINE or -DKM_PHASE_TIMERS builds only; tools/slow_targets.py): out32 = 16 x (earliest CTA start, latest CTA
+ * end); 0 scheduler, 1 / 2 / 3 CTA-per-target passes (256 / 512 nodes / general), 4 / 5 bubble passes, 8.. the first
+ * eight targets the CTA-per-target passes took */
+int km_debug_timeline(unsigned long long* out32, int reset);
 /* random 32-byte-sector gather over `bytes` of HBM: the ceiling for hash probes */
 int km_bench_random_gather(int device, uint64_t bytes, uint64_t n_loads, int iters, float* best_ms);
 /* device-resident counting benchmark: n_reads reads of read_len bases drawn from a pseudo-random genome of `genome` bases
