@@ -151,4 +151,4 @@ EXPORTS = ["km_table_link", "km_last_error", "km_device_count", "km_version", "k
            "km_get_child_batch", "km_find_batch", "km_result_get", "km_result_free", "km_result_format_target", "km_result_format_all", "km_result_text", "km_find_text", "km_table_create_layout", "km_table_export", "km_table_write_jf", "km_table_create_shard", "km_table_shard_export_fd", "km_table_shard_attach_fd", "km_shard_owner", "km_debug_format_fixed", "km_debug_nat_cmp",
            "km_table_count_text", "km_table_set_routing", "km_table_recount", "km_shard_owner_device", "km_route_partition", "km_route_unpermute",
            "km_find_plan_create", "km_find_plan_launch", "km_find_plan_fetch", "km_find_plan_free", "km_find_plan_last_ms", "km_find_plan_kernel_ms",
-           "km_bench_random_gather", "km_bench_lookup", "km_bench_make_queries", "km_bench_count", "km_debug_walk_cycles", "km_debug_phase_cycles", "km_debug_target_cycles"]
+           "km_bench_random_gather", "km_bench_lookup", "km_bench_make_queries", "km_bench_count", "km_debug_walk_cycles", "km_debug_phase_cycles", "km_debug_target_cycles", "km_debug_timeline"]
