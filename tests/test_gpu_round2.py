@@ -174,3 +174,39 @@ def test_jf_files_with_other_k_and_strandedness(engine, tmp_path, k, canonical, 
         assert got_rec["nodes"] == sorted([kk, int(v)] for kk, v in f.node_data.items())
         n_variant_rows += sum(1 for r in want if "Substitution" in str(r))
     assert n_variant_rows >= 20
+
+
+def test_resident_plan_replayed_as_a_graph_does_the_same_work(engine):
+    """km_find_plan_launch replays the launch sequence as one CUDA graph from a plan's third launch on (what bench.py's
+    `value` times): the results fetched after graph launches must be the rows of a direct launch, the phase events must
+    still be timeable, and a plan of another layout on the same table must not be confused with it."""
+    from km_b200 import synth
+    panel = synth.make_panel(600, seed=synth.PANEL_SEED + 9, two_variant_frac=0.3)
+    t = engine.Table.create(capacity=len(panel.keys) + 50_000)
+    t.build_synthetic(synth.TABLE_SEED, 40_000)
+    t.insert(panel.keys, panel.counts, mode="overwrite")
+    direct = t.find_batch(panel.targets, want_graph=False)
+    plan = t.plan(panel.targets)
+    other = t.plan(panel.targets[:100])
+    try:
+        for _ in range(6):                      # launches 1-2 direct, 3 captures, 4-6 replay
+            plan.launch()
+            other.launch()
+        res = plan.fetch(want_graph=False)
+        ms = plan.kernel_ms()
+        assert all(m > 0.0 for m in ms), ms
+        assert (res.status == direct.status).all() and (res.row_count == direct.row_count).all()
+        names = [n for n in res.rows.dtype.names if n not in ("path_id",)]
+        for i in range(len(panel.targets)):
+            a = res.rows[int(res.row_first[i]):int(res.row_first[i]) + int(res.row_count[i])]
+            b = direct.rows[int(direct.row_first[i]):int(direct.row_first[i]) + int(direct.row_count[i])]
+            a, b = np.sort(a, order=["kind", "var_begin", "var_end", "cluster_id"]), np.sort(b, order=["kind", "var_begin", "var_end", "cluster_id"])
+            for n in names:
+                assert np.array_equal(a[n], b[n], equal_nan=True) if a[n].dtype.kind == "f" else (a[n] == b[n]).all(), (i, n)
+        small = other.fetch(want_graph=False)
+        assert (small.row_count == direct.row_count[:100]).all()
+        assert res.format_all("p.jf", engine.PackedTargets(panel.targets, panel.names)) == \
+            direct.format_all("p.jf", engine.PackedTargets(panel.targets, panel.names))
+    finally:
+        plan.close()
+        other.close()
