@@ -13,7 +13,7 @@ from oracle.compare import compare_rows
 from oracle.store import KmerStore, lib as olib
 
 from emu_harness import EmuTable, lib as elib
-from helpers import record_of
+from helpers import record_of, wide_cluster_case
 
 
 def _check(rec, got, tag):
@@ -221,3 +221,26 @@ def test_exact_three_column_solve_matches_lstsq_at_every_rank():
         ranks.add(int(np.linalg.matrix_rank(A)))
         assert np.allclose(x, want, rtol=1e-9, atol=1e-9 * max(1.0, float(np.abs(want).max()))), (A.shape, x, want)
     assert ranks == {0, 1, 2, 3}
+
+
+@pytest.mark.parametrize("n_alleles", [2, 3, 4, 5])
+def test_wide_clusters_match_the_oracle(n_alleles):
+    """Several substitutions within one k-mer length of each other, each on its own haplotype: one cluster of n variants
+    (MutationFinder.py:651-723, 749-811), an (n + 1)-column least-squares problem.  quant.h solves three columns exactly
+    from integer cofactors, three and four with the state in registers, five and more in memory with the Jacobi
+    eigen-decomposition; all must give the oracle's rows and raw floats."""
+    ref, keys, vals = wide_cluster_case(n_alleles)
+    t = EmuTable.from_keys(keys, vals)
+    store = KmerStore(31, True, len(keys))
+    store.insert(keys, vals)
+    jf = ko.OracleJellyfish(store, "w.jf", 0.05, 5)
+    f = ko.OracleFinder(ko.Target(ref, "wide", 31), jf).run()
+    want = f.get_paths()
+    res = t.find_batch([ref])
+    assert int(res.status[0]) == 0
+    got = record_of(res, 0, "w.jf", "wide")
+    errs, _ = compare_rows([str(r) for r in want], got["rows"],
+                           [[float(r.rvaf), float(r.expr), float(r.ref_expr)] for r in want], got["raw"])
+    assert not errs, errs
+    sizes = [r for r in got["rows"] if "cluster" in r.split("\t")[11]]
+    assert any("n=%d" % n_alleles in r.split("\t")[11] for r in sizes), [r.split("\t")[11] for r in got["rows"]]

@@ -7,7 +7,7 @@ from oracle import jf_format, km_oracle as ko
 from oracle.compare import compare_rows
 from oracle.store import KmerStore
 
-from helpers import record_of
+from helpers import record_of, wide_cluster_case
 
 pytestmark = pytest.mark.gpu
 
@@ -210,3 +210,29 @@ def test_resident_plan_replayed_as_a_graph_does_the_same_work(engine):
     finally:
         plan.close()
         other.close()
+
+
+def test_wide_clusters_on_the_device_match_the_oracle(engine):
+    """Clusters of 2..5 variants in ONE batch (3..6 columns: the exact three-column solve, the register-resident
+    refinement, the in-memory path with the Jacobi eigen-decomposition -- all warp-collective on the device) next to
+    ordinary targets: rows and raw floats equal the oracle's."""
+    cases = [wide_cluster_case(n) for n in (2, 3, 4, 5)] + [wide_cluster_case(n, seed=300) for n in (2, 3)]
+    keys = np.concatenate([c[1] for c in cases])
+    vals = np.concatenate([c[2] for c in cases])
+    uk, inv = np.unique(keys, return_inverse=True)
+    assert len(uk) == len(keys)                      # the six cases share no k-mer
+    t = engine.Table.create(capacity=len(keys) + 1024)
+    t.insert(keys, vals)
+    store = KmerStore(31, True, len(keys))
+    store.insert(keys, vals)
+    jf = ko.OracleJellyfish(store, "w.jf", 0.05, 5)
+    res = t.find_batch([c[0] for c in cases])
+    for i, (ref, _, _) in enumerate(cases):
+        assert int(res.status[i]) == 0
+        want = ko.OracleFinder(ko.Target(ref, "wide%d" % i, 31), jf).run().get_paths()
+        got = record_of(res, i, "w.jf", "wide%d" % i)
+        errs, _ = compare_rows([str(r) for r in want], got["rows"],
+                               [[float(r.rvaf), float(r.expr), float(r.ref_expr)] for r in want], got["raw"])
+        assert not errs, (i, errs)
+    text, status = t.find_text(engine.PackedTargets([c[0] for c in cases], ["wide%d" % i for i in range(len(cases))]), "w.jf")
+    assert text == "".join(res.format_target(i, "w.jf", "wide%d" % i) for i in range(len(cases)))
