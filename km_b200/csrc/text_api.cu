@@ -345,7 +345,10 @@ extern "C" int km_find_text(km_table* t, const char* seqs, const int64_t* offset
         // together at the end, so the host can format the first while the GPU works on the rest
         int prio_lo = 0, prio_hi = 0;
         CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));          // lo = least urgent (0), hi = most urgent (negative)
-        const int prio = std::min(prio_lo, prio_hi + (int)t->lanes.size());
+        // KM_LANE_PRIORITIES (experiments): 0 = all lanes alike, 2 = only lane 0 urgent; default: one level per lane
+        static const int prio_mode = getenv("KM_LANE_PRIORITIES") ? atoi(getenv("KM_LANE_PRIORITIES")) : 1;
+        const int lane_no = (int)t->lanes.size();
+        const int prio = prio_mode == 0 ? prio_lo : prio_mode == 2 ? (lane_no == 0 ? prio_hi : prio_lo) : std::min(prio_lo, prio_hi + lane_no);
         CU(cudaStreamCreateWithPriority(&L->stream, cudaStreamNonBlocking, prio));
         CU(cudaStreamCreateWithPriority(&L->side, cudaStreamNonBlocking, prio));
         CU(cudaStreamCreateWithPriority(&L->side2, cudaStreamNonBlocking, prio));

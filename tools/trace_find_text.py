@@ -1,5 +1,5 @@
 """Host-clock timeline of km_find_text on the bench configuration (KM_TRACE):
-    python tools/trace_find_text.py [n_sub]"""
+    python tools/trace_find_text.py [n_sub] [panel seed offset]          (KM_TRACE=2: device timeline too)"""
 import os
 import sys
 import time
@@ -9,7 +9,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from km_b200 import engine, synth   # noqa: E402
 
 n_sub = int(sys.argv[1]) if len(sys.argv) > 1 else 0
-panel = synth.make_panel(10000, seed=synth.PANEL_SEED)
+panel = synth.make_panel(10000, seed=synth.PANEL_SEED + (int(sys.argv[2]) if len(sys.argv) > 2 else 0))
 t = engine.Table.create(capacity=2_000_000_000 + len(panel.keys))
 t.build_synthetic(synth.TABLE_SEED, 2_000_000_000)
 t.insert(panel.keys, panel.counts)
