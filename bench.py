@@ -135,6 +135,14 @@ def _cpu_worker(conn, job, keys, counts, bg_seed, bg_n, kind, workdir):
         conn.send(("error", "%s\n%s" % (e, traceback.format_exc())))
 
 
+def workload_config(workload, targets, table_keys, world):
+    """`config` of the JSON line: names the workload; identical on the native and the --impl reference arm."""
+    return {"workload": workload, "targets_per_gpu": targets, "table_keys": table_keys,
+            "parallelism": "targets sharded x%d, table replicated, no data-path collective" % world,
+            "l2": "table (%.0f GB of 32-byte buckets) and per-step visited sets are far larger than the 126 MB L2; "
+                  "no explicit flush" % (table_keys * 32 / 1e9)}
+
+
 def cpu_arm(panel, bg_seed, bg_n, n_sample, steps, warmup, cores=None, kind="reference", budget_s=None, table_keys=None):
     """Times find_mutation on the CPU over `n_sample` targets of the panel, one process per core, each over a
     contiguous 1/P slice.  budget_s: if the warm-up predicts that `steps` passes exceed it,
@@ -523,7 +531,7 @@ def main():
             "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u64 keys / u32 counts / f32 graph weights / f64 solver",
-            "data": "synthetic", "config": {"workload": workload},
+            "data": "synthetic", "config": workload_config(workload, args.targets, args.table_keys, max(1, args.gpus)),
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": r["cores"], "kind": kind, "sample": r["sample"],
                              "issued_lookups_per_s": r["issued_lookups_per_s"]},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
@@ -813,12 +821,11 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64 keys / u32 counts / f32 graph weights / f64 solver",
             "data": "synthetic",
-            "config": {"workload": workload, "targets_per_gpu": args.targets, "table_keys": table_keys,
-                       "table_distinct": info["n_keys"], "table_gb": info["bytes"] / 1e9, "table_build_s": t_build,
+            # `config` names the workload and is the same object on both arms (--impl reference prints it too); what this run
+            # measured about it sits in `config_measured`
+            "config": workload_config(workload, args.targets, table_keys, world),
+            "config_measured": {"table_distinct": info["n_keys"], "table_gb": info["bytes"] / 1e9, "table_build_s": t_build,
                        "table_layout": "family lines (128 B, two copies per k-mer)" if info["layout"] else "sector buckets (32 B)",
-                       "parallelism": "targets sharded x%d, table replicated, no data-path collective" % world,
-                       "l2": "table (%.0f GB) and per-step visited sets are far larger than the 126 MB L2; no explicit flush"
-                             % (info["bytes"] / 1e9),
                        "ref_kmers": int(n_ref.sum()), "rows": n_rows, "capacity_retries": retries,
                        "launch_parts": best_parts,
                        "ms_per_step_by_parts": {str(k): v for k, v in tried.items()}},
