@@ -94,6 +94,7 @@ KM_HD unsigned long long warp_sum64(unsigned long long v) {
 KM_HD bool warp_leader() { return (threadIdx.x & 31) == 0; }
 KM_HD unsigned long long warp_bcast64(unsigned long long v) { return __shfl_sync(0xFFFFFFFFu, v, 0); }      // lane 0's value
 KM_HD uint32_t warp_min32(uint32_t v) { return __reduce_min_sync(0xFFFFFFFFu, v); }
+KM_HD uint32_t warp_add32(uint32_t v) { return __reduce_add_sync(0xFFFFFFFFu, v); }      // the sum, on every lane (one REDUX)
 KM_HD uint32_t warp_or32(uint32_t v) { return __reduce_or_sync(0xFFFFFFFFu, v); }
 // lanes holding the same 64-bit value (all 32 lanes must call)
 KM_HD uint32_t warp_match64(uint64_t v) { return __match_any_sync(0xFFFFFFFFu, (unsigned long long)v); }
@@ -154,6 +155,7 @@ KM_HD unsigned long long warp_sum64(unsigned long long v) { return v; }
 KM_HD bool warp_leader() { return true; }
 KM_HD unsigned long long warp_bcast64(unsigned long long v) { return v; }
 KM_HD uint32_t warp_min32(uint32_t v) { return v; }
+KM_HD uint32_t warp_add32(uint32_t v) { return v; }
 KM_HD uint32_t warp_or32(uint32_t v) { return v; }
 KM_HD uint32_t warp_match64(uint64_t) { return 1u; }
 KM_HD int warp_shfl32(int v, int) { return v; }
