@@ -244,3 +244,28 @@ def test_wide_clusters_match_the_oracle(n_alleles):
     assert not errs, errs
     sizes = [r for r in got["rows"] if "cluster" in r.split("\t")[11]]
     assert any("n=%d" % n_alleles in r.split("\t")[11] for r in sizes), [r.split("\t")[11] for r in got["rows"]]
+
+
+def _wide_golden():
+    import json
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "wide_clusters.json")) as f:
+        return json.load(f)
+
+
+def test_wide_clusters_and_long_refinements_match_the_reference_goldens():
+    """The same cases against records of the UNMODIFIED reference (tests/golden/make_golden_wide.py): clusters of 2..5
+    variants and the tandem duplications whose refinement runs for hundreds of steps -- node sets, alternative paths, rows,
+    raw floats at 1e-6."""
+    from km_b200 import synth
+    g = _wide_golden()
+    for case in g["wide"]:
+        ref, keys, vals = wide_cluster_case(case["n"], seed=case["seed"])
+        res = EmuTable.from_keys(keys, vals).find_batch([ref])
+        assert int(res.status[0]) == 0
+        _check(case["record"], record_of(res, 0, "w.jf", case["name"]), case["name"])
+    lg = g["long"]
+    panel = synth.make_panel(lg["n_targets"], seed=synth.PANEL_SEED + lg["panel_seed_offset"])
+    res = EmuTable.from_keys(panel.keys, panel.counts).find_batch([panel.targets[i] for i in lg["picks"]])
+    for j, (i, rec) in enumerate(zip(lg["picks"], lg["records"])):
+        assert int(res.status[j]) == 0
+        _check(rec, record_of(res, j, "p.jf", panel.names[i]), panel.names[i])

@@ -236,3 +236,37 @@ def test_wide_clusters_on_the_device_match_the_oracle(engine):
         assert not errs, (i, errs)
     text, status = t.find_text(engine.PackedTargets([c[0] for c in cases], ["wide%d" % i for i in range(len(cases))]), "w.jf")
     assert text == "".join(res.format_target(i, "w.jf", "wide%d" % i) for i in range(len(cases)))
+
+
+def test_wide_clusters_and_long_refinements_match_the_reference_goldens_on_the_device(engine):
+    """tests/golden/wide_clusters.json (records of the UNMODIFIED reference, make_golden_wide.py): clusters of 2..5 variants
+    and the long-refinement duplications, all in two batches through the CUDA path -- node sets, alternative paths, rows, raw
+    floats at 1e-6."""
+    import json
+    import os
+    from km_b200 import synth
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "wide_clusters.json")) as f:
+        g = json.load(f)
+
+    def check(rec, got, tag):
+        assert got["nodes"] == rec["nodes"], tag
+        assert got["alt_sequences"] == rec["alt_sequences"], tag
+        errs, _ = compare_rows(rec["rows"], got["rows"], rec["raw"], got["raw"])
+        assert not errs, (tag, errs)
+    cases = [wide_cluster_case(c["n"], seed=c["seed"]) for c in g["wide"]]
+    keys = np.concatenate([c[1] for c in cases])
+    vals = np.concatenate([c[2] for c in cases])
+    t = engine.Table.create(capacity=len(keys) + 1024)
+    t.insert(keys, vals)
+    res = t.find_batch([c[0] for c in cases])
+    for i, c in enumerate(g["wide"]):
+        assert int(res.status[i]) == 0
+        check(c["record"], record_of(res, i, "w.jf", c["name"]), c["name"])
+    lg = g["long"]
+    panel = synth.make_panel(lg["n_targets"], seed=synth.PANEL_SEED + lg["panel_seed_offset"])
+    t2 = engine.Table.create(capacity=len(panel.keys) + 1024)
+    t2.insert(panel.keys, panel.counts)
+    res = t2.find_batch([panel.targets[i] for i in lg["picks"]])
+    for j, (i, rec) in enumerate(zip(lg["picks"], lg["records"])):
+        assert int(res.status[j]) == 0
+        check(rec, record_of(res, j, "p.jf", panel.names[i]), panel.names[i])
