@@ -205,8 +205,16 @@ static void format_range(const km_result* r, int lo, int hi, const char* db_name
 // contiguous range of targets into its own buffer, the pieces are then copied side by side.
 static int build_text(const km_result* r, const char* db_name, const char* names, const int64_t* name_off, int32_t threads) {
     const int n = r->n_targets;
+    {
+        // the text at hand was made for (db_name, names)?  Compared in place: the key of a 10,000-target panel is 140 KB, and
+        // this is on the path of every km_find_text + km_result_text pair
+        const size_t dl = strlen(db_name), nb = n ? (size_t)name_off[n] : 0;
+        const std::string& k = r->fmt_key;
+        if (r->text_len >= 0 && k.size() == dl + 1 + nb && memcmp(k.data(), db_name, dl) == 0 && k[dl] == '\0' &&
+            (nb == 0 || memcmp(k.data() + dl + 1, names, nb) == 0))
+            return 0;
+    }
     std::string key = std::string(db_name) + '\0' + (n ? std::string(names, (size_t)name_off[n]) : std::string());
-    if (r->text_len >= 0 && r->fmt_key == key) return 0;
     int nt = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
     nt = std::max(1, std::min(nt, std::max(1, n / 64)));
     std::vector<std::vector<char>> piece((size_t)nt);
@@ -524,6 +532,8 @@ extern "C" int km_find_text(km_table* t, const char* seqs, const int64_t* offset
             });
         }
         tr.mark("all submitted");
+        // (while the pool works: the key km_result_text recognises this text by)
+        res->fmt_key = std::string(db_name) + '\0' + (n ? std::string(names, (size_t)name_off[n]) : std::string());
         latch.wait();
         tr.mark("all placed");
         if (tr.device) {
@@ -579,7 +589,6 @@ extern "C" int km_find_text(km_table* t, const char* seqs, const int64_t* offset
             res->n_launches += part->n_launches; res->n_retries += part->n_retries;
             res->bytes_h2d += part->bytes_h2d; res->bytes_d2h += part->bytes_d2h;
         }
-        res->fmt_key = std::string(db_name) + '\0' + (n ? std::string(names, (size_t)name_off[n]) : std::string());
         *out = res;
         tr.mark("done");
         return 0;
