@@ -22,6 +22,7 @@ table is replicated, there is no collective on the data path.
 """
 import argparse
 import ctypes
+import gc
 import json
 import os
 import subprocess
@@ -263,6 +264,8 @@ def strong_leg(args, table, dist, dev, rank, world, panel, text_rank0, barrier, 
     plan = cohort.ShardPlan(packed0, world, rank, 31)
     for _ in range(max(3, args.warmup)):
         text, status = cohort.find_mutation_sharded(table, plan, "panel.jf", dist)
+    gc.collect()
+    gc.disable()                # (as for the e2e loop of main(): no generation-2 collection inside a region of a few ms)
     barrier()
     torch.cuda.synchronize(dev)
     t0 = time.perf_counter()
@@ -271,6 +274,7 @@ def strong_leg(args, table, dist, dev, rank, world, panel, text_rank0, barrier, 
     torch.cuda.synchronize(dev)
     barrier()
     e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - t0)) / args.steps
+    gc.enable()
     same = bool(np.array_equal(text, text_rank0)) if rank == 0 else None
     # device-only: every rank's share resident in HBM, K launches, CUDA events, max over ranks
     share = table.plan(plan.mine.sequences)
@@ -706,6 +710,11 @@ def main():
 
     for _ in range(args.warmup):
         text, status = e2e_step()
+    # wall-clock region of a few milliseconds in a process that holds the panel, the parity rows and the CPU arm's results as
+    # Python objects: a generation-2 pass of the cyclic collector (10-30 ms, tools/e2e_jitter.py saw one in 900 calls)
+    # would be most of it -- collect now, and not inside
+    gc.collect()
+    gc.disable()
     barrier()
     torch.cuda.synchronize(dev)
     t0 = time.perf_counter()
@@ -714,6 +723,7 @@ def main():
     torch.cuda.synchronize(dev)
     barrier()
     e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - t0)) / args.steps
+    gc.enable()
     e2e_value = world * args.targets / (e2e_ms / 1e3)
     h2d, d2h = table.last_timing["h2d_bytes"], table.last_timing["d2h_bytes"]
     # the same work as two calls (km_find_batch, then km_result_text), for the split between them
