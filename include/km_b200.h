@@ -3,7 +3,7 @@
  * Drop-in boundary: the reference (pure Python, km 2.2.2) reaches its only native code,
  * the Jellyfish library, through four calls in km/utils/Jellyfish.py.  A km maintainer
  * would bind the functions below with ctypes (INTEGRATION.md shows the stub); this repo's
- * own km-compatible host layer (km_b200/utils/*.py) is that binding.
+ * own km-compatible host layer (the modules of km_b200/utils) is that binding.
  *
  * Conventions: plain C types only.  Every function returning int returns 0 on success and
  * a negative KM_E_* code on failure; km_last_error() then holds a message (thread local).
