@@ -270,3 +270,24 @@ def test_wide_clusters_and_long_refinements_match_the_reference_goldens_on_the_d
     for j, (i, rec) in enumerate(zip(lg["picks"], lg["records"])):
         assert int(res.status[j]) == 0
         check(rec, record_of(res, j, "p.jf", panel.names[i]), panel.names[i])
+
+
+def test_more_targets_than_the_scheduler_caches(engine):
+    """km_schedule_kernel keeps the work-list codes of the first 12,288 targets in shared memory and those beyond in the
+    walk's code array: a batch of 13,000 targets (a 1,000-target panel thirteen times over) must give every copy the rows
+    of the original, through km_find_batch and through km_find_text."""
+    from km_b200 import synth
+    panel = synth.make_panel(1000, seed=synth.PANEL_SEED + 21, two_variant_frac=0.2)
+    t = engine.Table.create(capacity=len(panel.keys) + 50_000)
+    t.build_synthetic(synth.TABLE_SEED, 40_000)
+    t.insert(panel.keys, panel.counts, mode="overwrite")
+    one = t.find_batch(panel.targets, want_graph=False)
+    reps = 13
+    many = t.find_batch(panel.targets * reps, want_graph=False)
+    assert (many.status == np.tile(one.status, reps)).all()
+    assert (many.row_count == np.tile(one.row_count, reps)).all()
+    assert (many.path_count == np.tile(one.path_count, reps)).all()
+    names = [n for r in range(reps) for n in panel.names]
+    text, status = t.find_text(engine.PackedTargets(panel.targets * reps, names), "p.jf")
+    text1, _ = t.find_text(engine.PackedTargets(panel.targets, panel.names), "p.jf")
+    assert text == text1 * reps
